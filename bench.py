@@ -1,0 +1,255 @@
+#!/usr/bin/env python
+"""Headline benchmark: FBANet BaseModel burst-SR forward, bursts/s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU forward (oracle port)
+
+One "step" = one forward over one batch of synthetic bursts (cfg2: batch 64 x 14x160x160 RGB per GPU,
+embed_dim 64, win 10, random-init weights).  N>1: one process per GPU under torchrun, bursts sharded
+across ranks, NO data-path collective (weak scaling); timing = max over ranks of CUDA-event time.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(num_frames=14, img_size=160, in_channels=3, embed_dim=64, window_length=10)
+MP_PER_BURST = (4 * CFG["img_size"]) ** 2 / 1e6  # 0.4096 output megapixels per burst
+WORKLOAD = "cfg2: BaseModel embed_dim=64 win=10 inference, synthetic 14x160x160 RGB bursts -> 640x640 (x4)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.samples.append([s.strip() for s in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_forward_rate(threads: int, reps: int, seed: int = 0):
+    """Reference CPU forward (oracle port) on the host cores: bursts/s over `reps` single-burst forwards."""
+    from oracle.fbanet_oracle import build_oracle  # the one place bench.py may execute oracle/
+    torch.set_num_threads(threads)
+    o = build_oracle(seed, **CFG)
+    x = torch.rand(1, CFG["num_frames"], CFG["in_channels"], CFG["img_size"], CFG["img_size"], generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        o(x)  # warm-up
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            o(x)
+            ts.append(time.perf_counter() - t0)
+    ts.sort()
+    return 1.0 / ts[len(ts) // 2], ts
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    from oracle.fbanet_oracle import build_oracle
+    o = build_oracle(0, **CFG)
+    x = torch.rand(1, CFG["num_frames"], CFG["in_channels"], CFG["img_size"], CFG["img_size"], generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            o(x)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            o(x)
+        dt = time.perf_counter() - t0
+    v = args.steps / dt
+    sample = f"{args.steps} steps x 1 burst (14x160x160 RGB) of the batch-64 workload, torch CPU fp32, {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "bursts_per_sec", "value": v, "unit": "bursts/s", "output_mp_per_s": v * MP_PER_BURST,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_step": 1, "note": "reference JAX forward is not executable (SURVEY F2/F3); CPU oracle port timed"},
+        "cpu_baseline": {"value": v, "unit": "bursts/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "bursts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="bursts per GPU per step")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-impl", default="auto", choices=["auto", "simt"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from fbanet_b200 import BaseModel, ops, _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    B = args.batch
+
+    model = BaseModel(**CFG, token_projection="linear", token_mlp="leff", dtype=args.dtype, seed=0,
+                      impl=L.IMPL_SIMT if args.kernel_impl == "simt" else L.IMPL_AUTO).to(dev).eval()
+    # burst sharding: rank r owns global bursts [r*B, (r+1)*B)  (pipeline/real_bsr_dataset.py:82-83 rule)
+    g = torch.Generator().manual_seed(1000 + rank)
+    host_in = torch.rand(B, CFG["num_frames"], CFG["in_channels"], CFG["img_size"], CFG["img_size"], generator=g).pin_memory()
+    host_out = torch.empty(B, CFG["in_channels"], 4 * CFG["img_size"], 4 * CFG["img_size"]).pin_memory()
+    x = host_in.to(dev)
+    stream = torch.cuda.Stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.cuda.stream(stream):
+        # ---- warm-up (also packs weights), kernel-level roofline instrumentation on the last warm-up ----
+        for _ in range(W):
+            y = model(x)
+        stream.synchronize()
+        ops.LAUNCHES = 0
+        model(x)
+        launches_per_step = ops.LAUNCHES
+        stream.synchronize()
+
+        # ---- device-resident timed region ----
+        graph = None
+        if not args.no_graph:
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream):
+                    y = model(x)
+                graph.replay()
+                stream.synchronize()
+            except Exception as e:  # capture is an optimisation, never a correctness dependency
+                print(f"[bench] CUDA graph capture failed ({e}); running eagerly", file=sys.stderr)
+                graph = None
+        sampler = ClockSampler(local) if rank == 0 else None
+        barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            if graph is not None:
+                graph.replay()
+            else:
+                y = model(x)
+        e1.record(stream)
+        stream.synchronize()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = e0.elapsed_time(e1)
+
+        # ---- dominant-kernel roofline: CUDA events around every conv/GEMM launch of one more eager pass ----
+        prof = ops.profile_conv_gemm(lambda: model(x), stream)
+
+        # ---- end to end through the public API with HOST buffers (pinned H2D + D2H inside the timed region) ----
+        for _ in range(2):
+            model.infer_host(host_in, host_out)
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record(stream)
+        for _ in range(args.steps):
+            model.infer_host(host_in, host_out)
+        h1.record(stream)
+        stream.synchronize()
+        barrier()
+        ms_e2e = h0.elapsed_time(h1)
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_src = peaks()
+    total_bursts = B * world * args.steps
+    value = total_bursts / (ms / 1e3)
+    e2e = total_bursts / (ms_e2e / 1e3)
+    peak_tf = pk["bf16_tflops_sustained"]
+    roof = {
+        "bound": "tensor", "kernel": prof["kernel"], "achieved": prof["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": prof["tflops"] / peak_tf, "traffic": None, "peak_source": pk_src + ", sustained bf16 (kernel timed inside a long step)",
+        "launches": prof["launches"], "share_of_step": prof["ms"] / (ms / args.steps), "flops_per_step": prof["flops"],
+    }
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, ts = cpu_forward_rate(threads, reps=5)
+        cpu = {"value": v, "unit": "bursts/s", "cores": threads, "kind": "port",
+               "sample": f"5 single-burst forwards (1/{B} of one step) of the CPU oracle, torch fp32, {threads} threads, median"}
+    line = {
+        "metric": "bursts_per_sec", "value": value, "unit": "bursts/s", "output_mp_per_s": value * MP_PER_BURST,
+        "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype if args.dtype != "fp32" else "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"burst-sharded x{world}, no collective",
+                   "l2": f"inputs {host_in.numel() * 4 / 1e6:.0f} MB/step + GB-scale activations > 126 MB L2", "cuda_graph": graph is not None,
+                   "weights": "random init (reference distributions), seed 0"},
+        "e2e": {"value": e2e, "unit": "bursts/s", "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

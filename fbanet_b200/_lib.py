@@ -1,0 +1,153 @@
+"""ctypes binding of ``include/fbanet_b200.h`` (the C-ABI shared library of sm_100a kernels).
+
+There is no CPU fallback: if the library is missing, loading raises and every op fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libfbanet_b200.so")
+ABI_VERSION = 3
+MAX_SRC = 16
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_PRELU, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2, 3, 4
+STORE_NHWC, STORE_PS2, STORE_CONVT2, STORE_NCHW_BASE = 0, 1, 2, 3
+IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+
+ERRORS = {-1: "bad shape", -2: "misaligned pointer/stride", -3: "unsupported dtype", -4: "CUDA launch failure", -5: "impl unsupported for this problem"}
+
+
+class Src(C.Structure):
+    _fields_ = [
+        ("ptr", C.c_void_p), ("row_scale", C.c_void_p), ("img_stride", C.c_int64), ("scale_img_stride", C.c_int64),
+        ("C", C.c_int32), ("ld", C.c_int32),
+    ]
+
+
+class ConvParams(C.Structure):
+    _fields_ = [
+        ("src", Src * MAX_SRC),
+        ("weight", C.c_void_p), ("bias", C.c_void_p), ("alpha", C.c_void_p), ("residual", C.c_void_p),
+        ("out", C.c_void_p), ("base", C.c_void_p),
+        ("res_img_stride", C.c_int64), ("out_img_stride", C.c_int64), ("base_img_stride", C.c_int64),
+        ("dtype", C.c_int32), ("impl", C.c_int32), ("nsrc", C.c_int32),
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+        ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32), ("Cout_store", C.c_int32),
+        ("act", C.c_int32), ("store_mode", C.c_int32), ("res_ld", C.c_int32), ("out_ld", C.c_int32),
+    ]
+
+
+class WarpParams(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("dst", C.c_void_p), ("M", C.c_void_p), ("coords", C.c_void_p),
+        ("s_frame", C.c_int64), ("s_y", C.c_int64), ("s_x", C.c_int64), ("s_c", C.c_int64),
+        ("d_frame", C.c_int64), ("d_y", C.c_int64), ("d_x", C.c_int64), ("d_c", C.c_int64),
+        ("frames", C.c_int32), ("frames_per_burst", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
+class ToNhwcParams(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("dst", C.c_void_p), ("dtype", C.c_int32),
+        ("frames", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cp", C.c_int32),
+    ]
+
+
+class LayerNormParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("y", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("rows", C.c_int64),
+        ("C", C.c_int32), ("x_ld", C.c_int32), ("y_ld", C.c_int32), ("dtype", C.c_int32), ("eps", C.c_float), ("_pad", C.c_int32),
+    ]
+
+
+class AttnParams(C.Structure):
+    _fields_ = [
+        ("qkv", C.c_void_p), ("out", C.c_void_p), ("bias_table", C.c_void_p), ("dtype", C.c_int32),
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("heads", C.c_int32), ("win", C.c_int32), ("shift", C.c_int32),
+        ("qkv_ld", C.c_int32), ("out_ld", C.c_int32), ("scale", C.c_float), ("impl", C.c_int32),
+    ]
+
+
+class DwconvParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("y", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p), ("dtype", C.c_int32),
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("act", C.c_int32),
+    ]
+
+
+class FafGateParams(C.Structure):
+    _fields_ = [
+        ("feat", C.c_void_p), ("gate", C.c_void_p), ("wsum", C.c_void_p), ("dtype", C.c_int32),
+        ("B", C.c_int32), ("F", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+    ]
+
+
+class TileParams(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("dst", C.c_void_p),
+        ("T", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("psize", C.c_int32), ("overlap", C.c_int32), ("tile_begin", C.c_int32), ("tile_end", C.c_int32),
+        ("scale", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
+STRUCTS = {
+    "fbanet_src": Src, "fbanet_conv_params": ConvParams, "fbanet_warp_params": WarpParams,
+    "fbanet_to_nhwc_params": ToNhwcParams, "fbanet_layernorm_params": LayerNormParams, "fbanet_attn_params": AttnParams,
+    "fbanet_dwconv_params": DwconvParams, "fbanet_faf_gate_params": FafGateParams, "fbanet_tile_params": TileParams,
+}
+
+# every symbol include/fbanet_b200.h declares
+OPS = {
+    "fbanet_warp_sm100": WarpParams, "fbanet_to_nhwc_sm100": ToNhwcParams, "fbanet_conv_gemm_sm100": ConvParams,
+    "fbanet_layernorm_sm100": LayerNormParams, "fbanet_window_attention_sm100": AttnParams, "fbanet_dwconv3x3_sm100": DwconvParams,
+    "fbanet_faf_gate_sm100": FafGateParams, "fbanet_tile_divide_sm100": TileParams, "fbanet_tile_merge_sm100": TileParams,
+}
+MISC_SYMBOLS = ["fbanet_abi_version", "fbanet_abi_sizeof", "fbanet_last_cuda_error", "fbanet_conv_gemm_tcgen05_supported"]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises RuntimeError when it is absent or its ABI does not match."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"fbanet_b200: CUDA library {LIB_PATH} is missing -- run `python -m fbanet_b200.build` "
+            "(or __graft_entry__.build()).  There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    lib.fbanet_abi_version.restype = C.c_int
+    lib.fbanet_abi_sizeof.restype = C.c_int
+    lib.fbanet_abi_sizeof.argtypes = [C.c_char_p]
+    lib.fbanet_last_cuda_error.restype = C.c_char_p
+    lib.fbanet_conv_gemm_tcgen05_supported.restype = C.c_int
+    lib.fbanet_conv_gemm_tcgen05_supported.argtypes = [C.POINTER(ConvParams)]
+    if lib.fbanet_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"fbanet_b200: ABI mismatch (library {lib.fbanet_abi_version()}, binding {ABI_VERSION}); rebuild")
+    for name, st in STRUCTS.items():
+        n = lib.fbanet_abi_sizeof(name.encode())
+        if n != C.sizeof(st):
+            raise RuntimeError(f"fbanet_b200: struct {name} is {n} bytes in the library but {C.sizeof(st)} in the binding")
+    for name, st in OPS.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(st), C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def call(name: str, params, stream: int) -> None:
+    lib = load()
+    rc = getattr(lib, name)(C.byref(params), C.c_void_p(stream))
+    if rc != 0:
+        msg = ERRORS.get(rc, f"error {rc}")
+        if rc == -4:
+            msg += ": " + lib.fbanet_last_cuda_error().decode()
+        raise RuntimeError(f"{name} failed: {msg}")

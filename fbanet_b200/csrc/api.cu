@@ -1,0 +1,77 @@
+// C-ABI glue: error reporting, ABI self-description, dispatch between implementations.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace fbanet {
+
+static thread_local char g_err[256] = "";
+
+void set_last_error(cudaError_t e) {
+  const char* s = cudaGetErrorString(e);
+  strncpy(g_err, s ? s : "unknown", sizeof(g_err) - 1);
+  g_err[sizeof(g_err) - 1] = 0;
+}
+
+int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return FBANET_OK;
+  set_last_error(e);
+  return FBANET_E_LAUNCH;
+}
+
+int conv_gemm_validate(const fbanet_conv_params* p);
+int conv_gemm_simt_launch(const fbanet_conv_params* p, cudaStream_t stream);
+int conv_gemm_tc_supported(const fbanet_conv_params* p);
+int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream);
+int window_attention_validate(const fbanet_attn_params* p);
+int window_attention_simt_launch(const fbanet_attn_params* p, cudaStream_t s);
+int window_attention_tc_supported(const fbanet_attn_params* p);
+int window_attention_tc_launch(const fbanet_attn_params* p, cudaStream_t s);
+
+}  // namespace fbanet
+
+using namespace fbanet;
+
+extern "C" int fbanet_abi_version(void) { return FBANET_ABI_VERSION; }
+
+extern "C" int fbanet_abi_sizeof(const char* n) {
+  if (!n) return -1;
+#define SZ(T) if (!strcmp(n, #T)) return (int)sizeof(T)
+  SZ(fbanet_src);
+  SZ(fbanet_conv_params);
+  SZ(fbanet_warp_params);
+  SZ(fbanet_to_nhwc_params);
+  SZ(fbanet_layernorm_params);
+  SZ(fbanet_attn_params);
+  SZ(fbanet_dwconv_params);
+  SZ(fbanet_faf_gate_params);
+  SZ(fbanet_tile_params);
+#undef SZ
+  return -1;
+}
+
+extern "C" const char* fbanet_last_cuda_error(void) { return g_err; }
+
+extern "C" int fbanet_conv_gemm_tcgen05_supported(const fbanet_conv_params* p) {
+  if (conv_gemm_validate(p) != FBANET_OK) return 0;
+  return conv_gemm_tc_supported(p);
+}
+
+extern "C" int fbanet_conv_gemm_sm100(const fbanet_conv_params* p, void* stream) {
+  int rc = conv_gemm_validate(p);
+  if (rc != FBANET_OK) return rc;
+  const bool tc_ok = conv_gemm_tc_supported(p) != 0;
+  if (p->impl == FBANET_IMPL_TCGEN05 && !tc_ok) return FBANET_E_UNSUPPORTED;
+  if (tc_ok && p->impl != FBANET_IMPL_SIMT) return conv_gemm_tc_launch(p, (cudaStream_t)stream);
+  return conv_gemm_simt_launch(p, (cudaStream_t)stream);
+}
+
+extern "C" int fbanet_window_attention_sm100(const fbanet_attn_params* p, void* stream) {
+  int rc = window_attention_validate(p);
+  if (rc != FBANET_OK) return rc;
+  const bool tc_ok = window_attention_tc_supported(p) != 0;
+  if (p->impl == FBANET_IMPL_TCGEN05 && !tc_ok) return FBANET_E_UNSUPPORTED;
+  if (tc_ok && p->impl != FBANET_IMPL_SIMT) return window_attention_tc_launch(p, (cudaStream_t)stream);
+  return window_attention_simt_launch(p, (cudaStream_t)stream);
+}

@@ -1,0 +1,332 @@
+// HBM-bound kernels of the BaseModel forward: homography warp (K1), layout conversion, LayerNorm (K8),
+// LeFF depthwise 3x3 + GELU (K7), FAF gate (K2a), full-size tile divide/merge (8f-1).
+#include "common.cuh"
+
+namespace fbanet {
+
+// ------------------------------------------------------------------------------------------------
+// K1  homography warp, bilinear, BORDER_CONSTANT 0, dst->src matrix (cv2 WARP_INVERSE_MAP).
+// One thread per destination pixel; coordinates in fp64 (fp32 cannot hold 1e-5 px at x~1920).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) warp_kernel(const fbanet_warp_params p) {
+  const int64_t total = (int64_t)p.frames * p.H * p.W;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % p.W);
+    const int y = (int)((idx / p.W) % p.H);
+    const int f = (int)(idx / ((int64_t)p.W * p.H));
+    const float* s = p.src + (int64_t)f * p.s_frame;
+    float* d = p.dst + (int64_t)f * p.d_frame + (int64_t)y * p.d_y + (int64_t)x * p.d_x;
+    if (f % p.frames_per_burst == 0) {  // base frame: identity (homography_alignment.py:168,179)
+      const float* s0 = s + (int64_t)y * p.s_y + (int64_t)x * p.s_x;
+      for (int c = 0; c < p.C; ++c) d[(int64_t)c * p.d_c] = s0[(int64_t)c * p.s_c];
+      if (p.coords) { double* co = p.coords + idx * 2; co[0] = x; co[1] = y; }
+      continue;
+    }
+    const double* M = p.M + (int64_t)f * 9;
+    const double X = x, Y = y;
+    const double u = fma(M[0], X, fma(M[1], Y, M[2]));
+    const double v = fma(M[3], X, fma(M[4], Y, M[5]));
+    const double w = fma(M[6], X, fma(M[7], Y, M[8]));
+    const double sx = u / w, sy = v / w;
+    if (p.coords) { double* co = p.coords + idx * 2; co[0] = sx; co[1] = sy; }
+    const double fx = floor(sx), fy = floor(sy);
+    const float ax = (float)(sx - fx), ay = (float)(sy - fy);
+    // clamp before the int conversion so wild homographies cannot overflow
+    const int x0 = (int)fmin(fmax(fx, -2.0), (double)p.W + 1.0);
+    const int y0 = (int)fmin(fmax(fy, -2.0), (double)p.H + 1.0);
+    const bool okx0 = x0 >= 0 && x0 < p.W, okx1 = x0 + 1 >= 0 && x0 + 1 < p.W;
+    const bool oky0 = y0 >= 0 && y0 < p.H, oky1 = y0 + 1 >= 0 && y0 + 1 < p.H;
+    const float w00 = (1.f - ay) * (1.f - ax), w01 = (1.f - ay) * ax, w10 = ay * (1.f - ax), w11 = ay * ax;
+    const float* r0 = s + (int64_t)y0 * p.s_y + (int64_t)x0 * p.s_x;
+    const float* r1 = r0 + p.s_y;
+    for (int c = 0; c < p.C; ++c) {
+      const int64_t oc = (int64_t)c * p.s_c;
+      float acc = 0.f;
+      if (oky0 && okx0) acc += w00 * __ldg(r0 + oc);
+      if (oky0 && okx1) acc += w01 * __ldg(r0 + p.s_x + oc);
+      if (oky1 && okx0) acc += w10 * __ldg(r1 + oc);
+      if (oky1 && okx1) acc += w11 * __ldg(r1 + p.s_x + oc);
+      d[(int64_t)c * p.d_c] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// planar fp32 [frames][C][H][W] -> channels-last [frames][H][W][Cp]
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) to_nhwc_kernel(const fbanet_to_nhwc_params p) {
+  const int64_t total = (int64_t)p.frames * p.H * p.W;
+  T* dst = reinterpret_cast<T*>(p.dst);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t hw = (int64_t)p.H * p.W;
+    const int64_t f = idx / hw, pix = idx % hw;
+    const float* s = p.src + f * p.C * hw + pix;
+    T* d = dst + idx * p.Cp;
+    for (int c = 0; c < p.Cp; ++c) d[c] = from_f32<T>(c < p.C ? __ldg(s + (int64_t)c * hw) : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8  LayerNorm: one warp per token, two-pass fp32 statistics, biased variance (torch / equinox).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int C>
+__global__ void __launch_bounds__(256) layernorm_kernel(const fbanet_layernorm_params p) {
+  constexpr int PER = C / 32;  // contiguous channels per lane
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const T* x = reinterpret_cast<const T*>(p.x) + row * p.x_ld + lane * PER;
+  float v[PER];
+  if constexpr (PER % Vec16<T>::N == 0) {
+#pragma unroll
+    for (int i = 0; i < PER; i += Vec16<T>::N) {
+      float t[Vec16<T>::N];
+      load_vec<T, Vec16<T>::N>(x + i, t);
+#pragma unroll
+      for (int j = 0; j < Vec16<T>::N; ++j) v[i + j] = t[j];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) v[i] = to_f32<T>(x[i]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { const float d = v[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + p.eps);
+  T* y = reinterpret_cast<T*>(p.y) + row * p.y_ld + lane * PER;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = lane * PER + i;
+    y[i] = from_f32<T>((v[i] - mean) * rstd * __ldg(p.gamma + c) + __ldg(p.beta + c));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7  depthwise 3x3 pad 1 + bias + activation, channels-last.  One thread = one pixel x VEC channels.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const fbanet_dwconv_params p) {
+  constexpr int V = Vec16<T>::N;
+  const int cg = p.C / V;
+  const int64_t total = (int64_t)p.N * p.H * p.W * cg;
+  const T* X = reinterpret_cast<const T*>(p.x);
+  T* Yo = reinterpret_cast<T*>(p.y);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(idx % cg) * V;
+    const int64_t pix = idx / cg;
+    const int x = (int)(pix % p.W);
+    const int y = (int)((pix / p.W) % p.H);
+    const int64_t n = pix / ((int64_t)p.W * p.H);
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = __ldg(p.bias + c0 + j);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= p.H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if (xx < 0 || xx >= p.W) continue;
+        float v[V];
+        load_vec<T, V>(X + ((n * p.H + yy) * p.W + xx) * p.C + c0, v);
+        const float* wt = p.weight + (ky * 3 + kx) * p.C + c0;
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = fmaf(v[j], __ldg(wt + j), acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = apply_act(acc[j], p.act, 0.f);
+    store_vec<T, V>(Yo + pix * p.C + c0, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2a  FAF gate.  One warp per (burst, pixel): the 3x3xC neighbourhood of the base frame is loaded
+// once into registers and re-used for the F-1 other frames; lanes split the channels.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int C>
+__global__ void __launch_bounds__(256) faf_gate_kernel(const fbanet_faf_gate_params p) {
+  constexpr int PER = C / 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t hw = (int64_t)p.H * p.W;
+  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= (int64_t)p.B * hw) return;
+  const int64_t b = gw / hw, pix = gw % hw;
+  const int y = (int)(pix / p.W), x = (int)(pix % p.W);
+  const T* feat = reinterpret_cast<const T*>(p.feat);
+  float ref[9][PER], wt[9][PER];
+  bool ok[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+    ok[t] = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      wt[t][i] = __ldg(p.wsum + t * C + lane * PER + i);
+      ref[t][i] = ok[t] ? to_f32<T>(feat[((b * p.F) * hw + (int64_t)yy * p.W + xx) * C + lane * PER + i]) : 0.f;
+    }
+  }
+  for (int f = 1; f < p.F; ++f) {
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      if (!ok[t]) continue;
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      const T* q = feat + ((b * p.F + f) * hw + (int64_t)yy * p.W + xx) * C + lane * PER;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) acc = fmaf(wt[t][i], to_f32<T>(q[i]) - ref[t][i], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) p.gate[(b * (p.F - 1) + (f - 1)) * hw + pix] = 1.0f / (1.0f + expf(-fabsf(acc)));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// full-size tiling: reflect index helper (torch 'reflect': no edge repeat)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// divide: dst[tile][t][c][ty][tx] = padded(src)[t][c][i*ps + ty - ov][j*ps + tx - ov], where `padded`
+// is reflect-pad bottom/right to a multiple of psize, then reflect-pad `ov` all round (two nested reflects).
+__global__ void __launch_bounds__(256) tile_divide_kernel(const fbanet_tile_params p) {
+  const int ts = p.psize + 2 * p.overlap;
+  const int Hp = (p.H + p.psize - 1) / p.psize * p.psize, Wp = (p.W + p.psize - 1) / p.psize * p.psize;
+  const int nwt = Wp / p.psize;
+  const int64_t per_tile = (int64_t)p.T * p.C * ts * ts;
+  const int64_t total = (int64_t)(p.tile_end - p.tile_begin) * per_tile;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int tx = (int)(idx % ts);
+    const int ty = (int)((idx / ts) % ts);
+    const int64_t tc = (idx / ((int64_t)ts * ts)) % ((int64_t)p.T * p.C);
+    const int tile = p.tile_begin + (int)(idx / per_tile);
+    const int i = tile / nwt, j = tile % nwt;
+    int yy = reflect_idx(i * p.psize + ty - p.overlap, Hp);  // outer pad (on the Hp x Wp image)
+    int xx = reflect_idx(j * p.psize + tx - p.overlap, Wp);
+    yy = reflect_idx(yy, p.H);                                // inner pad (bottom/right only => i >= H)
+    xx = reflect_idx(xx, p.W);
+    p.dst[idx] = __ldg(p.src + (tc * p.H + yy) * p.W + xx);
+  }
+}
+
+// merge: dst[c][Y][X] = tiles[tile(Y,X)][c][ov4 + Y%ps4][ov4 + X%ps4]   (psize/overlap given low-res; x scale)
+__global__ void __launch_bounds__(256) tile_merge_kernel(const fbanet_tile_params p) {
+  const int sc = p.scale, ps = p.psize * sc, ov = p.overlap * sc, ts = ps + 2 * ov;
+  const int Wp = (p.W + p.psize - 1) / p.psize * p.psize;
+  const int nwt = Wp / p.psize;
+  const int HH = p.H * sc, WW = p.W * sc;
+  const int64_t total = (int64_t)p.C * HH * WW;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int X = (int)(idx % WW);
+    const int Y = (int)((idx / WW) % HH);
+    const int c = (int)(idx / ((int64_t)WW * HH));
+    const int tile = (Y / ps) * nwt + X / ps;
+    if (tile < p.tile_begin || tile >= p.tile_end) continue;
+    p.dst[idx] = __ldg(p.src + (((int64_t)(tile - p.tile_begin) * p.C + c) * ts + ov + Y % ps) * ts + ov + X % ps);
+  }
+}
+
+static int grid_for(int64_t total, int block) {
+  int64_t g = (total + block - 1) / block;
+  const int64_t cap = 148 * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace fbanet
+
+using namespace fbanet;
+
+extern "C" int fbanet_warp_sm100(const fbanet_warp_params* p, void* stream) {
+  if (!p || !p->src || !p->dst || !p->M || p->frames <= 0 || p->frames_per_burst <= 0 || p->H <= 0 || p->W <= 0 || p->C <= 0)
+    return FBANET_E_BADSHAPE;
+  const int64_t total = (int64_t)p->frames * p->H * p->W;
+  warp_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch();
+}
+
+extern "C" int fbanet_to_nhwc_sm100(const fbanet_to_nhwc_params* p, void* stream) {
+  if (!p || !p->src || !p->dst || p->Cp < p->C || p->frames <= 0) return FBANET_E_BADSHAPE;
+  const int64_t total = (int64_t)p->frames * p->H * p->W;
+  if (p->dtype == FBANET_F32) to_nhwc_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  else if (p->dtype == FBANET_BF16) to_nhwc_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  else return FBANET_E_DTYPE;
+  return check_launch();
+}
+
+template <typename T>
+static int launch_ln(const fbanet_layernorm_params* p, cudaStream_t s) {
+  const int blocks = ceil_div(p->rows, 8);
+  switch (p->C) {
+    case 32: layernorm_kernel<T, 32><<<blocks, 256, 0, s>>>(*p); break;
+    case 64: layernorm_kernel<T, 64><<<blocks, 256, 0, s>>>(*p); break;
+    case 128: layernorm_kernel<T, 128><<<blocks, 256, 0, s>>>(*p); break;
+    case 256: layernorm_kernel<T, 256><<<blocks, 256, 0, s>>>(*p); break;
+    case 512: layernorm_kernel<T, 512><<<blocks, 256, 0, s>>>(*p); break;
+    default: return FBANET_E_BADSHAPE;
+  }
+  return check_launch();
+}
+
+extern "C" int fbanet_layernorm_sm100(const fbanet_layernorm_params* p, void* stream) {
+  if (!p || !p->x || !p->y || !p->gamma || !p->beta || p->rows <= 0) return FBANET_E_BADSHAPE;
+  const int v = p->dtype == FBANET_F32 ? 4 : 8;
+  if (p->x_ld % v || ((uintptr_t)p->x % 16)) return FBANET_E_ALIGN;
+  if (p->dtype == FBANET_F32) return launch_ln<float>(p, (cudaStream_t)stream);
+  if (p->dtype == FBANET_BF16) return launch_ln<bf16>(p, (cudaStream_t)stream);
+  return FBANET_E_DTYPE;
+}
+
+extern "C" int fbanet_dwconv3x3_sm100(const fbanet_dwconv_params* p, void* stream) {
+  if (!p || !p->x || !p->y || !p->weight || !p->bias || p->N <= 0) return FBANET_E_BADSHAPE;
+  const int v = p->dtype == FBANET_F32 ? 4 : 8;
+  if (p->C % v) return FBANET_E_BADSHAPE;
+  if (((uintptr_t)p->x % 16) || ((uintptr_t)p->y % 16)) return FBANET_E_ALIGN;
+  const int64_t total = (int64_t)p->N * p->H * p->W * (p->C / v);
+  if (p->dtype == FBANET_F32) dwconv3x3_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  else if (p->dtype == FBANET_BF16) dwconv3x3_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  else return FBANET_E_DTYPE;
+  return check_launch();
+}
+
+template <typename T>
+static int launch_gate(const fbanet_faf_gate_params* p, cudaStream_t s) {
+  const int blocks = ceil_div((int64_t)p->B * p->H * p->W, 8);
+  switch (p->C) {
+    case 32: faf_gate_kernel<T, 32><<<blocks, 256, 0, s>>>(*p); break;
+    case 64: faf_gate_kernel<T, 64><<<blocks, 256, 0, s>>>(*p); break;
+    case 128: faf_gate_kernel<T, 128><<<blocks, 256, 0, s>>>(*p); break;
+    default: return FBANET_E_BADSHAPE;
+  }
+  return check_launch();
+}
+
+extern "C" int fbanet_faf_gate_sm100(const fbanet_faf_gate_params* p, void* stream) {
+  if (!p || !p->feat || !p->gate || !p->wsum || p->B <= 0 || p->F < 2) return FBANET_E_BADSHAPE;
+  if (p->dtype == FBANET_F32) return launch_gate<float>(p, (cudaStream_t)stream);
+  if (p->dtype == FBANET_BF16) return launch_gate<bf16>(p, (cudaStream_t)stream);
+  return FBANET_E_DTYPE;
+}
+
+extern "C" int fbanet_tile_divide_sm100(const fbanet_tile_params* p, void* stream) {
+  if (!p || !p->src || !p->dst || p->tile_end <= p->tile_begin || p->overlap >= p->H || p->overlap >= p->W) return FBANET_E_BADSHAPE;
+  const int ts = p->psize + 2 * p->overlap;
+  const int64_t total = (int64_t)(p->tile_end - p->tile_begin) * p->T * p->C * ts * ts;
+  tile_divide_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch();
+}
+
+extern "C" int fbanet_tile_merge_sm100(const fbanet_tile_params* p, void* stream) {
+  if (!p || !p->src || !p->dst || p->tile_end <= p->tile_begin || p->scale < 1) return FBANET_E_BADSHAPE;
+  const int64_t total = (int64_t)p->C * p->H * p->scale * p->W * p->scale;
+  tile_merge_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch();
+}

@@ -1,0 +1,489 @@
+"""B200-native FBANet ``BaseModel``: the reference's model API over hand-written sm_100a kernels.
+
+Mirrors ``/root/reference/fba_net/models/fba_net.py`` (``FBANetModel``): same constructor fields, the
+torch callers' ``model(burst[B,T,C,H,W]) -> [B,C,4H,4W]`` forward (``test_in_any_resolution.py:85``,
+``train.py.bak:166``) and the Uformer-lineage ``state_dict`` key layout so
+``model_best.pth``-style checkpoints load unchanged.  The ``nn`` modules below are *parameter containers
+only*: the forward never calls torch operators for compute -- every step is a kernel from
+``include/fbanet_b200.h`` (see ``ops.py``); there is no CPU / eager fallback.
+
+Data layout in HBM: activations are channels-last ``[N,H,W,C]`` (tokens ``[T,C]`` are the same memory),
+fp32 (parity path) or bf16 (throughput path, fp32 accumulate).  Skip concatenations are never copied:
+producers write straight into channel slices of the concat buffer, consumers read multi-source.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers (key layout == SURVEY.md Appendix B)
+# ------------------------------------------------------------------------------------------------
+class _ResBlock(nn.Module):  # blocks/residual.py:21-29
+    def __init__(self, c):
+        super().__init__()
+        self.body = nn.Sequential(nn.Conv2d(c, c, 3, 1, 1), nn.ReLU(), nn.Conv2d(c, c, 3, 1, 1))
+
+
+class _FAF(nn.Module):  # blocks/federated_affinity_fusion.py:34-65
+    def __init__(self, nf, frames):
+        super().__init__()
+        self.temporal_attn0 = nn.Conv2d(nf, nf, 3, 1, 1)
+        self.temporal_attn1 = nn.Conv2d(nf, nf, 3, 1, 1)
+        self.feature_fusion = nn.Sequential(nn.Conv2d(nf * frames, nf, 1, 1, 0), nn.PReLU(init=0.1))
+        self.downsample0 = nn.Conv2d(nf, 2 * nf, 4, 2, 1)
+        self.downsample1 = nn.Conv2d(2 * nf, 4 * nf, 4, 2, 1)
+        self.upsample0 = nn.ConvTranspose2d(4 * nf, 2 * nf, 2, 2)
+        self.upsample1 = nn.ConvTranspose2d(4 * nf, nf, 2, 2)
+        self.res_blocks = nn.ModuleList([nn.Sequential(_ResBlock(nf * m), _ResBlock(nf * m)) for m in (1, 2, 4, 4, 2)])
+        self.fusion_tail = nn.Conv2d(2 * nf, nf, 3, 1, 1)
+
+
+class _Proj(nn.Module):  # layers/input_projection.py, output_projection(_hwc).py: conv3x3 + PReLU
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.proj = nn.Sequential(nn.Conv2d(cin, cout, 3, 1, 1), nn.PReLU())
+
+
+class _QKV(nn.Module):  # layers/linear_projection.py:24-44
+    def __init__(self, dim):
+        super().__init__()
+        self.to_q = nn.Linear(dim, dim)
+        self.to_kv = nn.Linear(dim, 2 * dim)
+
+
+def _rel_index(w: int) -> torch.Tensor:
+    """Swin relative position index: ``(dy+w-1)(2w-1) + (dx+w-1)``."""
+    ys, xs = torch.meshgrid(torch.arange(w), torch.arange(w), indexing="ij")
+    ys, xs = ys.flatten(), xs.flatten()
+    return (ys[:, None] - ys[None, :] + w - 1) * (2 * w - 1) + (xs[:, None] - xs[None, :] + w - 1)
+
+
+class _Attn(nn.Module):  # layers/window_attention.py:140-157
+    def __init__(self, dim, win, heads):
+        super().__init__()
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * win - 1) ** 2, heads))
+        self.register_buffer("relative_position_index", _rel_index(win))
+        self.qkv = _QKV(dim)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _LeFF(nn.Module):  # layers/locally_enhanced_feed_forward.py:24-57
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.linear1 = nn.Sequential(nn.Linear(dim, hidden))
+        self.dwconv = nn.Sequential(nn.Conv2d(hidden, hidden, 3, 1, 1, groups=hidden))
+        self.linear2 = nn.Sequential(nn.Linear(hidden, dim))
+
+
+class _Layer(nn.Module):  # layers/fba_net.py:50-111
+    def __init__(self, dim, res, heads, win, shift, mlp_ratio):
+        super().__init__()
+        if min(res) <= win:
+            shift, win = 0, min(res)
+        assert res[0] % win == 0 and res[1] % win == 0, f"input resolution {res} is not divisible by window length {win}"
+        assert dim % heads == 0, "dim must be divisible by number of heads"
+        self.dim, self.res, self.heads, self.win, self.shift = dim, res, heads, win, shift
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = _Attn(dim, win, heads)
+        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = _LeFF(dim, int(dim * mlp_ratio))
+
+
+class _Block(nn.Module):  # blocks/fba_net.py:35-62
+    def __init__(self, dim, res, depth, heads, win, mlp_ratio):
+        super().__init__()
+        self.blocks = nn.ModuleList([_Layer(dim, res, heads, win, 0 if i % 2 == 0 else win // 2, mlp_ratio) for i in range(depth)])
+
+
+class _Down(nn.Module):  # layers/downsample.py
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = nn.Sequential(nn.Conv2d(cin, cout, 4, 2, 1))
+
+
+class _Up(nn.Module):  # layers/upsample.py
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.deconv = nn.Sequential(nn.ConvTranspose2d(cin, cout, 2, 2))
+
+
+def _init_reference_distributions(model: nn.Module, seed: int) -> None:
+    """Equinox-default init: U(+-1/sqrt(fan_in)) for conv/linear weight and bias, LN 1/0,
+    PReLU 0.25 (FAF 0.1), rel-pos table trunc-normal(std .02).  The reference's own JAX key stream
+    (keygen.py:7-15) is not reproducible without JAX."""
+    gen = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            owner = model.get_submodule(name.rsplit(".", 1)[0]) if "." in name else model
+            leaf = name.rsplit(".", 1)[-1]
+            if isinstance(owner, nn.LayerNorm):
+                p.fill_(1.0 if leaf == "weight" else 0.0)
+            elif isinstance(owner, nn.PReLU):
+                p.fill_(0.1 if "feature_fusion" in name else 0.25)
+            elif leaf == "relative_position_bias_table":
+                nn.init.trunc_normal_(p, std=0.02, a=-0.04, b=0.04, generator=gen)
+            else:
+                if isinstance(owner, nn.ConvTranspose2d):
+                    fan_in = owner.in_channels * owner.kernel_size[0] * owner.kernel_size[1]
+                elif isinstance(owner, nn.Conv2d):
+                    fan_in = (owner.in_channels // owner.groups) * owner.kernel_size[0] * owner.kernel_size[1]
+                else:
+                    fan_in = owner.in_features
+                lim = 1.0 / math.sqrt(fan_in)
+                p.copy_((torch.rand(p.shape, generator=gen) * 2 - 1) * lim)
+
+
+# ------------------------------------------------------------------------------------------------
+# the model
+# ------------------------------------------------------------------------------------------------
+class BaseModel(nn.Module):
+    """FBANet BaseModel (``FBANetModel``, models/fba_net.py:30-322) on B200.
+
+    ``dtype``: ``"bf16"`` (default, throughput path) or ``"fp32"`` (parity path, <=1e-3 max-abs vs the
+    CPU oracle).  ``gelu``: ``"tanh"`` (reference default, Appendix A-13) or ``"erf"``.
+    """
+
+    def __init__(
+        self,
+        num_frames: int = 14,
+        img_size: int = 128,
+        in_channels: int = 3,
+        embed_dim: int = 32,
+        depths: Sequence[int] = (2, 2, 2, 2, 2, 2, 2, 2, 2),
+        heads: Sequence[int] = (1, 2, 4, 8, 16, 16, 8, 4, 2),
+        window_length: int = 8,
+        mlp_ratio: float = 4.0,
+        use_qkv_bias: bool = True,
+        qk_scale: Optional[float] = None,
+        drop_rate: float = 0.0,
+        attn_drop_rate: float = 0.0,
+        drop_path_rate: float = 0.1,
+        normalization=None,
+        token_projection: str = "linear",
+        token_mlp: str = "ffn",
+        use_se_layer: bool = False,
+        dtype: str = "bf16",
+        gelu: str = "tanh",
+        seed: int = 0,
+        impl: int = L.IMPL_AUTO,
+    ):
+        super().__init__()
+        if token_projection != "linear" or token_mlp != "leff" or use_se_layer or normalization is not None or not use_qkv_bias:
+            raise NotImplementedError(
+                "fbanet_b200 implements the BaseModel configuration the reference runs "
+                "(token_projection='linear', token_mlp='leff', no SE, LayerNorm, qkv bias); see DESIGN.md"
+            )
+        if img_size % 4:
+            raise ValueError("img_size must be a multiple of 4")
+        E, S, w = embed_dim, img_size, window_length
+        self.num_frames, self.img_size, self.in_channels, self.embed_dim = num_frames, S, in_channels, E
+        self.window_length, self.qk_scale = w, qk_scale
+        self.compute_dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[dtype]
+        self.gelu_act = {"tanh": L.ACT_GELU_TANH, "erf": L.ACT_GELU_ERF}[gelu]
+        self.impl = impl
+        self.head = nn.Conv2d(in_channels, E, 3, 1, 1)
+        self.body = nn.Sequential(_ResBlock(E), _ResBlock(E))
+        self.fusion = _FAF(E, num_frames)
+        self.input_proj = _Proj(E, E)
+        self.output_proj = _Proj(2 * E, E)
+        self.output_proj_2 = _Proj(2 * E, E)
+        self.output_proj_HG2_0 = _Proj(8 * E, 4 * E)
+        self.output_proj_HG2_1 = _Proj(4 * E, 2 * E)
+        for hg in ("HG1", "HG2"):  # A-24: HG2 reuses heads[0], [1], [4], [5], [6]
+            setattr(self, f"{hg}_encoderlayer_0", _Block(E, (S, S), depths[0], heads[0], w, mlp_ratio))
+            setattr(self, f"{hg}_downsample_0", _Down(E, 2 * E))
+            setattr(self, f"{hg}_encoderlayer_1", _Block(2 * E, (S // 2, S // 2), depths[1], heads[1], w, mlp_ratio))
+            setattr(self, f"{hg}_downsample_1", _Down(2 * E, 4 * E))
+            setattr(self, f"conv_{hg}", _Block(4 * E, (S // 4, S // 4), depths[4], heads[4], w, mlp_ratio))
+            setattr(self, f"{hg}_upsample_0", _Up(4 * E, 2 * E))
+            setattr(self, f"{hg}_decoderlayer_0", _Block(4 * E, (S // 2, S // 2), depths[5], heads[5], w, mlp_ratio))
+            setattr(self, f"{hg}_upsample_1", _Up(4 * E, E))
+            setattr(self, f"{hg}_decoderlayer_1", _Block(2 * E, (S, S), depths[6], heads[6], w, mlp_ratio))
+        self.tail = nn.Sequential(  # A-17: x4 = two (conv E->4E, PixelShuffle(2)) + conv E->C_in
+            nn.Sequential(nn.Conv2d(E, 4 * E, 3, 1, 1), nn.PixelShuffle(2), nn.Conv2d(E, 4 * E, 3, 1, 1), nn.PixelShuffle(2)),
+            nn.Conv2d(E, in_channels, 3, 1, 1),
+        )
+        _init_reference_distributions(self, seed)
+        self._packed: Dict[str, torch.Tensor] = {}
+        self._packed_sig = None
+        self.requires_grad_(False)
+
+    # -- weight packing --------------------------------------------------------------------------
+    def _signature(self):
+        dev = self.head.weight.device
+        return (str(dev), self.compute_dtype, tuple(p._version for p in self.parameters()), tuple(p.data_ptr() for p in self.parameters()))
+
+    def packed(self) -> Dict[str, torch.Tensor]:
+        """Kernel-ready weights (K-major GEMM operands, fp32 biases), cached until parameters change."""
+        sig = self._signature()
+        if sig != self._packed_sig:
+            self._packed = self._pack()
+            self._packed_sig = sig
+        return self._packed
+
+    def _pack(self) -> Dict[str, torch.Tensor]:
+        T = self.compute_dtype
+        P: Dict[str, torch.Tensor] = {}
+        cin_pad = 4 if T == torch.float32 else 8  # head input channels padded to a 16-byte pixel
+
+        def conv_w(w, pad_cin=None):  # [Co,Ci,kh,kw] -> [Co, kh*kw*Ci]
+            w = w.detach().float().permute(0, 2, 3, 1)
+            if pad_cin is not None and pad_cin > w.shape[-1]:
+                w = torch.nn.functional.pad(w, (0, pad_cin - w.shape[-1]))
+            return w.reshape(w.shape[0], -1).to(T).contiguous()
+
+        def f32(t):
+            return t.detach().float().contiguous()
+
+        def put_conv(name, m, pad_cin=None):
+            P[name + ".w"] = conv_w(m.weight, pad_cin)
+            P[name + ".b"] = f32(m.bias)
+
+        def put_convT(name, m):  # [Ci,Co,2,2] -> rows (i,j,co), cols ci
+            w = m.weight.detach().float().permute(2, 3, 1, 0)
+            P[name + ".w"] = w.reshape(-1, w.shape[-1]).to(T).contiguous()
+            P[name + ".b"] = f32(m.bias).repeat(4)
+
+        def put_lin(name, m):
+            P[name + ".w"] = m.weight.detach().to(T).contiguous()
+            P[name + ".b"] = f32(m.bias)
+
+        put_conv("head", self.head, cin_pad)
+        for i, rb in enumerate(self.body):
+            put_conv(f"body.{i}.0", rb.body[0])
+            put_conv(f"body.{i}.2", rb.body[2])
+        fu = self.fusion
+        # K2a: gate weights = sum over output channels of temporal_attn1 (temporal_attn0 and the biases
+        # cancel in |aff_f - aff_0|; DESIGN.md "FAF gate identity").  Summed in fp64.
+        P["fusion.wsum"] = fu.temporal_attn1.weight.detach().double().sum(0).permute(1, 2, 0).reshape(9, -1).float().contiguous()
+        put_conv("fusion.fuse", fu.feature_fusion[0])
+        P["fusion.fuse.alpha"] = f32(fu.feature_fusion[1].weight)
+        put_conv("fusion.down0", fu.downsample0)
+        put_conv("fusion.down1", fu.downsample1)
+        put_convT("fusion.up0", fu.upsample0)
+        put_convT("fusion.up1", fu.upsample1)
+        for i, seq in enumerate(fu.res_blocks):
+            for j, rb in enumerate(seq):
+                put_conv(f"fusion.rb.{i}.{j}.0", rb.body[0])
+                put_conv(f"fusion.rb.{i}.{j}.2", rb.body[2])
+        put_conv("fusion.tail", fu.fusion_tail)
+        for n in ("input_proj", "output_proj", "output_proj_2", "output_proj_HG2_0", "output_proj_HG2_1"):
+            m = getattr(self, n)
+            put_conv(n, m.proj[0])
+            P[n + ".alpha"] = f32(m.proj[1].weight)
+        for hg in ("HG1", "HG2"):
+            for bn in (f"{hg}_encoderlayer_0", f"{hg}_encoderlayer_1", f"conv_{hg}", f"{hg}_decoderlayer_0", f"{hg}_decoderlayer_1"):
+                for i, ly in enumerate(getattr(self, bn).blocks):
+                    k = f"{bn}.{i}"
+                    P[k + ".ln1.g"], P[k + ".ln1.b"] = f32(ly.norm1.weight), f32(ly.norm1.bias)
+                    P[k + ".ln2.g"], P[k + ".ln2.b"] = f32(ly.norm2.weight), f32(ly.norm2.bias)
+                    a = ly.attn
+                    P[k + ".qkv.w"] = torch.cat([a.qkv.to_q.weight.detach(), a.qkv.to_kv.weight.detach()], 0).to(T).contiguous()
+                    P[k + ".qkv.b"] = torch.cat([f32(a.qkv.to_q.bias), f32(a.qkv.to_kv.bias)], 0).contiguous()
+                    P[k + ".rpb"] = f32(a.relative_position_bias_table)
+                    put_lin(k + ".proj", a.proj)
+                    put_lin(k + ".fc1", ly.mlp.linear1[0])
+                    put_lin(k + ".fc2", ly.mlp.linear2[0])
+                    dw = ly.mlp.dwconv[0]
+                    P[k + ".dw.w"] = dw.weight.detach().float().reshape(dw.weight.shape[0], 9).t().contiguous()
+                    P[k + ".dw.b"] = f32(dw.bias)
+            put_conv(f"{hg}_downsample_0", getattr(self, f"{hg}_downsample_0").conv[0])
+            put_conv(f"{hg}_downsample_1", getattr(self, f"{hg}_downsample_1").conv[0])
+            put_convT(f"{hg}_upsample_0", getattr(self, f"{hg}_upsample_0").deconv[0])
+            put_convT(f"{hg}_upsample_1", getattr(self, f"{hg}_upsample_1").deconv[0])
+        put_conv("tail.0.0", self.tail[0][0])
+        put_conv("tail.0.2", self.tail[0][2])
+        put_conv("tail.1", self.tail[1])
+        return P
+
+    # -- building blocks ---------------------------------------------------------------------------
+    def _new(self, *shape):
+        return torch.empty(shape, device=self.head.weight.device, dtype=self.compute_dtype)
+
+    def _conv3(self, P, name, srcs, out=None, act=L.ACT_NONE, alpha=None, residual=None, store=L.STORE_NHWC, **kw):
+        w = P[name + ".w"]
+        N, H, W, _ = srcs[0].shape
+        if out is None:
+            out = self._new(N, H, W, w.shape[0])
+        return ops.conv_gemm(srcs, w, out, kh=3, kw=3, stride=1, pad=1, bias=P[name + ".b"], act=act, alpha=alpha,
+                             residual=residual, store_mode=store, impl=self.impl, **kw)
+
+    def _resblock(self, P, name, x, out=None):
+        """x + conv(relu(conv(x)))  (blocks/residual.py:28)"""
+        t = self._conv3(P, name + ".0", [x], act=L.ACT_RELU)
+        return self._conv3(P, name + ".2", [t], out=out, residual=x)
+
+    def _down(self, P, name, x, out=None):
+        N, H, W, _ = x.shape
+        w = P[name + ".w"]
+        if out is None:
+            out = self._new(N, H // 2, W // 2, w.shape[0])
+        return ops.conv_gemm([x], w, out, kh=4, kw=4, stride=2, pad=1, bias=P[name + ".b"], impl=self.impl)
+
+    def _up(self, P, name, x, out):
+        """ConvTranspose2d(2,2) as a per-pixel GEMM with a 2x2 scatter store into ``out`` (a concat slice)."""
+        return ops.conv_gemm([x], P[name + ".w"], out, bias=P[name + ".b"], store_mode=L.STORE_CONVT2, impl=self.impl)
+
+    def _lin(self, P, name, x4, out=None, act=L.ACT_NONE, residual=None):
+        w = P[name + ".w"]
+        if out is None:
+            out = self._new(*x4.shape[:3], w.shape[0])
+        return ops.conv_gemm([x4], w, out, bias=P[name + ".b"], act=act, residual=residual, impl=self.impl)
+
+    def _layer(self, P, key, ly: _Layer, x, out=None):
+        """LeWin block (layers/fba_net.py:139-250 with Appendix A-4): x + Attn(LN1 x); + LeFF(LN2 .)."""
+        B, H, W, Cd = x.shape
+        ln1 = ops.layernorm(x.view(-1, Cd), P[key + ".ln1.g"], P[key + ".ln1.b"]).view(B, H, W, Cd)
+        qkv = self._lin(P, key + ".qkv", ln1)
+        scale = self.qk_scale or (Cd // ly.heads) ** -0.5
+        att = ops.window_attention(qkv.view(-1, 3 * Cd), P[key + ".rpb"], B, H, W, ly.heads, ly.win, ly.shift, scale, impl=self.impl)
+        x1 = self._lin(P, key + ".proj", att.view(B, H, W, Cd), residual=x)
+        ln2 = ops.layernorm(x1.view(-1, Cd), P[key + ".ln2.g"], P[key + ".ln2.b"]).view(B, H, W, Cd)
+        h = self._lin(P, key + ".fc1", ln2, act=self.gelu_act)
+        h = ops.dwconv3x3(h, P[key + ".dw.w"], P[key + ".dw.b"], self.gelu_act)
+        return self._lin(P, key + ".fc2", h, out=out, residual=x1)
+
+    def _block(self, P, name, x, out=None):
+        blk = getattr(self, name).blocks
+        for i, ly in enumerate(blk):
+            x = self._layer(P, f"{name}.{i}", ly, x, out=out if i == len(blk) - 1 else None)
+        return x
+
+    def _faf(self, P, feat):
+        """FAFBlock (blocks/federated_affinity_fusion.py:166-182). feat ``[B,F,H,W,E]``."""
+        B, Fr, H, W, E = feat.shape
+        gate = ops.faf_gate(feat, P["fusion.wsum"])  # :79-99 collapsed, see _pack
+        srcs = [feat[:, f] for f in range(Fr)]
+        scales = [None] + [gate[:, f - 1] for f in range(1, Fr)]
+        z = ops.conv_gemm(srcs, P["fusion.fuse.w"], self._new(B, H, W, E), bias=P["fusion.fuse.b"], act=L.ACT_PRELU,
+                          alpha=P["fusion.fuse.alpha"], row_scales=scales, impl=self.impl)  # :121-128
+        cat4 = self._new(B, H, W, 2 * E)            # [up1 | r0]
+        cat3 = self._new(B, H // 2, W // 2, 4 * E)  # [up0 | r1]
+        r0 = cat4[..., E:]
+        r1 = cat3[..., 2 * E:]
+        t = self._resblock(P, "fusion.rb.0.0", z)
+        self._resblock(P, "fusion.rb.0.1", t, out=r0)
+        t = self._down(P, "fusion.down0", r0)
+        t = self._resblock(P, "fusion.rb.1.0", t)
+        self._resblock(P, "fusion.rb.1.1", t, out=r1)
+        t = self._down(P, "fusion.down1", r1)
+        t = self._resblock(P, "fusion.rb.2.0", t)
+        r2 = self._resblock(P, "fusion.rb.2.1", t)
+        self._up(P, "fusion.up0", r2, cat3[..., : 2 * E])
+        t = self._resblock(P, "fusion.rb.3.0", cat3)
+        r3 = self._resblock(P, "fusion.rb.3.1", t)
+        self._up(P, "fusion.up1", r3, cat4[..., :E])
+        t = self._resblock(P, "fusion.rb.4.0", cat4)
+        r4 = self._resblock(P, "fusion.rb.4.1", t)
+        return self._conv3(P, "fusion.tail", [r4], residual=z), z, gate  # :161
+
+    def _hourglass(self, P, hg, y, prev, st):
+        """models/fba_net.py:271-287 (HG1) / :294-310 (HG2).  ``prev`` = HG1's (cat0, cat1) concat buffers."""
+        B, S, _, E = y.shape
+        if prev is None:
+            cat1 = self._new(B, S, S, 2 * E)            # [up1 | conv0]
+            cat0 = self._new(B, S // 2, S // 2, 4 * E)  # [up0 | conv1]
+            conv0, up1 = cat1[..., E:], cat1[..., :E]
+            conv1, up0 = cat0[..., 2 * E:], cat0[..., : 2 * E]
+        else:
+            conv0, up1 = self._new(B, S, S, E), self._new(B, S, S, E)
+            conv1, up0 = self._new(B, S // 2, S // 2, 2 * E), self._new(B, S // 2, S // 2, 2 * E)
+        self._block(P, f"{hg}_encoderlayer_0", y, out=conv0)
+        pool0 = self._down(P, f"{hg}_downsample_0", conv0)
+        self._block(P, f"{hg}_encoderlayer_1", pool0, out=conv1)
+        pool1 = self._down(P, f"{hg}_downsample_1", conv1)
+        conv2 = self._block(P, f"conv_{hg}", pool1)
+        self._up(P, f"{hg}_upsample_0", conv2, up0)
+        if prev is None:
+            d0_in = cat0
+        else:  # output_proj_HG2_0(cat[up0, conv1, up0_2, conv1_2])  (:305)
+            d0_in = self._conv3(P, "output_proj_HG2_0", [prev[0], up0, conv1], act=L.ACT_PRELU, alpha=P["output_proj_HG2_0.alpha"])
+        deconv0 = self._block(P, f"{hg}_decoderlayer_0", d0_in)
+        self._up(P, f"{hg}_upsample_1", deconv0, up1)
+        if prev is None:
+            d1_in = cat1
+        else:  # output_proj_HG2_1(cat[up1, conv0, up1_2, conv0_2])  (:309)
+            d1_in = self._conv3(P, "output_proj_HG2_1", [prev[1], up1, conv0], act=L.ACT_PRELU, alpha=P["output_proj_HG2_1.alpha"])
+        deconv1 = self._block(P, f"{hg}_decoderlayer_1", d1_in)
+        if st is not None:
+            for k, v in dict(conv0=conv0, pool0=pool0, conv1=conv1, pool1=pool1, conv2=conv2, up0=up0, deconv0_in=d0_in,
+                             deconv0=deconv0, up1=up1, deconv1_in=d1_in, deconv1=deconv1).items():
+                st[f"{hg}.{k}"] = v
+        return deconv1, ((cat0, cat1) if prev is None else None)
+
+    # -- forward -----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_stages(self, x: torch.Tensor, stages: Optional[dict] = None) -> torch.Tensor:
+        """The forward; when ``stages`` is a dict every named intermediate (channels-last) is recorded."""
+        L.load()  # fail loudly if the CUDA library is absent
+        if x.dim() != 5 or tuple(x.shape[1:]) != (self.num_frames, self.in_channels, self.img_size, self.img_size):
+            raise AssertionError(  # mirrors assert_shape at models/fba_net.py:244
+                f"expected burst [B,{self.num_frames},{self.in_channels},{self.img_size},{self.img_size}], got {tuple(x.shape)}"
+            )
+        if not x.is_cuda:
+            raise RuntimeError("fbanet_b200.BaseModel runs on CUDA tensors only (use infer_host for host buffers); no CPU fallback")
+        x = x.contiguous().float()
+        P = self.packed()
+        st = stages
+        B, Fr, Cin, S, _ = x.shape
+        E, T = self.embed_dim, self.compute_dtype
+        cin_pad = 4 if T == torch.float32 else 8
+        xn = ops.to_nhwc(x.view(B * Fr, Cin, S, S), cin_pad, T)
+        f = self._conv3(P, "head", [xn], alg_cin=Cin)                            # :255
+        if st is not None:
+            st["head"] = f.view(B, Fr, S, S, E)
+        f = self._resblock(P, "body.0", f)                                        # :258
+        f = self._resblock(P, "body.1", f)
+        feat = f.view(B, Fr, S, S, E)
+        fused, z, gate = self._faf(P, feat)                                       # :262
+        y = self._conv3(P, "input_proj", [fused], act=L.ACT_PRELU, alpha=P["input_proj.alpha"])  # :266
+        if st is not None:
+            st.update({"body": feat, "faf.gate": gate, "faf.fuse1x1": z, "fusion": fused, "input_proj": y})
+        d1, prev = self._hourglass(P, "HG1", y, None, st)                         # :271-287
+        y1 = self._conv3(P, "output_proj", [d1], act=L.ACT_PRELU, alpha=P["output_proj.alpha"])  # :290
+        d1_2, _ = self._hourglass(P, "HG2", y1, prev, st)                         # :294-310
+        y2 = self._conv3(P, "output_proj_2", [d1_2], act=L.ACT_PRELU, alpha=P["output_proj_2.alpha"])  # :313
+        t1 = self._conv3(P, "tail.0.0", [y2], out=self._new(B, 2 * S, 2 * S, E), store=L.STORE_PS2)  # :315
+        t2 = self._conv3(P, "tail.0.2", [t1], out=self._new(B, 4 * S, 4 * S, E), store=L.STORE_PS2)
+        out = torch.empty((B, Cin, 4 * S, 4 * S), device=x.device, dtype=torch.float32)
+        self._conv3(P, "tail.1", [t2], out=out, store=L.STORE_NCHW_BASE, base=x[:, 0], cout_store=Cin)  # :315-320 (+ bilinear x4 base)
+        if st is not None:
+            st.update({"output_proj": y1, "output_proj_2": y2, "tail.ps1": t1, "tail.ps2": t2, "out": out})
+        return out
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.forward_stages(x, None)
+
+    @torch.no_grad()
+    def forward_fhwc(self, x: torch.Tensor) -> torch.Tensor:
+        """The reference's JAX signature: ``x [F,H,W,C] -> [4H,4W,C]`` (models/fba_net.py:242)."""
+        return self.forward(x.permute(0, 3, 1, 2).unsqueeze(0)).squeeze(0).permute(1, 2, 0)
+
+    @torch.no_grad()
+    def infer_host(self, burst: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """End-to-end call with HOST buffers: pinned H2D copy, forward, D2H copy of the SR image."""
+        dev = self.head.weight.device
+        if not burst.is_pinned():
+            burst = burst.pin_memory()
+        xd = burst.to(dev, non_blocking=True)
+        y = self.forward(xd)
+        if out is None:
+            out = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
+        out.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out
+
+    # -- checkpoint compatibility (utils/model_utils.py:28-48) ----------------------------------------
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        sd = {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+        r = super().load_state_dict(sd, strict=strict, assign=assign)
+        self._packed_sig = None
+        return r

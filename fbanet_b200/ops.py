@@ -1,0 +1,274 @@
+"""Thin torch-tensor wrappers over the C-ABI kernels (``include/fbanet_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the stream; every op is a hand-written sm_100a
+kernel launched through ctypes on ``torch.cuda.current_stream()``.  No op has a CPU or eager fallback.
+
+Channels-last views: a tensor ``[N,H,W,C]`` with ``stride(-1) == 1`` and ``stride(1) == W*stride(2)``
+(channel slices of wider buffers are fine -- that is how concat-free skip connections are wired).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+
+# launch counter: bench.py reports how many of OUR kernels ran in the timed region
+LAUNCHES = 0
+# when a list, conv_gemm appends (start_event, end_event, algorithmic_flops) per launch (bench roofline)
+_PROFILE = None
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _call(name, p):
+    global LAUNCHES
+    LAUNCHES += 1
+    L.call(name, p, _stream())
+
+
+def _cl(t: torch.Tensor):
+    """(ptr, C, ld, img_stride) of a channels-last view ``[N,H,W,C]``."""
+    assert t.is_cuda and t.dim() == 4, "expected a CUDA [N,H,W,C] view"
+    N, H, W, Cc = t.shape
+    sN, sH, sW, sC = t.stride()
+    assert sC == 1 and (H == 1 or sH == W * sW), f"not a channels-last view: shape {tuple(t.shape)} stride {t.stride()}"
+    if N == 1:
+        sN = H * W * sW
+    return t.data_ptr(), Cc, sW, sN
+
+
+def conv_gemm(
+    srcs: Sequence[torch.Tensor],
+    weight: torch.Tensor,
+    out: torch.Tensor,
+    *,
+    kh: int = 1,
+    kw: int = 1,
+    stride: int = 1,
+    pad: int = 0,
+    bias: Optional[torch.Tensor] = None,
+    act: int = L.ACT_NONE,
+    alpha: Optional[torch.Tensor] = None,
+    residual: Optional[torch.Tensor] = None,
+    store_mode: int = L.STORE_NHWC,
+    row_scales: Optional[Sequence[Optional[torch.Tensor]]] = None,
+    base: Optional[torch.Tensor] = None,
+    cout_store: Optional[int] = None,
+    impl: int = L.IMPL_AUTO,
+    alg_cin: Optional[int] = None,
+) -> torch.Tensor:
+    """out = act(conv(concat(srcs)) + bias) + residual.  ``weight`` is packed ``[Cout, kh*kw*sum(C)]``."""
+    p = L.ConvParams()
+    dt = srcs[0].dtype
+    p.dtype = _DT[dt]
+    p.impl = impl
+    p.nsrc = len(srcs)
+    assert 1 <= len(srcs) <= L.MAX_SRC
+    N, H, W, _ = srcs[0].shape
+    ctot = 0
+    for i, s in enumerate(srcs):
+        assert s.dtype == dt and s.shape[:3] == (N, H, W)
+        ptr, Cc, ld, istr = _cl(s)
+        p.src[i].ptr, p.src[i].C, p.src[i].ld, p.src[i].img_stride = ptr, Cc, ld, istr
+        ctot += Cc
+        rs = row_scales[i] if row_scales is not None else None
+        if rs is not None:  # [N,H,W] fp32 view, contiguous inside an image
+            assert rs.dtype == torch.float32 and rs.shape == (N, H, W) and rs.stride(2) == 1 and rs.stride(1) == W
+            p.src[i].row_scale = rs.data_ptr()
+            p.src[i].scale_img_stride = rs.stride(0) if N > 1 else H * W
+    cout = weight.shape[0]
+    assert weight.dtype == dt and weight.is_contiguous() and weight.shape[1] == kh * kw * ctot, (weight.shape, kh, kw, ctot)
+    p.weight = weight.data_ptr()
+    p.N, p.H, p.W = N, H, W
+    p.KH, p.KW, p.stride, p.pad = kh, kw, stride, pad
+    Ho = (H + 2 * pad - kh) // stride + 1
+    Wo = (W + 2 * pad - kw) // stride + 1
+    p.Ho, p.Wo, p.Cout = Ho, Wo, cout
+    p.Cout_store = cout if cout_store is None else cout_store
+    p.act, p.store_mode = act, store_mode
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == cout
+        p.bias = bias.data_ptr()
+    if alpha is not None:
+        assert alpha.dtype == torch.float32
+        p.alpha = alpha.data_ptr()
+    if residual is not None:
+        assert residual.dtype == dt and residual.shape == (N, Ho, Wo, cout)
+        rp, _, rld, ris = _cl(residual)
+        p.residual, p.res_ld, p.res_img_stride = rp, rld, ris
+    if store_mode == L.STORE_NCHW_BASE:
+        assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == (N, p.Cout_store, Ho, Wo)
+        assert base is not None and base.dtype == torch.float32 and base.shape == (N, p.Cout_store, Ho // 4, Wo // 4)
+        assert base.stride(3) == 1 and base.stride(2) == Wo // 4 and base.stride(1) == (Ho // 4) * (Wo // 4)
+        p.out, p.out_img_stride = out.data_ptr(), p.Cout_store * Ho * Wo
+        p.base, p.base_img_stride = base.data_ptr(), (base.stride(0) if N > 1 else 0)
+    else:
+        assert out.dtype == dt
+        if store_mode == L.STORE_NHWC:
+            assert out.shape == (N, Ho, Wo, p.Cout_store)
+        elif store_mode == L.STORE_PS2:
+            assert out.shape == (N, 2 * Ho, 2 * Wo, cout // 4)
+        else:
+            assert out.shape == (N, 2 * Ho, 2 * Wo, cout // 4)
+        op, _, old, ois = _cl(out)
+        p.out, p.out_ld, p.out_img_stride = op, old, ois
+    if _PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _call("fbanet_conv_gemm_sm100", p)
+        e1.record()
+        flops = 2.0 * N * Ho * Wo * kh * kw * (ctot if alg_cin is None else alg_cin) * p.Cout_store
+        _PROFILE.append((e0, e1, flops))
+        return out
+    _call("fbanet_conv_gemm_sm100", p)
+    return out
+
+
+def profile_conv_gemm(fn, stream) -> dict:
+    """Run ``fn`` once with CUDA events around every implicit-GEMM launch; returns summed device time,
+    algorithmic FLOPs (2*M*K*N with unpadded channels) and the achieved TFLOP/s of that kernel family."""
+    global _PROFILE
+    _PROFILE = []
+    try:
+        fn()
+        stream.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b, _ in _PROFILE)
+        flops = sum(f for _, _, f in _PROFILE)
+        n = len(_PROFILE)
+    finally:
+        _PROFILE = None
+    return {"kernel": "fbanet_conv_gemm_sm100 (implicit-GEMM conv/linear, all launches of one step)", "ms": ms, "flops": flops,
+            "launches": n, "tflops": flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}
+
+
+def tcgen05_supported(p: L.ConvParams) -> bool:
+    return bool(L.load().fbanet_conv_gemm_tcgen05_supported(C.byref(p)))
+
+
+def to_nhwc(x: torch.Tensor, cp: int, dtype: torch.dtype) -> torch.Tensor:
+    """planar fp32 ``[frames,C,H,W]`` -> channels-last ``[frames,H,W,cp]`` (zero padded channels)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    Fr, Cc, H, W = x.shape
+    out = torch.empty((Fr, H, W, cp), device=x.device, dtype=dtype)
+    p = L.ToNhwcParams()
+    p.src, p.dst, p.dtype = x.data_ptr(), out.data_ptr(), _DT[dtype]
+    p.frames, p.C, p.H, p.W, p.Cp = Fr, Cc, H, W, cp
+    _call("fbanet_to_nhwc_sm100", p)
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """LayerNorm over the last dim of a ``[rows, C]`` view (row stride may exceed C)."""
+    assert x.is_cuda and x.dim() == 2 and x.stride(1) == 1
+    rows, Cc = x.shape
+    y = torch.empty((rows, Cc), device=x.device, dtype=x.dtype)
+    p = L.LayerNormParams()
+    p.x, p.y, p.gamma, p.beta = x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+    p.rows, p.C, p.x_ld, p.y_ld, p.dtype, p.eps = rows, Cc, x.stride(0), Cc, _DT[x.dtype], eps
+    _call("fbanet_layernorm_sm100", p)
+    return y
+
+
+def window_attention(qkv: torch.Tensor, bias_table: torch.Tensor, B: int, H: int, W: int, heads: int, win: int, shift: int,
+                     scale: float, impl: int = L.IMPL_AUTO) -> torch.Tensor:
+    """qkv ``[B*H*W, 3C]`` -> ``[B*H*W, C]``."""
+    assert qkv.is_cuda and qkv.dim() == 2 and qkv.stride(1) == 1 and qkv.shape[0] == B * H * W
+    Cc = qkv.shape[1] // 3
+    out = torch.empty((B * H * W, Cc), device=qkv.device, dtype=qkv.dtype)
+    assert bias_table.dtype == torch.float32 and bias_table.is_contiguous() and bias_table.shape == ((2 * win - 1) ** 2, heads)
+    p = L.AttnParams()
+    p.qkv, p.out, p.bias_table, p.dtype = qkv.data_ptr(), out.data_ptr(), bias_table.data_ptr(), _DT[qkv.dtype]
+    p.B, p.H, p.W, p.C, p.heads, p.win, p.shift = B, H, W, Cc, heads, win, shift
+    p.qkv_ld, p.out_ld, p.scale, p.impl = qkv.stride(0), Cc, scale, impl
+    _call("fbanet_window_attention_sm100", p)
+    return out
+
+
+def dwconv3x3(x: torch.Tensor, weight9c: torch.Tensor, bias: torch.Tensor, act: int) -> torch.Tensor:
+    """depthwise 3x3 pad 1 + bias + act on contiguous ``[N,H,W,C]``; ``weight9c`` is ``[9,C]`` fp32."""
+    assert x.is_cuda and x.is_contiguous() and x.dim() == 4
+    N, H, W, Cc = x.shape
+    y = torch.empty_like(x)
+    p = L.DwconvParams()
+    p.x, p.y, p.weight, p.bias, p.dtype = x.data_ptr(), y.data_ptr(), weight9c.data_ptr(), bias.data_ptr(), _DT[x.dtype]
+    p.N, p.H, p.W, p.C, p.act = N, H, W, Cc, act
+    _call("fbanet_dwconv3x3_sm100", p)
+    return y
+
+
+def faf_gate(feat: torch.Tensor, wsum: torch.Tensor) -> torch.Tensor:
+    """feat ``[B,F,H,W,C]`` contiguous -> gate ``[B,F-1,H,W]`` fp32."""
+    assert feat.is_cuda and feat.is_contiguous() and feat.dim() == 5
+    B, Fr, H, W, Cc = feat.shape
+    gate = torch.empty((B, Fr - 1, H, W), device=feat.device, dtype=torch.float32)
+    p = L.FafGateParams()
+    p.feat, p.gate, p.wsum, p.dtype = feat.data_ptr(), gate.data_ptr(), wsum.data_ptr(), _DT[feat.dtype]
+    p.B, p.F, p.H, p.W, p.C = B, Fr, H, W, Cc
+    _call("fbanet_faf_gate_sm100", p)
+    return gate
+
+
+def warp_burst(burst: torch.Tensor, M: torch.Tensor, layout: str = "BTCHW", return_coords: bool = False):
+    """Homography warp with bilinear sampling (cv2 ``INTER_LINEAR + WARP_INVERSE_MAP``, border 0).
+
+    ``burst``: fp32 ``[B,T,C,H,W]`` (layout ``"BTCHW"``) or ``[B,T,H,W,C]`` (``"BTHWC"``, the cv2 layout);
+    ``M``: ``[B,T,3,3]`` float64 dst->src matrices (entry for frame 0 ignored: the base frame is copied).
+    """
+    assert burst.is_cuda and burst.dtype == torch.float32 and burst.is_contiguous() and burst.dim() == 5
+    B, T = burst.shape[:2]
+    if layout == "BTCHW":
+        Cc, H, W = burst.shape[2:]
+        sf, sc, sy, sx = Cc * H * W, H * W, W, 1
+    elif layout == "BTHWC":
+        H, W, Cc = burst.shape[2:]
+        sf, sy, sx, sc = H * W * Cc, W * Cc, Cc, 1
+    else:
+        raise ValueError(layout)
+    M = M.to(device=burst.device, dtype=torch.float64).contiguous()
+    assert M.shape == (B, T, 3, 3)
+    out = torch.empty_like(burst)
+    coords = torch.empty((B, T, H, W, 2), device=burst.device, dtype=torch.float64) if return_coords else None
+    p = L.WarpParams()
+    p.src, p.dst, p.M = burst.data_ptr(), out.data_ptr(), M.data_ptr()
+    p.coords = coords.data_ptr() if coords is not None else None
+    p.s_frame, p.s_y, p.s_x, p.s_c = sf, sy, sx, sc
+    p.d_frame, p.d_y, p.d_x, p.d_c = sf, sy, sx, sc
+    p.frames, p.frames_per_burst, p.H, p.W, p.C = B * T, T, H, W, Cc
+    _call("fbanet_warp_sm100", p)
+    return (out, coords) if return_coords else out
+
+
+def tile_divide(burst: torch.Tensor, psize: int, overlap: int, tile_begin: int = 0, tile_end: Optional[int] = None) -> torch.Tensor:
+    """``[T,C,H,W]`` fp32 -> ``[tiles,T,C,psize+2ov,psize+2ov]`` (reflect padded, tile index row-major)."""
+    assert burst.is_cuda and burst.dtype == torch.float32 and burst.is_contiguous() and burst.dim() == 4
+    T, Cc, H, W = burst.shape
+    nh, nw = -(-H // psize), -(-W // psize)
+    tile_end = nh * nw if tile_end is None else tile_end
+    ts = psize + 2 * overlap
+    out = torch.empty((tile_end - tile_begin, T, Cc, ts, ts), device=burst.device, dtype=torch.float32)
+    p = L.TileParams()
+    p.src, p.dst = burst.data_ptr(), out.data_ptr()
+    p.T, p.C, p.H, p.W, p.psize, p.overlap, p.tile_begin, p.tile_end, p.scale = T, Cc, H, W, psize, overlap, tile_begin, tile_end, 1
+    _call("fbanet_tile_divide_sm100", p)
+    return out
+
+
+def tile_merge(tiles: torch.Tensor, out: torch.Tensor, H: int, W: int, psize: int, overlap: int, scale: int,
+               tile_begin: int = 0, tile_end: Optional[int] = None) -> torch.Tensor:
+    """SR tiles ``[n,C,scale*(psize+2ov)]^2`` -> centre-cropped stitch into ``out [C, scale*H, scale*W]``."""
+    assert tiles.is_cuda and tiles.dtype == torch.float32 and tiles.is_contiguous() and out.is_contiguous()
+    nh, nw = -(-H // psize), -(-W // psize)
+    tile_end = nh * nw if tile_end is None else tile_end
+    assert tiles.shape[0] == tile_end - tile_begin and out.shape == (tiles.shape[1], scale * H, scale * W)
+    p = L.TileParams()
+    p.src, p.dst = tiles.data_ptr(), out.data_ptr()
+    p.T, p.C, p.H, p.W, p.psize, p.overlap, p.tile_begin, p.tile_end, p.scale = 1, tiles.shape[1], H, W, psize, overlap, tile_begin, tile_end, scale
+    _call("fbanet_tile_merge_sm100", p)
+    return out

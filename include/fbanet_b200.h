@@ -1,0 +1,210 @@
+/*
+ * fbanet_b200 -- C ABI of the B200 (sm_100a) kernels behind the FBANet BaseModel burst-SR forward.
+ *
+ * Drop-in boundary: the reference has no first-party native code; every op below
+ * replaces a library call the reference reaches through JAX/XLA/cuDNN or OpenCV.  The Python host
+ * (fbanet_b200/model.py) mirrors the reference's model API (`get_arch(opt)`, `model(burst) -> SR`,
+ * state_dict key layout) and calls these entry points through ctypes.
+ *
+ * Conventions
+ *   - every entry point: `int fbanet_<op>_sm100(const <op>_params*, void* stream)`; `stream` is a
+ *     cudaStream_t.  Returns 0 or a negative FBANET_E_* code; never throws, never synchronises, never
+ *     allocates or frees caller memory.  Launch errors are reported through the return code
+ *     (cudaGetLastError) -- the Python wrapper turns them into RuntimeError.
+ *   - all pointers are DEVICE pointers owned by the caller.  Tensors are channels-last views:
+ *     element (n, y, x, c) of a view lives at  ptr + n*img_stride + (y*W + x)*ld + c   (in elements).
+ *     Tokens [T, C] of the transformer are exactly such views with T = H*W (t = y*W + x).
+ *   - dtype: FBANET_F32 (parity path, fp32 storage + fp32 FMA) or FBANET_BF16 (bf16 storage, fp32
+ *     accumulate; dense contractions on tcgen05 tensor cores when `impl` allows).
+ *   - stateless and re-entrant; stream ordered; safe for one-process-per-GPU sharding.
+ */
+#ifndef FBANET_B200_H
+#define FBANET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FBANET_ABI_VERSION 3
+
+enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
+
+enum {
+  FBANET_OK = 0,
+  FBANET_E_BADSHAPE = -1,   /* unsupported / inconsistent shape            */
+  FBANET_E_ALIGN = -2,      /* pointer or stride not aligned as required   */
+  FBANET_E_DTYPE = -3,      /* unsupported dtype for this op               */
+  FBANET_E_LAUNCH = -4,     /* CUDA launch failure (see fbanet_last_cuda_error) */
+  FBANET_E_UNSUPPORTED = -5 /* requested impl cannot run this problem      */
+};
+
+enum { FBANET_ACT_NONE = 0, FBANET_ACT_RELU = 1, FBANET_ACT_PRELU = 2, FBANET_ACT_GELU_TANH = 3, FBANET_ACT_GELU_ERF = 4 };
+
+/* how the GEMM result tile [rows = N*Ho*Wo pixels, cols = Cout] is stored */
+enum {
+  FBANET_STORE_NHWC = 0,     /* out(n,y,x,col)                                                     */
+  FBANET_STORE_PS2 = 1,      /* PixelShuffle(2): col = 4c+2i+j -> out(n, 2y+i, 2x+j, c)            */
+  FBANET_STORE_CONVT2 = 2,   /* ConvTranspose 2x2 s2: col = (2i+j)*Co + co -> out(n,2y+i,2x+j,co)  */
+  FBANET_STORE_NCHW_BASE = 3 /* fp32 planar out[n][col][y][x] + bilinear x4 of `base` (final conv) */
+};
+
+enum { FBANET_IMPL_AUTO = 0, FBANET_IMPL_SIMT = 1, FBANET_IMPL_TCGEN05 = 2 };
+
+#define FBANET_MAX_SRC 16
+
+/* One channels-last source view of an implicit-GEMM operand (concat-free inputs: the K axis of the
+ * contraction runs over taps x (src0 channels, src1 channels, ...)). */
+typedef struct fbanet_src {
+  const void* ptr;        /* element (0,0,0,0)                                                   */
+  const float* row_scale; /* optional per-pixel fp32 multiplier (FAF gate), index n*scale_img_stride + y*W + x */
+  int64_t img_stride;     /* elements between images                                             */
+  int64_t scale_img_stride;
+  int32_t C;              /* channels taken from this source                                     */
+  int32_t ld;             /* elements between pixels                                             */
+} fbanet_src;
+
+/* K3/K4/K5/K9: implicit-GEMM convolution / linear layer with fused epilogue.
+ * Replaces eqx.nn.Conv2d / ConvTranspose2d / Linear call sites:
+ *   layers/conv2d.py:33-43, layers/conv2d_transpose.py:20-26, layers/linear_projection.py:27-28,
+ *   layers/window_attention.py:157, layers/locally_enhanced_feed_forward.py:27,56,
+ *   blocks/residual.py:21-29, blocks/upsampler.py:22-32, models/fba_net.py:255-320.
+ * out = act(conv(concat(src...)) + bias) + residual, stored per `store_mode`. */
+typedef struct fbanet_conv_params {
+  fbanet_src src[FBANET_MAX_SRC];
+  const void* weight;     /* packed [Cout][KH*KW*Ctot] (k = (ky*KW+kx)*Ctot + c), dtype = `dtype`    */
+  const float* bias;      /* [Cout] fp32 or NULL                                                    */
+  const float* alpha;     /* PReLU slope (device scalar) when act == PRELU                          */
+  const void* residual;   /* optional, NHWC view shaped like the output rows (store NHWC only)      */
+  void* out;
+  const float* base;      /* STORE_NCHW_BASE: low-res frame, planar fp32 [n][c][Ho/4][Wo/4]          */
+  int64_t res_img_stride;
+  int64_t out_img_stride; /* elements between output images                                         */
+  int64_t base_img_stride;
+  int32_t dtype;
+  int32_t impl;
+  int32_t nsrc;
+  int32_t N, H, W;        /* input images and their size                                            */
+  int32_t KH, KW, stride, pad;
+  int32_t Ho, Wo;         /* GEMM rows per image = Ho*Wo                                            */
+  int32_t Cout;           /* GEMM columns (weight rows)                                             */
+  int32_t Cout_store;     /* columns actually stored (<= Cout; Cout may be zero-padded)             */
+  int32_t act;
+  int32_t store_mode;
+  int32_t res_ld;
+  int32_t out_ld;         /* elements between output pixels (NHWC family)                           */
+} fbanet_conv_params;
+
+/* K1: homography warp with bilinear sampling.  Replaces cv2.warpPerspective / cv2.warpAffine with
+ * INTER_LINEAR + WARP_INVERSE_MAP (homography_alignment.py:46-55,120-129): M maps dst -> src,
+ * taps outside the image contribute 0, frame 0 of every burst is copied.  Source coordinates are
+ * evaluated in fp64 (exact to <1e-9 px; no 1/32-px quantisation).  fp32 samples, arbitrary strides so
+ * both the [F,H,W,C] (cv2) and the [B,T,C,H,W] (model input) layouts are served. */
+typedef struct fbanet_warp_params {
+  const float* src;
+  float* dst;
+  const double* M;        /* [frames][9] row-major 3x3                                              */
+  double* coords;         /* optional debug output [frames][H][W][2] = (sx, sy), else NULL          */
+  int64_t s_frame, s_y, s_x, s_c; /* source strides in elements                                     */
+  int64_t d_frame, d_y, d_x, d_c; /* destination strides                                            */
+  int32_t frames;         /* total frames = bursts * frames_per_burst                               */
+  int32_t frames_per_burst;
+  int32_t H, W, C;
+  int32_t _pad;
+} fbanet_warp_params;
+
+/* planar fp32 burst [frames][C][H][W] -> channels-last [frames][H][W][Cp] (zero padded channels) */
+typedef struct fbanet_to_nhwc_params {
+  const float* src;
+  void* dst;
+  int32_t dtype;
+  int32_t frames, C, H, W, Cp;
+} fbanet_to_nhwc_params;
+
+/* K8: LayerNorm over channels, eps, affine (layers/fba_net.py:77-79,196,246). */
+typedef struct fbanet_layernorm_params {
+  const void* x;
+  void* y;
+  const float* gamma;
+  const float* beta;
+  int64_t rows;
+  int32_t C, x_ld, y_ld;
+  int32_t dtype;
+  float eps;
+  int32_t _pad;
+} fbanet_layernorm_params;
+
+/* K6: windowed multi-head self-attention over a token map (layers/fba_net.py:139-250 +
+ * layers/window_attention.py:159-248): cyclic shift, window partition, q*scale, q k^T + relative
+ * position bias (+ shift mask, -100), softmax, P v, window reverse, inverse shift.
+ * qkv is [B*H*W, 3C] = (q | k | v), heads-major inside each; out is [B*H*W, C]. */
+typedef struct fbanet_attn_params {
+  const void* qkv;
+  void* out;
+  const float* bias_table; /* [(2*win-1)^2][heads] fp32                                             */
+  int32_t dtype;
+  int32_t B, H, W, C, heads, win, shift;
+  int32_t qkv_ld, out_ld;
+  float scale;
+  int32_t impl;
+} fbanet_attn_params;
+
+/* K7: LeFF depthwise 3x3 (pad 1) + bias + GELU on a channels-last map
+ * (layers/locally_enhanced_feed_forward.py:39-52). weight packed [9][C] fp32. */
+typedef struct fbanet_dwconv_params {
+  const void* x;
+  void* y;
+  const float* weight;
+  const float* bias;
+  int32_t dtype;
+  int32_t N, H, W, C;
+  int32_t act;
+} fbanet_dwconv_params;
+
+/* K2 (gate): Federated-Affinity gate (blocks/federated_affinity_fusion.py:79-99).
+ * gate[b][f-1][p] = sigmoid(| sum_{tap,c} wsum[tap][c] * (feat[b][f] - feat[b][0])(p+tap, c) |), f >= 1,
+ * where wsum = sum over output channels of temporal_attn1.weight -- algebraically identical to the
+ * reference's  |sum_c(E_f - R) - sum_c(E_0 - R)|  (R and the bias cancel). */
+typedef struct fbanet_faf_gate_params {
+  const void* feat;       /* [B][F][H][W][C] channels-last                                          */
+  float* gate;            /* [B][F-1][H][W] fp32                                                    */
+  const float* wsum;      /* [9][C] fp32                                                            */
+  int32_t dtype;
+  int32_t B, F, H, W, C;
+} fbanet_faf_gate_params;
+
+/* Full-size tiling (utils/dataset_utils.py:5-58,140-180): reflect-pad + overlapping tile gather,
+ * centre-crop stitch.  Planar fp32. */
+typedef struct fbanet_tile_params {
+  const float* src;       /* divide: [T][C][H][W] burst ; merge: [tiles][C][4*(psize+2*ov)]^2 tiles  */
+  float* dst;             /* divide: [tiles][T][C][psize+2ov][psize+2ov] ; merge: [C][4H][4W]        */
+  int32_t T, C, H, W;     /* low-res burst size                                                     */
+  int32_t psize, overlap; /* low-res tile core and halo (80, 40)                                    */
+  int32_t tile_begin, tile_end; /* tile range handled by this call (rank sharding)                  */
+  int32_t scale;          /* 1 for divide, 4 for merge                                              */
+  int32_t _pad;
+} fbanet_tile_params;
+
+int fbanet_abi_version(void);
+/* sizeof() of the named parameter struct as compiled, for binding self-checks; -1 if unknown */
+int fbanet_abi_sizeof(const char* struct_name);
+/* text of the last CUDA error seen by this library on the calling thread */
+const char* fbanet_last_cuda_error(void);
+/* 1 if the tcgen05 implicit-GEMM can run this problem, else 0 */
+int fbanet_conv_gemm_tcgen05_supported(const fbanet_conv_params* p);
+
+int fbanet_warp_sm100(const fbanet_warp_params* p, void* stream);
+int fbanet_to_nhwc_sm100(const fbanet_to_nhwc_params* p, void* stream);
+int fbanet_conv_gemm_sm100(const fbanet_conv_params* p, void* stream);
+int fbanet_layernorm_sm100(const fbanet_layernorm_params* p, void* stream);
+int fbanet_window_attention_sm100(const fbanet_attn_params* p, void* stream);
+int fbanet_dwconv3x3_sm100(const fbanet_dwconv_params* p, void* stream);
+int fbanet_faf_gate_sm100(const fbanet_faf_gate_params* p, void* stream);
+int fbanet_tile_divide_sm100(const fbanet_tile_params* p, void* stream);
+int fbanet_tile_merge_sm100(const fbanet_tile_params* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FBANET_B200_H */

@@ -1,0 +1,44 @@
+"""CPU-side checks of the C-ABI library: it builds, loads, exports every symbol include/fbanet_b200.h
+declares, and the ctypes structs match the compiled layout.  No kernels are launched."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_abi_matches(lib):
+    from fbanet_b200 import _lib
+    assert lib.fbanet_abi_version() == _lib.ABI_VERSION
+    for name, st in _lib.STRUCTS.items():
+        assert lib.fbanet_abi_sizeof(name.encode()) == ctypes.sizeof(st), name
+    assert lib.fbanet_abi_sizeof(b"nope") == -1
+
+
+def test_every_declared_symbol_is_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "fbanet_b200.h")).read()
+    decl = set(re.findall(r"^(?:int|const char\*)\s+(fbanet_\w+)\s*\(", hdr, flags=re.M))
+    from fbanet_b200 import _lib
+    assert decl == set(_lib.OPS) | set(_lib.MISC_SYMBOLS), decl ^ (set(_lib.OPS) | set(_lib.MISC_SYMBOLS))
+    for s in decl:
+        assert hasattr(lib, s), s
+
+
+def test_bad_params_are_rejected_without_a_gpu(lib):
+    from fbanet_b200 import _lib
+    p = _lib.ConvParams()
+    assert lib.fbanet_conv_gemm_sm100(ctypes.byref(p), None) == -1  # null weight/out: bad shape, nothing launched
+    a = _lib.AttnParams()
+    assert lib.fbanet_window_attention_sm100(ctypes.byref(a), None) == -1
+    w = _lib.WarpParams()
+    assert lib.fbanet_warp_sm100(ctypes.byref(w), None) == -1
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from fbanet_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libfbanet_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()

@@ -1,0 +1,128 @@
+"""Whole-model parity of the CUDA BaseModel against the CPU oracle (random init, identical weights).
+
+Bars (BASELINE.json north_star): fp32 max-abs <= 1e-3; bf16 PSNR delta <= 0.01 dB.  The PSNR delta is
+measured against a synthetic ground truth (bilinear x4 of the base frame + fixed noise), i.e.
+|PSNR(bf16 out, gt) - PSNR(oracle out, gt)|; the direct bf16-vs-oracle PSNR is asserted too."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(num_frames=4, img_size=40, in_channels=3, embed_dim=32, window_length=10)
+FULL = dict(num_frames=14, img_size=160, in_channels=3, embed_dim=64, window_length=10)
+RAW = dict(num_frames=14, img_size=80, in_channels=4, embed_dim=64, window_length=10)
+
+
+def _pair(cfg, dtype, cuda, seed=0):
+    from fbanet_b200 import BaseModel
+    from oracle.fbanet_oracle import build_oracle
+    o = build_oracle(seed, **cfg)
+    m = BaseModel(**cfg, token_projection="linear", token_mlp="leff", dtype=dtype)
+    m.load_state_dict(o.state_dict())
+    return o, m.to(cuda).eval()
+
+
+def _burst(cfg, B, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(B, cfg["num_frames"], cfg["in_channels"], cfg["img_size"], cfg["img_size"], generator=g)
+
+
+def _to_oracle_layout(name, t, ref):
+    t = t.float().cpu()
+    if name in ("head", "body"):          # [B,F,H,W,E] -> [B,F,E,H,W]
+        return t.permute(0, 1, 4, 2, 3)
+    if name in ("faf.gate", "out"):
+        return t
+    if ref.dim() == 3:                     # tokens [B,T,C]
+        return t.reshape(t.shape[0], -1, t.shape[-1])
+    return t.permute(0, 3, 1, 2)           # image [B,C,H,W]
+
+
+def test_small_model_every_stage_fp32(cuda):
+    o, m = _pair(SMALL, "fp32", cuda)
+    x = _burst(SMALL, 2)
+    with torch.no_grad():
+        ref = o.forward_stages(x)
+    st = {}
+    m.forward_stages(x.to(cuda), st)
+    worst = {}
+    for k, r in ref.items():
+        if k not in st:
+            continue
+        got = _to_oracle_layout(k, st[k], r)
+        assert got.shape == r.shape, (k, got.shape, r.shape)
+        worst[k] = (got - r).abs().max().item()
+    print(worst)
+    assert len(worst) >= 30
+    bad = {k: v for k, v in worst.items() if v > 2e-4}
+    assert not bad, bad
+
+
+def test_small_model_bf16_close(cuda):
+    from oracle.fbanet_oracle import psnr
+    o, m = _pair(SMALL, "bf16", cuda)
+    x = _burst(SMALL, 2)
+    with torch.no_grad():
+        ref = o(x)
+    got = m(x.to(cuda)).cpu()
+    assert psnr(got, ref) > 40.0, psnr(got, ref)
+
+
+def test_input_shape_assert(cuda):
+    _, m = _pair(SMALL, "fp32", cuda)
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 4, 3, 32, 32, device=cuda))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4, 3, 40, 40))  # CPU tensor: no CPU fallback
+
+
+@pytest.mark.parametrize("cfg", [FULL, RAW], ids=["rgb160", "raw80"])
+def test_full_config_fp32_within_1e3(cuda, cfg):
+    """BASELINE configs[0] / configs[2] shapes, batch 1: max abs error <= 1e-3 in fp32."""
+    o, m = _pair(cfg, "fp32", cuda)
+    x = _burst(cfg, 1)
+    with torch.no_grad():
+        ref = o(x)
+    got = m(x.to(cuda)).cpu()
+    err = (got - ref).abs().max().item()
+    print("max abs err", err)
+    assert got.shape == ref.shape == (1, cfg["in_channels"], 4 * cfg["img_size"], 4 * cfg["img_size"])
+    assert err <= 1e-3, err
+
+
+def test_full_config_bf16_psnr_delta(cuda):
+    from oracle.fbanet_oracle import psnr
+    o, m = _pair(FULL, "bf16", cuda)
+    x = _burst(FULL, 1)
+    with torch.no_grad():
+        ref = o(x)
+    got = m(x.to(cuda)).cpu()
+    g = torch.Generator().manual_seed(7)
+    gt = (torch.nn.functional.interpolate(x[:, 0], scale_factor=4, mode="bilinear", align_corners=False)
+          + 0.05 * torch.randn(ref.shape, generator=g)).clamp(0, 1)
+    delta = abs(psnr(got.clamp(0, 1), gt) - psnr(ref.clamp(0, 1), gt))
+    direct = psnr(got, ref)
+    print("psnr delta", delta, "direct psnr", direct)
+    assert delta <= 0.01, delta
+    assert direct >= 40.0, direct
+
+
+def test_batch_invariance_and_host_api(cuda):
+    """bursts are independent units (jax.vmap(model), train.py:35): batch of 3 == three singles; and the
+    host-buffer entry point returns the same image."""
+    _, m = _pair(SMALL, "fp32", cuda)
+    x = _burst(SMALL, 3, seed=3)
+    full = m(x.to(cuda)).cpu()
+    for i in range(3):
+        one = m(x[i:i + 1].to(cuda)).cpu()
+        assert torch.equal(one, full[i:i + 1])
+    host = m.infer_host(x)
+    assert torch.equal(host, full)
+
+
+def test_fhwc_adaptor(cuda):
+    _, m = _pair(SMALL, "fp32", cuda)
+    x = _burst(SMALL, 1)
+    a = m(x.to(cuda))[0].permute(1, 2, 0)
+    b = m.forward_fhwc(x[0].permute(0, 2, 3, 1).to(cuda))
+    assert torch.equal(a, b)

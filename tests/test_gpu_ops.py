@@ -1,0 +1,304 @@
+"""Per-kernel parity: every C-ABI op against the CPU oracle / torch CPU functional ops on seeded inputs.
+fp32 path: tight tolerances (fp32 re-association only).  bf16 path: inputs/weights rounded to bf16 on both
+sides, tolerance = bf16 output rounding."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def _tol(dt):
+    return (2e-5, 2e-5) if dt == torch.float32 else (2e-2, 2e-2)
+
+
+def _close(got, ref, dt, scale=1.0):
+    atol, rtol = _tol(dt)
+    got, ref = got.float().cpu(), ref.float().cpu()
+    err = (got - ref).abs().max().item()
+    assert torch.allclose(got, ref, atol=atol * scale, rtol=rtol), f"max abs err {err}"
+
+
+def _nhwc(x, dt, dev):  # [N,C,H,W] cpu -> [N,H,W,C] device
+    return x.permute(0, 2, 3, 1).contiguous().to(device=dev, dtype=dt)
+
+
+def _pack(w, dt, dev):
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous().to(device=dev, dtype=dt)
+
+
+def _r(dt, *shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    t = (torch.rand(shape, generator=g) * 2 - 1) * scale
+    return t.to(dt).float() if dt == torch.bfloat16 else t
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("cin,cout,hw,act", [(3, 64, 20, 0), (64, 64, 24, 1), (128, 64, 16, 2), (64, 256, 10, 3), (64, 3, 12, 0)])
+def test_conv3x3(cuda, dt, cin, cout, hw, act):
+    from fbanet_b200 import ops, _lib as L
+    x = _r(dt, 2, cin, hw, hw, seed=1)
+    w = _r(dt, cout, cin, 3, 3, seed=2, scale=1 / math.sqrt(cin * 9))
+    b = _r(torch.float32, cout, seed=3, scale=0.1)
+    res = _r(dt, 2, cout, hw, hw, seed=4)
+    alpha = torch.tensor([0.25])
+    ref = F.conv2d(x, w, b, padding=1)
+    ref = {0: lambda v: v, 1: F.relu, 2: lambda v: F.prelu(v, alpha), 3: lambda v: F.gelu(v, approximate="tanh")}[act](ref) + res
+    cp = cin if cin % 8 == 0 else 8
+    xd = torch.zeros(2, hw, hw, cp, device=cuda, dtype=dt)
+    xd[..., :cin] = _nhwc(x, dt, cuda)
+    wp = torch.zeros(cout, 3, 3, cp)
+    wp[..., :cin] = w.permute(0, 2, 3, 1)
+    out = torch.empty(2, hw, hw, cout, device=cuda, dtype=dt)
+    ops.conv_gemm([xd], wp.reshape(cout, -1).to(cuda, dt), out, kh=3, kw=3, pad=1, bias=b.to(cuda), act=act,
+                  alpha=alpha.to(cuda), residual=_nhwc(res, dt, cuda))
+    _close(out.permute(0, 3, 1, 2), ref, dt)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_conv_multisource_strided_views(cuda, dt):
+    """concat-free inputs: three sources (one a channel slice of a wider buffer), output into a slice."""
+    from fbanet_b200 import ops
+    a, b_, c = _r(dt, 2, 64, 12, 12, seed=1), _r(dt, 2, 32, 12, 12, seed=2), _r(dt, 2, 32, 12, 12, seed=3)
+    w = _r(dt, 64, 128, 3, 3, seed=4, scale=0.03)
+    bias = _r(torch.float32, 64, seed=5)
+    ref = F.conv2d(torch.cat([a, b_, c], 1), w, bias, padding=1)
+    wide = torch.zeros(2, 12, 12, 96, device=cuda, dtype=dt)
+    wide[..., 64:] = _nhwc(c, dt, cuda)
+    outbuf = torch.zeros(2, 12, 12, 128, device=cuda, dtype=dt)
+    ops.conv_gemm([_nhwc(a, dt, cuda), _nhwc(b_, dt, cuda), wide[..., 64:]], _pack(w, dt, cuda), outbuf[..., 64:], kh=3, kw=3, pad=1,
+                  bias=bias.to(cuda))
+    _close(outbuf[..., 64:].permute(0, 3, 1, 2), ref, dt)
+    assert outbuf[..., :64].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_conv4x4_stride2(cuda, dt):
+    from fbanet_b200 import ops
+    x, w, b = _r(dt, 2, 64, 20, 20, seed=1), _r(dt, 128, 64, 4, 4, seed=2, scale=0.03), _r(torch.float32, 128, seed=3)
+    ref = F.conv2d(x, w, b, stride=2, padding=1)
+    out = torch.empty(2, 10, 10, 128, device=cuda, dtype=dt)
+    ops.conv_gemm([_nhwc(x, dt, cuda)], _pack(w, dt, cuda), out, kh=4, kw=4, stride=2, pad=1, bias=b.to(cuda))
+    _close(out.permute(0, 3, 1, 2), ref, dt)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_conv_transpose2x2(cuda, dt):
+    from fbanet_b200 import ops, _lib as L
+    x, w, b = _r(dt, 2, 128, 10, 10, seed=1), _r(dt, 128, 64, 2, 2, seed=2, scale=0.05), _r(torch.float32, 64, seed=3)
+    ref = F.conv_transpose2d(x, w, b, stride=2)
+    wp = w.permute(2, 3, 1, 0).reshape(4 * 64, 128).contiguous().to(cuda, dt)
+    out = torch.empty(2, 20, 20, 64, device=cuda, dtype=dt)
+    ops.conv_gemm([_nhwc(x, dt, cuda)], wp, out, bias=b.repeat(4).to(cuda), store_mode=L.STORE_CONVT2)
+    _close(out.permute(0, 3, 1, 2), ref, dt)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_conv_pixelshuffle_store(cuda, dt):
+    from fbanet_b200 import ops, _lib as L
+    x, w, b = _r(dt, 1, 64, 12, 12, seed=1), _r(dt, 256, 64, 3, 3, seed=2, scale=0.03), _r(torch.float32, 256, seed=3)
+    ref = F.pixel_shuffle(F.conv2d(x, w, b, padding=1), 2)
+    out = torch.empty(1, 24, 24, 64, device=cuda, dtype=dt)
+    ops.conv_gemm([_nhwc(x, dt, cuda)], _pack(w, dt, cuda), out, kh=3, kw=3, pad=1, bias=b.to(cuda), store_mode=L.STORE_PS2)
+    _close(out.permute(0, 3, 1, 2), ref, dt)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_final_conv_with_bilinear_base(cuda, dt):
+    from fbanet_b200 import ops, _lib as L
+    x, w, b = _r(dt, 2, 64, 32, 32, seed=1), _r(dt, 3, 64, 3, 3, seed=2, scale=0.03), _r(torch.float32, 3, seed=3)
+    burst = torch.rand(2, 5, 3, 8, 8, generator=torch.Generator().manual_seed(4))
+    ref = F.conv2d(x, w, b, padding=1) + F.interpolate(burst[:, 0], scale_factor=4, mode="bilinear", align_corners=False)
+    bd = burst.to(cuda)
+    out = torch.empty(2, 3, 32, 32, device=cuda, dtype=torch.float32)
+    ops.conv_gemm([_nhwc(x, dt, cuda)], _pack(w, dt, cuda), out, kh=3, kw=3, pad=1, bias=b.to(cuda), store_mode=L.STORE_NCHW_BASE, base=bd[:, 0])
+    _close(out, ref, dt)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_linear_gelu_residual(cuda, dt):
+    from fbanet_b200 import ops, _lib as L
+    x, w, b = _r(dt, 1, 300, 128, seed=1), _r(dt, 512, 128, seed=2, scale=0.08), _r(torch.float32, 512, seed=3)
+    ref = F.gelu(F.linear(x, w, b), approximate="tanh")
+    out = torch.empty(1, 15, 20, 512, device=cuda, dtype=dt)
+    ops.conv_gemm([x.view(1, 15, 20, 128).to(cuda, dt)], w.to(cuda, dt), out, bias=b.to(cuda), act=L.ACT_GELU_TANH)
+    _close(out.view(1, 300, 512), ref, dt)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_faf_fuse_1x1_with_gate(cuda, dt):
+    """K2: 14-source 1x1 conv with the per-pixel gate applied to frames 1..F-1 (federated_affinity_fusion.py:95-128)."""
+    from fbanet_b200 import ops, _lib as L
+    B, Fr, E, S = 2, 14, 64, 12
+    feat = _r(dt, B, Fr, E, S, S, seed=1)
+    gate = torch.rand(B, Fr - 1, S, S, generator=torch.Generator().manual_seed(2)) * 0.5 + 0.5
+    w, b = _r(dt, E, Fr * E, 1, 1, seed=3, scale=0.03), _r(torch.float32, E, seed=4)
+    g = torch.cat([feat[:, :1], feat[:, 1:] * gate[:, :, None]], 1)
+    ref = F.prelu(F.conv2d(g.reshape(B, Fr * E, S, S), w, b), torch.tensor([0.1]))
+    fd = feat.permute(0, 1, 3, 4, 2).contiguous().to(cuda, dt)
+    gd = gate.to(cuda)
+    out = torch.empty(B, S, S, E, device=cuda, dtype=dt)
+    ops.conv_gemm([fd[:, f] for f in range(Fr)], w.reshape(E, -1).to(cuda, dt), out, bias=b.to(cuda), act=L.ACT_PRELU,
+                  alpha=torch.tensor([0.1], device=cuda), row_scales=[None] + [gd[:, f - 1] for f in range(1, Fr)])
+    _close(out.permute(0, 3, 1, 2), ref, dt, scale=2.0)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_faf_gate_matches_reference_formula(cuda, dt):
+    """gate kernel (collapsed form) vs the reference's as-written affinity maths in float64."""
+    from fbanet_b200 import ops
+    B, Fr, E, S = 2, 6, 64, 14
+    feat = _r(dt, B, Fr, E, S, S, seed=1)
+    w0, b0 = _r(torch.float32, E, E, 3, 3, seed=2, scale=0.04), _r(torch.float32, E, seed=3)
+    w1, b1 = _r(torch.float32, E, E, 3, 3, seed=4, scale=0.04), _r(torch.float32, E, seed=5)
+    fd64 = feat.double()
+    ref_e = F.conv2d(fd64[:, 0], w0.double(), b0.double(), padding=1)
+    emb = F.conv2d(fd64.reshape(B * Fr, E, S, S), w1.double(), b1.double(), padding=1).view(B, Fr, E, S, S)
+    aff = (emb - ref_e[:, None]).sum(2)
+    ref = torch.sigmoid((aff[:, 1:] - aff[:, :1]).abs())
+    wsum = w1.double().sum(0).permute(1, 2, 0).reshape(9, E).float().contiguous().to(cuda)
+    gate = ops.faf_gate(feat.permute(0, 1, 3, 4, 2).contiguous().to(cuda, dt), wsum)
+    assert (gate.cpu().double() - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("C", [64, 128, 256])
+def test_layernorm(cuda, dt, C):
+    from fbanet_b200 import ops
+    x = _r(dt, 1000, C, seed=1, scale=2.0) + 0.3
+    g, b = _r(torch.float32, C, seed=2) + 1.0, _r(torch.float32, C, seed=3)
+    ref = F.layer_norm(x, (C,), g, b, 1e-5)
+    y = ops.layernorm(x.to(cuda, dt), g.to(cuda), b.to(cuda))
+    _close(y, ref, dt, scale=2.0)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_dwconv_gelu(cuda, dt):
+    from fbanet_b200 import ops, _lib as L
+    x, w, b = _r(dt, 2, 256, 14, 10, seed=1), _r(torch.float32, 256, 1, 3, 3, seed=2, scale=0.3), _r(torch.float32, 256, seed=3)
+    ref = F.gelu(F.conv2d(x, w, b, padding=1, groups=256), approximate="tanh")
+    y = ops.dwconv3x3(_nhwc(x, dt, cuda), w.reshape(256, 9).t().contiguous().to(cuda), b.to(cuda), L.ACT_GELU_TANH)
+    _close(y.permute(0, 3, 1, 2), ref, dt)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("C,heads,HW,win,shift", [(64, 1, 20, 10, 0), (64, 1, 20, 10, 5), (128, 2, 30, 10, 5), (256, 16, 20, 10, 5),
+                                                   (128, 8, 20, 10, 0), (64, 4, 5, 5, 0), (128, 8, 8, 4, 2)])
+def test_window_attention(cuda, dt, C, heads, HW, win, shift):
+    """K6 against the oracle's WindowAttention + roll/partition/mask (layers/fba_net.py:139-250)."""
+    from fbanet_b200 import ops
+    from oracle.fbanet_oracle import shift_attn_mask, window_partition, window_reverse, relative_position_index
+    B, H, W = 2, HW, HW
+    N, dh = win * win, C // heads
+    qkv = _r(dt, B, H, W, 3 * C, seed=1, scale=1.5)
+    table = _r(torch.float32, (2 * win - 1) ** 2, heads, seed=2, scale=0.5)
+    scale = dh ** -0.5
+    y = qkv
+    if shift:
+        y = torch.roll(y, (-shift, -shift), (1, 2))
+    yw = window_partition(y, win)  # [B*nW, N, 3C]
+    q, k, v = (yw[..., i * C:(i + 1) * C].view(-1, N, heads, dh).permute(0, 2, 1, 3) for i in range(3))
+    attn = (q * scale) @ k.transpose(-2, -1)
+    bias = table[relative_position_index(win).view(-1)].view(N, N, heads).permute(2, 0, 1)
+    attn = attn + bias[None]
+    if shift:
+        mask = shift_attn_mask(H, W, win, shift)
+        nW = mask.shape[0]
+        attn = (attn.view(B, nW, heads, N, N) + mask[None, :, None]).view(-1, heads, N, N)
+    o = (torch.softmax(attn, -1) @ v).transpose(1, 2).reshape(-1, N, C)
+    o = window_reverse(o, win, B, H, W)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    got = ops.window_attention(qkv.reshape(-1, 3 * C).to(cuda, dt), table.to(cuda), B, H, W, heads, win, shift, scale)
+    _close(got.view(B, H, W, C), o, dt, scale=2.0)
+
+
+def test_to_nhwc(cuda):
+    from fbanet_b200 import ops
+    x = torch.rand(6, 3, 9, 7, generator=torch.Generator().manual_seed(0))
+    for dt, cp in ((torch.float32, 4), (torch.bfloat16, 8)):
+        y = ops.to_nhwc(x.to(cuda), cp, dt).cpu().float()
+        assert torch.equal(y[..., :3], x.permute(0, 2, 3, 1).to(dt).float())
+        assert y[..., 3:].abs().max().item() == 0
+
+
+def _rand_homographies(B, T, seed=1):
+    """H = I + eps; translation U(-4,4), affine U(-.01,.01), perspective U(-1e-5,1e-5)."""
+    g = np.random.default_rng(seed)
+    M = np.tile(np.eye(3), (B, T, 1, 1))
+    M[..., :2, :2] += g.uniform(-0.01, 0.01, (B, T, 2, 2))
+    M[..., :2, 2] += g.uniform(-4, 4, (B, T, 2))
+    M[..., 2, :2] += g.uniform(-1e-5, 1e-5, (B, T, 2))
+    M[:, 0] = np.eye(3)
+    return M
+
+
+@pytest.mark.parametrize("layout", ["BTCHW", "BTHWC"])
+def test_warp_matches_float64_oracle(cuda, layout):
+    """K1: coordinates within 1e-5 px of the float64 closed form, samples to fp32 rounding."""
+    from fbanet_b200 import ops
+    from oracle.fbanet_oracle import warp_frame, warp_coords
+    B, T, Cc, H, W = 2, 5, 4, 40, 56
+    burst = torch.rand(B, T, H, W, Cc, generator=torch.Generator().manual_seed(0))
+    M = _rand_homographies(B, T)
+    src = burst if layout == "BTHWC" else burst.permute(0, 1, 4, 2, 3).contiguous()
+    out, coords = ops.warp_burst(src.to(cuda), torch.from_numpy(M), layout=layout, return_coords=True)
+    out = out.cpu() if layout == "BTHWC" else out.cpu().permute(0, 1, 3, 4, 2)
+    for b in range(B):
+        assert torch.equal(out[b, 0], burst[b, 0])  # base frame untouched
+        for t in range(1, T):
+            sx, sy = warp_coords(M[b, t], H, W)
+            c = coords[b, t].cpu().numpy()
+            assert np.abs(c[..., 0] - sx).max() < 1e-5 and np.abs(c[..., 1] - sy).max() < 1e-5
+            ref = warp_frame(burst[b, t].numpy(), M[b, t])
+            assert np.abs(out[b, t].numpy() - ref).max() < 2e-6
+
+
+def test_warp_large_frame_coordinates(cuda):
+    """fp32 cannot represent 1e-5 px at x ~ 1900; the kernel evaluates coordinates in fp64."""
+    from fbanet_b200 import ops
+    from oracle.fbanet_oracle import warp_coords
+    H, W = 270, 1920
+    burst = torch.rand(1, 2, 1, H, W, generator=torch.Generator().manual_seed(0))
+    M = _rand_homographies(1, 2, seed=3)
+    _, coords = ops.warp_burst(burst.to(cuda), torch.from_numpy(M), return_coords=True)
+    sx, sy = warp_coords(M[0, 1], H, W)
+    c = coords[0, 1].cpu().numpy()
+    assert np.abs(c[..., 0] - sx).max() < 1e-5 and np.abs(c[..., 1] - sy).max() < 1e-5
+
+
+def test_warp_vs_cv2_quantised(cuda):
+    """Secondary pin: cv2.warpPerspective == bilinear with coords rounded to 1/32 px; our exact
+    warp must agree with cv2 to the size of that quantisation on a smooth image."""
+    cv2 = pytest.importorskip("cv2")
+    from fbanet_b200 import ops
+    H, W = 48, 64
+    yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    img = np.stack([np.sin(xx / 9.0) * np.cos(yy / 7.0), xx / W, yy / H], -1).astype(np.float32)
+    M = _rand_homographies(1, 2, seed=5)
+    ref = cv2.warpPerspective(img, M[0, 1], (W, H), flags=cv2.INTER_LINEAR + cv2.WARP_INVERSE_MAP)
+    burst = torch.from_numpy(np.stack([img, img])[None])
+    out = ops.warp_burst(burst.to(cuda), torch.from_numpy(M), layout="BTHWC").cpu().numpy()[0, 1]
+    inner = (slice(6, -6), slice(6, -6))
+    assert np.abs(out[inner] - ref[inner]).max() < 5e-3
+
+
+def test_tile_divide_merge(cuda):
+    """8f-1: GPU reflect-pad tiling + stitch vs the restated utils/dataset_utils.py."""
+    from fbanet_b200 import ops
+    from oracle.fbanet_oracle import tensor_divide_burst, tensor_merge
+    T, Cc, H, W, ps, ov = 3, 3, 50, 70, 20, 10
+    burst = torch.rand(1, T, Cc, H, W, generator=torch.Generator().manual_seed(0))
+    ref = tensor_divide_burst(burst, ps, ov)
+    got = ops.tile_divide(burst[0].to(cuda), ps, ov)
+    assert torch.equal(got.cpu(), ref)
+    sr = torch.rand(ref.shape[0], Cc, 4 * (ps + 2 * ov), 4 * (ps + 2 * ov), generator=torch.Generator().manual_seed(1))
+    refm = tensor_merge(sr, (4 * H, 4 * W), 4 * ps, 4 * ov)
+    out = torch.zeros(Cc, 4 * H, 4 * W, device=cuda)
+    ops.tile_merge(sr.to(cuda), out, H, W, ps, ov, 4)
+    assert torch.equal(out.cpu(), refm[0])
