@@ -44,10 +44,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.index, self.samples, self._halt = index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 r = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                                    capture_output=True, text=True, timeout=5)
@@ -55,10 +55,10 @@ class ClockSampler(threading.Thread):
                     self.samples.append([s.strip() for s in r.stdout.strip().split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
         mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
