@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libfbanet_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -38,6 +38,7 @@ class ConvParams(C.Structure):
         ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
         ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32), ("Cout_store", C.c_int32),
         ("act", C.c_int32), ("store_mode", C.c_int32), ("res_ld", C.c_int32), ("out_ld", C.c_int32),
+        ("src_s2d", C.c_int32), ("_pad", C.c_int32),
     ]
 
 
@@ -54,6 +55,14 @@ class ToNhwcParams(C.Structure):
     _fields_ = [
         ("src", C.c_void_p), ("dst", C.c_void_p), ("dtype", C.c_int32),
         ("frames", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cp", C.c_int32),
+        ("im2col3x3", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
+class S2dParams(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("dst", C.c_void_p), ("img_stride", C.c_int64), ("dtype", C.c_int32),
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("ld", C.c_int32),
     ]
 
 
@@ -81,8 +90,8 @@ class DwconvParams(C.Structure):
 
 class FafGateParams(C.Structure):
     _fields_ = [
-        ("feat", C.c_void_p), ("gate", C.c_void_p), ("wsum", C.c_void_p), ("dtype", C.c_int32),
-        ("B", C.c_int32), ("F", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+        ("feat", C.c_void_p), ("gate", C.c_void_p), ("wsum", C.c_void_p), ("gated", C.c_void_p), ("dtype", C.c_int32),
+        ("B", C.c_int32), ("F", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("_pad", C.c_int32),
     ]
 
 
@@ -97,13 +106,13 @@ class TileParams(C.Structure):
 
 STRUCTS = {
     "fbanet_src": Src, "fbanet_conv_params": ConvParams, "fbanet_warp_params": WarpParams,
-    "fbanet_to_nhwc_params": ToNhwcParams, "fbanet_layernorm_params": LayerNormParams, "fbanet_attn_params": AttnParams,
+    "fbanet_to_nhwc_params": ToNhwcParams, "fbanet_s2d_params": S2dParams, "fbanet_layernorm_params": LayerNormParams, "fbanet_attn_params": AttnParams,
     "fbanet_dwconv_params": DwconvParams, "fbanet_faf_gate_params": FafGateParams, "fbanet_tile_params": TileParams,
 }
 
 # every symbol include/fbanet_b200.h declares
 OPS = {
-    "fbanet_warp_sm100": WarpParams, "fbanet_to_nhwc_sm100": ToNhwcParams, "fbanet_conv_gemm_sm100": ConvParams,
+    "fbanet_warp_sm100": WarpParams, "fbanet_to_nhwc_sm100": ToNhwcParams, "fbanet_space_to_depth_sm100": S2dParams, "fbanet_conv_gemm_sm100": ConvParams,
     "fbanet_layernorm_sm100": LayerNormParams, "fbanet_window_attention_sm100": AttnParams, "fbanet_dwconv3x3_sm100": DwconvParams,
     "fbanet_faf_gate_sm100": FafGateParams, "fbanet_tile_divide_sm100": TileParams, "fbanet_tile_merge_sm100": TileParams,
 }

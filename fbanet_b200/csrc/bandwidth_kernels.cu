@@ -63,7 +63,40 @@ __global__ void __launch_bounds__(256) to_nhwc_kernel(const fbanet_to_nhwc_param
     const int64_t f = idx / hw, pix = idx % hw;
     const float* s = p.src + f * p.C * hw + pix;
     T* d = dst + idx * p.Cp;
-    for (int c = 0; c < p.Cp; ++c) d[c] = from_f32<T>(c < p.C ? __ldg(s + (int64_t)c * hw) : 0.f);
+    if (!p.im2col3x3) {
+      for (int c = 0; c < p.Cp; ++c) d[c] = from_f32<T>(c < p.C ? __ldg(s + (int64_t)c * hw) : 0.f);
+    } else {
+      const int y = (int)(pix / p.W), x = (int)(pix % p.W);
+      for (int c = 0; c < p.Cp; ++c) {
+        float v = 0.f;
+        if (c < 9 * p.C) {
+          const int tap = c / p.C, ch = c - tap * p.C;
+          const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+          if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) v = __ldg(p.src + (f * p.C + ch) * hw + (int64_t)yy * p.W + xx);
+        }
+        d[c] = from_f32<T>(v);
+      }
+    }
+  }
+}
+
+// channels-last view -> space-to-depth(2), one thread per 16-byte vector of the destination
+template <typename T>
+__global__ void __launch_bounds__(256) s2d_kernel(const fbanet_s2d_params p) {
+  constexpr int V = Vec16<T>::N;
+  const int cg = p.C / V, Ho = p.H / 2, Wo = p.W / 2;
+  const int64_t total = (int64_t)p.N * Ho * Wo * 4 * cg;
+  const T* src = reinterpret_cast<const T*>(p.src);
+  T* dst = reinterpret_cast<T*>(p.dst);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(idx % cg) * V;
+    int64_t r = idx / cg;
+    const int sub = (int)(r % 4); r /= 4;
+    const int x = (int)(r % Wo); r /= Wo;
+    const int y = (int)(r % Ho);
+    const int64_t n = r / Ho;
+    const T* s = src + n * p.img_stride + ((int64_t)(2 * y + (sub >> 1)) * p.W + (2 * x + (sub & 1))) * p.ld + c0;
+    *reinterpret_cast<uint4*>(dst + idx * V) = *reinterpret_cast<const uint4*>(s);
   }
 }
 
@@ -183,7 +216,20 @@ __global__ void __launch_bounds__(256) faf_gate_kernel(const fbanet_faf_gate_par
       for (int i = 0; i < PER; ++i) acc = fmaf(wt[t][i], to_f32<T>(q[i]) - ref[t][i], acc);
     }
     acc = warp_sum(acc);
-    if (lane == 0) p.gate[(b * (p.F - 1) + (f - 1)) * hw + pix] = 1.0f / (1.0f + expf(-fabsf(acc)));
+    const float g = 1.0f / (1.0f + expf(-fabsf(acc)));
+    if (lane == 0 && p.gate) p.gate[(b * (p.F - 1) + (f - 1)) * hw + pix] = g;
+    if (p.gated) {  // centre tap of frame f, scaled (federated_affinity_fusion.py:102-105); pixel-major [B][H][W][F][C]
+      const T* q = feat + ((b * p.F + f) * hw + pix) * C + lane * PER;
+      T* o = reinterpret_cast<T*>(p.gated) + (((b * hw + pix) * p.F) + f) * C + lane * PER;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) o[i] = from_f32<T>(to_f32<T>(q[i]) * g);
+    }
+  }
+  if (p.gated) {  // frame 0 is passed through unscaled (:103)
+    const T* q = feat + ((b * p.F) * hw + pix) * C + lane * PER;
+    T* o = reinterpret_cast<T*>(p.gated) + ((b * hw + pix) * p.F) * C + lane * PER;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) o[i] = q[i];
   }
 }
 
@@ -262,6 +308,18 @@ extern "C" int fbanet_to_nhwc_sm100(const fbanet_to_nhwc_params* p, void* stream
   return check_launch();
 }
 
+extern "C" int fbanet_space_to_depth_sm100(const fbanet_s2d_params* p, void* stream) {
+  if (!p || !p->src || !p->dst || p->N <= 0 || (p->H % 2) || (p->W % 2)) return FBANET_E_BADSHAPE;
+  const int v = p->dtype == FBANET_F32 ? 4 : 8;
+  if (p->C % v) return FBANET_E_BADSHAPE;
+  if ((p->ld % v) || (p->img_stride % v) || ((uintptr_t)p->src % 16) || ((uintptr_t)p->dst % 16)) return FBANET_E_ALIGN;
+  const int64_t total = (int64_t)p->N * (p->H / 2) * (p->W / 2) * 4 * (p->C / v);
+  if (p->dtype == FBANET_F32) s2d_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  else if (p->dtype == FBANET_BF16) s2d_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  else return FBANET_E_DTYPE;
+  return check_launch();
+}
+
 template <typename T>
 static int launch_ln(const fbanet_layernorm_params* p, cudaStream_t s) {
   const int blocks = ceil_div(p->rows, 8);
@@ -310,7 +368,7 @@ static int launch_gate(const fbanet_faf_gate_params* p, cudaStream_t s) {
 }
 
 extern "C" int fbanet_faf_gate_sm100(const fbanet_faf_gate_params* p, void* stream) {
-  if (!p || !p->feat || !p->gate || !p->wsum || p->B <= 0 || p->F < 2) return FBANET_E_BADSHAPE;
+  if (!p || !p->feat || (!p->gate && !p->gated) || !p->wsum || p->B <= 0 || p->F < 2) return FBANET_E_BADSHAPE;
   if (p->dtype == FBANET_F32) return launch_gate<float>(p, (cudaStream_t)stream);
   if (p->dtype == FBANET_BF16) return launch_gate<bf16>(p, (cudaStream_t)stream);
   return FBANET_E_DTYPE;

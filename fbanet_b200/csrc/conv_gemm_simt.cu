@@ -182,6 +182,7 @@ int conv_gemm_validate(const fbanet_conv_params* p) {
   if (p->N <= 0 || p->H <= 0 || p->W <= 0 || p->Ho <= 0 || p->Wo <= 0 || p->Cout <= 0 || p->KH <= 0 || p->KW <= 0 || p->stride <= 0)
     return FBANET_E_BADSHAPE;
   if (p->Cout_store <= 0 || p->Cout_store > p->Cout) return FBANET_E_BADSHAPE;
+  if (p->src_s2d && (p->KH != 4 || p->KW != 4 || p->stride != 2 || p->pad != 1 || (p->H % 2) || (p->W % 2))) return FBANET_E_BADSHAPE;
   if ((p->H + 2 * p->pad - p->KH) / p->stride + 1 != p->Ho || (p->W + 2 * p->pad - p->KW) / p->stride + 1 != p->Wo) return FBANET_E_BADSHAPE;
   for (int s = 0; s < p->nsrc; ++s)
     if (!p->src[s].ptr || p->src[s].C <= 0 || p->src[s].ld < p->src[s].C) return FBANET_E_BADSHAPE;

@@ -1,6 +1,528 @@
-// placeholder until the tcgen05 implicit-GEMM lands; reports "unsupported".
+// K3/K4/K5/K9 on the 5th-gen tensor cores: implicit-GEMM convolution / linear layer, bf16 x bf16 -> fp32.
+//
+//   out[pixel, co] = act( sum_{step} A_step[pixel, 0:64] . B_step[co, 0:64] + bias[co] ) + residual
+//
+// One K-step = one (tap, source, 64-channel chunk).  The A tile of a step is a TMA box
+// {64 channels, tw, th, 1 image} of the channels-last source shifted by the tap offset (dx, dy): TMA
+// zero-fills the out-of-image part, so there is no im2col buffer and no halo code, and the box lands in
+// shared memory already in the canonical K-major SWIZZLE_128B layout tcgen05.mma reads.  The B tile is a
+// {64, BN} box of the packed weights [Cout][K].  Accumulators live in TMEM (2 x BN fp32 columns, double
+// buffered) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Warp roles (256 threads, persistent, 1 CTA/SM): warp 0 = TMA producer (one lane), warp 1 = MMA issuer
+// (one lane), warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> bias/act/residual ->
+// bf16 -> 16-byte global stores, each thread owns one pixel row).
+#include <cuda.h>
+#include <string.h>
+
 #include "common.cuh"
+
 namespace fbanet {
-int conv_gemm_tc_supported(const fbanet_conv_params*) { return 0; }
-int conv_gemm_tc_launch(const fbanet_conv_params*, cudaStream_t) { return FBANET_E_UNSUPPORTED; }
+
+constexpr int TC_MAX_STEPS = 160;
+constexpr int TC_MAX_SRC = 4;
+constexpr int TC_BK = 64;            // channels per K-step (128 bytes of bf16 = one swizzle row)
+constexpr int TC_A_BYTES = 128 * TC_BK * 2;
+
+struct KStep { int16_t src, c0, dx, dy; };
+
+struct TcParams {
+  CUtensorMap amap[TC_MAX_SRC];
+  CUtensorMap bmap;
+  KStep steps[TC_MAX_STEPS];
+  const float* bias;
+  const float* alpha;
+  const bf16* residual;
+  void* out;
+  const float* base;
+  int64_t res_img_stride, out_img_stride, base_img_stride;
+  int nsteps;
+  int N, Ho, Wo;          // tile space == output pixels
+  int tw, th, tiles_x, tiles_y;
+  int BN, n_tiles_n, Cout, Cout_store;
+  int act, store_mode, res_ld, out_ld;
+  int stages, a_box_bytes;
+  int total_tiles;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row atoms of 1024 bytes)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset = 1024 B between 8-row atoms
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 128
+__device__ __forceinline__ uint32_t make_idesc_bf16(int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;                    // c_format = F32
+  d |= 1u << 7;                    // a_format = BF16
+  d |= 1u << 10;                   // b_format = BF16
+  d |= (uint32_t)(N >> 3) << 17;   // n_dim
+  d |= (uint32_t)(128 >> 4) << 24; // m_dim
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, "
+      "%27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+// bias + activation + residual + store of 32 (or 16) accumulator columns of one pixel row
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t (&v)[32], const int nc, const int col0, const int img,
+                                               const int y, const int x, const float alpha) {
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = (j < nc) ? __uint_as_float(v[j]) : 0.f;
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < nc) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+      }
+    }
+  }
+  if (p.act != FBANET_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act, alpha);
+  }
+  if (p.store_mode == FBANET_STORE_NCHW_BASE) {
+    // final conv: fp32 planar out + bilinear x4 (align_corners=False) of the low-res base frame
+    const int Hb = p.Ho >> 2, Wb = p.Wo >> 2;
+    float sy = 0.25f * (y + 0.5f) - 0.5f, sx = 0.25f * (x + 0.5f) - 0.5f;
+    sy = sy < 0.f ? 0.f : sy;
+    sx = sx < 0.f ? 0.f : sx;
+    const int yb = (int)sy, xb = (int)sx;
+    const int y1 = yb + (yb < Hb - 1 ? 1 : 0), x1 = xb + (xb < Wb - 1 ? 1 : 0);
+    const float wy = sy - yb, wx = sx - xb, hy = 1.f - wy, hx = 1.f - wx;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int col = col0 + j;
+      if (col < p.Cout_store) {
+        const float* bp = p.base + img * p.base_img_stride + (int64_t)col * Hb * Wb;
+        const float bl = hy * (hx * __ldg(bp + yb * Wb + xb) + wx * __ldg(bp + yb * Wb + x1)) +
+                         wy * (hx * __ldg(bp + y1 * Wb + xb) + wx * __ldg(bp + y1 * Wb + x1));
+        reinterpret_cast<float*>(p.out)[img * p.out_img_stride + ((int64_t)col * p.Ho + y) * p.Wo + x] = f[j] + bl;
+      }
+    }
+    return;
+  }
+  int64_t opix;
+  int ocol;
+  if (p.store_mode == FBANET_STORE_NHWC) {
+    opix = (int64_t)y * p.Wo + x;
+    ocol = col0;
+    if (p.residual) {
+      const bf16* rp = p.residual + img * p.res_img_stride + opix * p.res_ld + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        if (j < nc) {
+          float t[8];
+          load_vec<bf16, 8>(rp + j, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[j + e] += t[e];
+        }
+      }
+    }
+  } else {  // FBANET_STORE_CONVT2: col = (2i+j)*Co + co
+    const int Co = p.Cout >> 2;
+    const int qq = col0 / Co;
+    ocol = col0 - qq * Co;
+    opix = (int64_t)(2 * y + (qq >> 1)) * (2 * p.Wo) + (2 * x + (qq & 1));
+  }
+  bf16* op = reinterpret_cast<bf16*>(p.out) + img * p.out_img_stride + opix * p.out_ld + ocol;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    if (j < nc && col0 + j < p.Cout_store) {
+      float t[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t[e] = f[j + e];
+      store_vec<bf16, 8>(op + j, t);
+    }
+  }
+}
+
+constexpr int TC_MAX_STAGES = 8;
+
+__global__ void __launch_bounds__(256, 1) conv_gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the 128B swizzle needs
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = p.BN, stages = p.stages;
+  const uint32_t b_bytes = (uint32_t)BN * TC_BK * 2;
+  const uint32_t stage_bytes = TC_A_BYTES + b_bytes;   // multiple of 1024
+  const uint32_t tmem_cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < TC_MAX_SRC; ++s) tma_prefetch_desc(&p.amap[s]);
+    tma_prefetch_desc(&p.bmap);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
+        const int img = mt / tiles_per_img, r = mt % tiles_per_img;
+        const int y0 = (r / p.tiles_x) * p.th, x0 = (r % p.tiles_x) * p.tw;
+        for (int s = 0; s < p.nsteps; ++s) {
+          const KStep ks = p.steps[s];
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)p.a_box_bytes + b_bytes);
+          tma_load_4d(sa, &p.amap[ks.src], &full_bar[stage], ks.c0, x0 + ks.dx, y0 + ks.dy, img);
+          tma_load_2d(sa + TC_A_BYTES, &p.bmap, &full_bar[stage], s * TC_BK, nt * BN);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int s = 0; s < p.nsteps; ++s) {
+          mbar_wait(&full_bar[stage], phase);          // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)           // advance 32 bytes (16 bf16) inside the swizzle row
+            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((s | k) != 0));
+          umma_commit(&empty_bar[stage]);              // frees the smem slot when these MMAs retire
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);                  // accumulator ready for the epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int q = warp & 3;                            // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int ly = row / p.tw, lx = row - ly * p.tw;
+    const float alpha = (p.act == FBANET_ACT_PRELU) ? __ldg(p.alpha) : 0.f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
+      const int img = mt / tiles_per_img, r = mt % tiles_per_img;
+      const int y = (r / p.tiles_x) * p.th + ly, x = (r % p.tiles_x) * p.tw + lx;
+      const bool valid = (ly < p.th) && (y < p.Ho) && (x < p.Wo);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        const int nc = (BN - c0 >= 32) ? 32 : 16;
+        if (nc == 32) tmem_ld32(taddr0 + c0, v); else tmem_ld16(taddr0 + c0, v);
+        tmem_ld_wait();
+        if (valid) epilogue_chunk(p, v, nc, nt * BN + c0, img, y, x, alpha);
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+static int pick_bn(int cout) {
+  if (cout <= 256) return cout;
+  for (int bn = 256; bn >= 64; bn -= 32)
+    if (cout % bn == 0) return bn;
+  return 0;
+}
+
+static void pick_tile(int H, int W, int* tw_out, int* th_out) {
+  const int cands[] = {8, 16, 32, 64, 128};
+  int64_t best = -1;
+  auto consider = [&](int tw) {
+    if (tw < 1 || tw > 128) return;
+    int th = 128 / tw;
+    if (th > 256) return;
+    const int64_t cost = (int64_t)((W + tw - 1) / tw) * ((H + th - 1) / th);  // #tiles, each costs a full 128-row MMA
+    if (best < 0 || cost < best) { best = cost; *tw_out = tw; *th_out = th; }
+  };
+  for (int c : cands) consider(c);
+  if (W <= 128) consider(W);
+}
+
+// conv kinds the tensor-core path takes
+static bool tc_shape_ok(const fbanet_conv_params* p) {
+  if (p->dtype != FBANET_BF16) return false;
+  if (p->nsrc > TC_MAX_SRC) return false;
+  if (p->store_mode == FBANET_STORE_PS2) return false;
+  const bool s1 = p->stride == 1 && p->KH == p->KW && (p->KH == 1 || p->KH == 3) && p->pad == p->KH / 2;
+  const bool s2d = p->src_s2d && p->stride == 2 && p->KH == 4 && p->KW == 4 && p->pad == 1;
+  if (!s1 && !s2d) return false;
+  if (p->src_s2d && !s2d) return false;
+  int ctot = 0;
+  for (int s = 0; s < p->nsrc; ++s) {
+    const fbanet_src& S = p->src[s];
+    if (S.row_scale) return false;
+    const int cc = s2d ? S.C / 4 : S.C;
+    if (cc % TC_BK || (s2d && S.C % 4)) return false;
+    if ((S.ld % 8) || (S.img_stride % 8) || ((uintptr_t)S.ptr % 16)) return false;
+    ctot += cc;
+  }
+  const int taps = p->KH * p->KW;
+  if (taps * (ctot / TC_BK) > TC_MAX_STEPS) return false;
+  const int bn = pick_bn(p->Cout);
+  if (bn == 0 || (bn % 16) || bn < 16) return false;
+  if (bn % 32 && bn != 16) return false;
+  if ((uintptr_t)p->weight % 16) return false;
+  if (p->store_mode == FBANET_STORE_NHWC || p->store_mode == FBANET_STORE_CONVT2) {
+    if ((p->out_ld % 8) || (p->out_img_stride % 8) || ((uintptr_t)p->out % 16)) return false;
+    if (p->Cout_store % 8) return false;
+    if (p->store_mode == FBANET_STORE_CONVT2 && ((p->Cout / 4) % 32)) return false;
+    if (p->residual && ((p->res_ld % 8) || (p->res_img_stride % 8) || ((uintptr_t)p->residual % 16))) return false;
+  } else if (p->store_mode == FBANET_STORE_NCHW_BASE) {
+    if (bn != 16 || p->Cout_store > 16) return false;
+  }
+  if (p->bias && ((uintptr_t)p->bias % 16)) return false;
+  return get_encode() != nullptr;
+}
+
+int conv_gemm_tc_supported(const fbanet_conv_params* p) { return tc_shape_ok(p) ? 1 : 0; }
+
+int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
+  if (!tc_shape_ok(p)) return FBANET_E_UNSUPPORTED;
+  EncodeTiledFn encode = get_encode();
+  static thread_local TcParams tp;  // ~2.3 KB; filled per call, passed by value
+  memset(&tp, 0, sizeof(tp));
+  const bool s2d = p->src_s2d != 0;
+  // tile space = output pixels; for s2d sources the source view already has the output resolution
+  const int Hs = s2d ? p->H / 2 : p->H, Ws = s2d ? p->W / 2 : p->W;
+  if (Hs != p->Ho || Ws != p->Wo) return FBANET_E_BADSHAPE;
+  int tw = 16, th = 8;
+  pick_tile(p->Ho, p->Wo, &tw, &th);
+  tp.tw = tw; tp.th = th;
+  tp.tiles_x = (p->Wo + tw - 1) / tw;
+  tp.tiles_y = (p->Ho + th - 1) / th;
+  tp.N = p->N; tp.Ho = p->Ho; tp.Wo = p->Wo;
+  tp.BN = pick_bn(p->Cout);
+  tp.n_tiles_n = p->Cout / tp.BN;
+  tp.Cout = p->Cout; tp.Cout_store = p->Cout_store;
+  tp.a_box_bytes = tw * th * TC_BK * 2;
+  tp.total_tiles = p->N * tp.tiles_x * tp.tiles_y * tp.n_tiles_n;
+
+  int ctot = 0;
+  for (int s = 0; s < p->nsrc; ++s) {
+    const fbanet_src& S = p->src[s];
+    const cuuint64_t dims[4] = {(cuuint64_t)S.C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)p->N};
+    const cuuint64_t strides[3] = {(cuuint64_t)S.ld * 2, (cuuint64_t)S.ld * 2 * Ws, (cuuint64_t)S.img_stride * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)tw, (cuuint32_t)th, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tp.amap[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(S.ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return FBANET_E_BADSHAPE;
+    ctot += s2d ? S.C / 4 : S.C;
+  }
+  for (int s = p->nsrc; s < TC_MAX_SRC; ++s) tp.amap[s] = tp.amap[0];
+  const int taps = p->KH * p->KW;
+  const int K = taps * ctot;
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)p->Cout};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)tp.BN};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tp.bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p->weight), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return FBANET_E_BADSHAPE;
+  }
+  // K-step table in weight order: k = (tap * Ctot + concat channel)
+  int ns = 0;
+  for (int tap = 0; tap < taps; ++tap) {
+    const int ky = tap / p->KW, kx = tap % p->KW;
+    for (int s = 0; s < p->nsrc; ++s) {
+      const int cc = s2d ? p->src[s].C / 4 : p->src[s].C;
+      for (int c0 = 0; c0 < cc; c0 += TC_BK) {
+        KStep& st = tp.steps[ns++];
+        st.src = (int16_t)s;
+        if (s2d) {
+          // input row 2y-1+ky = 2*(y+dy) + ys ; s2d channel block (ys*2+xs)*cc
+          const int ry = ky - 1, rx = kx - 1;
+          const int ys = ry & 1, xs = rx & 1;
+          st.dy = (int16_t)((ry - ys) / 2);
+          st.dx = (int16_t)((rx - xs) / 2);
+          st.c0 = (int16_t)((ys * 2 + xs) * cc + c0);
+        } else {
+          st.dy = (int16_t)(ky - p->pad);
+          st.dx = (int16_t)(kx - p->pad);
+          st.c0 = (int16_t)c0;
+        }
+      }
+    }
+  }
+  tp.nsteps = ns;
+  tp.bias = p->bias; tp.alpha = p->alpha; tp.residual = reinterpret_cast<const bf16*>(p->residual);
+  tp.out = p->out; tp.base = p->base;
+  tp.res_img_stride = p->res_img_stride; tp.out_img_stride = p->out_img_stride; tp.base_img_stride = p->base_img_stride;
+  tp.act = p->act; tp.store_mode = p->store_mode; tp.res_ld = p->res_ld; tp.out_ld = p->out_ld;
+
+  const int stage_bytes = TC_A_BYTES + tp.BN * TC_BK * 2;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages > ns * 2) stages = ns * 2 < 2 ? 2 : ns * 2;
+  tp.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_last_error(e); return FBANET_E_LAUNCH; }
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = tp.total_tiles < sms ? tp.total_tiles : sms;
+  conv_gemm_tcgen05_kernel<<<grid, 256, smem, stream>>>(tp);
+  return check_launch();
+}
+
 }  // namespace fbanet

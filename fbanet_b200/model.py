@@ -232,6 +232,7 @@ class BaseModel(nn.Module):
     def _pack(self) -> Dict[str, torch.Tensor]:
         T = self.compute_dtype
         P: Dict[str, torch.Tensor] = {}
+        tc = self._use_tc()
         cin_pad = 4 if T == torch.float32 else 8  # head input channels padded to a 16-byte pixel
 
         def conv_w(w, pad_cin=None):  # [Co,Ci,kh,kw] -> [Co, kh*kw*Ci]
@@ -256,7 +257,12 @@ class BaseModel(nn.Module):
             P[name + ".w"] = m.weight.detach().to(T).contiguous()
             P[name + ".b"] = f32(m.bias)
 
-        put_conv("head", self.head, cin_pad)
+        if tc:  # head conv as a K=64 1x1 GEMM over the im2col'd burst (ops.to_nhwc(im2col3x3=True))
+            w = self.head.weight.detach().float().permute(0, 2, 3, 1).reshape(self.embed_dim, -1)
+            P["head.w"] = torch.nn.functional.pad(w, (0, 64 - w.shape[1])).to(T).contiguous()
+            P["head.b"] = f32(self.head.bias)
+        else:
+            put_conv("head", self.head, cin_pad)
         for i, rb in enumerate(self.body):
             put_conv(f"body.{i}.0", rb.body[0])
             put_conv(f"body.{i}.2", rb.body[2])
@@ -299,10 +305,22 @@ class BaseModel(nn.Module):
             put_conv(f"{hg}_downsample_1", getattr(self, f"{hg}_downsample_1").conv[0])
             put_convT(f"{hg}_upsample_0", getattr(self, f"{hg}_upsample_0").deconv[0])
             put_convT(f"{hg}_upsample_1", getattr(self, f"{hg}_upsample_1").deconv[0])
-        put_conv("tail.0.0", self.tail[0][0])
-        put_conv("tail.0.2", self.tail[0][2])
+        # PixelShuffle(2) folded into the store: rows re-ordered from co = 4c+2i+j to (2i+j)*E + c so the
+        # tile is written with the ConvTranspose-style 2x2 scatter (contiguous channel runs per sub-pixel)
+        E = self.embed_dim
+        for n, m in (("tail.0.0", self.tail[0][0]), ("tail.0.2", self.tail[0][2])):
+            w = conv_w(m.weight)
+            P[n + ".w"] = w.view(E, 4, -1).permute(1, 0, 2).reshape(4 * E, -1).contiguous()
+            P[n + ".b"] = f32(m.bias).view(E, 4).t().reshape(-1).contiguous()
         put_conv("tail.1", self.tail[1])
+        if tc:  # final conv: GEMM N padded to the tensor-core minimum of 16 columns (zero rows)
+            P["tail.1.w"] = torch.nn.functional.pad(P["tail.1.w"], (0, 0, 0, 16 - self.in_channels)).contiguous()
+            P["tail.1.b"] = torch.nn.functional.pad(P["tail.1.b"], (0, 16 - self.in_channels)).contiguous()
         return P
+
+    def _use_tc(self) -> bool:
+        """bf16 + 64-channel granularity -> every dense contraction runs on the tcgen05 kernel."""
+        return self.compute_dtype == torch.bfloat16 and self.impl != L.IMPL_SIMT and self.embed_dim % 64 == 0
 
     # -- building blocks ---------------------------------------------------------------------------
     def _new(self, *shape):
@@ -326,6 +344,9 @@ class BaseModel(nn.Module):
         w = P[name + ".w"]
         if out is None:
             out = self._new(N, H // 2, W // 2, w.shape[0])
+        if self._use_tc():  # TMA cannot stride: feed the 4x4 s2 conv a space-to-depth view
+            return ops.conv_gemm([ops.space_to_depth(x)], w, out, kh=4, kw=4, stride=2, pad=1, bias=P[name + ".b"], impl=self.impl,
+                                 src_s2d=True)
         return ops.conv_gemm([x], w, out, kh=4, kw=4, stride=2, pad=1, bias=P[name + ".b"], impl=self.impl)
 
     def _up(self, P, name, x, out):
@@ -360,11 +381,17 @@ class BaseModel(nn.Module):
     def _faf(self, P, feat):
         """FAFBlock (blocks/federated_affinity_fusion.py:166-182). feat ``[B,F,H,W,E]``."""
         B, Fr, H, W, E = feat.shape
-        gate = ops.faf_gate(feat, P["fusion.wsum"])  # :79-99 collapsed, see _pack
-        srcs = [feat[:, f] for f in range(Fr)]
-        scales = [None] + [gate[:, f - 1] for f in range(1, Fr)]
-        z = ops.conv_gemm(srcs, P["fusion.fuse.w"], self._new(B, H, W, E), bias=P["fusion.fuse.b"], act=L.ACT_PRELU,
-                          alpha=P["fusion.fuse.alpha"], row_scales=scales, impl=self.impl)  # :121-128
+        if self._use_tc():
+            # gate kernel also emits the gated features pixel-major [B,H,W,F*E] = the K axis of the 1x1 fusion GEMM
+            gate, gated = ops.faf_gate(feat, P["fusion.wsum"], want_gate=True, want_gated=True)
+            z = ops.conv_gemm([gated], P["fusion.fuse.w"], self._new(B, H, W, E), bias=P["fusion.fuse.b"], act=L.ACT_PRELU,
+                              alpha=P["fusion.fuse.alpha"], impl=self.impl)
+        else:
+            gate = ops.faf_gate(feat, P["fusion.wsum"])  # :79-99 collapsed, see _pack
+            srcs = [feat[:, f] for f in range(Fr)]
+            scales = [None] + [gate[:, f - 1] for f in range(1, Fr)]
+            z = ops.conv_gemm(srcs, P["fusion.fuse.w"], self._new(B, H, W, E), bias=P["fusion.fuse.b"], act=L.ACT_PRELU,
+                              alpha=P["fusion.fuse.alpha"], row_scales=scales, impl=self.impl)  # :121-128
         cat4 = self._new(B, H, W, 2 * E)            # [up1 | r0]
         cat3 = self._new(B, H // 2, W // 2, 4 * E)  # [up0 | r1]
         r0 = cat4[..., E:]
@@ -436,8 +463,12 @@ class BaseModel(nn.Module):
         B, Fr, Cin, S, _ = x.shape
         E, T = self.embed_dim, self.compute_dtype
         cin_pad = 4 if T == torch.float32 else 8
-        xn = ops.to_nhwc(x.view(B * Fr, Cin, S, S), cin_pad, T)
-        f = self._conv3(P, "head", [xn], alg_cin=Cin)                            # :255
+        if self._use_tc():
+            xn = ops.to_nhwc(x.view(B * Fr, Cin, S, S), 64, T, im2col3x3=True)
+            f = ops.conv_gemm([xn], P["head.w"], self._new(B * Fr, S, S, E), bias=P["head.b"], impl=self.impl, alg_cin=9 * Cin)  # :255
+        else:
+            xn = ops.to_nhwc(x.view(B * Fr, Cin, S, S), cin_pad, T)
+            f = self._conv3(P, "head", [xn], alg_cin=Cin)                        # :255
         if st is not None:
             st["head"] = f.view(B, Fr, S, S, E)
         f = self._resblock(P, "body.0", f)                                        # :258
@@ -451,8 +482,8 @@ class BaseModel(nn.Module):
         y1 = self._conv3(P, "output_proj", [d1], act=L.ACT_PRELU, alpha=P["output_proj.alpha"])  # :290
         d1_2, _ = self._hourglass(P, "HG2", y1, prev, st)                         # :294-310
         y2 = self._conv3(P, "output_proj_2", [d1_2], act=L.ACT_PRELU, alpha=P["output_proj_2.alpha"])  # :313
-        t1 = self._conv3(P, "tail.0.0", [y2], out=self._new(B, 2 * S, 2 * S, E), store=L.STORE_PS2)  # :315
-        t2 = self._conv3(P, "tail.0.2", [t1], out=self._new(B, 4 * S, 4 * S, E), store=L.STORE_PS2)
+        t1 = self._conv3(P, "tail.0.0", [y2], out=self._new(B, 2 * S, 2 * S, E), store=L.STORE_CONVT2)  # :315 (PixelShuffle in the store)
+        t2 = self._conv3(P, "tail.0.2", [t1], out=self._new(B, 4 * S, 4 * S, E), store=L.STORE_CONVT2)
         out = torch.empty((B, Cin, 4 * S, 4 * S), device=x.device, dtype=torch.float32)
         self._conv3(P, "tail.1", [t2], out=out, store=L.STORE_NCHW_BASE, base=x[:, 0], cout_store=Cin)  # :315-320 (+ bilinear x4 base)
         if st is not None:

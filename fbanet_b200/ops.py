@@ -63,6 +63,7 @@ def conv_gemm(
     cout_store: Optional[int] = None,
     impl: int = L.IMPL_AUTO,
     alg_cin: Optional[int] = None,
+    src_s2d: bool = False,
 ) -> torch.Tensor:
     """out = act(conv(concat(srcs)) + bias) + residual.  ``weight`` is packed ``[Cout, kh*kw*sum(C)]``."""
     p = L.ConvParams()
@@ -72,6 +73,7 @@ def conv_gemm(
     p.nsrc = len(srcs)
     assert 1 <= len(srcs) <= L.MAX_SRC
     N, H, W, _ = srcs[0].shape
+    p.src_s2d = 1 if src_s2d else 0
     ctot = 0
     for i, s in enumerate(srcs):
         assert s.dtype == dt and s.shape[:3] == (N, H, W)
@@ -83,6 +85,9 @@ def conv_gemm(
             assert rs.dtype == torch.float32 and rs.shape == (N, H, W) and rs.stride(2) == 1 and rs.stride(1) == W
             p.src[i].row_scale = rs.data_ptr()
             p.src[i].scale_img_stride = rs.stride(0) if N > 1 else H * W
+    if src_s2d:  # sources are [N,H/2,W/2,4C] space-to-depth views of the logical [N,H,W,C] inputs
+        ctot //= 4
+        H, W = 2 * H, 2 * W
     cout = weight.shape[0]
     assert weight.dtype == dt and weight.is_contiguous() and weight.shape[1] == kh * kw * ctot, (weight.shape, kh, kw, ctot)
     p.weight = weight.data_ptr()
@@ -152,15 +157,29 @@ def tcgen05_supported(p: L.ConvParams) -> bool:
     return bool(L.load().fbanet_conv_gemm_tcgen05_supported(C.byref(p)))
 
 
-def to_nhwc(x: torch.Tensor, cp: int, dtype: torch.dtype) -> torch.Tensor:
-    """planar fp32 ``[frames,C,H,W]`` -> channels-last ``[frames,H,W,cp]`` (zero padded channels)."""
+def to_nhwc(x: torch.Tensor, cp: int, dtype: torch.dtype, im2col3x3: bool = False) -> torch.Tensor:
+    """planar fp32 ``[frames,C,H,W]`` -> channels-last ``[frames,H,W,cp]`` (zero padded channels);
+    ``im2col3x3``: channel ``(ky*3+kx)*C + c`` = 3x3 neighbourhood (zero padded), for the head conv."""
     assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
     Fr, Cc, H, W = x.shape
     out = torch.empty((Fr, H, W, cp), device=x.device, dtype=dtype)
     p = L.ToNhwcParams()
     p.src, p.dst, p.dtype = x.data_ptr(), out.data_ptr(), _DT[dtype]
     p.frames, p.C, p.H, p.W, p.Cp = Fr, Cc, H, W, cp
+    p.im2col3x3 = 1 if im2col3x3 else 0
     _call("fbanet_to_nhwc_sm100", p)
+    return out
+
+
+def space_to_depth(x: torch.Tensor) -> torch.Tensor:
+    """channels-last view ``[N,H,W,C]`` -> contiguous ``[N,H/2,W/2,4C]``, channel ``(ys*2+xs)*C + c``."""
+    ptr, Cc, ld, istr = _cl(x)
+    N, H, W, _ = x.shape
+    out = torch.empty((N, H // 2, W // 2, 4 * Cc), device=x.device, dtype=x.dtype)
+    p = L.S2dParams()
+    p.src, p.dst, p.img_stride, p.dtype = ptr, out.data_ptr(), istr, _DT[x.dtype]
+    p.N, p.H, p.W, p.C, p.ld = N, H, W, Cc, ld
+    _call("fbanet_space_to_depth_sm100", p)
     return out
 
 
@@ -203,16 +222,22 @@ def dwconv3x3(x: torch.Tensor, weight9c: torch.Tensor, bias: torch.Tensor, act: 
     return y
 
 
-def faf_gate(feat: torch.Tensor, wsum: torch.Tensor) -> torch.Tensor:
-    """feat ``[B,F,H,W,C]`` contiguous -> gate ``[B,F-1,H,W]`` fp32."""
+def faf_gate(feat: torch.Tensor, wsum: torch.Tensor, want_gate: bool = True, want_gated: bool = False):
+    """feat ``[B,F,H,W,C]`` contiguous -> gate ``[B,F-1,H,W]`` fp32 and/or gated features
+    ``[B,H,W,F*C]`` (pixel-major; frame 0 copied, frames >= 1 scaled) for the tensor-core fusion GEMM."""
     assert feat.is_cuda and feat.is_contiguous() and feat.dim() == 5
     B, Fr, H, W, Cc = feat.shape
-    gate = torch.empty((B, Fr - 1, H, W), device=feat.device, dtype=torch.float32)
+    gate = torch.empty((B, Fr - 1, H, W), device=feat.device, dtype=torch.float32) if want_gate else None
+    gated = torch.empty((B, H, W, Fr * Cc), device=feat.device, dtype=feat.dtype) if want_gated else None
     p = L.FafGateParams()
-    p.feat, p.gate, p.wsum, p.dtype = feat.data_ptr(), gate.data_ptr(), wsum.data_ptr(), _DT[feat.dtype]
+    p.feat, p.wsum, p.dtype = feat.data_ptr(), wsum.data_ptr(), _DT[feat.dtype]
+    p.gate = gate.data_ptr() if gate is not None else None
+    p.gated = gated.data_ptr() if gated is not None else None
     p.B, p.F, p.H, p.W, p.C = B, Fr, H, W, Cc
     _call("fbanet_faf_gate_sm100", p)
-    return gate
+    if want_gate and want_gated:
+        return gate, gated
+    return gated if want_gated else gate
 
 
 def warp_burst(burst: torch.Tensor, M: torch.Tensor, layout: str = "BTCHW", return_coords: bool = False):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 3
+#define FBANET_ABI_VERSION 4
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -94,6 +94,10 @@ typedef struct fbanet_conv_params {
   int32_t store_mode;
   int32_t res_ld;
   int32_t out_ld;         /* elements between output pixels (NHWC family)                           */
+  int32_t src_s2d;        /* 1: sources are space-to-depth(2) views [N,H/2,W/2,(ys,xs,c)] of the logical
+                             [N,H,W,C] inputs (fbanet_space_to_depth_sm100); only KH=KW=4, stride 2, pad 1,
+                             tensor-core path.  src[i].C is then 4*C_i.                                */
+  int32_t _pad;
 } fbanet_conv_params;
 
 /* K1: homography warp with bilinear sampling.  Replaces cv2.warpPerspective / cv2.warpAffine with
@@ -114,13 +118,27 @@ typedef struct fbanet_warp_params {
   int32_t _pad;
 } fbanet_warp_params;
 
-/* planar fp32 burst [frames][C][H][W] -> channels-last [frames][H][W][Cp] (zero padded channels) */
+/* planar fp32 burst [frames][C][H][W] -> channels-last [frames][H][W][Cp] (zero padded channels).
+ * im2col3x3 = 1: channel (ky*3+kx)*C + c holds src(c, y+ky-1, x+kx-1) (zero outside), so the head conv
+ * 3x3 (C_in = 3 or 4) becomes a K = Cp 1x1 GEMM for the tensor cores (models/fba_net.py:255). */
 typedef struct fbanet_to_nhwc_params {
   const float* src;
   void* dst;
   int32_t dtype;
   int32_t frames, C, H, W, Cp;
+  int32_t im2col3x3;
+  int32_t _pad;
 } fbanet_to_nhwc_params;
+
+/* channels-last view [N,H,W,C] -> contiguous [N,H/2,W/2,4C], channel (ys*2+xs)*C + c = src(2y+ys, 2x+xs, c).
+ * Feeds the 4x4 stride-2 downsampling convs (layers/downsample_flatten.py:6-13) to the TMA/tcgen05 path. */
+typedef struct fbanet_s2d_params {
+  const void* src;
+  void* dst;
+  int64_t img_stride;
+  int32_t dtype;
+  int32_t N, H, W, C, ld;
+} fbanet_s2d_params;
 
 /* K8: LayerNorm over channels, eps, affine (layers/fba_net.py:77-79,196,246). */
 typedef struct fbanet_layernorm_params {
@@ -168,10 +186,13 @@ typedef struct fbanet_dwconv_params {
  * reference's  |sum_c(E_f - R) - sum_c(E_0 - R)|  (R and the bias cancel). */
 typedef struct fbanet_faf_gate_params {
   const void* feat;       /* [B][F][H][W][C] channels-last                                          */
-  float* gate;            /* [B][F-1][H][W] fp32                                                    */
+  float* gate;            /* [B][F-1][H][W] fp32, or NULL                                           */
   const float* wsum;      /* [9][C] fp32                                                            */
+  void* gated;            /* optional [B][H][W][F][C] (pixel-major = the 1x1 fusion conv's K axis f*C + c):
+                             feat[b][0] for f = 0, feat[b][f] * gate[b][f-1] for f >= 1 (:102-105,121-128) */
   int32_t dtype;
   int32_t B, F, H, W, C;
+  int32_t _pad;
 } fbanet_faf_gate_params;
 
 /* Full-size tiling (utils/dataset_utils.py:5-58,140-180): reflect-pad + overlapping tile gather,
@@ -196,6 +217,7 @@ int fbanet_conv_gemm_tcgen05_supported(const fbanet_conv_params* p);
 
 int fbanet_warp_sm100(const fbanet_warp_params* p, void* stream);
 int fbanet_to_nhwc_sm100(const fbanet_to_nhwc_params* p, void* stream);
+int fbanet_space_to_depth_sm100(const fbanet_s2d_params* p, void* stream);
 int fbanet_conv_gemm_sm100(const fbanet_conv_params* p, void* stream);
 int fbanet_layernorm_sm100(const fbanet_layernorm_params* p, void* stream);
 int fbanet_window_attention_sm100(const fbanet_attn_params* p, void* stream);

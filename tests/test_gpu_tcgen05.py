@@ -1,0 +1,166 @@
+"""tcgen05/TMA implicit-GEMM kernel (bf16) against torch CPU fp32 references on bf16-rounded operands.
+``impl=IMPL_TCGEN05`` is forced so a silent SIMT fallback cannot make these pass."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def _r(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return ((torch.rand(shape, generator=g) * 2 - 1) * scale).to(BF).float()
+
+
+def _nhwc(x, dev):
+    return x.permute(0, 2, 3, 1).contiguous().to(dev, BF)
+
+
+def _pack(w, dev):
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous().to(dev, BF)
+
+
+def _check(got, ref, tol=2e-2):
+    got, ref = got.float().cpu(), ref.float()
+    err = (got - ref).abs().max().item()
+    assert torch.allclose(got, ref, atol=tol, rtol=tol), f"max abs err {err}"
+
+
+@pytest.mark.parametrize("cin,cout,h,w,act,res", [
+    (64, 64, 160, 160, 1, False), (64, 64, 24, 40, 0, True), (128, 128, 80, 80, 0, True), (256, 256, 40, 40, 1, False),
+    (128, 64, 20, 20, 2, False), (64, 256, 10, 10, 3, False), (256, 128, 33, 17, 0, True), (64, 64, 5, 7, 0, False)])
+def test_tc_conv3x3(cuda, cin, cout, h, w, act, res):
+    from fbanet_b200 import ops, _lib as L
+    n = 3 if h <= 40 else 1
+    x, wt, b = _r(n, cin, h, w, seed=1), _r(cout, cin, 3, 3, seed=2, scale=1 / math.sqrt(cin * 9)), _r(cout, seed=3, scale=0.1)
+    r = _r(n, cout, h, w, seed=4)
+    alpha = torch.tensor([0.25])
+    ref = F.conv2d(x, wt, b, padding=1)
+    ref = {0: lambda v: v, 1: F.relu, 2: lambda v: F.prelu(v, alpha), 3: lambda v: F.gelu(v, approximate="tanh")}[act](ref)
+    if res:
+        ref = ref + r
+    out = torch.empty(n, h, w, cout, device=cuda, dtype=BF)
+    ops.conv_gemm([_nhwc(x, cuda)], _pack(wt, cuda), out, kh=3, kw=3, pad=1, bias=b.to(cuda), act=act, alpha=alpha.to(cuda),
+                  residual=_nhwc(r, cuda) if res else None, impl=L.IMPL_TCGEN05)
+    _check(out.permute(0, 3, 1, 2), ref)
+
+
+def test_tc_multisource_views_and_slice_output(cuda):
+    from fbanet_b200 import ops, _lib as L
+    a, b_, c = _r(2, 256, 20, 20, seed=1), _r(2, 128, 20, 20, seed=2), _r(2, 128, 20, 20, seed=3)
+    w, bias = _r(256, 512, 3, 3, seed=4, scale=0.02), _r(256, seed=5)
+    ref = F.prelu(F.conv2d(torch.cat([a, b_, c], 1), w, bias, padding=1), torch.tensor([0.25]))
+    wide = torch.zeros(2, 20, 20, 192, device=cuda, dtype=BF)
+    wide[..., 64:] = _nhwc(c, cuda)
+    outbuf = torch.zeros(2, 20, 20, 512, device=cuda, dtype=BF)
+    ops.conv_gemm([_nhwc(a, cuda), _nhwc(b_, cuda), wide[..., 64:]], _pack(w, cuda), outbuf[..., 256:], kh=3, kw=3, pad=1, bias=bias.to(cuda),
+                  act=L.ACT_PRELU, alpha=torch.tensor([0.25], device=cuda), impl=L.IMPL_TCGEN05)
+    _check(outbuf[..., 256:].permute(0, 3, 1, 2), ref)
+    assert outbuf[..., :256].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 192), (128, 384), (256, 768), (128, 512), (256, 1024), (512, 128), (1024, 256), (896, 64)])
+def test_tc_linear(cuda, cin, cout):
+    """token GEMMs: qkv (N=3C, BN 192/256 tiling), LeFF fc1/fc2, FAF 1x1 (K=896)."""
+    from fbanet_b200 import ops, _lib as L
+    T = 1700
+    x, w, b = _r(1, T, cin, seed=1), _r(cout, cin, seed=2, scale=1 / math.sqrt(cin)), _r(cout, seed=3)
+    r = _r(1, T, cout, seed=4)
+    ref = F.linear(x, w, b) + r
+    out = torch.empty(1, 34, 50, cout, device=cuda, dtype=BF)
+    ops.conv_gemm([x.view(1, 34, 50, cin).to(cuda, BF)], w.to(cuda, BF), out, bias=b.to(cuda), residual=r.view(1, 34, 50, cout).to(cuda, BF),
+                  impl=L.IMPL_TCGEN05)
+    _check(out.view(1, T, cout), ref, tol=3e-2)
+
+
+@pytest.mark.parametrize("cin,co,hw", [(256, 128, 40), (256, 64, 80), (256, 128, 10)])
+def test_tc_conv_transpose(cuda, cin, co, hw):
+    from fbanet_b200 import ops, _lib as L
+    x, w, b = _r(2, cin, hw, hw, seed=1), _r(cin, co, 2, 2, seed=2, scale=0.05), _r(co, seed=3)
+    ref = F.conv_transpose2d(x, w, b, stride=2)
+    wp = w.permute(2, 3, 1, 0).reshape(4 * co, cin).contiguous().to(cuda, BF)
+    cat = torch.zeros(2, 2 * hw, 2 * hw, 2 * co, device=cuda, dtype=BF)
+    ops.conv_gemm([_nhwc(x, cuda)], wp, cat[..., :co], bias=b.repeat(4).to(cuda), store_mode=L.STORE_CONVT2, impl=L.IMPL_TCGEN05)
+    _check(cat[..., :co].permute(0, 3, 1, 2), ref)
+    assert cat[..., co:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(64, 128, 160), (128, 256, 80), (64, 128, 20)])
+def test_tc_downsample_space_to_depth(cuda, cin, cout, hw):
+    from fbanet_b200 import ops, _lib as L
+    n = 2
+    x, w, b = _r(n, cin, hw, hw, seed=1), _r(cout, cin, 4, 4, seed=2, scale=1 / math.sqrt(16 * cin)), _r(cout, seed=3)
+    ref = F.conv2d(x, w, b, stride=2, padding=1)
+    wide = torch.zeros(n, hw, hw, 2 * cin, device=cuda, dtype=BF)
+    wide[..., cin:] = _nhwc(x, cuda)  # strided source view, as conv0 inside the concat buffer
+    s2d = ops.space_to_depth(wide[..., cin:])
+    xs = x.permute(0, 2, 3, 1).reshape(n, hw // 2, 2, hw // 2, 2, cin).permute(0, 1, 3, 2, 4, 5).reshape(n, hw // 2, hw // 2, 4 * cin)
+    assert torch.equal(s2d.float().cpu(), xs)
+    out = torch.empty(n, hw // 2, hw // 2, cout, device=cuda, dtype=BF)
+    ops.conv_gemm([s2d], _pack(w, cuda), out, kh=4, kw=4, stride=2, pad=1, bias=b.to(cuda), src_s2d=True, impl=L.IMPL_TCGEN05)
+    _check(out.permute(0, 3, 1, 2), ref)
+
+
+def test_tc_final_conv_nchw_base(cuda):
+    from fbanet_b200 import ops, _lib as L
+    x, w, b = _r(2, 64, 64, 96, seed=1), _r(3, 64, 3, 3, seed=2, scale=0.03), _r(3, seed=3)
+    burst = torch.rand(2, 5, 3, 16, 24, generator=torch.Generator().manual_seed(4))
+    ref = F.conv2d(x, w, b, padding=1) + F.interpolate(burst[:, 0], scale_factor=4, mode="bilinear", align_corners=False)
+    wp = F.pad(_pack(w, cuda), (0, 0, 0, 13))
+    bp = F.pad(b, (0, 13)).to(cuda)
+    out = torch.empty(2, 3, 64, 96, device=cuda, dtype=torch.float32)
+    ops.conv_gemm([_nhwc(x, cuda)], wp.contiguous(), out, kh=3, kw=3, pad=1, bias=bp, store_mode=L.STORE_NCHW_BASE, base=burst.to(cuda)[:, 0],
+                  cout_store=3, impl=L.IMPL_TCGEN05)
+    _check(out, ref, tol=1e-2)
+
+
+def test_tc_head_im2col(cuda):
+    from fbanet_b200 import ops, _lib as L
+    x = torch.rand(6, 3, 40, 40, generator=torch.Generator().manual_seed(1))
+    w, b = _r(64, 3, 3, 3, seed=2, scale=0.2), _r(64, seed=3)
+    ref = F.conv2d(x.to(BF).float(), w, b, padding=1)
+    xn = ops.to_nhwc(x.to(cuda), 64, BF, im2col3x3=True)
+    wp = F.pad(w.permute(0, 2, 3, 1).reshape(64, 27), (0, 37)).to(cuda, BF).contiguous()
+    out = torch.empty(6, 40, 40, 64, device=cuda, dtype=BF)
+    ops.conv_gemm([xn], wp, out, bias=b.to(cuda), impl=L.IMPL_TCGEN05)
+    _check(out.permute(0, 3, 1, 2), ref)
+
+
+def test_tc_gated_features_and_fuse(cuda):
+    """K2 on the tensor-core path: gate kernel emits pixel-major gated features, 1x1 fusion GEMM K=F*E."""
+    from fbanet_b200 import ops, _lib as L
+    B, Fr, E, S = 2, 14, 64, 20
+    feat = _r(B, Fr, S, S, E, seed=1)
+    w1 = _r(E, E, 3, 3, seed=4, scale=0.04)
+    wsum = w1.double().sum(0).permute(1, 2, 0).reshape(9, E).float().contiguous()
+    fd = feat.to(cuda, BF)
+    gate, gated = ops.faf_gate(fd, wsum.to(cuda), want_gate=True, want_gated=True)
+    g = gate.cpu()
+    exp = torch.cat([feat[:, :1], feat[:, 1:] * g[..., None]], 1).permute(0, 2, 3, 1, 4).reshape(B, S, S, Fr * E)
+    _check(gated, exp, tol=1e-2)
+    w, b = _r(E, Fr * E, seed=5, scale=0.03), _r(E, seed=6)
+    ref = F.prelu(F.linear(gated.float().cpu(), w, b), torch.tensor([0.1]))
+    out = torch.empty(B, S, S, E, device=cuda, dtype=BF)
+    ops.conv_gemm([gated], w.to(cuda, BF), out, bias=b.to(cuda), act=L.ACT_PRELU, alpha=torch.tensor([0.1], device=cuda), impl=L.IMPL_TCGEN05)
+    _check(out, ref)
+
+
+def test_tc_persistent_many_tiles(cuda):
+    """more tiles than SMs and than pipeline stages: exercises the persistent loop, barrier phase wrap and
+    TMEM double buffering (batch 24 x 80x80 -> 1200 M-tiles x 2 N-tiles)."""
+    from fbanet_b200 import ops, _lib as L
+    x, w, b = _r(24, 128, 80, 80, seed=1), _r(512, 128, seed=2, scale=0.08), _r(512, seed=3)
+    ref = F.gelu(F.linear(x.permute(0, 2, 3, 1), w, b), approximate="tanh")
+    out = torch.empty(24, 80, 80, 512, device=cuda, dtype=BF)
+    ops.conv_gemm([_nhwc(x, cuda)], w.to(cuda, BF), out, bias=b.to(cuda), act=L.ACT_GELU_TANH, impl=L.IMPL_TCGEN05)
+    _check(out, ref)
+
+
+def test_unsupported_shapes_are_refused(cuda):
+    from fbanet_b200 import ops, _lib as L
+    x = torch.zeros(1, 8, 8, 32, device=cuda, dtype=BF)
+    with pytest.raises(RuntimeError, match="unsupported"):
+        ops.conv_gemm([x], torch.zeros(64, 32, device=cuda, dtype=BF), torch.empty(1, 8, 8, 64, device=cuda, dtype=BF), impl=L.IMPL_TCGEN05)
