@@ -505,17 +505,17 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   tp.act = p->act; tp.store_mode = p->store_mode; tp.res_ld = p->res_ld; tp.out_ld = p->out_ld;
 
   const int stage_bytes = TC_A_BYTES + tp.BN * TC_BK * 2;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (196 * 1024) / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages > ns * 2) stages = ns * 2 < 2 ? 2 : ns * 2;
   tp.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { set_last_error(e); return FBANET_E_LAUNCH; }
-    attr_set = true;
+  static size_t smem_opted_in = 0;  // opt-in limit is per function; raise it only when a launch needs more
+  if (smem > smem_opted_in) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cudaGetLastError(); set_last_error(e); return FBANET_E_LAUNCH; }
+    smem_opted_in = smem;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

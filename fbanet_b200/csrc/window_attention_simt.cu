@@ -89,7 +89,7 @@ static int launch_attn(const fbanet_attn_params* p, cudaStream_t s) {
   if (smem > 227 * 1024) return FBANET_E_BADSHAPE;
   auto kern = window_attention_simt_kernel<T, DH>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_last_error(e); return FBANET_E_LAUNCH; }
+  if (e != cudaSuccess) { cudaGetLastError(); set_last_error(e); return FBANET_E_LAUNCH; }
   dim3 grid(p->B * (p->H / p->win) * (p->W / p->win), p->heads);
   kern<<<grid, 128, smem, s>>>(*p);
   return check_launch();
