@@ -80,6 +80,33 @@ __global__ void __launch_bounds__(256) to_nhwc_kernel(const fbanet_to_nhwc_param
   }
 }
 
+// head-conv im2col, bf16: 8 threads per pixel, each builds one 16-byte vector (8 of the Cp channels)
+__global__ void __launch_bounds__(256) im2col3x3_bf16_kernel(const fbanet_to_nhwc_params p) {
+  const int vpp = p.Cp / 8;  // vectors per pixel
+  const int64_t hw = (int64_t)p.H * p.W;
+  const int64_t total = (int64_t)p.frames * hw * vpp;
+  bf16* dst = reinterpret_cast<bf16*>(p.dst);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % vpp);
+    const int64_t gp = idx / vpp;
+    const int64_t f = gp / hw, pix = gp % hw;
+    const int y = (int)(pix / p.W), x = (int)(pix % p.W);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = v * 8 + j;
+      float val = 0.f;
+      if (c < 9 * p.C) {
+        const int tap = c / p.C, ch = c - tap * p.C;
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) val = __ldg(p.src + (f * p.C + ch) * hw + (int64_t)yy * p.W + xx);
+      }
+      o[j] = val;
+    }
+    store_vec<bf16, 8>(dst + idx * 8, o);
+  }
+}
+
 // channels-last view -> space-to-depth(2), one thread per 16-byte vector of the destination
 template <typename T>
 __global__ void __launch_bounds__(256) s2d_kernel(const fbanet_s2d_params p) {
@@ -139,6 +166,42 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const fbanet_layernorm_p
   }
 }
 
+// K8 (bf16 fast path): C/8 threads per token, one 16-byte load/store per thread, xor-shuffle reductions
+template <int C>
+__global__ void __launch_bounds__(256) layernorm_bf16_kernel(const fbanet_layernorm_params p) {
+  constexpr int TPT = C / 8;  // threads per token (8, 16 or 32)
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = gt / TPT;
+  const int sub = (int)(gt % TPT);
+  const bool ok = row < p.rows;  // rows padded to a whole warp: keep all lanes alive for the shuffles
+  float v[8];
+  if (ok) load_vec<bf16, 8>(reinterpret_cast<const bf16*>(p.x) + row * p.x_ld + sub * 8, v);
+  else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+#pragma unroll
+  for (int o = TPT / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q += d * d; }
+#pragma unroll
+  for (int o = TPT / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.0f / C) + p.eps);
+  if (!ok) return;
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + sub * 8)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + sub * 8 + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + sub * 8)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + sub * 8 + 4));
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float o8[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o8[i] = (v[i] - mean) * rstd * gg[i] + bb[i];
+  store_vec<bf16, 8>(reinterpret_cast<bf16*>(p.y) + row * p.y_ld + sub * 8, o8);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K7  depthwise 3x3 pad 1 + bias + activation, channels-last.  One thread = one pixel x VEC channels.
 // ------------------------------------------------------------------------------------------------
@@ -176,6 +239,80 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const fbanet_dwconv_para
 #pragma unroll
     for (int j = 0; j < V; ++j) acc[j] = apply_act(acc[j], p.act, 0.f);
     store_vec<T, V>(Yo + pix * p.C + c0, acc);
+  }
+}
+
+// K7 (bf16 fast path): one thread = 8 channels x a horizontal run of SEG pixels.  The 9x8 weights live in
+// registers for the whole run and a 3x3 window of packed bf16 vectors slides along x, so every output costs
+// three 16-byte loads (one per input row) instead of nine loads plus 80 scalar weight loads.
+template <int SEG>
+__global__ void __launch_bounds__(128) dwconv3x3_bf16_run_kernel(const fbanet_dwconv_params p) {
+  const int cg = p.C / 8;
+  const int segs = (p.W + SEG - 1) / SEG;
+  const int64_t total = (int64_t)p.N * p.H * segs * cg;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = (int)(idx % cg) * 8;
+  int64_t r = idx / cg;
+  const int seg = (int)(r % segs); r /= segs;
+  const int y = (int)(r % p.H);
+  const int64_t n = r / p.H;
+  const int x_begin = seg * SEG, x_end = min(x_begin + SEG, p.W);
+  const bf16* X = reinterpret_cast<const bf16*>(p.x) + n * (int64_t)p.H * p.W * p.C + c0;
+  bf16* Y = reinterpret_cast<bf16*>(p.y) + (n * (int64_t)p.H + y) * p.W * p.C + c0;
+
+  float w[9][8], bias[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.weight + t * p.C + c0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.weight + t * p.C + c0 + 4));
+    w[t][0] = a.x; w[t][1] = a.y; w[t][2] = a.z; w[t][3] = a.w; w[t][4] = b.x; w[t][5] = b.y; w[t][6] = b.z; w[t][7] = b.w;
+  }
+  {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4));
+    bias[0] = a.x; bias[1] = a.y; bias[2] = a.z; bias[3] = a.w; bias[4] = b.x; bias[5] = b.y; bias[6] = b.z; bias[7] = b.w;
+  }
+  const bool rok[3] = {y - 1 >= 0, true, y + 1 < p.H};
+  const bf16* rows[3] = {X + (int64_t)(y - 1) * p.W * p.C, X + (int64_t)y * p.W * p.C, X + (int64_t)(y + 1) * p.W * p.C};
+  auto ld = [&](int rr, int xx) -> uint4 {
+    if (!rok[rr] || xx < 0 || xx >= p.W) return make_uint4(0, 0, 0, 0);
+    return *reinterpret_cast<const uint4*>(rows[rr] + (int64_t)xx * p.C);
+  };
+  uint4 win[3][3];  // [row][column x-1, x, x+1]
+#pragma unroll
+  for (int rr = 0; rr < 3; ++rr) { win[rr][1] = ld(rr, x_begin - 1); win[rr][2] = ld(rr, x_begin); }
+  uint4 nxt[3];
+#pragma unroll
+  for (int rr = 0; rr < 3; ++rr) nxt[rr] = ld(rr, x_begin + 1);
+  for (int x = x_begin; x < x_end; ++x) {
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr) { win[rr][0] = win[rr][1]; win[rr][1] = win[rr][2]; win[rr][2] = nxt[rr]; }
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr) nxt[rr] = ld(rr, x + 2);  // prefetch the column used by the next step
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias[j];
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&win[rr][cc]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          acc[2 * j] = fmaf(f.x, w[rr * 3 + cc][2 * j], acc[2 * j]);
+          acc[2 * j + 1] = fmaf(f.y, w[rr * 3 + cc][2 * j + 1], acc[2 * j + 1]);
+        }
+      }
+    if (p.act == FBANET_ACT_GELU_TANH) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = gelu_tanh_fast(acc[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = apply_act(acc[j], p.act, 0.f);
+    }
+    store_vec<bf16, 8>(Y + (int64_t)x * p.C, acc);
   }
 }
 
@@ -233,6 +370,68 @@ __global__ void __launch_bounds__(256) faf_gate_kernel(const fbanet_faf_gate_par
   }
 }
 
+// K2a (bf16 fast path, C = 64): 8 threads per pixel, each owns 8 channels (one 16-byte vector per tap).
+// The base frame's 3x3 neighbourhood and the 9x8 gate weights stay in registers across the F-1 frames; the
+// centre tap of every frame is re-used for the gated-feature write (pixel-major [B][H][W][F][C]).
+__global__ void __launch_bounds__(128) faf_gate_bf16_c64_kernel(const fbanet_faf_gate_params p) {
+  constexpr int C = 64;
+  const int sub = threadIdx.x & 7;
+  const int64_t hw = (int64_t)p.H * p.W;
+  const int64_t gp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const bool live = gp < (int64_t)p.B * hw;  // keep dead lanes for the shuffles
+  const int64_t gpc = live ? gp : 0;
+  const int64_t b = gpc / hw, pix = gpc % hw;
+  const int y = (int)(pix / p.W), x = (int)(pix % p.W);
+  const bf16* feat = reinterpret_cast<const bf16*>(p.feat) + sub * 8;
+  float w[9][8];
+  uint4 ref[9];
+  bool ok[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+    ok[t] = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.wsum + t * C + sub * 8));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(p.wsum + t * C + sub * 8 + 4));
+    w[t][0] = a.x; w[t][1] = a.y; w[t][2] = a.z; w[t][3] = a.w; w[t][4] = c.x; w[t][5] = c.y; w[t][6] = c.z; w[t][7] = c.w;
+    ref[t] = ok[t] ? *reinterpret_cast<const uint4*>(feat + ((b * p.F) * hw + (int64_t)yy * p.W + xx) * C) : make_uint4(0, 0, 0, 0);
+  }
+  bf16* gated = p.gated ? reinterpret_cast<bf16*>(p.gated) + ((b * hw + pix) * p.F) * C + sub * 8 : nullptr;
+  if (gated && live) *reinterpret_cast<uint4*>(gated) = ref[4];  // frame 0 passes through (:103)
+  for (int f = 1; f < p.F; ++f) {
+    uint4 v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      v[t] = ok[t] ? *reinterpret_cast<const uint4*>(feat + ((b * p.F + f) * hw + (int64_t)yy * p.W + xx) * C) : make_uint4(0, 0, 0, 0);
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&v[t]);
+      const __nv_bfloat162* hr = reinterpret_cast<const __nv_bfloat162*>(&ref[t]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = __bfloat1622float2(hv[j]), r = __bfloat1622float2(hr[j]);
+        acc = fmaf(w[t][2 * j], a.x - r.x, acc);
+        acc = fmaf(w[t][2 * j + 1], a.y - r.y, acc);
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    const float g = 1.0f / (1.0f + __expf(-fabsf(acc)));
+    if (!live) continue;
+    if (sub == 0 && p.gate) p.gate[(b * (p.F - 1) + (f - 1)) * hw + pix] = g;
+    if (gated) {
+      float o[8];
+      const __nv_bfloat162* hc = reinterpret_cast<const __nv_bfloat162*>(&v[4]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 a = __bfloat1622float2(hc[j]); o[2 * j] = a.x * g; o[2 * j + 1] = a.y * g; }
+      store_vec<bf16, 8>(gated + (int64_t)f * C, o);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // full-size tiling: reflect index helper (torch 'reflect': no edge repeat)
 // ------------------------------------------------------------------------------------------------
@@ -283,7 +482,7 @@ __global__ void __launch_bounds__(256) tile_merge_kernel(const fbanet_tile_param
 
 static int grid_for(int64_t total, int block) {
   int64_t g = (total + block - 1) / block;
-  const int64_t cap = 148 * 16;
+  const int64_t cap = 148 * 32;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -303,8 +502,12 @@ extern "C" int fbanet_to_nhwc_sm100(const fbanet_to_nhwc_params* p, void* stream
   if (!p || !p->src || !p->dst || p->Cp < p->C || p->frames <= 0) return FBANET_E_BADSHAPE;
   const int64_t total = (int64_t)p->frames * p->H * p->W;
   if (p->dtype == FBANET_F32) to_nhwc_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
-  else if (p->dtype == FBANET_BF16) to_nhwc_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
-  else return FBANET_E_DTYPE;
+  else if (p->dtype == FBANET_BF16) {
+    if (p->im2col3x3 && p->Cp % 8 == 0 && ((uintptr_t)p->dst % 16) == 0)
+      im2col3x3_bf16_kernel<<<grid_for(total * (p->Cp / 8), 256), 256, 0, (cudaStream_t)stream>>>(*p);
+    else
+      to_nhwc_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  } else return FBANET_E_DTYPE;
   return check_launch();
 }
 
@@ -339,7 +542,14 @@ extern "C" int fbanet_layernorm_sm100(const fbanet_layernorm_params* p, void* st
   const int v = p->dtype == FBANET_F32 ? 4 : 8;
   if (p->x_ld % v || ((uintptr_t)p->x % 16)) return FBANET_E_ALIGN;
   if (p->dtype == FBANET_F32) return launch_ln<float>(p, (cudaStream_t)stream);
-  if (p->dtype == FBANET_BF16) return launch_ln<bf16>(p, (cudaStream_t)stream);
+  if (p->dtype == FBANET_BF16) {
+    const bool fast = (p->y_ld % 8) == 0 && ((uintptr_t)p->y % 16) == 0 && ((uintptr_t)p->gamma % 16) == 0 && ((uintptr_t)p->beta % 16) == 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (fast && p->C == 64) { layernorm_bf16_kernel<64><<<ceil_div(p->rows * 8, 256), 256, 0, st>>>(*p); return check_launch(); }
+    if (fast && p->C == 128) { layernorm_bf16_kernel<128><<<ceil_div(p->rows * 16, 256), 256, 0, st>>>(*p); return check_launch(); }
+    if (fast && p->C == 256) { layernorm_bf16_kernel<256><<<ceil_div(p->rows * 32, 256), 256, 0, st>>>(*p); return check_launch(); }
+    return launch_ln<bf16>(p, st);
+  }
   return FBANET_E_DTYPE;
 }
 
@@ -350,8 +560,12 @@ extern "C" int fbanet_dwconv3x3_sm100(const fbanet_dwconv_params* p, void* strea
   if (((uintptr_t)p->x % 16) || ((uintptr_t)p->y % 16)) return FBANET_E_ALIGN;
   const int64_t total = (int64_t)p->N * p->H * p->W * (p->C / v);
   if (p->dtype == FBANET_F32) dwconv3x3_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
-  else if (p->dtype == FBANET_BF16) dwconv3x3_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
-  else return FBANET_E_DTYPE;
+  else if (p->dtype == FBANET_BF16) {
+    if (((uintptr_t)p->weight % 16) || ((uintptr_t)p->bias % 16)) return FBANET_E_ALIGN;
+    constexpr int SEG = 16;
+    const int64_t threads = (int64_t)p->N * p->H * ((p->W + SEG - 1) / SEG) * (p->C / 8);
+    dwconv3x3_bf16_run_kernel<SEG><<<ceil_div(threads, 128), 128, 0, (cudaStream_t)stream>>>(*p);
+  } else return FBANET_E_DTYPE;
   return check_launch();
 }
 
@@ -370,7 +584,14 @@ static int launch_gate(const fbanet_faf_gate_params* p, cudaStream_t s) {
 extern "C" int fbanet_faf_gate_sm100(const fbanet_faf_gate_params* p, void* stream) {
   if (!p || !p->feat || (!p->gate && !p->gated) || !p->wsum || p->B <= 0 || p->F < 2) return FBANET_E_BADSHAPE;
   if (p->dtype == FBANET_F32) return launch_gate<float>(p, (cudaStream_t)stream);
-  if (p->dtype == FBANET_BF16) return launch_gate<bf16>(p, (cudaStream_t)stream);
+  if (p->dtype == FBANET_BF16) {
+    if (p->C == 64 && ((uintptr_t)p->feat % 16) == 0 && ((uintptr_t)p->wsum % 16) == 0 && ((uintptr_t)p->gated % 16) == 0) {
+      const int64_t threads = (int64_t)p->B * p->H * p->W * 8;
+      faf_gate_bf16_c64_kernel<<<ceil_div(threads, 128), 128, 0, (cudaStream_t)stream>>>(*p);
+      return check_launch();
+    }
+    return launch_gate<bf16>(p, (cudaStream_t)stream);
+  }
   return FBANET_E_DTYPE;
 }
 

@@ -27,6 +27,13 @@ __device__ __forceinline__ float gelu_tanh(float u) {
   float inner = k0 * (u + k1 * u * u * u);
   return 0.5f * u * (1.0f + tanhf(inner));
 }
+// bf16-path GELU: single MUFU.TANH (abs err ~5e-4, below bf16 output rounding)
+__device__ __forceinline__ float gelu_tanh_fast(float u) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(k0 * fmaf(k1 * u * u, u, u)));
+  return 0.5f * u * (1.0f + th);
+}
 __device__ __forceinline__ float gelu_erf(float u) { return 0.5f * u * (1.0f + erff(u * 0.7071067811865476f)); }
 
 __device__ __forceinline__ float apply_act(float v, int act, float alpha) {

@@ -166,9 +166,18 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
       }
     }
   }
-  if (p.act != FBANET_ACT_NONE) {
+  if (p.act == FBANET_ACT_RELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act, alpha);
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+  } else if (p.act == FBANET_ACT_PRELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : alpha * f[j];
+  } else if (p.act == FBANET_ACT_GELU_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_tanh_fast(f[j]);
+  } else if (p.act == FBANET_ACT_GELU_ERF) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
   }
   if (p.store_mode == FBANET_STORE_NCHW_BASE) {
     // final conv: fp32 planar out + bilinear x4 (align_corners=False) of the low-res base frame
