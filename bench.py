@@ -123,6 +123,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-impl", default="auto", choices=["auto", "simt"])
+    ap.add_argument("--breakdown", action="store_true", help="print a per-kernel CUDA-event breakdown of one step to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -195,6 +196,13 @@ def main():
 
         # ---- dominant-kernel roofline: CUDA events around every conv/GEMM launch of one more eager pass ----
         prof = ops.profile_conv_gemm(lambda: model(x), stream)
+
+        if args.breakdown and rank == 0:
+            bd = ops.profile_ops(lambda: model(x), stream)
+            tot = sum(v[0] for v in bd.values())
+            print(f"[breakdown] one step, eager, CUDA events: {tot:.2f} ms", file=sys.stderr)
+            for k, (t_ms, n) in sorted(bd.items(), key=lambda kv: -kv[1][0]):
+                print(f"[breakdown] {t_ms:9.3f} ms {100 * t_ms / tot:5.1f}%  n={n:3d}  {k}", file=sys.stderr)
 
         # ---- end to end through the public API with HOST buffers (pinned H2D + D2H inside the timed region) ----
         for _ in range(2):

@@ -27,10 +27,38 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def _call(name, p):
+# when a list, every launch appends (op name, start_event, end_event, tag) -- per-kernel breakdowns
+_OPPROF = None
+
+
+def _call(name, p, tag=""):
     global LAUNCHES
     LAUNCHES += 1
+    if _OPPROF is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.call(name, p, _stream())
+        e1.record()
+        _OPPROF.append((name, e0, e1, tag))
+        return
     L.call(name, p, _stream())
+
+
+def profile_ops(fn, stream) -> dict:
+    """Run ``fn`` once with CUDA events around every kernel launch; {op name: (total ms, launches)}."""
+    global _OPPROF
+    _OPPROF = []
+    try:
+        fn()
+        stream.synchronize()
+        out = {}
+        for name, a, b, tag in _OPPROF:
+            k = name + (":" + tag if tag else "")
+            ms, n = out.get(k, (0.0, 0))
+            out[k] = (ms + a.elapsed_time(b), n + 1)
+    finally:
+        _OPPROF = None
+    return out
 
 
 def _cl(t: torch.Tensor):
@@ -132,7 +160,7 @@ def conv_gemm(
         flops = 2.0 * N * Ho * Wo * kh * kw * (ctot if alg_cin is None else alg_cin) * p.Cout_store
         _PROFILE.append((e0, e1, flops))
         return out
-    _call("fbanet_conv_gemm_sm100", p)
+    _call("fbanet_conv_gemm_sm100", p, tag=f"k{kh}s{stride} {ctot}->{cout} @{Ho}x{Wo} act{act}{' res' if residual is not None else ''} st{store_mode}")
     return out
 
 
