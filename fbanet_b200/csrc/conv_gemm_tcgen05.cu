@@ -23,26 +23,35 @@ constexpr int TC_MAX_STEPS = 160;
 constexpr int TC_MAX_SRC = 4;
 constexpr int TC_BK = 64;            // channels per K-step (128 bytes of bf16 = one swizzle row)
 constexpr int TC_A_BYTES = 128 * TC_BK * 2;
+constexpr int TC_MAX_CHUNKS = 32;
+constexpr int TC_HALO_TW = 8, TC_HALO_TH = 16;                       // 3x3 halo mode tile: 8 wide x 16 tall
+constexpr int TC_HALO_COPY = (TC_HALO_TH + 2) * TC_HALO_TW * 128;    // one dx-shifted copy: 18 rows x 1 KB
+constexpr int TC_HALO_SLOT = 3 * TC_HALO_COPY;                       // 54 KB per 64-channel chunk
 
+// generic mode: one A box + one B slab per K-step
 struct KStep { int16_t src, c0, dx, dy; };
+// halo mode (3x3 stride 1): one 64-channel chunk = 3 dx-shifted halo boxes, re-used by the 9 taps
+struct Chunk { int16_t src, c0; int32_t cg; };   // cg = offset of the chunk in the concatenated channel axis
 
 struct TcParams {
   CUtensorMap amap[TC_MAX_SRC];
   CUtensorMap bmap;
   KStep steps[TC_MAX_STEPS];
+  Chunk chunks[TC_MAX_CHUNKS];
   const float* bias;
   const float* alpha;
   const bf16* residual;
   void* out;
   const float* base;
   int64_t res_img_stride, out_img_stride, base_img_stride;
-  int nsteps;
+  int nsteps;             // K-steps per tile (MMA groups of 4)
+  int halo, nchunks, ctot;
   int N, Ho, Wo;          // tile space == output pixels
-  int tw, th, tiles_x, tiles_y;
+  int tw, th, tiles_x, tiles_y, m_tiles;
   int BN, n_tiles_n, Cout, Cout_store;
   int act, store_mode, res_ld, out_ld;
-  int stages, a_box_bytes;
-  int total_tiles;
+  int a_slots, a_slot_bytes, a_box_bytes;
+  int b_slots, b_resident;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -235,19 +244,22 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
   }
 }
 
-constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_MAX_A_SLOTS = 8;
+constexpr int TC_NUM_THREADS = 384;   // warps: 0 A-producer, 1 MMA, 2 TMEM alloc, 3 B-producer, 4..11 epilogue
 
-__global__ void __launch_bounds__(256, 1) conv_gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], tmem_full[2], tmem_empty[2];
+  __shared__ __align__(8) uint64_t a_full[TC_MAX_A_SLOTS], a_empty[TC_MAX_A_SLOTS], tmem_full[2], tmem_empty[2];
+  __shared__ __align__(8) uint64_t b_full[TC_MAX_STEPS], b_empty[TC_MAX_STEPS];
   __shared__ uint32_t tmem_base_slot;
 
   // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the 128B swizzle needs
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int BN = p.BN, stages = p.stages;
+  const int BN = p.BN;
   const uint32_t b_bytes = (uint32_t)BN * TC_BK * 2;
-  const uint32_t stage_bytes = TC_A_BYTES + b_bytes;   // multiple of 1024
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + (size_t)p.a_slots * p.a_slot_bytes;
   const uint32_t tmem_cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 
   if (warp == 0 && lane == 0) {
@@ -255,8 +267,9 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_tcgen05_kernel(const __grid_
     tma_prefetch_desc(&p.bmap);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    for (int s = 0; s < p.a_slots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < p.b_slots; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -268,78 +281,134 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_tcgen05_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
+  // static tile schedule: this CTA owns one N-tile (so resident weights stay valid) and every
+  // (gridDim/n_tiles_n)-th M-tile; neighbouring CTAs share A tiles in L2.
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int nt = blockIdx.x % p.n_tiles_n;
+  const int mt0 = blockIdx.x / p.n_tiles_n, mt_step = gridDim.x / p.n_tiles_n;
+  const int units = p.halo ? p.nchunks : p.nsteps;   // A-slot fills per tile
+  const int taps = p.halo ? 9 : 1;                   // K-steps served by one A slot
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= A producer (TMA) =================
     if (lane == 0) {
-      int stage = 0;
+      int slot = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
+      for (int mt = mt0; mt < p.m_tiles; mt += mt_step) {
         const int img = mt / tiles_per_img, r = mt % tiles_per_img;
         const int y0 = (r / p.tiles_x) * p.th, x0 = (r % p.tiles_x) * p.tw;
-        for (int s = 0; s < p.nsteps; ++s) {
-          const KStep ks = p.steps[s];
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          mbar_expect_tx(&full_bar[stage], (uint32_t)p.a_box_bytes + b_bytes);
-          tma_load_4d(sa, &p.amap[ks.src], &full_bar[stage], ks.c0, x0 + ks.dx, y0 + ks.dy, img);
-          tma_load_2d(sa + TC_A_BYTES, &p.bmap, &full_bar[stage], s * TC_BK, nt * BN);
-          if (++stage == stages) { stage = 0; phase ^= 1; }
+        for (int u = 0; u < units; ++u) {
+          mbar_wait(&a_empty[slot], phase ^ 1);
+          uint8_t* sa = smem_a + (size_t)slot * p.a_slot_bytes;
+          if (p.halo) {
+            const Chunk ch = p.chunks[u];
+            mbar_expect_tx(&a_full[slot], 3u * (uint32_t)TC_HALO_COPY);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) tma_load_4d(sa + d * TC_HALO_COPY, &p.amap[ch.src], &a_full[slot], ch.c0, x0 + d - 1, y0 - 1, img);
+          } else {
+            const KStep ks = p.steps[u];
+            mbar_expect_tx(&a_full[slot], (uint32_t)p.a_box_bytes);
+            tma_load_4d(sa, &p.amap[ks.src], &a_full[slot], ks.c0, x0 + ks.dx, y0 + ks.dy, img);
+          }
+          if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
         }
+      }
+    }
+  } else if (warp == 3) {
+    // ================= B producer (TMA): weight slabs [BN x 64] =================
+    if (lane == 0) {
+      auto bk = [&](int s) -> int {   // K offset of K-step s in the packed weights
+        if (!p.halo) return s * TC_BK;
+        const int u = s / 9, t = s - u * 9;
+        return t * p.ctot + p.chunks[u].cg;
+      };
+      if (p.b_resident) {
+        if (mt0 < p.m_tiles)
+          for (int s = 0; s < p.nsteps; ++s) {
+            mbar_expect_tx(&b_full[s], b_bytes);
+            tma_load_2d(smem_b + (size_t)s * b_bytes, &p.bmap, &b_full[s], bk(s), nt * BN);
+          }
+      } else {
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int mt = mt0; mt < p.m_tiles; mt += mt_step)
+          for (int s = 0; s < p.nsteps; ++s) {
+            mbar_wait(&b_empty[slot], phase ^ 1);
+            mbar_expect_tx(&b_full[slot], b_bytes);
+            tma_load_2d(smem_b + (size_t)slot * b_bytes, &p.bmap, &b_full[slot], bk(s), nt * BN);
+            if (++slot == p.b_slots) { slot = 0; phase ^= 1; }
+          }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(BN);
-      int stage = 0;
-      uint32_t phase = 0;
+      int aslot = 0, bslot = 0;
+      uint32_t aphase = 0, bphase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int s = 0; s < p.nsteps; ++s) {
-          mbar_wait(&full_bar[stage], phase);          // TMA bytes have landed
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + TC_A_BYTES);
+        int s = 0;
+        for (int u = 0; u < units; ++u) {
+          mbar_wait(&a_full[aslot], aphase);
+          const uint32_t sa = smem_u32(smem_a + (size_t)aslot * p.a_slot_bytes);
+          for (int t = 0; t < taps; ++t, ++s) {
+            uint32_t sb;
+            if (p.b_resident) {
+              mbar_wait(&b_full[s], 0);                // completes once, stays complete
+              sb = smem_u32(smem_b + (size_t)s * b_bytes);
+            } else {
+              mbar_wait(&b_full[bslot], bphase);
+              sb = smem_u32(smem_b + (size_t)bslot * b_bytes);
+            }
+            tc_fence_after();
+            // halo mode: tap (ky,kx) reads the dx-shifted copy kx, starting ky rows (1 KB each) down
+            const uint32_t a_addr = p.halo ? sa + (uint32_t)((t % 3) * TC_HALO_COPY + (t / 3) * 1024) : sa;
+            const uint64_t adesc = make_sw128_desc(a_addr), bdesc = make_sw128_desc(sb);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)           // advance 32 bytes (16 bf16) inside the swizzle row
-            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((s | k) != 0));
-          umma_commit(&empty_bar[stage]);              // frees the smem slot when these MMAs retire
-          if (++stage == stages) { stage = 0; phase ^= 1; }
+            for (int k = 0; k < TC_BK / 16; ++k)       // advance 32 bytes (16 bf16) inside the swizzle row
+              umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((s | k) != 0));
+            if (!p.b_resident) {
+              umma_commit(&b_empty[bslot]);
+              if (++bslot == p.b_slots) { bslot = 0; bphase ^= 1; }
+            }
+          }
+          umma_commit(&a_empty[aslot]);               // frees the A slot when these MMAs retire
+          if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);                  // accumulator ready for the epilogue
       }
     }
   } else if (warp >= 4) {
-    // ================= epilogue =================
+    // ================= epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =================
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;
+    const int ncols = (BN >= 32) ? BN / 2 : (half == 0 ? BN : 0);
+    const int cbeg = half * (BN / 2);
     const int row = q * 32 + lane;
     const int ly = row / p.tw, lx = row - ly * p.tw;
     const float alpha = (p.act == FBANET_ACT_PRELU) ? __ldg(p.alpha) : 0.f;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
       const int img = mt / tiles_per_img, r = mt % tiles_per_img;
       const int y = (r / p.tiles_x) * p.th + ly, x = (r % p.tiles_x) * p.tw + lx;
       const bool valid = (ly < p.th) && (y < p.Ho) && (x < p.Wo);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cbeg);
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t v[32];
-        const int nc = (BN - c0 >= 32) ? 32 : 16;
+        const int nc = (ncols - c0 >= 32) ? 32 : 16;
         if (nc == 32) tmem_ld32(taddr0 + c0, v); else tmem_ld16(taddr0 + c0, v);
         tmem_ld_wait();
-        if (valid) epilogue_chunk(p, v, nc, nt * BN + c0, img, y, x, alpha);
+        if (valid) epilogue_chunk(p, v, nc, nt * BN + cbeg + c0, img, y, x, alpha);
         __syncwarp();
       }
       tc_fence_before();
@@ -377,9 +446,10 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int pick_bn(int cout) {
-  if (cout <= 256) return cout;
-  for (int bn = 256; bn >= 64; bn -= 32)
+static int pick_bn(int cout, bool halo) {
+  const int cap = halo ? 128 : 256;   // halo mode keeps B slabs at <= 16 KB so two 54 KB A slots fit beside the ring
+  if (cout <= cap) return cout;
+  for (int bn = cap; bn >= 64; bn -= 64)
     if (cout % bn == 0) return bn;
   return 0;
 }
@@ -397,6 +467,8 @@ static void pick_tile(int H, int W, int* tw_out, int* th_out) {
   for (int c : cands) consider(c);
   if (W <= 128) consider(W);
 }
+
+static bool is_halo(const fbanet_conv_params* p) { return p->stride == 1 && p->KH == 3 && p->KW == 3 && p->pad == 1 && !p->src_s2d; }
 
 // conv kinds the tensor-core path takes
 static bool tc_shape_ok(const fbanet_conv_params* p) {
@@ -418,9 +490,9 @@ static bool tc_shape_ok(const fbanet_conv_params* p) {
   }
   const int taps = p->KH * p->KW;
   if (taps * (ctot / TC_BK) > TC_MAX_STEPS) return false;
-  const int bn = pick_bn(p->Cout);
-  if (bn == 0 || (bn % 16) || bn < 16) return false;
-  if (bn % 32 && bn != 16) return false;
+  if (is_halo(p) && ctot / TC_BK > TC_MAX_CHUNKS) return false;
+  const int bn = pick_bn(p->Cout, is_halo(p));
+  if (bn != 16 && bn != 64 && bn != 128 && bn != 192 && bn != 256) return false;
   if ((uintptr_t)p->weight % 16) return false;
   if (p->store_mode == FBANET_STORE_NHWC || p->store_mode == FBANET_STORE_CONVT2) {
     if ((p->out_ld % 8) || (p->out_img_stride % 8) || ((uintptr_t)p->out % 16)) return false;
@@ -439,30 +511,32 @@ int conv_gemm_tc_supported(const fbanet_conv_params* p) { return tc_shape_ok(p) 
 int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   if (!tc_shape_ok(p)) return FBANET_E_UNSUPPORTED;
   EncodeTiledFn encode = get_encode();
-  static thread_local TcParams tp;  // ~2.3 KB; filled per call, passed by value
+  static thread_local TcParams tp;  // ~2.6 KB; filled per call, passed by value
   memset(&tp, 0, sizeof(tp));
   const bool s2d = p->src_s2d != 0;
+  const bool halo = is_halo(p);
   // tile space = output pixels; for s2d sources the source view already has the output resolution
   const int Hs = s2d ? p->H / 2 : p->H, Ws = s2d ? p->W / 2 : p->W;
   if (Hs != p->Ho || Ws != p->Wo) return FBANET_E_BADSHAPE;
   int tw = 16, th = 8;
-  pick_tile(p->Ho, p->Wo, &tw, &th);
+  if (halo) { tw = TC_HALO_TW; th = TC_HALO_TH; } else pick_tile(p->Ho, p->Wo, &tw, &th);
   tp.tw = tw; tp.th = th;
   tp.tiles_x = (p->Wo + tw - 1) / tw;
   tp.tiles_y = (p->Ho + th - 1) / th;
+  tp.m_tiles = p->N * tp.tiles_x * tp.tiles_y;
   tp.N = p->N; tp.Ho = p->Ho; tp.Wo = p->Wo;
-  tp.BN = pick_bn(p->Cout);
+  tp.BN = pick_bn(p->Cout, halo);
   tp.n_tiles_n = p->Cout / tp.BN;
   tp.Cout = p->Cout; tp.Cout_store = p->Cout_store;
   tp.a_box_bytes = tw * th * TC_BK * 2;
-  tp.total_tiles = p->N * tp.tiles_x * tp.tiles_y * tp.n_tiles_n;
+  tp.halo = halo ? 1 : 0;
 
   int ctot = 0;
   for (int s = 0; s < p->nsrc; ++s) {
     const fbanet_src& S = p->src[s];
     const cuuint64_t dims[4] = {(cuuint64_t)S.C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)p->N};
     const cuuint64_t strides[3] = {(cuuint64_t)S.ld * 2, (cuuint64_t)S.ld * 2 * Ws, (cuuint64_t)S.img_stride * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)tw, (cuuint32_t)th, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)tw, (cuuint32_t)(halo ? th + 2 : th), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&tp.amap[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(S.ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -471,6 +545,7 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
     ctot += s2d ? S.C / 4 : S.C;
   }
   for (int s = p->nsrc; s < TC_MAX_SRC; ++s) tp.amap[s] = tp.amap[0];
+  tp.ctot = ctot;
   const int taps = p->KH * p->KW;
   const int K = taps * ctot;
   {
@@ -483,26 +558,39 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return FBANET_E_BADSHAPE;
   }
-  // K-step table in weight order: k = (tap * Ctot + concat channel)
   int ns = 0;
-  for (int tap = 0; tap < taps; ++tap) {
-    const int ky = tap / p->KW, kx = tap % p->KW;
-    for (int s = 0; s < p->nsrc; ++s) {
-      const int cc = s2d ? p->src[s].C / 4 : p->src[s].C;
-      for (int c0 = 0; c0 < cc; c0 += TC_BK) {
-        KStep& st = tp.steps[ns++];
-        st.src = (int16_t)s;
-        if (s2d) {
-          // input row 2y-1+ky = 2*(y+dy) + ys ; s2d channel block (ys*2+xs)*cc
-          const int ry = ky - 1, rx = kx - 1;
-          const int ys = ry & 1, xs = rx & 1;
-          st.dy = (int16_t)((ry - ys) / 2);
-          st.dx = (int16_t)((rx - xs) / 2);
-          st.c0 = (int16_t)((ys * 2 + xs) * cc + c0);
-        } else {
-          st.dy = (int16_t)(ky - p->pad);
-          st.dx = (int16_t)(kx - p->pad);
-          st.c0 = (int16_t)c0;
+  if (halo) {
+    // chunk table: (source, channel offset); the 9 taps of a chunk re-use its halo boxes
+    int nch = 0, cg = 0;
+    for (int s = 0; s < p->nsrc; ++s)
+      for (int c0 = 0; c0 < p->src[s].C; c0 += TC_BK) {
+        Chunk& ch = tp.chunks[nch++];
+        ch.src = (int16_t)s; ch.c0 = (int16_t)c0; ch.cg = cg;
+        cg += TC_BK;
+      }
+    tp.nchunks = nch;
+    ns = nch * 9;
+  } else {
+    // K-step table in weight order: k = (tap * Ctot + concat channel)
+    for (int tap = 0; tap < taps; ++tap) {
+      const int ky = tap / p->KW, kx = tap % p->KW;
+      for (int s = 0; s < p->nsrc; ++s) {
+        const int cc = s2d ? p->src[s].C / 4 : p->src[s].C;
+        for (int c0 = 0; c0 < cc; c0 += TC_BK) {
+          KStep& st = tp.steps[ns++];
+          st.src = (int16_t)s;
+          if (s2d) {
+            // input row 2y-1+ky = 2*(y+dy) + ys ; s2d channel block (ys*2+xs)*cc
+            const int ry = ky - 1, rx = kx - 1;
+            const int ys = ry & 1, xs = rx & 1;
+            st.dy = (int16_t)((ry - ys) / 2);
+            st.dx = (int16_t)((rx - xs) / 2);
+            st.c0 = (int16_t)((ys * 2 + xs) * cc + c0);
+          } else {
+            st.dy = (int16_t)(ky - p->pad);
+            st.dx = (int16_t)(kx - p->pad);
+            st.c0 = (int16_t)c0;
+          }
         }
       }
     }
@@ -513,12 +601,27 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   tp.res_img_stride = p->res_img_stride; tp.out_img_stride = p->out_img_stride; tp.base_img_stride = p->base_img_stride;
   tp.act = p->act; tp.store_mode = p->store_mode; tp.res_ld = p->res_ld; tp.out_ld = p->out_ld;
 
-  const int stage_bytes = TC_A_BYTES + tp.BN * TC_BK * 2;
-  int stages = (196 * 1024) / stage_bytes;
-  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-  if (stages > ns * 2) stages = ns * 2 < 2 ? 2 : ns * 2;
-  tp.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  // shared-memory plan: A ring + B ring (or all B slabs resident when they fit)
+  const int budget = 198 * 1024;
+  const int b_bytes = tp.BN * TC_BK * 2;
+  tp.a_slot_bytes = halo ? TC_HALO_SLOT : TC_A_BYTES;
+  const int a_min = halo ? 2 : 3;
+  const int units = halo ? tp.nchunks : ns;
+  if ((int64_t)ns * b_bytes + (int64_t)a_min * tp.a_slot_bytes <= budget) {
+    tp.b_resident = 1;
+    tp.b_slots = ns;
+    int a = (budget - ns * b_bytes) / tp.a_slot_bytes;
+    tp.a_slots = a > TC_MAX_A_SLOTS ? TC_MAX_A_SLOTS : a;
+  } else {
+    tp.b_resident = 0;
+    tp.a_slots = halo ? 2 : 4;
+    int b = (budget - tp.a_slots * tp.a_slot_bytes) / b_bytes;
+    if (b > 8) b = 8;
+    if (b < 2) return FBANET_E_UNSUPPORTED;
+    tp.b_slots = b;
+  }
+  if (tp.a_slots > units * 2 && units * 2 >= 2) tp.a_slots = units * 2;
+  const size_t smem = (size_t)tp.a_slots * tp.a_slot_bytes + (size_t)tp.b_slots * b_bytes + 1024;
 
   static size_t smem_opted_in = 0;  // opt-in limit is per function; raise it only when a launch needs more
   if (smem > smem_opted_in) {
@@ -529,8 +632,12 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = tp.total_tiles < sms ? tp.total_tiles : sms;
-  conv_gemm_tcgen05_kernel<<<grid, 256, smem, stream>>>(tp);
+  // persistent grid: a multiple of n_tiles_n (each CTA owns one N-tile), at most one CTA per SM
+  int per_n = sms / tp.n_tiles_n;
+  if (per_n < 1) per_n = 1;
+  if (per_n > tp.m_tiles) per_n = tp.m_tiles;
+  const int grid = per_n * tp.n_tiles_n;
+  conv_gemm_tcgen05_kernel<<<grid, TC_NUM_THREADS, smem, stream>>>(tp);
   return check_launch();
 }
 
