@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libfbanet_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -66,6 +66,13 @@ class S2dParams(C.Structure):
     ]
 
 
+class HeadConvParams(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("dst", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p), ("dtype", C.c_int32),
+        ("frames", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cout", C.c_int32),
+    ]
+
+
 class LayerNormParams(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("y", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("rows", C.c_int64),
@@ -106,13 +113,13 @@ class TileParams(C.Structure):
 
 STRUCTS = {
     "fbanet_src": Src, "fbanet_conv_params": ConvParams, "fbanet_warp_params": WarpParams,
-    "fbanet_to_nhwc_params": ToNhwcParams, "fbanet_s2d_params": S2dParams, "fbanet_layernorm_params": LayerNormParams, "fbanet_attn_params": AttnParams,
+    "fbanet_to_nhwc_params": ToNhwcParams, "fbanet_s2d_params": S2dParams, "fbanet_head_conv_params": HeadConvParams, "fbanet_layernorm_params": LayerNormParams, "fbanet_attn_params": AttnParams,
     "fbanet_dwconv_params": DwconvParams, "fbanet_faf_gate_params": FafGateParams, "fbanet_tile_params": TileParams,
 }
 
 # every symbol include/fbanet_b200.h declares
 OPS = {
-    "fbanet_warp_sm100": WarpParams, "fbanet_to_nhwc_sm100": ToNhwcParams, "fbanet_space_to_depth_sm100": S2dParams, "fbanet_conv_gemm_sm100": ConvParams,
+    "fbanet_warp_sm100": WarpParams, "fbanet_to_nhwc_sm100": ToNhwcParams, "fbanet_space_to_depth_sm100": S2dParams, "fbanet_head_conv_sm100": HeadConvParams, "fbanet_conv_gemm_sm100": ConvParams,
     "fbanet_layernorm_sm100": LayerNormParams, "fbanet_window_attention_sm100": AttnParams, "fbanet_dwconv3x3_sm100": DwconvParams,
     "fbanet_faf_gate_sm100": FafGateParams, "fbanet_tile_divide_sm100": TileParams, "fbanet_tile_merge_sm100": TileParams,
 }

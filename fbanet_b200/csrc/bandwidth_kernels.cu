@@ -107,6 +107,75 @@ __global__ void __launch_bounds__(256) im2col3x3_bf16_kernel(const fbanet_to_nhw
   }
 }
 
+// Head conv: one thread = two horizontally adjacent pixels x 64 output channels.  The 3 x 4 x C input
+// patch sits in registers, the [9C][64] weights in shared memory (read as broadcast float4).
+template <typename T, int CIN>
+__global__ void __launch_bounds__(128) head_conv_kernel(const fbanet_head_conv_params p) {
+  constexpr int CO = 64, K = 9 * CIN;
+  __shared__ __align__(16) float ws[K * CO];
+  __shared__ __align__(16) float bs[CO];
+  for (int i = threadIdx.x; i < K * CO; i += blockDim.x) ws[i] = __ldg(p.weight + i);
+  if (threadIdx.x < CO) bs[threadIdx.x] = __ldg(p.bias + threadIdx.x);
+  __syncthreads();
+  const int wp = (p.W + 1) / 2;  // pixel pairs per row
+  const int64_t hw = (int64_t)p.H * p.W;
+  const int64_t total = (int64_t)p.frames * p.H * wp;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int xp = (int)(idx % wp);
+  const int y = (int)((idx / wp) % p.H);
+  const int64_t f = idx / ((int64_t)wp * p.H);
+  const int x0 = xp * 2;
+  float in[3][4][CIN];  // rows y-1..y+1, columns x0-1..x0+2
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int yy = y + r - 1, xx = x0 + c - 1;
+      const bool ok = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+#pragma unroll
+      for (int ch = 0; ch < CIN; ++ch) in[r][c][ch] = ok ? __ldg(p.src + (f * CIN + ch) * hw + (int64_t)yy * p.W + xx) : 0.f;
+    }
+  float a0[CO], a1[CO];
+#pragma unroll
+  for (int j = 0; j < CO; ++j) { a0[j] = bs[j]; a1[j] = bs[j]; }
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int ch = 0; ch < CIN; ++ch) {
+        const float v0 = in[r][c][ch], v1 = in[r][c + 1][ch];
+        const float4* wr = reinterpret_cast<const float4*>(ws + ((r * 3 + c) * CIN + ch) * CO);
+#pragma unroll
+        for (int j = 0; j < CO / 4; ++j) {
+          const float4 w4 = wr[j];
+          a0[4 * j] = fmaf(v0, w4.x, a0[4 * j]); a0[4 * j + 1] = fmaf(v0, w4.y, a0[4 * j + 1]);
+          a0[4 * j + 2] = fmaf(v0, w4.z, a0[4 * j + 2]); a0[4 * j + 3] = fmaf(v0, w4.w, a0[4 * j + 3]);
+          a1[4 * j] = fmaf(v1, w4.x, a1[4 * j]); a1[4 * j + 1] = fmaf(v1, w4.y, a1[4 * j + 1]);
+          a1[4 * j + 2] = fmaf(v1, w4.z, a1[4 * j + 2]); a1[4 * j + 3] = fmaf(v1, w4.w, a1[4 * j + 3]);
+        }
+      }
+  constexpr int V = Vec16<T>::N;
+  T* o = reinterpret_cast<T*>(p.dst) + ((f * p.H + y) * p.W + x0) * CO;
+#pragma unroll
+  for (int j = 0; j < CO; j += V) {
+    float t[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) t[e] = a0[j + e];
+    store_vec<T, V>(o + j, t);
+  }
+  if (x0 + 1 < p.W) {
+#pragma unroll
+    for (int j = 0; j < CO; j += V) {
+      float t[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) t[e] = a1[j + e];
+      store_vec<T, V>(o + CO + j, t);
+    }
+  }
+}
+
 // channels-last view -> space-to-depth(2), one thread per 16-byte vector of the destination
 template <typename T>
 __global__ void __launch_bounds__(256) s2d_kernel(const fbanet_s2d_params p) {
@@ -243,8 +312,15 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const fbanet_dwconv_para
 }
 
 // K7 (bf16 fast path): one thread = 8 channels x a horizontal run of SEG pixels.  The 9x8 weights live in
-// registers for the whole run and a 3x3 window of packed bf16 vectors slides along x, so every output costs
-// three 16-byte loads (one per input row) instead of nine loads plus 80 scalar weight loads.
+// registers for the whole run and a 3x3 window of fp32 columns slides along x (each loaded vector is
+// unpacked once and used for three outputs), so every output costs three 16-byte loads instead of nine
+// loads plus 80 scalar weight loads.  The x loop is unrolled by 3 so the window rotates by renaming.
+__device__ __forceinline__ void unpack8(const uint4& v, float (&o)[8]) {
+  const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { o[2 * i] = __uint_as_float(u[i] << 16); o[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+}
+
 template <int SEG>
 __global__ void __launch_bounds__(128) dwconv3x3_bf16_run_kernel(const fbanet_dwconv_params p) {
   const int cg = p.C / 8;
@@ -279,31 +355,29 @@ __global__ void __launch_bounds__(128) dwconv3x3_bf16_run_kernel(const fbanet_dw
     if (!rok[rr] || xx < 0 || xx >= p.W) return make_uint4(0, 0, 0, 0);
     return *reinterpret_cast<const uint4*>(rows[rr] + (int64_t)xx * p.C);
   };
-  uint4 win[3][3];  // [row][column x-1, x, x+1]
-#pragma unroll
-  for (int rr = 0; rr < 3; ++rr) { win[rr][1] = ld(rr, x_begin - 1); win[rr][2] = ld(rr, x_begin); }
+  float col[3][3][8];   // [column slot][row][channel]; slot (x+1)%3 holds input column x
   uint4 nxt[3];
 #pragma unroll
+  for (int rr = 0; rr < 3; ++rr) { unpack8(ld(rr, x_begin - 1), col[0][rr]); unpack8(ld(rr, x_begin), col[1][rr]); }
+#pragma unroll
   for (int rr = 0; rr < 3; ++rr) nxt[rr] = ld(rr, x_begin + 1);
-  for (int x = x_begin; x < x_end; ++x) {
+
+  auto step = [&](int x, float (&cl)[3][8], float (&cm)[3][8], float (&cr)[3][8]) {
+    // cl = column x-1, cm = column x, cr <- column x+1 (arrives from the prefetch registers)
 #pragma unroll
-    for (int rr = 0; rr < 3; ++rr) { win[rr][0] = win[rr][1]; win[rr][1] = win[rr][2]; win[rr][2] = nxt[rr]; }
+    for (int rr = 0; rr < 3; ++rr) unpack8(nxt[rr], cr[rr]);
 #pragma unroll
-    for (int rr = 0; rr < 3; ++rr) nxt[rr] = ld(rr, x + 2);  // prefetch the column used by the next step
+    for (int rr = 0; rr < 3; ++rr) nxt[rr] = ld(rr, x + 2);
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = bias[j];
 #pragma unroll
     for (int rr = 0; rr < 3; ++rr)
 #pragma unroll
-      for (int cc = 0; cc < 3; ++cc) {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&win[rr][cc]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(h[j]);
-          acc[2 * j] = fmaf(f.x, w[rr * 3 + cc][2 * j], acc[2 * j]);
-          acc[2 * j + 1] = fmaf(f.y, w[rr * 3 + cc][2 * j + 1], acc[2 * j + 1]);
-        }
+      for (int j = 0; j < 8; ++j) {
+        acc[j] = fmaf(cl[rr][j], w[rr * 3 + 0][j], acc[j]);
+        acc[j] = fmaf(cm[rr][j], w[rr * 3 + 1][j], acc[j]);
+        acc[j] = fmaf(cr[rr][j], w[rr * 3 + 2][j], acc[j]);
       }
     if (p.act == FBANET_ACT_GELU_TANH) {
 #pragma unroll
@@ -313,7 +387,15 @@ __global__ void __launch_bounds__(128) dwconv3x3_bf16_run_kernel(const fbanet_dw
       for (int j = 0; j < 8; ++j) acc[j] = apply_act(acc[j], p.act, 0.f);
     }
     store_vec<bf16, 8>(Y + (int64_t)x * p.C, acc);
+  };
+  int x = x_begin;
+  for (; x + 2 < x_end; x += 3) {
+    step(x, col[0], col[1], col[2]);
+    step(x + 1, col[1], col[2], col[0]);
+    step(x + 2, col[2], col[0], col[1]);
   }
+  if (x < x_end) { step(x, col[0], col[1], col[2]); ++x; }
+  if (x < x_end) { step(x, col[1], col[2], col[0]); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -371,8 +453,9 @@ __global__ void __launch_bounds__(256) faf_gate_kernel(const fbanet_faf_gate_par
 }
 
 // K2a (bf16 fast path, C = 64): 8 threads per pixel, each owns 8 channels (one 16-byte vector per tap).
-// The base frame's 3x3 neighbourhood and the 9x8 gate weights stay in registers across the F-1 frames; the
-// centre tap of every frame is re-used for the gated-feature write (pixel-major [B][H][W][F][C]).
+// gate_f = sigmoid(|w.x_f - w.x_0|) with w.x the 3x3x64 dot product (linear, so the base-frame term is
+// computed once); the centre tap of every frame is re-used for the gated-feature write
+// (pixel-major [B][H][W][F][C]).
 __global__ void __launch_bounds__(128) faf_gate_bf16_c64_kernel(const fbanet_faf_gate_params p) {
   constexpr int C = 64;
   const int sub = threadIdx.x & 7;
@@ -384,49 +467,48 @@ __global__ void __launch_bounds__(128) faf_gate_bf16_c64_kernel(const fbanet_faf
   const int y = (int)(pix / p.W), x = (int)(pix % p.W);
   const bf16* feat = reinterpret_cast<const bf16*>(p.feat) + sub * 8;
   float w[9][8];
-  uint4 ref[9];
+  int64_t off[9];
   bool ok[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
     const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
     ok[t] = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+    off[t] = ((int64_t)yy * p.W + xx) * C;
     const float4 a = __ldg(reinterpret_cast<const float4*>(p.wsum + t * C + sub * 8));
     const float4 c = __ldg(reinterpret_cast<const float4*>(p.wsum + t * C + sub * 8 + 4));
     w[t][0] = a.x; w[t][1] = a.y; w[t][2] = a.z; w[t][3] = a.w; w[t][4] = c.x; w[t][5] = c.y; w[t][6] = c.z; w[t][7] = c.w;
-    ref[t] = ok[t] ? *reinterpret_cast<const uint4*>(feat + ((b * p.F) * hw + (int64_t)yy * p.W + xx) * C) : make_uint4(0, 0, 0, 0);
   }
   bf16* gated = p.gated ? reinterpret_cast<bf16*>(p.gated) + ((b * hw + pix) * p.F) * C + sub * 8 : nullptr;
-  if (gated && live) *reinterpret_cast<uint4*>(gated) = ref[4];  // frame 0 passes through (:103)
-  for (int f = 1; f < p.F; ++f) {
+  float s0 = 0.f;
+  for (int f = 0; f < p.F; ++f) {
+    const bf16* fr = feat + (b * p.F + f) * hw * C;
     uint4 v[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-      v[t] = ok[t] ? *reinterpret_cast<const uint4*>(feat + ((b * p.F + f) * hw + (int64_t)yy * p.W + xx) * C) : make_uint4(0, 0, 0, 0);
-    }
+    for (int t = 0; t < 9; ++t) v[t] = ok[t] ? *reinterpret_cast<const uint4*>(fr + off[t]) : make_uint4(0, 0, 0, 0);
     float acc = 0.f;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&v[t]);
-      const __nv_bfloat162* hr = reinterpret_cast<const __nv_bfloat162*>(&ref[t]);
+      float xv[8];
+      unpack8(v[t], xv);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 a = __bfloat1622float2(hv[j]), r = __bfloat1622float2(hr[j]);
-        acc = fmaf(w[t][2 * j], a.x - r.x, acc);
-        acc = fmaf(w[t][2 * j + 1], a.y - r.y, acc);
-      }
+      for (int j = 0; j < 8; ++j) acc = fmaf(w[t][j], xv[j], acc);
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    const float g = 1.0f / (1.0f + __expf(-fabsf(acc)));
+    if (f == 0) {
+      s0 = acc;
+      if (gated && live) *reinterpret_cast<uint4*>(gated) = v[4];  // frame 0 passes through (:103)
+      continue;
+    }
+    const float g = 1.0f / (1.0f + __expf(-fabsf(acc - s0)));
     if (!live) continue;
     if (sub == 0 && p.gate) p.gate[(b * (p.F - 1) + (f - 1)) * hw + pix] = g;
     if (gated) {
-      float o[8];
-      const __nv_bfloat162* hc = reinterpret_cast<const __nv_bfloat162*>(&v[4]);
+      float xv[8], o[8];
+      unpack8(v[4], xv);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { const float2 a = __bfloat1622float2(hc[j]); o[2 * j] = a.x * g; o[2 * j + 1] = a.y * g; }
+      for (int j = 0; j < 8; ++j) o[j] = xv[j] * g;
       store_vec<bf16, 8>(gated + (int64_t)f * C, o);
     }
   }
@@ -511,6 +593,23 @@ extern "C" int fbanet_to_nhwc_sm100(const fbanet_to_nhwc_params* p, void* stream
   return check_launch();
 }
 
+template <typename T>
+static int launch_head(const fbanet_head_conv_params* p, cudaStream_t s) {
+  const int64_t total = (int64_t)p->frames * p->H * ((p->W + 1) / 2);
+  if (p->C == 3) head_conv_kernel<T, 3><<<ceil_div(total, 128), 128, 0, s>>>(*p);
+  else if (p->C == 4) head_conv_kernel<T, 4><<<ceil_div(total, 128), 128, 0, s>>>(*p);
+  else return FBANET_E_BADSHAPE;
+  return check_launch();
+}
+
+extern "C" int fbanet_head_conv_sm100(const fbanet_head_conv_params* p, void* stream) {
+  if (!p || !p->src || !p->dst || !p->weight || !p->bias || p->frames <= 0 || p->Cout != 64) return FBANET_E_BADSHAPE;
+  if ((uintptr_t)p->dst % 16) return FBANET_E_ALIGN;
+  if (p->dtype == FBANET_F32) return launch_head<float>(p, (cudaStream_t)stream);
+  if (p->dtype == FBANET_BF16) return launch_head<bf16>(p, (cudaStream_t)stream);
+  return FBANET_E_DTYPE;
+}
+
 extern "C" int fbanet_space_to_depth_sm100(const fbanet_s2d_params* p, void* stream) {
   if (!p || !p->src || !p->dst || p->N <= 0 || (p->H % 2) || (p->W % 2)) return FBANET_E_BADSHAPE;
   const int v = p->dtype == FBANET_F32 ? 4 : 8;
@@ -562,7 +661,7 @@ extern "C" int fbanet_dwconv3x3_sm100(const fbanet_dwconv_params* p, void* strea
   if (p->dtype == FBANET_F32) dwconv3x3_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
   else if (p->dtype == FBANET_BF16) {
     if (((uintptr_t)p->weight % 16) || ((uintptr_t)p->bias % 16)) return FBANET_E_ALIGN;
-    constexpr int SEG = 16;
+    constexpr int SEG = 20;
     const int64_t threads = (int64_t)p->N * p->H * ((p->W + SEG - 1) / SEG) * (p->C / 8);
     dwconv3x3_bf16_run_kernel<SEG><<<ceil_div(threads, 128), 128, 0, (cudaStream_t)stream>>>(*p);
   } else return FBANET_E_DTYPE;

@@ -155,6 +155,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+// one lane of a fully converged warp; keeps the surrounding control flow warp-uniform so the compiler
+// leaves barrier/descriptor values in uniform registers (a `lane == 0` branch makes it emit
+// ELECT + R2UR waterfall loops around every UTCHMMA / UTMALDG)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
@@ -290,15 +304,15 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
   const int taps = p.halo ? 9 : 1;                   // K-steps served by one A slot
 
   if (warp == 0) {
-    // ================= A producer (TMA) =================
-    if (lane == 0) {
-      int slot = 0;
-      uint32_t phase = 0;
-      for (int mt = mt0; mt < p.m_tiles; mt += mt_step) {
-        const int img = mt / tiles_per_img, r = mt % tiles_per_img;
-        const int y0 = (r / p.tiles_x) * p.th, x0 = (r % p.tiles_x) * p.tw;
-        for (int u = 0; u < units; ++u) {
-          mbar_wait(&a_empty[slot], phase ^ 1);
+    // ================= A producer (TMA); warp-uniform loop, one elected lane issues =================
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int mt = mt0; mt < p.m_tiles; mt += mt_step) {
+      const int img = mt / tiles_per_img, r = mt % tiles_per_img;
+      const int y0 = (r / p.tiles_x) * p.th, x0 = (r % p.tiles_x) * p.tw;
+      for (int u = 0; u < units; ++u) {
+        mbar_wait(&a_empty[slot], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem_a + (size_t)slot * p.a_slot_bytes;
           if (p.halo) {
             const Chunk ch = p.chunks[u];
@@ -310,78 +324,84 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
             mbar_expect_tx(&a_full[slot], (uint32_t)p.a_box_bytes);
             tma_load_4d(sa, &p.amap[ks.src], &a_full[slot], ks.c0, x0 + ks.dx, y0 + ks.dy, img);
           }
-          if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
       }
     }
   } else if (warp == 3) {
     // ================= B producer (TMA): weight slabs [BN x 64] =================
-    if (lane == 0) {
-      auto bk = [&](int s) -> int {   // K offset of K-step s in the packed weights
-        if (!p.halo) return s * TC_BK;
-        const int u = s / 9, t = s - u * 9;
-        return t * p.ctot + p.chunks[u].cg;
-      };
-      if (p.b_resident) {
-        if (mt0 < p.m_tiles)
-          for (int s = 0; s < p.nsteps; ++s) {
+    auto bk = [&](int s) -> int {   // K offset of K-step s in the packed weights
+      if (!p.halo) return s * TC_BK;
+      const int u = s / 9, t = s - u * 9;
+      return t * p.ctot + p.chunks[u].cg;
+    };
+    if (p.b_resident) {
+      if (mt0 < p.m_tiles)
+        for (int s = 0; s < p.nsteps; ++s) {
+          if (elect_one()) {
             mbar_expect_tx(&b_full[s], b_bytes);
             tma_load_2d(smem_b + (size_t)s * b_bytes, &p.bmap, &b_full[s], bk(s), nt * BN);
           }
-      } else {
-        int slot = 0;
-        uint32_t phase = 0;
-        for (int mt = mt0; mt < p.m_tiles; mt += mt_step)
-          for (int s = 0; s < p.nsteps; ++s) {
-            mbar_wait(&b_empty[slot], phase ^ 1);
+          __syncwarp();
+        }
+    } else {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int mt = mt0; mt < p.m_tiles; mt += mt_step)
+        for (int s = 0; s < p.nsteps; ++s) {
+          mbar_wait(&b_empty[slot], phase ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(&b_full[slot], b_bytes);
             tma_load_2d(smem_b + (size_t)slot * b_bytes, &p.bmap, &b_full[slot], bk(s), nt * BN);
-            if (++slot == p.b_slots) { slot = 0; phase ^= 1; }
           }
-      }
+          __syncwarp();
+          if (++slot == p.b_slots) { slot = 0; phase ^= 1; }
+        }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BN);
-      int aslot = 0, bslot = 0;
-      uint32_t aphase = 0, bphase = 0;
-      int it = 0;
-      for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        int s = 0;
-        for (int u = 0; u < units; ++u) {
-          mbar_wait(&a_full[aslot], aphase);
-          const uint32_t sa = smem_u32(smem_a + (size_t)aslot * p.a_slot_bytes);
-          for (int t = 0; t < taps; ++t, ++s) {
-            uint32_t sb;
-            if (p.b_resident) {
-              mbar_wait(&b_full[s], 0);                // completes once, stays complete
-              sb = smem_u32(smem_b + (size_t)s * b_bytes);
-            } else {
-              mbar_wait(&b_full[bslot], bphase);
-              sb = smem_u32(smem_b + (size_t)bslot * b_bytes);
-            }
-            tc_fence_after();
-            // halo mode: tap (ky,kx) reads the dx-shifted copy kx, starting ky rows (1 KB each) down
-            const uint32_t a_addr = p.halo ? sa + (uint32_t)((t % 3) * TC_HALO_COPY + (t / 3) * 1024) : sa;
-            const uint64_t adesc = make_sw128_desc(a_addr), bdesc = make_sw128_desc(sb);
+    // ================= MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma =================
+    const uint32_t idesc = make_idesc_bf16(BN);
+    const uint64_t desc_hi = make_sw128_desc(0);       // descriptor with a zero start address
+    const uint32_t sa0 = smem_u32(smem_a), sb0 = smem_u32(smem_b);
+    int aslot = 0, bslot = 0;
+    uint32_t aphase = 0, bphase = 0;
+    int it = 0;
+    for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);     // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      int s = 0;
+      for (int u = 0; u < units; ++u) {
+        mbar_wait(&a_full[aslot], aphase);
+        const uint32_t sa = sa0 + (uint32_t)aslot * (uint32_t)p.a_slot_bytes;
+        for (int t = 0; t < taps; ++t, ++s) {
+          uint32_t sb;
+          if (p.b_resident) {
+            mbar_wait(&b_full[s], 0);                  // completes once, stays complete
+            sb = sb0 + (uint32_t)s * b_bytes;
+          } else {
+            mbar_wait(&b_full[bslot], bphase);
+            sb = sb0 + (uint32_t)bslot * b_bytes;
+          }
+          tc_fence_after();
+          // halo mode: tap (ky,kx) reads the dx-shifted copy kx, starting ky rows (1 KB each) down
+          const uint32_t a_addr = p.halo ? sa + (uint32_t)((t % 3) * TC_HALO_COPY + (t / 3) * 1024) : sa;
+          const uint64_t adesc = desc_hi + (uint64_t)(a_addr >> 4), bdesc = desc_hi + (uint64_t)(sb >> 4);
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k)       // advance 32 bytes (16 bf16) inside the swizzle row
               umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((s | k) != 0));
-            if (!p.b_resident) {
-              umma_commit(&b_empty[bslot]);
-              if (++bslot == p.b_slots) { bslot = 0; bphase ^= 1; }
-            }
+            if (!p.b_resident) umma_commit(&b_empty[bslot]);
+            if (t == taps - 1) umma_commit(&a_empty[aslot]);                       // frees the A slot when these MMAs retire
+            if (t == taps - 1 && u == units - 1) umma_commit(&tmem_full[acc]);     // accumulator ready for the epilogue
           }
-          umma_commit(&a_empty[aslot]);               // frees the A slot when these MMAs retire
-          if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
+          __syncwarp();
+          if (!p.b_resident) { if (++bslot == p.b_slots) { bslot = 0; bphase ^= 1; } }
         }
-        umma_commit(&tmem_full[acc]);                  // accumulator ready for the epilogue
+        if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
       }
     }
   } else if (warp >= 4) {

@@ -24,19 +24,41 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// NT = number of 8-key tiles (keys padded to 8*NT, a multiple of 16); MT = number of 16-row query tiles
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"((uint32_t)__cvta_generic_to_shared(smem_row)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"((uint32_t)__cvta_generic_to_shared(smem_row)));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+               : "=r"(r[0]), "=r"(r[1])
+               : "r"((uint32_t)__cvta_generic_to_shared(smem_row)));
+}
+
+// NT = number of 8-key tiles (keys padded to 8*NT, a multiple of 16); MT = number of 16-row query tiles.
+// K and V of a window are staged row-major [key][DH+8] with cp.async into a double buffer: the copies for
+// window i+1 are in flight while window i is computed.  Fragments come from ldmatrix (.trans for V).
 template <int DH, int NT, int MT>
 __global__ void __launch_bounds__(MT * 32) window_attention_tc_kernel(const fbanet_attn_params p, const int win_chunk) {
   constexpr int NP = NT * 8;          // padded keys
-  constexpr int KS = DH + 8;          // K row stride (elements): conflict-free fragment loads
-  constexpr int VS = NP + 8;          // V^T row stride
+  constexpr int KS = DH + 8;          // row stride (elements): conflict-free ldmatrix rows
+  constexpr int CPR = DH / 8;         // 16-byte chunks per row
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int win = p.win, N = win * win;
   float* biasS = reinterpret_cast<float*>(smem_attn);                 // [N][NP] bias (+ -inf for padded keys)
-  bf16* Ks = reinterpret_cast<bf16*>(biasS + N * NP);                 // [NP][KS]
-  bf16* Vt = Ks + NP * KS;                                            // [DH][VS]
-  int* tok = reinterpret_cast<int*>(Vt + DH * VS);                    // [NP]
-  int* reg = tok + NP;                                                // [NP]
+  bf16* KV = reinterpret_cast<bf16*>(biasS + N * NP);                 // [2 buffers][K | V][NP][KS]
+  int* tokS = reinterpret_cast<int*>(KV + 4 * NP * KS);               // [2][NP] token index inside the image
+  int* regS = tokS + 2 * NP;                                          // [2][NP] shift-mask region id
 
   const int head = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -45,7 +67,41 @@ __global__ void __launch_bounds__(MT * 32) window_attention_tc_kernel(const fban
   const int total_windows = p.B * nw_img;
   const bf16* qkv = reinterpret_cast<const bf16*>(p.qkv);
 
-  // ---- expand the relative-position bias of this head once ----
+  const int w_begin = blockIdx.x * win_chunk;
+  const int w_end = min(w_begin + win_chunk, total_windows);
+
+  // token / region tables and K,V copies of window `wid` into buffer `buf`
+  auto stage = [&](int wid, int buf) {
+    const int b = wid / nw_img, wl = wid - b * nw_img;
+    const int wy = wl / nwx, wx = wl - wy * nwx;
+    const int64_t img_tok0 = (int64_t)b * p.H * p.W;
+    bf16* Kb = KV + (size_t)buf * 2 * NP * KS;
+    bf16* Vb = Kb + NP * KS;
+    for (int e = tid; e < NP * CPR; e += blockDim.x) {
+      const int j = e / CPR, c = (e - j * CPR) * 8;
+      int tk = 0, rg = 0;
+      if (j < N) {
+        const int iy = j / win, ix = j - iy * win;
+        const int ys = wy * win + iy, xs = wx * win + ix;
+        int y = ys + p.shift, x = xs + p.shift;
+        if (y >= p.H) y -= p.H;
+        if (x >= p.W) x -= p.W;
+        tk = y * p.W + x;
+        rg = p.shift > 0 ? shift_region_tc(ys, p.H, win, p.shift) * 3 + shift_region_tc(xs, p.W, win, p.shift) : 0;
+        const bf16* row = qkv + (img_tok0 + tk) * p.qkv_ld + head * DH + c;
+        cp_async16(Kb + j * KS + c, row + p.C);
+        cp_async16(Vb + j * KS + c, row + 2 * p.C);
+      } else {
+        *reinterpret_cast<uint4*>(Kb + j * KS + c) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(Vb + j * KS + c) = make_uint4(0, 0, 0, 0);
+      }
+      if (c == 0) { tokS[buf * NP + j] = tk; regS[buf * NP + j] = rg; }
+    }
+    cp_async_commit();
+  };
+
+  if (w_begin < w_end) stage(w_begin, 0);
+  // ---- expand the relative-position bias of this head once (overlaps the first copies) ----
   for (int e = tid; e < N * NP; e += blockDim.x) {
     const int i = e / NP, j = e - i * NP;
     float b = -1e30f;
@@ -56,43 +112,20 @@ __global__ void __launch_bounds__(MT * 32) window_attention_tc_kernel(const fban
     biasS[e] = b;
   }
 
-  const int w_begin = blockIdx.x * win_chunk;
-  const int w_end = min(w_begin + win_chunk, total_windows);
   for (int wid = w_begin; wid < w_end; ++wid) {
+    const int buf = (wid - w_begin) & 1;
+    cp_async_wait_all();
+    __syncthreads();  // window `wid` staged; every warp is done with the other buffer
+    if (wid + 1 < w_end) stage(wid + 1, buf ^ 1);
+
     const int b = wid / nw_img, wl = wid - b * nw_img;
     const int wy = wl / nwx, wx = wl - wy * nwx;
     const int64_t img_tok0 = (int64_t)b * p.H * p.W;
     const bool masked = p.shift > 0 && (wy == nwy - 1 || wx == nwx - 1);
-    __syncthreads();  // previous window fully consumed (and biasS visible on the first trip)
-    for (int i = tid; i < NP; i += blockDim.x) {
-      int tk = 0, rg = 0;
-      if (i < N) {
-        const int iy = i / win, ix = i - iy * win;
-        const int ys = wy * win + iy, xs = wx * win + ix;
-        const int y = (ys + p.shift) % p.H, x = (xs + p.shift) % p.W;
-        tk = y * p.W + x;
-        rg = p.shift > 0 ? shift_region_tc(ys, p.H, win, p.shift) * 3 + shift_region_tc(xs, p.W, win, p.shift) : 0;
-      }
-      tok[i] = tk;
-      reg[i] = rg;
-    }
-    __syncthreads();
-    // ---- K -> Ks[key][ch], V -> Vt[ch][key]; 16-byte global loads ----
-    constexpr int VEC = 8, CPR = DH / VEC;  // 16-byte chunks per row
-    for (int e = tid; e < NP * CPR; e += blockDim.x) {
-      const int j = e / CPR, c = (e - j * CPR) * VEC;
-      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-      if (j < N) {
-        const bf16* row = qkv + (img_tok0 + tok[j]) * p.qkv_ld + head * DH + c;
-        kv = *reinterpret_cast<const uint4*>(row + p.C);
-        vv = *reinterpret_cast<const uint4*>(row + 2 * p.C);
-      }
-      *reinterpret_cast<uint4*>(Ks + j * KS + c) = kv;
-      const bf16* ve = reinterpret_cast<const bf16*>(&vv);
-#pragma unroll
-      for (int u = 0; u < VEC; ++u) Vt[(c + u) * VS + j] = ve[u];
-    }
-    __syncthreads();
+    const bf16* Kb = KV + (size_t)buf * 2 * NP * KS;
+    const bf16* Vb = Kb + NP * KS;
+    const int* tok = tokS + buf * NP;
+    const int* reg = regS + buf * NP;
 
     // ---- this warp's 16 query rows ----
     const int r0 = warp * 16 + g, r1 = r0 + 8;
@@ -104,41 +137,39 @@ __global__ void __launch_bounds__(MT * 32) window_attention_tc_kernel(const fban
 #pragma unroll
       for (int kk = 0; kk < DH / 16; ++kk) {
         const int c = kk * 16 + 2 * t;
-        const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
-        __nv_bfloat162 x00 = v0 ? *reinterpret_cast<const __nv_bfloat162*>(q0 + c) : z;
-        __nv_bfloat162 x10 = v1 ? *reinterpret_cast<const __nv_bfloat162*>(q1 + c) : z;
-        __nv_bfloat162 x01 = v0 ? *reinterpret_cast<const __nv_bfloat162*>(q0 + c + 8) : z;
-        __nv_bfloat162 x11 = v1 ? *reinterpret_cast<const __nv_bfloat162*>(q1 + c + 8) : z;
-        qa[kk][0] = *reinterpret_cast<uint32_t*>(&x00);
-        qa[kk][1] = *reinterpret_cast<uint32_t*>(&x10);
-        qa[kk][2] = *reinterpret_cast<uint32_t*>(&x01);
-        qa[kk][3] = *reinterpret_cast<uint32_t*>(&x11);
+        qa[kk][0] = v0 ? *reinterpret_cast<const uint32_t*>(q0 + c) : 0u;
+        qa[kk][1] = v1 ? *reinterpret_cast<const uint32_t*>(q1 + c) : 0u;
+        qa[kk][2] = v0 ? *reinterpret_cast<const uint32_t*>(q0 + c + 8) : 0u;
+        qa[kk][3] = v1 ? *reinterpret_cast<const uint32_t*>(q1 + c + 8) : 0u;
       }
     }
-    // S = q k^T  (scale applied afterwards in fp32: (q.k)*scale == (q*scale).k up to rounding of the product)
+    // S = q k^T  (scale applied afterwards in fp32).  One ldmatrix.x4 = B fragments of two key tiles.
     float s[NT][4];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; nt += 2) {
 #pragma unroll
       for (int kk = 0; kk < DH / 16; ++kk) {
-        uint32_t bfrag[2];
-        const bf16* kp = Ks + (nt * 8 + g) * KS + kk * 16 + 2 * t;
-        bfrag[0] = *reinterpret_cast<const uint32_t*>(kp);
-        bfrag[1] = *reinterpret_cast<const uint32_t*>(kp + 8);
-        mma_bf16_16816(s[nt], qa[kk], bfrag);
+        // matrices: (keys nt*8.., ch kk*16..+7), (same keys, ch +8), (keys (nt+1)*8.., ch ..+7), (.., ch +8)
+        uint32_t kb[4];
+        const int mi = lane >> 3;
+        ldmatrix_x4(kb, Kb + ((nt + (mi >> 1)) * 8 + (lane & 7)) * KS + kk * 16 + (mi & 1) * 8);
+        const uint32_t b0[2] = {kb[0], kb[1]}, b1[2] = {kb[2], kb[3]};
+        mma_bf16_16816(s[nt], qa[kk], b0);
+        mma_bf16_16816(s[nt + 1], qa[kk], b1);
       }
     }
     // + bias (+ mask), row max
-    const float* b0 = biasS + (v0 ? r0 : 0) * NP;
-    const float* b1 = biasS + (v1 ? r1 : 0) * NP;
+    const float* bb0p = biasS + (v0 ? r0 : 0) * NP;
+    const float* bb1p = biasS + (v1 ? r1 : 0) * NP;
     const int rg0 = reg[v0 ? r0 : 0], rg1 = reg[v1 ? r1 : 0];
     float m0 = -1e30f, m1 = -1e30f;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       const int j = nt * 8 + 2 * t;
-      const float2 bb0 = *reinterpret_cast<const float2*>(b0 + j);
-      const float2 bb1 = *reinterpret_cast<const float2*>(b1 + j);
+      const float2 bb0 = *reinterpret_cast<const float2*>(bb0p + j);
+      const float2 bb1 = *reinterpret_cast<const float2*>(bb1p + j);
       s[nt][0] = fmaf(s[nt][0], p.scale, bb0.x);
       s[nt][1] = fmaf(s[nt][1], p.scale, bb0.y);
       s[nt][2] = fmaf(s[nt][2], p.scale, bb1.x);
@@ -173,7 +204,7 @@ __global__ void __launch_bounds__(MT * 32) window_attention_tc_kernel(const fban
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    // O = P v
+    // O = P v ; V fragments via ldmatrix.trans from the row-major [key][ch] tile
     float o[DH / 8][4];
 #pragma unroll
     for (int dn = 0; dn < DH / 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
@@ -185,12 +216,14 @@ __global__ void __launch_bounds__(MT * 32) window_attention_tc_kernel(const fban
       pa[2] = pack_bf16(s[2 * ks + 1][0], s[2 * ks + 1][1]);
       pa[3] = pack_bf16(s[2 * ks + 1][2], s[2 * ks + 1][3]);
 #pragma unroll
-      for (int dn = 0; dn < DH / 8; ++dn) {
-        uint32_t bfrag[2];
-        const bf16* vp = Vt + (dn * 8 + g) * VS + ks * 16 + 2 * t;
-        bfrag[0] = *reinterpret_cast<const uint32_t*>(vp);
-        bfrag[1] = *reinterpret_cast<const uint32_t*>(vp + 8);
-        mma_bf16_16816(o[dn], pa, bfrag);
+      for (int dn = 0; dn < DH / 8; dn += 2) {
+        // matrices: (keys 16ks..+7, ch dn*8), (keys +8.., ch dn*8), (keys 16ks.., ch (dn+1)*8), (keys +8.., ch (dn+1)*8)
+        uint32_t vb[4];
+        const int mi = lane >> 3;
+        ldmatrix_x4_trans(vb, Vb + (ks * 16 + (mi & 1) * 8 + (lane & 7)) * KS + (dn + (mi >> 1)) * 8);
+        const uint32_t b0[2] = {vb[0], vb[1]}, b1[2] = {vb[2], vb[3]};
+        mma_bf16_16816(o[dn], pa, b0);
+        mma_bf16_16816(o[dn + 1], pa, b1);
       }
     }
     const float i0 = 1.f / l0, i1 = 1.f / l1;
@@ -206,13 +239,14 @@ __global__ void __launch_bounds__(MT * 32) window_attention_tc_kernel(const fban
       for (int dn = 0; dn < DH / 8; ++dn) *reinterpret_cast<__nv_bfloat162*>(op + dn * 8) = __floats2bfloat162_rn(o[dn][2] * i1, o[dn][3] * i1);
     }
   }
+  cp_async_wait_all();
 }
 
 template <int DH, int NT, int MT>
 static int launch_tc(const fbanet_attn_params* p, cudaStream_t s) {
   constexpr int NP = NT * 8;
   const int N = p->win * p->win;
-  const size_t smem = (size_t)N * NP * 4 + (size_t)NP * (DH + 8) * 2 + (size_t)DH * (NP + 8) * 2 + 2 * NP * 4;
+  const size_t smem = (size_t)N * NP * 4 + (size_t)4 * NP * (DH + 8) * 2 + (size_t)4 * NP * 4;
   auto kern = window_attention_tc_kernel<DH, NT, MT>;
   static size_t opted = 0;
   if (smem > opted) {

@@ -257,7 +257,11 @@ class BaseModel(nn.Module):
             P[name + ".w"] = m.weight.detach().to(T).contiguous()
             P[name + ".b"] = f32(m.bias)
 
-        if tc:  # head conv as a K=64 1x1 GEMM over the im2col'd burst (ops.to_nhwc(im2col3x3=True))
+        if tc and self.embed_dim == 64 and self.in_channels in (3, 4):
+            # head conv (K = 9*C_in, store-bound) runs on the CUDA cores straight from the planar burst
+            P["head.wkc"] = self.head.weight.detach().float().permute(2, 3, 1, 0).reshape(-1, self.embed_dim).contiguous()
+            P["head.b"] = f32(self.head.bias)
+        elif tc:  # head conv as a K=64 1x1 GEMM over the im2col'd burst (ops.to_nhwc(im2col3x3=True))
             w = self.head.weight.detach().float().permute(0, 2, 3, 1).reshape(self.embed_dim, -1)
             P["head.w"] = torch.nn.functional.pad(w, (0, 64 - w.shape[1])).to(T).contiguous()
             P["head.b"] = f32(self.head.bias)
@@ -463,7 +467,9 @@ class BaseModel(nn.Module):
         B, Fr, Cin, S, _ = x.shape
         E, T = self.embed_dim, self.compute_dtype
         cin_pad = 4 if T == torch.float32 else 8
-        if self._use_tc():
+        if "head.wkc" in P:
+            f = ops.head_conv(x.view(B * Fr, Cin, S, S), P["head.wkc"], P["head.b"], T)  # :255
+        elif self._use_tc():
             xn = ops.to_nhwc(x.view(B * Fr, Cin, S, S), 64, T, im2col3x3=True)
             f = ops.conv_gemm([xn], P["head.w"], self._new(B * Fr, S, S, E), bias=P["head.b"], impl=self.impl, alg_cin=9 * Cin)  # :255
         else:

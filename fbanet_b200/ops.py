@@ -199,6 +199,21 @@ def to_nhwc(x: torch.Tensor, cp: int, dtype: torch.dtype, im2col3x3: bool = Fals
     return out
 
 
+def head_conv(x: torch.Tensor, weight_kc: torch.Tensor, bias: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """3x3 pad-1 conv from the planar fp32 burst ``[frames,C,H,W]`` to channels-last ``[frames,H,W,64]``;
+    ``weight_kc`` is fp32 ``[9*C, 64]`` (k = (ky*3+kx)*C + c)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    Fr, Cc, H, W = x.shape
+    cout = weight_kc.shape[1]
+    assert weight_kc.dtype == torch.float32 and weight_kc.is_contiguous() and weight_kc.shape[0] == 9 * Cc
+    out = torch.empty((Fr, H, W, cout), device=x.device, dtype=dtype)
+    p = L.HeadConvParams()
+    p.src, p.dst, p.weight, p.bias, p.dtype = x.data_ptr(), out.data_ptr(), weight_kc.data_ptr(), bias.data_ptr(), _DT[dtype]
+    p.frames, p.C, p.H, p.W, p.Cout = Fr, Cc, H, W, cout
+    _call("fbanet_head_conv_sm100", p)
+    return out
+
+
 def space_to_depth(x: torch.Tensor) -> torch.Tensor:
     """channels-last view ``[N,H,W,C]`` -> contiguous ``[N,H/2,W/2,4C]``, channel ``(ys*2+xs)*C + c``."""
     ptr, Cc, ld, istr = _cl(x)

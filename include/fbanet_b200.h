@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 4
+#define FBANET_ABI_VERSION 5
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -130,6 +130,19 @@ typedef struct fbanet_to_nhwc_params {
   int32_t _pad;
 } fbanet_to_nhwc_params;
 
+/* Head conv (models/fba_net.py:88,255): 3x3 pad 1 straight from the planar fp32 burst [frames][C][H][W]
+ * (C = 3 RGB / 4 RAW) to channels-last [frames][H][W][Cout], Cout = 64.  K = 9*C is too shallow for the
+ * tensor cores and the op is store-bound, so it is a CUDA-core kernel (fp32 FMA, fp32 accumulate).
+ * weight: fp32 [9*C][Cout] with k = (ky*3+kx)*C + c. */
+typedef struct fbanet_head_conv_params {
+  const float* src;
+  void* dst;
+  const float* weight;
+  const float* bias;
+  int32_t dtype;          /* of dst */
+  int32_t frames, C, H, W, Cout;
+} fbanet_head_conv_params;
+
 /* channels-last view [N,H,W,C] -> contiguous [N,H/2,W/2,4C], channel (ys*2+xs)*C + c = src(2y+ys, 2x+xs, c).
  * Feeds the 4x4 stride-2 downsampling convs (layers/downsample_flatten.py:6-13) to the TMA/tcgen05 path. */
 typedef struct fbanet_s2d_params {
@@ -218,6 +231,7 @@ int fbanet_conv_gemm_tcgen05_supported(const fbanet_conv_params* p);
 int fbanet_warp_sm100(const fbanet_warp_params* p, void* stream);
 int fbanet_to_nhwc_sm100(const fbanet_to_nhwc_params* p, void* stream);
 int fbanet_space_to_depth_sm100(const fbanet_s2d_params* p, void* stream);
+int fbanet_head_conv_sm100(const fbanet_head_conv_params* p, void* stream);
 int fbanet_conv_gemm_sm100(const fbanet_conv_params* p, void* stream);
 int fbanet_layernorm_sm100(const fbanet_layernorm_params* p, void* stream);
 int fbanet_window_attention_sm100(const fbanet_attn_params* p, void* stream);

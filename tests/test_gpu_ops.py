@@ -302,3 +302,17 @@ def test_tile_divide_merge(cuda):
     out = torch.zeros(Cc, 4 * H, 4 * W, device=cuda)
     ops.tile_merge(sr.to(cuda), out, H, W, ps, ov, 4)
     assert torch.equal(out.cpu(), refm[0])
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("cin,hw", [(3, (21, 33)), (4, (16, 16))])
+def test_head_conv_direct(cuda, dt, cin, hw):
+    """models/fba_net.py:255 head conv straight from the planar burst (CUDA-core kernel)."""
+    from fbanet_b200 import ops
+    H, W = hw
+    x = torch.rand(5, cin, H, W, generator=torch.Generator().manual_seed(1))
+    w, b = _r(torch.float32, 64, cin, 3, 3, seed=2, scale=0.2), _r(torch.float32, 64, seed=3)
+    ref = F.conv2d(x, w, b, padding=1)
+    wkc = w.permute(2, 3, 1, 0).reshape(9 * cin, 64).contiguous()
+    out = ops.head_conv(x.to(cuda), wkc.to(cuda), b.to(cuda), dt)
+    _close(out.permute(0, 3, 1, 2), ref, dt)
