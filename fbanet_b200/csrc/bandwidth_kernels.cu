@@ -1,5 +1,7 @@
 // HBM-bound kernels of the BaseModel forward: homography warp (K1), layout conversion, LayerNorm (K8),
 // LeFF depthwise 3x3 + GELU (K7), FAF gate (K2a), full-size tile divide/merge (8f-1).
+#include <string.h>
+
 #include "common.cuh"
 
 namespace fbanet {
@@ -321,14 +323,26 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&o)[8]) {
   for (int i = 0; i < 4; ++i) { o[2 * i] = __uint_as_float(u[i] << 16); o[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
 }
 
-template <int SEG>
+template <int V> struct PackV;
+template <> struct PackV<8> { typedef uint4 type; };
+template <> struct PackV<4> { typedef uint2 type; };
+__device__ __forceinline__ void unpackv(const uint2& v, float (&o)[4]) {
+  o[0] = __uint_as_float(v.x << 16); o[1] = __uint_as_float(v.x & 0xffff0000u);
+  o[2] = __uint_as_float(v.y << 16); o[3] = __uint_as_float(v.y & 0xffff0000u);
+}
+__device__ __forceinline__ void unpackv(const uint4& v, float (&o)[8]) { unpack8(v, o); }
+
+// V = channels per thread (4: ~110 registers, 16+ resident warps/SM; the loads of the next TWO columns
+// are in flight while a column is computed)
+template <int SEG, int V>
 __global__ void __launch_bounds__(128) dwconv3x3_bf16_run_kernel(const fbanet_dwconv_params p) {
-  const int cg = p.C / 8;
+  typedef typename PackV<V>::type PV;
+  const int cg = p.C / V;
   const int segs = (p.W + SEG - 1) / SEG;
   const int64_t total = (int64_t)p.N * p.H * segs * cg;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int c0 = (int)(idx % cg) * 8;
+  const int c0 = (int)(idx % cg) * V;
   int64_t r = idx / cg;
   const int seg = (int)(r % segs); r /= segs;
   const int y = (int)(r % p.H);
@@ -337,56 +351,59 @@ __global__ void __launch_bounds__(128) dwconv3x3_bf16_run_kernel(const fbanet_dw
   const bf16* X = reinterpret_cast<const bf16*>(p.x) + n * (int64_t)p.H * p.W * p.C + c0;
   bf16* Y = reinterpret_cast<bf16*>(p.y) + (n * (int64_t)p.H + y) * p.W * p.C + c0;
 
-  float w[9][8], bias[8];
+  float w[9][V], bias[V];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p.weight + t * p.C + c0));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p.weight + t * p.C + c0 + 4));
-    w[t][0] = a.x; w[t][1] = a.y; w[t][2] = a.z; w[t][3] = a.w; w[t][4] = b.x; w[t][5] = b.y; w[t][6] = b.z; w[t][7] = b.w;
-  }
-  {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4));
-    bias[0] = a.x; bias[1] = a.y; bias[2] = a.z; bias[3] = a.w; bias[4] = b.x; bias[5] = b.y; bias[6] = b.z; bias[7] = b.w;
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < V; j += 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p.weight + t * p.C + c0 + j));
+      w[t][j] = a.x; w[t][j + 1] = a.y; w[t][j + 2] = a.z; w[t][j + 3] = a.w;
+    }
+#pragma unroll
+  for (int j = 0; j < V; j += 4) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+    bias[j] = a.x; bias[j + 1] = a.y; bias[j + 2] = a.z; bias[j + 3] = a.w;
   }
   const bool rok[3] = {y - 1 >= 0, true, y + 1 < p.H};
   const bf16* rows[3] = {X + (int64_t)(y - 1) * p.W * p.C, X + (int64_t)y * p.W * p.C, X + (int64_t)(y + 1) * p.W * p.C};
-  auto ld = [&](int rr, int xx) -> uint4 {
-    if (!rok[rr] || xx < 0 || xx >= p.W) return make_uint4(0, 0, 0, 0);
-    return *reinterpret_cast<const uint4*>(rows[rr] + (int64_t)xx * p.C);
+  auto ld = [&](int rr, int xx) -> PV {
+    PV z;
+    memset(&z, 0, sizeof(z));
+    if (!rok[rr] || xx < 0 || xx >= p.W) return z;
+    return *reinterpret_cast<const PV*>(rows[rr] + (int64_t)xx * p.C);
   };
-  float col[3][3][8];   // [column slot][row][channel]; slot (x+1)%3 holds input column x
-  uint4 nxt[3];
+  float col[3][3][V];   // [column slot][row][channel]
+  PV nxa[3], nxb[3];    // columns x+1 and x+2 in flight
 #pragma unroll
-  for (int rr = 0; rr < 3; ++rr) { unpack8(ld(rr, x_begin - 1), col[0][rr]); unpack8(ld(rr, x_begin), col[1][rr]); }
+  for (int rr = 0; rr < 3; ++rr) { unpackv(ld(rr, x_begin - 1), col[0][rr]); unpackv(ld(rr, x_begin), col[1][rr]); }
 #pragma unroll
-  for (int rr = 0; rr < 3; ++rr) nxt[rr] = ld(rr, x_begin + 1);
+  for (int rr = 0; rr < 3; ++rr) { nxa[rr] = ld(rr, x_begin + 1); nxb[rr] = ld(rr, x_begin + 2); }
 
-  auto step = [&](int x, float (&cl)[3][8], float (&cm)[3][8], float (&cr)[3][8]) {
+  auto step = [&](int x, float (&cl)[3][V], float (&cm)[3][V], float (&cr)[3][V]) {
     // cl = column x-1, cm = column x, cr <- column x+1 (arrives from the prefetch registers)
 #pragma unroll
-    for (int rr = 0; rr < 3; ++rr) unpack8(nxt[rr], cr[rr]);
+    for (int rr = 0; rr < 3; ++rr) { unpackv(nxa[rr], cr[rr]); nxa[rr] = nxb[rr]; }
 #pragma unroll
-    for (int rr = 0; rr < 3; ++rr) nxt[rr] = ld(rr, x + 2);
-    float acc[8];
+    for (int rr = 0; rr < 3; ++rr) nxb[rr] = ld(rr, x + 3);
+    float acc[V];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bias[j];
+    for (int j = 0; j < V; ++j) acc[j] = bias[j];
 #pragma unroll
     for (int rr = 0; rr < 3; ++rr)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < V; ++j) {
         acc[j] = fmaf(cl[rr][j], w[rr * 3 + 0][j], acc[j]);
         acc[j] = fmaf(cm[rr][j], w[rr * 3 + 1][j], acc[j]);
         acc[j] = fmaf(cr[rr][j], w[rr * 3 + 2][j], acc[j]);
       }
     if (p.act == FBANET_ACT_GELU_TANH) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = gelu_tanh_fast(acc[j]);
+      for (int j = 0; j < V; ++j) acc[j] = gelu_tanh_fast(acc[j]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = apply_act(acc[j], p.act, 0.f);
+      for (int j = 0; j < V; ++j) acc[j] = apply_act(acc[j], p.act, 0.f);
     }
-    store_vec<bf16, 8>(Y + (int64_t)x * p.C, acc);
+    store_vec<bf16, V>(Y + (int64_t)x * p.C, acc);
   };
   int x = x_begin;
   for (; x + 2 < x_end; x += 3) {
@@ -661,9 +678,9 @@ extern "C" int fbanet_dwconv3x3_sm100(const fbanet_dwconv_params* p, void* strea
   if (p->dtype == FBANET_F32) dwconv3x3_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
   else if (p->dtype == FBANET_BF16) {
     if (((uintptr_t)p->weight % 16) || ((uintptr_t)p->bias % 16)) return FBANET_E_ALIGN;
-    constexpr int SEG = 20;
-    const int64_t threads = (int64_t)p->N * p->H * ((p->W + SEG - 1) / SEG) * (p->C / 8);
-    dwconv3x3_bf16_run_kernel<SEG><<<ceil_div(threads, 128), 128, 0, (cudaStream_t)stream>>>(*p);
+    constexpr int SEG = 20, V = 4;
+    const int64_t threads = (int64_t)p->N * p->H * ((p->W + SEG - 1) / SEG) * (p->C / V);
+    dwconv3x3_bf16_run_kernel<SEG, V><<<ceil_div(threads, 128), 128, 0, (cudaStream_t)stream>>>(*p);
   } else return FBANET_E_DTYPE;
   return check_launch();
 }

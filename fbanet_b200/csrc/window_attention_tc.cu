@@ -19,6 +19,11 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -49,7 +54,7 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], const void* 
 // K and V of a window are staged row-major [key][DH+8] with cp.async into a double buffer: the copies for
 // window i+1 are in flight while window i is computed.  Fragments come from ldmatrix (.trans for V).
 template <int DH, int NT, int MT>
-__global__ void __launch_bounds__(MT * 32) window_attention_tc_kernel(const fbanet_attn_params p, const int win_chunk) {
+__global__ void __launch_bounds__(MT * 32, (DH == 16 && MT == 7) ? 3 : 1) window_attention_tc_kernel(const fbanet_attn_params p, const int win_chunk) {
   constexpr int NP = NT * 8;          // padded keys
   constexpr int KS = DH + 8;          // row stride (elements): conflict-free ldmatrix rows
   constexpr int CPR = DH / 8;         // 16-byte chunks per row
@@ -60,16 +65,27 @@ __global__ void __launch_bounds__(MT * 32) window_attention_tc_kernel(const fban
   int* tokS = reinterpret_cast<int*>(KV + 4 * NP * KS);               // [2][NP] token index inside the image
   int* regS = tokS + 2 * NP;                                          // [2][NP] shift-mask region id
 
-  const int head = blockIdx.y;
+  const int head = blockIdx.x;   // heads fastest: the CTAs sharing a window's token rows run together (L2 reuse)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int nwx = p.W / win, nwy = p.H / win, nw_img = nwx * nwy;
   const int total_windows = p.B * nw_img;
   const bf16* qkv = reinterpret_cast<const bf16*>(p.qkv);
 
-  const int w_begin = blockIdx.x * win_chunk;
+  const int w_begin = blockIdx.y * win_chunk;
   const int w_end = min(w_begin + win_chunk, total_windows);
 
+  // per-thread staging slots are the same for every window: (key j, 16-byte chunk c, in-window y/x)
+  constexpr int SLOTS = (NP * CPR + MT * 32 - 1) / (MT * 32);
+  int sj[SLOTS], sc[SLOTS], siy[SLOTS], six[SLOTS];
+#pragma unroll
+  for (int k = 0; k < SLOTS; ++k) {
+    const int e = tid + k * MT * 32;
+    sj[k] = e / CPR;
+    sc[k] = (e - sj[k] * CPR) * 8;
+    siy[k] = sj[k] / win;
+    six[k] = sj[k] - siy[k] * win;
+  }
   // token / region tables and K,V copies of window `wid` into buffer `buf`
   auto stage = [&](int wid, int buf) {
     const int b = wid / nw_img, wl = wid - b * nw_img;
@@ -77,11 +93,13 @@ __global__ void __launch_bounds__(MT * 32) window_attention_tc_kernel(const fban
     const int64_t img_tok0 = (int64_t)b * p.H * p.W;
     bf16* Kb = KV + (size_t)buf * 2 * NP * KS;
     bf16* Vb = Kb + NP * KS;
-    for (int e = tid; e < NP * CPR; e += blockDim.x) {
-      const int j = e / CPR, c = (e - j * CPR) * 8;
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) {
+      const int j = sj[k], c = sc[k];
+      if (j >= NP) continue;
       int tk = 0, rg = 0;
       if (j < N) {
-        const int iy = j / win, ix = j - iy * win;
+        const int iy = siy[k], ix = six[k];
         const int ys = wy * win + iy, xs = wx * win + ix;
         int y = ys + p.shift, x = xs + p.shift;
         if (y >= p.H) y -= p.H;
@@ -109,8 +127,9 @@ __global__ void __launch_bounds__(MT * 32) window_attention_tc_kernel(const fban
       const int yi = i / win, xi = i - yi * win, yj = j / win, xj = j - yj * win;
       b = __ldg(p.bias_table + ((yi - yj + win - 1) * (2 * win - 1) + (xi - xj + win - 1)) * p.heads + head);
     }
-    biasS[e] = b;
+    biasS[e] = b * 1.4426950408889634f;   // logits are kept in log2 units: exp(x) = 2^(x log2 e)
   }
+  const float scale2 = p.scale * 1.4426950408889634f;
 
   for (int wid = w_begin; wid < w_end; ++wid) {
     const int buf = (wid - w_begin) & 1;
@@ -170,16 +189,17 @@ __global__ void __launch_bounds__(MT * 32) window_attention_tc_kernel(const fban
       const int j = nt * 8 + 2 * t;
       const float2 bb0 = *reinterpret_cast<const float2*>(bb0p + j);
       const float2 bb1 = *reinterpret_cast<const float2*>(bb1p + j);
-      s[nt][0] = fmaf(s[nt][0], p.scale, bb0.x);
-      s[nt][1] = fmaf(s[nt][1], p.scale, bb0.y);
-      s[nt][2] = fmaf(s[nt][2], p.scale, bb1.x);
-      s[nt][3] = fmaf(s[nt][3], p.scale, bb1.y);
+      s[nt][0] = fmaf(s[nt][0], scale2, bb0.x);
+      s[nt][1] = fmaf(s[nt][1], scale2, bb0.y);
+      s[nt][2] = fmaf(s[nt][2], scale2, bb1.x);
+      s[nt][3] = fmaf(s[nt][3], scale2, bb1.y);
       if (masked) {
+        constexpr float M = 100.f * 1.4426950408889634f;
         const int ja = reg[j], jb = reg[j + 1];
-        if (ja != rg0) s[nt][0] -= 100.f;
-        if (jb != rg0) s[nt][1] -= 100.f;
-        if (ja != rg1) s[nt][2] -= 100.f;
-        if (jb != rg1) s[nt][3] -= 100.f;
+        if (ja != rg0) s[nt][0] -= M;
+        if (jb != rg0) s[nt][1] -= M;
+        if (ja != rg1) s[nt][2] -= M;
+        if (jb != rg1) s[nt][3] -= M;
       }
       m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
       m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
@@ -189,14 +209,12 @@ __global__ void __launch_bounds__(MT * 32) window_attention_tc_kernel(const fban
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
     float l0 = 0.f, l1 = 0.f;
-    constexpr float LOG2E = 1.4426950408889634f;
-    const float mm0 = m0 * LOG2E, mm1 = m1 * LOG2E;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      s[nt][0] = exp2f(fmaf(s[nt][0], LOG2E, -mm0));
-      s[nt][1] = exp2f(fmaf(s[nt][1], LOG2E, -mm0));
-      s[nt][2] = exp2f(fmaf(s[nt][2], LOG2E, -mm1));
-      s[nt][3] = exp2f(fmaf(s[nt][3], LOG2E, -mm1));
+      s[nt][0] = ex2_approx(s[nt][0] - m0);
+      s[nt][1] = ex2_approx(s[nt][1] - m0);
+      s[nt][2] = ex2_approx(s[nt][2] - m1);
+      s[nt][3] = ex2_approx(s[nt][3] - m1);
       l0 += s[nt][0] + s[nt][1];
       l1 += s[nt][2] + s[nt][3];
     }
@@ -259,7 +277,7 @@ static int launch_tc(const fbanet_attn_params* p, cudaStream_t s) {
   int chunk = (total_windows * p->heads + 1183) / 1184;
   if (chunk < 4) chunk = 4;
   if (chunk > 32) chunk = 32;
-  dim3 grid((total_windows + chunk - 1) / chunk, p->heads);
+  dim3 grid(p->heads, (total_windows + chunk - 1) / chunk);
   kern<<<grid, MT * 32, smem, s>>>(*p, chunk);
   return check_launch();
 }

@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Micro-benchmarks of the non-GEMM kernels at the cfg2 (batch 64) shapes: window attention, LeFF depthwise
+conv, LayerNorm, FAF gate, head conv.  `--case NAME --reps 1` for ncu captures."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fbanet_b200 import ops, _lib as L  # noqa: E402
+
+BF = torch.bfloat16
+dev = torch.device("cuda:0")
+
+
+def timeit(name, fn, reps, gbytes):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"{name:28s} {ms:8.3f} ms   alg {gbytes:6.2f} GB -> {gbytes / ms:7.2f} TB/s", flush=True)
+
+
+def attn(B, S, C, heads, shift):
+    qkv = (torch.rand(B * S * S, 3 * C, device=dev) - 0.5).to(BF)
+    table = torch.rand(361, heads, device=dev) * 0.1
+    return (lambda: ops.window_attention(qkv, table, B, S, S, heads, 10, shift, (C // heads) ** -0.5)), 2 * B * S * S * 4 * C / 1e9
+
+
+def dw(B, S, C):
+    x = (torch.rand(B, S, S, C, device=dev) - 0.5).to(BF)
+    w, b = torch.rand(9, C, device=dev) - 0.5, torch.rand(C, device=dev)
+    return (lambda: ops.dwconv3x3(x, w, b, L.ACT_GELU_TANH)), 2 * 2 * x.numel() / 1e9
+
+
+def ln(B, S, C):
+    x = (torch.rand(B * S * S, C, device=dev) - 0.5).to(BF)
+    g, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+    return (lambda: ops.layernorm(x, g, b)), 2 * 2 * x.numel() / 1e9
+
+
+def gate(B, S):
+    feat = (torch.rand(B, 14, S, S, 64, device=dev) - 0.5).to(BF)
+    ws = torch.rand(9, 64, device=dev) - 0.5
+    return (lambda: ops.faf_gate(feat, ws, want_gate=True, want_gated=True)), 2 * 2 * feat.numel() / 1e9
+
+
+def head(B, S):
+    x = torch.rand(B * 14, 3, S, S, device=dev)
+    w, b = torch.rand(27, 64, device=dev) - 0.5, torch.rand(64, device=dev)
+    return (lambda: ops.head_conv(x, w, b, BF)), (x.numel() * 4 + B * 14 * S * S * 64 * 2) / 1e9
+
+
+CASES = {
+    "attn_dec1_128x8_s5": lambda: attn(64, 160, 128, 8, 5),
+    "attn_dec1_128x8_s0": lambda: attn(64, 160, 128, 8, 0),
+    "attn_dec0_256x16_s5": lambda: attn(64, 80, 256, 16, 5),
+    "attn_enc0_64x1_s5": lambda: attn(64, 160, 64, 1, 5),
+    "attn_enc1_128x2_s5": lambda: attn(64, 80, 128, 2, 5),
+    "attn_bott_256x16_s5": lambda: attn(64, 40, 256, 16, 5),
+    "dw_160_512": lambda: dw(64, 160, 512),
+    "dw_160_256": lambda: dw(64, 160, 256),
+    "dw_80_1024": lambda: dw(64, 80, 1024),
+    "ln_160_128": lambda: ln(64, 160, 128),
+    "ln_160_64": lambda: ln(64, 160, 64),
+    "ln_80_256": lambda: ln(64, 80, 256),
+    "gate_160": lambda: gate(64, 160),
+    "head_160": lambda: head(64, 160),
+}
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case", default="all")
+    ap.add_argument("--reps", type=int, default=5)
+    a = ap.parse_args()
+    for n in (CASES if a.case == "all" else a.case.split(",")):
+        fn, gb = CASES[n]()
+        timeit(n, fn, a.reps, gb)
+        del fn
+        torch.cuda.empty_cache()
