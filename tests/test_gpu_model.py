@@ -126,3 +126,64 @@ def test_fhwc_adaptor(cuda):
     a = m(x.to(cuda))[0].permute(1, 2, 0)
     b = m.forward_fhwc(x[0].permute(0, 2, 3, 1).to(cuda))
     assert torch.equal(a, b)
+
+
+def test_golden_fixtures_on_gpu(cuda):
+    """The committed golden vectors (tests/golden) through the CUDA path."""
+    import os
+    import numpy as np
+    from fbanet_b200 import BaseModel, ops
+    from oracle.fbanet_oracle import build_oracle
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    g = torch.load(os.path.join(gold, "small_model.pt"))
+    m = BaseModel(**g["cfg"], token_projection="linear", token_mlp="leff", dtype="fp32")
+    m.load_state_dict(build_oracle(g["seed"], **g["cfg"]).state_dict())
+    got = m.to(cuda)(g["x"].to(cuda)).cpu()
+    assert (got - g["out"]).abs().max().item() <= 1e-4
+    w = np.load(os.path.join(gold, "warp.npz"))
+    out = ops.warp_burst(torch.from_numpy(w["burst"])[None].to(cuda), torch.from_numpy(w["M"])[None], layout="BTHWC").cpu().numpy()[0]
+    assert np.abs(out - w["out"]).max() < 2e-6
+
+
+def test_tiled_full_resolution_matches_reference_driver(cuda):
+    """BASELINE config 4 in miniature: reflect-pad tiling + per-tile forward + centre-crop stitch against the
+    restated test_in_any_resolution.py loop (oracle model, oracle tiling), incl. a 2-rank tile shard."""
+    from fbanet_b200.tiling import infer_full_resolution
+    from oracle.fbanet_oracle import tensor_divide_burst, tensor_merge
+    cfg = dict(num_frames=3, img_size=40, in_channels=3, embed_dim=32, window_length=10)
+    o, m = _pair(cfg, "fp32", cuda)
+    x = torch.rand(1, 3, 3, 50, 70, generator=torch.Generator().manual_seed(5))
+    tiles = tensor_divide_burst(x, 20, 10)
+    with torch.no_grad():
+        sr = torch.cat([o(tiles[i:i + 1]) for i in range(tiles.shape[0])], 0)
+    ref = tensor_merge(sr, (200, 280), psize=80, overlap=40)
+    got = infer_full_resolution(m, x.to(cuda), psize=20, overlap=10, tile_batch=5).cpu()
+    assert got.shape == ref.shape == (1, 3, 200, 280)
+    assert (got - ref).abs().max().item() <= 1e-3
+    # tile sharding over 2 ranks: the two partial canvases add up to the full image
+    out = torch.zeros(3, 200, 280, device=cuda)
+    for r in range(2):
+        infer_full_resolution(m, x.to(cuda), psize=20, overlap=10, tile_batch=4, rank=r, world=2, out=out)
+    assert (out.cpu()[None] - ref).abs().max().item() <= 1e-3
+
+
+def test_raw_config_with_warp_front_end_bf16(cuda):
+    """BASELINE config 3 shape: 14x4x80x80 packed-Bayer burst, homography warp + FAF + SR, bf16 path."""
+    import numpy as np
+    from fbanet_b200 import ops
+    from oracle.fbanet_oracle import psnr, warp_burst as warp_ref
+    o, m = _pair(RAW, "bf16", cuda)
+    x = _burst(RAW, 1, seed=2)
+    rng = np.random.default_rng(1)
+    M = np.tile(np.eye(3), (1, 14, 1, 1))
+    M[..., :2, :2] += rng.uniform(-0.01, 0.01, (1, 14, 2, 2))
+    M[..., :2, 2] += rng.uniform(-4, 4, (1, 14, 2))
+    M[..., 2, :2] += rng.uniform(-1e-5, 1e-5, (1, 14, 2))
+    xw = ops.warp_burst(x.to(cuda), torch.from_numpy(M))
+    ref_w = torch.from_numpy(warp_ref(x[0].permute(0, 2, 3, 1).numpy(), M[0])).permute(0, 3, 1, 2).float()[None]
+    assert (xw.cpu() - ref_w).abs().max().item() < 2e-6
+    with torch.no_grad():
+        ref = o(ref_w)
+    got = m(xw).cpu()
+    assert got.shape == (1, 4, 320, 320)
+    assert psnr(got, ref) > 40.0

@@ -1,0 +1,105 @@
+"""CPU checks of the drop-in boundary's host side: arch registry, state_dict key layout, checkpoint
+helpers, weight packing, sharding arithmetic.  No kernel is launched (no GPU needed)."""
+import os
+import types
+
+import pytest
+import torch
+
+from fbanet_b200 import BaseModel, get_arch, load_checkpoint, save_checkpoint
+from fbanet_b200.dist import shard_range
+
+
+def _opt(**kw):
+    d = dict(arch="BaseModel", train_ps=40, embed_dim=32, win_size=10, token_projection="linear", token_mlp="leff")
+    d.update(kw)
+    return types.SimpleNamespace(**d)
+
+
+def test_get_arch_contract():
+    m = get_arch(_opt())
+    assert isinstance(m, BaseModel) and m.img_size == 40 and m.embed_dim == 32 and m.window_length == 10
+    assert m.num_frames == 14 and m.in_channels == 3  # dataclass defaults of the reference (models/fba_net.py:31-47)
+    with pytest.raises(Exception, match="Arch error!"):
+        get_arch(_opt(arch="Uformer"))
+    with pytest.raises(NotImplementedError):
+        get_arch(_opt(token_mlp="ffn"))  # non-default options are out of scope and say so loudly
+
+
+def test_state_dict_key_layout_matches_appendix_b_and_oracle():
+    from oracle.fbanet_oracle import OracleBaseModel
+    cfg = dict(num_frames=4, img_size=40, in_channels=3, embed_dim=32, window_length=10)
+    m = BaseModel(**cfg, token_projection="linear", token_mlp="leff")
+    sd = m.state_dict()
+    ref = OracleBaseModel(**cfg).state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    assert all(sd[k].shape == ref[k].shape for k in sd)
+    for k in ("head.weight", "body.1.body.2.bias", "fusion.feature_fusion.1.weight", "fusion.res_blocks.4.1.body.0.weight",
+              "input_proj.proj.1.weight", "HG1_encoderlayer_0.blocks.1.attn.relative_position_bias_table",
+              "HG2_decoderlayer_1.blocks.0.attn.qkv.to_kv.weight", "conv_HG1.blocks.0.mlp.dwconv.0.weight",
+              "HG1_downsample_0.conv.0.weight", "HG2_upsample_1.deconv.0.bias", "output_proj_HG2_0.proj.0.weight", "tail.0.2.weight", "tail.1.bias"):
+        assert k in sd, k
+    assert sd["fusion.feature_fusion.0.weight"].shape == (32, 4 * 32, 1, 1)
+    assert sd["HG1_upsample_0.deconv.0.weight"].shape == (128, 64, 2, 2)  # torch ConvT layout [in,out,kh,kw]
+    assert sd["HG1_encoderlayer_0.blocks.0.attn.relative_position_index"].shape == (100, 100)
+
+
+def test_full_size_parameter_count():
+    m = BaseModel(num_frames=14, img_size=160, in_channels=3, embed_dim=64, window_length=10, token_projection="linear", token_mlp="leff")
+    assert sum(p.numel() for p in m.parameters()) == 19_217_237
+
+
+def test_checkpoint_roundtrip_with_module_prefix(tmp_path):
+    cfg = dict(num_frames=4, img_size=40, in_channels=3, embed_dim=32, window_length=10, token_projection="linear", token_mlp="leff")
+    a, b = BaseModel(**cfg, seed=1), BaseModel(**cfg, seed=2)
+    assert not torch.equal(a.head.weight, b.head.weight)
+    state = {"epoch": 7, "state_dict": {"module." + k: v for k, v in a.state_dict().items()}, "optimizer": {}}
+    path = save_checkpoint(str(tmp_path), state, "sess")
+    assert os.path.basename(path) == "model_epoch_7_sess.pth"
+    load_checkpoint(b, path)
+    assert all(torch.equal(a.state_dict()[k], b.state_dict()[k]) for k in a.state_dict())
+    from fbanet_b200 import load_start_epoch
+    assert load_start_epoch(path) == 7
+    bad = dict(state, state_dict={"module.nope": torch.zeros(1)})
+    torch.save(bad, path)
+    with pytest.raises(RuntimeError):
+        load_checkpoint(b, path)  # missing / unexpected keys are reported, not swallowed
+
+
+def test_weight_packing_shapes_and_cache():
+    cfg = dict(num_frames=4, img_size=40, in_channels=3, embed_dim=64, window_length=10, token_projection="linear", token_mlp="leff")
+    m = BaseModel(**cfg, dtype="bf16")
+    P = m.packed()
+    assert P["body.0.0.w"].shape == (64, 9 * 64) and P["body.0.0.w"].dtype == torch.bfloat16
+    assert P["head.wkc"].shape == (27, 64) and P["head.wkc"].dtype == torch.float32
+    assert P["fusion.wsum"].shape == (9, 64)
+    assert P["fusion.up0.w"].shape == (4 * 128, 256) and P["fusion.up0.b"].shape == (512,)
+    assert P["HG1_encoderlayer_1.0.qkv.w"].shape == (3 * 128, 128)
+    assert P["tail.1.w"].shape == (16, 9 * 64)  # final conv padded to the tensor-core minimum N
+    # conv weight packing is tap-major / channel-minor: k = (ky*3+kx)*Cin + c
+    w = m.body[0].body[0].weight
+    assert torch.equal(P["body.0.0.w"][5, (1 * 3 + 2) * 64 + 7].float(), w[5, 7, 1, 2].to(torch.bfloat16).float())
+    # PixelShuffle folded into the store: row (2i+j)*E + c  <-  out channel 4c+2i+j
+    wt = m.tail[0][0].weight
+    assert torch.equal(P["tail.0.0.w"][(2 * 1 + 0) * 64 + 3, 0].float(), wt[4 * 3 + 2, 0, 0, 0].to(torch.bfloat16).float())
+    assert m.packed() is P
+    with torch.no_grad():
+        m.head.bias.add_(1.0)
+    assert m.packed() is not P  # in-place parameter change invalidates the cache
+    f = BaseModel(**cfg, dtype="fp32").packed()
+    assert f["head.w"].shape == (64, 9 * 4) and f["head.w"].dtype == torch.float32
+
+
+def test_cpu_tensor_is_refused():
+    m = BaseModel(num_frames=4, img_size=40, embed_dim=32, window_length=10, token_projection="linear", token_mlp="leff")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 4, 3, 40, 40))
+
+
+@pytest.mark.parametrize("n,world", [(64, 8), (336, 8), (10, 4), (3, 8), (0, 2)])
+def test_shard_range_tiles_exactly(n, world):
+    spans = [shard_range(n, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    sizes = [e - b for b, e in spans]
+    assert max(sizes) - min(sizes) <= 1
