@@ -29,10 +29,12 @@ __device__ __forceinline__ float gelu_tanh(float u) {
 }
 // bf16-path GELU: single MUFU.TANH (abs err ~5e-4, below bf16 output rounding)
 __device__ __forceinline__ float gelu_tanh_fast(float u) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
   float th;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(k0 * fmaf(k1 * u * u, u, u)));
-  return 0.5f * u * (1.0f + th);
+  const float inner = fmaf(u * u, k0k1, k0) * u;   // k0 (u + k1 u^3): FMUL, FFMA, FMUL
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(inner));
+  const float hu = 0.5f * u;
+  return fmaf(hu, th, hu);                          // 0.5 u (1 + tanh): FMUL, FFMA
 }
 __device__ __forceinline__ float gelu_erf(float u) { return 0.5f * u * (1.0f + erff(u * 0.7071067811865476f)); }
 

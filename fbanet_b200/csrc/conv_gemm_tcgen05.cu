@@ -13,6 +13,7 @@
 // (one lane), warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> bias/act/residual ->
 // bf16 -> 16-byte global stores, each thread owns one pixel row).
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -36,6 +37,8 @@ struct Chunk { int16_t src, c0; int32_t cg; };   // cg = offset of the chunk in 
 struct TcParams {
   CUtensorMap amap[TC_MAX_SRC];
   CUtensorMap bmap;
+  CUtensorMap omap[4];    // TMA-store epilogue: output view(s); 4 = the (i,j) sub-pixel planes of the 2x2 scatter store
+  CUtensorMap rmap;       // residual view (TMA-loaded into the staging tile)
   KStep steps[TC_MAX_STEPS];
   Chunk chunks[TC_MAX_CHUNKS];
   const float* bias;
@@ -52,6 +55,7 @@ struct TcParams {
   int act, store_mode, res_ld, out_ld;
   int a_slots, a_slot_bytes, a_box_bytes;
   int b_slots, b_resident;
+  int tma_store;          // 1: epilogue stages 128x64 bf16 tiles in smem and stores them with TMA
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -99,6 +103,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -174,19 +187,34 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void apply_act_vec(float (&f)[NV], const int act, const float alpha) {
+  if (act == FBANET_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) f[j] = fmaxf(f[j], 0.f);
+  } else if (act == FBANET_ACT_PRELU) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) f[j] = f[j] > 0.f ? f[j] : alpha * f[j];
+  } else if (act == FBANET_ACT_GELU_TANH) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) f[j] = gelu_tanh_fast(f[j]);
+  } else if (act == FBANET_ACT_GELU_ERF) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) f[j] = gelu_erf(f[j]);
+  }
+}
+
 // bias + activation + residual + store of 32 (or 16) accumulator columns of one pixel row
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t (&v)[32], const int nc, const int col0, const int img,
-                                               const int y, const int x, const float alpha) {
+                                               const int y, const int x, const float alpha, const float* bias_s) {
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = (j < nc) ? __uint_as_float(v[j]) : 0.f;
-  if (p.bias) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (j < nc) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-      }
+  for (int j = 0; j < 32; j += 4) {   // bias of this CTA's N-tile sits in shared memory (broadcast reads)
+    if (j < nc) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j);
+      f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
     }
   }
   if (p.act == FBANET_ACT_RELU) {
@@ -258,6 +286,23 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
   }
 }
 
+// Issue the MMAs of one A slot (TAPS K-steps x 4 tcgen05.mma), fully unrolled so that descriptor offsets are
+// immediates.  Called by the elected lane only.  HALO: tap t reads copy (t%3), ky = t/3 rows down.
+template <int TAPS, bool HALO>
+__device__ __forceinline__ void issue_unit_resident(const uint32_t tmem_d, const uint32_t idesc, const uint64_t desc_hi, const uint32_t a_lo,
+                                                    uint32_t b_lo, const uint32_t b_step_lo, const bool first_unit) {
+#pragma unroll
+  for (int t = 0; t < TAPS; ++t) {
+    const uint32_t at = a_lo + (HALO ? (uint32_t)(((t % 3) * TC_HALO_COPY + (t / 3) * 1024) >> 4) : 0u);
+#pragma unroll
+    for (int k = 0; k < TC_BK / 16; ++k) {
+      const uint32_t accum = (t == 0 && k == 0) ? (first_unit ? 0u : 1u) : 1u;
+      umma_bf16(tmem_d, desc_hi + (uint64_t)(at + 2 * k), desc_hi + (uint64_t)(b_lo + 2 * k), idesc, accum);
+    }
+    b_lo += b_step_lo;
+  }
+}
+
 constexpr int TC_MAX_A_SLOTS = 8;
 constexpr int TC_NUM_THREADS = 384;   // warps: 0 A-producer, 1 MMA, 2 TMEM alloc, 3 B-producer, 4..11 epilogue
 
@@ -266,6 +311,8 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
   __shared__ __align__(8) uint64_t a_full[TC_MAX_A_SLOTS], a_empty[TC_MAX_A_SLOTS], tmem_full[2], tmem_empty[2];
   __shared__ __align__(8) uint64_t b_full[TC_MAX_STEPS], b_empty[TC_MAX_STEPS];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float bias_s[256];
+  __shared__ __align__(8) uint64_t res_bar[2];
 
   // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the 128B swizzle needs
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -274,21 +321,27 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
   const uint32_t b_bytes = (uint32_t)BN * TC_BK * 2;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)p.a_slots * p.a_slot_bytes;
+  uint8_t* smem_stage = smem_b + (size_t)p.b_slots * b_bytes;   // 2 x 16 KB epilogue staging tiles (one per column half)
   const uint32_t tmem_cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < TC_MAX_SRC; ++s) tma_prefetch_desc(&p.amap[s]);
     tma_prefetch_desc(&p.bmap);
+    if (p.tma_store) { tma_prefetch_desc(&p.omap[0]); tma_prefetch_desc(&p.rmap); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.a_slots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.b_slots; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); mbar_init(&res_bar[a], 1); }
     fence_barrier_init();
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (warp >= 4) {   // this CTA owns N-tile blockIdx.x % n_tiles_n for its whole life: stage its bias once
+    const int i = threadIdx.x - 128;
+    if (i < 256) bias_s[i] = (p.bias && i < BN) ? __ldg(p.bias + (blockIdx.x % p.n_tiles_n) * BN + i) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -346,94 +399,191 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
           __syncwarp();
         }
     } else {
-      int slot = 0;
-      uint32_t phase = 0;
+      const uint32_t bmask = (uint32_t)p.b_slots - 1, bshift = (uint32_t)__ffs(p.b_slots) - 1;
+      uint32_t g = 0;
       for (int mt = mt0; mt < p.m_tiles; mt += mt_step)
-        for (int s = 0; s < p.nsteps; ++s) {
-          mbar_wait(&b_empty[slot], phase ^ 1);
+        for (int s = 0; s < p.nsteps; ++s, ++g) {
+          const uint32_t slot = g & bmask;
+          mbar_wait(&b_empty[slot], ((g >> bshift) & 1) ^ 1);
           if (elect_one()) {
             mbar_expect_tx(&b_full[slot], b_bytes);
             tma_load_2d(smem_b + (size_t)slot * b_bytes, &p.bmap, &b_full[slot], bk(s), nt * BN);
           }
           __syncwarp();
-          if (++slot == p.b_slots) { slot = 0; phase ^= 1; }
         }
     }
   } else if (warp == 1) {
     // ================= MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma =================
+    // All loop state is warp-uniform (ring slots are derived from a running step counter, b_slots is a
+    // power of two), so everything inside the elected block stays in uniform registers.
     const uint32_t idesc = make_idesc_bf16(BN);
     const uint64_t desc_hi = make_sw128_desc(0);       // descriptor with a zero start address
     const uint32_t sa0 = smem_u32(smem_a), sb0 = smem_u32(smem_b);
-    int aslot = 0, bslot = 0;
-    uint32_t aphase = 0, bphase = 0;
+    const uint32_t bmask = (uint32_t)p.b_slots - 1, bshift = (uint32_t)__ffs(p.b_slots) - 1;
+    int aslot = 0;
+    uint32_t aphase = 0, gs = 0;                       // gs = B slabs consumed so far (ring mode)
+    bool b_landed = false;                             // resident weights: waited for once
     int it = 0;
     for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);     // epilogue has drained this accumulator
-      tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-      int s = 0;
       for (int u = 0; u < units; ++u) {
         mbar_wait(&a_full[aslot], aphase);
+        if (p.b_resident && !b_landed)
+          for (int t = 0; t < taps; ++t) mbar_wait(&b_full[u * taps + t], 0);
+        tc_fence_after();
         const uint32_t sa = sa0 + (uint32_t)aslot * (uint32_t)p.a_slot_bytes;
-        for (int t = 0; t < taps; ++t, ++s) {
-          uint32_t sb;
-          if (p.b_resident) {
-            mbar_wait(&b_full[s], 0);                  // completes once, stays complete
-            sb = sb0 + (uint32_t)s * b_bytes;
-          } else {
-            mbar_wait(&b_full[bslot], bphase);
-            sb = sb0 + (uint32_t)bslot * b_bytes;
-          }
-          tc_fence_after();
-          // halo mode: tap (ky,kx) reads the dx-shifted copy kx, starting ky rows (1 KB each) down
-          const uint32_t a_addr = p.halo ? sa + (uint32_t)((t % 3) * TC_HALO_COPY + (t / 3) * 1024) : sa;
-          const uint64_t adesc = desc_hi + (uint64_t)(a_addr >> 4), bdesc = desc_hi + (uint64_t)(sb >> 4);
+        if (p.b_resident) {
+          // resident weights: straight-line issue with immediate descriptor offsets
           if (elect_one()) {
+            const uint32_t b_lo = (sb0 + (uint32_t)(u * taps) * b_bytes) >> 4;
+            if (p.halo) issue_unit_resident<9, true>(tmem_d, idesc, desc_hi, sa >> 4, b_lo, b_bytes >> 4, u == 0);
+            else issue_unit_resident<1, false>(tmem_d, idesc, desc_hi, sa >> 4, b_lo, b_bytes >> 4, u == 0);
+            umma_commit(&a_empty[aslot]);
+            if (u == units - 1) umma_commit(&tmem_full[acc]);
+          }
+        } else if (elect_one()) {
+          for (int t = 0; t < taps; ++t) {
+            const int s = u * taps + t;
+            uint32_t sb;
+            if (p.b_resident) {
+              sb = sb0 + (uint32_t)s * b_bytes;
+            } else {
+              const uint32_t g = gs + (uint32_t)t, slot = g & bmask;
+              mbar_wait(&b_full[slot], (g >> bshift) & 1);
+              tc_fence_after();
+              sb = sb0 + slot * b_bytes;
+            }
+            // halo mode: tap (ky,kx) reads the dx-shifted copy kx, starting ky rows (1 KB each) down
+            const uint32_t a_addr = p.halo ? sa + (uint32_t)((t % 3) * TC_HALO_COPY + (t / 3) * 1024) : sa;
+            const uint64_t adesc = desc_hi + (uint64_t)(a_addr >> 4), bdesc = desc_hi + (uint64_t)(sb >> 4);
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k)       // advance 32 bytes (16 bf16) inside the swizzle row
               umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((s | k) != 0));
-            if (!p.b_resident) umma_commit(&b_empty[bslot]);
-            if (t == taps - 1) umma_commit(&a_empty[aslot]);                       // frees the A slot when these MMAs retire
-            if (t == taps - 1 && u == units - 1) umma_commit(&tmem_full[acc]);     // accumulator ready for the epilogue
+            if (!p.b_resident) umma_commit(&b_empty[(gs + (uint32_t)t) & bmask]);
           }
-          __syncwarp();
-          if (!p.b_resident) { if (++bslot == p.b_slots) { bslot = 0; bphase ^= 1; } }
+          umma_commit(&a_empty[aslot]);                             // frees the A slot when these MMAs retire
+          if (u == units - 1) umma_commit(&tmem_full[acc]);         // accumulator ready for the epilogue
         }
+        __syncwarp();
+        gs += (uint32_t)taps;
         if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
       }
+      b_landed = true;
     }
   } else if (warp >= 4) {
     // ================= epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =================
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;
-    const int ncols = (BN >= 32) ? BN / 2 : (half == 0 ? BN : 0);
-    const int cbeg = half * (BN / 2);
     const int row = q * 32 + lane;
     const int ly = row / p.tw, lx = row - ly * p.tw;
     const float alpha = (p.act == FBANET_ACT_PRELU) ? __ldg(p.alpha) : 0.f;
     int it = 0;
-    for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      const int img = mt / tiles_per_img, r = mt % tiles_per_img;
-      const int y = (r / p.tiles_x) * p.th + ly, x = (r % p.tiles_x) * p.tw + lx;
-      const bool valid = (ly < p.th) && (y < p.Ho) && (x < p.Wo);
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cbeg);
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
-        uint32_t v[32];
-        const int nc = (ncols - c0 >= 32) ? 32 : 16;
-        if (nc == 32) tmem_ld32(taddr0 + c0, v); else tmem_ld16(taddr0 + c0, v);
-        tmem_ld_wait();
-        if (valid) epilogue_chunk(p, v, nc, nt * BN + cbeg + c0, img, y, x, alpha);
+    if (p.tma_store) {
+      // ---- staged epilogue: 64-column chunks -> swizzled 128x64 bf16 smem tile -> one TMA store per chunk.
+      // (Per-thread 16-byte global stores touch 32 lines per instruction and cap an SM at ~16 B/clk.)
+      uint8_t* stage = smem_stage + half * 16384;
+      uint8_t* row_ptr = stage + (size_t)row * 128;
+      const int r7 = row & 7;
+      const int nchunks = BN >> 6;
+      const bool has_res = p.residual != nullptr;
+      const int Co = p.store_mode == FBANET_STORE_CONVT2 ? (p.Cout >> 2) : p.Cout;
+      uint32_t res_phase = 0;
+      for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const int img = mt / tiles_per_img, r = mt % tiles_per_img;
+        const int y0 = (r / p.tiles_x) * p.th, x0 = (r % p.tiles_x) * p.tw;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        for (int cidx = half; cidx < nchunks; cidx += 2) {
+          const int col0 = nt * BN + cidx * 64;          // GEMM column of the chunk
+          uint32_t v0[32], v1[32];
+          tmem_ld32(taddr0 + cidx * 64, v0);
+          tmem_ld32(taddr0 + cidx * 64 + 32, v1);
+          if (q == 0) {
+            if (elect_one()) {
+              bulk_wait_read0();                         // the previous store has finished reading the tile
+              if (has_res) {
+                mbar_expect_tx(&res_bar[half], (uint32_t)p.a_box_bytes);
+                tma_load_4d(stage, &p.rmap, &res_bar[half], col0, x0, y0, img);
+              }
+            }
+            __syncwarp();
+          }
+          named_bar_sync(1 + half, 128);                 // staging tile is free (and the residual is on its way)
+          tmem_ld_wait();
+          if (has_res) { mbar_wait(&res_bar[half], res_phase); res_phase ^= 1; }
+          const float* bs = bias_s + cidx * 64;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {                  // 8 columns = one 16-byte smem chunk at a time
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(c < 4 ? v0[c * 8 + e] : v1[(c - 4) * 8 + e]);
+            const float4 b0 = *reinterpret_cast<const float4*>(bs + c * 8), b1 = *reinterpret_cast<const float4*>(bs + c * 8 + 4);
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            apply_act_vec<8>(f, p.act, alpha);
+            uint4* sp = reinterpret_cast<uint4*>(row_ptr + ((c ^ r7) << 4));   // SWIZZLE_128B position of chunk c in this row
+            if (has_res) {
+              const uint4 rv = *sp;
+              const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { f[2 * e] += __uint_as_float(ru[e] << 16); f[2 * e + 1] += __uint_as_float(ru[e] & 0xffff0000u); }
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+              o[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *sp = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          fence_proxy_async();                           // generic-proxy smem writes -> visible to the TMA engine
+          named_bar_sync(1 + half, 128);
+          if (q == 0) {
+            if (elect_one()) {
+              const int qq = col0 / Co;                  // 2x2 scatter store: sub-pixel plane of this chunk (0 for NHWC)
+              tma_store_4d(&p.omap[qq], stage, col0 - qq * Co, x0, y0, img);
+              bulk_commit();
+            }
+            __syncwarp();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
+      if (q == 0) {
+        if (elect_one()) bulk_wait0();                   // all stores of this CTA have completed
         __syncwarp();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    } else {
+      const int ncols = (BN >= 32) ? BN / 2 : (half == 0 ? BN : 0);
+      const int cbeg = half * (BN / 2);
+      for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const int img = mt / tiles_per_img, r = mt % tiles_per_img;
+        const int y = (r / p.tiles_x) * p.th + ly, x = (r % p.tiles_x) * p.tw + lx;
+        const bool valid = (ly < p.th) && (y < p.Ho) && (x < p.Wo);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cbeg);
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t v[32];
+          const int nc = (ncols - c0 >= 32) ? 32 : 16;
+          if (nc == 32) tmem_ld32(taddr0 + c0, v); else tmem_ld16(taddr0 + c0, v);
+          tmem_ld_wait();
+          if (valid) epilogue_chunk(p, v, nc, nt * BN + cbeg + c0, img, y, x, alpha, bias_s + cbeg + c0);
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
     }
   }
 
@@ -621,8 +771,46 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   tp.res_img_stride = p->res_img_stride; tp.out_img_stride = p->out_img_stride; tp.base_img_stride = p->base_img_stride;
   tp.act = p->act; tp.store_mode = p->store_mode; tp.res_ld = p->res_ld; tp.out_ld = p->out_ld;
 
-  // shared-memory plan: A ring + B ring (or all B slabs resident when they fit)
-  const int budget = 198 * 1024;
+  // TMA-store epilogue for the channels-last store modes (64-column chunks)
+  // Measured (profiles/r1_notes.md): the staged TMA store only pays for wide plain stores (qkv-type GEMMs, BN >= 192,
+  // no activation / residual); elsewhere the two extra named barriers per chunk cost more than the coalescing gains
+  // because those layers already sit at the HBM write rate.  FBANET_TC_TMA_STORE=0/1 forces it off/on.
+  const bool store_ok = (p->store_mode == FBANET_STORE_NHWC || (p->store_mode == FBANET_STORE_CONVT2 && (p->Cout / 4) % 64 == 0)) && tp.BN % 64 == 0;
+  static const char* force = getenv("FBANET_TC_TMA_STORE");
+  if (force) tp.tma_store = (store_ok && force[0] == '1') ? 1 : 0;
+  else tp.tma_store = (store_ok && tp.BN >= 192 && p->act == FBANET_ACT_NONE && !p->residual) ? 1 : 0;
+  if (tp.tma_store) {
+    const bool ct = p->store_mode == FBANET_STORE_CONVT2;
+    const int Co = ct ? p->Cout / 4 : p->Cout_store;
+    const int64_t sx = ct ? 2 * (int64_t)p->out_ld : p->out_ld;                    // elements between tile-space pixels
+    const int64_t sy = ct ? 4 * (int64_t)p->Wo * p->out_ld : (int64_t)p->Wo * p->out_ld;
+    for (int qq = 0; qq < (ct ? 4 : 1); ++qq) {
+      const int64_t off = ct ? ((int64_t)(qq >> 1) * 2 * p->Wo + (qq & 1)) * p->out_ld : 0;
+      const cuuint64_t dims[4] = {(cuuint64_t)Co, (cuuint64_t)p->Wo, (cuuint64_t)p->Ho, (cuuint64_t)p->N};
+      const cuuint64_t strides[3] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)p->out_img_stride * 2};
+      const cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, 1};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = encode(&tp.omap[qq], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, reinterpret_cast<bf16*>(p->out) + off, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return FBANET_E_BADSHAPE;
+    }
+    for (int qq = (ct ? 4 : 1); qq < 4; ++qq) tp.omap[qq] = tp.omap[0];
+    tp.rmap = tp.omap[0];
+    if (p->residual) {
+      const cuuint64_t dims[4] = {(cuuint64_t)p->Cout, (cuuint64_t)p->Wo, (cuuint64_t)p->Ho, (cuuint64_t)p->N};
+      const cuuint64_t strides[3] = {(cuuint64_t)p->res_ld * 2, (cuuint64_t)p->Wo * p->res_ld * 2, (cuuint64_t)p->res_img_stride * 2};
+      const cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, 1};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = encode(&tp.rmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->residual), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return FBANET_E_BADSHAPE;
+    }
+  }
+  // shared-memory plan: A ring + B ring (or all B slabs resident when they fit) + 2 staging tiles
+  const int stage_bytes = tp.tma_store ? 2 * 16384 : 0;
+  const int budget = 216 * 1024 - stage_bytes;
   const int b_bytes = tp.BN * TC_BK * 2;
   tp.a_slot_bytes = halo ? TC_HALO_SLOT : TC_A_BYTES;
   const int a_min = halo ? 2 : 3;
@@ -636,12 +824,11 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
     tp.b_resident = 0;
     tp.a_slots = halo ? 2 : 4;
     int b = (budget - tp.a_slots * tp.a_slot_bytes) / b_bytes;
-    if (b > 8) b = 8;
     if (b < 2) return FBANET_E_UNSUPPORTED;
-    tp.b_slots = b;
+    tp.b_slots = b >= 8 ? 8 : (b >= 4 ? 4 : 2);   // power of two: ring slot = step & (slots-1)
   }
   if (tp.a_slots > units * 2 && units * 2 >= 2) tp.a_slots = units * 2;
-  const size_t smem = (size_t)tp.a_slots * tp.a_slot_bytes + (size_t)tp.b_slots * b_bytes + 1024;
+  const size_t smem = (size_t)tp.a_slots * tp.a_slot_bytes + (size_t)tp.b_slots * b_bytes + stage_bytes + 1024;
 
   static size_t smem_opted_in = 0;  // opt-in limit is per function; raise it only when a launch needs more
   if (smem > smem_opted_in) {
