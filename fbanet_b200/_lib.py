@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libfbanet_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -102,6 +102,15 @@ class FafGateParams(C.Structure):
     ]
 
 
+class LeffFc2Params(C.Structure):
+    _fields_ = [
+        ("h1", C.c_void_p), ("dw_weight", C.c_void_p), ("dw_bias", C.c_void_p), ("w2", C.c_void_p), ("bias2", C.c_void_p),
+        ("residual", C.c_void_p), ("out", C.c_void_p), ("res_img_stride", C.c_int64), ("out_img_stride", C.c_int64),
+        ("res_ld", C.c_int32), ("out_ld", C.c_int32),
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("Hd", C.c_int32), ("act", C.c_int32),
+    ]
+
+
 class TileParams(C.Structure):
     _fields_ = [
         ("src", C.c_void_p), ("dst", C.c_void_p),
@@ -114,16 +123,16 @@ class TileParams(C.Structure):
 STRUCTS = {
     "fbanet_src": Src, "fbanet_conv_params": ConvParams, "fbanet_warp_params": WarpParams,
     "fbanet_to_nhwc_params": ToNhwcParams, "fbanet_s2d_params": S2dParams, "fbanet_head_conv_params": HeadConvParams, "fbanet_layernorm_params": LayerNormParams, "fbanet_attn_params": AttnParams,
-    "fbanet_dwconv_params": DwconvParams, "fbanet_faf_gate_params": FafGateParams, "fbanet_tile_params": TileParams,
+    "fbanet_dwconv_params": DwconvParams, "fbanet_faf_gate_params": FafGateParams, "fbanet_leff_fc2_params": LeffFc2Params, "fbanet_tile_params": TileParams,
 }
 
 # every symbol include/fbanet_b200.h declares
 OPS = {
     "fbanet_warp_sm100": WarpParams, "fbanet_to_nhwc_sm100": ToNhwcParams, "fbanet_space_to_depth_sm100": S2dParams, "fbanet_head_conv_sm100": HeadConvParams, "fbanet_conv_gemm_sm100": ConvParams,
     "fbanet_layernorm_sm100": LayerNormParams, "fbanet_window_attention_sm100": AttnParams, "fbanet_dwconv3x3_sm100": DwconvParams,
-    "fbanet_faf_gate_sm100": FafGateParams, "fbanet_tile_divide_sm100": TileParams, "fbanet_tile_merge_sm100": TileParams,
+    "fbanet_faf_gate_sm100": FafGateParams, "fbanet_leff_fc2_sm100": LeffFc2Params, "fbanet_tile_divide_sm100": TileParams, "fbanet_tile_merge_sm100": TileParams,
 }
-MISC_SYMBOLS = ["fbanet_abi_version", "fbanet_abi_sizeof", "fbanet_last_cuda_error", "fbanet_conv_gemm_tcgen05_supported"]
+MISC_SYMBOLS = ["fbanet_abi_version", "fbanet_abi_sizeof", "fbanet_last_cuda_error", "fbanet_conv_gemm_tcgen05_supported", "fbanet_leff_fc2_supported"]
 
 _lib = None
 
@@ -145,6 +154,8 @@ def load() -> C.CDLL:
     lib.fbanet_last_cuda_error.restype = C.c_char_p
     lib.fbanet_conv_gemm_tcgen05_supported.restype = C.c_int
     lib.fbanet_conv_gemm_tcgen05_supported.argtypes = [C.POINTER(ConvParams)]
+    lib.fbanet_leff_fc2_supported.restype = C.c_int
+    lib.fbanet_leff_fc2_supported.argtypes = [C.POINTER(LeffFc2Params)]
     if lib.fbanet_abi_version() != ABI_VERSION:
         raise RuntimeError(f"fbanet_b200: ABI mismatch (library {lib.fbanet_abi_version()}, binding {ABI_VERSION}); rebuild")
     for name, st in STRUCTS.items():

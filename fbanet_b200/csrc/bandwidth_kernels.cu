@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const fbanet_head_conv_p
   const int wp = (p.W + 1) / 2;  // pixel pairs per row
   const int64_t hw = (int64_t)p.H * p.W;
   const int64_t total = (int64_t)p.frames * p.H * wp;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+  const int64_t idx0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t idx = idx0 < total ? idx0 : total - 1;   // dead lanes recompute the last item (kept for the warp-wide store)
   const int xp = (int)(idx % wp);
   const int y = (int)((idx / wp) % p.H);
   const int64_t f = idx / ((int64_t)wp * p.H);
@@ -158,22 +158,74 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const fbanet_head_conv_p
           a1[4 * j + 2] = fmaf(v1, w4.z, a1[4 * j + 2]); a1[4 * j + 3] = fmaf(v1, w4.w, a1[4 * j + 3]);
         }
       }
-  constexpr int V = Vec16<T>::N;
-  T* o = reinterpret_cast<T*>(p.dst) + ((f * p.H + y) * p.W + x0) * CO;
-#pragma unroll
-  for (int j = 0; j < CO; j += V) {
-    float t[V];
-#pragma unroll
-    for (int e = 0; e < V; ++e) t[e] = a0[j + e];
-    store_vec<T, V>(o + j, t);
-  }
-  if (x0 + 1 < p.W) {
-#pragma unroll
+  if constexpr (sizeof(T) == 2) {
+    // Each thread owns 2 adjacent pixels x 64 channels = 256 contiguous bytes (bf16) of the output row.  A
+    // per-thread 16-byte store would touch 32 different lines per instruction, so the warp's 32 x 2 pixels are
+    // first transposed through shared memory and then written as contiguous 512-byte runs.
+    constexpr int V = Vec16<T>::N;
+    constexpr int ROW = 2 * CO;                       // elements per thread
+    __shared__ __align__(16) T stage[4][32][ROW + V];  // +V: rows 16 B apart in bank space
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T* my = stage[warp][lane];
+  #pragma unroll
     for (int j = 0; j < CO; j += V) {
       float t[V];
-#pragma unroll
+  #pragma unroll
+      for (int e = 0; e < V; ++e) t[e] = a0[j + e];
+      store_vec<T, V>(my + j, t);
+  #pragma unroll
       for (int e = 0; e < V; ++e) t[e] = a1[j + e];
-      store_vec<T, V>(o + CO + j, t);
+      store_vec<T, V>(my + CO + j, t);
+    }
+    __syncwarp();
+    // the warp's threads are consecutive pixel pairs of one row segment (idx is linear in (f, y, xp)), except across
+    // row ends; write thread by thread, 32 lanes x 16 B per instruction
+    constexpr int VPT = ROW / V;                      // 16-byte vectors per thread row
+    const int64_t warp_idx0 = (int64_t)blockIdx.x * blockDim.x + warp * 32;
+    if ((p.W & 1) == 0) {
+      // even width: (frame, row, pixel pair) is linear in memory, so the warp's 32 x 2 pixels are ONE contiguous run
+      T* wbase = reinterpret_cast<T*>(p.dst) + warp_idx0 * ROW;
+      const int64_t lim = (total - warp_idx0) * (ROW / V);   // vectors that exist (last warp may be partial)
+#pragma unroll 4
+      for (int i = lane; i < 32 * VPT; i += 32) {
+        if (i >= lim) break;
+        const int tsrc = i / VPT, vsrc = i - tsrc * VPT;
+        *reinterpret_cast<uint4*>(wbase + (int64_t)i * V) = *reinterpret_cast<const uint4*>(stage[warp][tsrc] + vsrc * V);
+      }
+    } else {
+      for (int i = lane; i < 32 * VPT; i += 32) {
+        const int tsrc = i / VPT, vsrc = i - tsrc * VPT;
+        const int64_t tidx = warp_idx0 + tsrc;
+        if (tidx >= total) continue;
+        const int txp = (int)(tidx % wp);
+        const int ty = (int)((tidx / wp) % p.H);
+        const int64_t tf = tidx / ((int64_t)wp * p.H);
+        const int tx0 = txp * 2;
+        const int el = vsrc * V;                        // element offset inside the 2-pixel run
+        if (el >= CO && tx0 + 1 >= p.W) continue;       // odd width: second pixel does not exist
+        T* dstp = reinterpret_cast<T*>(p.dst) + ((tf * p.H + ty) * p.W + tx0) * CO + el;
+        *reinterpret_cast<uint4*>(dstp) = *reinterpret_cast<const uint4*>(stage[warp][tsrc] + el);
+      }
+    }
+  } else {
+    if (idx0 >= total) return;
+    constexpr int V4 = Vec16<T>::N;
+    T* o = reinterpret_cast<T*>(p.dst) + ((f * p.H + y) * p.W + x0) * CO;
+#pragma unroll
+    for (int j = 0; j < CO; j += V4) {
+      float t[V4];
+#pragma unroll
+      for (int e = 0; e < V4; ++e) t[e] = a0[j + e];
+      store_vec<T, V4>(o + j, t);
+    }
+    if (x0 + 1 < p.W) {
+#pragma unroll
+      for (int j = 0; j < CO; j += V4) {
+        float t[V4];
+#pragma unroll
+        for (int e = 0; e < V4; ++e) t[e] = a1[j + e];
+        store_vec<T, V4>(o + CO + j, t);
+      }
     }
   }
 }

@@ -1,0 +1,326 @@
+// Fused LeFF tail (bf16):  out = fc2( GELU( depthwise3x3( h1 ) + b_dw ) ) + b2 + residual
+// (layers/locally_enhanced_feed_forward.py:39-57 with the residual of layers/fba_net.py:248).
+//
+// The depthwise conv is the A-operand PRODUCER of the fc2 GEMM: for every 64-channel chunk of the hidden
+// dimension a TMA box brings the (8+2)x(16+2) halo of h1 = GELU(fc1(.)) into shared memory, 8 CUDA-core warps
+// compute depthwise 3x3 + bias + GELU for the 8x16 output pixels and write the bf16 result straight into the
+// K-major SWIZZLE_128B A tile that tcgen05.mma consumes, while the tensor core accumulates
+// acc[128 px, C] += A[128, 64] . W2[C, 64]^T in TMEM.  The dwconv output (the largest tensor of the forward)
+// never goes to HBM: one 2x1.7 GB round trip per dec1 layer at batch 64 disappears.
+//
+// Warps (384 threads, persistent, 1 CTA/SM): 0 = h1 halo TMA, 1 = MMA issuer, 2 = TMEM alloc, 3 = W2 TMA,
+// 4..11 = depthwise producer + epilogue (the epilogue of tile i runs after chunk 0 of tile i+1 is produced).
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace fbanet {
+
+constexpr int LF_TW = 8, LF_TH = 16;                       // output tile (pixels)
+constexpr int LF_HW = LF_TW + 2, LF_HH = LF_TH + 2;        // halo tile
+constexpr int LF_H_BYTES = LF_HW * LF_HH * 128;            // 23040: halo pixels x 64 ch bf16
+constexpr int LF_H_SLOT = 23552;                           // padded to 1 KB
+constexpr int LF_A_BYTES = 128 * 128;                      // A tile: 128 px x 64 ch bf16
+constexpr int LF_THREADS = 384;
+
+struct LeffParams {
+  CUtensorMap hmap;   // h1 [N,H,W,Hd]: box {64, 10, 18, 1}, no swizzle (read by CUDA cores)
+  CUtensorMap wmap;   // W2 [C][Hd]:   box {64, C}, SWIZZLE_128B (tcgen05 B operand)
+  const float* dw_w;  // [9][Hd]
+  const float* dw_b;  // [Hd]
+  const float* bias2; // [C]
+  const bf16* residual;
+  bf16* out;
+  int64_t res_img_stride, out_img_stride;
+  int res_ld, out_ld;
+  int N, H, W, C, Hd, act;
+  int tiles_x, tiles_y, m_tiles, nchunks, b_slots;
+};
+
+__global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_constant__ LeffParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t h_full[2], h_empty[2], a_full[2], a_empty[2], b_full[8], b_empty[8], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float bias_s[256];
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                   // 2 x 16 KB, 1024-aligned (swizzle atoms)
+  uint8_t* smem_b = smem_a + 2 * LF_A_BYTES;                // b_slots x C*128
+  const uint32_t b_bytes = (uint32_t)p.C * 128u;
+  uint8_t* smem_h = smem_b + (size_t)p.b_slots * b_bytes;   // 2 x halo tiles
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = p.C;
+  const uint32_t tmem_cols = (2 * C <= 128) ? 128 : (2 * C <= 256 ? 256 : 512);
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.hmap); tma_prefetch_desc(&p.wmap); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&h_full[s], 1); mbar_init(&h_empty[s], 8);
+      mbar_init(&a_full[s], 8); mbar_init(&a_empty[s], 1);
+      mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8);
+    }
+    for (int s = 0; s < p.b_slots; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (warp >= 4) {
+    const int i = threadIdx.x - 128;
+    bias_s[i] = (p.bias2 && i < C) ? __ldg(p.bias2 + i) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const uint32_t bmask = (uint32_t)p.b_slots - 1, bshift = (uint32_t)__ffs(p.b_slots) - 1;
+
+  if (warp == 0) {
+    // ================= h1 halo producer =================
+    uint32_t g = 0;
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+      const int img = mt / tiles_per_img, r = mt % tiles_per_img;
+      const int y0 = (r / p.tiles_x) * LF_TH, x0 = (r % p.tiles_x) * LF_TW;
+      for (int c = 0; c < p.nchunks; ++c, ++g) {
+        const uint32_t hs = g & 1;
+        mbar_wait(&h_empty[hs], ((g >> 1) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&h_full[hs], (uint32_t)LF_H_BYTES);
+          tma_load_4d(smem_h + hs * LF_H_SLOT, &p.hmap, &h_full[hs], c * 64, x0 - 1, y0 - 1, img);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 3) {
+    // ================= W2 slab producer =================
+    uint32_t g = 0;
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+      for (int c = 0; c < p.nchunks; ++c, ++g) {
+        const uint32_t slot = g & bmask;
+        mbar_wait(&b_empty[slot], ((g >> bshift) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&b_full[slot], b_bytes);
+          tma_load_2d(smem_b + (size_t)slot * b_bytes, &p.wmap, &b_full[slot], c * 64, 0);
+        }
+        __syncwarp();
+      }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = make_idesc_bf16(C);
+    const uint64_t desc_hi = make_sw128_desc(0);
+    const uint32_t sa0 = smem_u32(smem_a), sb0 = smem_u32(smem_b);
+    uint32_t g = 0;
+    int it = 0;
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&tmem_empty[acc], (((uint32_t)it >> 1) & 1) ^ 1);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * C);
+      for (int c = 0; c < p.nchunks; ++c, ++g) {
+        const uint32_t as = g & 1, slot = g & bmask;
+        mbar_wait(&a_full[as], (g >> 1) & 1);
+        mbar_wait(&b_full[slot], (g >> bshift) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_lo = (sa0 + as * LF_A_BYTES) >> 4, b_lo = (sb0 + slot * b_bytes) >> 4;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_d, desc_hi + (uint64_t)(a_lo + 2 * k), desc_hi + (uint64_t)(b_lo + 2 * k), idesc, (uint32_t)((c | k) != 0));
+          umma_commit(&a_empty[as]);
+          umma_commit(&b_empty[slot]);
+          if (c == p.nchunks - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= depthwise producer + epilogue =================
+    const int tl = threadIdx.x - 128;          // 0..255
+    const int cg4 = tl & 15;                   // 4-channel group inside the 64-channel chunk
+    const int pt = tl >> 4;                    // 0..15
+    const int col = pt & 7, rhalf = pt >> 3;   // output column, rows rhalf*8 .. +7
+    const int q = warp & 3, half = (warp - 4) >> 2;   // epilogue: TMEM lane quarter / column half
+    const bool erf_gelu = p.act == FBANET_ACT_GELU_ERF;
+
+    auto epilogue = [&](int mt, int it) {
+      const int acc = it & 1;
+      const int img = mt / tiles_per_img, r = mt % tiles_per_img;
+      const int row = q * 32 + lane;
+      const int y = (r / p.tiles_x) * LF_TH + row / LF_TW, x = (r % p.tiles_x) * LF_TW + row % LF_TW;
+      const bool valid = y < p.H && x < p.W;
+      mbar_wait(&tmem_full[acc], ((uint32_t)it >> 1) & 1);
+      tc_fence_after();
+      const int ncols = C / 2, cbeg = half * ncols;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C + cbeg);
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr0 + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          const int64_t pix = (int64_t)y * p.W + x;
+          const bf16* rp = p.residual ? p.residual + img * p.res_img_stride + pix * p.res_ld + cbeg + c0 : nullptr;
+          bf16* op = p.out + img * p.out_img_stride + pix * p.out_ld + cbeg + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float f[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cbeg + c0 + j), b1 = *reinterpret_cast<const float4*>(bias_s + cbeg + c0 + j + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]) + bb[e];
+            if (rp) {
+              float t[8];
+              load_vec<bf16, 8>(rp + j, t);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] += t[e];
+            }
+            store_vec<bf16, 8>(op + j, f);
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    };
+
+    uint32_t g = 0;
+    int it = 0, pend_mt = -1, pend_it = 0;
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++it) {
+      for (int c = 0; c < p.nchunks; ++c, ++g) {
+        const uint32_t hs = g & 1;
+        // depthwise weights / bias of this thread's 4 channels (L1-resident after the first tile)
+        const int ch0 = c * 64 + cg4 * 4;
+        float w[9][4], bdw[4];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(p.dw_w + (size_t)t * p.Hd + ch0));
+          w[t][0] = a.x; w[t][1] = a.y; w[t][2] = a.z; w[t][3] = a.w;
+        }
+        {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(p.dw_b + ch0));
+          bdw[0] = a.x; bdw[1] = a.y; bdw[2] = a.z; bdw[3] = a.w;
+        }
+        float acc[8][4];
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[o][e] = bdw[e];
+        mbar_wait(&h_full[hs], (g >> 1) & 1);       // halo tile landed
+        mbar_wait(&a_empty[hs], ((g >> 1) & 1) ^ 1);  // A slot consumed by the MMAs that used it last
+        const uint8_t* hbase = smem_h + hs * LF_H_SLOT + ((rhalf * 8) * LF_HW + col) * 128 + cg4 * 8;
+        uint8_t* abase = smem_a + hs * LF_A_BYTES;
+#pragma unroll
+        for (int hr = 0; hr < 10; ++hr) {           // halo rows feeding this thread's 8 output rows
+          float rv[3][4];
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const uint2 u = *reinterpret_cast<const uint2*>(hbase + (hr * LF_HW + kx) * 128);
+            rv[kx][0] = __uint_as_float(u.x << 16); rv[kx][1] = __uint_as_float(u.x & 0xffff0000u);
+            rv[kx][2] = __uint_as_float(u.y << 16); rv[kx][3] = __uint_as_float(u.y & 0xffff0000u);
+          }
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int o = hr - ky;                   // output row (within the thread's 8) this halo row feeds with tap row ky
+            if (o >= 0 && o < 8) {
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[o][e] = fmaf(rv[kx][e], w[ky * 3 + kx][e], acc[o][e]);
+            }
+          }
+          if (hr >= 2) {                             // output row hr-2 is complete
+            const int o = hr - 2;
+            float f[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) f[e] = erf_gelu ? gelu_erf(acc[o][e]) : gelu_tanh_fast(acc[o][e]);
+            const int rr = (rhalf * 8 + o) * LF_TW + col;        // A-tile row = pixel index in the 8x16 tile
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+            uint2 ov;
+            ov.x = *reinterpret_cast<const uint32_t*>(&h0);
+            ov.y = *reinterpret_cast<const uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(abase + rr * 128 + (((cg4 >> 1) ^ (rr & 7)) << 4) + (cg4 & 1) * 8) = ov;
+          }
+        }
+        fence_proxy_async();                          // A tile written through the generic proxy -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&a_full[hs]); mbar_arrive(&h_empty[hs]); }
+        if (c == 0 && pend_mt >= 0) { epilogue(pend_mt, pend_it); pend_mt = -1; }
+      }
+      pend_mt = mt; pend_it = it;
+    }
+    if (pend_mt >= 0) epilogue(pend_mt, pend_it);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
+}  // namespace fbanet
+
+using namespace fbanet;
+
+extern "C" int fbanet_leff_fc2_supported(const fbanet_leff_fc2_params* p) {
+  if (!p || !p->h1 || !p->dw_weight || !p->dw_bias || !p->w2 || !p->out) return 0;
+  if (p->C != 64 && p->C != 128 && p->C != 256) return 0;
+  if (p->Hd % 64 || p->Hd < 64 || p->N <= 0 || p->H <= 0 || p->W <= 0) return 0;
+  if (((uintptr_t)p->h1 % 16) || ((uintptr_t)p->w2 % 16) || ((uintptr_t)p->out % 16) || ((uintptr_t)p->dw_weight % 16) || ((uintptr_t)p->dw_bias % 16)) return 0;
+  if ((p->out_ld % 8) || (p->out_img_stride % 8)) return 0;
+  if (p->residual && (((uintptr_t)p->residual % 16) || (p->res_ld % 8) || (p->res_img_stride % 8))) return 0;
+  if (p->act != FBANET_ACT_GELU_TANH && p->act != FBANET_ACT_GELU_ERF) return 0;
+  return get_encode() != nullptr;
+}
+
+extern "C" int fbanet_leff_fc2_sm100(const fbanet_leff_fc2_params* p, void* stream) {
+  if (!fbanet_leff_fc2_supported(p)) return FBANET_E_UNSUPPORTED;
+  EncodeTiledFn encode = get_encode();
+  static thread_local LeffParams lp;
+  memset(&lp, 0, sizeof(lp));
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)p->Hd, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
+    const cuuint64_t strides[3] = {(cuuint64_t)p->Hd * 2, (cuuint64_t)p->Hd * 2 * p->W, (cuuint64_t)p->Hd * 2 * p->W * p->H};
+    const cuuint32_t box[4] = {64, LF_HW, LF_HH, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (encode(&lp.hmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->h1), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return FBANET_E_BADSHAPE;
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)p->Hd, (cuuint64_t)p->C};
+    const cuuint64_t strides[1] = {(cuuint64_t)p->Hd * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)p->C};
+    const cuuint32_t estr[2] = {1, 1};
+    if (encode(&lp.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p->w2), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return FBANET_E_BADSHAPE;
+  }
+  lp.dw_w = p->dw_weight; lp.dw_b = p->dw_bias; lp.bias2 = p->bias2;
+  lp.residual = reinterpret_cast<const bf16*>(p->residual); lp.out = reinterpret_cast<bf16*>(p->out);
+  lp.res_img_stride = p->res_img_stride; lp.out_img_stride = p->out_img_stride; lp.res_ld = p->res_ld; lp.out_ld = p->out_ld;
+  lp.N = p->N; lp.H = p->H; lp.W = p->W; lp.C = p->C; lp.Hd = p->Hd; lp.act = p->act;
+  lp.tiles_x = (p->W + LF_TW - 1) / LF_TW;
+  lp.tiles_y = (p->H + LF_TH - 1) / LF_TH;
+  lp.m_tiles = p->N * lp.tiles_x * lp.tiles_y;
+  lp.nchunks = p->Hd / 64;
+  const int b_bytes = p->C * 128;
+  int b = (200 * 1024 - 2 * LF_A_BYTES - 2 * LF_H_SLOT) / b_bytes;
+  lp.b_slots = b >= 8 ? 8 : (b >= 4 ? 4 : 2);
+  const size_t smem = 2 * LF_A_BYTES + (size_t)lp.b_slots * b_bytes + 2 * LF_H_SLOT + 1024;
+  static size_t opted = 0;
+  if (smem > opted) {
+    cudaError_t e = cudaFuncSetAttribute(leff_fc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cudaGetLastError(); set_last_error(e); return FBANET_E_LAUNCH; }
+    opted = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = lp.m_tiles < sms ? lp.m_tiles : sms;
+  leff_fc2_kernel<<<grid, LF_THREADS, smem, (cudaStream_t)stream>>>(lp);
+  return check_launch();
+}

@@ -189,6 +189,7 @@ class BaseModel(nn.Module):
         self.compute_dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[dtype]
         self.gelu_act = {"tanh": L.ACT_GELU_TANH, "erf": L.ACT_GELU_ERF}[gelu]
         self.impl = impl
+        self.fuse_leff = True
         self.head = nn.Conv2d(in_channels, E, 3, 1, 1)
         self.body = nn.Sequential(_ResBlock(E), _ResBlock(E))
         self.fusion = _FAF(E, num_frames)
@@ -373,6 +374,12 @@ class BaseModel(nn.Module):
         x1 = self._lin(P, key + ".proj", att.view(B, H, W, Cd), residual=x)
         ln2 = ops.layernorm(x1.view(-1, Cd), P[key + ".ln2.g"], P[key + ".ln2.b"]).view(B, H, W, Cd)
         h = self._lin(P, key + ".fc1", ln2, act=self.gelu_act)
+        if self._use_tc() and self.fuse_leff:
+            # depthwise 3x3 + GELU computed inside the fc2 GEMM as its A-operand producer (no HBM round trip)
+            if out is None:
+                out = self._new(B, H, W, Cd)
+            if ops.leff_fc2(h, P[key + ".dw.w"], P[key + ".dw.b"], P[key + ".fc2.w"], P[key + ".fc2.b"], out, x1, self.gelu_act) is not None:
+                return out
         h = ops.dwconv3x3(h, P[key + ".dw.w"], P[key + ".dw.b"], self.gelu_act)
         return self._lin(P, key + ".fc2", h, out=out, residual=x1)
 

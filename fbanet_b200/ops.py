@@ -265,6 +265,29 @@ def dwconv3x3(x: torch.Tensor, weight9c: torch.Tensor, bias: torch.Tensor, act: 
     return y
 
 
+def leff_fc2(h1: torch.Tensor, dw_w9c: torch.Tensor, dw_b: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, out: torch.Tensor,
+             residual: Optional[torch.Tensor], act: int) -> Optional[torch.Tensor]:
+    """Fused LeFF tail (bf16): ``out = Linear2(act(depthwise3x3(h1) + dw_b)) + b2 + residual``.  ``h1`` contiguous
+    ``[N,H,W,Hd]``; ``w2`` ``[C,Hd]`` bf16.  Returns ``None`` when the fused kernel does not take the shape (caller
+    then runs dwconv + GEMM)."""
+    assert h1.is_cuda and h1.is_contiguous() and h1.dtype == torch.bfloat16 and h1.dim() == 4
+    N, H, W, Hd = h1.shape
+    Cc = w2.shape[0]
+    assert w2.dtype == torch.bfloat16 and w2.is_contiguous() and w2.shape == (Cc, Hd) and out.shape == (N, H, W, Cc)
+    p = L.LeffFc2Params()
+    p.h1, p.dw_weight, p.dw_bias, p.w2, p.bias2 = h1.data_ptr(), dw_w9c.data_ptr(), dw_b.data_ptr(), w2.data_ptr(), b2.data_ptr()
+    op, _, old, ois = _cl(out)
+    p.out, p.out_ld, p.out_img_stride = op, old, ois
+    if residual is not None:
+        rp, _, rld, ris = _cl(residual)
+        p.residual, p.res_ld, p.res_img_stride = rp, rld, ris
+    p.N, p.H, p.W, p.C, p.Hd, p.act = N, H, W, Cc, Hd, act
+    if not L.load().fbanet_leff_fc2_supported(C.byref(p)):
+        return None
+    _call("fbanet_leff_fc2_sm100", p, tag=f"{Hd}->{Cc} @{H}x{W}")
+    return out
+
+
 def faf_gate(feat: torch.Tensor, wsum: torch.Tensor, want_gate: bool = True, want_gated: bool = False):
     """feat ``[B,F,H,W,C]`` contiguous -> gate ``[B,F-1,H,W]`` fp32 and/or gated features
     ``[B,H,W,F*C]`` (pixel-major; frame 0 copied, frames >= 1 scaled) for the tensor-core fusion GEMM."""

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 5
+#define FBANET_ABI_VERSION 6
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -193,6 +193,24 @@ typedef struct fbanet_dwconv_params {
   int32_t act;
 } fbanet_dwconv_params;
 
+/* K7+K5 fused (bf16, tensor cores): LeFF tail  out = Linear2(GELU(depthwise3x3(h1) + b_dw)) + b2 + residual
+ * (layers/locally_enhanced_feed_forward.py:39-57 + the residual of layers/fba_net.py:248).  h1 = GELU(Linear1(x))
+ * is a contiguous channels-last [N,H,W,Hd] tensor; the depthwise output never goes to HBM.
+ * dw_weight: fp32 [9][Hd]; w2: bf16 [C][Hd] (K-major); C in {64,128,256}; Hd % 64 == 0. */
+typedef struct fbanet_leff_fc2_params {
+  const void* h1;
+  const float* dw_weight;
+  const float* dw_bias;
+  const void* w2;
+  const float* bias2;
+  const void* residual;   /* optional view [N,H,W,C] */
+  void* out;              /* view [N,H,W,C] */
+  int64_t res_img_stride, out_img_stride;
+  int32_t res_ld, out_ld;
+  int32_t N, H, W, C, Hd;
+  int32_t act;            /* FBANET_ACT_GELU_TANH / _ERF (applied after the depthwise conv) */
+} fbanet_leff_fc2_params;
+
 /* K2 (gate): Federated-Affinity gate (blocks/federated_affinity_fusion.py:79-99).
  * gate[b][f-1][p] = sigmoid(| sum_{tap,c} wsum[tap][c] * (feat[b][f] - feat[b][0])(p+tap, c) |), f >= 1,
  * where wsum = sum over output channels of temporal_attn1.weight -- algebraically identical to the
@@ -225,6 +243,8 @@ int fbanet_abi_version(void);
 int fbanet_abi_sizeof(const char* struct_name);
 /* text of the last CUDA error seen by this library on the calling thread */
 const char* fbanet_last_cuda_error(void);
+/* 1 if the fused LeFF kernel takes this problem, else 0 */
+int fbanet_leff_fc2_supported(const fbanet_leff_fc2_params* p);
 /* 1 if the tcgen05 implicit-GEMM can run this problem, else 0 */
 int fbanet_conv_gemm_tcgen05_supported(const fbanet_conv_params* p);
 
@@ -237,6 +257,7 @@ int fbanet_layernorm_sm100(const fbanet_layernorm_params* p, void* stream);
 int fbanet_window_attention_sm100(const fbanet_attn_params* p, void* stream);
 int fbanet_dwconv3x3_sm100(const fbanet_dwconv_params* p, void* stream);
 int fbanet_faf_gate_sm100(const fbanet_faf_gate_params* p, void* stream);
+int fbanet_leff_fc2_sm100(const fbanet_leff_fc2_params* p, void* stream);
 int fbanet_tile_divide_sm100(const fbanet_tile_params* p, void* stream);
 int fbanet_tile_merge_sm100(const fbanet_tile_params* p, void* stream);
 

@@ -164,3 +164,22 @@ def test_unsupported_shapes_are_refused(cuda):
     x = torch.zeros(1, 8, 8, 32, device=cuda, dtype=BF)
     with pytest.raises(RuntimeError, match="unsupported"):
         ops.conv_gemm([x], torch.zeros(64, 32, device=cuda, dtype=BF), torch.empty(1, 8, 8, 64, device=cuda, dtype=BF), impl=L.IMPL_TCGEN05)
+
+
+@pytest.mark.parametrize("C,Hd,n,h,w", [(64, 256, 2, 32, 24), (128, 512, 2, 16, 40), (256, 1024, 1, 40, 40), (128, 512, 3, 20, 20), (64, 256, 70, 16, 16)])
+def test_fused_leff_dwconv_fc2(cuda, C, Hd, n, h, w):
+    """LeFF tail fused on the tensor cores: Linear2(GELU(dwconv3x3(h1) + b)) + b2 + residual
+    (locally_enhanced_feed_forward.py:39-57); the last case has more tiles than SMs (persistent loop, phase wrap)."""
+    from fbanet_b200 import ops, _lib as L
+    h1 = _r(n, Hd, h, w, seed=1)
+    dw, db = _r(Hd, 1, 3, 3, seed=2, scale=0.3), _r(Hd, seed=3, scale=0.1)
+    w2, b2 = _r(C, Hd, seed=4, scale=1 / math.sqrt(Hd)), _r(C, seed=5)
+    res = _r(n, C, h, w, seed=6)
+    mid = F.gelu(F.conv2d(h1, dw, db, padding=1, groups=Hd), approximate="tanh").to(BF).float()
+    ref = F.linear(mid.permute(0, 2, 3, 1), w2, b2) + res.permute(0, 2, 3, 1)
+    buf = torch.zeros(n, h, w, 2 * C, device=cuda, dtype=BF)  # output into a channel slice, as the concat buffers do
+    out = ops.leff_fc2(_nhwc(h1, cuda), dw.reshape(Hd, 9).t().contiguous().to(cuda), db.to(cuda), w2.to(cuda, BF), b2.to(cuda), buf[..., C:],
+                       _nhwc(res, cuda), L.ACT_GELU_TANH)
+    assert out is not None
+    _check(buf[..., C:], ref, tol=3e-2)
+    assert buf[..., :C].abs().max().item() == 0
