@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
       // ---- staged epilogue: 64-column chunks -> swizzled 128x64 bf16 smem tile -> one TMA store per chunk.
       // (Per-thread 16-byte global stores touch 32 lines per instruction and cap an SM at ~16 B/clk.)
       uint8_t* stage = smem_stage + half * 16384;
-      uint8_t* row_ptr = stage + (size_t)row * 128;
+      const uint32_t row_addr = smem_u32(stage) + (uint32_t)row * 128u;
       const int r7 = row & 7;
       const int nchunks = BN >> 6;
       const bool has_res = p.residual != nullptr;
@@ -398,9 +398,10 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
             const float4 b0 = *reinterpret_cast<const float4*>(bs + c * 8), b1 = *reinterpret_cast<const float4*>(bs + c * 8 + 4);
             f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
             apply_act_vec<8>(f, p.act, alpha);
-            uint4* sp = reinterpret_cast<uint4*>(row_ptr + ((c ^ r7) << 4));   // SWIZZLE_128B position of chunk c in this row
+            const uint32_t saddr = row_addr + (uint32_t)((c ^ r7) << 4);   // SWIZZLE_128B position of chunk c in this row
             if (has_res) {
-              const uint4 rv = *sp;
+              uint4 rv;
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(saddr));
               const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) { f[2 * e] += __uint_as_float(ru[e] << 16); f[2 * e + 1] += __uint_as_float(ru[e] & 0xffff0000u); }
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
               __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
               o[e] = *reinterpret_cast<uint32_t*>(&h);
             }
-            *sp = make_uint4(o[0], o[1], o[2], o[3]);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]));
           }
           fence_proxy_async();                           // generic-proxy smem writes -> visible to the TMA engine
           named_bar_sync(1 + half, 128);

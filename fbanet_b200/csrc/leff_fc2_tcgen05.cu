@@ -22,7 +22,9 @@ constexpr int LF_HW = LF_TW + 2, LF_HH = LF_TH + 2;        // halo tile
 constexpr int LF_H_BYTES = LF_HW * LF_HH * 128;            // 23040: halo pixels x 64 ch bf16
 constexpr int LF_H_SLOT = 23552;                           // padded to 1 KB
 constexpr int LF_A_BYTES = 128 * 128;                      // A tile: 128 px x 64 ch bf16
-constexpr int LF_THREADS = 384;
+constexpr int LF_DW_WARPS = 16;                            // depthwise/epilogue warps (4 output rows per thread)
+constexpr int LF_THREADS = 128 + 32 * LF_DW_WARPS;
+constexpr int LF_H_SLOTS = 4;                              // halo ring depth: TMA latency (~1-2 us) spans several chunks of compute
 
 struct LeffParams {
   CUtensorMap hmap;   // h1 [N,H,W,Hd]: box {64, 10, 18, 1}, no swizzle (read by CUDA cores)
@@ -40,7 +42,7 @@ struct LeffParams {
 
 __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_constant__ LeffParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t h_full[2], h_empty[2], a_full[2], a_empty[2], b_full[8], b_empty[8], tmem_full[2], tmem_empty[2];
+  __shared__ __align__(8) uint64_t h_full[LF_H_SLOTS], h_empty[LF_H_SLOTS], a_full[2], a_empty[2], b_full[8], b_empty[8], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float bias_s[256];
 
@@ -55,10 +57,10 @@ __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_co
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.hmap); tma_prefetch_desc(&p.wmap); }
   if (warp == 1 && lane == 0) {
+    for (int s = 0; s < LF_H_SLOTS; ++s) { mbar_init(&h_full[s], 1); mbar_init(&h_empty[s], LF_DW_WARPS); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&h_full[s], 1); mbar_init(&h_empty[s], 8);
-      mbar_init(&a_full[s], 8); mbar_init(&a_empty[s], 1);
-      mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8);
+      mbar_init(&a_full[s], LF_DW_WARPS); mbar_init(&a_empty[s], 1);
+      mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], LF_DW_WARPS);
     }
     for (int s = 0; s < p.b_slots; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     fence_barrier_init();
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_co
   }
   if (warp >= 4) {
     const int i = threadIdx.x - 128;
-    bias_s[i] = (p.bias2 && i < C) ? __ldg(p.bias2 + i) : 0.f;
+    if (i < 256) bias_s[i] = (p.bias2 && i < C) ? __ldg(p.bias2 + i) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -85,8 +87,8 @@ __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_co
       const int img = mt / tiles_per_img, r = mt % tiles_per_img;
       const int y0 = (r / p.tiles_x) * LF_TH, x0 = (r % p.tiles_x) * LF_TW;
       for (int c = 0; c < p.nchunks; ++c, ++g) {
-        const uint32_t hs = g & 1;
-        mbar_wait(&h_empty[hs], ((g >> 1) & 1) ^ 1);
+        const uint32_t hs = g & (LF_H_SLOTS - 1);
+        mbar_wait(&h_empty[hs], ((g / LF_H_SLOTS) & 1) ^ 1);
         if (elect_one()) {
           mbar_expect_tx(&h_full[hs], (uint32_t)LF_H_BYTES);
           tma_load_4d(smem_h + hs * LF_H_SLOT, &p.hmap, &h_full[hs], c * 64, x0 - 1, y0 - 1, img);
@@ -137,11 +139,13 @@ __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_co
     }
   } else if (warp >= 4) {
     // ================= depthwise producer + epilogue =================
-    const int tl = threadIdx.x - 128;          // 0..255
+    constexpr int RPT = 128 / (2 * LF_DW_WARPS);   // output rows per thread (4 with 16 warps)
+    constexpr int NCS = LF_DW_WARPS / 4;           // epilogue column slices
+    const int tl = threadIdx.x - 128;
     const int cg4 = tl & 15;                   // 4-channel group inside the 64-channel chunk
-    const int pt = tl >> 4;                    // 0..15
-    const int col = pt & 7, rhalf = pt >> 3;   // output column, rows rhalf*8 .. +7
-    const int q = warp & 3, half = (warp - 4) >> 2;   // epilogue: TMEM lane quarter / column half
+    const int pt = tl >> 4;                    // 0 .. 2*LF_DW_WARPS-1
+    const int col = pt & 7, rq = pt >> 3;      // output column, rows rq*RPT .. +RPT-1
+    const int q = warp & 3, cs = (warp - 4) >> 2;     // epilogue: TMEM lane quarter / column slice
     const bool erf_gelu = p.act == FBANET_ACT_GELU_ERF;
 
     auto epilogue = [&](int mt, int it) {
@@ -152,11 +156,12 @@ __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_co
       const bool valid = y < p.H && x < p.W;
       mbar_wait(&tmem_full[acc], ((uint32_t)it >> 1) & 1);
       tc_fence_after();
-      const int ncols = C / 2, cbeg = half * ncols;
+      const int ncols = C / NCS, cbeg = cs * ncols;   // 16, 32 or 64 columns per warp
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C + cbeg);
       for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(taddr0 + c0, v);
+        const int nc = ncols - c0 >= 32 ? 32 : 16;
+        if (nc == 32) tmem_ld32(taddr0 + c0, v); else tmem_ld16(taddr0 + c0, v);
         tmem_ld_wait();
         if (valid) {
           const int64_t pix = (int64_t)y * p.W + x;
@@ -164,6 +169,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_co
           bf16* op = p.out + img * p.out_img_stride + pix * p.out_ld + cbeg + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
+            if (j >= nc) break;
             float f[8];
             const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cbeg + c0 + j), b1 = *reinterpret_cast<const float4*>(bias_s + cbeg + c0 + j + 4);
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_co
     int it = 0, pend_mt = -1, pend_it = 0;
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++it) {
       for (int c = 0; c < p.nchunks; ++c, ++g) {
-        const uint32_t hs = g & 1;
+        const uint32_t hs = g & (LF_H_SLOTS - 1), as = g & 1;
         // depthwise weights / bias of this thread's 4 channels (L1-resident after the first tile)
         const int ch0 = c * 64 + cg4 * 4;
         float w[9][4], bdw[4];
@@ -202,28 +208,30 @@ __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_co
           const float4 a = __ldg(reinterpret_cast<const float4*>(p.dw_b + ch0));
           bdw[0] = a.x; bdw[1] = a.y; bdw[2] = a.z; bdw[3] = a.w;
         }
-        float acc[8][4];
+        float acc[RPT][4];
 #pragma unroll
-        for (int o = 0; o < 8; ++o)
+        for (int o = 0; o < RPT; ++o)
 #pragma unroll
           for (int e = 0; e < 4; ++e) acc[o][e] = bdw[e];
-        mbar_wait(&h_full[hs], (g >> 1) & 1);       // halo tile landed
-        mbar_wait(&a_empty[hs], ((g >> 1) & 1) ^ 1);  // A slot consumed by the MMAs that used it last
-        const uint8_t* hbase = smem_h + hs * LF_H_SLOT + ((rhalf * 8) * LF_HW + col) * 128 + cg4 * 8;
-        uint8_t* abase = smem_a + hs * LF_A_BYTES;
+        mbar_wait(&h_full[hs], (g / LF_H_SLOTS) & 1);  // halo tile landed
+        mbar_wait(&a_empty[as], ((g >> 1) & 1) ^ 1);   // A slot consumed by the MMAs that used it last
+        // explicit shared-space addresses: through generic pointers these became LD/ST (long-scoreboard) instead of LDS/STS
+        const uint32_t hbase = smem_u32(smem_h) + hs * LF_H_SLOT + ((rq * RPT) * LF_HW + col) * 128 + cg4 * 8;
+        const uint32_t abase = smem_u32(smem_a) + as * LF_A_BYTES;
 #pragma unroll
-        for (int hr = 0; hr < 10; ++hr) {           // halo rows feeding this thread's 8 output rows
+        for (int hr = 0; hr < RPT + 2; ++hr) {      // halo rows feeding this thread's RPT output rows
           float rv[3][4];
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
-            const uint2 u = *reinterpret_cast<const uint2*>(hbase + (hr * LF_HW + kx) * 128);
+            uint2 u;
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(u.x), "=r"(u.y) : "r"(hbase + (uint32_t)((hr * LF_HW + kx) * 128)));
             rv[kx][0] = __uint_as_float(u.x << 16); rv[kx][1] = __uint_as_float(u.x & 0xffff0000u);
             rv[kx][2] = __uint_as_float(u.y << 16); rv[kx][3] = __uint_as_float(u.y & 0xffff0000u);
           }
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
             const int o = hr - ky;                   // output row (within the thread's 8) this halo row feeds with tap row ky
-            if (o >= 0 && o < 8) {
+            if (o >= 0 && o < RPT) {
 #pragma unroll
               for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
@@ -235,17 +243,18 @@ __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_co
             float f[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) f[e] = erf_gelu ? gelu_erf(acc[o][e]) : gelu_tanh_fast(acc[o][e]);
-            const int rr = (rhalf * 8 + o) * LF_TW + col;        // A-tile row = pixel index in the 8x16 tile
+            const int rr = (rq * RPT + o) * LF_TW + col;        // A-tile row = pixel index in the 8x16 tile
             const __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
             uint2 ov;
             ov.x = *reinterpret_cast<const uint32_t*>(&h0);
             ov.y = *reinterpret_cast<const uint32_t*>(&h1);
-            *reinterpret_cast<uint2*>(abase + rr * 128 + (((cg4 >> 1) ^ (rr & 7)) << 4) + (cg4 & 1) * 8) = ov;
+            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(abase + (uint32_t)(rr * 128 + (((cg4 >> 1) ^ (rr & 7)) << 4) + (cg4 & 1) * 8)),
+                         "r"(ov.x), "r"(ov.y));
           }
         }
         fence_proxy_async();                          // A tile written through the generic proxy -> visible to the tensor core
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&a_full[hs]); mbar_arrive(&h_empty[hs]); }
+        if (lane == 0) { mbar_arrive(&a_full[as]); mbar_arrive(&h_empty[hs]); }
         if (c == 0 && pend_mt >= 0) { epilogue(pend_mt, pend_it); pend_mt = -1; }
       }
       pend_mt = mt; pend_it = it;
@@ -308,9 +317,9 @@ extern "C" int fbanet_leff_fc2_sm100(const fbanet_leff_fc2_params* p, void* stre
   lp.m_tiles = p->N * lp.tiles_x * lp.tiles_y;
   lp.nchunks = p->Hd / 64;
   const int b_bytes = p->C * 128;
-  int b = (200 * 1024 - 2 * LF_A_BYTES - 2 * LF_H_SLOT) / b_bytes;
+  int b = (208 * 1024 - 2 * LF_A_BYTES - LF_H_SLOTS * LF_H_SLOT) / b_bytes;
   lp.b_slots = b >= 8 ? 8 : (b >= 4 ? 4 : 2);
-  const size_t smem = 2 * LF_A_BYTES + (size_t)lp.b_slots * b_bytes + 2 * LF_H_SLOT + 1024;
+  const size_t smem = 2 * LF_A_BYTES + (size_t)lp.b_slots * b_bytes + LF_H_SLOTS * LF_H_SLOT + 1024;
   static size_t opted = 0;
   if (smem > opted) {
     cudaError_t e = cudaFuncSetAttribute(leff_fc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -57,7 +57,20 @@ def head(B, S):
     return (lambda: ops.head_conv(x, w, b, BF)), (x.numel() * 4 + B * 14 * S * S * 64 * 2) / 1e9
 
 
+def leff(B, S, C):
+    Hd = 4 * C
+    h1 = (torch.rand(B, S, S, Hd, device=dev) - 0.5).to(BF)
+    dw, db = torch.rand(9, Hd, device=dev) - 0.5, torch.rand(Hd, device=dev)
+    w2, b2 = ((torch.rand(C, Hd, device=dev) - 0.5) * 0.05).to(BF), torch.zeros(C, device=dev)
+    res = torch.zeros(B, S, S, C, device=dev, dtype=BF)
+    out = torch.empty_like(res)
+    return (lambda: ops.leff_fc2(h1, dw, db, w2, b2, out, res, L.ACT_GELU_TANH)), 2 * (h1.numel() + 2 * res.numel()) / 1e9
+
+
 CASES = {
+    "leff_dec1_128": lambda: leff(64, 160, 128),
+    "leff_dec0_256": lambda: leff(64, 80, 256),
+    "leff_enc0_64": lambda: leff(64, 160, 64),
     "attn_dec1_128x8_s5": lambda: attn(64, 160, 128, 8, 5),
     "attn_dec1_128x8_s0": lambda: attn(64, 160, 128, 8, 0),
     "attn_dec0_256x16_s5": lambda: attn(64, 80, 256, 16, 5),
