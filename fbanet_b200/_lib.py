@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libfbanet_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -73,6 +73,13 @@ class HeadConvParams(C.Structure):
     ]
 
 
+class AssembleParams(C.Structure):
+    _fields_ = [
+        ("sr", C.c_void_p), ("base", C.c_void_p), ("out", C.c_void_p), ("base_img_stride", C.c_int64), ("dtype", C.c_int32),
+        ("N", C.c_int32), ("C", C.c_int32), ("Cp", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+    ]
+
+
 class LayerNormParams(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("y", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("rows", C.c_int64),
@@ -122,13 +129,13 @@ class TileParams(C.Structure):
 
 STRUCTS = {
     "fbanet_src": Src, "fbanet_conv_params": ConvParams, "fbanet_warp_params": WarpParams,
-    "fbanet_to_nhwc_params": ToNhwcParams, "fbanet_s2d_params": S2dParams, "fbanet_head_conv_params": HeadConvParams, "fbanet_layernorm_params": LayerNormParams, "fbanet_attn_params": AttnParams,
+    "fbanet_to_nhwc_params": ToNhwcParams, "fbanet_s2d_params": S2dParams, "fbanet_head_conv_params": HeadConvParams, "fbanet_assemble_params": AssembleParams, "fbanet_layernorm_params": LayerNormParams, "fbanet_attn_params": AttnParams,
     "fbanet_dwconv_params": DwconvParams, "fbanet_faf_gate_params": FafGateParams, "fbanet_leff_fc2_params": LeffFc2Params, "fbanet_tile_params": TileParams,
 }
 
 # every symbol include/fbanet_b200.h declares
 OPS = {
-    "fbanet_warp_sm100": WarpParams, "fbanet_to_nhwc_sm100": ToNhwcParams, "fbanet_space_to_depth_sm100": S2dParams, "fbanet_head_conv_sm100": HeadConvParams, "fbanet_conv_gemm_sm100": ConvParams,
+    "fbanet_warp_sm100": WarpParams, "fbanet_to_nhwc_sm100": ToNhwcParams, "fbanet_space_to_depth_sm100": S2dParams, "fbanet_head_conv_sm100": HeadConvParams, "fbanet_assemble_sm100": AssembleParams, "fbanet_conv_gemm_sm100": ConvParams,
     "fbanet_layernorm_sm100": LayerNormParams, "fbanet_window_attention_sm100": AttnParams, "fbanet_dwconv3x3_sm100": DwconvParams,
     "fbanet_faf_gate_sm100": FafGateParams, "fbanet_leff_fc2_sm100": LeffFc2Params, "fbanet_tile_divide_sm100": TileParams, "fbanet_tile_merge_sm100": TileParams,
 }

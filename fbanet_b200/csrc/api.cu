@@ -44,6 +44,7 @@ extern "C" int fbanet_abi_sizeof(const char* n) {
   SZ(fbanet_to_nhwc_params);
   SZ(fbanet_s2d_params);
   SZ(fbanet_head_conv_params);
+  SZ(fbanet_assemble_params);
   SZ(fbanet_layernorm_params);
   SZ(fbanet_attn_params);
   SZ(fbanet_dwconv_params);

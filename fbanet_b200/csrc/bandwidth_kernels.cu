@@ -230,6 +230,33 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const fbanet_head_conv_p
   }
 }
 
+// final assembly: channels-last SR + bilinear x4 of the base frame -> planar fp32.  One thread per output pixel; lanes
+// run along X so every planar store is a coalesced 128-byte run.
+template <typename T>
+__global__ void __launch_bounds__(256) assemble_kernel(const fbanet_assemble_params p) {
+  const int64_t total = (int64_t)p.N * p.H * p.W;
+  const int Hb = p.H >> 2, Wb = p.W >> 2;
+  const T* sr = reinterpret_cast<const T*>(p.sr);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % p.W);
+    const int y = (int)((idx / p.W) % p.H);
+    const int64_t n = idx / ((int64_t)p.W * p.H);
+    float sy = 0.25f * (y + 0.5f) - 0.5f, sx = 0.25f * (x + 0.5f) - 0.5f;
+    sy = sy < 0.f ? 0.f : sy;
+    sx = sx < 0.f ? 0.f : sx;
+    const int yb = (int)sy, xb = (int)sx;
+    const int y1 = yb + (yb < Hb - 1 ? 1 : 0), x1 = xb + (xb < Wb - 1 ? 1 : 0);
+    const float wy = sy - yb, wx = sx - xb, hy = 1.f - wy, hx = 1.f - wx;
+    const T* s = sr + idx * p.Cp;
+    for (int c = 0; c < p.C; ++c) {
+      const float* bp = p.base + n * p.base_img_stride + (int64_t)c * Hb * Wb;
+      const float bl = hy * (hx * __ldg(bp + yb * Wb + xb) + wx * __ldg(bp + yb * Wb + x1)) +
+                       wy * (hx * __ldg(bp + y1 * Wb + xb) + wx * __ldg(bp + y1 * Wb + x1));
+      p.out[((n * p.C + c) * p.H + y) * p.W + x] = to_f32<T>(s[c]) + bl;
+    }
+  }
+}
+
 // channels-last view -> space-to-depth(2), one thread per 16-byte vector of the destination
 template <typename T>
 __global__ void __launch_bounds__(256) s2d_kernel(const fbanet_s2d_params p) {
@@ -677,6 +704,15 @@ extern "C" int fbanet_head_conv_sm100(const fbanet_head_conv_params* p, void* st
   if (p->dtype == FBANET_F32) return launch_head<float>(p, (cudaStream_t)stream);
   if (p->dtype == FBANET_BF16) return launch_head<bf16>(p, (cudaStream_t)stream);
   return FBANET_E_DTYPE;
+}
+
+extern "C" int fbanet_assemble_sm100(const fbanet_assemble_params* p, void* stream) {
+  if (!p || !p->sr || !p->base || !p->out || p->N <= 0 || p->C <= 0 || p->Cp < p->C || (p->H % 4) || (p->W % 4)) return FBANET_E_BADSHAPE;
+  const int64_t total = (int64_t)p->N * p->H * p->W;
+  if (p->dtype == FBANET_F32) assemble_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  else if (p->dtype == FBANET_BF16) assemble_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  else return FBANET_E_DTYPE;
+  return check_launch();
 }
 
 extern "C" int fbanet_space_to_depth_sm100(const fbanet_s2d_params* p, void* stream) {

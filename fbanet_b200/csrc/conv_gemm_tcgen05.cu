@@ -78,7 +78,8 @@ __device__ __forceinline__ void apply_act_vec(float (&f)[NV], const int act, con
 
 // bias + activation + residual + store of 32 (or 16) accumulator columns of one pixel row
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t (&v)[32], const int nc, const int col0, const int img,
-                                               const int y, const int x, const float alpha, const float* bias_s) {
+                                               const int y, const int x, const float alpha, const float* bias_s,
+                                               const uint4* rpre = nullptr) {
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = (j < nc) ? __uint_as_float(v[j]) : 0.f;
@@ -133,10 +134,10 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         if (j < nc) {
-          float t[8];
-          load_vec<bf16, 8>(rp + j, t);
+          const uint4 rv = rpre ? rpre[j >> 3] : *reinterpret_cast<const uint4*>(rp + j);   // rpre: fetched before the MMA wait
+          const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[j + e] += t[e];
+          for (int e = 0; e < 4; ++e) { f[j + 2 * e] += __uint_as_float(ru[e] << 16); f[j + 2 * e + 1] += __uint_as_float(ru[e] & 0xffff0000u); }
         }
       }
     }
@@ -442,6 +443,14 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
         const int img = mt / tiles_per_img, r = mt % tiles_per_img;
         const int y = (r / p.tiles_x) * p.th + ly, x = (r % p.tiles_x) * p.tw + lx;
         const bool valid = (ly < p.th) && (y < p.Ho) && (x < p.Wo);
+        // the residual of the first 32-column chunk is fetched while the MMAs of this tile are still running
+        uint4 rpre[4];
+        const bool pre = valid && p.residual != nullptr && ncols >= 32;
+        if (pre) {
+          const bf16* rp = p.residual + img * p.res_img_stride + ((int64_t)y * p.Wo + x) * p.res_ld + nt * BN + cbeg;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rpre[j] = *reinterpret_cast<const uint4*>(rp + j * 8);
+        }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cbeg);
@@ -450,7 +459,7 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
           const int nc = (ncols - c0 >= 32) ? 32 : 16;
           if (nc == 32) tmem_ld32(taddr0 + c0, v); else tmem_ld16(taddr0 + c0, v);
           tmem_ld_wait();
-          if (valid) epilogue_chunk(p, v, nc, nt * BN + cbeg + c0, img, y, x, alpha, bias_s + cbeg + c0);
+          if (valid) epilogue_chunk(p, v, nc, nt * BN + cbeg + c0, img, y, x, alpha, bias_s + cbeg + c0, (pre && c0 == 0) ? rpre : nullptr);
           __syncwarp();
         }
         tc_fence_before();

@@ -497,8 +497,14 @@ class BaseModel(nn.Module):
         y2 = self._conv3(P, "output_proj_2", [d1_2], act=L.ACT_PRELU, alpha=P["output_proj_2.alpha"])  # :313
         t1 = self._conv3(P, "tail.0.0", [y2], out=self._new(B, 2 * S, 2 * S, E), store=L.STORE_CONVT2)  # :315 (PixelShuffle in the store)
         t2 = self._conv3(P, "tail.0.2", [t1], out=self._new(B, 4 * S, 4 * S, E), store=L.STORE_CONVT2)
-        out = torch.empty((B, Cin, 4 * S, 4 * S), device=x.device, dtype=torch.float32)
-        self._conv3(P, "tail.1", [t2], out=out, store=L.STORE_NCHW_BASE, base=x[:, 0], cout_store=Cin)  # :315-320 (+ bilinear x4 base)
+        if self._use_tc():
+            # last conv stores channels-last (16 zero-padded columns, 8 kept); the planar fp32 + bilinear-base assembly
+            # is a separate coalesced bandwidth kernel (:315-320)
+            t3 = self._conv3(P, "tail.1", [t2], out=self._new(B, 4 * S, 4 * S, 8), cout_store=8)
+            out = ops.assemble(t3, x[:, 0], Cin)
+        else:
+            out = torch.empty((B, Cin, 4 * S, 4 * S), device=x.device, dtype=torch.float32)
+            self._conv3(P, "tail.1", [t2], out=out, store=L.STORE_NCHW_BASE, base=x[:, 0], cout_store=Cin)  # :315-320 (+ bilinear x4 base)
         if st is not None:
             st.update({"output_proj": y1, "output_proj_2": y2, "tail.ps1": t1, "tail.ps2": t2, "out": out})
         return out

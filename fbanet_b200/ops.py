@@ -214,6 +214,22 @@ def head_conv(x: torch.Tensor, weight_kc: torch.Tensor, bias: torch.Tensor, dtyp
     return out
 
 
+def assemble(sr: torch.Tensor, base: torch.Tensor, C_out: int) -> torch.Tensor:
+    """``out[n,c] = sr[n,:,:,c] + bilinear_x4(base[n,c])``: channels-last SR ``[N,4h,4w,Cp]`` + planar fp32 base
+    ``[N,C,h,w]`` (a view of the burst's frame 0) -> planar fp32 ``[N,C,4h,4w]``."""
+    assert sr.is_cuda and sr.is_contiguous() and sr.dim() == 4
+    N, H, W, Cp = sr.shape
+    assert base.dtype == torch.float32 and base.shape == (N, C_out, H // 4, W // 4)
+    assert base.stride(3) == 1 and base.stride(2) == W // 4 and base.stride(1) == (H // 4) * (W // 4)
+    out = torch.empty((N, C_out, H, W), device=sr.device, dtype=torch.float32)
+    p = L.AssembleParams()
+    p.sr, p.base, p.out = sr.data_ptr(), base.data_ptr(), out.data_ptr()
+    p.base_img_stride = base.stride(0) if N > 1 else 0
+    p.dtype, p.N, p.C, p.Cp, p.H, p.W = _DT[sr.dtype], N, C_out, Cp, H, W
+    _call("fbanet_assemble_sm100", p)
+    return out
+
+
 def space_to_depth(x: torch.Tensor) -> torch.Tensor:
     """channels-last view ``[N,H,W,C]`` -> contiguous ``[N,H/2,W/2,4C]``, channel ``(ys*2+xs)*C + c``."""
     ptr, Cc, ld, istr = _cl(x)

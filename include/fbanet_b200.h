@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 6
+#define FBANET_ABI_VERSION 7
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -143,6 +143,19 @@ typedef struct fbanet_head_conv_params {
   int32_t frames, C, H, W, Cout;
 } fbanet_head_conv_params;
 
+/* Final assembly (models/fba_net.py:317-320): out[n][c][Y][X] = sr(n,Y,X,c) + bilinear_x4(base)[n][c][Y][X], with
+ * sr channels-last [N,4h,4w,Cp] (first C channels used), base planar fp32 [n][c][h][w] (frame 0 of the burst, half-pixel
+ * centres, edge clamp), out planar fp32.  Splitting this from the last conv keeps that conv's epilogue a plain
+ * channels-last store and makes the planar fp32 writes fully coalesced. */
+typedef struct fbanet_assemble_params {
+  const void* sr;
+  const float* base;
+  float* out;
+  int64_t base_img_stride;
+  int32_t dtype;          /* of sr */
+  int32_t N, C, Cp, H, W; /* H, W = output (x4) size */
+} fbanet_assemble_params;
+
 /* channels-last view [N,H,W,C] -> contiguous [N,H/2,W/2,4C], channel (ys*2+xs)*C + c = src(2y+ys, 2x+xs, c).
  * Feeds the 4x4 stride-2 downsampling convs (layers/downsample_flatten.py:6-13) to the TMA/tcgen05 path. */
 typedef struct fbanet_s2d_params {
@@ -252,6 +265,7 @@ int fbanet_warp_sm100(const fbanet_warp_params* p, void* stream);
 int fbanet_to_nhwc_sm100(const fbanet_to_nhwc_params* p, void* stream);
 int fbanet_space_to_depth_sm100(const fbanet_s2d_params* p, void* stream);
 int fbanet_head_conv_sm100(const fbanet_head_conv_params* p, void* stream);
+int fbanet_assemble_sm100(const fbanet_assemble_params* p, void* stream);
 int fbanet_conv_gemm_sm100(const fbanet_conv_params* p, void* stream);
 int fbanet_layernorm_sm100(const fbanet_layernorm_params* p, void* stream);
 int fbanet_window_attention_sm100(const fbanet_attn_params* p, void* stream);

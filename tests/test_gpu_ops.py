@@ -316,3 +316,14 @@ def test_head_conv_direct(cuda, dt, cin, hw):
     wkc = w.permute(2, 3, 1, 0).reshape(9 * cin, 64).contiguous()
     out = ops.head_conv(x.to(cuda), wkc.to(cuda), b.to(cuda), dt)
     _close(out.permute(0, 3, 1, 2), ref, dt)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_assemble_sr_plus_bilinear_base(cuda, dt):
+    """models/fba_net.py:317-320: channels-last SR + bilinear x4 (align_corners=False) of frame 0 -> planar fp32."""
+    from fbanet_b200 import ops
+    sr = _r(dt, 2, 32, 48, 8, seed=1)
+    burst = torch.rand(2, 5, 3, 8, 12, generator=torch.Generator().manual_seed(2))
+    ref = sr[..., :3].permute(0, 3, 1, 2) + F.interpolate(burst[:, 0], scale_factor=4, mode="bilinear", align_corners=False)
+    out = ops.assemble(sr.to(cuda, dt), burst.to(cuda)[:, 0], 3)
+    assert (out.cpu() - ref).abs().max().item() < 1e-5
