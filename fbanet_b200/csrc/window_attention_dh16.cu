@@ -1,0 +1,307 @@
+// K6, head_dim = 16 / window 10x10 specialisation (bf16): the decoder and bottleneck stages of the model
+// (dim 256 x 16 heads, dim 128 x 8 heads -- 75 % of all score elements of a forward).
+//
+// One WARP owns one (window, head) item end to end; a CTA is 12 independent warps working on windows of the
+// same head, so the only CTA-wide barrier is the one after the head's relative-position bias has been
+// expanded into shared memory.  Per item the warp
+//   * stages the head's q | k | v rows of the (cyclically shifted) window with cp.async -- 100 rows x 32 B each,
+//     XOR-swizzled so every ldmatrix phase is bank-conflict free (the next item's rows are in flight while this
+//     one computes; q is double buffered, k/v are refilled as soon as their fragments are in registers);
+//   * keeps ALL of K (14 key tiles) and V (7 key steps x 2 channel tiles) as MMA B fragments in registers
+//     (56 registers) and walks the 7 query tiles: S = bias + q k^T is ONE m16n8k16 MMA per key tile whose
+//     accumulator is initialised with the bias fragment (stored fragment-major in smem: one LDS.128 per tile),
+//     softmax in registers, O = P v with the probabilities re-used as the A operand, and the row sum from one
+//     extra MMA against an all-ones B fragment;
+//   * writes O over the q rows it has consumed and streams it out with 16-byte stores.
+// The q columns of the fused qkv GEMM may be pre-multiplied by scale*log2(e) (`q_prescaled`), which removes
+// the per-score FFMA.  Bound: MUFU.EX2 (one per score) -- see DESIGN.md "K6".
+#include "common.cuh"
+
+namespace fbanet {
+
+namespace {
+
+constexpr int WIN = 10, NTOK = 100, NT = 14, MT = 7, WARPS = 12;
+constexpr int ROWB = 32;                      // bytes per staged row (16 bf16)
+constexpr int TILE_BYTES = 112 * ROWB;        // one q / k / v buffer
+constexpr int WARP_BYTES = 4 * TILE_BYTES;    // q0 | q1 | k | v
+constexpr int BIAS_BYTES = MT * NT * 32 * 16; // float4 per (query tile, key tile, lane)
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void cp16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// byte offset of 16-byte chunk `c` (0/1) of row `row` inside a swizzled [112][32 B] tile
+__device__ __forceinline__ uint32_t swz(int row, int c) { return (uint32_t)(row * ROWB + ((c ^ ((row >> 2) & 1)) << 4)); }
+
+template <bool PRESCALED>
+__global__ void __launch_bounds__(WARPS * 32, 1) window_attention_dh16_kernel(const fbanet_attn_params p, const int win_chunk) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3, mi = lane >> 3, l7 = lane & 7;
+  const int head = blockIdx.x;   // heads fastest: CTAs that share token rows are co-resident (DRAM page / L2 locality)
+  const int H = p.H, W = p.W, shift = p.shift;
+  const int nwx = W / WIN, nwy = H / WIN, nw_img = nwx * nwy;
+  const int total_windows = p.B * nw_img;
+  const int w_begin = blockIdx.y * win_chunk, w_end = min(w_begin + win_chunk, total_windows);
+
+  float4* biasF = reinterpret_cast<float4*>(smem);
+  const uint32_t smem_u = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t wbase = smem_u + BIAS_BYTES + warp * WARP_BYTES;
+  const uint32_t Ks = wbase + 2 * TILE_BYTES, Vs = wbase + 3 * TILE_BYTES;
+  uint8_t* wgen = smem + BIAS_BYTES + warp * WARP_BYTES;
+
+  const bf16* qkv = reinterpret_cast<const bf16*>(p.qkv) + head * 16;
+  bf16* outp = reinterpret_cast<bf16*>(p.out) + head * 16;
+  const int64_t ld = p.qkv_ld, old = p.out_ld;
+  const int C = p.C;
+
+  // q | k | v rows of window `wid` -> (q buffer `qb`, k, v); 200 (row, chunk) slots over 32 lanes
+  auto stage = [&](int wid, int qb) {
+    const int b = wid / nw_img, wl = wid - b * nw_img;
+    const int wy = wl / nwx, wx = wl - wy * nwx;
+    const int ty0 = wy * WIN + shift, tx0 = wx * WIN + shift;
+    const bf16* ibase = qkv + (int64_t)b * H * W * ld;
+    const uint32_t Qs = wbase + qb * TILE_BYTES;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const int e = lane + 32 * i;
+      if (e < 2 * NTOK) {
+        const int j = e >> 1, c = e & 1;
+        const int jy = (j * 205) >> 11, jx = j - jy * WIN;
+        int y = ty0 + jy, x = tx0 + jx;
+        if (y >= H) y -= H;
+        if (x >= W) x -= W;
+        const bf16* src = ibase + (int64_t)(y * W + x) * ld + c * 8;
+        const uint32_t d = swz(j, c);
+        cp16(Qs + d, src);
+        cp16(Ks + d, src + C);
+        cp16(Vs + d, src + 2 * C);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // zero the padding rows (100..111) of this warp's buffers once: padded keys must be finite, padded v rows zero
+  for (int e = lane; e < 4 * 12 * 2; e += 32) {
+    const int buf = e / 24, r = NTOK + (e % 24) / 2, c = e & 1;
+    *reinterpret_cast<uint4*>(wgen + buf * TILE_BYTES + r * ROWB + c * 16) = make_uint4(0, 0, 0, 0);
+  }
+  __syncwarp();
+  int wid = w_begin + warp;
+  if (wid < w_end) stage(wid, 0);
+
+  // ---- relative-position bias of this head, fragment-major, log2 units; padded keys -> -1e30 ----
+  for (int e = tid; e < MT * NT * 32 * 4; e += WARPS * 32) {
+    const int comp = e & 3, ln = (e >> 2) & 31, tile = e >> 7;
+    const int mt = tile / NT, nt = tile - mt * NT;
+    const int row = mt * 16 + (ln >> 2) + (comp >> 1) * 8, col = nt * 8 + 2 * (ln & 3) + (comp & 1);
+    float b = 0.f;
+    if (col >= NTOK) b = -1e30f;
+    else if (row < NTOK) {
+      const int yi = row / WIN, xi = row - yi * WIN, yj = col / WIN, xj = col - yj * WIN;
+      b = __ldg(p.bias_table + ((yi - yj + WIN - 1) * (2 * WIN - 1) + (xi - xj + WIN - 1)) * p.heads + head) * LOG2E;
+    }
+    reinterpret_cast<float*>(smem)[e] = b;
+  }
+  __syncthreads();
+
+  // per-thread key bitmasks for the Swin shift mask: bit (2*nt+u) <-> key nt*8+2t+u in the lower/right band
+  uint32_t keyHy = 0, keyHx = 0;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = nt * 8 + 2 * t + u, jy = (j * 205) >> 11, jx = j - jy * WIN;
+      if (jy >= WIN - shift) keyHy |= 1u << (2 * nt + u);
+      if (jx >= WIN - shift) keyHx |= 1u << (2 * nt + u);
+    }
+  const float scale2 = p.scale * LOG2E;
+  const uint32_t ones = 0x3F803F80u;   // bf16x2 (1, 1): B fragment of the row-sum MMA
+
+  // lane-constant ldmatrix offsets
+  const uint32_t kfo0 = swz((mi >> 1) * 8 + l7, mi & 1);            // + pr*16 rows: (mi>>1)*8 + l7 < 16, swizzle bit = bit 2 of row
+  const uint32_t vfo0 = swz((mi & 1) * 8 + l7, mi >> 1);
+  const uint32_t qfo0 = swz((mi & 1) * 8 + l7, mi >> 1);
+
+  for (int it = 0; wid < w_end; wid += WARPS, ++it) {
+    const int qb = it & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    // ---- K and V fragments of the whole window -> registers ----
+    uint32_t kf[7][4], vf[7][4];
+#pragma unroll
+    for (int pr = 0; pr < 7; ++pr) {
+      ldsm4(kf[pr], Ks + pr * 16 * ROWB + kfo0);     // 16 rows = 512 B: row bits 2.. unchanged mod the swizzle (16*k keeps bit 2)
+      ldsm4t(vf[pr], Vs + pr * 16 * ROWB + vfo0);
+    }
+    __syncwarp();
+    if (wid + WARPS < w_end) stage(wid + WARPS, qb ^ 1);
+
+    const int b = wid / nw_img, wl = wid - b * nw_img;
+    const int wy = wl / nwx, wx = wl - wy * nwx;
+    const bool wrap = shift > 0 && (wy == nwy - 1 || wx == nwx - 1);
+    const uint32_t wyl = (shift > 0 && wy == nwy - 1) ? 0xffffffffu : 0u, wxl = (shift > 0 && wx == nwx - 1) ? 0xffffffffu : 0u;
+    const uint32_t Qs = wbase + qb * TILE_BYTES;
+    uint8_t* Qg = wgen + qb * TILE_BYTES;
+
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      uint32_t qa[4];
+      ldsm4(qa, Qs + mt * 16 * ROWB + qfo0);
+      float s[NT][4];
+      const float4* bp = biasF + (mt * NT) * 32 + lane;
+      if (PRESCALED) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const float4 bv = bp[nt * 32];
+          s[nt][0] = bv.x; s[nt][1] = bv.y; s[nt][2] = bv.z; s[nt][3] = bv.w;
+        }
+      } else {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      }
+      if (PRESCALED && wrap) {   // Swin shift mask (-100 in natural units) folded into the accumulator init
+        constexpr float M = 100.f * LOG2E;
+        const int r0 = mt * 16 + g, r1 = r0 + 8;
+        const int r0y = (r0 * 205) >> 11, r0x = r0 - r0y * WIN, r1y = (r1 * 205) >> 11, r1x = r1 - r1y * WIN;
+        const uint32_t m0 = (wyl & (r0y >= WIN - shift ? ~keyHy : keyHy)) | (wxl & (r0x >= WIN - shift ? ~keyHx : keyHx));
+        const uint32_t m1 = (wyl & (r1y >= WIN - shift ? ~keyHy : keyHy)) | (wxl & (r1x >= WIN - shift ? ~keyHx : keyHx));
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          if (m0 & (1u << (2 * nt))) s[nt][0] -= M;
+          if (m0 & (2u << (2 * nt))) s[nt][1] -= M;
+          if (m1 & (1u << (2 * nt))) s[nt][2] -= M;
+          if (m1 & (2u << (2 * nt))) s[nt][3] -= M;
+        }
+      }
+#pragma unroll
+      for (int pr = 0; pr < 7; ++pr) {
+        mma16816(s[2 * pr], qa, kf[pr][0], kf[pr][1]);
+        mma16816(s[2 * pr + 1], qa, kf[pr][2], kf[pr][3]);
+      }
+      if (!PRESCALED) {
+        const int r0 = mt * 16 + g, r1 = r0 + 8;
+        const int r0y = (r0 * 205) >> 11, r0x = r0 - r0y * WIN, r1y = (r1 * 205) >> 11, r1x = r1 - r1y * WIN;
+        const uint32_t m0 = (wyl & (r0y >= WIN - shift ? ~keyHy : keyHy)) | (wxl & (r0x >= WIN - shift ? ~keyHx : keyHx));
+        const uint32_t m1 = (wyl & (r1y >= WIN - shift ? ~keyHy : keyHy)) | (wxl & (r1x >= WIN - shift ? ~keyHx : keyHx));
+        constexpr float M = 100.f * LOG2E;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const float4 bv = bp[nt * 32];
+          s[nt][0] = fmaf(s[nt][0], scale2, bv.x) - ((m0 & (1u << (2 * nt))) ? M : 0.f);
+          s[nt][1] = fmaf(s[nt][1], scale2, bv.y) - ((m0 & (2u << (2 * nt))) ? M : 0.f);
+          s[nt][2] = fmaf(s[nt][2], scale2, bv.z) - ((m1 & (1u << (2 * nt))) ? M : 0.f);
+          s[nt][3] = fmaf(s[nt][3], scale2, bv.w) - ((m1 & (2u << (2 * nt))) ? M : 0.f);
+        }
+      }
+      float mx0 = -1e30f, mx1 = -1e30f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+
+      float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f}, os[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 7; ++ks) {
+        uint32_t pa[4];
+        pa[0] = pack2(ex2(s[2 * ks][0] - mx0), ex2(s[2 * ks][1] - mx0));
+        pa[1] = pack2(ex2(s[2 * ks][2] - mx1), ex2(s[2 * ks][3] - mx1));
+        pa[2] = pack2(ex2(s[2 * ks + 1][0] - mx0), ex2(s[2 * ks + 1][1] - mx0));
+        pa[3] = pack2(ex2(s[2 * ks + 1][2] - mx1), ex2(s[2 * ks + 1][3] - mx1));
+        mma16816(o0, pa, vf[ks][0], vf[ks][1]);
+        mma16816(o1, pa, vf[ks][2], vf[ks][3]);
+        mma16816(os, pa, ones, ones);   // every column = sum of the bf16 probabilities P v used
+      }
+      const float i0 = __frcp_rn(os[0]), i1 = __frcp_rn(os[2]);
+      // O tile over the consumed q rows (same swizzle): (row, ch 2t..2t+1) and (row, ch 8+2t..)
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      *reinterpret_cast<uint32_t*>(Qg + swz(r0, 0) + 4 * t) = pack2(o0[0] * i0, o0[1] * i0);
+      *reinterpret_cast<uint32_t*>(Qg + swz(r0, 1) + 4 * t) = pack2(o1[0] * i0, o1[1] * i0);
+      *reinterpret_cast<uint32_t*>(Qg + swz(r1, 0) + 4 * t) = pack2(o0[2] * i1, o0[3] * i1);
+      *reinterpret_cast<uint32_t*>(Qg + swz(r1, 1) + 4 * t) = pack2(o1[2] * i1, o1[3] * i1);
+    }
+    __syncwarp();
+    // ---- stream the 100 x 32 B output rows ----
+    {
+      const int ty0 = wy * WIN + shift, tx0 = wx * WIN + shift;
+      bf16* obase = outp + (int64_t)b * H * W * old;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        const int e = lane + 32 * i;
+        if (e < 2 * NTOK) {
+          const int j = e >> 1, c = e & 1;
+          const int jy = (j * 205) >> 11, jx = j - jy * WIN;
+          int y = ty0 + jy, x = tx0 + jx;
+          if (y >= H) y -= H;
+          if (x >= W) x -= W;
+          const uint4 v = *reinterpret_cast<const uint4*>(Qg + swz(j, c));
+          *reinterpret_cast<uint4*>(obase + (int64_t)(y * W + x) * old + c * 8) = v;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+}  // namespace
+
+int window_attention_dh16_supported(const fbanet_attn_params* p) {
+  if (p->dtype != FBANET_BF16 || p->win != WIN || p->C != p->heads * 16) return 0;
+  if ((p->qkv_ld % 8) || (p->out_ld % 8) || ((uintptr_t)p->qkv % 16) || ((uintptr_t)p->out % 16)) return 0;
+  return 1;
+}
+
+int window_attention_dh16_launch(const fbanet_attn_params* p, cudaStream_t s) {
+  constexpr size_t smem = BIAS_BYTES + (size_t)WARPS * WARP_BYTES;
+  static int n_sm = 0;
+  static bool opted = false;
+  if (!opted) {
+    cudaError_t e = cudaFuncSetAttribute(window_attention_dh16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(window_attention_dh16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int dev = 0;
+    if (e == cudaSuccess) e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) { cudaGetLastError(); set_last_error(e); return FBANET_E_LAUNCH; }
+    opted = true;
+  }
+  const int total_windows = p->B * (p->H / WIN) * (p->W / WIN);
+  // one CTA per SM (smem-bound); every CTA serves one head: heads x floor(SMs / heads) CTAs
+  int nchunks = n_sm / p->heads;
+  if (nchunks < 1) nchunks = 1;
+  if (nchunks > total_windows) nchunks = total_windows;
+  const int chunk = (total_windows + nchunks - 1) / nchunks;
+  dim3 grid(p->heads, (total_windows + chunk - 1) / chunk);
+  if (p->q_prescaled) window_attention_dh16_kernel<true><<<grid, WARPS * 32, smem, s>>>(*p, chunk);
+  else window_attention_dh16_kernel<false><<<grid, WARPS * 32, smem, s>>>(*p, chunk);
+  return check_launch();
+}
+
+}  // namespace fbanet

@@ -7,6 +7,8 @@
 // Relative-position bias (+ -inf key padding) for the CTA's head is expanded once per CTA into shared
 // memory [N][NP]; the Swin shift mask is evaluated analytically and only for windows that touch the
 // wrapped edge.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fbanet {
@@ -53,16 +55,19 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], const void* 
 // NT = number of 8-key tiles (keys padded to 8*NT, a multiple of 16); MT = number of 16-row query tiles.
 // K and V of a window are staged row-major [key][DH+8] with cp.async into a double buffer: the copies for
 // window i+1 are in flight while window i is computed.  Fragments come from ldmatrix (.trans for V).
-template <int DH, int NT, int MT>
-__global__ void __launch_bounds__(MT * 32, (DH == 16 && MT == 7) ? 3 : 1) window_attention_tc_kernel(const fbanet_attn_params p, const int win_chunk) {
+// Column DH of the V tile holds 1.0, so one extra MMA per key step yields the softmax denominator
+// (sum of the bf16-rounded probabilities that P.v actually used) instead of 56 FADDs + shuffles per thread.
+// Windows that do not wrap around the image edge take a fast path: token = window base + per-thread constant.
+template <int DH, int NT, int MT, bool ONES>
+__global__ void __launch_bounds__(MT * 32, (MT == 7) ? (DH == 16 ? 3 : 2) : 1) window_attention_tc_kernel(const fbanet_attn_params p, const int win_chunk) {
   constexpr int NP = NT * 8;          // padded keys
-  constexpr int KS = DH + 8;          // row stride (elements): conflict-free ldmatrix rows
+  constexpr int KS = DH + 8;          // row stride (elements): conflict-free ldmatrix rows; column DH = ones column of V
   constexpr int CPR = DH / 8;         // 16-byte chunks per row
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int win = p.win, N = win * win;
-  float* biasS = reinterpret_cast<float*>(smem_attn);                 // [N][NP] bias (+ -inf for padded keys)
+  float* biasS = reinterpret_cast<float*>(smem_attn);                 // [N][NP] bias in log2 units (+ -inf for padded keys)
   bf16* KV = reinterpret_cast<bf16*>(biasS + N * NP);                 // [2 buffers][K | V][NP][KS]
-  int* tokS = reinterpret_cast<int*>(KV + 4 * NP * KS);               // [2][NP] token index inside the image
+  int* tokS = reinterpret_cast<int*>(KV + 4 * NP * KS);               // [2][NP] token index inside the image (wrapping windows)
   int* regS = tokS + 2 * NP;                                          // [2][NP] shift-mask region id
 
   const int head = blockIdx.x;   // heads fastest: the CTAs sharing a window's token rows run together (L2 reuse)
@@ -70,7 +75,8 @@ __global__ void __launch_bounds__(MT * 32, (DH == 16 && MT == 7) ? 3 : 1) window
   const int g = lane >> 2, t = lane & 3;
   const int nwx = p.W / win, nwy = p.H / win, nw_img = nwx * nwy;
   const int total_windows = p.B * nw_img;
-  const bf16* qkv = reinterpret_cast<const bf16*>(p.qkv);
+  const bf16* qkv = reinterpret_cast<const bf16*>(p.qkv) + head * DH;
+  bf16* outp = reinterpret_cast<bf16*>(p.out) + head * DH + 2 * t;
 
   const int w_begin = blockIdx.y * win_chunk;
   const int w_end = min(w_begin + win_chunk, total_windows);
@@ -86,50 +92,66 @@ __global__ void __launch_bounds__(MT * 32, (DH == 16 && MT == 7) ? 3 : 1) window
     siy[k] = sj[k] / win;
     six[k] = sj[k] - siy[k] * win;
   }
-  // token / region tables and K,V copies of window `wid` into buffer `buf`
+  // this thread's two query rows
+  const int r0 = warp * 16 + g, r1 = r0 + 8;
+  const bool v0 = r0 < N, v1 = r1 < N;
+  const int q0y = (v0 ? r0 : 0) / win, q0x = (v0 ? r0 : 0) % win, q1y = (v1 ? r1 : 0) / win, q1x = (v1 ? r1 : 0) % win;
+
+  // K,V copies (and, for wrapping windows, token/region tables) of window `wid` into buffer `buf`
   auto stage = [&](int wid, int buf) {
     const int b = wid / nw_img, wl = wid - b * nw_img;
     const int wy = wl / nwx, wx = wl - wy * nwx;
-    const int64_t img_tok0 = (int64_t)b * p.H * p.W;
+    const bool wrap = p.shift > 0 && (wy == nwy - 1 || wx == nwx - 1);
+    const int ty0 = wy * win + p.shift, tx0 = wx * win + p.shift;
+    const bf16* ibase = qkv + (int64_t)b * p.H * p.W * p.qkv_ld;
     bf16* Kb = KV + (size_t)buf * 2 * NP * KS;
     bf16* Vb = Kb + NP * KS;
 #pragma unroll
     for (int k = 0; k < SLOTS; ++k) {
       const int j = sj[k], c = sc[k];
       if (j >= NP) continue;
-      int tk = 0, rg = 0;
       if (j < N) {
-        const int iy = siy[k], ix = six[k];
-        const int ys = wy * win + iy, xs = wx * win + ix;
-        int y = ys + p.shift, x = xs + p.shift;
-        if (y >= p.H) y -= p.H;
-        if (x >= p.W) x -= p.W;
-        tk = y * p.W + x;
-        rg = p.shift > 0 ? shift_region_tc(ys, p.H, win, p.shift) * 3 + shift_region_tc(xs, p.W, win, p.shift) : 0;
-        const bf16* row = qkv + (img_tok0 + tk) * p.qkv_ld + head * DH + c;
+        int y = ty0 + siy[k], x = tx0 + six[k];
+        if (wrap) {
+          if (y >= p.H) y -= p.H;
+          if (x >= p.W) x -= p.W;
+          if (c == 0) {
+            tokS[buf * NP + j] = y * p.W + x;
+            regS[buf * NP + j] = shift_region_tc(wy * win + siy[k], p.H, win, p.shift) * 3 + shift_region_tc(wx * win + six[k], p.W, win, p.shift);
+          }
+        }
+        const bf16* row = ibase + (int64_t)(y * p.W + x) * p.qkv_ld + c;
         cp_async16(Kb + j * KS + c, row + p.C);
         cp_async16(Vb + j * KS + c, row + 2 * p.C);
+        if (c == 0) *reinterpret_cast<uint4*>(Vb + j * KS + DH) = make_uint4(0x00003F80u, 0, 0, 0);   // bf16 1.0 in column DH
       } else {
         *reinterpret_cast<uint4*>(Kb + j * KS + c) = make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint4*>(Vb + j * KS + c) = make_uint4(0, 0, 0, 0);
+        if (c == 0) *reinterpret_cast<uint4*>(Vb + j * KS + DH) = make_uint4(0, 0, 0, 0);
       }
-      if (c == 0) { tokS[buf * NP + j] = tk; regS[buf * NP + j] = rg; }
     }
     cp_async_commit();
   };
 
   if (w_begin < w_end) stage(w_begin, 0);
-  // ---- expand the relative-position bias of this head once (overlaps the first copies) ----
-  for (int e = tid; e < N * NP; e += blockDim.x) {
-    const int i = e / NP, j = e - i * NP;
-    float b = -1e30f;
-    if (j < N) {
-      const int yi = i / win, xi = i - yi * win, yj = j / win, xj = j - yj * win;
-      b = __ldg(p.bias_table + ((yi - yj + win - 1) * (2 * win - 1) + (xi - xj + win - 1)) * p.heads + head);
+  // ---- relative-position bias of this head -> smem, in log2 units (overlaps the first copies) ----
+  if (p.bias_expanded) {   // host-expanded [heads][N][NP]
+    const float4* src = reinterpret_cast<const float4*>(p.bias_expanded + (size_t)head * N * NP);
+    for (int e = tid; e < N * NP / 4; e += blockDim.x) reinterpret_cast<float4*>(biasS)[e] = __ldg(src + e);
+  } else {
+    for (int e = tid; e < N * NP; e += blockDim.x) {
+      const int i = e / NP, j = e - i * NP;
+      float b = -1e30f;
+      if (j < N) {
+        const int yi = i / win, xi = i - yi * win, yj = j / win, xj = j - yj * win;
+        b = __ldg(p.bias_table + ((yi - yj + win - 1) * (2 * win - 1) + (xi - xj + win - 1)) * p.heads + head);
+      }
+      biasS[e] = b * 1.4426950408889634f;   // exp(x) = 2^(x log2 e)
     }
-    biasS[e] = b * 1.4426950408889634f;   // logits are kept in log2 units: exp(x) = 2^(x log2 e)
   }
   const float scale2 = p.scale * 1.4426950408889634f;
+  const float* bb0p = biasS + (v0 ? r0 : 0) * NP + 2 * t;
+  const float* bb1p = biasS + (v1 ? r1 : 0) * NP + 2 * t;
 
   for (int wid = w_begin; wid < w_end; ++wid) {
     const int buf = (wid - w_begin) & 1;
@@ -139,68 +161,78 @@ __global__ void __launch_bounds__(MT * 32, (DH == 16 && MT == 7) ? 3 : 1) window
 
     const int b = wid / nw_img, wl = wid - b * nw_img;
     const int wy = wl / nwx, wx = wl - wy * nwx;
+    const bool wrap = p.shift > 0 && (wy == nwy - 1 || wx == nwx - 1);
     const int64_t img_tok0 = (int64_t)b * p.H * p.W;
-    const bool masked = p.shift > 0 && (wy == nwy - 1 || wx == nwx - 1);
     const bf16* Kb = KV + (size_t)buf * 2 * NP * KS;
     const bf16* Vb = Kb + NP * KS;
     const int* tok = tokS + buf * NP;
     const int* reg = regS + buf * NP;
+    int tok0, tok1;
+    if (wrap) {
+      tok0 = tok[v0 ? r0 : 0];
+      tok1 = tok[v1 ? r1 : 0];
+    } else {
+      const int wb = (wy * win + p.shift) * p.W + wx * win + p.shift;
+      tok0 = wb + q0y * p.W + q0x;
+      tok1 = wb + q1y * p.W + q1x;
+    }
 
     // ---- this warp's 16 query rows ----
-    const int r0 = warp * 16 + g, r1 = r0 + 8;
-    const bool v0 = r0 < N, v1 = r1 < N;
     uint32_t qa[DH / 16][4];
     {
-      const bf16* q0 = qkv + (img_tok0 + tok[v0 ? r0 : 0]) * p.qkv_ld + head * DH;
-      const bf16* q1 = qkv + (img_tok0 + tok[v1 ? r1 : 0]) * p.qkv_ld + head * DH;
+      const bf16* q0 = qkv + (img_tok0 + tok0) * p.qkv_ld + 2 * t;
+      const bf16* q1 = qkv + (img_tok0 + tok1) * p.qkv_ld + 2 * t;
 #pragma unroll
       for (int kk = 0; kk < DH / 16; ++kk) {
-        const int c = kk * 16 + 2 * t;
-        qa[kk][0] = v0 ? *reinterpret_cast<const uint32_t*>(q0 + c) : 0u;
-        qa[kk][1] = v1 ? *reinterpret_cast<const uint32_t*>(q1 + c) : 0u;
-        qa[kk][2] = v0 ? *reinterpret_cast<const uint32_t*>(q0 + c + 8) : 0u;
-        qa[kk][3] = v1 ? *reinterpret_cast<const uint32_t*>(q1 + c + 8) : 0u;
+        qa[kk][0] = v0 ? *reinterpret_cast<const uint32_t*>(q0 + kk * 16) : 0u;
+        qa[kk][1] = v1 ? *reinterpret_cast<const uint32_t*>(q1 + kk * 16) : 0u;
+        qa[kk][2] = v0 ? *reinterpret_cast<const uint32_t*>(q0 + kk * 16 + 8) : 0u;
+        qa[kk][3] = v1 ? *reinterpret_cast<const uint32_t*>(q1 + kk * 16 + 8) : 0u;
       }
     }
     // S = q k^T  (scale applied afterwards in fp32).  One ldmatrix.x4 = B fragments of two key tiles.
     float s[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    const int mi = lane >> 3;
+    const bf16* kfrag = Kb + ((mi >> 1) * 8 + (lane & 7)) * KS + (mi & 1) * 8;
 #pragma unroll
     for (int nt = 0; nt < NT; nt += 2) {
 #pragma unroll
       for (int kk = 0; kk < DH / 16; ++kk) {
         // matrices: (keys nt*8.., ch kk*16..+7), (same keys, ch +8), (keys (nt+1)*8.., ch ..+7), (.., ch +8)
         uint32_t kb[4];
-        const int mi = lane >> 3;
-        ldmatrix_x4(kb, Kb + ((nt + (mi >> 1)) * 8 + (lane & 7)) * KS + kk * 16 + (mi & 1) * 8);
+        ldmatrix_x4(kb, kfrag + nt * 8 * KS + kk * 16);
         const uint32_t b0[2] = {kb[0], kb[1]}, b1[2] = {kb[2], kb[3]};
         mma_bf16_16816(s[nt], qa[kk], b0);
         mma_bf16_16816(s[nt + 1], qa[kk], b1);
       }
     }
     // + bias (+ mask), row max
-    const float* bb0p = biasS + (v0 ? r0 : 0) * NP;
-    const float* bb1p = biasS + (v1 ? r1 : 0) * NP;
-    const int rg0 = reg[v0 ? r0 : 0], rg1 = reg[v1 ? r1 : 0];
     float m0 = -1e30f, m1 = -1e30f;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      const int j = nt * 8 + 2 * t;
-      const float2 bb0 = *reinterpret_cast<const float2*>(bb0p + j);
-      const float2 bb1 = *reinterpret_cast<const float2*>(bb1p + j);
+      const float2 bb0 = *reinterpret_cast<const float2*>(bb0p + nt * 8);
+      const float2 bb1 = *reinterpret_cast<const float2*>(bb1p + nt * 8);
       s[nt][0] = fmaf(s[nt][0], scale2, bb0.x);
       s[nt][1] = fmaf(s[nt][1], scale2, bb0.y);
       s[nt][2] = fmaf(s[nt][2], scale2, bb1.x);
       s[nt][3] = fmaf(s[nt][3], scale2, bb1.y);
-      if (masked) {
-        constexpr float M = 100.f * 1.4426950408889634f;
-        const int ja = reg[j], jb = reg[j + 1];
+    }
+    if (wrap) {   // Swin shift mask, only where the window straddles the wrapped edge
+      constexpr float M = 100.f * 1.4426950408889634f;
+      const int rg0 = reg[v0 ? r0 : 0], rg1 = reg[v1 ? r1 : 0];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int ja = reg[nt * 8 + 2 * t], jb = reg[nt * 8 + 2 * t + 1];
         if (ja != rg0) s[nt][0] -= M;
         if (jb != rg0) s[nt][1] -= M;
         if (ja != rg1) s[nt][2] -= M;
         if (jb != rg1) s[nt][3] -= M;
       }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
       m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
       m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
     }
@@ -208,51 +240,59 @@ __global__ void __launch_bounds__(MT * 32, (DH == 16 && MT == 7) ? 3 : 1) window
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      s[nt][0] = ex2_approx(s[nt][0] - m0);
-      s[nt][1] = ex2_approx(s[nt][1] - m0);
-      s[nt][2] = ex2_approx(s[nt][2] - m1);
-      s[nt][3] = ex2_approx(s[nt][3] - m1);
-      l0 += s[nt][0] + s[nt][1];
-      l1 += s[nt][2] + s[nt][3];
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    // O = P v ; V fragments via ldmatrix.trans from the row-major [key][ch] tile
-    float o[DH / 8][4];
+    // O = P v and l = P 1 ; V fragments via ldmatrix.trans from the row-major [key][ch] tile
+    float o[DH / 8][4], osum[4] = {0.f, 0.f, 0.f, 0.f}, lsum0 = 0.f, lsum1 = 0.f;
 #pragma unroll
     for (int dn = 0; dn < DH / 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+    const bf16* vfrag = Vb + ((mi & 1) * 8 + (lane & 7)) * KS + (mi >> 1) * 8;
+    const bf16* vones = Vb + (lane & 15) * KS + DH;
 #pragma unroll
     for (int ks = 0; ks < NT / 2; ++ks) {
       uint32_t pa[4];
-      pa[0] = pack_bf16(s[2 * ks][0], s[2 * ks][1]);
-      pa[1] = pack_bf16(s[2 * ks][2], s[2 * ks][3]);
-      pa[2] = pack_bf16(s[2 * ks + 1][0], s[2 * ks + 1][1]);
-      pa[3] = pack_bf16(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+      float e[8];
+      e[0] = ex2_approx(s[2 * ks][0] - m0); e[1] = ex2_approx(s[2 * ks][1] - m0);
+      e[2] = ex2_approx(s[2 * ks][2] - m1); e[3] = ex2_approx(s[2 * ks][3] - m1);
+      e[4] = ex2_approx(s[2 * ks + 1][0] - m0); e[5] = ex2_approx(s[2 * ks + 1][1] - m0);
+      e[6] = ex2_approx(s[2 * ks + 1][2] - m1); e[7] = ex2_approx(s[2 * ks + 1][3] - m1);
+      if (!ONES) { lsum0 += (e[0] + e[1]) + (e[4] + e[5]); lsum1 += (e[2] + e[3]) + (e[6] + e[7]); }
+      pa[0] = pack_bf16(e[0], e[1]);
+      pa[1] = pack_bf16(e[2], e[3]);
+      pa[2] = pack_bf16(e[4], e[5]);
+      pa[3] = pack_bf16(e[6], e[7]);
 #pragma unroll
       for (int dn = 0; dn < DH / 8; dn += 2) {
         // matrices: (keys 16ks..+7, ch dn*8), (keys +8.., ch dn*8), (keys 16ks.., ch (dn+1)*8), (keys +8.., ch (dn+1)*8)
         uint32_t vb[4];
-        const int mi = lane >> 3;
-        ldmatrix_x4_trans(vb, Vb + (ks * 16 + (mi & 1) * 8 + (lane & 7)) * KS + (dn + (mi >> 1)) * 8);
+        ldmatrix_x4_trans(vb, vfrag + ks * 16 * KS + dn * 8);
         const uint32_t b0[2] = {vb[0], vb[1]}, b1[2] = {vb[2], vb[3]};
         mma_bf16_16816(o[dn], pa, b0);
         mma_bf16_16816(o[dn + 1], pa, b1);
       }
+      if (ONES) {
+        uint32_t ob[2];
+        ldmatrix_x2_trans(ob, vones + ks * 16 * KS);
+        mma_bf16_16816(osum, pa, ob);
+      }
+    }
+    float l0, l1;
+    if (ONES) {   // column 0 of the ones tile lives in the t == 0 lane of each quad
+      l0 = __shfl_sync(0xffffffffu, osum[0], lane & ~3);
+      l1 = __shfl_sync(0xffffffffu, osum[2], lane & ~3);
+    } else {
+      lsum0 += __shfl_xor_sync(0xffffffffu, lsum0, 1);
+      lsum0 += __shfl_xor_sync(0xffffffffu, lsum0, 2);
+      lsum1 += __shfl_xor_sync(0xffffffffu, lsum1, 1);
+      lsum1 += __shfl_xor_sync(0xffffffffu, lsum1, 2);
+      l0 = lsum0; l1 = lsum1;
     }
     const float i0 = 1.f / l0, i1 = 1.f / l1;
-    bf16* out = reinterpret_cast<bf16*>(p.out);
     if (v0) {
-      bf16* op = out + (img_tok0 + tok[r0]) * p.out_ld + head * DH + 2 * t;
+      bf16* op = outp + (img_tok0 + tok0) * p.out_ld;
 #pragma unroll
       for (int dn = 0; dn < DH / 8; ++dn) *reinterpret_cast<__nv_bfloat162*>(op + dn * 8) = __floats2bfloat162_rn(o[dn][0] * i0, o[dn][1] * i0);
     }
     if (v1) {
-      bf16* op = out + (img_tok0 + tok[r1]) * p.out_ld + head * DH + 2 * t;
+      bf16* op = outp + (img_tok0 + tok1) * p.out_ld;
 #pragma unroll
       for (int dn = 0; dn < DH / 8; ++dn) *reinterpret_cast<__nv_bfloat162*>(op + dn * 8) = __floats2bfloat162_rn(o[dn][2] * i1, o[dn][3] * i1);
     }
@@ -260,12 +300,12 @@ __global__ void __launch_bounds__(MT * 32, (DH == 16 && MT == 7) ? 3 : 1) window
   cp_async_wait_all();
 }
 
-template <int DH, int NT, int MT>
+template <int DH, int NT, int MT, bool ONES>
 static int launch_tc(const fbanet_attn_params* p, cudaStream_t s) {
   constexpr int NP = NT * 8;
   const int N = p->win * p->win;
   const size_t smem = (size_t)N * NP * 4 + (size_t)4 * NP * (DH + 8) * 2 + (size_t)4 * NP * 4;
-  auto kern = window_attention_tc_kernel<DH, NT, MT>;
+  auto kern = window_attention_tc_kernel<DH, NT, MT, ONES>;
   static size_t opted = 0;
   if (smem > opted) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -294,10 +334,13 @@ int window_attention_tc_supported(const fbanet_attn_params* p) {
 template <int DH>
 static int dispatch_n(const fbanet_attn_params* p, cudaStream_t s) {
   switch (p->win * p->win) {
-    case 100: return launch_tc<DH, 14, 7>(p, s);
-    case 64: return launch_tc<DH, 8, 4>(p, s);
-    case 25: return launch_tc<DH, 4, 2>(p, s);
-    case 16: return launch_tc<DH, 2, 1>(p, s);
+    case 100: {
+      static const char* ones = getenv("FBANET_ATTN_ONES");   // experiment switch: softmax denominator via a ones column of V
+      return (ones && ones[0] == '1') ? launch_tc<DH, 14, 7, true>(p, s) : launch_tc<DH, 14, 7, false>(p, s);
+    }
+    case 64: return launch_tc<DH, 8, 4, false>(p, s);
+    case 25: return launch_tc<DH, 4, 2, false>(p, s);
+    case 16: return launch_tc<DH, 2, 1, false>(p, s);
     default: return FBANET_E_UNSUPPORTED;
   }
 }

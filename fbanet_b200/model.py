@@ -300,6 +300,8 @@ class BaseModel(nn.Module):
                     P[k + ".qkv.w"] = torch.cat([a.qkv.to_q.weight.detach(), a.qkv.to_kv.weight.detach()], 0).to(T).contiguous()
                     P[k + ".qkv.b"] = torch.cat([f32(a.qkv.to_q.bias), f32(a.qkv.to_kv.bias)], 0).contiguous()
                     P[k + ".rpb"] = f32(a.relative_position_bias_table)
+                    if tc:  # dense per-head bias in log2 units for the tensor-core attention kernel
+                        P[k + ".rpbx"] = ops.expand_rel_pos_bias(P[k + ".rpb"], ly.win)
                     put_lin(k + ".proj", a.proj)
                     put_lin(k + ".fc1", ly.mlp.linear1[0])
                     put_lin(k + ".fc2", ly.mlp.linear2[0])
@@ -370,7 +372,8 @@ class BaseModel(nn.Module):
         ln1 = ops.layernorm(x.view(-1, Cd), P[key + ".ln1.g"], P[key + ".ln1.b"]).view(B, H, W, Cd)
         qkv = self._lin(P, key + ".qkv", ln1)
         scale = self.qk_scale or (Cd // ly.heads) ** -0.5
-        att = ops.window_attention(qkv.view(-1, 3 * Cd), P[key + ".rpb"], B, H, W, ly.heads, ly.win, ly.shift, scale, impl=self.impl)
+        att = ops.window_attention(qkv.view(-1, 3 * Cd), P[key + ".rpb"], B, H, W, ly.heads, ly.win, ly.shift, scale, impl=self.impl,
+                                   bias_expanded=P.get(key + ".rpbx"))
         x1 = self._lin(P, key + ".proj", att.view(B, H, W, Cd), residual=x)
         ln2 = ops.layernorm(x1.view(-1, Cd), P[key + ".ln2.g"], P[key + ".ln2.b"]).view(B, H, W, Cd)
         h = self._lin(P, key + ".fc1", ln2, act=self.gelu_act)

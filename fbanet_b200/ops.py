@@ -254,8 +254,22 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return y
 
 
+def expand_rel_pos_bias(bias_table: torch.Tensor, win: int) -> torch.Tensor:
+    """Dense ``[heads, win^2, NP]`` fp32 bias in log2 units for the tensor-core attention kernel (``NP`` = keys padded to
+    a multiple of 16, padded keys = -1e30): ``log2(e) * table[(yi-yj+w-1)(2w-1) + (xi-xj+w-1), h]``."""
+    N = win * win
+    NP = (N + 15) // 16 * 16
+    ys, xs = torch.meshgrid(torch.arange(win), torch.arange(win), indexing="ij")
+    ys, xs = ys.flatten(), xs.flatten()
+    idx = ((ys[:, None] - ys[None, :] + win - 1) * (2 * win - 1) + (xs[:, None] - xs[None, :] + win - 1)).to(bias_table.device)
+    dense = bias_table.float()[idx.view(-1)].view(N, N, -1).permute(2, 0, 1) * 1.4426950408889634
+    out = torch.full((dense.shape[0], N, NP), -1e30, device=bias_table.device, dtype=torch.float32)
+    out[:, :, :N] = dense
+    return out.contiguous()
+
+
 def window_attention(qkv: torch.Tensor, bias_table: torch.Tensor, B: int, H: int, W: int, heads: int, win: int, shift: int,
-                     scale: float, impl: int = L.IMPL_AUTO) -> torch.Tensor:
+                     scale: float, impl: int = L.IMPL_AUTO, bias_expanded: Optional[torch.Tensor] = None) -> torch.Tensor:
     """qkv ``[B*H*W, 3C]`` -> ``[B*H*W, C]``."""
     assert qkv.is_cuda and qkv.dim() == 2 and qkv.stride(1) == 1 and qkv.shape[0] == B * H * W
     Cc = qkv.shape[1] // 3
@@ -265,6 +279,10 @@ def window_attention(qkv: torch.Tensor, bias_table: torch.Tensor, B: int, H: int
     p.qkv, p.out, p.bias_table, p.dtype = qkv.data_ptr(), out.data_ptr(), bias_table.data_ptr(), _DT[qkv.dtype]
     p.B, p.H, p.W, p.C, p.heads, p.win, p.shift = B, H, W, Cc, heads, win, shift
     p.qkv_ld, p.out_ld, p.scale, p.impl = qkv.stride(0), Cc, scale, impl
+    if bias_expanded is not None:
+        N = win * win
+        assert bias_expanded.dtype == torch.float32 and bias_expanded.is_contiguous() and bias_expanded.shape == (heads, N, (N + 15) // 16 * 16)
+        p.bias_expanded = bias_expanded.data_ptr()
     _call("fbanet_window_attention_sm100", p)
     return out
 

@@ -30,7 +30,8 @@ def timeit(name, fn, reps, gbytes):
 def attn(B, S, C, heads, shift):
     qkv = (torch.rand(B * S * S, 3 * C, device=dev) - 0.5).to(BF)
     table = torch.rand(361, heads, device=dev) * 0.1
-    return (lambda: ops.window_attention(qkv, table, B, S, S, heads, 10, shift, (C // heads) ** -0.5)), 2 * B * S * S * 4 * C / 1e9
+    bx = ops.expand_rel_pos_bias(table, 10)
+    return (lambda: ops.window_attention(qkv, table, B, S, S, heads, 10, shift, (C // heads) ** -0.5, bias_expanded=bx)), 2 * B * S * S * 4 * C / 1e9
 
 
 def dw(B, S, C):
