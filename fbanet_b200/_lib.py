@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libfbanet_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -92,6 +92,7 @@ class AttnParams(C.Structure):
         ("qkv", C.c_void_p), ("out", C.c_void_p), ("bias_table", C.c_void_p), ("dtype", C.c_int32),
         ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("heads", C.c_int32), ("win", C.c_int32), ("shift", C.c_int32),
         ("qkv_ld", C.c_int32), ("out_ld", C.c_int32), ("scale", C.c_float), ("impl", C.c_int32), ("bias_expanded", C.c_void_p),
+        ("q_prescaled", C.c_int32), ("_pad", C.c_int32),
     ]
 
 

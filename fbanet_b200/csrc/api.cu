@@ -28,6 +28,8 @@ int window_attention_validate(const fbanet_attn_params* p);
 int window_attention_simt_launch(const fbanet_attn_params* p, cudaStream_t s);
 int window_attention_tc_supported(const fbanet_attn_params* p);
 int window_attention_tc_launch(const fbanet_attn_params* p, cudaStream_t s);
+int window_attention_dh16_supported(const fbanet_attn_params* p);
+int window_attention_dh16_launch(const fbanet_attn_params* p, cudaStream_t s);
 
 }  // namespace fbanet
 
@@ -77,6 +79,10 @@ extern "C" int fbanet_window_attention_sm100(const fbanet_attn_params* p, void* 
   if (rc != FBANET_OK) return rc;
   const bool tc_ok = window_attention_tc_supported(p) != 0;
   if (p->impl == FBANET_IMPL_TCGEN05 && !tc_ok) return FBANET_E_UNSUPPORTED;
-  if (tc_ok && p->impl != FBANET_IMPL_SIMT) return window_attention_tc_launch(p, (cudaStream_t)stream);
+  if (tc_ok && p->impl != FBANET_IMPL_SIMT) {
+    if (window_attention_dh16_supported(p)) return window_attention_dh16_launch(p, (cudaStream_t)stream);
+    return window_attention_tc_launch(p, (cudaStream_t)stream);
+  }
+  if (p->q_prescaled) return FBANET_E_UNSUPPORTED;  // the fp32 / SIMT kernel applies `scale` itself
   return window_attention_simt_launch(p, (cudaStream_t)stream);
 }

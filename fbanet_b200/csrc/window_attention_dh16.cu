@@ -77,27 +77,30 @@ __global__ void __launch_bounds__(WARPS * 32, 1) window_attention_dh16_kernel(co
   const int64_t ld = p.qkv_ld, old = p.out_ld;
   const int C = p.C;
 
-  // q | k | v rows of window `wid` -> (q buffer `qb`, k, v); 200 (row, chunk) slots over 32 lanes
-  auto stage = [&](int wid, int qb) {
-    const int b = wid / nw_img, wl = wid - b * nw_img;
-    const int wy = wl / nwx, wx = wl - wy * nwx;
+  // q | k | v rows of window `wid` -> (q buffer `qb`, k, v); 200 (row, chunk) slots over 32 lanes: lane pair = one 32-byte row.
+  // All in-image offsets are 32-bit (an image's qkv rows span < 2^31 elements); the swizzled destination of slot i is a lane
+  // constant + 512*i because 16 rows keep bit 2 of the row index.
+  const int j0 = lane >> 1, c8 = (lane & 1) * 8;
+  const uint32_t d0 = swz(j0, lane & 1);
+  const uint32_t ldu = (uint32_t)p.qkv_ld, oldu = (uint32_t)p.out_ld;
+  auto stage = [&](int b, int wy, int wx, int qb) {
     const int ty0 = wy * WIN + shift, tx0 = wx * WIN + shift;
-    const bf16* ibase = qkv + (int64_t)b * H * W * ld;
-    const uint32_t Qs = wbase + qb * TILE_BYTES;
+    const bf16* ibq = qkv + (int64_t)b * H * W * ld;
+    const bf16* ibk = ibq + C;
+    const bf16* ibv = ibk + C;
+    const uint32_t Qs = wbase + qb * TILE_BYTES + d0;
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
-      const int e = lane + 32 * i;
-      if (e < 2 * NTOK) {
-        const int j = e >> 1, c = e & 1;
+      const int j = j0 + 16 * i;
+      if (i < 6 || j < NTOK) {
         const int jy = (j * 205) >> 11, jx = j - jy * WIN;
         int y = ty0 + jy, x = tx0 + jx;
-        if (y >= H) y -= H;
-        if (x >= W) x -= W;
-        const bf16* src = ibase + (int64_t)(y * W + x) * ld + c * 8;
-        const uint32_t d = swz(j, c);
-        cp16(Qs + d, src);
-        cp16(Ks + d, src + C);
-        cp16(Vs + d, src + 2 * C);
+        y -= (y >= H) ? H : 0;
+        x -= (x >= W) ? W : 0;
+        const uint32_t off = (uint32_t)(y * W + x) * ldu + c8;
+        cp16(Qs + i * 512, ibq + off);
+        cp16(Ks + d0 + i * 512, ibk + off);
+        cp16(Vs + d0 + i * 512, ibv + off);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -109,8 +112,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) window_attention_dh16_kernel(co
     *reinterpret_cast<uint4*>(wgen + buf * TILE_BYTES + r * ROWB + c * 16) = make_uint4(0, 0, 0, 0);
   }
   __syncwarp();
+  // window coordinates (image b, window row wy, window column wx) advance by WARPS windows per item without divisions
   int wid = w_begin + warp;
-  if (wid < w_end) stage(wid, 0);
+  int nb = wid / nw_img, nwy_ = (wid - nb * nw_img) / nwx, nwx_ = wid - nb * nw_img - nwy_ * nwx;   // "next" item = first item
+  if (wid < w_end) stage(nb, nwy_, nwx_, 0);
 
   // ---- relative-position bias of this head, fragment-major, log2 units; padded keys -> -1e30 ----
   for (int e = tid; e < MT * NT * 32 * 4; e += WARPS * 32) {
@@ -157,10 +162,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) window_attention_dh16_kernel(co
       ldsm4t(vf[pr], Vs + pr * 16 * ROWB + vfo0);
     }
     __syncwarp();
-    if (wid + WARPS < w_end) stage(wid + WARPS, qb ^ 1);
+    const int b = nb, wy = nwy_, wx = nwx_;
+    nwx_ += WARPS;
+    while (nwx_ >= nwx) { nwx_ -= nwx; ++nwy_; }
+    while (nwy_ >= nwy) { nwy_ -= nwy; ++nb; }
+    if (wid + WARPS < w_end) stage(nb, nwy_, nwx_, qb ^ 1);
 
-    const int b = wid / nw_img, wl = wid - b * nw_img;
-    const int wy = wl / nwx, wx = wl - wy * nwx;
     const bool wrap = shift > 0 && (wy == nwy - 1 || wx == nwx - 1);
     const uint32_t wyl = (shift > 0 && wy == nwy - 1) ? 0xffffffffu : 0u, wxl = (shift > 0 && wx == nwx - 1) ? 0xffffffffu : 0u;
     const uint32_t Qs = wbase + qb * TILE_BYTES;
@@ -254,15 +261,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) window_attention_dh16_kernel(co
       bf16* obase = outp + (int64_t)b * H * W * old;
 #pragma unroll
       for (int i = 0; i < 7; ++i) {
-        const int e = lane + 32 * i;
-        if (e < 2 * NTOK) {
-          const int j = e >> 1, c = e & 1;
+        const int j = j0 + 16 * i;
+        if (i < 6 || j < NTOK) {
           const int jy = (j * 205) >> 11, jx = j - jy * WIN;
           int y = ty0 + jy, x = tx0 + jx;
-          if (y >= H) y -= H;
-          if (x >= W) x -= W;
-          const uint4 v = *reinterpret_cast<const uint4*>(Qg + swz(j, c));
-          *reinterpret_cast<uint4*>(obase + (int64_t)(y * W + x) * old + c * 8) = v;
+          y -= (y >= H) ? H : 0;
+          x -= (x >= W) ? W : 0;
+          const uint4 v = *reinterpret_cast<const uint4*>(Qg + d0 + i * 512);
+          *reinterpret_cast<uint4*>(obase + ((uint32_t)(y * W + x) * oldu + c8)) = v;
         }
       }
     }

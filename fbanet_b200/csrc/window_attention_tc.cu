@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(MT * 32, (MT == 7) ? (DH == 16 ? 3 : 2) : 1) w
       biasS[e] = b * 1.4426950408889634f;   // exp(x) = 2^(x log2 e)
     }
   }
-  const float scale2 = p.scale * 1.4426950408889634f;
+  const float scale2 = p.q_prescaled ? 1.f : p.scale * 1.4426950408889634f;
   const float* bb0p = biasS + (v0 ? r0 : 0) * NP + 2 * t;
   const float* bb1p = biasS + (v1 ? r1 : 0) * NP + 2 * t;
 

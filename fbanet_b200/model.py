@@ -297,8 +297,11 @@ class BaseModel(nn.Module):
                     P[k + ".ln1.g"], P[k + ".ln1.b"] = f32(ly.norm1.weight), f32(ly.norm1.bias)
                     P[k + ".ln2.g"], P[k + ".ln2.b"] = f32(ly.norm2.weight), f32(ly.norm2.bias)
                     a = ly.attn
-                    P[k + ".qkv.w"] = torch.cat([a.qkv.to_q.weight.detach(), a.qkv.to_kv.weight.detach()], 0).to(T).contiguous()
-                    P[k + ".qkv.b"] = torch.cat([f32(a.qkv.to_q.bias), f32(a.qkv.to_kv.bias)], 0).contiguous()
+                    # tensor-core path: scale * log2(e) folded into the q projection (fp32, before the bf16 rounding), so the
+                    # attention kernel's scores come out of the MMA already in log2 units (window_attention.py:196-198)
+                    qs = (self.qk_scale or (ly.dim // ly.heads) ** -0.5) * math.log2(math.e) if tc else 1.0
+                    P[k + ".qkv.w"] = torch.cat([a.qkv.to_q.weight.detach().float() * qs, a.qkv.to_kv.weight.detach().float()], 0).to(T).contiguous()
+                    P[k + ".qkv.b"] = torch.cat([f32(a.qkv.to_q.bias) * qs, f32(a.qkv.to_kv.bias)], 0).contiguous()
                     P[k + ".rpb"] = f32(a.relative_position_bias_table)
                     if tc:  # dense per-head bias in log2 units for the tensor-core attention kernel
                         P[k + ".rpbx"] = ops.expand_rel_pos_bias(P[k + ".rpb"], ly.win)
@@ -373,7 +376,7 @@ class BaseModel(nn.Module):
         qkv = self._lin(P, key + ".qkv", ln1)
         scale = self.qk_scale or (Cd // ly.heads) ** -0.5
         att = ops.window_attention(qkv.view(-1, 3 * Cd), P[key + ".rpb"], B, H, W, ly.heads, ly.win, ly.shift, scale, impl=self.impl,
-                                   bias_expanded=P.get(key + ".rpbx"))
+                                   bias_expanded=P.get(key + ".rpbx"), q_prescaled=self._use_tc())
         x1 = self._lin(P, key + ".proj", att.view(B, H, W, Cd), residual=x)
         ln2 = ops.layernorm(x1.view(-1, Cd), P[key + ".ln2.g"], P[key + ".ln2.b"]).view(B, H, W, Cd)
         h = self._lin(P, key + ".fc1", ln2, act=self.gelu_act)

@@ -269,8 +269,10 @@ def expand_rel_pos_bias(bias_table: torch.Tensor, win: int) -> torch.Tensor:
 
 
 def window_attention(qkv: torch.Tensor, bias_table: torch.Tensor, B: int, H: int, W: int, heads: int, win: int, shift: int,
-                     scale: float, impl: int = L.IMPL_AUTO, bias_expanded: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """qkv ``[B*H*W, 3C]`` -> ``[B*H*W, C]``."""
+                     scale: float, impl: int = L.IMPL_AUTO, bias_expanded: Optional[torch.Tensor] = None,
+                     q_prescaled: bool = False) -> torch.Tensor:
+    """qkv ``[B*H*W, 3C]`` -> ``[B*H*W, C]``.  ``q_prescaled``: the q columns were produced by projection weights that
+    already carry ``scale * log2(e)`` (bf16 tensor-core kernels only); ``scale`` is then ignored."""
     assert qkv.is_cuda and qkv.dim() == 2 and qkv.stride(1) == 1 and qkv.shape[0] == B * H * W
     Cc = qkv.shape[1] // 3
     out = torch.empty((B * H * W, Cc), device=qkv.device, dtype=qkv.dtype)
@@ -279,6 +281,7 @@ def window_attention(qkv: torch.Tensor, bias_table: torch.Tensor, B: int, H: int
     p.qkv, p.out, p.bias_table, p.dtype = qkv.data_ptr(), out.data_ptr(), bias_table.data_ptr(), _DT[qkv.dtype]
     p.B, p.H, p.W, p.C, p.heads, p.win, p.shift = B, H, W, Cc, heads, win, shift
     p.qkv_ld, p.out_ld, p.scale, p.impl = qkv.stride(0), Cc, scale, impl
+    p.q_prescaled = 1 if q_prescaled else 0
     if bias_expanded is not None:
         N = win * win
         assert bias_expanded.dtype == torch.float32 and bias_expanded.is_contiguous() and bias_expanded.shape == (heads, N, (N + 15) // 16 * 16)

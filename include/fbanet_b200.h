@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 8
+#define FBANET_ABI_VERSION 9
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -195,6 +195,9 @@ typedef struct fbanet_attn_params {
   const float* bias_expanded; /* optional, tensor-core path: dense fp32 [heads][win^2][NP] = log2(e) * bias_table[index(i,j)][h]
                                  for j < win^2 and -1e30 for the padded keys (NP = win^2 rounded up to 16); NULL: the kernel
                                  expands bias_table itself */
+  int32_t q_prescaled;        /* nonzero: the q columns already carry scale*log2(e) (folded into the q projection weights by
+                                 the caller); `scale` is then ignored.  Tensor-core (bf16) kernels only. */
+  int32_t _pad;
 } fbanet_attn_params;
 
 /* K7: LeFF depthwise 3x3 (pad 1) + bias + GELU on a channels-last map

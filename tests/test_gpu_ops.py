@@ -188,11 +188,15 @@ def test_dwconv_gelu(cuda, dt):
 
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("C,heads,HW,win,shift", [(64, 1, 20, 10, 0), (64, 1, 20, 10, 5), (128, 2, 30, 10, 5), (256, 16, 20, 10, 5),
-                                                   (128, 8, 20, 10, 0), (64, 4, 5, 5, 0), (128, 8, 8, 4, 2)])
-def test_window_attention(cuda, dt, C, heads, HW, win, shift):
+                                                   (128, 8, 20, 10, 0), (64, 4, 5, 5, 0), (128, 8, 8, 4, 2), (128, 8, 40, 10, 5),
+                                                   (256, 16, 30, 10, 3)])
+@pytest.mark.parametrize("prescaled", [False, True])
+def test_window_attention(cuda, dt, C, heads, HW, win, shift, prescaled):
     """K6 against the oracle's WindowAttention + roll/partition/mask (layers/fba_net.py:139-250)."""
     from fbanet_b200 import ops
     from oracle.fbanet_oracle import shift_attn_mask, window_partition, window_reverse, relative_position_index
+    if prescaled and dt != torch.bfloat16:
+        pytest.skip("q_prescaled is a tensor-core (bf16) path option")
     B, H, W = 2, HW, HW
     N, dh = win * win, C // heads
     qkv = _r(dt, B, H, W, 3 * C, seed=1, scale=1.5)
@@ -214,7 +218,10 @@ def test_window_attention(cuda, dt, C, heads, HW, win, shift):
     o = window_reverse(o, win, B, H, W)
     if shift:
         o = torch.roll(o, (shift, shift), (1, 2))
-    got = ops.window_attention(qkv.reshape(-1, 3 * C).to(cuda, dt), table.to(cuda), B, H, W, heads, win, shift, scale)
+    qkv_in = qkv.reshape(-1, 3 * C).clone()
+    if prescaled:  # the caller folds scale*log2(e) into the q projection (model.py:_pack)
+        qkv_in[:, :C] = qkv_in[:, :C] * (scale * 1.4426950408889634)
+    got = ops.window_attention(qkv_in.to(cuda, dt), table.to(cuda), B, H, W, heads, win, shift, scale, q_prescaled=prescaled)
     _close(got.view(B, H, W, C), o, dt, scale=2.0)
 
 

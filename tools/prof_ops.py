@@ -31,7 +31,7 @@ def attn(B, S, C, heads, shift):
     qkv = (torch.rand(B * S * S, 3 * C, device=dev) - 0.5).to(BF)
     table = torch.rand(361, heads, device=dev) * 0.1
     bx = ops.expand_rel_pos_bias(table, 10)
-    return (lambda: ops.window_attention(qkv, table, B, S, S, heads, 10, shift, (C // heads) ** -0.5, bias_expanded=bx)), 2 * B * S * S * 4 * C / 1e9
+    return (lambda: ops.window_attention(qkv, table, B, S, S, heads, 10, shift, (C // heads) ** -0.5, bias_expanded=bx, q_prescaled=True)), 2 * B * S * S * 4 * C / 1e9
 
 
 def dw(B, S, C):
