@@ -15,6 +15,8 @@
 //   * writes O over the q rows it has consumed and streams it out with 16-byte stores.
 // The q columns of the fused qkv GEMM may be pre-multiplied by scale*log2(e) (`q_prescaled`), which removes
 // the per-score FFMA.  Bound: MUFU.EX2 (one per score) -- see DESIGN.md "K6".
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace fbanet {
@@ -22,6 +24,7 @@ namespace fbanet {
 namespace {
 
 constexpr int WIN = 10, NTOK = 100, NT = 14, MT = 7, WARPS = 12;
+constexpr int NTU = 13;                       // key tiles that hold real keys (tile 13 = keys 104..111 is padding)
 constexpr int ROWB = 32;                      // bytes per staged row (16 bf16)
 constexpr int TILE_BYTES = 112 * ROWB;        // one q / k / v buffer
 constexpr int WARP_BYTES = 4 * TILE_BYTES;    // q0 | q1 | k | v
@@ -36,7 +39,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 }
 __device__ __forceinline__ float ex2(float x) {
   float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // volatile: keeps the hand-made MUFU / MMA interleave
   return y;
 }
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
@@ -173,87 +176,111 @@ __global__ void __launch_bounds__(WARPS * 32, 1) window_attention_dh16_kernel(co
     const uint32_t Qs = wbase + qb * TILE_BYTES;
     uint8_t* Qg = wgen + qb * TILE_BYTES;
 
-#pragma unroll 1
-    for (int mt = 0; mt < MT; ++mt) {
-      uint32_t qa[4];
-      ldsm4(qa, Qs + mt * 16 * ROWB + qfo0);
-      float s[NT][4];
-      const float4* bp = biasF + (mt * NT) * 32 + lane;
+    // Scores of query tile `mt`: accumulator = bias fragment (PRESCALED) or 0, then one MMA per key tile.
+    float s[NTU][4];
+    uint32_t qa[4];
+    auto load_bias = [&](int mt, int nt) {
       if (PRESCALED) {
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const float4 bv = bp[nt * 32];
-          s[nt][0] = bv.x; s[nt][1] = bv.y; s[nt][2] = bv.z; s[nt][3] = bv.w;
-        }
+        const float4 bv = biasF[(mt * NT + nt) * 32 + lane];
+        s[nt][0] = bv.x; s[nt][1] = bv.y; s[nt][2] = bv.z; s[nt][3] = bv.w;
       } else {
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
       }
-      if (PRESCALED && wrap) {   // Swin shift mask (-100 in natural units) folded into the accumulator init
-        constexpr float M = 100.f * LOG2E;
-        const int r0 = mt * 16 + g, r1 = r0 + 8;
-        const int r0y = (r0 * 205) >> 11, r0x = r0 - r0y * WIN, r1y = (r1 * 205) >> 11, r1x = r1 - r1y * WIN;
-        const uint32_t m0 = (wyl & (r0y >= WIN - shift ? ~keyHy : keyHy)) | (wxl & (r0x >= WIN - shift ? ~keyHx : keyHx));
-        const uint32_t m1 = (wyl & (r1y >= WIN - shift ? ~keyHy : keyHy)) | (wxl & (r1x >= WIN - shift ? ~keyHx : keyHx));
+    };
+    auto score_mma = [&](int nt) { mma16816(s[nt], qa, kf[nt >> 1][(nt & 1) * 2], kf[nt >> 1][(nt & 1) * 2 + 1]); };
+    ldsm4(qa, Qs + qfo0);
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
+    for (int nt = 0; nt < NTU; ++nt) load_bias(0, nt);
+#pragma unroll
+    for (int nt = 0; nt < NTU; ++nt) score_mma(nt);
+
+    // One query tile: (mask) -> row max -> exp + P v, software pipelined by hand in two ways:
+    //  * the exps of key step ks+1 are issued before the packs / MMAs of step ks, so a pack never waits on the MUFU it has
+    //    just issued (one warp alone keeps the XU pipe busy);
+    //  * as soon as a pair of score registers has been packed it is re-initialised with the NEXT tile's bias and that tile's
+    //    score MMAs are issued, so the tensor-pipe S phase of tile mt+1 hides under the MUFU phase of tile mt.
+    auto tile = [&](const int mt, auto has_next_tag) {
+      constexpr bool HAS_NEXT = decltype(has_next_tag)::value;
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      if (!PRESCALED || wrap) {
+        uint32_t m0 = 0, m1 = 0;
+        if (wrap) {   // Swin shift mask (-100 in natural units)
+          const int r0y = (r0 * 205) >> 11, r0x = r0 - r0y * WIN, r1y = (r1 * 205) >> 11, r1x = r1 - r1y * WIN;
+          m0 = (wyl & (r0y >= WIN - shift ? ~keyHy : keyHy)) | (wxl & (r0x >= WIN - shift ? ~keyHx : keyHx));
+          m1 = (wyl & (r1y >= WIN - shift ? ~keyHy : keyHy)) | (wxl & (r1x >= WIN - shift ? ~keyHx : keyHx));
+        }
+        constexpr float M = 100.f * LOG2E;
+#pragma unroll
+        for (int nt = 0; nt < NTU; ++nt) {
+          if (!PRESCALED) {
+            const float4 bv = biasF[(mt * NT + nt) * 32 + lane];
+            s[nt][0] = fmaf(s[nt][0], scale2, bv.x); s[nt][1] = fmaf(s[nt][1], scale2, bv.y);
+            s[nt][2] = fmaf(s[nt][2], scale2, bv.z); s[nt][3] = fmaf(s[nt][3], scale2, bv.w);
+          }
           if (m0 & (1u << (2 * nt))) s[nt][0] -= M;
           if (m0 & (2u << (2 * nt))) s[nt][1] -= M;
           if (m1 & (1u << (2 * nt))) s[nt][2] -= M;
           if (m1 & (2u << (2 * nt))) s[nt][3] -= M;
         }
       }
+      // row max: four independent chains per row (the last key tile, keys 104..111, is padding only and never touched)
+      float ma0 = fmaxf(s[0][0], s[0][1]), mb0 = fmaxf(s[1][0], s[1][1]), mc0 = fmaxf(s[2][0], s[2][1]), md0 = fmaxf(s[3][0], s[3][1]);
+      float ma1 = fmaxf(s[0][2], s[0][3]), mb1 = fmaxf(s[1][2], s[1][3]), mc1 = fmaxf(s[2][2], s[2][3]), md1 = fmaxf(s[3][2], s[3][3]);
 #pragma unroll
-      for (int pr = 0; pr < 7; ++pr) {
-        mma16816(s[2 * pr], qa, kf[pr][0], kf[pr][1]);
-        mma16816(s[2 * pr + 1], qa, kf[pr][2], kf[pr][3]);
+      for (int nt = 4; nt < NTU; nt += 4) {
+        ma0 = fmaxf(ma0, fmaxf(s[nt][0], s[nt][1]));
+        ma1 = fmaxf(ma1, fmaxf(s[nt][2], s[nt][3]));
+        if (nt + 1 < NTU) { mb0 = fmaxf(mb0, fmaxf(s[nt + 1][0], s[nt + 1][1])); mb1 = fmaxf(mb1, fmaxf(s[nt + 1][2], s[nt + 1][3])); }
+        if (nt + 2 < NTU) { mc0 = fmaxf(mc0, fmaxf(s[nt + 2][0], s[nt + 2][1])); mc1 = fmaxf(mc1, fmaxf(s[nt + 2][2], s[nt + 2][3])); }
+        if (nt + 3 < NTU) { md0 = fmaxf(md0, fmaxf(s[nt + 3][0], s[nt + 3][1])); md1 = fmaxf(md1, fmaxf(s[nt + 3][2], s[nt + 3][3])); }
       }
-      if (!PRESCALED) {
-        const int r0 = mt * 16 + g, r1 = r0 + 8;
-        const int r0y = (r0 * 205) >> 11, r0x = r0 - r0y * WIN, r1y = (r1 * 205) >> 11, r1x = r1 - r1y * WIN;
-        const uint32_t m0 = (wyl & (r0y >= WIN - shift ? ~keyHy : keyHy)) | (wxl & (r0x >= WIN - shift ? ~keyHx : keyHx));
-        const uint32_t m1 = (wyl & (r1y >= WIN - shift ? ~keyHy : keyHy)) | (wxl & (r1x >= WIN - shift ? ~keyHx : keyHx));
-        constexpr float M = 100.f * LOG2E;
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const float4 bv = bp[nt * 32];
-          s[nt][0] = fmaf(s[nt][0], scale2, bv.x) - ((m0 & (1u << (2 * nt))) ? M : 0.f);
-          s[nt][1] = fmaf(s[nt][1], scale2, bv.y) - ((m0 & (2u << (2 * nt))) ? M : 0.f);
-          s[nt][2] = fmaf(s[nt][2], scale2, bv.z) - ((m1 & (1u << (2 * nt))) ? M : 0.f);
-          s[nt][3] = fmaf(s[nt][3], scale2, bv.w) - ((m1 & (2u << (2 * nt))) ? M : 0.f);
-        }
-      }
-      float mx0 = -1e30f, mx1 = -1e30f;
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-      }
+      float mx0 = fmaxf(fmaxf(ma0, mb0), fmaxf(mc0, md0)), mx1 = fmaxf(fmaxf(ma1, mb1), fmaxf(mc1, md1));
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
 
       float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f}, os[4] = {0.f, 0.f, 0.f, 0.f};
+      auto exps = [&](int nt) {
+        s[nt][0] = ex2(s[nt][0] - mx0); s[nt][1] = ex2(s[nt][1] - mx0);
+        s[nt][2] = ex2(s[nt][2] - mx1); s[nt][3] = ex2(s[nt][3] - mx1);
+      };
+      if (HAS_NEXT) ldsm4(qa, Qs + (mt + 1) * 16 * ROWB + qfo0);   // q fragment of the next tile (this tile's is dead)
+      exps(0); exps(1);
 #pragma unroll
       for (int ks = 0; ks < 7; ++ks) {
+        if (2 * ks + 2 < NTU) exps(2 * ks + 2);
+        if (2 * ks + 3 < NTU) exps(2 * ks + 3);
         uint32_t pa[4];
-        pa[0] = pack2(ex2(s[2 * ks][0] - mx0), ex2(s[2 * ks][1] - mx0));
-        pa[1] = pack2(ex2(s[2 * ks][2] - mx1), ex2(s[2 * ks][3] - mx1));
-        pa[2] = pack2(ex2(s[2 * ks + 1][0] - mx0), ex2(s[2 * ks + 1][1] - mx0));
-        pa[3] = pack2(ex2(s[2 * ks + 1][2] - mx1), ex2(s[2 * ks + 1][3] - mx1));
+        pa[0] = pack2(s[2 * ks][0], s[2 * ks][1]);
+        pa[1] = pack2(s[2 * ks][2], s[2 * ks][3]);
+        pa[2] = (2 * ks + 1 < NTU) ? pack2(s[2 * ks + 1][0], s[2 * ks + 1][1]) : 0u;
+        pa[3] = (2 * ks + 1 < NTU) ? pack2(s[2 * ks + 1][2], s[2 * ks + 1][3]) : 0u;
+        if (HAS_NEXT) {   // score registers of key tiles 2ks, 2ks+1 are free: next tile's bias; MMAs one step behind the loads
+          load_bias(mt + 1, 2 * ks);
+          if (2 * ks + 1 < NTU) load_bias(mt + 1, 2 * ks + 1);
+        }
         mma16816(o0, pa, vf[ks][0], vf[ks][1]);
         mma16816(o1, pa, vf[ks][2], vf[ks][3]);
         mma16816(os, pa, ones, ones);   // every column = sum of the bf16 probabilities P v used
+        if (HAS_NEXT && ks > 0) {
+          score_mma(2 * ks - 2);
+          score_mma(2 * ks - 1);
+        }
       }
-      const float i0 = __frcp_rn(os[0]), i1 = __frcp_rn(os[2]);
+      if (HAS_NEXT) score_mma(NTU - 1);
+      float i0, i1;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i0) : "f"(os[0]));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i1) : "f"(os[2]));
       // O tile over the consumed q rows (same swizzle): (row, ch 2t..2t+1) and (row, ch 8+2t..)
-      const int r0 = mt * 16 + g, r1 = r0 + 8;
       *reinterpret_cast<uint32_t*>(Qg + swz(r0, 0) + 4 * t) = pack2(o0[0] * i0, o0[1] * i0);
       *reinterpret_cast<uint32_t*>(Qg + swz(r0, 1) + 4 * t) = pack2(o1[0] * i0, o1[1] * i0);
       *reinterpret_cast<uint32_t*>(Qg + swz(r1, 0) + 4 * t) = pack2(o0[2] * i1, o0[3] * i1);
       *reinterpret_cast<uint32_t*>(Qg + swz(r1, 1) + 4 * t) = pack2(o1[2] * i1, o1[3] * i1);
-    }
+    };
+#pragma unroll 1
+    for (int mt = 0; mt < MT - 1; ++mt) tile(mt, std::true_type{});
+    tile(MT - 1, std::false_type{});
     __syncwarp();
     // ---- stream the 100 x 32 B output rows ----
     {
