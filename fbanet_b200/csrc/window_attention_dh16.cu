@@ -176,111 +176,128 @@ __global__ void __launch_bounds__(WARPS * 32, 1) window_attention_dh16_kernel(co
     const uint32_t Qs = wbase + qb * TILE_BYTES;
     uint8_t* Qg = wgen + qb * TILE_BYTES;
 
-    // Scores of query tile `mt`: accumulator = bias fragment (PRESCALED) or 0, then one MMA per key tile.
-    float s[NTU][4];
+    // ---- the 7 query tiles ----
+    // Softmax is shift invariant, and both fp32 and bf16 carry 8 exponent bits, so exp2(s - c) keeps full relative precision
+    // for ANY shift c within ~2^+-60 of the row maximum.  The fast path therefore uses c = 0: no row-max pass, no shuffles, no
+    // subtract per score, and -- because nothing depends on the whole row any more -- the keys are STREAMED: 16 keys at a
+    // time go bias -> score MMA -> exp -> pack -> P v MMA, two steps in flight, ~16 live score registers instead of 52.
+    // The row sum doubles as the safety check: unless 2^-60 < l < 2^60 for every row of the tile (NaN fails too) the tile is
+    // redone with the exact row maximum folded into the accumulator init.
     uint32_t qa[4];
-    auto load_bias = [&](int mt, int nt) {
+    float o0[4], o1[4], os[4];
+    const uint32_t wyl_ = wyl, wxl_ = wxl;
+    auto tile_masks = [&](const int mt, uint32_t& m0, uint32_t& m1) {
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      const int r0y = (r0 * 205) >> 11, r0x = r0 - r0y * WIN, r1y = (r1 * 205) >> 11, r1x = r1 - r1y * WIN;
+      m0 = (wyl_ & (r0y >= WIN - shift ? ~keyHy : keyHy)) | (wxl_ & (r0x >= WIN - shift ? ~keyHx : keyHx));
+      m1 = (wyl_ & (r1y >= WIN - shift ? ~keyHy : keyHy)) | (wxl_ & (r1x >= WIN - shift ? ~keyHx : keyHx));
+    };
+    // scores of key tile nt for query tile mt, in log2 units, minus the per-row shift (c0, c1)
+    auto score_tile = [&](float (&sc)[4], const int mt, const int nt, const uint32_t m0, const uint32_t m1, const float c0, const float c1,
+                          auto shifted_tag, auto wrap_tag) {
+      constexpr bool SHIFTED = decltype(shifted_tag)::value;
+      constexpr bool WRAP = decltype(wrap_tag)::value;   // compile-time copy of `wrap`: no branch per key tile
+      constexpr float M = 100.f * LOG2E;
+      const float4 bv = biasF[(mt * NT + nt) * 32 + lane];
       if (PRESCALED) {
-        const float4 bv = biasF[(mt * NT + nt) * 32 + lane];
-        s[nt][0] = bv.x; s[nt][1] = bv.y; s[nt][2] = bv.z; s[nt][3] = bv.w;
+        sc[0] = bv.x; sc[1] = bv.y; sc[2] = bv.z; sc[3] = bv.w;
+        if (WRAP) {   // Swin shift mask (-100 in natural units) folded into the accumulator init
+          if (m0 & (1u << (2 * nt))) sc[0] -= M;
+          if (m0 & (2u << (2 * nt))) sc[1] -= M;
+          if (m1 & (1u << (2 * nt))) sc[2] -= M;
+          if (m1 & (2u << (2 * nt))) sc[3] -= M;
+        }
+        if (SHIFTED) { sc[0] -= c0; sc[1] -= c0; sc[2] -= c1; sc[3] -= c1; }
+        mma16816(sc, qa, kf[nt >> 1][(nt & 1) * 2], kf[nt >> 1][(nt & 1) * 2 + 1]);
       } else {
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        sc[0] = sc[1] = sc[2] = sc[3] = 0.f;
+        mma16816(sc, qa, kf[nt >> 1][(nt & 1) * 2], kf[nt >> 1][(nt & 1) * 2 + 1]);
+        sc[0] = fmaf(sc[0], scale2, bv.x); sc[1] = fmaf(sc[1], scale2, bv.y);
+        sc[2] = fmaf(sc[2], scale2, bv.z); sc[3] = fmaf(sc[3], scale2, bv.w);
+        if (WRAP) {
+          if (m0 & (1u << (2 * nt))) sc[0] -= M;
+          if (m0 & (2u << (2 * nt))) sc[1] -= M;
+          if (m1 & (1u << (2 * nt))) sc[2] -= M;
+          if (m1 & (2u << (2 * nt))) sc[3] -= M;
+        }
+        if (SHIFTED) { sc[0] -= c0; sc[1] -= c0; sc[2] -= c1; sc[3] -= c1; }
       }
     };
-    auto score_mma = [&](int nt) { mma16816(s[nt], qa, kf[nt >> 1][(nt & 1) * 2], kf[nt >> 1][(nt & 1) * 2 + 1]); };
-    ldsm4(qa, Qs + qfo0);
+    // one query tile, keys streamed in 7 steps of 16: O = P v and l = P 1 with p = exp2(s - c)
+    auto stream_tile = [&](const int mt, const uint32_t m0, const uint32_t m1, const float c0, const float c1, auto shifted_tag, auto wrap_tag) {
+      float sa[2][4], sb[2][4];   // two steps in flight: [step parity][..] for key tiles 2ks (sa) and 2ks+1 (sb)
 #pragma unroll
-    for (int nt = 0; nt < NTU; ++nt) load_bias(0, nt);
-#pragma unroll
-    for (int nt = 0; nt < NTU; ++nt) score_mma(nt);
-
-    // One query tile: (mask) -> row max -> exp + P v, software pipelined by hand in two ways:
-    //  * the exps of key step ks+1 are issued before the packs / MMAs of step ks, so a pack never waits on the MUFU it has
-    //    just issued (one warp alone keeps the XU pipe busy);
-    //  * as soon as a pair of score registers has been packed it is re-initialised with the NEXT tile's bias and that tile's
-    //    score MMAs are issued, so the tensor-pipe S phase of tile mt+1 hides under the MUFU phase of tile mt.
-    auto tile = [&](const int mt, auto has_next_tag) {
-      constexpr bool HAS_NEXT = decltype(has_next_tag)::value;
-      const int r0 = mt * 16 + g, r1 = r0 + 8;
-      if (!PRESCALED || wrap) {
-        uint32_t m0 = 0, m1 = 0;
-        if (wrap) {   // Swin shift mask (-100 in natural units)
-          const int r0y = (r0 * 205) >> 11, r0x = r0 - r0y * WIN, r1y = (r1 * 205) >> 11, r1x = r1 - r1y * WIN;
-          m0 = (wyl & (r0y >= WIN - shift ? ~keyHy : keyHy)) | (wxl & (r0x >= WIN - shift ? ~keyHx : keyHx));
-          m1 = (wyl & (r1y >= WIN - shift ? ~keyHy : keyHy)) | (wxl & (r1x >= WIN - shift ? ~keyHx : keyHx));
-        }
-        constexpr float M = 100.f * LOG2E;
-#pragma unroll
-        for (int nt = 0; nt < NTU; ++nt) {
-          if (!PRESCALED) {
-            const float4 bv = biasF[(mt * NT + nt) * 32 + lane];
-            s[nt][0] = fmaf(s[nt][0], scale2, bv.x); s[nt][1] = fmaf(s[nt][1], scale2, bv.y);
-            s[nt][2] = fmaf(s[nt][2], scale2, bv.z); s[nt][3] = fmaf(s[nt][3], scale2, bv.w);
-          }
-          if (m0 & (1u << (2 * nt))) s[nt][0] -= M;
-          if (m0 & (2u << (2 * nt))) s[nt][1] -= M;
-          if (m1 & (1u << (2 * nt))) s[nt][2] -= M;
-          if (m1 & (2u << (2 * nt))) s[nt][3] -= M;
-        }
-      }
-      // row max: four independent chains per row (the last key tile, keys 104..111, is padding only and never touched)
-      float ma0 = fmaxf(s[0][0], s[0][1]), mb0 = fmaxf(s[1][0], s[1][1]), mc0 = fmaxf(s[2][0], s[2][1]), md0 = fmaxf(s[3][0], s[3][1]);
-      float ma1 = fmaxf(s[0][2], s[0][3]), mb1 = fmaxf(s[1][2], s[1][3]), mc1 = fmaxf(s[2][2], s[2][3]), md1 = fmaxf(s[3][2], s[3][3]);
-#pragma unroll
-      for (int nt = 4; nt < NTU; nt += 4) {
-        ma0 = fmaxf(ma0, fmaxf(s[nt][0], s[nt][1]));
-        ma1 = fmaxf(ma1, fmaxf(s[nt][2], s[nt][3]));
-        if (nt + 1 < NTU) { mb0 = fmaxf(mb0, fmaxf(s[nt + 1][0], s[nt + 1][1])); mb1 = fmaxf(mb1, fmaxf(s[nt + 1][2], s[nt + 1][3])); }
-        if (nt + 2 < NTU) { mc0 = fmaxf(mc0, fmaxf(s[nt + 2][0], s[nt + 2][1])); mc1 = fmaxf(mc1, fmaxf(s[nt + 2][2], s[nt + 2][3])); }
-        if (nt + 3 < NTU) { md0 = fmaxf(md0, fmaxf(s[nt + 3][0], s[nt + 3][1])); md1 = fmaxf(md1, fmaxf(s[nt + 3][2], s[nt + 3][3])); }
-      }
-      float mx0 = fmaxf(fmaxf(ma0, mb0), fmaxf(mc0, md0)), mx1 = fmaxf(fmaxf(ma1, mb1), fmaxf(mc1, md1));
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-
-      float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f}, os[4] = {0.f, 0.f, 0.f, 0.f};
-      auto exps = [&](int nt) {
-        s[nt][0] = ex2(s[nt][0] - mx0); s[nt][1] = ex2(s[nt][1] - mx0);
-        s[nt][2] = ex2(s[nt][2] - mx1); s[nt][3] = ex2(s[nt][3] - mx1);
-      };
-      if (HAS_NEXT) ldsm4(qa, Qs + (mt + 1) * 16 * ROWB + qfo0);   // q fragment of the next tile (this tile's is dead)
-      exps(0); exps(1);
+      for (int e = 0; e < 4; ++e) o0[e] = o1[e] = os[e] = 0.f;
+      score_tile(sa[0], mt, 0, m0, m1, c0, c1, shifted_tag, wrap_tag);
+      score_tile(sb[0], mt, 1, m0, m1, c0, c1, shifted_tag, wrap_tag);
 #pragma unroll
       for (int ks = 0; ks < 7; ++ks) {
-        if (2 * ks + 2 < NTU) exps(2 * ks + 2);
-        if (2 * ks + 3 < NTU) exps(2 * ks + 3);
+        const int cur = ks & 1, nxt = cur ^ 1;
+        if (2 * ks + 2 < NTU) score_tile(sa[nxt], mt, 2 * ks + 2, m0, m1, c0, c1, shifted_tag, wrap_tag);
+        if (2 * ks + 3 < NTU) score_tile(sb[nxt], mt, 2 * ks + 3, m0, m1, c0, c1, shifted_tag, wrap_tag);
         uint32_t pa[4];
-        pa[0] = pack2(s[2 * ks][0], s[2 * ks][1]);
-        pa[1] = pack2(s[2 * ks][2], s[2 * ks][3]);
-        pa[2] = (2 * ks + 1 < NTU) ? pack2(s[2 * ks + 1][0], s[2 * ks + 1][1]) : 0u;
-        pa[3] = (2 * ks + 1 < NTU) ? pack2(s[2 * ks + 1][2], s[2 * ks + 1][3]) : 0u;
-        if (HAS_NEXT) {   // score registers of key tiles 2ks, 2ks+1 are free: next tile's bias; MMAs one step behind the loads
-          load_bias(mt + 1, 2 * ks);
-          if (2 * ks + 1 < NTU) load_bias(mt + 1, 2 * ks + 1);
+        pa[0] = pack2(ex2(sa[cur][0]), ex2(sa[cur][1]));
+        pa[1] = pack2(ex2(sa[cur][2]), ex2(sa[cur][3]));
+        if (2 * ks + 1 < NTU) {
+          pa[2] = pack2(ex2(sb[cur][0]), ex2(sb[cur][1]));
+          pa[3] = pack2(ex2(sb[cur][2]), ex2(sb[cur][3]));
+        } else {
+          pa[2] = pa[3] = 0u;   // keys 104..111 are padding
         }
         mma16816(o0, pa, vf[ks][0], vf[ks][1]);
         mma16816(o1, pa, vf[ks][2], vf[ks][3]);
         mma16816(os, pa, ones, ones);   // every column = sum of the bf16 probabilities P v used
-        if (HAS_NEXT && ks > 0) {
-          score_mma(2 * ks - 2);
-          score_mma(2 * ks - 1);
-        }
       }
-      if (HAS_NEXT) score_mma(NTU - 1);
+    };
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      uint32_t m0 = 0, m1 = 0;
+      if (wrap) tile_masks(mt, m0, m1);
+      ldsm4(qa, Qs + mt * 16 * ROWB + qfo0);
+      if (wrap) stream_tile(mt, m0, m1, 0.f, 0.f, std::false_type{}, std::true_type{});
+      else stream_tile(mt, 0u, 0u, 0.f, 0.f, std::false_type{}, std::false_type{});
+      const bool ok = ((os[0] > 8.6e-19f && os[0] < 1.15e18f) || r0 >= NTOK) && ((os[2] > 8.6e-19f && os[2] < 1.15e18f) || r1 >= NTOK);
+      if (!__all_sync(0xffffffffu, ok)) {   // out-of-band row sum (huge logits): exact row maximum, then redo.  Cold.
+        float mx0 = -3.0e38f, mx1 = -3.0e38f;
+#pragma unroll 1
+        for (int nt = 0; nt < NTU; ++nt) {
+          float sc[4];
+          const float4 bv = biasF[(mt * NT + nt) * 32 + lane];
+          constexpr float M = 100.f * LOG2E;
+          sc[0] = sc[1] = sc[2] = sc[3] = 0.f;
+          const int pr = nt >> 1;
+          uint32_t kb0 = 0, kb1 = 0;
+#pragma unroll
+          for (int q = 0; q < 7; ++q) if (q == pr) { kb0 = (nt & 1) ? kf[q][2] : kf[q][0]; kb1 = (nt & 1) ? kf[q][3] : kf[q][1]; }
+          mma16816(sc, qa, kb0, kb1);
+          const float sq = PRESCALED ? 1.f : scale2;
+          sc[0] = fmaf(sc[0], sq, bv.x) - (((m0 >> (2 * nt)) & 1u) ? M : 0.f);
+          sc[1] = fmaf(sc[1], sq, bv.y) - (((m0 >> (2 * nt)) & 2u) ? M : 0.f);
+          sc[2] = fmaf(sc[2], sq, bv.z) - (((m1 >> (2 * nt)) & 1u) ? M : 0.f);
+          sc[3] = fmaf(sc[3], sq, bv.w) - (((m1 >> (2 * nt)) & 2u) ? M : 0.f);
+          mx0 = fmaxf(mx0, fmaxf(sc[0], sc[1]));
+          mx1 = fmaxf(mx1, fmaxf(sc[2], sc[3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        stream_tile(mt, m0, m1, mx0, mx1, std::true_type{}, std::true_type{});   // m0 = m1 = 0 when the window does not wrap
+      }
       float i0, i1;
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i0) : "f"(os[0]));
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i1) : "f"(os[2]));
       // O tile over the consumed q rows (same swizzle): (row, ch 2t..2t+1) and (row, ch 8+2t..)
-      *reinterpret_cast<uint32_t*>(Qg + swz(r0, 0) + 4 * t) = pack2(o0[0] * i0, o0[1] * i0);
-      *reinterpret_cast<uint32_t*>(Qg + swz(r0, 1) + 4 * t) = pack2(o1[0] * i0, o1[1] * i0);
-      *reinterpret_cast<uint32_t*>(Qg + swz(r1, 0) + 4 * t) = pack2(o0[2] * i1, o0[3] * i1);
-      *reinterpret_cast<uint32_t*>(Qg + swz(r1, 1) + 4 * t) = pack2(o1[2] * i1, o1[3] * i1);
-    };
-#pragma unroll 1
-    for (int mt = 0; mt < MT - 1; ++mt) tile(mt, std::true_type{});
-    tile(MT - 1, std::false_type{});
+      if (r0 < NTOK) {
+        *reinterpret_cast<uint32_t*>(Qg + swz(r0, 0) + 4 * t) = pack2(o0[0] * i0, o0[1] * i0);
+        *reinterpret_cast<uint32_t*>(Qg + swz(r0, 1) + 4 * t) = pack2(o1[0] * i0, o1[1] * i0);
+      }
+      if (r1 < NTOK) {
+        *reinterpret_cast<uint32_t*>(Qg + swz(r1, 0) + 4 * t) = pack2(o0[2] * i1, o0[3] * i1);
+        *reinterpret_cast<uint32_t*>(Qg + swz(r1, 1) + 4 * t) = pack2(o1[2] * i1, o1[3] * i1);
+      }
+    }
     __syncwarp();
     // ---- stream the 100 x 32 B output rows ----
     {

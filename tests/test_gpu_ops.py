@@ -225,6 +225,38 @@ def test_window_attention(cuda, dt, C, heads, HW, win, shift, prescaled):
     _close(got.view(B, H, W, C), o, dt, scale=2.0)
 
 
+@pytest.mark.parametrize("prescaled", [False, True])
+@pytest.mark.parametrize("mag", [6.0, 14.0])
+def test_window_attention_huge_logits(cuda, prescaled, mag):
+    """dh=16 kernel: logits far outside exp2's range must take the exact-row-max path (and moderate ones the shift-free fast
+    path) and still match softmax with max subtraction (layers/window_attention.py:230)."""
+    from fbanet_b200 import ops
+    from oracle.fbanet_oracle import shift_attn_mask, window_partition, window_reverse, relative_position_index
+    dt, B, H, W, C, heads, win, shift = torch.bfloat16, 1, 30, 30, 128, 8, 10, 5
+    N, dh = win * win, C // heads
+    qkv = _r(dt, B, H, W, 3 * C, seed=5, scale=mag)
+    qkv[..., 2 * C:] = _r(dt, B, H, W, C, seed=6, scale=1.0)
+    table = _r(torch.float32, (2 * win - 1) ** 2, heads, seed=2, scale=0.5)
+    scale = dh ** -0.5
+    qkv_in = qkv.reshape(-1, 3 * C).clone()
+    if prescaled:
+        qkv_in[:, :C] = (qkv_in[:, :C] * (scale * 1.4426950408889634)).to(dt).float()
+        qkv = qkv.clone()
+        qkv[..., :C] = qkv_in[:, :C].view(B, H, W, C) / (scale * 1.4426950408889634)  # reference sees the same rounded q
+    yw = window_partition(torch.roll(qkv, (-shift, -shift), (1, 2)), win)
+    q, k, v = (yw[..., i * C:(i + 1) * C].view(-1, N, heads, dh).permute(0, 2, 1, 3) for i in range(3))
+    attn = (q.double() * scale) @ k.double().transpose(-2, -1)
+    attn = attn + table[relative_position_index(win).view(-1)].view(N, N, heads).permute(2, 0, 1)[None].double()
+    mask = shift_attn_mask(H, W, win, shift)
+    attn = (attn.view(B, mask.shape[0], heads, N, N) + mask[None, :, None].double()).view(-1, heads, N, N)
+    assert attn.abs().max().item() > (300.0 if mag > 10 else 50.0)
+    o = (torch.softmax(attn, -1) @ v.double()).float().transpose(1, 2).reshape(-1, N, C)
+    o = torch.roll(window_reverse(o, win, B, H, W), (shift, shift), (1, 2))
+    got = ops.window_attention(qkv_in.to(cuda, dt), table.to(cuda), B, H, W, heads, win, shift, scale, q_prescaled=prescaled)
+    assert torch.isfinite(got.float()).all()
+    _close(got.view(B, H, W, C), o, dt, scale=2.0)
+
+
 def test_to_nhwc(cuda):
     from fbanet_b200 import ops
     x = torch.rand(6, 3, 9, 7, generator=torch.Generator().manual_seed(0))
