@@ -36,6 +36,33 @@ __device__ __forceinline__ float gelu_tanh_fast(float u) {
   const float hu = 0.5f * u;
   return fmaf(hu, th, hu);                          // 0.5 u (1 + tanh): FMUL, FFMA
 }
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack_f2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack_f2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma_f2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul_f2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add_f2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// two bf16 packed in a 32-bit word -> fp32 pair (exact: bf16 is the high half of fp32)
+__device__ __forceinline__ f32x2 bf16x2_to_f2(uint32_t u) { return pack_f2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+// tanh-GELU of a pair, bf16-path accuracy (MUFU.TANH): 5 packed ops + 2 MUFU
+__device__ __forceinline__ f32x2 gelu_tanh_fast_f2(f32x2 u) {
+  const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
+  const f32x2 inner = mul_f2(fma_f2(mul_f2(u, u), pack_f2(k0k1, k0k1), pack_f2(k0, k0)), u);
+  float i0, i1, t0, t1;
+  unpack_f2(inner, i0, i1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(i0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(i1));
+  const f32x2 hu = mul_f2(u, pack_f2(0.5f, 0.5f));
+  return fma_f2(hu, pack_f2(t0, t1), hu);
+}
+__device__ __forceinline__ uint32_t f2_to_bf16x2(f32x2 v) {
+  float lo, hi;
+  unpack_f2(v, lo, hi);
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 __device__ __forceinline__ float gelu_erf(float u) { return 0.5f * u * (1.0f + erff(u * 0.7071067811865476f)); }
 
 __device__ __forceinline__ float apply_act(float v, int act, float alpha) {

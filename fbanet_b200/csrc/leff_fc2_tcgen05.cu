@@ -8,8 +8,13 @@
 // acc[128 px, C] += A[128, 64] . W2[C, 64]^T in TMEM.  The dwconv output (the largest tensor of the forward)
 // never goes to HBM: one 2x1.7 GB round trip per dec1 layer at batch 64 disappears.
 //
-// Warps (384 threads, persistent, 1 CTA/SM): 0 = h1 halo TMA, 1 = MMA issuer, 2 = TMEM alloc, 3 = W2 TMA,
-// 4..11 = depthwise producer + epilogue (the epilogue of tile i runs after chunk 0 of tile i+1 is produced).
+// The residual add rides on the tensor core too: each 64-channel slice of the residual tile is TMA-loaded as an A operand
+// and multiplied by a 64x64 identity held in shared memory (acc[:, 64kc:64kc+64] = R_kc . I, exact in fp32), which
+// initialises the TMEM accumulator before the LeFF chunks accumulate into it.  The epilogue therefore never waits on a
+// global load (ncu: the four dependent residual LDGs cost ~4000 cycles per tile and warp when they sat in the epilogue).
+//
+// Warps (640 threads, persistent, 1 CTA/SM): 0 = h1 halo TMA, 1 = MMA issuer, 2 = TMEM alloc + residual TMA, 3 = W2 TMA,
+// 4..19 = depthwise producer + epilogue (the epilogue of tile i runs after chunk 0 of tile i+1 is produced).
 #include <string.h>
 
 #include "common.cuh"
@@ -25,10 +30,12 @@ constexpr int LF_A_BYTES = 128 * 128;                      // A tile: 128 px x 6
 constexpr int LF_DW_WARPS = 16;                            // depthwise/epilogue warps (4 output rows per thread)
 constexpr int LF_THREADS = 128 + 32 * LF_DW_WARPS;
 constexpr int LF_H_SLOTS = 4;                              // halo ring depth: TMA latency (~1-2 us) spans several chunks of compute
+constexpr int LF_I_BYTES = 64 * 128;                       // 64x64 bf16 identity (B operand of the residual MMAs)
 
 struct LeffParams {
   CUtensorMap hmap;   // h1 [N,H,W,Hd]: box {64, 10, 18, 1}, no swizzle (read by CUDA cores)
   CUtensorMap wmap;   // W2 [C][Hd]:   box {64, C}, SWIZZLE_128B (tcgen05 B operand)
+  CUtensorMap rmap;   // residual [N,H,W,C]: box {64, 8, 16, 1}, SWIZZLE_128B (A operand of the identity MMAs)
   const float* dw_w;  // [9][Hd]
   const float* dw_b;  // [Hd]
   const float* bias2; // [C]
@@ -37,25 +44,28 @@ struct LeffParams {
   int64_t res_img_stride, out_img_stride;
   int res_ld, out_ld;
   int N, H, W, C, Hd, act;
-  int tiles_x, tiles_y, m_tiles, nchunks, b_slots;
+  int tiles_x, tiles_y, m_tiles, nchunks, b_slots, r_slots;
 };
 
 __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_constant__ LeffParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t h_full[LF_H_SLOTS], h_empty[LF_H_SLOTS], a_full[2], a_empty[2], b_full[8], b_empty[8], tmem_full[2], tmem_empty[2];
+  __shared__ __align__(8) uint64_t h_full[LF_H_SLOTS], h_empty[LF_H_SLOTS], a_full[2], a_empty[2], b_full[8], b_empty[8], tmem_full[2], tmem_empty[2], r_full[2], r_empty[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float bias_s[256];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                   // 2 x 16 KB, 1024-aligned (swizzle atoms)
-  uint8_t* smem_b = smem_a + 2 * LF_A_BYTES;                // b_slots x C*128
+  uint8_t* smem_r = smem_a + 2 * LF_A_BYTES;                // r_slots x 16 KB residual slices (A operand layout)
+  uint8_t* smem_i = smem_r + p.r_slots * LF_A_BYTES;        // 8 KB identity
+  uint8_t* smem_b = smem_i + LF_I_BYTES;                    // b_slots x C*128
   const uint32_t b_bytes = (uint32_t)p.C * 128u;
   uint8_t* smem_h = smem_b + (size_t)p.b_slots * b_bytes;   // 2 x halo tiles
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = p.C;
   const uint32_t tmem_cols = (2 * C <= 128) ? 128 : (2 * C <= 256 ? 256 : 512);
 
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.hmap); tma_prefetch_desc(&p.wmap); }
+  const bool has_res = p.residual != nullptr;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.hmap); tma_prefetch_desc(&p.wmap); if (has_res) tma_prefetch_desc(&p.rmap); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < LF_H_SLOTS; ++s) { mbar_init(&h_full[s], 1); mbar_init(&h_empty[s], LF_DW_WARPS); }
     for (int s = 0; s < 2; ++s) {
@@ -63,6 +73,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_co
       mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], LF_DW_WARPS);
     }
     for (int s = 0; s < p.b_slots; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&r_full[s], 1); mbar_init(&r_empty[s], 1); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -72,6 +83,19 @@ __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_co
   if (warp >= 4) {
     const int i = threadIdx.x - 128;
     if (i < 256) bias_s[i] = (p.bias2 && i < C) ? __ldg(p.bias2 + i) : 0.f;
+    if (i < 64) {   // identity row i in the K-major SWIZZLE_128B layout: 16-byte chunk c of row n sits at chunk c ^ (n & 7)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (c == (i >> 3)) {
+          const uint32_t one = (i & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0 in element (i & 7) of the chunk
+          const int wsel = (i & 7) >> 1;
+          v.x = wsel == 0 ? one : 0u; v.y = wsel == 1 ? one : 0u; v.z = wsel == 2 ? one : 0u; v.w = wsel == 3 ? one : 0u;
+        }
+        *reinterpret_cast<uint4*>(smem_i + i * 128 + ((c ^ (i & 7)) << 4)) = v;
+      }
+      fence_proxy_async();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -96,6 +120,25 @@ __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_co
         __syncwarp();
       }
     }
+  } else if (warp == 2) {
+    // ================= residual slice producer =================
+    if (has_res) {
+      const uint32_t rsh = (uint32_t)p.r_slots - 1;   // r_slots is 1 or 2
+      uint32_t rg = 0;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+        const int img = mt / tiles_per_img, r = mt % tiles_per_img;
+        const int y0 = (r / p.tiles_x) * LF_TH, x0 = (r % p.tiles_x) * LF_TW;
+        for (int kc = 0; kc < C / 64; ++kc, ++rg) {
+          const uint32_t rs = rg & rsh;
+          mbar_wait(&r_empty[rs], ((rg >> rsh) & 1) ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&r_full[rs], (uint32_t)LF_A_BYTES);
+            tma_load_4d(smem_r + rs * LF_A_BYTES, &p.rmap, &r_full[rs], kc * 64, x0, y0, img);
+          }
+          __syncwarp();
+        }
+      }
+    }
   } else if (warp == 3) {
     // ================= W2 slab producer =================
     uint32_t g = 0;
@@ -114,12 +157,30 @@ __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_co
     const uint32_t idesc = make_idesc_bf16(C);
     const uint64_t desc_hi = make_sw128_desc(0);
     const uint32_t sa0 = smem_u32(smem_a), sb0 = smem_u32(smem_b);
-    uint32_t g = 0;
+    const uint32_t idesc64 = make_idesc_bf16(64);
+    const uint32_t sr0 = smem_u32(smem_r), si0 = smem_u32(smem_i) >> 4;
+    const uint32_t rsh = (uint32_t)p.r_slots - 1;
+    uint32_t g = 0, rg = 0;
     int it = 0;
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++it) {
       const int acc = it & 1;
       mbar_wait(&tmem_empty[acc], (((uint32_t)it >> 1) & 1) ^ 1);
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * C);
+      if (has_res) {   // acc[:, 64kc .. 64kc+63] = residual slice . I  (initialises the accumulator)
+        for (int kc = 0; kc < C / 64; ++kc, ++rg) {
+          const uint32_t rs = rg & rsh;
+          mbar_wait(&r_full[rs], (rg >> rsh) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_lo = (sr0 + rs * LF_A_BYTES) >> 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_d + (uint32_t)(kc * 64), desc_hi + (uint64_t)(a_lo + 2 * k), desc_hi + (uint64_t)(si0 + 2 * k), idesc64, (uint32_t)(k != 0));
+            umma_commit(&r_empty[rs]);
+          }
+          __syncwarp();
+        }
+      }
       for (int c = 0; c < p.nchunks; ++c, ++g) {
         const uint32_t as = g & 1, slot = g & bmask;
         mbar_wait(&a_full[as], (g >> 1) & 1);
@@ -129,7 +190,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_co
           const uint32_t a_lo = (sa0 + as * LF_A_BYTES) >> 4, b_lo = (sb0 + slot * b_bytes) >> 4;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_d, desc_hi + (uint64_t)(a_lo + 2 * k), desc_hi + (uint64_t)(b_lo + 2 * k), idesc, (uint32_t)((c | k) != 0));
+            umma_bf16(tmem_d, desc_hi + (uint64_t)(a_lo + 2 * k), desc_hi + (uint64_t)(b_lo + 2 * k), idesc, (uint32_t)(has_res || (c | k) != 0));
           umma_commit(&a_empty[as]);
           umma_commit(&b_empty[slot]);
           if (c == p.nchunks - 1) umma_commit(&tmem_full[acc]);
@@ -165,7 +226,6 @@ __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_co
         tmem_ld_wait();
         if (valid) {
           const int64_t pix = (int64_t)y * p.W + x;
-          const bf16* rp = p.residual ? p.residual + img * p.res_img_stride + pix * p.res_ld + cbeg + c0 : nullptr;
           bf16* op = p.out + img * p.out_img_stride + pix * p.out_ld + cbeg + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
@@ -175,12 +235,6 @@ __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_co
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]) + bb[e];
-            if (rp) {
-              float t[8];
-              load_vec<bf16, 8>(rp + j, t);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] += t[e];
-            }
             store_vec<bf16, 8>(op + j, f);
           }
         }
@@ -198,56 +252,63 @@ __global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_co
         const uint32_t hs = g & (LF_H_SLOTS - 1), as = g & 1;
         // depthwise weights / bias of this thread's 4 channels (L1-resident after the first tile)
         const int ch0 = c * 64 + cg4 * 4;
-        float w[9][4], bdw[4];
+        // packed fp32x2 arithmetic (FFMA2): channel pairs (0,1) and (2,3) of the thread's 4 channels
+        f32x2 w[9][2], bdw[2];
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           const float4 a = __ldg(reinterpret_cast<const float4*>(p.dw_w + (size_t)t * p.Hd + ch0));
-          w[t][0] = a.x; w[t][1] = a.y; w[t][2] = a.z; w[t][3] = a.w;
+          w[t][0] = pack_f2(a.x, a.y); w[t][1] = pack_f2(a.z, a.w);
         }
         {
           const float4 a = __ldg(reinterpret_cast<const float4*>(p.dw_b + ch0));
-          bdw[0] = a.x; bdw[1] = a.y; bdw[2] = a.z; bdw[3] = a.w;
+          bdw[0] = pack_f2(a.x, a.y); bdw[1] = pack_f2(a.z, a.w);
         }
-        float acc[RPT][4];
+        f32x2 acc[RPT][2];
 #pragma unroll
-        for (int o = 0; o < RPT; ++o)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) acc[o][e] = bdw[e];
+        for (int o = 0; o < RPT; ++o) { acc[o][0] = bdw[0]; acc[o][1] = bdw[1]; }
         mbar_wait(&h_full[hs], (g / LF_H_SLOTS) & 1);  // halo tile landed
         mbar_wait(&a_empty[as], ((g >> 1) & 1) ^ 1);   // A slot consumed by the MMAs that used it last
         // explicit shared-space addresses: through generic pointers these became LD/ST (long-scoreboard) instead of LDS/STS
-        const uint32_t hbase = smem_u32(smem_h) + hs * LF_H_SLOT + ((rq * RPT) * LF_HW + col) * 128 + cg4 * 8;
+        uint32_t hbase = smem_u32(smem_h) + hs * LF_H_SLOT + ((rq * RPT) * LF_HW + col) * 128 + cg4 * 8;
         const uint32_t abase = smem_u32(smem_a) + as * LF_A_BYTES;
+        // The halo loads below are plain (non-volatile) asm so the compiler may hoist them ahead of the FMAs of earlier rows;
+        // laundering the base address here pins them after the two barrier waits above.
+        asm volatile("" : "+r"(hbase) : : "memory");
 #pragma unroll
         for (int hr = 0; hr < RPT + 2; ++hr) {      // halo rows feeding this thread's RPT output rows
-          float rv[3][4];
+          f32x2 rv[3][2];
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
             uint2 u;
-            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(u.x), "=r"(u.y) : "r"(hbase + (uint32_t)((hr * LF_HW + kx) * 128)));
-            rv[kx][0] = __uint_as_float(u.x << 16); rv[kx][1] = __uint_as_float(u.x & 0xffff0000u);
-            rv[kx][2] = __uint_as_float(u.y << 16); rv[kx][3] = __uint_as_float(u.y & 0xffff0000u);
+            asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(u.x), "=r"(u.y) : "r"(hbase + (uint32_t)((hr * LF_HW + kx) * 128)));
+            rv[kx][0] = bf16x2_to_f2(u.x);
+            rv[kx][1] = bf16x2_to_f2(u.y);
           }
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
-            const int o = hr - ky;                   // output row (within the thread's 8) this halo row feeds with tap row ky
+            const int o = hr - ky;                   // output row (within the thread's RPT) this halo row feeds with tap row ky
             if (o >= 0 && o < RPT) {
 #pragma unroll
-              for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) acc[o][e] = fmaf(rv[kx][e], w[ky * 3 + kx][e], acc[o][e]);
+              for (int kx = 0; kx < 3; ++kx) {
+                acc[o][0] = fma_f2(rv[kx][0], w[ky * 3 + kx][0], acc[o][0]);
+                acc[o][1] = fma_f2(rv[kx][1], w[ky * 3 + kx][1], acc[o][1]);
+              }
             }
           }
           if (hr >= 2) {                             // output row hr-2 is complete
             const int o = hr - 2;
-            float f[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) f[e] = erf_gelu ? gelu_erf(acc[o][e]) : gelu_tanh_fast(acc[o][e]);
-            const int rr = (rq * RPT + o) * LF_TW + col;        // A-tile row = pixel index in the 8x16 tile
-            const __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
             uint2 ov;
-            ov.x = *reinterpret_cast<const uint32_t*>(&h0);
-            ov.y = *reinterpret_cast<const uint32_t*>(&h1);
+            if (erf_gelu) {
+              float f[4];
+              unpack_f2(acc[o][0], f[0], f[1]);
+              unpack_f2(acc[o][1], f[2], f[3]);
+              ov.x = f2_to_bf16x2(pack_f2(gelu_erf(f[0]), gelu_erf(f[1])));
+              ov.y = f2_to_bf16x2(pack_f2(gelu_erf(f[2]), gelu_erf(f[3])));
+            } else {
+              ov.x = f2_to_bf16x2(gelu_tanh_fast_f2(acc[o][0]));
+              ov.y = f2_to_bf16x2(gelu_tanh_fast_f2(acc[o][1]));
+            }
+            const int rr = (rq * RPT + o) * LF_TW + col;        // A-tile row = pixel index in the 8x16 tile
             asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(abase + (uint32_t)(rr * 128 + (((cg4 >> 1) ^ (rr & 7)) << 4) + (cg4 & 1) * 8)),
                          "r"(ov.x), "r"(ov.y));
           }
@@ -308,6 +369,15 @@ extern "C" int fbanet_leff_fc2_sm100(const fbanet_leff_fc2_params* p, void* stre
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return FBANET_E_BADSHAPE;
   }
+  if (p->residual) {
+    const cuuint64_t dims[4] = {(cuuint64_t)p->C, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
+    const cuuint64_t strides[3] = {(cuuint64_t)p->res_ld * 2, (cuuint64_t)p->res_ld * 2 * p->W, (cuuint64_t)p->res_img_stride * 2};
+    const cuuint32_t box[4] = {64, LF_TW, LF_TH, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (encode(&lp.rmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->residual), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return FBANET_E_BADSHAPE;
+  }
   lp.dw_w = p->dw_weight; lp.dw_b = p->dw_bias; lp.bias2 = p->bias2;
   lp.residual = reinterpret_cast<const bf16*>(p->residual); lp.out = reinterpret_cast<bf16*>(p->out);
   lp.res_img_stride = p->res_img_stride; lp.out_img_stride = p->out_img_stride; lp.res_ld = p->res_ld; lp.out_ld = p->out_ld;
@@ -317,9 +387,11 @@ extern "C" int fbanet_leff_fc2_sm100(const fbanet_leff_fc2_params* p, void* stre
   lp.m_tiles = p->N * lp.tiles_x * lp.tiles_y;
   lp.nchunks = p->Hd / 64;
   const int b_bytes = p->C * 128;
-  int b = (208 * 1024 - 2 * LF_A_BYTES - LF_H_SLOTS * LF_H_SLOT) / b_bytes;
+  lp.r_slots = p->C == 256 ? 1 : 2;   // residual slices in flight (C/64 per tile); one slot is all that fits beside 32 KB weight slabs
+  const int fixed = 2 * LF_A_BYTES + lp.r_slots * LF_A_BYTES + LF_I_BYTES + LF_H_SLOTS * LF_H_SLOT;
+  int b = (226 * 1024 - fixed) / b_bytes;
   lp.b_slots = b >= 8 ? 8 : (b >= 4 ? 4 : 2);
-  const size_t smem = 2 * LF_A_BYTES + (size_t)lp.b_slots * b_bytes + LF_H_SLOTS * LF_H_SLOT + 1024;
+  const size_t smem = (size_t)fixed + (size_t)lp.b_slots * b_bytes + 1024;
   static size_t opted = 0;
   if (smem > opted) {
     cudaError_t e = cudaFuncSetAttribute(leff_fc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
