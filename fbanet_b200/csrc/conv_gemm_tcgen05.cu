@@ -56,7 +56,7 @@ struct TcParams {
   int act, store_mode, res_ld, out_ld;
   int a_slots, a_slot_bytes, a_box_bytes;
   int b_slots, b_resident;
-  int tma_store;          // 1: epilogue stages 128x64 bf16 tiles in smem and stores them with TMA
+  int tma_store;          // 1: each epilogue warp stages 32x64 bf16 sub-tiles in smem and stores them with TMA
 };
 
 template <int NV>
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
   __shared__ __align__(8) uint64_t b_full[TC_MAX_STEPS], b_empty[TC_MAX_STEPS];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float bias_s[256];
-  __shared__ __align__(8) uint64_t res_bar[2];
+  __shared__ __align__(8) uint64_t res_bar[8];
 
   // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the 128B swizzle needs
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
   const uint32_t b_bytes = (uint32_t)BN * TC_BK * 2;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)p.a_slots * p.a_slot_bytes;
-  uint8_t* smem_stage = smem_b + (size_t)p.b_slots * b_bytes;   // 2 x 16 KB epilogue staging tiles (one per column half)
+  uint8_t* smem_stage = smem_b + (size_t)p.b_slots * b_bytes;   // 8 epilogue warps x 2 x 4 KB staging sub-tiles
   const uint32_t tmem_cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 
   if (warp == 0 && lane == 0) {
@@ -205,7 +205,8 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.a_slots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.b_slots; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); mbar_init(&res_bar[a], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+    for (int a = 0; a < 8; ++a) mbar_init(&res_bar[a], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -355,85 +356,98 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
     const float alpha = (p.act == FBANET_ACT_PRELU) ? __ldg(p.alpha) : 0.f;
     int it = 0;
     if (p.tma_store) {
-      // ---- staged epilogue: 64-column chunks -> swizzled 128x64 bf16 smem tile -> one TMA store per chunk.
+      // ---- per-warp staged epilogue.  A warp owns 32 pixel rows of the tile (its TMEM lane quarter), which form a
+      // rectangle {bw, 32/bw} of the output image, so it can stage and TMA-store its own 32 x 64-column sub-tiles (4 KB,
+      // SWIZZLE_128B) with no CTA-level barrier at all: tcgen05.ld -> bias/act(/residual) -> st.shared -> fence ->
+      // __syncwarp -> one bulk store.  Two staging buffers per warp: the store of chunk k drains while chunk k+1 is computed.
+      // The residual sub-tile is TMA-loaded into the staging buffer first and added in place.  64-column chunks are dealt
+      // alternately to the two warps of a lane quarter, counted across tiles so any chunks-per-tile count balances.
       // (Per-thread 16-byte global stores touch 32 lines per instruction and cap an SM at ~16 B/clk.)
-      uint8_t* stage = smem_stage + half * 16384;
-      const uint32_t row_addr = smem_u32(stage) + (uint32_t)row * 128u;
-      const int r7 = row & 7;
+      const int ew = warp - 4;                             // 0..7
+      uint8_t* stage0 = smem_stage + ew * 8192;
+      const uint32_t stage_u = smem_u32(stage0);
+      const int r7 = lane & 7;
       const int nchunks = BN >> 6;
       const bool has_res = p.residual != nullptr;
       const int Co = p.store_mode == FBANET_STORE_CONVT2 ? (p.Cout >> 2) : p.Cout;
-      uint32_t res_phase = 0;
+      const int wy0 = (q * 32) / p.tw, wx0 = (q * 32) % p.tw;   // this warp's rectangle inside the tile
+      uint32_t res_phase = 0, nb = 0;
       for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         const int img = mt / tiles_per_img, r = mt % tiles_per_img;
-        const int y0 = (r / p.tiles_x) * p.th, x0 = (r % p.tiles_x) * p.tw;
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
+        const int y0 = (r / p.tiles_x) * p.th + wy0, x0 = (r % p.tiles_x) * p.tw + wx0;
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-        for (int cidx = half; cidx < nchunks; cidx += 2) {
+        bool waited = false;
+        for (int cidx = 0; cidx < nchunks; ++cidx) {
+          if (((it * nchunks + cidx) & 1) != half) continue;
           const int col0 = nt * BN + cidx * 64;          // GEMM column of the chunk
-          uint32_t v0[32], v1[32];
-          tmem_ld32(taddr0 + cidx * 64, v0);
-          tmem_ld32(taddr0 + cidx * 64 + 32, v1);
-          if (q == 0) {
-            if (elect_one()) {
-              bulk_wait_read0();                         // the previous store has finished reading the tile
-              if (has_res) {
-                mbar_expect_tx(&res_bar[half], (uint32_t)p.a_box_bytes);
-                tma_load_4d(stage, &p.rmap, &res_bar[half], col0, x0, y0, img);
-              }
+          const uint32_t sbuf = stage_u + (nb & 1) * 4096;
+          uint8_t* gbuf = stage0 + (nb & 1) * 4096;
+          ++nb;
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used this buffer has read it
+            if (has_res) {
+              mbar_expect_tx(&res_bar[ew], 4096u);
+              tma_load_4d(gbuf, &p.rmap, &res_bar[ew], col0, x0, y0, img);
             }
-            __syncwarp();
           }
-          named_bar_sync(1 + half, 128);                 // staging tile is free (and the residual is on its way)
+          __syncwarp();
+          if (!waited) { mbar_wait(&tmem_full[acc], acc_phase); tc_fence_after(); waited = true; }
+          uint32_t v[64];
+          tmem_ld32(taddr0 + cidx * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld32(taddr0 + cidx * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
           tmem_ld_wait();
-          if (has_res) { mbar_wait(&res_bar[half], res_phase); res_phase ^= 1; }
+          if (has_res) { mbar_wait(&res_bar[ew], res_phase); res_phase ^= 1; }
           const float* bs = bias_s + cidx * 64;
+          const uint32_t row_addr = sbuf + (uint32_t)lane * 128u;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {                  // 8 columns = one 16-byte smem chunk at a time
-            float f[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(c < 4 ? v0[c * 8 + e] : v1[(c - 4) * 8 + e]);
             const float4 b0 = *reinterpret_cast<const float4*>(bs + c * 8), b1 = *reinterpret_cast<const float4*>(bs + c * 8 + 4);
-            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-            apply_act_vec<8>(f, p.act, alpha);
+            f32x2 f[4];
+            f[0] = add_f2(pack_f2(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1])), pack_f2(b0.x, b0.y));
+            f[1] = add_f2(pack_f2(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3])), pack_f2(b0.z, b0.w));
+            f[2] = add_f2(pack_f2(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5])), pack_f2(b1.x, b1.y));
+            f[3] = add_f2(pack_f2(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7])), pack_f2(b1.z, b1.w));
+            if (p.act == FBANET_ACT_GELU_TANH) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) f[e] = gelu_tanh_fast_f2(f[e]);
+            } else if (p.act != FBANET_ACT_NONE) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float lo, hi;
+                unpack_f2(f[e], lo, hi);
+                if (p.act == FBANET_ACT_RELU) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+                else if (p.act == FBANET_ACT_PRELU) { lo = lo > 0.f ? lo : alpha * lo; hi = hi > 0.f ? hi : alpha * hi; }
+                else { lo = gelu_erf(lo); hi = gelu_erf(hi); }
+                f[e] = pack_f2(lo, hi);
+              }
+            }
             const uint32_t saddr = row_addr + (uint32_t)((c ^ r7) << 4);   // SWIZZLE_128B position of chunk c in this row
             if (has_res) {
               uint4 rv;
               asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(saddr));
-              const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) { f[2 * e] += __uint_as_float(ru[e] << 16); f[2 * e + 1] += __uint_as_float(ru[e] & 0xffff0000u); }
+              f[0] = add_f2(f[0], bf16x2_to_f2(rv.x)); f[1] = add_f2(f[1], bf16x2_to_f2(rv.y));
+              f[2] = add_f2(f[2], bf16x2_to_f2(rv.z)); f[3] = add_f2(f[3], bf16x2_to_f2(rv.w));
             }
-            uint32_t o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-              o[e] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]));
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(f2_to_bf16x2(f[0])), "r"(f2_to_bf16x2(f[1])),
+                         "r"(f2_to_bf16x2(f[2])), "r"(f2_to_bf16x2(f[3])));
           }
           fence_proxy_async();                           // generic-proxy smem writes -> visible to the TMA engine
-          named_bar_sync(1 + half, 128);
-          if (q == 0) {
-            if (elect_one()) {
-              const int qq = col0 / Co;                  // 2x2 scatter store: sub-pixel plane of this chunk (0 for NHWC)
-              tma_store_4d(&p.omap[qq], stage, col0 - qq * Co, x0, y0, img);
-              bulk_commit();
-            }
-            __syncwarp();
+          __syncwarp();
+          if (lane == 0) {
+            const int qq = col0 / Co;                    // 2x2 scatter store: sub-pixel plane of this chunk (0 for NHWC)
+            tma_store_4d(&p.omap[qq], gbuf, col0 - qq * Co, x0, y0, img);
+            bulk_commit();
           }
         }
+        if (!waited) { mbar_wait(&tmem_full[acc], acc_phase); tc_fence_after(); }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       }
-      if (q == 0) {
-        if (elect_one()) bulk_wait0();                   // all stores of this CTA have completed
-        __syncwarp();
-      }
+      if (lane == 0) bulk_wait0();                       // all stores of this warp have completed
+      __syncwarp();
     } else {
       const int ncols = (BN >= 32) ? BN / 2 : (half == 0 ? BN : 0);
       const int cbeg = half * (BN / 2);
@@ -649,24 +663,24 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   tp.res_img_stride = p->res_img_stride; tp.out_img_stride = p->out_img_stride; tp.base_img_stride = p->base_img_stride;
   tp.act = p->act; tp.store_mode = p->store_mode; tp.res_ld = p->res_ld; tp.out_ld = p->out_ld;
 
-  // TMA-store epilogue for the channels-last store modes (64-column chunks)
-  // Measured (profiles/r1_notes.md): the staged TMA store only pays for wide plain stores (qkv-type GEMMs, BN >= 192,
-  // no activation / residual); elsewhere the two extra named barriers per chunk cost more than the coalescing gains
-  // because those layers already sit at the HBM write rate.  FBANET_TC_TMA_STORE=0/1 forces it off/on.
-  const bool store_ok = (p->store_mode == FBANET_STORE_NHWC || (p->store_mode == FBANET_STORE_CONVT2 && (p->Cout / 4) % 64 == 0)) && tp.BN % 64 == 0;
-  static const char* force = getenv("FBANET_TC_TMA_STORE");
-  if (force) tp.tma_store = (store_ok && force[0] == '1') ? 1 : 0;
-  else tp.tma_store = (store_ok && tp.BN >= 192 && p->act == FBANET_ACT_NONE && !p->residual) ? 1 : 0;
+  // TMA-store epilogue for the channels-last store modes: 64-column chunks, one 32-row rectangle {bw, 32/bw} per epilogue warp.
+  // Needs a tile width that divides (or is a multiple of) 32 so a warp's 32 accumulator rows are a rectangle of the image.
+  const bool rect_ok = tw == 8 || tw == 16 || tw == 32 || tw == 64 || tw == 128;
+  const bool store_ok = rect_ok && (p->store_mode == FBANET_STORE_NHWC || (p->store_mode == FBANET_STORE_CONVT2 && (p->Cout / 4) % 64 == 0)) &&
+                        tp.BN % 64 == 0 && p->Cout_store == p->Cout;
+  static const char* force = getenv("FBANET_TC_TMA_STORE");   // experiment switch: 0 = per-thread 16-byte stores everywhere
+  tp.tma_store = (store_ok && !(force && force[0] == '0')) ? 1 : 0;
   if (tp.tma_store) {
     const bool ct = p->store_mode == FBANET_STORE_CONVT2;
     const int Co = ct ? p->Cout / 4 : p->Cout_store;
+    const int bw = tw < 32 ? tw : 32, bh = 32 / bw;
     const int64_t sx = ct ? 2 * (int64_t)p->out_ld : p->out_ld;                    // elements between tile-space pixels
     const int64_t sy = ct ? 4 * (int64_t)p->Wo * p->out_ld : (int64_t)p->Wo * p->out_ld;
     for (int qq = 0; qq < (ct ? 4 : 1); ++qq) {
       const int64_t off = ct ? ((int64_t)(qq >> 1) * 2 * p->Wo + (qq & 1)) * p->out_ld : 0;
       const cuuint64_t dims[4] = {(cuuint64_t)Co, (cuuint64_t)p->Wo, (cuuint64_t)p->Ho, (cuuint64_t)p->N};
       const cuuint64_t strides[3] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)p->out_img_stride * 2};
-      const cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, 1};
+      const cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
       const cuuint32_t estr[4] = {1, 1, 1, 1};
       CUresult r = encode(&tp.omap[qq], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, reinterpret_cast<bf16*>(p->out) + off, dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -678,7 +692,7 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
     if (p->residual) {
       const cuuint64_t dims[4] = {(cuuint64_t)p->Cout, (cuuint64_t)p->Wo, (cuuint64_t)p->Ho, (cuuint64_t)p->N};
       const cuuint64_t strides[3] = {(cuuint64_t)p->res_ld * 2, (cuuint64_t)p->Wo * p->res_ld * 2, (cuuint64_t)p->res_img_stride * 2};
-      const cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, 1};
+      const cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
       const cuuint32_t estr[4] = {1, 1, 1, 1};
       CUresult r = encode(&tp.rmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->residual), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -686,26 +700,40 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
       if (r != CUDA_SUCCESS) return FBANET_E_BADSHAPE;
     }
   }
-  // shared-memory plan: A ring + B ring (or all B slabs resident when they fit) + 2 staging tiles
-  const int stage_bytes = tp.tma_store ? 2 * 16384 : 0;
-  const int budget = 216 * 1024 - stage_bytes;
+  // shared-memory plan: A ring + B ring (or all B slabs resident when they fit) + the epilogue staging sub-tiles.
+  // The staged TMA-store epilogue is kept only where its 64 KB do not cost the mainloop anything (same weight residency,
+  // same B ring, >= 4 A slots): the 3x3 halo convs and the K = 896 fusion GEMM need that memory for operands.
   const int b_bytes = tp.BN * TC_BK * 2;
   tp.a_slot_bytes = halo ? TC_HALO_SLOT : TC_A_BYTES;
   const int a_min = halo ? 2 : 3;
   const int units = halo ? tp.nchunks : ns;
-  if ((int64_t)ns * b_bytes + (int64_t)a_min * tp.a_slot_bytes <= budget) {
-    tp.b_resident = 1;
-    tp.b_slots = ns;
-    int a = (budget - ns * b_bytes) / tp.a_slot_bytes;
-    tp.a_slots = a > TC_MAX_A_SLOTS ? TC_MAX_A_SLOTS : a;
-  } else {
-    tp.b_resident = 0;
-    tp.a_slots = halo ? 2 : 4;
-    int b = (budget - tp.a_slots * tp.a_slot_bytes) / b_bytes;
-    if (b < 2) return FBANET_E_UNSUPPORTED;
-    tp.b_slots = b >= 8 ? 8 : (b >= 4 ? 4 : 2);   // power of two: ring slot = step & (slots-1)
+  struct Plan { int resident, a_slots, b_slots; };
+  auto plan = [&](int budget, Plan* pl) -> bool {
+    if ((int64_t)ns * b_bytes + (int64_t)a_min * tp.a_slot_bytes <= budget) {
+      pl->resident = 1;
+      pl->b_slots = ns;
+      const int a = (budget - ns * b_bytes) / tp.a_slot_bytes;
+      pl->a_slots = a > TC_MAX_A_SLOTS ? TC_MAX_A_SLOTS : a;
+    } else {
+      pl->resident = 0;
+      pl->a_slots = halo ? 2 : 4;
+      const int b = (budget - pl->a_slots * tp.a_slot_bytes) / b_bytes;
+      if (b < 2) return false;
+      pl->b_slots = b >= 8 ? 8 : (b >= 4 ? 4 : 2);   // power of two: ring slot = step & (slots-1)
+    }
+    if (pl->a_slots > units * 2 && units * 2 >= 2) pl->a_slots = units * 2;
+    return true;
+  };
+  const int stage_full = 8 * 2 * 4096;
+  Plan p0, p1;
+  if (!plan(216 * 1024, &p0)) return FBANET_E_UNSUPPORTED;
+  if (tp.tma_store) {
+    const int want_a = p0.a_slots < 4 ? p0.a_slots : 4;
+    if (!(plan(216 * 1024 - stage_full, &p1) && p1.resident == p0.resident && p1.b_slots == p0.b_slots && p1.a_slots >= want_a)) tp.tma_store = 0;
+    else p0 = p1;
   }
-  if (tp.a_slots > units * 2 && units * 2 >= 2) tp.a_slots = units * 2;
+  const int stage_bytes = tp.tma_store ? stage_full : 0;
+  tp.b_resident = p0.resident; tp.a_slots = p0.a_slots; tp.b_slots = p0.b_slots;
   const size_t smem = (size_t)tp.a_slots * tp.a_slot_bytes + (size_t)tp.b_slots * b_bytes + stage_bytes + 1024;
 
   static size_t smem_opted_in = 0;  // opt-in limit is per function; raise it only when a launch needs more

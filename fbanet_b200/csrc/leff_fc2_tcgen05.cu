@@ -15,6 +15,7 @@
 //
 // Warps (640 threads, persistent, 1 CTA/SM): 0 = h1 halo TMA, 1 = MMA issuer, 2 = TMEM alloc + residual TMA, 3 = W2 TMA,
 // 4..19 = depthwise producer + epilogue (the epilogue of tile i runs after chunk 0 of tile i+1 is produced).
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -27,8 +28,6 @@ constexpr int LF_HW = LF_TW + 2, LF_HH = LF_TH + 2;        // halo tile
 constexpr int LF_H_BYTES = LF_HW * LF_HH * 128;            // 23040: halo pixels x 64 ch bf16
 constexpr int LF_H_SLOT = 23552;                           // padded to 1 KB
 constexpr int LF_A_BYTES = 128 * 128;                      // A tile: 128 px x 64 ch bf16
-constexpr int LF_DW_WARPS = 16;                            // depthwise/epilogue warps (4 output rows per thread)
-constexpr int LF_THREADS = 128 + 32 * LF_DW_WARPS;
 constexpr int LF_H_SLOTS = 4;                              // halo ring depth: TMA latency (~1-2 us) spans several chunks of compute
 constexpr int LF_I_BYTES = 64 * 128;                       // 64x64 bf16 identity (B operand of the residual MMAs)
 
@@ -47,7 +46,9 @@ struct LeffParams {
   int tiles_x, tiles_y, m_tiles, nchunks, b_slots, r_slots;
 };
 
-__global__ void __launch_bounds__(LF_THREADS, 1) leff_fc2_kernel(const __grid_constant__ LeffParams p) {
+// LF_DW_WARPS = depthwise/epilogue warps: 16 (4 output rows per thread) or 8 (8 rows per thread)
+template <int LF_DW_WARPS>
+__global__ void __launch_bounds__(128 + 32 * LF_DW_WARPS, 1) leff_fc2_kernel(const __grid_constant__ LeffParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t h_full[LF_H_SLOTS], h_empty[LF_H_SLOTS], a_full[2], a_empty[2], b_full[8], b_empty[8], tmem_full[2], tmem_empty[2], r_full[2], r_empty[2];
   __shared__ uint32_t tmem_base_slot;
@@ -392,9 +393,12 @@ extern "C" int fbanet_leff_fc2_sm100(const fbanet_leff_fc2_params* p, void* stre
   int b = (226 * 1024 - fixed) / b_bytes;
   lp.b_slots = b >= 8 ? 8 : (b >= 4 ? 4 : 2);
   const size_t smem = (size_t)fixed + (size_t)lp.b_slots * b_bytes + 1024;
+  static const char* env8 = getenv("FBANET_LEFF_WARPS8");
+  const bool w8 = env8 && env8[0] == '1';
   static size_t opted = 0;
   if (smem > opted) {
-    cudaError_t e = cudaFuncSetAttribute(leff_fc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(leff_fc2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(leff_fc2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cudaGetLastError(); set_last_error(e); return FBANET_E_LAUNCH; }
     opted = smem;
   }
@@ -402,6 +406,7 @@ extern "C" int fbanet_leff_fc2_sm100(const fbanet_leff_fc2_params* p, void* stre
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = lp.m_tiles < sms ? lp.m_tiles : sms;
-  leff_fc2_kernel<<<grid, LF_THREADS, smem, (cudaStream_t)stream>>>(lp);
+  if (w8) leff_fc2_kernel<8><<<grid, 128 + 32 * 8, smem, (cudaStream_t)stream>>>(lp);
+  else leff_fc2_kernel<16><<<grid, 128 + 32 * 16, smem, (cudaStream_t)stream>>>(lp);
   return check_launch();
 }
