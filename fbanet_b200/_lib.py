@@ -9,12 +9,12 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libfbanet_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_PRELU, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2, 3, 4
-STORE_NHWC, STORE_PS2, STORE_CONVT2, STORE_NCHW_BASE = 0, 1, 2, 3
+STORE_NHWC, STORE_PS2, STORE_CONVT2, STORE_NCHW_BASE, STORE_NHWC_F32 = 0, 1, 2, 3, 4
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 
 ERRORS = {-1: "bad shape", -2: "misaligned pointer/stride", -3: "unsupported dtype", -4: "CUDA launch failure", -5: "impl unsupported for this problem"}
@@ -107,6 +107,7 @@ class FafGateParams(C.Structure):
     _fields_ = [
         ("feat", C.c_void_p), ("gate", C.c_void_p), ("wsum", C.c_void_p), ("gated", C.c_void_p), ("dtype", C.c_int32),
         ("B", C.c_int32), ("F", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("_pad", C.c_int32),
+        ("score", C.c_void_p),
     ]
 
 

@@ -610,6 +610,51 @@ __global__ void __launch_bounds__(128) faf_gate_bf16_c64_kernel(const fbanet_faf
   }
 }
 
+// K2a with precomputed scores (bf16, C = 64): the 3x3x64 dot products come from the tensor cores (implicit GEMM with the
+// summed kernel as a 2-row weight matrix, fp32 NHWC_F32 store), so this kernel is pure streaming: 8 threads per pixel,
+// 16 bytes each, gate_f = sigmoid(|s_f - s_0|), gated features written pixel-major [B][H][W][F][C].
+__global__ void __launch_bounds__(256) faf_gate_apply_bf16_c64_kernel(const fbanet_faf_gate_params p) {
+  constexpr int C = 64;
+  const int sub = threadIdx.x & 7;
+  const int64_t hw = (int64_t)p.H * p.W;
+  const int64_t gp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  if (gp >= (int64_t)p.B * hw) return;
+  const int64_t b = gp / hw, pix = gp % hw;
+  const bf16* feat = reinterpret_cast<const bf16*>(p.feat) + (b * p.F * hw + pix) * C + sub * 8;
+  const float2* sc = reinterpret_cast<const float2*>(p.score) + b * p.F * hw + pix;
+  bf16* gated = p.gated ? reinterpret_cast<bf16*>(p.gated) + ((b * hw + pix) * p.F) * C + sub * 8 : nullptr;
+  const float2 s00 = __ldg(sc);
+  const float s0 = s00.x + s00.y;
+  if (gated) *reinterpret_cast<uint4*>(gated) = __ldg(reinterpret_cast<const uint4*>(feat));   // frame 0 passes through (:103)
+#pragma unroll 1
+  for (int f0 = 1; f0 < p.F; f0 += 4) {   // 4 frames in flight per thread
+    uint4 v[4];
+    float2 s[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (f0 + k < p.F) {
+        s[k] = __ldg(sc + (int64_t)(f0 + k) * hw);
+        if (gated) v[k] = __ldg(reinterpret_cast<const uint4*>(feat + (int64_t)(f0 + k) * hw * C));
+      }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (f0 + k < p.F) {
+        const int f = f0 + k;
+        const float g = 1.0f / (1.0f + __expf(-fabsf((s[k].x + s[k].y) - s0)));
+        if (sub == 0 && p.gate) p.gate[(b * (p.F - 1) + (f - 1)) * hw + pix] = g;
+        if (gated) {
+          const f32x2 g2 = pack_f2(g, g);
+          uint4 o;
+          o.x = f2_to_bf16x2(mul_f2(bf16x2_to_f2(v[k].x), g2));
+          o.y = f2_to_bf16x2(mul_f2(bf16x2_to_f2(v[k].y), g2));
+          o.z = f2_to_bf16x2(mul_f2(bf16x2_to_f2(v[k].z), g2));
+          o.w = f2_to_bf16x2(mul_f2(bf16x2_to_f2(v[k].w), g2));
+          *reinterpret_cast<uint4*>(gated + (int64_t)f * C) = o;
+        }
+      }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // full-size tiling: reflect index helper (torch 'reflect': no edge repeat)
 // ------------------------------------------------------------------------------------------------
@@ -788,6 +833,12 @@ static int launch_gate(const fbanet_faf_gate_params* p, cudaStream_t s) {
 extern "C" int fbanet_faf_gate_sm100(const fbanet_faf_gate_params* p, void* stream) {
   if (!p || !p->feat || (!p->gate && !p->gated) || !p->wsum || p->B <= 0 || p->F < 2) return FBANET_E_BADSHAPE;
   if (p->dtype == FBANET_F32) return launch_gate<float>(p, (cudaStream_t)stream);
+  if (p->score) {   // scores precomputed on the tensor cores
+    if (p->dtype != FBANET_BF16 || p->C != 64 || ((uintptr_t)p->feat % 16) || ((uintptr_t)p->gated % 16) || ((uintptr_t)p->score % 8)) return FBANET_E_UNSUPPORTED;
+    const int64_t threads = (int64_t)p->B * p->H * p->W * 8;
+    faf_gate_apply_bf16_c64_kernel<<<ceil_div(threads, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+    return check_launch();
+  }
   if (p->dtype == FBANET_BF16) {
     if (p->C == 64 && ((uintptr_t)p->feat % 16) == 0 && ((uintptr_t)p->wsum % 16) == 0 && ((uintptr_t)p->gated % 16) == 0) {
       const int64_t threads = (int64_t)p->B * p->H * p->W * 8;

@@ -189,7 +189,8 @@ int conv_gemm_validate(const fbanet_conv_params* p) {
   if (p->residual && p->store_mode != FBANET_STORE_NHWC) return FBANET_E_BADSHAPE;
   if ((p->store_mode == FBANET_STORE_PS2 || p->store_mode == FBANET_STORE_CONVT2) && (p->Cout % 4)) return FBANET_E_BADSHAPE;
   if (p->store_mode == FBANET_STORE_NCHW_BASE && (!p->base || (p->Ho % 4) || (p->Wo % 4))) return FBANET_E_BADSHAPE;
-  if (p->store_mode < 0 || p->store_mode > 3) return FBANET_E_BADSHAPE;
+  if (p->store_mode < 0 || p->store_mode > 4) return FBANET_E_BADSHAPE;
+  if (p->store_mode == FBANET_STORE_NHWC_F32 && p->dtype != FBANET_BF16) return FBANET_E_BADSHAPE;
   if (p->act == FBANET_ACT_PRELU && !p->alpha) return FBANET_E_BADSHAPE;
   if (p->dtype != FBANET_F32 && p->dtype != FBANET_BF16) return FBANET_E_DTYPE;
   return FBANET_OK;

@@ -57,6 +57,7 @@ struct TcParams {
   int a_slots, a_slot_bytes, a_box_bytes;
   int b_slots, b_resident;
   int tma_store;          // 1: each epilogue warp stages 32x64 bf16 sub-tiles in smem and stores them with TMA
+  int stage_bufs;         // staging buffers per epilogue warp (2, or 1 when shared memory is tight)
 };
 
 template <int NV>
@@ -122,6 +123,13 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
         reinterpret_cast<float*>(p.out)[img * p.out_img_stride + ((int64_t)col * p.Ho + y) * p.Wo + x] = f[j] + bl;
       }
     }
+    return;
+  }
+  if (p.store_mode == FBANET_STORE_NHWC_F32) {   // narrow fp32 score map
+    float* op = reinterpret_cast<float*>(p.out) + img * p.out_img_stride + ((int64_t)y * p.Wo + x) * p.out_ld + col0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nc && col0 + j < p.Cout_store) op[j] = f[j];
     return;
   }
   int64_t opix;
@@ -364,7 +372,8 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
       // alternately to the two warps of a lane quarter, counted across tiles so any chunks-per-tile count balances.
       // (Per-thread 16-byte global stores touch 32 lines per instruction and cap an SM at ~16 B/clk.)
       const int ew = warp - 4;                             // 0..7
-      uint8_t* stage0 = smem_stage + ew * 8192;
+      const uint32_t nbufs = (uint32_t)p.stage_bufs;
+      uint8_t* stage0 = smem_stage + ew * 4096 * nbufs;
       const uint32_t stage_u = smem_u32(stage0);
       const int r7 = lane & 7;
       const int nchunks = BN >> 6;
@@ -382,11 +391,13 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
         for (int cidx = 0; cidx < nchunks; ++cidx) {
           if (((it * nchunks + cidx) & 1) != half) continue;
           const int col0 = nt * BN + cidx * 64;          // GEMM column of the chunk
-          const uint32_t sbuf = stage_u + (nb & 1) * 4096;
-          uint8_t* gbuf = stage0 + (nb & 1) * 4096;
+          const uint32_t boff = (nbufs == 2 ? (nb & 1u) : 0u) * 4096u;
+          const uint32_t sbuf = stage_u + boff;
+          uint8_t* gbuf = stage0 + boff;
           ++nb;
-          if (lane == 0) {
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used this buffer has read it
+          if (lane == 0) {   // the store that last used this buffer has read it
+            if (nbufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             if (has_res) {
               mbar_expect_tx(&res_bar[ew], 4096u);
               tma_load_4d(gbuf, &p.rmap, &res_bar[ew], col0, x0, y0, img);
@@ -563,6 +574,8 @@ static bool tc_shape_ok(const fbanet_conv_params* p) {
     if (p->residual && ((p->res_ld % 8) || (p->res_img_stride % 8) || ((uintptr_t)p->residual % 16))) return false;
   } else if (p->store_mode == FBANET_STORE_NCHW_BASE) {
     if (bn != 16 || p->Cout_store > 16) return false;
+  } else if (p->store_mode == FBANET_STORE_NHWC_F32) {
+    if (p->residual || ((uintptr_t)p->out % 4)) return false;
   }
   if (p->bias && ((uintptr_t)p->bias % 16)) return false;
   return get_encode() != nullptr;
@@ -724,15 +737,19 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
     if (pl->a_slots > units * 2 && units * 2 >= 2) pl->a_slots = units * 2;
     return true;
   };
-  const int stage_full = 8 * 2 * 4096;
   Plan p0, p1;
   if (!plan(216 * 1024, &p0)) return FBANET_E_UNSUPPORTED;
+  int stage_bytes = 0;
   if (tp.tma_store) {
     const int want_a = p0.a_slots < 4 ? p0.a_slots : 4;
-    if (!(plan(216 * 1024 - stage_full, &p1) && p1.resident == p0.resident && p1.b_slots == p0.b_slots && p1.a_slots >= want_a)) tp.tma_store = 0;
-    else p0 = p1;
+    tp.tma_store = 0;
+    for (int bufs = 2; bufs >= 1 && !tp.tma_store; --bufs) {
+      const int sb = 8 * bufs * 4096;
+      if (plan(216 * 1024 - sb, &p1) && p1.resident == p0.resident && p1.b_slots == p0.b_slots && p1.a_slots >= want_a) {
+        tp.tma_store = 1; tp.stage_bufs = bufs; stage_bytes = sb; p0 = p1;
+      }
+    }
   }
-  const int stage_bytes = tp.tma_store ? stage_full : 0;
   tp.b_resident = p0.resident; tp.a_slots = p0.a_slots; tp.b_slots = p0.b_slots;
   const size_t smem = (size_t)tp.a_slots * tp.a_slot_bytes + (size_t)tp.b_slots * b_bytes + stage_bytes + 1024;
 

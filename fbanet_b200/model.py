@@ -275,6 +275,8 @@ class BaseModel(nn.Module):
         # K2a: gate weights = sum over output channels of temporal_attn1 (temporal_attn0 and the biases
         # cancel in |aff_f - aff_0|; DESIGN.md "FAF gate identity").  Summed in fp64.
         P["fusion.wsum"] = fu.temporal_attn1.weight.detach().double().sum(0).permute(1, 2, 0).reshape(9, -1).float().contiguous()
+        if tc and self.embed_dim == 64:  # the same dot products as a 3x3 implicit GEMM on the tensor cores (hi/lo weight rows)
+            P["fusion.wscore"] = ops.faf_score_weight(P["fusion.wsum"], T)
         put_conv("fusion.fuse", fu.feature_fusion[0])
         P["fusion.fuse.alpha"] = f32(fu.feature_fusion[1].weight)
         put_conv("fusion.down0", fu.downsample0)
@@ -400,7 +402,8 @@ class BaseModel(nn.Module):
         B, Fr, H, W, E = feat.shape
         if self._use_tc():
             # gate kernel also emits the gated features pixel-major [B,H,W,F*E] = the K axis of the 1x1 fusion GEMM
-            gate, gated = ops.faf_gate(feat, P["fusion.wsum"], want_gate=True, want_gated=True)
+            score = ops.faf_scores(feat, P["fusion.wscore"]) if "fusion.wscore" in P else None
+            gate, gated = ops.faf_gate(feat, P["fusion.wsum"], want_gate=True, want_gated=True, score=score)
             z = ops.conv_gemm([gated], P["fusion.fuse.w"], self._new(B, H, W, E), bias=P["fusion.fuse.b"], act=L.ACT_PRELU,
                               alpha=P["fusion.fuse.alpha"], impl=self.impl)
         else:

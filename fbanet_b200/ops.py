@@ -142,6 +142,10 @@ def conv_gemm(
         assert base.stride(3) == 1 and base.stride(2) == Wo // 4 and base.stride(1) == (Ho // 4) * (Wo // 4)
         p.out, p.out_img_stride = out.data_ptr(), p.Cout_store * Ho * Wo
         p.base, p.base_img_stride = base.data_ptr(), (base.stride(0) if N > 1 else 0)
+    elif store_mode == L.STORE_NHWC_F32:
+        assert out.dtype == torch.float32 and out.shape == (N, Ho, Wo, p.Cout_store)
+        op, _, old, ois = _cl(out)
+        p.out, p.out_ld, p.out_img_stride = op, old, ois
     else:
         assert out.dtype == dt
         if store_mode == L.STORE_NHWC:
@@ -325,9 +329,11 @@ def leff_fc2(h1: torch.Tensor, dw_w9c: torch.Tensor, dw_b: torch.Tensor, w2: tor
     return out
 
 
-def faf_gate(feat: torch.Tensor, wsum: torch.Tensor, want_gate: bool = True, want_gated: bool = False):
+def faf_gate(feat: torch.Tensor, wsum: torch.Tensor, want_gate: bool = True, want_gated: bool = False,
+             score: Optional[torch.Tensor] = None):
     """feat ``[B,F,H,W,C]`` contiguous -> gate ``[B,F-1,H,W]`` fp32 and/or gated features
-    ``[B,H,W,F*C]`` (pixel-major; frame 0 copied, frames >= 1 scaled) for the tensor-core fusion GEMM."""
+    ``[B,H,W,F*C]`` (pixel-major; frame 0 copied, frames >= 1 scaled) for the tensor-core fusion GEMM.
+    ``score`` ``[B*F,H,W,2]`` fp32: the ``wsum`` dot products already computed by :func:`faf_scores`."""
     assert feat.is_cuda and feat.is_contiguous() and feat.dim() == 5
     B, Fr, H, W, Cc = feat.shape
     gate = torch.empty((B, Fr - 1, H, W), device=feat.device, dtype=torch.float32) if want_gate else None
@@ -337,10 +343,32 @@ def faf_gate(feat: torch.Tensor, wsum: torch.Tensor, want_gate: bool = True, wan
     p.gate = gate.data_ptr() if gate is not None else None
     p.gated = gated.data_ptr() if gated is not None else None
     p.B, p.F, p.H, p.W, p.C = B, Fr, H, W, Cc
+    if score is not None:
+        assert score.dtype == torch.float32 and score.is_contiguous() and score.shape == (B * Fr, H, W, 2)
+        p.score = score.data_ptr()
     _call("fbanet_faf_gate_sm100", p)
     if want_gate and want_gated:
         return gate, gated
     return gated if want_gated else gate
+
+
+def faf_score_weight(wsum: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Pack the summed FAF kernel ``wsum [9][C]`` (fp32) as the ``[16, 9*C]`` weight of a 3x3 implicit GEMM whose output
+    column 0 / 1 carry the hi / lo ``dtype`` halves of ``wsum`` (hi + lo keeps ~16 mantissa bits), rows 2..15 zero."""
+    w = wsum.reshape(-1).float()
+    hi = w.to(dtype)
+    lo = (w - hi.float()).to(dtype)
+    out = torch.zeros((16, w.numel()), device=wsum.device, dtype=dtype)
+    out[0], out[1] = hi, lo
+    return out.contiguous()
+
+
+def faf_scores(feat: torch.Tensor, score_weight: torch.Tensor) -> torch.Tensor:
+    """``wsum (*) feat`` for every frame on the tensor cores: feat ``[B,F,H,W,C]`` bf16 -> ``[B*F,H,W,2]`` fp32 (hi, lo parts)."""
+    B, Fr, H, W, Cc = feat.shape
+    out = torch.empty((B * Fr, H, W, 2), device=feat.device, dtype=torch.float32)
+    return conv_gemm([feat.view(B * Fr, H, W, Cc)], score_weight, out, kh=3, kw=3, pad=1, store_mode=L.STORE_NHWC_F32, cout_store=2,
+                     impl=L.IMPL_TCGEN05)
 
 
 def warp_burst(burst: torch.Tensor, M: torch.Tensor, layout: str = "BTCHW", return_coords: bool = False):

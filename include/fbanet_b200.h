@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 9
+#define FBANET_ABI_VERSION 10
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -47,7 +47,9 @@ enum {
   FBANET_STORE_NHWC = 0,     /* out(n,y,x,col)                                                     */
   FBANET_STORE_PS2 = 1,      /* PixelShuffle(2): col = 4c+2i+j -> out(n, 2y+i, 2x+j, c)            */
   FBANET_STORE_CONVT2 = 2,   /* ConvTranspose 2x2 s2: col = (2i+j)*Co + co -> out(n,2y+i,2x+j,co)  */
-  FBANET_STORE_NCHW_BASE = 3 /* fp32 planar out[n][col][y][x] + bilinear x4 of `base` (final conv) */
+  FBANET_STORE_NCHW_BASE = 3, /* fp32 planar out[n][col][y][x] + bilinear x4 of `base` (final conv) */
+  FBANET_STORE_NHWC_F32 = 4   /* fp32 out(n,y,x,col) for col < Cout_store, whatever the compute dtype (tensor-core path only):
+                                 narrow score maps that must not be rounded to bf16, e.g. the FAF affinity scores */
 };
 
 enum { FBANET_IMPL_AUTO = 0, FBANET_IMPL_SIMT = 1, FBANET_IMPL_TCGEN05 = 2 };
@@ -243,6 +245,9 @@ typedef struct fbanet_faf_gate_params {
   int32_t dtype;
   int32_t B, F, H, W, C;
   int32_t _pad;
+  const float* score;     /* optional [B][F][H][W][2] fp32: the 3x3xC dot products  wsum (*) feat  already computed (on the tensor
+                             cores, as hi + lo bf16 halves of wsum: score = s[0] + s[1]); the kernel then only forms the gates
+                             and streams the gated features.  NULL: the kernel computes them itself from `wsum`. */
 } fbanet_faf_gate_params;
 
 /* Full-size tiling (utils/dataset_utils.py:5-58,140-180): reflect-pad + overlapping tile gather,

@@ -166,6 +166,34 @@ def test_faf_gate_matches_reference_formula(cuda, dt):
     assert (gate.cpu().double() - ref).abs().max().item() < 2e-5
 
 
+def test_faf_gate_tensor_core_scores(cuda):
+    """bf16 path: the wsum dot products as a 3x3 implicit GEMM (hi/lo weight rows, fp32 NHWC_F32 store) feeding the streaming
+    gate-apply kernel == the as-written affinity maths in float64 (blocks/federated_affinity_fusion.py:79-105), and the
+    gated features == feat * gate in the pixel-major layout of the 1x1 fusion GEMM."""
+    from fbanet_b200 import ops
+    dt = torch.bfloat16
+    B, Fr, E, S = 2, 6, 64, 24
+    feat = _r(dt, B, Fr, E, S, S, seed=1)
+    w1 = _r(torch.float32, E, E, 3, 3, seed=4, scale=0.04)
+    fd64 = feat.double()
+    emb = F.conv2d(fd64.reshape(B * Fr, E, S, S), w1.double(), None, padding=1).view(B, Fr, E, S, S)
+    aff = emb.sum(2)
+    ref = torch.sigmoid((aff[:, 1:] - aff[:, :1]).abs())
+    wsum = w1.double().sum(0).permute(1, 2, 0).reshape(9, E).float().contiguous().to(cuda)
+    fd = feat.permute(0, 1, 3, 4, 2).contiguous().to(cuda, dt)
+    score = ops.faf_scores(fd, ops.faf_score_weight(wsum, dt))
+    s_ref = aff.reshape(B * Fr, S, S)
+    assert ((score[..., 0] + score[..., 1]).cpu().double() - s_ref).abs().max().item() < 2e-4 * max(1.0, s_ref.abs().max().item())
+    gate, gated = ops.faf_gate(fd, wsum, want_gate=True, want_gated=True, score=score)
+    assert (gate.cpu().double() - ref).abs().max().item() < 1e-4
+    g_all = torch.cat([torch.ones(B, 1, S, S, dtype=torch.float64), ref], 1)                      # frame 0 passes through
+    want = (fd64 * g_all[:, :, None]).permute(0, 3, 4, 1, 2).reshape(B, S, S, Fr * E)             # [B,H,W,F*C]
+    _close(gated, want.float(), dt)
+    # and the same gate as the CUDA-core kernel computes on its own
+    gate2 = ops.faf_gate(fd, wsum)
+    assert (gate2 - gate).abs().max().item() < 1e-4
+
+
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("C", [64, 128, 256])
 def test_layernorm(cuda, dt, C):
