@@ -124,6 +124,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-impl", default="auto", choices=["auto", "simt"])
     ap.add_argument("--breakdown", action="store_true", help="print a per-kernel CUDA-event breakdown of one step to stderr")
+    ap.add_argument("--host-chunk", type=int, default=0, help="bursts per pipelined chunk of the end-to-end (host buffer) call; 0 = model default")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -205,6 +206,8 @@ def main():
                 print(f"[breakdown] {t_ms:9.3f} ms {100 * t_ms / tot:5.1f}%  n={n:3d}  {k}", file=sys.stderr)
 
         # ---- end to end through the public API with HOST buffers (pinned H2D + D2H inside the timed region) ----
+        if args.host_chunk:
+            model.host_chunk = args.host_chunk
         for _ in range(2):
             model.infer_host(host_in, host_out)
         barrier()
@@ -250,7 +253,7 @@ def main():
                    "l2": f"inputs {host_in.numel() * 4 / 1e6:.0f} MB/step + GB-scale activations > 126 MB L2", "cuda_graph": graph is not None,
                    "weights": "random init (reference distributions), seed 0"},
         "e2e": {"value": e2e, "unit": "bursts/s", "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps, "host_chunk": model.host_chunk},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
     }

@@ -190,6 +190,10 @@ class BaseModel(nn.Module):
         self.gelu_act = {"tanh": L.ACT_GELU_TANH, "erf": L.ACT_GELU_ERF}[gelu]
         self.impl = impl
         self.fuse_leff = True
+        self.host_chunk = 32       # bursts per pipelined chunk of infer_host (int, or an explicit schedule of chunk sizes)
+        self._io_streams = None
+        self.host_graphs = True    # infer_host replays CUDA graphs (captured per chunk size) instead of launching eagerly
+        self._host_graphs = {}
         self.head = nn.Conv2d(in_channels, E, 3, 1, 1)
         self.body = nn.Sequential(_ResBlock(E), _ResBlock(E))
         self.fusion = _FAF(E, num_frames)
@@ -526,18 +530,95 @@ class BaseModel(nn.Module):
         """The reference's JAX signature: ``x [F,H,W,C] -> [4H,4W,C]`` (models/fba_net.py:242)."""
         return self.forward(x.permute(0, 3, 1, 2).unsqueeze(0)).squeeze(0).permute(1, 2, 0)
 
+    def _host_graph(self, n: int, slot: int):
+        """CUDA graph of one forward over ``n`` bursts with static input/output buffers (two slots per size, so consecutive
+        chunks of :meth:`infer_host` can be in flight); re-captured whenever the packed weights change."""
+        self.packed()
+        key = (n, slot)
+        ent = self._host_graphs.get(key)
+        if ent is not None and ent[3] is self._packed_sig:
+            return ent[:3]
+        dev = self.head.weight.device
+        x_static = torch.zeros((n, self.num_frames, self.in_channels, self.img_size, self.img_size), device=dev, dtype=torch.float32)
+        self.forward(x_static)                      # eager warm-up: weight packing, kernel attributes, allocator pools
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            y_static = self.forward(x_static)
+        self._host_graphs[key] = (g, x_static, y_static, self._packed_sig)
+        return g, x_static, y_static
+
     @torch.no_grad()
-    def infer_host(self, burst: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """End-to-end call with HOST buffers: pinned H2D copy, forward, D2H copy of the SR image."""
+    def infer_host(self, burst: torch.Tensor, out: Optional[torch.Tensor] = None, chunk=None) -> torch.Tensor:
+        """End-to-end call with HOST buffers: pinned H2D copy, forward, D2H copy of the SR image.
+
+        The batch is processed in chunks of ``chunk`` bursts (default ``self.host_chunk``) on three streams, so the H2D copy of
+        chunk i+1 and the D2H copy of chunk i-1 overlap the forward of chunk i; only the first upload and the last download
+        are exposed.  Each chunk's forward is a CUDA-graph replay over static device buffers (``self.host_graphs``; two
+        buffer sets alternate), captured on first use.  Returns after the last download has completed."""
         dev = self.head.weight.device
         if not burst.is_pinned():
             burst = burst.pin_memory()
-        xd = burst.to(dev, non_blocking=True)
-        y = self.forward(xd)
+        B = burst.shape[0]
         if out is None:
-            out = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
-        out.copy_(y, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+            out = torch.empty((B, self.in_channels, 4 * self.img_size, 4 * self.img_size), dtype=torch.float32, pin_memory=True)
+        chunk = chunk or self.host_chunk
+        if isinstance(chunk, int):
+            sizes = [max(1, min(B, chunk))] * ((B + max(1, min(B, chunk)) - 1) // max(1, min(B, chunk)))
+        else:   # explicit schedule, e.g. (8, 24, 24, 8): small first / last chunks shorten the exposed upload / download
+            sizes = [int(c) for c in chunk]
+        bounds, i0 = [], 0
+        for n in sizes:
+            if i0 >= B:
+                break
+            bounds.append((i0, min(B, i0 + n)))
+            i0 += n
+        if i0 < B:
+            bounds.append((i0, B))
+        comp = torch.cuda.current_stream(dev)
+        if self._io_streams is None or self._io_streams[0].device != dev:
+            self._io_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_in, s_out = self._io_streams
+        if self.host_graphs:   # capture (first use of a chunk size) happens before any copy is queued
+            for k, (a, b) in enumerate(bounds):
+                self._host_graph(b - a, k & 1)
+        s_in.wait_stream(comp)   # the caller's stream may still be producing / consuming these buffers
+        s_out.wait_stream(comp)
+        ev_comp = [None, None]   # forward that last read slot's input buffer
+        ev_out = [None, None]    # download that last read slot's output buffer
+        for k, (i0, i1) in enumerate(bounds):
+            slot = k & 1
+            if self.host_graphs:
+                g, xs, ys = self._host_graph(i1 - i0, slot)
+                with torch.cuda.stream(s_in):
+                    if ev_comp[slot] is not None:
+                        s_in.wait_event(ev_comp[slot])
+                    xs.copy_(burst[i0:i1], non_blocking=True)
+                    ev_in = torch.cuda.Event()
+                    ev_in.record(s_in)
+                comp.wait_event(ev_in)
+                if ev_out[slot] is not None:
+                    comp.wait_event(ev_out[slot])
+                g.replay()
+                y = ys
+            else:
+                with torch.cuda.stream(s_in):
+                    xd = burst[i0:i1].to(dev, non_blocking=True)
+                    ev_in = torch.cuda.Event()
+                    ev_in.record(s_in)
+                comp.wait_event(ev_in)
+                xd.record_stream(comp)
+                y = self.forward(xd)
+                y.record_stream(s_out)
+            ev_comp[slot] = torch.cuda.Event()
+            ev_comp[slot].record(comp)
+            s_out.wait_event(ev_comp[slot])
+            with torch.cuda.stream(s_out):
+                out[i0:i1].copy_(y, non_blocking=True)
+                ev_out[slot] = torch.cuda.Event()
+                ev_out[slot].record(s_out)
+        comp.wait_stream(s_out)
+        comp.synchronize()
         return out
 
     # -- checkpoint compatibility (utils/model_utils.py:28-48) ----------------------------------------

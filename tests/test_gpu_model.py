@@ -118,6 +118,10 @@ def test_batch_invariance_and_host_api(cuda):
         assert torch.equal(one, full[i:i + 1])
     host = m.infer_host(x)
     assert torch.equal(host, full)
+    # chunked, three-stream pipeline (H2D / forward / D2H overlapped): any chunk size gives the same image, repeatedly
+    for chunk in (1, 2, 3):
+        for _ in range(2):
+            assert torch.equal(m.infer_host(x, chunk=chunk), full)
 
 
 def test_fhwc_adaptor(cuda):
