@@ -2,6 +2,8 @@
 // LeFF depthwise 3x3 + GELU (K7), FAF gate (K2a), full-size tile divide/merge (8f-1).
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fbanet {
@@ -711,6 +713,11 @@ static int grid_for(int64_t total, int block) {
 
 }  // namespace fbanet
 
+namespace fbanet {
+int head_conv_tc_supported(const fbanet_head_conv_params* p);
+int head_conv_tc_launch(const fbanet_head_conv_params* p, cudaStream_t stream);
+}  // namespace fbanet
+
 using namespace fbanet;
 
 extern "C" int fbanet_warp_sm100(const fbanet_warp_params* p, void* stream) {
@@ -747,7 +754,11 @@ extern "C" int fbanet_head_conv_sm100(const fbanet_head_conv_params* p, void* st
   if (!p || !p->src || !p->dst || !p->weight || !p->bias || p->frames <= 0 || p->Cout != 64) return FBANET_E_BADSHAPE;
   if ((uintptr_t)p->dst % 16) return FBANET_E_ALIGN;
   if (p->dtype == FBANET_F32) return launch_head<float>(p, (cudaStream_t)stream);
-  if (p->dtype == FBANET_BF16) return launch_head<bf16>(p, (cudaStream_t)stream);
+  if (p->dtype == FBANET_BF16) {
+    static const char* no_tc = getenv("FBANET_HEAD_TC");   // experiment switch: 0 = CUDA-core head conv
+    if (!(no_tc && no_tc[0] == '0') && head_conv_tc_supported(p)) return head_conv_tc_launch(p, (cudaStream_t)stream);
+    return launch_head<bf16>(p, (cudaStream_t)stream);
+  }
   return FBANET_E_DTYPE;
 }
 

@@ -385,6 +385,21 @@ def test_head_conv_direct(cuda, dt, cin, hw):
     _close(out.permute(0, 3, 1, 2), ref, dt)
 
 
+@pytest.mark.parametrize("cin,hw,frames", [(3, (32, 24), 5), (4, (20, 44), 3), (3, (160, 160), 14)])
+def test_head_conv_tensor_core_keeps_fp32_samples(cuda, cin, hw, frames):
+    """bf16 head conv on tcgen05: samples enter as hi + lo bf16 halves, so only the weights are rounded to bf16 -- the
+    result must match the fp32 conv with bf16-rounded weights to bf16 output rounding, including ragged tiles."""
+    from fbanet_b200 import ops
+    H, W = hw
+    x = torch.rand(frames, cin, H, W, generator=torch.Generator().manual_seed(1))
+    w, b = _r(torch.float32, 64, cin, 3, 3, seed=2, scale=0.2), _r(torch.float32, 64, seed=3)
+    ref = F.conv2d(x.double(), w.bfloat16().double(), b.double(), padding=1).float()
+    wkc = w.permute(2, 3, 1, 0).reshape(9 * cin, 64).contiguous()
+    out = ops.head_conv(x.to(cuda), wkc.to(cuda), b.to(cuda), torch.bfloat16).float().cpu().permute(0, 3, 1, 2)
+    err = (out - ref).abs()
+    assert (err <= 2.0 ** -8 * ref.abs() + 1e-4).all(), err.max().item()   # bf16 rounding of the output only
+
+
 @pytest.mark.parametrize("dt", DTYPES)
 def test_assemble_sr_plus_bilinear_base(cuda, dt):
     """models/fba_net.py:317-320: channels-last SR + bilinear x4 (align_corners=False) of frame 0 -> planar fp32."""
