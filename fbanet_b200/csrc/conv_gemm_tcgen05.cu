@@ -29,6 +29,13 @@ constexpr int TC_MAX_CHUNKS = 32;
 constexpr int TC_HALO_TW = 8, TC_HALO_TH = 16;                       // 3x3 halo mode tile: 8 wide x 16 tall
 constexpr int TC_HALO_COPY = (TC_HALO_TH + 2) * TC_HALO_TW * 128;    // one dx-shifted copy: 18 rows x 1 KB
 constexpr int TC_HALO_SLOT = 3 * TC_HALO_COPY;                       // 54 KB per 64-channel chunk
+// wide-box halo mode (p.halo >= 2): ONE box {64 ch, 16 px, 18 rows} at x0-4 per chunk.  An image row of the box is 2 KB = two
+// swizzle atoms, so tap (ky,kx) is the same buffer read from byte offset ky*2048 + (3+kx)*128 with a 2 KB stride between the
+// 8-row atoms.  TMA and tcgen05.mma both derive the 128B-swizzle XOR from shared-memory ADDRESS bits [7:9], so a start
+// address that is only 128-byte aligned needs nothing else (descriptor base offset 0; mode 2, which sets it to the row
+// phase, is kept only as the experiment that proved it wrong).  36 KB instead of 54 KB per chunk through TMA / L2.
+constexpr int TC_HALO_WROW = 16 * 128;
+constexpr int TC_HALO_WSLOT = (TC_HALO_TH + 2) * TC_HALO_WROW;
 
 // generic mode: one A box + one B slab per K-step
 struct KStep { int16_t src, c0, dx, dy; };
@@ -169,16 +176,23 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
 
 // Issue the MMAs of one A slot (TAPS K-steps x 4 tcgen05.mma), fully unrolled so that descriptor offsets are
 // immediates.  Called by the elected lane only.  HALO: tap t reads copy (t%3), ky = t/3 rows down.
-template <int TAPS, bool HALO>
-__device__ __forceinline__ void issue_unit_resident(const uint32_t tmem_d, const uint32_t idesc, const uint64_t desc_hi, const uint32_t a_lo,
-                                                    uint32_t b_lo, const uint32_t b_step_lo, const bool first_unit) {
+// HALO: 0 = plain A tile, 1 = three dx-shifted copies, 2 = wide box + base offset, 3 = wide box, base offset 0
+template <int TAPS, int HALO>
+__device__ __forceinline__ void issue_unit_resident(const uint32_t tmem_d, const uint32_t idesc, const uint64_t desc_hi, const uint64_t desc_wide,
+                                                    const uint32_t a_lo, uint32_t b_lo, const uint32_t b_step_lo, const bool first_unit) {
 #pragma unroll
   for (int t = 0; t < TAPS; ++t) {
-    const uint32_t at = a_lo + (HALO ? (uint32_t)(((t % 3) * TC_HALO_COPY + (t / 3) * 1024) >> 4) : 0u);
+    uint32_t at = a_lo;
+    uint64_t dA = desc_hi;
+    if (HALO == 1) at += (uint32_t)(((t % 3) * TC_HALO_COPY + (t / 3) * 1024) >> 4);
+    if (HALO >= 2) {
+      at += (uint32_t)(((t / 3) * TC_HALO_WROW + (3 + t % 3) * 128) >> 4);
+      dA = desc_wide + (HALO == 2 ? ((uint64_t)((3 + t % 3) & 7) << 49) : 0ull);
+    }
 #pragma unroll
     for (int k = 0; k < TC_BK / 16; ++k) {
       const uint32_t accum = (t == 0 && k == 0) ? (first_unit ? 0u : 1u) : 1u;
-      umma_bf16(tmem_d, desc_hi + (uint64_t)(at + 2 * k), desc_hi + (uint64_t)(b_lo + 2 * k), idesc, accum);
+      umma_bf16(tmem_d, dA + (uint64_t)(at + 2 * k), desc_hi + (uint64_t)(b_lo + 2 * k), idesc, accum);
     }
     b_lo += b_step_lo;
   }
@@ -251,9 +265,14 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
           uint8_t* sa = smem_a + (size_t)slot * p.a_slot_bytes;
           if (p.halo) {
             const Chunk ch = p.chunks[u];
-            mbar_expect_tx(&a_full[slot], 3u * (uint32_t)TC_HALO_COPY);
+            if (p.halo == 1) {
+              mbar_expect_tx(&a_full[slot], 3u * (uint32_t)TC_HALO_COPY);
 #pragma unroll
-            for (int d = 0; d < 3; ++d) tma_load_4d(sa + d * TC_HALO_COPY, &p.amap[ch.src], &a_full[slot], ch.c0, x0 + d - 1, y0 - 1, img);
+              for (int d = 0; d < 3; ++d) tma_load_4d(sa + d * TC_HALO_COPY, &p.amap[ch.src], &a_full[slot], ch.c0, x0 + d - 1, y0 - 1, img);
+            } else {
+              mbar_expect_tx(&a_full[slot], (uint32_t)TC_HALO_WSLOT);
+              tma_load_4d(sa, &p.amap[ch.src], &a_full[slot], ch.c0, x0 - 4, y0 - 1, img);
+            }
           } else {
             const KStep ks = p.steps[u];
             mbar_expect_tx(&a_full[slot], (uint32_t)p.a_box_bytes);
@@ -300,6 +319,7 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
     // power of two), so everything inside the elected block stays in uniform registers.
     const uint32_t idesc = make_idesc_bf16(BN);
     const uint64_t desc_hi = make_sw128_desc(0);       // descriptor with a zero start address
+    const uint64_t desc_wide = (desc_hi & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)(TC_HALO_WROW >> 4) << 32);   // 2 KB between 8-row atoms
     const uint32_t sa0 = smem_u32(smem_a), sb0 = smem_u32(smem_b);
     const uint32_t bmask = (uint32_t)p.b_slots - 1, bshift = (uint32_t)__ffs(p.b_slots) - 1;
     int aslot = 0;
@@ -321,8 +341,10 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
           // resident weights: straight-line issue with immediate descriptor offsets
           if (elect_one()) {
             const uint32_t b_lo = (sb0 + (uint32_t)(u * taps) * b_bytes) >> 4;
-            if (p.halo) issue_unit_resident<9, true>(tmem_d, idesc, desc_hi, sa >> 4, b_lo, b_bytes >> 4, u == 0);
-            else issue_unit_resident<1, false>(tmem_d, idesc, desc_hi, sa >> 4, b_lo, b_bytes >> 4, u == 0);
+            if (p.halo == 1) issue_unit_resident<9, 1>(tmem_d, idesc, desc_hi, desc_wide, sa >> 4, b_lo, b_bytes >> 4, u == 0);
+            else if (p.halo == 2) issue_unit_resident<9, 2>(tmem_d, idesc, desc_hi, desc_wide, sa >> 4, b_lo, b_bytes >> 4, u == 0);
+            else if (p.halo == 3) issue_unit_resident<9, 3>(tmem_d, idesc, desc_hi, desc_wide, sa >> 4, b_lo, b_bytes >> 4, u == 0);
+            else issue_unit_resident<1, 0>(tmem_d, idesc, desc_hi, desc_wide, sa >> 4, b_lo, b_bytes >> 4, u == 0);
             umma_commit(&a_empty[aslot]);
             if (u == units - 1) umma_commit(&tmem_full[acc]);
           }
@@ -339,8 +361,14 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
               sb = sb0 + slot * b_bytes;
             }
             // halo mode: tap (ky,kx) reads the dx-shifted copy kx, starting ky rows (1 KB each) down
-            const uint32_t a_addr = p.halo ? sa + (uint32_t)((t % 3) * TC_HALO_COPY + (t / 3) * 1024) : sa;
-            const uint64_t adesc = desc_hi + (uint64_t)(a_addr >> 4), bdesc = desc_hi + (uint64_t)(sb >> 4);
+            uint32_t a_addr = sa;
+            uint64_t dA = desc_hi;
+            if (p.halo == 1) a_addr += (uint32_t)((t % 3) * TC_HALO_COPY + (t / 3) * 1024);
+            else if (p.halo >= 2) {
+              a_addr += (uint32_t)((t / 3) * TC_HALO_WROW + (3 + t % 3) * 128);
+              dA = desc_wide + (p.halo == 2 ? ((uint64_t)((3 + t % 3) & 7) << 49) : 0ull);
+            }
+            const uint64_t adesc = dA + (uint64_t)(a_addr >> 4), bdesc = desc_hi + (uint64_t)(sb >> 4);
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k)       // advance 32 bytes (16 bf16) inside the swizzle row
               umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((s | k) != 0));
@@ -519,8 +547,17 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int pick_bn(int cout, bool halo) {
-  const int cap = halo ? 128 : 256;   // halo mode keeps B slabs at <= 16 KB so two 54 KB A slots fit beside the ring
+static int conv_ctot(const fbanet_conv_params* p) {
+  int c = 0;
+  for (int s = 0; s < p->nsrc; ++s) c += p->src_s2d ? p->src[s].C / 4 : p->src[s].C;
+  return c;
+}
+
+// N tile.  3x3 halo convs with a deep K (>= 128 input channels) take full 256-column tiles: the A halo is then fetched once
+// per pixel tile instead of once per 128 output channels and the MMAs run at N = 256 (0.84 -> 0.66 ms on 512->256 @80x80,
+// 1475 TFLOP/s); with a shallow K (the 64->256 tail convs) the longer epilogue per tile is not hidden and 128 stays better.
+static int pick_bn(int cout, bool halo, int ctot) {
+  const int cap = (halo && ctot < 128) ? 128 : 256;
   if (cout <= cap) return cout;
   for (int bn = cap; bn >= 64; bn -= 64)
     if (cout % bn == 0) return bn;
@@ -564,7 +601,7 @@ static bool tc_shape_ok(const fbanet_conv_params* p) {
   const int taps = p->KH * p->KW;
   if (taps * (ctot / TC_BK) > TC_MAX_STEPS) return false;
   if (is_halo(p) && ctot / TC_BK > TC_MAX_CHUNKS) return false;
-  const int bn = pick_bn(p->Cout, is_halo(p));
+  const int bn = pick_bn(p->Cout, is_halo(p), conv_ctot(p));
   if (bn != 16 && bn != 64 && bn != 128 && bn != 192 && bn != 256) return false;
   if ((uintptr_t)p->weight % 16) return false;
   if (p->store_mode == FBANET_STORE_NHWC || p->store_mode == FBANET_STORE_CONVT2) {
@@ -600,18 +637,24 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   tp.tiles_y = (p->Ho + th - 1) / th;
   tp.m_tiles = p->N * tp.tiles_x * tp.tiles_y;
   tp.N = p->N; tp.Ho = p->Ho; tp.Wo = p->Wo;
-  tp.BN = pick_bn(p->Cout, halo);
+  tp.BN = pick_bn(p->Cout, halo, conv_ctot(p));
   tp.n_tiles_n = p->Cout / tp.BN;
   tp.Cout = p->Cout; tp.Cout_store = p->Cout_store;
   tp.a_box_bytes = tw * th * TC_BK * 2;
-  tp.halo = halo ? 1 : 0;
+  // Measured (profiles/r1_notes.md): the wide box wins 4-16 % for N tiles of 128 and for N = 16, where TMA / L2 traffic
+  // bounds the tile, and loses 7 % at N = 64, where the MMA's fetch of A rows that straddle 1 KB boundaries shows instead.
+  // The hardware swizzle is purely address based: base-offset 0 (mode 3) is the correct descriptor, mode 2 computes garbage.
+  static const char* henv = getenv("FBANET_TC_HALO");   // experiment switch: 1 = three dx-shifted copies, 3 = one wide box
+  const int halo_mode = halo ? (henv ? atoi(henv) : (tp.BN == 64 ? 1 : 3)) : 0;
+  if (halo && (halo_mode < 1 || halo_mode > 3)) return FBANET_E_UNSUPPORTED;
+  tp.halo = halo_mode;
 
   int ctot = 0;
   for (int s = 0; s < p->nsrc; ++s) {
     const fbanet_src& S = p->src[s];
     const cuuint64_t dims[4] = {(cuuint64_t)S.C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)p->N};
     const cuuint64_t strides[3] = {(cuuint64_t)S.ld * 2, (cuuint64_t)S.ld * 2 * Ws, (cuuint64_t)S.img_stride * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)tw, (cuuint32_t)(halo ? th + 2 : th), 1};
+    const cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(halo_mode >= 2 ? 16 : tw), (cuuint32_t)(halo ? th + 2 : th), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&tp.amap[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(S.ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -715,9 +758,9 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   }
   // shared-memory plan: A ring + B ring (or all B slabs resident when they fit) + the epilogue staging sub-tiles.
   // The staged TMA-store epilogue is kept only where its 64 KB do not cost the mainloop anything (same weight residency,
-  // same B ring, >= 4 A slots): the 3x3 halo convs and the K = 896 fusion GEMM need that memory for operands.
+  // same B ring, >= 3 A slots): the 3x3 halo convs and the K = 896 fusion GEMM need that memory for operands.
   const int b_bytes = tp.BN * TC_BK * 2;
-  tp.a_slot_bytes = halo ? TC_HALO_SLOT : TC_A_BYTES;
+  tp.a_slot_bytes = halo ? (halo_mode >= 2 ? TC_HALO_WSLOT : TC_HALO_SLOT) : TC_A_BYTES;
   const int a_min = halo ? 2 : 3;
   const int units = halo ? tp.nchunks : ns;
   struct Plan { int resident, a_slots, b_slots; };
@@ -741,7 +784,7 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   if (!plan(216 * 1024, &p0)) return FBANET_E_UNSUPPORTED;
   int stage_bytes = 0;
   if (tp.tma_store) {
-    const int want_a = p0.a_slots < 4 ? p0.a_slots : 4;
+    const int want_a = p0.a_slots < 3 ? p0.a_slots : 3;
     tp.tma_store = 0;
     for (int bufs = 2; bufs >= 1 && !tp.tma_store; --bufs) {
       const int sb = 8 * bufs * 4096;
