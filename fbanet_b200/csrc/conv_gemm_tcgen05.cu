@@ -777,7 +777,8 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
       if (b < 2) return false;
       pl->b_slots = b >= 8 ? 8 : (b >= 4 ? 4 : 2);   // power of two: ring slot = step & (slots-1)
     }
-    if (pl->a_slots > units * 2 && units * 2 >= 2) pl->a_slots = units * 2;
+    static const char* ecap = getenv("FBANET_TC_ACAP");   // experiment: 1 = old cap of two tiles of prefetch
+    if (ecap && ecap[0] == '1' && pl->a_slots > units * 2 && units * 2 >= 2) pl->a_slots = units * 2;
     return true;
   };
   Plan p0, p1;
