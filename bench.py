@@ -198,12 +198,20 @@ def main():
         # ---- dominant-kernel roofline: CUDA events around every conv/GEMM launch of one more eager pass ----
         prof = ops.profile_conv_gemm(lambda: model(x), stream)
 
+        # ---- per-kernel CUDA-event pass: the bandwidth-bound kernels against the HBM roofline (algorithmic bytes / time) ----
+        fam = ops.profile_ops(lambda: model(x), stream, by_tag=False)
+        # K1 homography warp: not part of the cfg2 step (its bursts are pre-aligned), measured on the same burst shape
+        Mh = torch.eye(3, dtype=torch.float64).repeat(B, CFG["num_frames"], 1, 1)
+        Mh[:, 1:, :2, 2] = torch.rand(B, CFG["num_frames"] - 1, 2, generator=torch.Generator().manual_seed(1), dtype=torch.float64) * 8 - 4
+        Mh = Mh.to(dev)
+        ops.warp_burst(x, Mh)
+        fam.update(ops.profile_ops(lambda: [ops.warp_burst(x, Mh) for _ in range(3)], stream, by_tag=False))
         if args.breakdown and rank == 0:
             bd = ops.profile_ops(lambda: model(x), stream)
             tot = sum(v[0] for v in bd.values())
             print(f"[breakdown] one step, eager, CUDA events: {tot:.2f} ms", file=sys.stderr)
-            for k, (t_ms, n) in sorted(bd.items(), key=lambda kv: -kv[1][0]):
-                print(f"[breakdown] {t_ms:9.3f} ms {100 * t_ms / tot:5.1f}%  n={n:3d}  {k}", file=sys.stderr)
+            for k, (t_ms, n, by) in sorted(bd.items(), key=lambda kv: -kv[1][0]):
+                print(f"[breakdown] {t_ms:9.3f} ms {100 * t_ms / tot:5.1f}%  n={n:3d}  {by / t_ms / 1e9 if t_ms else 0:6.2f} TB/s alg  {k}", file=sys.stderr)
 
         # ---- end to end through the public API with HOST buffers (pinned H2D + D2H inside the timed region) ----
         if args.host_chunk:
@@ -234,11 +242,32 @@ def main():
     value = total_bursts / (ms / 1e3)
     e2e = total_bursts / (ms_e2e / 1e3)
     peak_tf = pk["bf16_tflops_sustained"]
+    # DRAM traffic of the dominant kernel family from the committed ncu launch list of this same command
+    # (profiles/*_kernel_summary_*.json, tools/launch_summary.py): bytes per launch, like `achieved`
+    traffic, traffic_src = None, None
+    summ = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if "kernel_summary" in f and f.endswith(".json")) if os.path.isdir(os.path.join(ROOT, "profiles")) else []
+    if summ:
+        sj = json.load(open(os.path.join(ROOT, "profiles", summ[-1])))
+        cf = sj.get("families", {}).get("conv_gemm_tcgen05_kernel")
+        if cf and cf.get("launches"):
+            traffic = cf["dram_bytes"] / cf["launches"]
+            traffic_src = f"profiles/{summ[-1]} (ncu dram__bytes_read+write, {cf['launches']} launches of one batch-{sj.get('batch', 64)} step)"
     roof = {
         "bound": "tensor", "kernel": prof["kernel"], "achieved": prof["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": prof["tflops"] / peak_tf, "traffic": None, "peak_source": pk_src + ", sustained bf16 (kernel timed inside a long step)",
+        "frac": prof["tflops"] / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
+        "algorithmic_bytes_per_launch": (fam.get("fbanet_conv_gemm_sm100", (0, 1, 0))[2] / max(1, fam.get("fbanet_conv_gemm_sm100", (0, 1, 0))[1])),
+        "peak_source": pk_src + ", sustained bf16 (kernel timed inside a long step)",
         "launches": prof["launches"], "share_of_step": prof["ms"] / (ms / args.steps), "flops_per_step": prof["flops"],
     }
+    hbm_peak = pk["hbm_gbs"]
+    hbm_kernels = []
+    for name in ("fbanet_warp_sm100", "fbanet_faf_gate_sm100", "fbanet_head_conv_sm100", "fbanet_layernorm_sm100", "fbanet_assemble_sm100",
+                 "fbanet_window_attention_sm100", "fbanet_leff_fc2_sm100"):
+        if name in fam and fam[name][0] > 0:
+            t_ms, n, by = fam[name]
+            gbs = by / t_ms / 1e6
+            hbm_kernels.append({"kernel": name, "bound": "hbm", "launches": n, "ms": t_ms, "algorithmic_bytes": by, "achieved": gbs, "peak": hbm_peak,
+                                "unit": "GB/s", "frac": gbs / hbm_peak})
     cpu = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -255,7 +284,7 @@ def main():
         "e2e": {"value": e2e, "unit": "bursts/s", "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
                 "ms_per_step": ms_e2e / args.steps, "host_chunk": model.host_chunk},
         "gpu_launches": launches_per_step * args.steps,
-        "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+        "roofline": roof, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu, "clocks": clocks,
     }
     print(json.dumps(line))
     if world > 1:

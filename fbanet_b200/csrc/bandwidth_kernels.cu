@@ -12,38 +12,71 @@ namespace fbanet {
 // K1  homography warp, bilinear, BORDER_CONSTANT 0, dst->src matrix (cv2 WARP_INVERSE_MAP).
 // One thread per destination pixel; coordinates in fp64 (fp32 cannot hold 1e-5 px at x~1920).
 // ------------------------------------------------------------------------------------------------
+// CT = compile-time channel count (0: runtime loop).  One fp64 reciprocal per pixel instead of two divisions; the 4*C taps
+// are fetched before any arithmetic on them so every thread keeps them all in flight.
+template <int CT>
 __global__ void __launch_bounds__(256) warp_kernel(const fbanet_warp_params p) {
   const int64_t total = (int64_t)p.frames * p.H * p.W;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int x = (int)(idx % p.W);
-    const int y = (int)((idx / p.W) % p.H);
-    const int f = (int)(idx / ((int64_t)p.W * p.H));
-    const float* s = p.src + (int64_t)f * p.s_frame;
-    float* d = p.dst + (int64_t)f * p.d_frame + (int64_t)y * p.d_y + (int64_t)x * p.d_x;
-    if (f % p.frames_per_burst == 0) {  // base frame: identity (homography_alignment.py:168,179)
-      const float* s0 = s + (int64_t)y * p.s_y + (int64_t)x * p.s_x;
-      for (int c = 0; c < p.C; ++c) d[(int64_t)c * p.d_c] = s0[(int64_t)c * p.s_c];
-      if (p.coords) { double* co = p.coords + idx * 2; co[0] = x; co[1] = y; }
-      continue;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int C = CT ? CT : p.C;
+  const int x = (int)(idx % p.W);
+  const int y = (int)((idx / p.W) % p.H);
+  const int f = (int)(idx / ((int64_t)p.W * p.H));
+  const float* s = p.src + (int64_t)f * p.s_frame;
+  float* d = p.dst + (int64_t)f * p.d_frame + (int64_t)y * p.d_y + (int64_t)x * p.d_x;
+  if (f % p.frames_per_burst == 0) {  // base frame: identity (homography_alignment.py:168,179)
+    const float* s0 = s + (int64_t)y * p.s_y + (int64_t)x * p.s_x;
+#pragma unroll
+    for (int c = 0; c < C; ++c) d[(int64_t)c * p.d_c] = __ldg(s0 + (int64_t)c * p.s_c);
+    if (p.coords) { double* co = p.coords + idx * 2; co[0] = x; co[1] = y; }
+    return;
+  }
+  const double* M = p.M + (int64_t)f * 9;
+  const double X = x, Y = y;
+  const double u = fma(__ldg(M + 0), X, fma(__ldg(M + 1), Y, __ldg(M + 2)));
+  const double v = fma(__ldg(M + 3), X, fma(__ldg(M + 4), Y, __ldg(M + 5)));
+  const double w = fma(__ldg(M + 6), X, fma(__ldg(M + 7), Y, __ldg(M + 8)));
+  double sx, sy;
+  if (p.coords) {   // parity / test path: the two correctly rounded quotients
+    sx = u / w; sy = v / w;
+    double* co = p.coords + idx * 2; co[0] = sx; co[1] = sy;
+  } else {          // one reciprocal (0.5 ulp) and two products: relative error < 2^-51, i.e. < 1e-12 px
+    const double iw = 1.0 / w;
+    sx = u * iw; sy = v * iw;
+  }
+  const double fx = floor(sx), fy = floor(sy);
+  const float ax = (float)(sx - fx), ay = (float)(sy - fy);
+  // clamp before the int conversion so wild homographies cannot overflow
+  const int x0 = (int)fmin(fmax(fx, -2.0), (double)p.W + 1.0);
+  const int y0 = (int)fmin(fmax(fy, -2.0), (double)p.H + 1.0);
+  const bool okx0 = x0 >= 0 && x0 < p.W, okx1 = x0 + 1 >= 0 && x0 + 1 < p.W;
+  const bool oky0 = y0 >= 0 && y0 < p.H, oky1 = y0 + 1 >= 0 && y0 + 1 < p.H;
+  const float w00 = (1.f - ay) * (1.f - ax), w01 = (1.f - ay) * ax, w10 = ay * (1.f - ax), w11 = ay * ax;
+  const float* r0 = s + (int64_t)y0 * p.s_y + (int64_t)x0 * p.s_x;
+  const float* r1 = r0 + p.s_y;
+  if (CT) {
+    float t[CT ? CT : 1][4];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      const int64_t oc = (int64_t)c * p.s_c;
+      t[c][0] = (oky0 && okx0) ? __ldg(r0 + oc) : 0.f;
+      t[c][1] = (oky0 && okx1) ? __ldg(r0 + p.s_x + oc) : 0.f;
+      t[c][2] = (oky1 && okx0) ? __ldg(r1 + oc) : 0.f;
+      t[c][3] = (oky1 && okx1) ? __ldg(r1 + p.s_x + oc) : 0.f;
     }
-    const double* M = p.M + (int64_t)f * 9;
-    const double X = x, Y = y;
-    const double u = fma(M[0], X, fma(M[1], Y, M[2]));
-    const double v = fma(M[3], X, fma(M[4], Y, M[5]));
-    const double w = fma(M[6], X, fma(M[7], Y, M[8]));
-    const double sx = u / w, sy = v / w;
-    if (p.coords) { double* co = p.coords + idx * 2; co[0] = sx; co[1] = sy; }
-    const double fx = floor(sx), fy = floor(sy);
-    const float ax = (float)(sx - fx), ay = (float)(sy - fy);
-    // clamp before the int conversion so wild homographies cannot overflow
-    const int x0 = (int)fmin(fmax(fx, -2.0), (double)p.W + 1.0);
-    const int y0 = (int)fmin(fmax(fy, -2.0), (double)p.H + 1.0);
-    const bool okx0 = x0 >= 0 && x0 < p.W, okx1 = x0 + 1 >= 0 && x0 + 1 < p.W;
-    const bool oky0 = y0 >= 0 && y0 < p.H, oky1 = y0 + 1 >= 0 && y0 + 1 < p.H;
-    const float w00 = (1.f - ay) * (1.f - ax), w01 = (1.f - ay) * ax, w10 = ay * (1.f - ax), w11 = ay * ax;
-    const float* r0 = s + (int64_t)y0 * p.s_y + (int64_t)x0 * p.s_x;
-    const float* r1 = r0 + p.s_y;
-    for (int c = 0; c < p.C; ++c) {
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      // same summation order as the runtime-C loop below (bit-identical results)
+      float acc = 0.f;
+      if (oky0 && okx0) acc += w00 * t[c][0];
+      if (oky0 && okx1) acc += w01 * t[c][1];
+      if (oky1 && okx0) acc += w10 * t[c][2];
+      if (oky1 && okx1) acc += w11 * t[c][3];
+      d[(int64_t)c * p.d_c] = acc;
+    }
+  } else {
+    for (int c = 0; c < C; ++c) {
       const int64_t oc = (int64_t)c * p.s_c;
       float acc = 0.f;
       if (oky0 && okx0) acc += w00 * __ldg(r0 + oc);
@@ -724,7 +757,10 @@ extern "C" int fbanet_warp_sm100(const fbanet_warp_params* p, void* stream) {
   if (!p || !p->src || !p->dst || !p->M || p->frames <= 0 || p->frames_per_burst <= 0 || p->H <= 0 || p->W <= 0 || p->C <= 0)
     return FBANET_E_BADSHAPE;
   const int64_t total = (int64_t)p->frames * p->H * p->W;
-  warp_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  const int blocks = ceil_div(total, 256);
+  if (p->C == 3) warp_kernel<3><<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+  else if (p->C == 4) warp_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+  else warp_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
   return check_launch();
 }
 

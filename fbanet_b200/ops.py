@@ -31,7 +31,9 @@ def _stream() -> int:
 _OPPROF = None
 
 
-def _call(name, p, tag=""):
+def _call(name, p, tag="", nbytes=0):
+    """Launch one C-ABI op on the current stream.  ``nbytes``: ALGORITHMIC HBM bytes of the launch (tensors that must be read
+    once + written once), used by the roofline accounting of ``profile_ops``."""
     global LAUNCHES
     LAUNCHES += 1
     if _OPPROF is not None:
@@ -39,23 +41,23 @@ def _call(name, p, tag=""):
         e0.record()
         L.call(name, p, _stream())
         e1.record()
-        _OPPROF.append((name, e0, e1, tag))
+        _OPPROF.append((name, e0, e1, tag, nbytes))
         return
     L.call(name, p, _stream())
 
 
-def profile_ops(fn, stream) -> dict:
-    """Run ``fn`` once with CUDA events around every kernel launch; {op name: (total ms, launches)}."""
+def profile_ops(fn, stream, by_tag: bool = True) -> dict:
+    """Run ``fn`` once with CUDA events around every kernel launch; {op name[:tag]: (total ms, launches, algorithmic bytes)}."""
     global _OPPROF
     _OPPROF = []
     try:
         fn()
         stream.synchronize()
         out = {}
-        for name, a, b, tag in _OPPROF:
-            k = name + (":" + tag if tag else "")
-            ms, n = out.get(k, (0.0, 0))
-            out[k] = (ms + a.elapsed_time(b), n + 1)
+        for name, a, b, tag, nbytes in _OPPROF:
+            k = name + (":" + tag if (tag and by_tag) else "")
+            ms, n, by = out.get(k, (0.0, 0, 0))
+            out[k] = (ms + a.elapsed_time(b), n + 1, by + nbytes)
     finally:
         _OPPROF = None
     return out
@@ -164,7 +166,9 @@ def conv_gemm(
         flops = 2.0 * N * Ho * Wo * kh * kw * (ctot if alg_cin is None else alg_cin) * p.Cout_store
         _PROFILE.append((e0, e1, flops))
         return out
-    _call("fbanet_conv_gemm_sm100", p, tag=f"k{kh}s{stride} {ctot}->{cout} @{Ho}x{Wo} act{act}{' res' if residual is not None else ''} st{store_mode}")
+    esz = srcs[0].element_size()
+    nbytes = N * H * W * ctot * esz + out.numel() * out.element_size() + (residual.numel() * esz if residual is not None else 0) + weight.numel() * esz
+    _call("fbanet_conv_gemm_sm100", p, tag=f"k{kh}s{stride} {ctot}->{cout} @{Ho}x{Wo} act{act}{' res' if residual is not None else ''} st{store_mode}", nbytes=nbytes)
     return out
 
 
@@ -214,7 +218,7 @@ def head_conv(x: torch.Tensor, weight_kc: torch.Tensor, bias: torch.Tensor, dtyp
     p = L.HeadConvParams()
     p.src, p.dst, p.weight, p.bias, p.dtype = x.data_ptr(), out.data_ptr(), weight_kc.data_ptr(), bias.data_ptr(), _DT[dtype]
     p.frames, p.C, p.H, p.W, p.Cout = Fr, Cc, H, W, cout
-    _call("fbanet_head_conv_sm100", p)
+    _call("fbanet_head_conv_sm100", p, nbytes=x.numel() * 4 + out.numel() * out.element_size())
     return out
 
 
@@ -230,7 +234,7 @@ def assemble(sr: torch.Tensor, base: torch.Tensor, C_out: int) -> torch.Tensor:
     p.sr, p.base, p.out = sr.data_ptr(), base.data_ptr(), out.data_ptr()
     p.base_img_stride = base.stride(0) if N > 1 else 0
     p.dtype, p.N, p.C, p.Cp, p.H, p.W = _DT[sr.dtype], N, C_out, Cp, H, W
-    _call("fbanet_assemble_sm100", p)
+    _call("fbanet_assemble_sm100", p, nbytes=N * H * W * C_out * sr.element_size() + base.numel() * 4 + out.numel() * 4)
     return out
 
 
@@ -254,7 +258,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     p = L.LayerNormParams()
     p.x, p.y, p.gamma, p.beta = x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr()
     p.rows, p.C, p.x_ld, p.y_ld, p.dtype, p.eps = rows, Cc, x.stride(0), Cc, _DT[x.dtype], eps
-    _call("fbanet_layernorm_sm100", p)
+    _call("fbanet_layernorm_sm100", p, nbytes=2 * x.numel() * x.element_size())
     return y
 
 
@@ -290,7 +294,7 @@ def window_attention(qkv: torch.Tensor, bias_table: torch.Tensor, B: int, H: int
         N = win * win
         assert bias_expanded.dtype == torch.float32 and bias_expanded.is_contiguous() and bias_expanded.shape == (heads, N, (N + 15) // 16 * 16)
         p.bias_expanded = bias_expanded.data_ptr()
-    _call("fbanet_window_attention_sm100", p)
+    _call("fbanet_window_attention_sm100", p, nbytes=(qkv.numel() + out.numel()) * qkv.element_size())
     return out
 
 
@@ -325,7 +329,7 @@ def leff_fc2(h1: torch.Tensor, dw_w9c: torch.Tensor, dw_b: torch.Tensor, w2: tor
     p.N, p.H, p.W, p.C, p.Hd, p.act = N, H, W, Cc, Hd, act
     if not L.load().fbanet_leff_fc2_supported(C.byref(p)):
         return None
-    _call("fbanet_leff_fc2_sm100", p, tag=f"{Hd}->{Cc} @{H}x{W}")
+    _call("fbanet_leff_fc2_sm100", p, tag=f"{Hd}->{Cc} @{H}x{W}", nbytes=(h1.numel() + out.numel() * (2 if residual is not None else 1) + w2.numel()) * 2)
     return out
 
 
@@ -346,7 +350,8 @@ def faf_gate(feat: torch.Tensor, wsum: torch.Tensor, want_gate: bool = True, wan
     if score is not None:
         assert score.dtype == torch.float32 and score.is_contiguous() and score.shape == (B * Fr, H, W, 2)
         p.score = score.data_ptr()
-    _call("fbanet_faf_gate_sm100", p)
+    nbytes = feat.numel() * feat.element_size() * (2 if want_gated else 1) + (gate.numel() * 4 if gate is not None else 0) + (score.numel() * 4 if score is not None else 0)
+    _call("fbanet_faf_gate_sm100", p, nbytes=nbytes)
     if want_gate and want_gated:
         return gate, gated
     return gated if want_gated else gate
@@ -397,7 +402,7 @@ def warp_burst(burst: torch.Tensor, M: torch.Tensor, layout: str = "BTCHW", retu
     p.s_frame, p.s_y, p.s_x, p.s_c = sf, sy, sx, sc
     p.d_frame, p.d_y, p.d_x, p.d_c = sf, sy, sx, sc
     p.frames, p.frames_per_burst, p.H, p.W, p.C = B * T, T, H, W, Cc
-    _call("fbanet_warp_sm100", p)
+    _call("fbanet_warp_sm100", p, nbytes=2 * burst.numel() * 4)
     return (out, coords) if return_coords else out
 
 

@@ -58,6 +58,15 @@ def head(B, S):
     return (lambda: ops.head_conv(x, w, b, BF)), (x.numel() * 4 + B * 14 * S * S * 64 * 2) / 1e9
 
 
+def warp(B, S):
+    x = torch.rand(B, 14, 3, S, S, device=dev)
+    M = torch.eye(3, dtype=torch.float64).repeat(B, 14, 1, 1)
+    M[:, 1:, :2, 2] = torch.rand(B, 13, 2, dtype=torch.float64) * 8 - 4
+    M[:, 1:, 2, :2] = (torch.rand(B, 13, 2, dtype=torch.float64) - 0.5) * 2e-5
+    M = M.to(dev)
+    return (lambda: ops.warp_burst(x, M)), 2 * x.numel() * 4 / 1e9
+
+
 def leff(B, S, C):
     Hd = 4 * C
     h1 = (torch.rand(B, S, S, Hd, device=dev) - 0.5).to(BF)
@@ -86,6 +95,7 @@ CASES = {
     "ln_80_256": lambda: ln(64, 80, 256),
     "gate_160": lambda: gate(64, 160),
     "head_160": lambda: head(64, 160),
+    "warp_160": lambda: warp(64, 160),
 }
 
 if __name__ == "__main__":
