@@ -132,6 +132,11 @@ def main():
     import torch.distributed as dist
     from fbanet_b200 import BaseModel, ops, _lib as L
 
+    # stdout carries exactly ONE JSON line: library banners (NCCL prints its version to stdout) go to stderr until then
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -236,6 +241,8 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
 
     pk, pk_src = peaks()
     total_bursts = B * world * args.steps
