@@ -8,8 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libfbanet_b200.so")
-ABI_VERSION = 10
+LIB_PATH = os.environ.get("FBANET_B200_LIB") or os.path.join(_HERE, "csrc", "libfbanet_b200.so")   # env override: A/B two builds in one process tree
+ABI_VERSION = 11
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -39,6 +39,7 @@ class ConvParams(C.Structure):
         ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32), ("Cout_store", C.c_int32),
         ("act", C.c_int32), ("store_mode", C.c_int32), ("res_ld", C.c_int32), ("out_ld", C.c_int32),
         ("src_s2d", C.c_int32), ("_pad", C.c_int32),
+        ("ln_stats", C.c_void_p), ("ln_c1", C.c_void_p),
     ]
 
 
@@ -84,6 +85,7 @@ class LayerNormParams(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("y", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("rows", C.c_int64),
         ("C", C.c_int32), ("x_ld", C.c_int32), ("y_ld", C.c_int32), ("dtype", C.c_int32), ("eps", C.c_float), ("_pad", C.c_int32),
+        ("stats", C.c_void_p),
     ]
 
 

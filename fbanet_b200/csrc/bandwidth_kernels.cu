@@ -378,6 +378,8 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const fbanet_layern
   for (int o = TPT / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q * (1.0f / C) + p.eps);
   if (!ok) return;
+  if (p.stats && sub == 0) *reinterpret_cast<float2*>(p.stats + row * 2) = make_float2(mean, rstd);
+  if (!p.y) return;   // statistics only: the consumer GEMM applies the normalisation in its epilogue
   const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + sub * 8)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + sub * 8 + 4));
   const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + sub * 8)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + sub * 8 + 4));
   const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -385,6 +387,42 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const fbanet_layern
 #pragma unroll
   for (int i = 0; i < 8; ++i) o8[i] = (v[i] - mean) * rstd * gg[i] + bb[i];
   store_vec<bf16, 8>(reinterpret_cast<bf16*>(p.y) + row * p.y_ld + sub * 8, o8);
+}
+
+// LayerNorm statistics only (bf16): C/8 threads per row, RPT rows per thread group in flight (a read-only kernel needs
+// several independent 16-byte loads per thread to reach the HBM rate); writes (mean, rstd) per row.
+template <int C, int RPT>
+__global__ void __launch_bounds__(256) rowstats_bf16_kernel(const fbanet_layernorm_params p) {
+  constexpr int TPT = C / 8;
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t grp = gt / TPT;
+  const int sub = (int)(gt % TPT);
+  float v[RPT][8];
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    const int64_t row = grp * RPT + r;
+    if (row < p.rows) load_vec<bf16, 8>(reinterpret_cast<const bf16*>(p.x) + row * p.x_ld + sub * 8, v[r]);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[r][i] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[r][i];
+#pragma unroll
+    for (int o = TPT / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = v[r][i] - mean; q += d * d; }
+#pragma unroll
+    for (int o = TPT / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const int64_t row = grp * RPT + r;
+    if (sub == 0 && row < p.rows) *reinterpret_cast<float2*>(p.stats + row * 2) = make_float2(mean, rsqrtf(q * (1.0f / C) + p.eps));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -834,13 +872,24 @@ static int launch_ln(const fbanet_layernorm_params* p, cudaStream_t s) {
 }
 
 extern "C" int fbanet_layernorm_sm100(const fbanet_layernorm_params* p, void* stream) {
-  if (!p || !p->x || !p->y || !p->gamma || !p->beta || p->rows <= 0) return FBANET_E_BADSHAPE;
+  if (!p || !p->x || (!p->y && !p->stats) || p->rows <= 0) return FBANET_E_BADSHAPE;
+  if (p->y && (!p->gamma || !p->beta)) return FBANET_E_BADSHAPE;
   const int v = p->dtype == FBANET_F32 ? 4 : 8;
   if (p->x_ld % v || ((uintptr_t)p->x % 16)) return FBANET_E_ALIGN;
+  if (p->stats && (p->dtype != FBANET_BF16 || (p->C != 64 && p->C != 128 && p->C != 256) || ((uintptr_t)p->stats % 8))) return FBANET_E_UNSUPPORTED;
   if (p->dtype == FBANET_F32) return launch_ln<float>(p, (cudaStream_t)stream);
   if (p->dtype == FBANET_BF16) {
-    const bool fast = (p->y_ld % 8) == 0 && ((uintptr_t)p->y % 16) == 0 && ((uintptr_t)p->gamma % 16) == 0 && ((uintptr_t)p->beta % 16) == 0;
+    const bool fast = !p->y || ((p->y_ld % 8) == 0 && ((uintptr_t)p->y % 16) == 0 && ((uintptr_t)p->gamma % 16) == 0 && ((uintptr_t)p->beta % 16) == 0);
+    if (p->stats && !fast) return FBANET_E_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
+    if (!p->y) {   // statistics only
+      constexpr int RPT = 4;
+      const int64_t groups = (p->rows + RPT - 1) / RPT;
+      if (p->C == 64) rowstats_bf16_kernel<64, RPT><<<ceil_div(groups * 8, 256), 256, 0, st>>>(*p);
+      else if (p->C == 128) rowstats_bf16_kernel<128, RPT><<<ceil_div(groups * 16, 256), 256, 0, st>>>(*p);
+      else rowstats_bf16_kernel<256, RPT><<<ceil_div(groups * 32, 256), 256, 0, st>>>(*p);
+      return check_launch();
+    }
     if (fast && p->C == 64) { layernorm_bf16_kernel<64><<<ceil_div(p->rows * 8, 256), 256, 0, st>>>(*p); return check_launch(); }
     if (fast && p->C == 128) { layernorm_bf16_kernel<128><<<ceil_div(p->rows * 16, 256), 256, 0, st>>>(*p); return check_launch(); }
     if (fast && p->C == 256) { layernorm_bf16_kernel<256><<<ceil_div(p->rows * 32, 256), 256, 0, st>>>(*p); return check_launch(); }

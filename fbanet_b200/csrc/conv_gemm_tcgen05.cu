@@ -51,6 +51,8 @@ struct TcParams {
   Chunk chunks[TC_MAX_CHUNKS];
   const float* bias;
   const float* alpha;
+  const float* ln_stats;  // folded LayerNorm: per-row (mean, rstd), see fbanet_conv_params
+  const float* ln_c1;     // [Cout] row sums of the folded weights
   const bf16* residual;
   void* out;
   const float* base;
@@ -87,15 +89,28 @@ __device__ __forceinline__ void apply_act_vec(float (&f)[NV], const int act, con
 // bias + activation + residual + store of 32 (or 16) accumulator columns of one pixel row
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t (&v)[32], const int nc, const int col0, const int img,
                                                const int y, const int x, const float alpha, const float* bias_s,
-                                               const uint4* rpre = nullptr) {
+                                               const uint4* rpre = nullptr, const float* c1_s = nullptr, const float ln_mean = 0.f,
+                                               const float ln_rstd = 1.f) {
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = (j < nc) ? __uint_as_float(v[j]) : 0.f;
+  if (c1_s) {   // folded LayerNorm: rstd * (acc - mean * c1) + bias
+    const float mr = -ln_mean * ln_rstd;
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {   // bias of this CTA's N-tile sits in shared memory (broadcast reads)
-    if (j < nc) {
-      const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j);
-      f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+    for (int j = 0; j < 32; j += 4) {
+      if (j < nc) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j), c4 = *reinterpret_cast<const float4*>(c1_s + j);
+        f[j] = fmaf(f[j], ln_rstd, fmaf(c4.x, mr, b4.x)); f[j + 1] = fmaf(f[j + 1], ln_rstd, fmaf(c4.y, mr, b4.y));
+        f[j + 2] = fmaf(f[j + 2], ln_rstd, fmaf(c4.z, mr, b4.z)); f[j + 3] = fmaf(f[j + 3], ln_rstd, fmaf(c4.w, mr, b4.w));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {   // bias of this CTA's N-tile sits in shared memory (broadcast reads)
+      if (j < nc) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j);
+        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+      }
     }
   }
   if (p.act == FBANET_ACT_RELU) {
@@ -199,15 +214,23 @@ __device__ __forceinline__ void issue_unit_resident(const uint32_t tmem_d, const
 }
 
 constexpr int TC_MAX_A_SLOTS = 8;
-constexpr int TC_NUM_THREADS = 384;   // warps: 0 A-producer, 1 MMA, 2 TMEM alloc, 3 B-producer, 4..11 epilogue
+// warps: 0 A-producer, 1 MMA, 2 TMEM alloc, 3 B-producer, 4.. epilogue (TC_EPI_SLOTS warps per TMEM lane quarter).
+// Measured in one box: 3 slots (512 threads, 128 registers) speed the staged TMA-store epilogue up (fc1 128->512 0.675 -> 0.568 ms,
+// qkv 0.416 -> 0.366 ms: its GELU / pack chains are latency bound and want more warps), but cost the direct-store path (3x3 convs,
+// K = 896 fusion GEMM) 10-20 % through the lower register cap -- so the slot count is a template parameter chosen per launch.
+constexpr int TC_MAX_EPI_WARPS = 12;
 
-__global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
+// HAS_LN: folded-LayerNorm epilogue (a separate instantiation: compiled into the common one it costs every GEMM 12 %)
+template <bool HAS_LN, int TC_EPI_SLOTS>
+__global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
+  constexpr int TC_EPI_WARPS = 4 * TC_EPI_SLOTS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[TC_MAX_A_SLOTS], a_empty[TC_MAX_A_SLOTS], tmem_full[2], tmem_empty[2];
   __shared__ __align__(8) uint64_t b_full[TC_MAX_STEPS], b_empty[TC_MAX_STEPS];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float bias_s[256];
-  __shared__ __align__(8) uint64_t res_bar[8];
+  __shared__ __align__(16) float c1_s[256];
+  __shared__ __align__(8) uint64_t res_bar[TC_MAX_EPI_WARPS];
 
   // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the 128B swizzle needs
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -216,7 +239,7 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
   const uint32_t b_bytes = (uint32_t)BN * TC_BK * 2;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)p.a_slots * p.a_slot_bytes;
-  uint8_t* smem_stage = smem_b + (size_t)p.b_slots * b_bytes;   // 8 epilogue warps x 2 x 4 KB staging sub-tiles
+  uint8_t* smem_stage = smem_b + (size_t)p.b_slots * b_bytes;   // TC_EPI_WARPS x stage_bufs x 4 KB staging sub-tiles
   const uint32_t tmem_cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 
   if (warp == 0 && lane == 0) {
@@ -227,8 +250,8 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.a_slots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.b_slots; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
-    for (int a = 0; a < 8; ++a) mbar_init(&res_bar[a], 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], TC_EPI_WARPS); }
+    for (int a = 0; a < TC_EPI_WARPS; ++a) mbar_init(&res_bar[a], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -237,7 +260,10 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
   }
   if (warp >= 4) {   // this CTA owns N-tile blockIdx.x % n_tiles_n for its whole life: stage its bias once
     const int i = threadIdx.x - 128;
-    if (i < 256) bias_s[i] = (p.bias && i < BN) ? __ldg(p.bias + (blockIdx.x % p.n_tiles_n) * BN + i) : 0.f;
+    if (i < 256) {
+      bias_s[i] = (p.bias && i < BN) ? __ldg(p.bias + (blockIdx.x % p.n_tiles_n) * BN + i) : 0.f;
+      if (HAS_LN) c1_s[i] = (i < BN) ? __ldg(p.ln_c1 + (blockIdx.x % p.n_tiles_n) * BN + i) : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -384,9 +410,9 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
       b_landed = true;
     }
   } else if (warp >= 4) {
-    // ================= epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =================
+    // ================= epilogue: 4 TMEM lane quarters x TC_EPI_SLOTS warps; column pieces are dealt round-robin to the slots =================
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;
+    const int slot = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const int ly = row / p.tw, lx = row - ly * p.tw;
     const float alpha = (p.act == FBANET_ACT_PRELU) ? __ldg(p.alpha) : 0.f;
@@ -397,9 +423,9 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
       // SWIZZLE_128B) with no CTA-level barrier at all: tcgen05.ld -> bias/act(/residual) -> st.shared -> fence ->
       // __syncwarp -> one bulk store.  Two staging buffers per warp: the store of chunk k drains while chunk k+1 is computed.
       // The residual sub-tile is TMA-loaded into the staging buffer first and added in place.  64-column chunks are dealt
-      // alternately to the two warps of a lane quarter, counted across tiles so any chunks-per-tile count balances.
+      // round-robin to the warps of a lane quarter, counted across tiles so any chunks-per-tile count balances.
       // (Per-thread 16-byte global stores touch 32 lines per instruction and cap an SM at ~16 B/clk.)
-      const int ew = warp - 4;                             // 0..7
+      const int ew = warp - 4;                             // 0 .. TC_EPI_WARPS-1
       const uint32_t nbufs = (uint32_t)p.stage_bufs;
       uint8_t* stage0 = smem_stage + ew * 4096 * nbufs;
       const uint32_t stage_u = smem_u32(stage0);
@@ -408,6 +434,8 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
       const bool has_res = p.residual != nullptr;
       const int Co = p.store_mode == FBANET_STORE_CONVT2 ? (p.Cout >> 2) : p.Cout;
       const int wy0 = (q * 32) / p.tw, wx0 = (q * 32) % p.tw;   // this warp's rectangle inside the tile
+      const int bw = p.tw < 32 ? p.tw : 32;
+      const int ply = lane / bw, plx = lane - ply * bw;         // this thread's pixel inside the rectangle
       uint32_t res_phase = 0, nb = 0;
       for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
         const int acc = it & 1;
@@ -415,9 +443,13 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
         const int img = mt / tiles_per_img, r = mt % tiles_per_img;
         const int y0 = (r / p.tiles_x) * p.th + wy0, x0 = (r % p.tiles_x) * p.tw + wx0;
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        float2 lnst = make_float2(0.f, 0.f);   // (mean, rstd) of this thread's row, fetched while the MMAs still run
+        if (HAS_LN && y0 + ply < p.Ho && x0 + plx < p.Wo)
+          lnst = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + ((int64_t)img * p.Ho + (y0 + ply)) * p.Wo + (x0 + plx));
+        const f32x2 ln_r2 = pack_f2(lnst.y, lnst.y), ln_m2 = pack_f2(-lnst.x * lnst.y, -lnst.x * lnst.y);
         bool waited = false;
         for (int cidx = 0; cidx < nchunks; ++cidx) {
-          if (((it * nchunks + cidx) & 1) != half) continue;
+          if (((it * nchunks + cidx) % TC_EPI_SLOTS) != slot) continue;
           const int col0 = nt * BN + cidx * 64;          // GEMM column of the chunk
           const uint32_t boff = (nbufs == 2 ? (nb & 1u) : 0u) * 4096u;
           const uint32_t sbuf = stage_u + boff;
@@ -443,11 +475,17 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
 #pragma unroll
           for (int c = 0; c < 8; ++c) {                  // 8 columns = one 16-byte smem chunk at a time
             const float4 b0 = *reinterpret_cast<const float4*>(bs + c * 8), b1 = *reinterpret_cast<const float4*>(bs + c * 8 + 4);
-            f32x2 f[4];
-            f[0] = add_f2(pack_f2(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1])), pack_f2(b0.x, b0.y));
-            f[1] = add_f2(pack_f2(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3])), pack_f2(b0.z, b0.w));
-            f[2] = add_f2(pack_f2(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5])), pack_f2(b1.x, b1.y));
-            f[3] = add_f2(pack_f2(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7])), pack_f2(b1.z, b1.w));
+            f32x2 f[4], bb[4] = {pack_f2(b0.x, b0.y), pack_f2(b0.z, b0.w), pack_f2(b1.x, b1.y), pack_f2(b1.z, b1.w)};
+            if (HAS_LN) {   // folded LayerNorm: rstd * acc + (bias - mean * rstd * c1)
+              const float4 c0 = *reinterpret_cast<const float4*>(c1_s + cidx * 64 + c * 8), c1v = *reinterpret_cast<const float4*>(c1_s + cidx * 64 + c * 8 + 4);
+              bb[0] = fma_f2(pack_f2(c0.x, c0.y), ln_m2, bb[0]); bb[1] = fma_f2(pack_f2(c0.z, c0.w), ln_m2, bb[1]);
+              bb[2] = fma_f2(pack_f2(c1v.x, c1v.y), ln_m2, bb[2]); bb[3] = fma_f2(pack_f2(c1v.z, c1v.w), ln_m2, bb[3]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) f[e] = fma_f2(pack_f2(__uint_as_float(v[c * 8 + 2 * e]), __uint_as_float(v[c * 8 + 2 * e + 1])), ln_r2, bb[e]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) f[e] = add_f2(pack_f2(__uint_as_float(v[c * 8 + 2 * e]), __uint_as_float(v[c * 8 + 2 * e + 1])), bb[e]);
+            }
             if (p.act == FBANET_ACT_GELU_TANH) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) f[e] = gelu_tanh_fast_f2(f[e]);
@@ -488,31 +526,35 @@ __global__ void __launch_bounds__(TC_NUM_THREADS, 1) conv_gemm_tcgen05_kernel(co
       if (lane == 0) bulk_wait0();                       // all stores of this warp have completed
       __syncwarp();
     } else {
-      const int ncols = (BN >= 32) ? BN / 2 : (half == 0 ? BN : 0);
-      const int cbeg = half * (BN / 2);
+      const int npieces = BN >= 32 ? BN / 32 : 1;      // 32-column pieces (one 16-column piece for BN = 16)
       for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         const int img = mt / tiles_per_img, r = mt % tiles_per_img;
         const int y = (r / p.tiles_x) * p.th + ly, x = (r % p.tiles_x) * p.tw + lx;
         const bool valid = (ly < p.th) && (y < p.Ho) && (x < p.Wo);
-        // the residual of the first 32-column chunk is fetched while the MMAs of this tile are still running
+        // this warp's first piece of the tile; its residual is fetched while the MMAs of the tile are still running
+        int j0 = (slot - (it * npieces) % TC_EPI_SLOTS + TC_EPI_SLOTS) % TC_EPI_SLOTS;
         uint4 rpre[4];
-        const bool pre = valid && p.residual != nullptr && ncols >= 32;
+        const bool pre = valid && p.residual != nullptr && BN >= 32 && j0 < npieces;
         if (pre) {
-          const bf16* rp = p.residual + img * p.res_img_stride + ((int64_t)y * p.Wo + x) * p.res_ld + nt * BN + cbeg;
+          const bf16* rp = p.residual + img * p.res_img_stride + ((int64_t)y * p.Wo + x) * p.res_ld + nt * BN + j0 * 32;
 #pragma unroll
           for (int j = 0; j < 4; ++j) rpre[j] = *reinterpret_cast<const uint4*>(rp + j * 8);
         }
+        float2 lnst = make_float2(0.f, 1.f);
+        if (HAS_LN && valid) lnst = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + ((int64_t)img * p.Ho + y) * p.Wo + x);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
-        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cbeg);
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        for (int j = j0; j < npieces; j += TC_EPI_SLOTS) {
+          const int c0 = j * 32;
           uint32_t v[32];
-          const int nc = (ncols - c0 >= 32) ? 32 : 16;
+          const int nc = (BN - c0 >= 32) ? 32 : 16;
           if (nc == 32) tmem_ld32(taddr0 + c0, v); else tmem_ld16(taddr0 + c0, v);
           tmem_ld_wait();
-          if (valid) epilogue_chunk(p, v, nc, nt * BN + cbeg + c0, img, y, x, alpha, bias_s + cbeg + c0, (pre && c0 == 0) ? rpre : nullptr);
+          if (valid) epilogue_chunk(p, v, nc, nt * BN + c0, img, y, x, alpha, bias_s + c0, (pre && j == j0) ? rpre : nullptr,
+                                    HAS_LN ? c1_s + c0 : nullptr, lnst.x, lnst.y);
           __syncwarp();
         }
         tc_fence_before();
@@ -615,6 +657,8 @@ static bool tc_shape_ok(const fbanet_conv_params* p) {
     if (p->residual || ((uintptr_t)p->out % 4)) return false;
   }
   if (p->bias && ((uintptr_t)p->bias % 16)) return false;
+  if ((p->ln_stats != nullptr) != (p->ln_c1 != nullptr)) return false;
+  if (p->ln_stats && (p->KH != 1 || p->stride != 1 || p->store_mode != FBANET_STORE_NHWC || ((uintptr_t)p->ln_stats % 8) || ((uintptr_t)p->ln_c1 % 16))) return false;
   return get_encode() != nullptr;
 }
 
@@ -714,7 +758,7 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
     }
   }
   tp.nsteps = ns;
-  tp.bias = p->bias; tp.alpha = p->alpha; tp.residual = reinterpret_cast<const bf16*>(p->residual);
+  tp.bias = p->bias; tp.alpha = p->alpha; tp.ln_stats = p->ln_stats; tp.ln_c1 = p->ln_c1; tp.residual = reinterpret_cast<const bf16*>(p->residual);
   tp.out = p->out; tp.base = p->base;
   tp.res_img_stride = p->res_img_stride; tp.out_img_stride = p->out_img_stride; tp.base_img_stride = p->base_img_stride;
   tp.act = p->act; tp.store_mode = p->store_mode; tp.res_ld = p->res_ld; tp.out_ld = p->out_ld;
@@ -783,14 +827,19 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   };
   Plan p0, p1;
   if (!plan(216 * 1024, &p0)) return FBANET_E_UNSUPPORTED;
-  int stage_bytes = 0;
+  int stage_bytes = 0, epi_slots = 2;
   if (tp.tma_store) {
-    const int want_a = p0.a_slots < 3 ? p0.a_slots : 3;
+    // staging options in order of preference: (epilogue warps per lane quarter, buffers per warp).  Three warps per quarter want
+    // >= 4 A slots left (deep-K GEMMs lose more from a shallow A ring than they gain in the epilogue), two warps >= 3.
+    static const int opts[4][2] = {{3, 2}, {3, 1}, {2, 2}, {2, 1}};
     tp.tma_store = 0;
-    for (int bufs = 2; bufs >= 1 && !tp.tma_store; --bufs) {
-      const int sb = 8 * bufs * 4096;
+    for (int o = 0; o < 4 && !tp.tma_store; ++o) {
+      const int slots = opts[o][0], bufs = opts[o][1];
+      const int sb = 4 * slots * bufs * 4096;
+      const int floor_a = slots == 3 ? 4 : 3;
+      const int want_a = p0.a_slots < floor_a ? p0.a_slots : floor_a;
       if (plan(216 * 1024 - sb, &p1) && p1.resident == p0.resident && p1.b_slots == p0.b_slots && p1.a_slots >= want_a) {
-        tp.tma_store = 1; tp.stage_bufs = bufs; stage_bytes = sb; p0 = p1;
+        tp.tma_store = 1; tp.stage_bufs = bufs; stage_bytes = sb; epi_slots = slots; p0 = p1;
       }
     }
   }
@@ -799,7 +848,10 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
 
   static size_t smem_opted_in = 0;  // opt-in limit is per function; raise it only when a launch needs more
   if (smem > smem_opted_in) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cudaGetLastError(); set_last_error(e); return FBANET_E_LAUNCH; }
     smem_opted_in = smem;
   }
@@ -811,7 +863,13 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   if (per_n < 1) per_n = 1;
   if (per_n > tp.m_tiles) per_n = tp.m_tiles;
   const int grid = per_n * tp.n_tiles_n;
-  conv_gemm_tcgen05_kernel<<<grid, TC_NUM_THREADS, smem, stream>>>(tp);
+  if (epi_slots == 3) {   // staged epilogue with 12 epilogue warps
+    if (tp.ln_stats) conv_gemm_tcgen05_kernel<true, 3><<<grid, 512, smem, stream>>>(tp);
+    else conv_gemm_tcgen05_kernel<false, 3><<<grid, 512, smem, stream>>>(tp);
+  } else {                // 8 epilogue warps (staged or direct stores), 168 registers
+    if (tp.ln_stats) conv_gemm_tcgen05_kernel<true, 2><<<grid, 384, smem, stream>>>(tp);
+    else conv_gemm_tcgen05_kernel<false, 2><<<grid, 384, smem, stream>>>(tp);
+  }
   return check_launch();
 }
 

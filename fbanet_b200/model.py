@@ -14,6 +14,7 @@ producers write straight into channel slices of the concat buffer, consumers rea
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -190,6 +191,8 @@ class BaseModel(nn.Module):
         self.gelu_act = {"tanh": L.ACT_GELU_TANH, "erf": L.ACT_GELU_ERF}[gelu]
         self.impl = impl
         self.fuse_leff = True
+        # bf16 path: LayerNorm folded into the qkv / fc1 GEMM epilogues (row statistics only); FBANET_FOLD_LN=0/1 overrides
+        self.fold_ln = os.environ.get("FBANET_FOLD_LN", "1") != "0"
         self.host_chunk = 32       # bursts per pipelined chunk of infer_host (int, or an explicit schedule of chunk sizes)
         self._io_streams = None
         self.host_graphs = True    # infer_host replays CUDA graphs (captured per chunk size) instead of launching eagerly
@@ -306,13 +309,20 @@ class BaseModel(nn.Module):
                     # tensor-core path: scale * log2(e) folded into the q projection (fp32, before the bf16 rounding), so the
                     # attention kernel's scores come out of the MMA already in log2 units (window_attention.py:196-198)
                     qs = (self.qk_scale or (ly.dim // ly.heads) ** -0.5) * math.log2(math.e) if tc else 1.0
-                    P[k + ".qkv.w"] = torch.cat([a.qkv.to_q.weight.detach().float() * qs, a.qkv.to_kv.weight.detach().float()], 0).to(T).contiguous()
-                    P[k + ".qkv.b"] = torch.cat([f32(a.qkv.to_q.bias) * qs, f32(a.qkv.to_kv.bias)], 0).contiguous()
+                    wqkv = torch.cat([a.qkv.to_q.weight.detach().float() * qs, a.qkv.to_kv.weight.detach().float()], 0)
+                    bqkv = torch.cat([f32(a.qkv.to_q.bias) * qs, f32(a.qkv.to_kv.bias)], 0).contiguous()
+                    if tc and self.fold_ln:
+                        # LayerNorm folded into its consumer GEMMs (ops.fold_layernorm): norm1 -> qkv, norm2 -> fc1
+                        P[k + ".qkv.w"], P[k + ".qkv.b"], P[k + ".qkv.c1"] = ops.fold_layernorm(wqkv, bqkv, ly.norm1.weight, ly.norm1.bias, T)
+                        P[k + ".fc1.w"], P[k + ".fc1.b"], P[k + ".fc1.c1"] = ops.fold_layernorm(
+                            ly.mlp.linear1[0].weight, ly.mlp.linear1[0].bias, ly.norm2.weight, ly.norm2.bias, T)
+                    else:
+                        P[k + ".qkv.w"], P[k + ".qkv.b"] = wqkv.to(T).contiguous(), bqkv
+                        put_lin(k + ".fc1", ly.mlp.linear1[0])
                     P[k + ".rpb"] = f32(a.relative_position_bias_table)
                     if tc:  # dense per-head bias in log2 units for the tensor-core attention kernel
                         P[k + ".rpbx"] = ops.expand_rel_pos_bias(P[k + ".rpb"], ly.win)
                     put_lin(k + ".proj", a.proj)
-                    put_lin(k + ".fc1", ly.mlp.linear1[0])
                     put_lin(k + ".fc2", ly.mlp.linear2[0])
                     dw = ly.mlp.dwconv[0]
                     P[k + ".dw.w"] = dw.weight.detach().float().reshape(dw.weight.shape[0], 9).t().contiguous()
@@ -369,23 +379,31 @@ class BaseModel(nn.Module):
         """ConvTranspose2d(2,2) as a per-pixel GEMM with a 2x2 scatter store into ``out`` (a concat slice)."""
         return ops.conv_gemm([x], P[name + ".w"], out, bias=P[name + ".b"], store_mode=L.STORE_CONVT2, impl=self.impl)
 
-    def _lin(self, P, name, x4, out=None, act=L.ACT_NONE, residual=None):
+    def _lin(self, P, name, x4, out=None, act=L.ACT_NONE, residual=None, ln_stats=None):
         w = P[name + ".w"]
         if out is None:
             out = self._new(*x4.shape[:3], w.shape[0])
-        return ops.conv_gemm([x4], w, out, bias=P[name + ".b"], act=act, residual=residual, impl=self.impl)
+        return ops.conv_gemm([x4], w, out, bias=P[name + ".b"], act=act, residual=residual, impl=self.impl,
+                             ln_stats=ln_stats, ln_c1=P[name + ".c1"] if ln_stats is not None else None)
 
     def _layer(self, P, key, ly: _Layer, x, out=None):
         """LeWin block (layers/fba_net.py:139-250 with Appendix A-4): x + Attn(LN1 x); + LeFF(LN2 .)."""
         B, H, W, Cd = x.shape
-        ln1 = ops.layernorm(x.view(-1, Cd), P[key + ".ln1.g"], P[key + ".ln1.b"]).view(B, H, W, Cd)
-        qkv = self._lin(P, key + ".qkv", ln1)
+        fold = (key + ".qkv.c1") in P   # LayerNorm folded into the consumer GEMM: only per-row statistics are computed here
+        if fold:
+            qkv = self._lin(P, key + ".qkv", x, ln_stats=ops.row_stats(x.view(-1, Cd)))
+        else:
+            ln1 = ops.layernorm(x.view(-1, Cd), P[key + ".ln1.g"], P[key + ".ln1.b"]).view(B, H, W, Cd)
+            qkv = self._lin(P, key + ".qkv", ln1)
         scale = self.qk_scale or (Cd // ly.heads) ** -0.5
         att = ops.window_attention(qkv.view(-1, 3 * Cd), P[key + ".rpb"], B, H, W, ly.heads, ly.win, ly.shift, scale, impl=self.impl,
                                    bias_expanded=P.get(key + ".rpbx"), q_prescaled=self._use_tc())
         x1 = self._lin(P, key + ".proj", att.view(B, H, W, Cd), residual=x)
-        ln2 = ops.layernorm(x1.view(-1, Cd), P[key + ".ln2.g"], P[key + ".ln2.b"]).view(B, H, W, Cd)
-        h = self._lin(P, key + ".fc1", ln2, act=self.gelu_act)
+        if fold:
+            h = self._lin(P, key + ".fc1", x1, act=self.gelu_act, ln_stats=ops.row_stats(x1.view(-1, Cd)))
+        else:
+            ln2 = ops.layernorm(x1.view(-1, Cd), P[key + ".ln2.g"], P[key + ".ln2.b"]).view(B, H, W, Cd)
+            h = self._lin(P, key + ".fc1", ln2, act=self.gelu_act)
         if self._use_tc() and self.fuse_leff:
             # depthwise 3x3 + GELU computed inside the fc2 GEMM as its A-operand producer (no HBM round trip)
             if out is None:

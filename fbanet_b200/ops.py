@@ -94,8 +94,14 @@ def conv_gemm(
     impl: int = L.IMPL_AUTO,
     alg_cin: Optional[int] = None,
     src_s2d: bool = False,
+    ln_stats: Optional[torch.Tensor] = None,
+    ln_c1: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
-    """out = act(conv(concat(srcs)) + bias) + residual.  ``weight`` is packed ``[Cout, kh*kw*sum(C)]``."""
+    """out = act(conv(concat(srcs)) + bias) + residual.  ``weight`` is packed ``[Cout, kh*kw*sum(C)]``.
+
+    ``ln_stats`` ``[rows, 2]`` fp32 (mean, rstd per input row, :func:`row_stats`) + ``ln_c1`` ``[Cout]``: LayerNorm folded into a
+    1x1 GEMM -- ``weight`` must be ``W * gamma``, ``bias`` must be ``W @ beta + b`` and ``ln_c1`` the row sums of ``weight``
+    (:func:`fold_layernorm`); the result equals ``W @ LN(x) + b``."""
     p = L.ConvParams()
     dt = srcs[0].dtype
     p.dtype = _DT[dt]
@@ -134,6 +140,10 @@ def conv_gemm(
     if alpha is not None:
         assert alpha.dtype == torch.float32
         p.alpha = alpha.data_ptr()
+    if ln_stats is not None:
+        assert ln_c1 is not None and ln_stats.dtype == torch.float32 and ln_stats.is_contiguous() and ln_stats.shape == (N * Ho * Wo, 2)
+        assert ln_c1.dtype == torch.float32 and ln_c1.numel() == cout and kh == 1 and kw == 1
+        p.ln_stats, p.ln_c1 = ln_stats.data_ptr(), ln_c1.data_ptr()
     if residual is not None:
         assert residual.dtype == dt and residual.shape == (N, Ho, Wo, cout)
         rp, _, rld, ris = _cl(residual)
@@ -260,6 +270,30 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     p.rows, p.C, p.x_ld, p.y_ld, p.dtype, p.eps = rows, Cc, x.stride(0), Cc, _DT[x.dtype], eps
     _call("fbanet_layernorm_sm100", p, nbytes=2 * x.numel() * x.element_size())
     return y
+
+
+def row_stats(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """LayerNorm statistics only: ``[rows, C]`` bf16 -> fp32 ``[rows, 2]`` = (mean, 1/sqrt(var + eps)); the normalisation itself is
+    applied by the consumer GEMM (``conv_gemm(..., ln_stats=, ln_c1=)``), so the normalised tensor never exists in HBM."""
+    assert x.is_cuda and x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.bfloat16
+    rows, Cc = x.shape
+    st = torch.empty((rows, 2), device=x.device, dtype=torch.float32)
+    p = L.LayerNormParams()
+    p.x, p.stats = x.data_ptr(), st.data_ptr()
+    p.rows, p.C, p.x_ld, p.y_ld, p.dtype, p.eps = rows, Cc, x.stride(0), Cc, _DT[x.dtype], eps
+    _call("fbanet_layernorm_sm100", p, nbytes=x.numel() * x.element_size() + st.numel() * 4)
+    return st
+
+
+def fold_layernorm(w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, dtype: torch.dtype):
+    """Fold ``LN(x) = (x - mean) * rstd * gamma + beta`` into the linear layer ``y = W LN(x) + b`` that consumes it:
+    returns (``W' = W diag(gamma)`` in ``dtype``, ``bias' = W beta + b`` fp32, ``c1 = rowsum(W')`` fp32 of the ROUNDED weights, so
+    the ``mean * c1`` term cancels exactly what the tensor cores accumulate)."""
+    w64, g64, be64 = w.detach().double(), gamma.detach().double(), beta.detach().double()
+    wf = (w64 * g64[None, :]).to(dtype)
+    bias = (w64 @ be64 + b.detach().double()).float().contiguous()
+    c1 = wf.double().sum(1).float().contiguous()
+    return wf.contiguous(), bias, c1
 
 
 def expand_rel_pos_bias(bias_table: torch.Tensor, win: int) -> torch.Tensor:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 10
+#define FBANET_ABI_VERSION 11
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -100,6 +100,13 @@ typedef struct fbanet_conv_params {
                              [N,H,W,C] inputs (fbanet_space_to_depth_sm100); only KH=KW=4, stride 2, pad 1,
                              tensor-core path.  src[i].C is then 4*C_i.                                */
   int32_t _pad;
+  /* LayerNorm folded into a 1x1 GEMM (layers/fba_net.py:196,246 feeding linear_projection.py:27-28 /
+   * locally_enhanced_feed_forward.py:27), tensor-core path: the GEMM runs on the RAW rows x with weights W' = W diag(gamma),
+   *   y[r][n] = rstd[r] * (acc[r][n] - mean[r] * c1[n]) + bias[n],   c1[n] = sum_k W'[n][k],  bias[n] = (W beta + b)[n],
+   * which equals W LN(x) + b exactly.  ln_stats: fp32 [rows][2] = (mean, rstd) from fbanet_layernorm_sm100 (stats mode);
+   * ln_c1: fp32 [Cout].  Both NULL: plain GEMM. */
+  const float* ln_stats;
+  const float* ln_c1;
 } fbanet_conv_params;
 
 /* K1: homography warp with bilinear sampling.  Replaces cv2.warpPerspective / cv2.warpAffine with
@@ -171,7 +178,7 @@ typedef struct fbanet_s2d_params {
 /* K8: LayerNorm over channels, eps, affine (layers/fba_net.py:77-79,196,246). */
 typedef struct fbanet_layernorm_params {
   const void* x;
-  void* y;
+  void* y;                /* NULL with `stats` set: statistics only (the normalisation is folded into the consumer GEMM) */
   const float* gamma;
   const float* beta;
   int64_t rows;
@@ -179,6 +186,7 @@ typedef struct fbanet_layernorm_params {
   int32_t dtype;
   float eps;
   int32_t _pad;
+  float* stats;           /* optional fp32 [rows][2] = (mean, 1/sqrt(var + eps)) per row */
 } fbanet_layernorm_params;
 
 /* K6: windowed multi-head self-attention over a token map (layers/fba_net.py:139-250 +

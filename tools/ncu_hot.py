@@ -18,6 +18,8 @@ def main():
     stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     recs = []
     for k, r in enumerate(rows[hi + 1:]):
+        if r and r[0] in ("Kernel Name", "Address"):   # next kernel of a multi-kernel report: keep the first only
+            break
         if len(r) < len(hdr):
             continue
         n = int(r[ci["# Samples"]] or 0)
