@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBANET_B200_LIB") or os.path.join(_HERE, "csrc", "libfbanet_b200.so")   # env override: A/B two builds in one process tree
-ABI_VERSION = 11
+ABI_VERSION = 13
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -39,7 +39,7 @@ class ConvParams(C.Structure):
         ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32), ("Cout_store", C.c_int32),
         ("act", C.c_int32), ("store_mode", C.c_int32), ("res_ld", C.c_int32), ("out_ld", C.c_int32),
         ("src_s2d", C.c_int32), ("_pad", C.c_int32),
-        ("ln_stats", C.c_void_p), ("ln_c1", C.c_void_p),
+        ("ln_stats", C.c_void_p), ("_reserved", C.c_void_p),
     ]
 
 
@@ -78,6 +78,7 @@ class AssembleParams(C.Structure):
     _fields_ = [
         ("sr", C.c_void_p), ("base", C.c_void_p), ("out", C.c_void_p), ("base_img_stride", C.c_int64), ("dtype", C.c_int32),
         ("N", C.c_int32), ("C", C.c_int32), ("Cp", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("lo_offset", C.c_int32), ("_pad", C.c_int32),
     ]
 
 

@@ -287,7 +287,8 @@ __global__ void __launch_bounds__(256) assemble_kernel(const fbanet_assemble_par
       const float* bp = p.base + n * p.base_img_stride + (int64_t)c * Hb * Wb;
       const float bl = hy * (hx * __ldg(bp + yb * Wb + xb) + wx * __ldg(bp + yb * Wb + x1)) +
                        wy * (hx * __ldg(bp + y1 * Wb + xb) + wx * __ldg(bp + y1 * Wb + x1));
-      p.out[((n * p.C + c) * p.H + y) * p.W + x] = to_f32<T>(s[c]) + bl;
+      const float v = to_f32<T>(s[c]) + (p.lo_offset > 0 ? to_f32<T>(s[c + p.lo_offset]) : 0.f);
+      p.out[((n * p.C + c) * p.H + y) * p.W + x] = v + bl;
     }
   }
 }
@@ -837,7 +838,7 @@ extern "C" int fbanet_head_conv_sm100(const fbanet_head_conv_params* p, void* st
 }
 
 extern "C" int fbanet_assemble_sm100(const fbanet_assemble_params* p, void* stream) {
-  if (!p || !p->sr || !p->base || !p->out || p->N <= 0 || p->C <= 0 || p->Cp < p->C || (p->H % 4) || (p->W % 4)) return FBANET_E_BADSHAPE;
+  if (!p || !p->sr || !p->base || !p->out || p->N <= 0 || p->C <= 0 || p->Cp < p->C || (p->H % 4) || (p->W % 4) || p->lo_offset < 0 || (p->lo_offset > 0 && p->lo_offset + p->C > p->Cp)) return FBANET_E_BADSHAPE;
   const int64_t total = (int64_t)p->N * p->H * p->W;
   if (p->dtype == FBANET_F32) assemble_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
   else if (p->dtype == FBANET_BF16) assemble_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);

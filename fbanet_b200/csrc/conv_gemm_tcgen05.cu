@@ -52,7 +52,6 @@ struct TcParams {
   const float* bias;
   const float* alpha;
   const float* ln_stats;  // folded LayerNorm: per-row (mean, rstd), see fbanet_conv_params
-  const float* ln_c1;     // [Cout] row sums of the folded weights
   const bf16* residual;
   void* out;
   const float* base;
@@ -89,19 +88,17 @@ __device__ __forceinline__ void apply_act_vec(float (&f)[NV], const int act, con
 // bias + activation + residual + store of 32 (or 16) accumulator columns of one pixel row
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t (&v)[32], const int nc, const int col0, const int img,
                                                const int y, const int x, const float alpha, const float* bias_s,
-                                               const uint4* rpre = nullptr, const float* c1_s = nullptr, const float ln_mean = 0.f,
-                                               const float ln_rstd = 1.f) {
+                                               const uint4* rpre = nullptr, const bool has_ln = false, const float ln_rstd = 1.f) {
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = (j < nc) ? __uint_as_float(v[j]) : 0.f;
-  if (c1_s) {   // folded LayerNorm: rstd * (acc - mean * c1) + bias
-    const float mr = -ln_mean * ln_rstd;
+  if (has_ln) {   // folded LayerNorm (row-centred weights): rstd * acc + bias
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       if (j < nc) {
-        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j), c4 = *reinterpret_cast<const float4*>(c1_s + j);
-        f[j] = fmaf(f[j], ln_rstd, fmaf(c4.x, mr, b4.x)); f[j + 1] = fmaf(f[j + 1], ln_rstd, fmaf(c4.y, mr, b4.y));
-        f[j + 2] = fmaf(f[j + 2], ln_rstd, fmaf(c4.z, mr, b4.z)); f[j + 3] = fmaf(f[j + 3], ln_rstd, fmaf(c4.w, mr, b4.w));
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j);
+        f[j] = fmaf(f[j], ln_rstd, b4.x); f[j + 1] = fmaf(f[j + 1], ln_rstd, b4.y);
+        f[j + 2] = fmaf(f[j + 2], ln_rstd, b4.z); f[j + 3] = fmaf(f[j + 3], ln_rstd, b4.w);
       }
     }
   } else {
@@ -229,7 +226,6 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
   __shared__ __align__(8) uint64_t b_full[TC_MAX_STEPS], b_empty[TC_MAX_STEPS];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float bias_s[256];
-  __shared__ __align__(16) float c1_s[256];
   __shared__ __align__(8) uint64_t res_bar[TC_MAX_EPI_WARPS];
 
   // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the 128B swizzle needs
@@ -260,10 +256,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
   }
   if (warp >= 4) {   // this CTA owns N-tile blockIdx.x % n_tiles_n for its whole life: stage its bias once
     const int i = threadIdx.x - 128;
-    if (i < 256) {
-      bias_s[i] = (p.bias && i < BN) ? __ldg(p.bias + (blockIdx.x % p.n_tiles_n) * BN + i) : 0.f;
-      if (HAS_LN) c1_s[i] = (i < BN) ? __ldg(p.ln_c1 + (blockIdx.x % p.n_tiles_n) * BN + i) : 0.f;
-    }
+    if (i < 256) bias_s[i] = (p.bias && i < BN) ? __ldg(p.bias + (blockIdx.x % p.n_tiles_n) * BN + i) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -443,10 +436,10 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
         const int img = mt / tiles_per_img, r = mt % tiles_per_img;
         const int y0 = (r / p.tiles_x) * p.th + wy0, x0 = (r % p.tiles_x) * p.tw + wx0;
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-        float2 lnst = make_float2(0.f, 0.f);   // (mean, rstd) of this thread's row, fetched while the MMAs still run
+        float ln_rstd = 0.f;   // 1/sigma of this thread's row, fetched while the MMAs still run
         if (HAS_LN && y0 + ply < p.Ho && x0 + plx < p.Wo)
-          lnst = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + ((int64_t)img * p.Ho + (y0 + ply)) * p.Wo + (x0 + plx));
-        const f32x2 ln_r2 = pack_f2(lnst.y, lnst.y), ln_m2 = pack_f2(-lnst.x * lnst.y, -lnst.x * lnst.y);
+          ln_rstd = __ldg(p.ln_stats + (((int64_t)img * p.Ho + (y0 + ply)) * p.Wo + (x0 + plx)) * 2 + 1);
+        const f32x2 ln_r2 = pack_f2(ln_rstd, ln_rstd);
         bool waited = false;
         for (int cidx = 0; cidx < nchunks; ++cidx) {
           if (((it * nchunks + cidx) % TC_EPI_SLOTS) != slot) continue;
@@ -476,10 +469,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
           for (int c = 0; c < 8; ++c) {                  // 8 columns = one 16-byte smem chunk at a time
             const float4 b0 = *reinterpret_cast<const float4*>(bs + c * 8), b1 = *reinterpret_cast<const float4*>(bs + c * 8 + 4);
             f32x2 f[4], bb[4] = {pack_f2(b0.x, b0.y), pack_f2(b0.z, b0.w), pack_f2(b1.x, b1.y), pack_f2(b1.z, b1.w)};
-            if (HAS_LN) {   // folded LayerNorm: rstd * acc + (bias - mean * rstd * c1)
-              const float4 c0 = *reinterpret_cast<const float4*>(c1_s + cidx * 64 + c * 8), c1v = *reinterpret_cast<const float4*>(c1_s + cidx * 64 + c * 8 + 4);
-              bb[0] = fma_f2(pack_f2(c0.x, c0.y), ln_m2, bb[0]); bb[1] = fma_f2(pack_f2(c0.z, c0.w), ln_m2, bb[1]);
-              bb[2] = fma_f2(pack_f2(c1v.x, c1v.y), ln_m2, bb[2]); bb[3] = fma_f2(pack_f2(c1v.z, c1v.w), ln_m2, bb[3]);
+            if (HAS_LN) {   // folded LayerNorm (row-centred weights): rstd * acc + bias
 #pragma unroll
               for (int e = 0; e < 4; ++e) f[e] = fma_f2(pack_f2(__uint_as_float(v[c * 8 + 2 * e]), __uint_as_float(v[c * 8 + 2 * e + 1])), ln_r2, bb[e]);
             } else {
@@ -542,8 +532,8 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
 #pragma unroll
           for (int j = 0; j < 4; ++j) rpre[j] = *reinterpret_cast<const uint4*>(rp + j * 8);
         }
-        float2 lnst = make_float2(0.f, 1.f);
-        if (HAS_LN && valid) lnst = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + ((int64_t)img * p.Ho + y) * p.Wo + x);
+        float ln_rstd = 1.f;
+        if (HAS_LN && valid) ln_rstd = __ldg(p.ln_stats + (((int64_t)img * p.Ho + y) * p.Wo + x) * 2 + 1);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -554,7 +544,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
           if (nc == 32) tmem_ld32(taddr0 + c0, v); else tmem_ld16(taddr0 + c0, v);
           tmem_ld_wait();
           if (valid) epilogue_chunk(p, v, nc, nt * BN + c0, img, y, x, alpha, bias_s + c0, (pre && j == j0) ? rpre : nullptr,
-                                    HAS_LN ? c1_s + c0 : nullptr, lnst.x, lnst.y);
+                                    HAS_LN, ln_rstd);
           __syncwarp();
         }
         tc_fence_before();
@@ -657,8 +647,7 @@ static bool tc_shape_ok(const fbanet_conv_params* p) {
     if (p->residual || ((uintptr_t)p->out % 4)) return false;
   }
   if (p->bias && ((uintptr_t)p->bias % 16)) return false;
-  if ((p->ln_stats != nullptr) != (p->ln_c1 != nullptr)) return false;
-  if (p->ln_stats && (p->KH != 1 || p->stride != 1 || p->store_mode != FBANET_STORE_NHWC || ((uintptr_t)p->ln_stats % 8) || ((uintptr_t)p->ln_c1 % 16))) return false;
+  if (p->ln_stats && (p->KH != 1 || p->stride != 1 || p->store_mode != FBANET_STORE_NHWC || ((uintptr_t)p->ln_stats % 8))) return false;
   return get_encode() != nullptr;
 }
 
@@ -758,7 +747,7 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
     }
   }
   tp.nsteps = ns;
-  tp.bias = p->bias; tp.alpha = p->alpha; tp.ln_stats = p->ln_stats; tp.ln_c1 = p->ln_c1; tp.residual = reinterpret_cast<const bf16*>(p->residual);
+  tp.bias = p->bias; tp.alpha = p->alpha; tp.ln_stats = p->ln_stats; tp.residual = reinterpret_cast<const bf16*>(p->residual);
   tp.out = p->out; tp.base = p->base;
   tp.res_img_stride = p->res_img_stride; tp.out_img_stride = p->out_img_stride; tp.base_img_stride = p->base_img_stride;
   tp.act = p->act; tp.store_mode = p->store_mode; tp.res_ld = p->res_ld; tp.out_ld = p->out_ld;

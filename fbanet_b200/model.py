@@ -191,8 +191,10 @@ class BaseModel(nn.Module):
         self.gelu_act = {"tanh": L.ACT_GELU_TANH, "erf": L.ACT_GELU_ERF}[gelu]
         self.impl = impl
         self.fuse_leff = True
-        # bf16 path: LayerNorm folded into the qkv / fc1 GEMM epilogues (row statistics only); FBANET_FOLD_LN=0/1 overrides
-        self.fold_ln = os.environ.get("FBANET_FOLD_LN", "1") != "0"
+        # bf16 path, optional: LayerNorm folded into the qkv / fc1 GEMMs (row statistics only; ops.fold_layernorm).  -1.3 ms per
+        # batch-64 step and a lower mean PSNR delta over seeds (0.0043 vs 0.0049 dB), but one of three seeds lands at 0.0105 dB,
+        # 5 % over the 0.01 dB parity tolerance, so it stays off by default; FBANET_FOLD_LN=1 (or the attribute) turns it on.
+        self.fold_ln = os.environ.get("FBANET_FOLD_LN", "0") == "1"
         self.host_chunk = 32       # bursts per pipelined chunk of infer_host (int, or an explicit schedule of chunk sizes)
         self._io_streams = None
         self.host_graphs = True    # infer_host replays CUDA graphs (captured per chunk size) instead of launching eagerly
@@ -313,9 +315,10 @@ class BaseModel(nn.Module):
                     bqkv = torch.cat([f32(a.qkv.to_q.bias) * qs, f32(a.qkv.to_kv.bias)], 0).contiguous()
                     if tc and self.fold_ln:
                         # LayerNorm folded into its consumer GEMMs (ops.fold_layernorm): norm1 -> qkv, norm2 -> fc1
-                        P[k + ".qkv.w"], P[k + ".qkv.b"], P[k + ".qkv.c1"] = ops.fold_layernorm(wqkv, bqkv, ly.norm1.weight, ly.norm1.bias, T)
-                        P[k + ".fc1.w"], P[k + ".fc1.b"], P[k + ".fc1.c1"] = ops.fold_layernorm(
+                        P[k + ".qkv.w"], P[k + ".qkv.b"] = ops.fold_layernorm(wqkv, bqkv, ly.norm1.weight, ly.norm1.bias, T)
+                        P[k + ".fc1.w"], P[k + ".fc1.b"] = ops.fold_layernorm(
                             ly.mlp.linear1[0].weight, ly.mlp.linear1[0].bias, ly.norm2.weight, ly.norm2.bias, T)
+                        P[k + ".ln_folded"] = P[k + ".qkv.b"]   # marker: this layer's LayerNorms live in its GEMMs
                     else:
                         P[k + ".qkv.w"], P[k + ".qkv.b"] = wqkv.to(T).contiguous(), bqkv
                         put_lin(k + ".fc1", ly.mlp.linear1[0])
@@ -339,9 +342,17 @@ class BaseModel(nn.Module):
             P[n + ".w"] = w.view(E, 4, -1).permute(1, 0, 2).reshape(4 * E, -1).contiguous()
             P[n + ".b"] = f32(m.bias).view(E, 4).t().reshape(-1).contiguous()
         put_conv("tail.1", self.tail[1])
-        if tc:  # final conv: GEMM N padded to the tensor-core minimum of 16 columns (zero rows)
-            P["tail.1.w"] = torch.nn.functional.pad(P["tail.1.w"], (0, 0, 0, 16 - self.in_channels)).contiguous()
-            P["tail.1.b"] = torch.nn.functional.pad(P["tail.1.b"], (0, 16 - self.in_channels)).contiguous()
+        if tc:
+            # final conv: GEMM N padded to the tensor-core minimum of 16 columns.  The spare rows carry the LO bf16 halves of the
+            # weights (rows 0..3 hi, rows 4..7 lo, summed by the assembly kernel): its weight rounding error is a fixed,
+            # pixel-independent perturbation that goes straight to the output image, and it is free to remove here.
+            w32 = self.tail[1].weight.detach().float().permute(0, 2, 3, 1).reshape(self.in_channels, -1)
+            hi = w32.to(T)
+            lo = (w32 - hi.float()).to(T)
+            w16 = torch.zeros((16, w32.shape[1]), device=w32.device, dtype=T)
+            w16[: self.in_channels], w16[4: 4 + self.in_channels] = hi, lo
+            P["tail.1.w"] = w16.contiguous()
+            P["tail.1.b"] = torch.nn.functional.pad(f32(self.tail[1].bias), (0, 16 - self.in_channels)).contiguous()
         return P
 
     def _use_tc(self) -> bool:
@@ -383,13 +394,12 @@ class BaseModel(nn.Module):
         w = P[name + ".w"]
         if out is None:
             out = self._new(*x4.shape[:3], w.shape[0])
-        return ops.conv_gemm([x4], w, out, bias=P[name + ".b"], act=act, residual=residual, impl=self.impl,
-                             ln_stats=ln_stats, ln_c1=P[name + ".c1"] if ln_stats is not None else None)
+        return ops.conv_gemm([x4], w, out, bias=P[name + ".b"], act=act, residual=residual, impl=self.impl, ln_stats=ln_stats)
 
     def _layer(self, P, key, ly: _Layer, x, out=None):
         """LeWin block (layers/fba_net.py:139-250 with Appendix A-4): x + Attn(LN1 x); + LeFF(LN2 .)."""
         B, H, W, Cd = x.shape
-        fold = (key + ".qkv.c1") in P   # LayerNorm folded into the consumer GEMM: only per-row statistics are computed here
+        fold = (key + ".ln_folded") in P   # LayerNorm folded into the consumer GEMM: only per-row statistics are computed here
         if fold:
             qkv = self._lin(P, key + ".qkv", x, ln_stats=ops.row_stats(x.view(-1, Cd)))
         else:
@@ -529,10 +539,12 @@ class BaseModel(nn.Module):
         t1 = self._conv3(P, "tail.0.0", [y2], out=self._new(B, 2 * S, 2 * S, E), store=L.STORE_CONVT2)  # :315 (PixelShuffle in the store)
         t2 = self._conv3(P, "tail.0.2", [t1], out=self._new(B, 4 * S, 4 * S, E), store=L.STORE_CONVT2)
         if self._use_tc():
-            # last conv stores channels-last (16 zero-padded columns, 8 kept); the planar fp32 + bilinear-base assembly
-            # is a separate coalesced bandwidth kernel (:315-320)
-            t3 = self._conv3(P, "tail.1", [t2], out=self._new(B, 4 * S, 4 * S, 8), cout_store=8)
-            out = ops.assemble(t3, x[:, 0], Cin)
+            # last conv stores its (few) real columns channels-last in FP32 -- rounding the SR residual to bf16 right before the
+            # base add would be the largest single error of the whole bf16 path; the planar fp32 + bilinear-base assembly is a
+            # separate coalesced bandwidth kernel (:315-320)
+            t3 = torch.empty((B, 4 * S, 4 * S, 8), device=x.device, dtype=torch.float32)   # columns 0..3 hi-weight part, 4..7 lo-weight part
+            self._conv3(P, "tail.1", [t2], out=t3, store=L.STORE_NHWC_F32, cout_store=8)
+            out = ops.assemble(t3, x[:, 0], Cin, lo_offset=4)
         else:
             out = torch.empty((B, Cin, 4 * S, 4 * S), device=x.device, dtype=torch.float32)
             self._conv3(P, "tail.1", [t2], out=out, store=L.STORE_NCHW_BASE, base=x[:, 0], cout_store=Cin)  # :315-320 (+ bilinear x4 base)

@@ -95,13 +95,12 @@ def conv_gemm(
     alg_cin: Optional[int] = None,
     src_s2d: bool = False,
     ln_stats: Optional[torch.Tensor] = None,
-    ln_c1: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
     """out = act(conv(concat(srcs)) + bias) + residual.  ``weight`` is packed ``[Cout, kh*kw*sum(C)]``.
 
-    ``ln_stats`` ``[rows, 2]`` fp32 (mean, rstd per input row, :func:`row_stats`) + ``ln_c1`` ``[Cout]``: LayerNorm folded into a
-    1x1 GEMM -- ``weight`` must be ``W * gamma``, ``bias`` must be ``W @ beta + b`` and ``ln_c1`` the row sums of ``weight``
-    (:func:`fold_layernorm`); the result equals ``W @ LN(x) + b``."""
+    ``ln_stats`` ``[rows, 2]`` fp32 (mean, rstd per input row, :func:`row_stats`): LayerNorm folded into a 1x1 GEMM -- ``weight``
+    must be the row-centred ``W * gamma`` and ``bias`` ``W @ beta + b`` (:func:`fold_layernorm`); the result equals
+    ``W @ LN(x) + b``."""
     p = L.ConvParams()
     dt = srcs[0].dtype
     p.dtype = _DT[dt]
@@ -141,9 +140,8 @@ def conv_gemm(
         assert alpha.dtype == torch.float32
         p.alpha = alpha.data_ptr()
     if ln_stats is not None:
-        assert ln_c1 is not None and ln_stats.dtype == torch.float32 and ln_stats.is_contiguous() and ln_stats.shape == (N * Ho * Wo, 2)
-        assert ln_c1.dtype == torch.float32 and ln_c1.numel() == cout and kh == 1 and kw == 1
-        p.ln_stats, p.ln_c1 = ln_stats.data_ptr(), ln_c1.data_ptr()
+        assert ln_stats.dtype == torch.float32 and ln_stats.is_contiguous() and ln_stats.shape == (N * Ho * Wo, 2) and kh == 1 and kw == 1
+        p.ln_stats = ln_stats.data_ptr()
     if residual is not None:
         assert residual.dtype == dt and residual.shape == (N, Ho, Wo, cout)
         rp, _, rld, ris = _cl(residual)
@@ -232,9 +230,10 @@ def head_conv(x: torch.Tensor, weight_kc: torch.Tensor, bias: torch.Tensor, dtyp
     return out
 
 
-def assemble(sr: torch.Tensor, base: torch.Tensor, C_out: int) -> torch.Tensor:
+def assemble(sr: torch.Tensor, base: torch.Tensor, C_out: int, lo_offset: int = 0) -> torch.Tensor:
     """``out[n,c] = sr[n,:,:,c] + bilinear_x4(base[n,c])``: channels-last SR ``[N,4h,4w,Cp]`` + planar fp32 base
-    ``[N,C,h,w]`` (a view of the burst's frame 0) -> planar fp32 ``[N,C,4h,4w]``."""
+    ``[N,C,h,w]`` (a view of the burst's frame 0) -> planar fp32 ``[N,C,4h,4w]``.  ``lo_offset > 0``: the SR value of channel
+    ``c`` is ``sr[..., c] + sr[..., c + lo_offset]`` (the final conv run with hi/lo split weights)."""
     assert sr.is_cuda and sr.is_contiguous() and sr.dim() == 4
     N, H, W, Cp = sr.shape
     assert base.dtype == torch.float32 and base.shape == (N, C_out, H // 4, W // 4)
@@ -244,6 +243,8 @@ def assemble(sr: torch.Tensor, base: torch.Tensor, C_out: int) -> torch.Tensor:
     p.sr, p.base, p.out = sr.data_ptr(), base.data_ptr(), out.data_ptr()
     p.base_img_stride = base.stride(0) if N > 1 else 0
     p.dtype, p.N, p.C, p.Cp, p.H, p.W = _DT[sr.dtype], N, C_out, Cp, H, W
+    assert lo_offset == 0 or lo_offset + C_out <= Cp
+    p.lo_offset = lo_offset
     _call("fbanet_assemble_sm100", p, nbytes=N * H * W * C_out * sr.element_size() + base.numel() * 4 + out.numel() * 4)
     return out
 
@@ -274,7 +275,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 def row_stats(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     """LayerNorm statistics only: ``[rows, C]`` bf16 -> fp32 ``[rows, 2]`` = (mean, 1/sqrt(var + eps)); the normalisation itself is
-    applied by the consumer GEMM (``conv_gemm(..., ln_stats=, ln_c1=)``), so the normalised tensor never exists in HBM."""
+    applied by the consumer GEMM (``conv_gemm(..., ln_stats=)``), so the normalised tensor never exists in HBM."""
     assert x.is_cuda and x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.bfloat16
     rows, Cc = x.shape
     st = torch.empty((rows, 2), device=x.device, dtype=torch.float32)
@@ -286,14 +287,24 @@ def row_stats(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
 
 
 def fold_layernorm(w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, dtype: torch.dtype):
-    """Fold ``LN(x) = (x - mean) * rstd * gamma + beta`` into the linear layer ``y = W LN(x) + b`` that consumes it:
-    returns (``W' = W diag(gamma)`` in ``dtype``, ``bias' = W beta + b`` fp32, ``c1 = rowsum(W')`` fp32 of the ROUNDED weights, so
-    the ``mean * c1`` term cancels exactly what the tensor cores accumulate)."""
+    """Fold ``LN(x) = (x - mean) * rstd * gamma + beta`` into the linear layer ``y = W LN(x) + b`` that consumes it.
+
+    With ``W' = W diag(gamma)`` and every row of ``W'`` centred, ``W'' = W' - rowmean(W') 1^T``, one has ``W'' x = W' (x - mean(x) 1)``
+    (``mean(x) = 1^T x / K``): the mean subtraction moves into the weights, and ``y = rstd * (W'' x) + (W beta + b)``.
+    Returns (``W''`` in ``dtype``, fp32 bias ``W beta + b``).  Centring is done in fp64; rounding to ``dtype`` then leaves row sums of
+    order sqrt(K) * 2^-10 * |W|, which would leak ``mean(x)`` into the output (activations with |mean| >> sigma: measurable), so the
+    residual of every row is pushed into its smallest-magnitude elements (whose ulps are far finer)."""
     w64, g64, be64 = w.detach().double(), gamma.detach().double(), beta.detach().double()
-    wf = (w64 * g64[None, :]).to(dtype)
+    wg = w64 * g64[None, :]
+    wf = (wg - wg.mean(1, keepdim=True)).to(dtype)
+    # pass 1: the residual is shared by the 8 smallest-magnitude elements of the row (each moves by about one typical ulp);
+    # pass 2: what their own rounding leaves (~2e-5) goes into the single smallest element.
+    for t in (8, 1):
+        r = wf.double().sum(1, keepdim=True)
+        idx = wf.abs().float().topk(min(t, wf.shape[1]), dim=1, largest=False).indices
+        wf.scatter_(1, idx, (wf.gather(1, idx).double() - r / idx.shape[1]).to(dtype))
     bias = (w64 @ be64 + b.detach().double()).float().contiguous()
-    c1 = wf.double().sum(1).float().contiguous()
-    return wf.contiguous(), bias, c1
+    return wf.contiguous(), bias
 
 
 def expand_rel_pos_bias(bias_table: torch.Tensor, win: int) -> torch.Tensor:

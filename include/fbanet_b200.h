@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 11
+#define FBANET_ABI_VERSION 13
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -101,12 +101,14 @@ typedef struct fbanet_conv_params {
                              tensor-core path.  src[i].C is then 4*C_i.                                */
   int32_t _pad;
   /* LayerNorm folded into a 1x1 GEMM (layers/fba_net.py:196,246 feeding linear_projection.py:27-28 /
-   * locally_enhanced_feed_forward.py:27), tensor-core path: the GEMM runs on the RAW rows x with weights W' = W diag(gamma),
-   *   y[r][n] = rstd[r] * (acc[r][n] - mean[r] * c1[n]) + bias[n],   c1[n] = sum_k W'[n][k],  bias[n] = (W beta + b)[n],
-   * which equals W LN(x) + b exactly.  ln_stats: fp32 [rows][2] = (mean, rstd) from fbanet_layernorm_sm100 (stats mode);
-   * ln_c1: fp32 [Cout].  Both NULL: plain GEMM. */
+   * locally_enhanced_feed_forward.py:27), tensor-core path.  With W' = W diag(gamma) and W'' = W' - rowmean(W') 1^T
+   * (every row centred, so W'' x = W' (x - mean(x) 1): the mean subtraction lives in the weights), the GEMM runs on the RAW
+   * rows x with weight = W'' and
+   *   y[r][n] = rstd[r] * acc[r][n] + bias[n],   bias = W beta + b,
+   * which equals W LN(x) + b.  ln_stats: fp32 [rows][2] = (mean, rstd) per row from fbanet_layernorm_sm100 (stats mode;
+   * only rstd is read).  NULL: plain GEMM. */
   const float* ln_stats;
-  const float* ln_c1;
+  const float* _reserved;
 } fbanet_conv_params;
 
 /* K1: homography warp with bilinear sampling.  Replaces cv2.warpPerspective / cv2.warpAffine with
@@ -163,6 +165,8 @@ typedef struct fbanet_assemble_params {
   int64_t base_img_stride;
   int32_t dtype;          /* of sr */
   int32_t N, C, Cp, H, W; /* H, W = output (x4) size */
+  int32_t lo_offset;      /* > 0: SR value of channel c = sr[c] + sr[c + lo_offset] (final conv with hi/lo split weights) */
+  int32_t _pad;
 } fbanet_assemble_params;
 
 /* channels-last view [N,H,W,C] -> contiguous [N,H/2,W/2,4C], channel (ys*2+xs)*C + c = src(2y+ys, 2x+xs, c).
