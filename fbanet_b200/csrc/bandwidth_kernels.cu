@@ -352,42 +352,49 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const fbanet_layernorm_p
   }
 }
 
-// K8 (bf16 fast path): C/8 threads per token, one 16-byte load/store per thread, xor-shuffle reductions
-template <int C>
+// K8 (bf16 fast path): C/8 threads per token, RPT tokens per thread group (their 16-byte loads are all issued before the first
+// reduction: one load in flight per thread left the kernel at 4.6 TB/s), xor-shuffle reductions, one 16-byte store per token.
+template <int C, int RPT>
 __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const fbanet_layernorm_params p) {
   constexpr int TPT = C / 8;  // threads per token (8, 16 or 32)
   const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t row = gt / TPT;
+  const int64_t grp = gt / TPT;
   const int sub = (int)(gt % TPT);
-  const bool ok = row < p.rows;  // rows padded to a whole warp: keep all lanes alive for the shuffles
-  float v[8];
-  if (ok) load_vec<bf16, 8>(reinterpret_cast<const bf16*>(p.x) + row * p.x_ld + sub * 8, v);
-  else {
+  float v[RPT][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  for (int r = 0; r < RPT; ++r) {
+    const int64_t row = grp * RPT + r;   // rows padded to a whole group: keep all lanes alive for the shuffles
+    if (row < p.rows) load_vec<bf16, 8>(reinterpret_cast<const bf16*>(p.x) + row * p.x_ld + sub * 8, v[r]);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[r][i] = 0.f;
+    }
   }
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s += v[i];
-#pragma unroll
-  for (int o = TPT / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s * (1.0f / C);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q += d * d; }
-#pragma unroll
-  for (int o = TPT / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q * (1.0f / C) + p.eps);
-  if (!ok) return;
-  if (p.stats && sub == 0) *reinterpret_cast<float2*>(p.stats + row * 2) = make_float2(mean, rstd);
-  if (!p.y) return;   // statistics only: the consumer GEMM applies the normalisation in its epilogue
   const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + sub * 8)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + sub * 8 + 4));
   const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + sub * 8)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + sub * 8 + 4));
   const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-  float o8[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o8[i] = (v[i] - mean) * rstd * gg[i] + bb[i];
-  store_vec<bf16, 8>(reinterpret_cast<bf16*>(p.y) + row * p.y_ld + sub * 8, o8);
+  for (int r = 0; r < RPT; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[r][i];
+#pragma unroll
+    for (int o = TPT / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = v[r][i] - mean; q += d * d; }
+#pragma unroll
+    for (int o = TPT / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.0f / C) + p.eps);
+    const int64_t row = grp * RPT + r;
+    if (row >= p.rows) continue;
+    if (p.stats && sub == 0) *reinterpret_cast<float2*>(p.stats + row * 2) = make_float2(mean, rstd);
+    float o8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o8[i] = (v[r][i] - mean) * rstd * gg[i] + bb[i];
+    store_vec<bf16, 8>(reinterpret_cast<bf16*>(p.y) + row * p.y_ld + sub * 8, o8);
+  }
 }
 
 // LayerNorm statistics only (bf16): C/8 threads per row, RPT rows per thread group in flight (a read-only kernel needs
@@ -891,9 +898,13 @@ extern "C" int fbanet_layernorm_sm100(const fbanet_layernorm_params* p, void* st
       else rowstats_bf16_kernel<256, RPT><<<ceil_div(groups * 32, 256), 256, 0, st>>>(*p);
       return check_launch();
     }
-    if (fast && p->C == 64) { layernorm_bf16_kernel<64><<<ceil_div(p->rows * 8, 256), 256, 0, st>>>(*p); return check_launch(); }
-    if (fast && p->C == 128) { layernorm_bf16_kernel<128><<<ceil_div(p->rows * 16, 256), 256, 0, st>>>(*p); return check_launch(); }
-    if (fast && p->C == 256) { layernorm_bf16_kernel<256><<<ceil_div(p->rows * 32, 256), 256, 0, st>>>(*p); return check_launch(); }
+    {
+      constexpr int RPT = 2;
+      const int64_t groups = (p->rows + RPT - 1) / RPT;
+      if (fast && p->C == 64) { layernorm_bf16_kernel<64, RPT><<<ceil_div(groups * 8, 256), 256, 0, st>>>(*p); return check_launch(); }
+      if (fast && p->C == 128) { layernorm_bf16_kernel<128, RPT><<<ceil_div(groups * 16, 256), 256, 0, st>>>(*p); return check_launch(); }
+      if (fast && p->C == 256) { layernorm_bf16_kernel<256, 1><<<ceil_div(p->rows * 32, 256), 256, 0, st>>>(*p); return check_launch(); }   // a full warp per row already
+    }
     return launch_ln<bf16>(p, st);
   }
   return FBANET_E_DTYPE;
