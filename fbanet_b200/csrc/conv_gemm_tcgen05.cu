@@ -66,6 +66,9 @@ struct TcParams {
   int b_slots, b_resident;
   int tma_store;          // 1: each epilogue warp stages 32x64 bf16 sub-tiles in smem and stores them with TMA
   int stage_bufs;         // staging buffers per epilogue warp (2, or 1 when shared memory is tight)
+  int nacc, nacc_shift;   // accumulator stages in TMEM (4 when 4 x BN <= 512 columns, else 2) and log2 of it
+  int debug;              // FBANET_TC_DEBUG timing experiments (results are garbage): 1 = epilogue only hands the accumulator back,
+                          // 2 = no tcgen05.mma issued (commits only), 4 = A producer arrives without loading
 };
 
 template <int NV>
@@ -186,27 +189,66 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
   }
 }
 
-// Issue the MMAs of one A slot (TAPS K-steps x 4 tcgen05.mma), fully unrolled so that descriptor offsets are
-// immediates.  Called by the elected lane only.  HALO: tap t reads copy (t%3), ky = t/3 rows down.
-// HALO: 0 = plain A tile, 1 = three dx-shifted copies, 2 = wide box + base offset, 3 = wide box, base offset 0
+// The MMA issuer's loop for resident weights, one instantiation per A layout.
+// HALO: 0 = plain A tile (one K-step per slot), 1 = three dx-shifted halo copies (tap (ky,kx) = copy kx, ky rows of 1 KB down),
+// 3 = one wide halo box (tap starts at byte ky*2048 + (3+kx)*128, 2 KB between 8-row atoms, descriptor base offset 0).
+// Everything the loop needs is passed in registers, barriers as raw shared addresses, and the taps are a ROLLED loop whose
+// operand addresses advance by constants: measured on the 64->64 body conv and the N = 16 final conv (ncu source view,
+// tools/prof_bound.py), the issuing warp spent ~500 cycles per tile outside the tcgen05.mma instructions -- first in LDCU
+// (kernel parameter) -> branch chains and generic->shared conversions, then, with the 36 MMAs unrolled, in ~150 uniform-register
+// instructions (with spills) that ptxas hoisted in front of the first MMA to precompute all 72 descriptors.  That is longer than
+// the work the tcgen05 queue holds, so the tensor pipe ran dry once per tile (43 % active on the body conv where
+// tools/ubench/umma.cu gives 57-64 % as the N = 64 ceiling).
 template <int TAPS, int HALO>
-__device__ __forceinline__ void issue_unit_resident(const uint32_t tmem_d, const uint32_t idesc, const uint64_t desc_hi, const uint64_t desc_wide,
-                                                    const uint32_t a_lo, uint32_t b_lo, const uint32_t b_step_lo, const bool first_unit) {
+__device__ __forceinline__ void mma_loop_resident(const int mt0, const int mt_step, const int m_tiles, const int units, const int a_slots,
+                                                  const uint32_t a_slot16, const uint32_t sa16_0, const uint32_t sb16_0, const uint32_t bstep16,
+                                                  const uint32_t tmem_base, const uint32_t BN, const uint32_t idesc, const uint32_t bar_af,
+                                                  const uint32_t bar_ae, const uint32_t bar_tf, const uint32_t bar_te, const bool nomma, const uint32_t nacc_mask,
+                                                  const uint32_t nacc_shift) {
+  const uint64_t desc_b = make_sw128_desc(0);        // descriptor with a zero start address
+  const uint64_t desc_a = HALO >= 2 ? ((desc_b & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)(TC_HALO_WROW >> 4) << 32)) : desc_b;   // wide: 2 KB between atoms
+  constexpr uint32_t A_START = HALO >= 2 ? (3u * 128u) >> 4 : 0u;
+  constexpr uint32_t A_KX = HALO == 1 ? (uint32_t)TC_HALO_COPY >> 4 : (HALO >= 2 ? 128u >> 4 : 0u);                 // next tap in the row
+  int aslot = 0;
+  uint32_t aphase = 0, sa16 = sa16_0;
+  int it = 0;
+  for (int mt = mt0; mt < m_tiles; mt += mt_step, ++it) {
+    const uint32_t acc = (uint32_t)it & nacc_mask;
+    mbar_wait_a(bar_te + acc * 8u, (((uint32_t)it >> nacc_shift) & 1u) ^ 1u);     // epilogue has drained this accumulator
+    const uint32_t tmem_d = tmem_base + acc * BN;
+    uint32_t b16 = sb16_0;
+    for (int u = 0; u < units; ++u) {
+      mbar_wait_a(bar_af + (uint32_t)aslot * 8u, aphase);
+      tc_fence_after();
+      uint32_t at = sa16 + A_START;
+      int kx = 0;
+#pragma unroll 1
+      for (int t = 0; t < TAPS; ++t) {
+        if (elect_one() && !nomma) {
+          const uint32_t first = (u == 0 && t == 0) ? 0u : 1u;
 #pragma unroll
-  for (int t = 0; t < TAPS; ++t) {
-    uint32_t at = a_lo;
-    uint64_t dA = desc_hi;
-    if (HALO == 1) at += (uint32_t)(((t % 3) * TC_HALO_COPY + (t / 3) * 1024) >> 4);
-    if (HALO >= 2) {
-      at += (uint32_t)(((t / 3) * TC_HALO_WROW + (3 + t % 3) * 128) >> 4);
-      dA = desc_wide + (HALO == 2 ? ((uint64_t)((3 + t % 3) & 7) << 49) : 0ull);
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16(tmem_d, desc_a + (uint64_t)(at + 2 * k), desc_b + (uint64_t)(b16 + 2 * k), idesc, k == 0 ? first : 1u);
+        }
+        __syncwarp();
+        b16 += bstep16;
+        if (TAPS > 1) {   // next tap: one step along the row, or back to its start and one image row down
+          if (++kx < 3) at += A_KX;
+          else {
+            kx = 0;
+            if (HALO == 1) at += (uint32_t)(1024 >> 4) - 2u * ((uint32_t)TC_HALO_COPY >> 4);
+            else at += ((uint32_t)TC_HALO_WROW >> 4) - 2u * (128u >> 4);
+          }
+        }
+      }
+      if (elect_one()) {
+        umma_commit_a(bar_ae + (uint32_t)aslot * 8u);                     // frees the A slot when these MMAs retire
+        if (u == units - 1) umma_commit_a(bar_tf + acc * 8u);             // accumulator ready for the epilogue
+      }
+      __syncwarp();
+      sa16 += a_slot16;
+      if (++aslot == a_slots) { aslot = 0; aphase ^= 1u; sa16 = sa16_0; }
     }
-#pragma unroll
-    for (int k = 0; k < TC_BK / 16; ++k) {
-      const uint32_t accum = (t == 0 && k == 0) ? (first_unit ? 0u : 1u) : 1u;
-      umma_bf16(tmem_d, dA + (uint64_t)(at + 2 * k), desc_hi + (uint64_t)(b_lo + 2 * k), idesc, accum);
-    }
-    b_lo += b_step_lo;
   }
 }
 
@@ -222,7 +264,7 @@ template <bool HAS_LN, int TC_EPI_SLOTS>
 __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   constexpr int TC_EPI_WARPS = 4 * TC_EPI_SLOTS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t a_full[TC_MAX_A_SLOTS], a_empty[TC_MAX_A_SLOTS], tmem_full[2], tmem_empty[2];
+  __shared__ __align__(8) uint64_t a_full[TC_MAX_A_SLOTS], a_empty[TC_MAX_A_SLOTS], tmem_full[4], tmem_empty[4];
   __shared__ __align__(8) uint64_t b_full[TC_MAX_STEPS], b_empty[TC_MAX_STEPS];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float bias_s[256];
@@ -236,7 +278,9 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)p.a_slots * p.a_slot_bytes;
   uint8_t* smem_stage = smem_b + (size_t)p.b_slots * b_bytes;   // TC_EPI_WARPS x stage_bufs x 4 KB staging sub-tiles
-  const uint32_t tmem_cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  const int acc_cols = p.nacc * BN;
+  const uint32_t tmem_cols = (acc_cols <= 32) ? 32 : (acc_cols <= 64 ? 64 : (acc_cols <= 128 ? 128 : (acc_cols <= 256 ? 256 : 512)));
+  const int nacc_mask = p.nacc - 1, nacc_shift = p.nacc_shift;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < TC_MAX_SRC; ++s) tma_prefetch_desc(&p.amap[s]);
@@ -246,7 +290,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.a_slots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.b_slots; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], TC_EPI_WARPS); }
+    for (int a = 0; a < 4; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], TC_EPI_WARPS); }
     for (int a = 0; a < TC_EPI_WARPS; ++a) mbar_init(&res_bar[a], 1);
     fence_barrier_init();
   }
@@ -280,7 +324,9 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
       const int y0 = (r / p.tiles_x) * p.th, x0 = (r % p.tiles_x) * p.tw;
       for (int u = 0; u < units; ++u) {
         mbar_wait(&a_empty[slot], phase ^ 1);
-        if (elect_one()) {
+        if (p.debug & 4) {
+          if (elect_one()) mbar_arrive(&a_full[slot]);
+        } else if (elect_one()) {
           uint8_t* sa = smem_a + (size_t)slot * p.a_slot_bytes;
           if (p.halo) {
             const Chunk ch = p.chunks[u];
@@ -343,42 +389,38 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
     const uint32_t bmask = (uint32_t)p.b_slots - 1, bshift = (uint32_t)__ffs(p.b_slots) - 1;
     int aslot = 0;
     uint32_t aphase = 0, gs = 0;                       // gs = B slabs consumed so far (ring mode)
-    bool b_landed = false;                             // resident weights: waited for once
     int it = 0;
+    if (p.b_resident) {
+      if (mt0 < p.m_tiles)
+        for (int s = 0; s < p.nsteps; ++s) mbar_wait(&b_full[s], 0);
+      const int halo = p.halo, a_slots = p.a_slots, m_tiles = p.m_tiles;
+      const uint32_t a_slot16 = (uint32_t)p.a_slot_bytes >> 4;
+      const bool nomma = (p.debug & 2) != 0;
+      const uint32_t bar_af = smem_u32(&a_full[0]), bar_ae = smem_u32(&a_empty[0]), bar_tf = smem_u32(&tmem_full[0]), bar_te = smem_u32(&tmem_empty[0]);
+#define FBANET_MMA_LOOP(T, H) \
+  mma_loop_resident<T, H>(mt0, mt_step, m_tiles, units, a_slots, a_slot16, sa0 >> 4, sb0 >> 4, b_bytes >> 4, tmem_base, (uint32_t)BN, idesc, bar_af, bar_ae, bar_tf, bar_te, nomma, (uint32_t)nacc_mask, (uint32_t)nacc_shift)
+      if (halo == 0) FBANET_MMA_LOOP(1, 0);
+      else if (halo == 1) FBANET_MMA_LOOP(9, 1);
+      else if (halo == 3) FBANET_MMA_LOOP(9, 3);
+      // (halo mode 2, descriptor base offset = row phase, was the experiment that proved the swizzle address based: the launcher rejects it)
+#undef FBANET_MMA_LOOP
+    } else {
     for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = it & nacc_mask;
+      const uint32_t acc_phase = (it >> nacc_shift) & 1;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);     // epilogue has drained this accumulator
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
       for (int u = 0; u < units; ++u) {
         mbar_wait(&a_full[aslot], aphase);
-        if (p.b_resident && !b_landed)
-          for (int t = 0; t < taps; ++t) mbar_wait(&b_full[u * taps + t], 0);
         tc_fence_after();
         const uint32_t sa = sa0 + (uint32_t)aslot * (uint32_t)p.a_slot_bytes;
-        if (p.b_resident) {
-          // resident weights: straight-line issue with immediate descriptor offsets
-          if (elect_one()) {
-            const uint32_t b_lo = (sb0 + (uint32_t)(u * taps) * b_bytes) >> 4;
-            if (p.halo == 1) issue_unit_resident<9, 1>(tmem_d, idesc, desc_hi, desc_wide, sa >> 4, b_lo, b_bytes >> 4, u == 0);
-            else if (p.halo == 2) issue_unit_resident<9, 2>(tmem_d, idesc, desc_hi, desc_wide, sa >> 4, b_lo, b_bytes >> 4, u == 0);
-            else if (p.halo == 3) issue_unit_resident<9, 3>(tmem_d, idesc, desc_hi, desc_wide, sa >> 4, b_lo, b_bytes >> 4, u == 0);
-            else issue_unit_resident<1, 0>(tmem_d, idesc, desc_hi, desc_wide, sa >> 4, b_lo, b_bytes >> 4, u == 0);
-            umma_commit(&a_empty[aslot]);
-            if (u == units - 1) umma_commit(&tmem_full[acc]);
-          }
-        } else if (elect_one()) {
+        if (elect_one()) {
           for (int t = 0; t < taps; ++t) {
             const int s = u * taps + t;
-            uint32_t sb;
-            if (p.b_resident) {
-              sb = sb0 + (uint32_t)s * b_bytes;
-            } else {
-              const uint32_t g = gs + (uint32_t)t, slot = g & bmask;
-              mbar_wait(&b_full[slot], (g >> bshift) & 1);
-              tc_fence_after();
-              sb = sb0 + slot * b_bytes;
-            }
+            const uint32_t g = gs + (uint32_t)t, slot = g & bmask;
+            mbar_wait(&b_full[slot], (g >> bshift) & 1);
+            tc_fence_after();
+            const uint32_t sb = sb0 + slot * b_bytes;
             // halo mode: tap (ky,kx) reads the dx-shifted copy kx, starting ky rows (1 KB each) down
             uint32_t a_addr = sa;
             uint64_t dA = desc_hi;
@@ -390,8 +432,8 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
             const uint64_t adesc = dA + (uint64_t)(a_addr >> 4), bdesc = desc_hi + (uint64_t)(sb >> 4);
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k)       // advance 32 bytes (16 bf16) inside the swizzle row
-              umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((s | k) != 0));
-            if (!p.b_resident) umma_commit(&b_empty[(gs + (uint32_t)t) & bmask]);
+              if (!(p.debug & 2)) umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((s | k) != 0));
+            umma_commit(&b_empty[slot]);
           }
           umma_commit(&a_empty[aslot]);                             // frees the A slot when these MMAs retire
           if (u == units - 1) umma_commit(&tmem_full[acc]);         // accumulator ready for the epilogue
@@ -400,7 +442,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
         gs += (uint32_t)taps;
         if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
       }
-      b_landed = true;
+    }
     }
   } else if (warp >= 4) {
     // ================= epilogue: 4 TMEM lane quarters x TC_EPI_SLOTS warps; column pieces are dealt round-robin to the slots =================
@@ -410,7 +452,15 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
     const int ly = row / p.tw, lx = row - ly * p.tw;
     const float alpha = (p.act == FBANET_ACT_PRELU) ? __ldg(p.alpha) : 0.f;
     int it = 0;
-    if (p.tma_store) {
+    if (p.debug & 1) {
+      for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
+        mbar_wait(&tmem_full[it & nacc_mask], (it >> nacc_shift) & 1);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[it & nacc_mask]);
+      }
+    } else if (p.tma_store) {
       // ---- per-warp staged epilogue.  A warp owns 32 pixel rows of the tile (its TMEM lane quarter), which form a
       // rectangle {bw, 32/bw} of the output image, so it can stage and TMA-store its own 32 x 64-column sub-tiles (4 KB,
       // SWIZZLE_128B) with no CTA-level barrier at all: tcgen05.ld -> bias/act(/residual) -> st.shared -> fence ->
@@ -431,8 +481,8 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
       const int ply = lane / bw, plx = lane - ply * bw;         // this thread's pixel inside the rectangle
       uint32_t res_phase = 0, nb = 0;
       for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
+        const int acc = it & nacc_mask;
+        const uint32_t acc_phase = (it >> nacc_shift) & 1;
         const int img = mt / tiles_per_img, r = mt % tiles_per_img;
         const int y0 = (r / p.tiles_x) * p.th + wy0, x0 = (r % p.tiles_x) * p.tw + wx0;
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -518,8 +568,8 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
     } else {
       const int npieces = BN >= 32 ? BN / 32 : 1;      // 32-column pieces (one 16-column piece for BN = 16)
       for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
+        const int acc = it & nacc_mask;
+        const uint32_t acc_phase = (it >> nacc_shift) & 1;
         const int img = mt / tiles_per_img, r = mt % tiles_per_img;
         const int y = (r / p.tiles_x) * p.th + ly, x = (r % p.tiles_x) * p.tw + lx;
         const bool valid = (ly < p.th) && (y < p.Ho) && (x < p.Wo);
@@ -679,7 +729,7 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   // The hardware swizzle is purely address based: base-offset 0 (mode 3) is the correct descriptor, mode 2 computes garbage.
   static const char* henv = getenv("FBANET_TC_HALO");   // experiment switch: 1 = three dx-shifted copies, 3 = one wide box
   const int halo_mode = halo ? (henv ? atoi(henv) : (tp.BN == 64 ? 1 : 3)) : 0;
-  if (halo && (halo_mode < 1 || halo_mode > 3)) return FBANET_E_UNSUPPORTED;
+  if (halo && halo_mode != 1 && halo_mode != 3) return FBANET_E_UNSUPPORTED;
   tp.halo = halo_mode;
 
   int ctot = 0;
@@ -833,6 +883,12 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
     }
   }
   tp.b_resident = p0.resident; tp.a_slots = p0.a_slots; tp.b_slots = p0.b_slots;
+  { const char* dbg = getenv("FBANET_TC_DEBUG"); tp.debug = dbg ? atoi(dbg) : 0; }
+  // accumulator stages in TMEM.  Four (N tiles up to 128) were measured against two on every layer shape and change nothing:
+  // the gap between "MMA-only" (1.55 ms) + "epilogue-only" (1.28 ms) and both together (1.77 ms) on the 64->64 body conv is not
+  // the two-deep accumulator hand-off (tools/prof_bound.py; the chip is power capped, every active unit costs clock).  Kept as
+  // an experiment switch: FBANET_TC_NACC=4.
+  { const char* na = getenv("FBANET_TC_NACC"); tp.nacc = (4 * tp.BN <= 512 && na && na[0] == '4') ? 4 : 2; tp.nacc_shift = tp.nacc == 4 ? 2 : 1; }
   const size_t smem = (size_t)tp.a_slots * tp.a_slot_bytes + (size_t)tp.b_slots * b_bytes + stage_bytes + 1024;
 
   static size_t smem_opted_in = 0;  // opt-in limit is per function; raise it only when a launch needs more
