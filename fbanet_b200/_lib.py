@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBANET_B200_LIB") or os.path.join(_HERE, "csrc", "libfbanet_b200.so")   # env override: A/B two builds in one process tree
-ABI_VERSION = 13
+ABI_VERSION = 14
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -132,10 +132,32 @@ class TileParams(C.Structure):
     ]
 
 
+MAX_BANDS = 8
+
+
+class TileBandParams(C.Structure):
+    _fields_ = [
+        ("band", C.c_void_p * MAX_BANDS), ("tiles", C.c_void_p), ("row0", C.c_int32 * (MAX_BANDS + 1)), ("nbands", C.c_int32),
+        ("T", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("psize", C.c_int32), ("overlap", C.c_int32), ("tile_begin", C.c_int32), ("tile_end", C.c_int32),
+        ("scale", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
+class FlowWarpParams(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("dst", C.c_void_p), ("flow", C.c_void_p),
+        ("s_frame", C.c_int64), ("s_y", C.c_int64), ("s_x", C.c_int64), ("s_c", C.c_int64),
+        ("d_frame", C.c_int64), ("d_y", C.c_int64), ("d_x", C.c_int64), ("d_c", C.c_int64),
+        ("frames", C.c_int32), ("frames_per_burst", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
 STRUCTS = {
     "fbanet_src": Src, "fbanet_conv_params": ConvParams, "fbanet_warp_params": WarpParams,
     "fbanet_to_nhwc_params": ToNhwcParams, "fbanet_s2d_params": S2dParams, "fbanet_head_conv_params": HeadConvParams, "fbanet_assemble_params": AssembleParams, "fbanet_layernorm_params": LayerNormParams, "fbanet_attn_params": AttnParams,
     "fbanet_dwconv_params": DwconvParams, "fbanet_faf_gate_params": FafGateParams, "fbanet_leff_fc2_params": LeffFc2Params, "fbanet_tile_params": TileParams,
+    "fbanet_tile_band_params": TileBandParams, "fbanet_flow_warp_params": FlowWarpParams,
 }
 
 # every symbol include/fbanet_b200.h declares
@@ -143,6 +165,7 @@ OPS = {
     "fbanet_warp_sm100": WarpParams, "fbanet_to_nhwc_sm100": ToNhwcParams, "fbanet_space_to_depth_sm100": S2dParams, "fbanet_head_conv_sm100": HeadConvParams, "fbanet_assemble_sm100": AssembleParams, "fbanet_conv_gemm_sm100": ConvParams,
     "fbanet_layernorm_sm100": LayerNormParams, "fbanet_window_attention_sm100": AttnParams, "fbanet_dwconv3x3_sm100": DwconvParams,
     "fbanet_faf_gate_sm100": FafGateParams, "fbanet_leff_fc2_sm100": LeffFc2Params, "fbanet_tile_divide_sm100": TileParams, "fbanet_tile_merge_sm100": TileParams,
+    "fbanet_tile_divide_banded_sm100": TileBandParams, "fbanet_tile_merge_banded_sm100": TileBandParams, "fbanet_flow_warp_sm100": FlowWarpParams,
 }
 MISC_SYMBOLS = ["fbanet_abi_version", "fbanet_abi_sizeof", "fbanet_last_cuda_error", "fbanet_conv_gemm_tcgen05_supported", "fbanet_leff_fc2_supported"]
 

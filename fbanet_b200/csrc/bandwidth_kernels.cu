@@ -855,6 +855,114 @@ __global__ void __launch_bounds__(256) tile_merge_kernel(const fbanet_tile_param
   }
 }
 
+// ---- row-band variants (cfg4 on several GPUs): the source / destination image is a set of row bands, band k possibly in a peer
+// GPU's memory.  A tile row that crosses a band boundary is read from (written to) the neighbour over NVLink by plain loads
+// (stores): the halo exchange is part of the gather, no staging copy and no collective.
+__device__ __forceinline__ int band_of(const fbanet_tile_band_params& p, int y) {
+  int k = 0;
+#pragma unroll
+  for (int b = 1; b < FBANET_MAX_BANDS; ++b) k += (b < p.nbands && y >= p.row0[b]) ? 1 : 0;
+  return k;
+}
+
+__global__ void __launch_bounds__(256) tile_divide_banded_kernel(const fbanet_tile_band_params p) {
+  const int ts = p.psize + 2 * p.overlap;
+  const int Hp = (p.H + p.psize - 1) / p.psize * p.psize, Wp = (p.W + p.psize - 1) / p.psize * p.psize;
+  const int nwt = Wp / p.psize;
+  const int64_t per_tile = (int64_t)p.T * p.C * ts * ts;
+  const int64_t total = (int64_t)(p.tile_end - p.tile_begin) * per_tile;
+  float* dst = reinterpret_cast<float*>(p.tiles);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int tx = (int)(idx % ts);
+    const int ty = (int)((idx / ts) % ts);
+    const int64_t tc = (idx / ((int64_t)ts * ts)) % ((int64_t)p.T * p.C);
+    const int tile = p.tile_begin + (int)(idx / per_tile);
+    const int i = tile / nwt, j = tile % nwt;
+    int yy = reflect_idx(i * p.psize + ty - p.overlap, Hp);
+    int xx = reflect_idx(j * p.psize + tx - p.overlap, Wp);
+    yy = reflect_idx(yy, p.H);
+    xx = reflect_idx(xx, p.W);
+    const int k = band_of(p, yy);
+    const int r0 = p.row0[k], rows = p.row0[k + 1] - r0;
+    dst[idx] = *(reinterpret_cast<const float*>(p.band[k]) + (tc * rows + (yy - r0)) * p.W + xx);   // possibly a peer load: no __ldg
+  }
+}
+
+// one thread per pixel of a tile's x`scale` centre square; the owner band of the output row takes the store
+__global__ void __launch_bounds__(256) tile_merge_banded_kernel(const fbanet_tile_band_params p) {
+  const int sc = p.scale, ps = p.psize * sc, ov = p.overlap * sc, ts = ps + 2 * ov;
+  const int Wp = (p.W + p.psize - 1) / p.psize * p.psize;
+  const int nwt = Wp / p.psize;
+  const int HH = p.H * sc, WW = p.W * sc;
+  const int64_t per_tile = (int64_t)p.C * ps * ps;
+  const int64_t total = (int64_t)(p.tile_end - p.tile_begin) * per_tile;
+  const float* src = reinterpret_cast<const float*>(p.tiles);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % ps);
+    const int y = (int)((idx / ps) % ps);
+    const int c = (int)((idx / ((int64_t)ps * ps)) % p.C);
+    const int lt = (int)(idx / per_tile), tile = p.tile_begin + lt;
+    const int Y = (tile / nwt) * ps + y, X = (tile % nwt) * ps + x;
+    if (Y >= HH || X >= WW) continue;   // the reflect padding to a multiple of psize is cropped away
+    const int k = band_of(p, Y / sc);
+    const int r0 = p.row0[k] * sc, rows = (p.row0[k + 1] - p.row0[k]) * sc;
+    reinterpret_cast<float*>(p.band[k])[((int64_t)c * rows + (Y - r0)) * WW + X] = __ldg(src + (((int64_t)lt * p.C + c) * ts + ov + y) * ts + ov + x);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 8f-4  optical-flow registration: bilinear sample at (y - fy, x - fx), indices clamped (map_coordinates order=1, mode="nearest")
+// ------------------------------------------------------------------------------------------------
+template <int CT>
+__global__ void __launch_bounds__(256) flow_warp_kernel(const fbanet_flow_warp_params p) {
+  const int64_t total = (int64_t)p.frames * p.H * p.W;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int C = CT ? CT : p.C;
+  const int x = (int)(idx % p.W);
+  const int y = (int)((idx / p.W) % p.H);
+  const int f = (int)(idx / ((int64_t)p.W * p.H));
+  const float* s = p.src + (int64_t)f * p.s_frame;
+  float* d = p.dst + (int64_t)f * p.d_frame + (int64_t)y * p.d_y + (int64_t)x * p.d_x;
+  int64_t ff = f;   // index of this frame's flow field
+  if (p.frames_per_burst > 0) {
+    const int b = f / p.frames_per_burst, t = f - b * p.frames_per_burst;
+    if (t == 0) {   // base frame: not registered
+      const float* s0 = s + (int64_t)y * p.s_y + (int64_t)x * p.s_x;
+      for (int c = 0; c < C; ++c) d[(int64_t)c * p.d_c] = __ldg(s0 + (int64_t)c * p.s_c);
+      return;
+    }
+    ff = (int64_t)b * (p.frames_per_burst - 1) + (t - 1);
+  }
+  const float2 fl = __ldg(reinterpret_cast<const float2*>(p.flow) + (ff * p.H + y) * p.W + x);   // (dy, dx)
+  const float cy = __fsub_rn((float)y, fl.x), cx = __fsub_rn((float)x, fl.y);                      // grid - flow, one fp32 rounding
+  const float fy = floorf(cy), fx = floorf(cx);
+  const float uy = cy - fy, ux = cx - fx, ly = 1.f - uy, lx = 1.f - ux;                              // upper / lower weights
+  // clamp in float first (a wild flow must not overflow the int conversion), then to the image
+  const int y0i = (int)fminf(fmaxf(fy, -1.f), (float)p.H), x0i = (int)fminf(fmaxf(fx, -1.f), (float)p.W);
+  const int y0 = min(max(y0i, 0), p.H - 1), y1 = min(max(y0i + 1, 0), p.H - 1);
+  const int x0 = min(max(x0i, 0), p.W - 1), x1 = min(max(x0i + 1, 0), p.W - 1);
+  const float* r0 = s + (int64_t)y0 * p.s_y;
+  const float* r1 = s + (int64_t)y1 * p.s_y;
+  const int64_t o0 = (int64_t)x0 * p.s_x, o1 = (int64_t)x1 * p.s_x;
+  float t[CT ? CT : 1][4];
+  if (CT) {
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      const int64_t oc = (int64_t)c * p.s_c;
+      t[c][0] = __ldg(r0 + o0 + oc); t[c][1] = __ldg(r0 + o1 + oc); t[c][2] = __ldg(r1 + o0 + oc); t[c][3] = __ldg(r1 + o1 + oc);
+    }
+#pragma unroll
+    for (int c = 0; c < CT; ++c)   // jax sums the four (index, weight) products in the order (lo,lo), (lo,hi), (hi,lo), (hi,hi)
+      d[(int64_t)c * p.d_c] = ((t[c][0] * (ly * lx) + t[c][1] * (ly * ux)) + t[c][2] * (uy * lx)) + t[c][3] * (uy * ux);
+  } else {
+    for (int c = 0; c < C; ++c) {
+      const int64_t oc = (int64_t)c * p.s_c;
+      d[(int64_t)c * p.d_c] = ((__ldg(r0 + o0 + oc) * (ly * lx) + __ldg(r0 + o1 + oc) * (ly * ux)) + __ldg(r1 + o0 + oc) * (uy * lx)) + __ldg(r1 + o1 + oc) * (uy * ux);
+    }
+  }
+}
+
 static int grid_for(int64_t total, int block) {
   int64_t g = (total + block - 1) / block;
   const int64_t cap = 148 * 32;
@@ -1043,6 +1151,42 @@ extern "C" int fbanet_tile_divide_sm100(const fbanet_tile_params* p, void* strea
   const int ts = p->psize + 2 * p->overlap;
   const int64_t total = (int64_t)(p->tile_end - p->tile_begin) * p->T * p->C * ts * ts;
   tile_divide_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch();
+}
+
+static bool bands_ok(const fbanet_tile_band_params* p) {
+  if (!p || !p->tiles || p->nbands < 1 || p->nbands > FBANET_MAX_BANDS || p->tile_end <= p->tile_begin) return false;
+  if (p->row0[0] != 0 || p->row0[p->nbands] != p->H) return false;
+  for (int k = 0; k < p->nbands; ++k)
+    if (!p->band[k] || p->row0[k + 1] <= p->row0[k]) return false;
+  return true;
+}
+
+extern "C" int fbanet_tile_divide_banded_sm100(const fbanet_tile_band_params* p, void* stream) {
+  if (!bands_ok(p) || p->overlap >= p->H || p->overlap >= p->W) return FBANET_E_BADSHAPE;
+  const int ts = p->psize + 2 * p->overlap;
+  const int64_t total = (int64_t)(p->tile_end - p->tile_begin) * p->T * p->C * ts * ts;
+  tile_divide_banded_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch();
+}
+
+extern "C" int fbanet_tile_merge_banded_sm100(const fbanet_tile_band_params* p, void* stream) {
+  if (!bands_ok(p) || p->scale < 1) return FBANET_E_BADSHAPE;
+  const int64_t total = (int64_t)(p->tile_end - p->tile_begin) * p->C * p->psize * p->scale * p->psize * p->scale;
+  tile_merge_banded_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch();
+}
+
+extern "C" int fbanet_flow_warp_sm100(const fbanet_flow_warp_params* p, void* stream) {
+  if (!p || !p->src || !p->dst || !p->flow || p->frames <= 0 || p->frames_per_burst < 0 || p->frames_per_burst == 1 || p->H <= 0 ||
+      p->W <= 0 || p->C <= 0 || ((uintptr_t)p->flow % 8))
+    return FBANET_E_BADSHAPE;
+  if (p->frames_per_burst > 0 && p->frames % p->frames_per_burst) return FBANET_E_BADSHAPE;
+  const int64_t total = (int64_t)p->frames * p->H * p->W;
+  const int blocks = (int)((total + 255) / 256);
+  if (p->C == 3) flow_warp_kernel<3><<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+  else if (p->C == 4) flow_warp_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+  else flow_warp_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
   return check_launch();
 }
 

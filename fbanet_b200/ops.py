@@ -451,6 +451,66 @@ def warp_burst(burst: torch.Tensor, M: torch.Tensor, layout: str = "BTCHW", retu
     return (out, coords) if return_coords else out
 
 
+def flow_warp_burst(burst: torch.Tensor, flow: torch.Tensor, layout: str = "BTCHW") -> torch.Tensor:
+    """Optical-flow registration (``registration/optical_flow/register.py:11-47``): every non-base frame is resampled at
+    ``grid - flow`` bilinearly with edge-clamped indices (``map_coordinates(order=1, mode="nearest")``).
+
+    ``burst``: fp32 ``[B,T,C,H,W]`` (``"BTCHW"``) or ``[B,T,H,W,C]`` (``"BTHWC"``, the reference's frame layout);
+    ``flow``: fp32 ``[B,T-1,H,W,2]`` with last axis (dy, dx) -- no field for the base frame, which is copied.
+    ``T = 1`` bursts with ``flow [B,1,H,W,2]`` are the single-frame ``register_frame(frame, flow)`` call."""
+    assert burst.is_cuda and burst.dtype == torch.float32 and burst.is_contiguous() and burst.dim() == 5
+    B, T = burst.shape[:2]
+    if layout == "BTCHW":
+        Cc, H, W = burst.shape[2:]
+        sf, sc, sy, sx = Cc * H * W, H * W, W, 1
+    elif layout == "BTHWC":
+        H, W, Cc = burst.shape[2:]
+        sf, sy, sx, sc = H * W * Cc, W * Cc, Cc, 1
+    else:
+        raise ValueError(layout)
+    single = T == 1
+    flow = flow.to(device=burst.device, dtype=torch.float32).contiguous()
+    assert flow.shape == (B, 1 if single else T - 1, H, W, 2), f"flow {tuple(flow.shape)} does not match burst {tuple(burst.shape)}"
+    out = torch.empty_like(burst)
+    p = L.FlowWarpParams()
+    p.src, p.dst, p.flow = burst.data_ptr(), out.data_ptr(), flow.data_ptr()
+    p.s_frame, p.s_y, p.s_x, p.s_c = sf, sy, sx, sc
+    p.d_frame, p.d_y, p.d_x, p.d_c = sf, sy, sx, sc
+    p.frames, p.frames_per_burst, p.H, p.W, p.C = B * T, 0 if single else T, H, W, Cc
+    _call("fbanet_flow_warp_sm100", p, nbytes=2 * burst.numel() * 4 + flow.numel() * 4)
+    return out
+
+
+def _band_params(bands, row0, tiles, T, Cc, H, W, psize, overlap, tile_begin, tile_end, scale):
+    assert 1 <= len(bands) <= L.MAX_BANDS and len(row0) == len(bands) + 1 and row0[0] == 0 and row0[-1] == H
+    p = L.TileBandParams()
+    for k, b in enumerate(bands):
+        p.band[k] = int(b)
+        p.row0[k] = int(row0[k])
+    p.row0[len(bands)] = H
+    p.nbands, p.tiles = len(bands), tiles.data_ptr()
+    p.T, p.C, p.H, p.W, p.psize, p.overlap, p.tile_begin, p.tile_end, p.scale = T, Cc, H, W, psize, overlap, tile_begin, tile_end, scale
+    return p
+
+
+def tile_divide_banded(bands, row0, T: int, Cc: int, H: int, W: int, psize: int, overlap: int, tile_begin: int, tile_end: int,
+                       device) -> torch.Tensor:
+    """Row-band form of :func:`tile_divide`: ``bands[k]`` is the device address (possibly peer memory) of the fp32 band
+    ``[T,C,row0[k+1]-row0[k],W]``.  Returns the local tiles ``[n,T,C,ts,ts]``."""
+    ts = psize + 2 * overlap
+    out = torch.empty((tile_end - tile_begin, T, Cc, ts, ts), device=device, dtype=torch.float32)
+    _call("fbanet_tile_divide_banded_sm100", _band_params(bands, row0, out, T, Cc, H, W, psize, overlap, tile_begin, tile_end, 1))
+    return out
+
+
+def tile_merge_banded(tiles: torch.Tensor, bands, row0, H: int, W: int, psize: int, overlap: int, scale: int, tile_begin: int,
+                      tile_end: int) -> None:
+    """Row-band form of :func:`tile_merge`: the x``scale`` centre of every tile is written into the output band that owns its rows
+    (``bands[k]``: address of fp32 ``[C, scale*(row0[k+1]-row0[k]), scale*W]``, possibly peer memory)."""
+    assert tiles.is_cuda and tiles.dtype == torch.float32 and tiles.is_contiguous() and tiles.shape[0] == tile_end - tile_begin
+    _call("fbanet_tile_merge_banded_sm100", _band_params(bands, row0, tiles, 1, tiles.shape[1], H, W, psize, overlap, tile_begin, tile_end, scale))
+
+
 def tile_divide(burst: torch.Tensor, psize: int, overlap: int, tile_begin: int = 0, tile_end: Optional[int] = None) -> torch.Tensor:
     """``[T,C,H,W]`` fp32 -> ``[tiles,T,C,psize+2ov,psize+2ov]`` (reflect padded, tile index row-major)."""
     assert burst.is_cuda and burst.dtype == torch.float32 and burst.is_contiguous() and burst.dim() == 4

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 13
+#define FBANET_ABI_VERSION 14
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -274,6 +274,46 @@ typedef struct fbanet_tile_params {
   int32_t _pad;
 } fbanet_tile_params;
 
+/* Full-size tiling over ROW BANDS held on several GPUs of one box (BASELINE config 4): the [T][C][H][W] burst is
+ * sharded by image rows, band k = rows [row0[k], row0[k+1]) of every (t, c) plane, stored [T][C][rows_k][W] on GPU k.  band[k]
+ * is that buffer's address AS MAPPED INTO THE CALLING PROCESS (CUDA peer / symmetric memory: the kernel's loads and stores go
+ * over NVLink), so one launch does the reflect-padded tile gather AND the halo exchange: a tile whose 40-pixel halo crosses a band
+ * boundary simply reads those rows from the neighbour's memory.  The merge writes each x4 tile centre into the band that owns
+ * its output rows (band k of the output = rows [scale*row0[k], scale*row0[k+1]) of [C][scale*H][scale*W], stored
+ * [C][scale*rows_k][scale*W]).  Same index arithmetic as fbanet_tile_params (utils/dataset_utils.py:5-58,140-180;
+ * test_in_any_resolution.py:62-101); with nbands = 1 and row0 = {0, H} it is the plain divide / merge. */
+#define FBANET_MAX_BANDS 8
+typedef struct fbanet_tile_band_params {
+  void* band[FBANET_MAX_BANDS];       /* divide: source bands (read) ; merge: output bands (written)     */
+  void* tiles;                        /* divide: dst [tiles][T][C][ts][ts] ; merge: src [tiles][C][scale*ts]^2, local */
+  int32_t row0[FBANET_MAX_BANDS + 1]; /* low-res row boundaries, row0[0] = 0, row0[nbands] = H           */
+  int32_t nbands;
+  int32_t T, C, H, W;
+  int32_t psize, overlap;
+  int32_t tile_begin, tile_end;
+  int32_t scale;                      /* 1 for divide, 4 for merge                                       */
+  int32_t _pad;
+} fbanet_tile_band_params;
+
+/* Optical-flow registration of a burst.  Replaces registration/optical_flow/register.py:11-47
+ * (`jsp.ndimage.map_coordinates(frame, grid - flow, order=1, mode="nearest")` per channel): destination pixel (y, x) samples
+ * the source at (y - flow[y][x][0], x - flow[y][x][1]) -- flow's last axis is (dy, dx) -- bilinearly, indices clamped to the
+ * image (edge replicate).  The coordinate is formed in fp32 exactly as the reference does (int grid - fp32 flow, one
+ * rounding); the interpolation weights are (c - floor(c)) and 1 - that, as jax's map_coordinates computes them.
+ * flow holds one field per NON-base frame: [bursts][frames_per_burst - 1][H][W][2]; frame 0 of every burst is copied
+ * (pipeline/real_bsr_iterator.py:121-166: "the reference frame should not be included").  frames_per_burst = 0: every
+ * frame has a flow field (the single-frame register_frame call).  Strides as in fbanet_warp_params. */
+typedef struct fbanet_flow_warp_params {
+  const float* src;
+  float* dst;
+  const float* flow;
+  int64_t s_frame, s_y, s_x, s_c;
+  int64_t d_frame, d_y, d_x, d_c;
+  int32_t frames, frames_per_burst;
+  int32_t H, W, C;
+  int32_t _pad;
+} fbanet_flow_warp_params;
+
 int fbanet_abi_version(void);
 /* sizeof() of the named parameter struct as compiled, for binding self-checks; -1 if unknown */
 int fbanet_abi_sizeof(const char* struct_name);
@@ -297,6 +337,9 @@ int fbanet_faf_gate_sm100(const fbanet_faf_gate_params* p, void* stream);
 int fbanet_leff_fc2_sm100(const fbanet_leff_fc2_params* p, void* stream);
 int fbanet_tile_divide_sm100(const fbanet_tile_params* p, void* stream);
 int fbanet_tile_merge_sm100(const fbanet_tile_params* p, void* stream);
+int fbanet_tile_divide_banded_sm100(const fbanet_tile_band_params* p, void* stream);
+int fbanet_tile_merge_banded_sm100(const fbanet_tile_band_params* p, void* stream);
+int fbanet_flow_warp_sm100(const fbanet_flow_warp_params* p, void* stream);
 
 #ifdef __cplusplus
 }

@@ -510,6 +510,40 @@ def warp_burst(burst: np.ndarray, Ms: np.ndarray) -> np.ndarray:
 # ----------------------------------------------------------------------------------------------
 # full-size tiling -- utils/dataset_utils.py:5-58,140-180 with A-25
 # ----------------------------------------------------------------------------------------------
+def flow_register_frame(frame: np.ndarray, flow: np.ndarray) -> np.ndarray:
+    """``register_frame(frame[H,W,C], flow[H,W,2]) -> [H,W,C]`` of ``registration/optical_flow/register.py:22-47``: every channel is
+    sampled at ``mgrid - flow`` (flow's last axis is (dy, dx), ``:32,37``) by ``jsp.ndimage.map_coordinates(order=1,
+    mode="nearest")`` (``:11-19``).  Restated from the jax implementation the reference pins (jax 0.4.20,
+    ``jax/_src/scipy/ndimage.py``): ``lower = floor(c)``, weights ``(1 - (c - lower), c - lower)``, indices ``lower`` and
+    ``lower + 1`` clipped to the image, the four ``weight_y * weight_x * value`` products summed in (lo,lo), (lo,hi), (hi,lo),
+    (hi,hi) order; coordinates in float32 as JAX computes them without x64.  Pinned against ``scipy.ndimage.map_coordinates``
+    (float64) in ``tests/test_oracle.py``."""
+    H, W, _ = frame.shape
+    gy, gx = np.mgrid[:H, :W]
+    cy = (gy.astype(np.float32) - flow[..., 0].astype(np.float32)).astype(np.float32)
+    cx = (gx.astype(np.float32) - flow[..., 1].astype(np.float32)).astype(np.float32)
+    ly, lx = np.floor(cy), np.floor(cx)
+    uy, ux = (cy - ly).astype(np.float32), (cx - lx).astype(np.float32)
+    y0 = np.clip(ly.astype(np.int64), 0, H - 1)
+    y1 = np.clip(ly.astype(np.int64) + 1, 0, H - 1)
+    x0 = np.clip(lx.astype(np.int64), 0, W - 1)
+    x1 = np.clip(lx.astype(np.int64) + 1, 0, W - 1)
+    f = frame.astype(np.float32)
+    wy0, wx0 = (1 - uy)[..., None], (1 - ux)[..., None]
+    wy1, wx1 = uy[..., None], ux[..., None]
+    out = ((wy0 * wx0) * f[y0, x0] + (wy0 * wx1) * f[y0, x1]) + (wy1 * wx0) * f[y1, x0]
+    return (out + (wy1 * wx1) * f[y1, x1]).astype(np.float32)
+
+
+def flow_register_burst(burst: np.ndarray, flows: np.ndarray) -> np.ndarray:
+    """``[F,H,W,C]`` burst + ``[F-1,H,W,2]`` flows -> registered burst; frame 0 is the reference frame and has no flow
+    (``pipeline/real_bsr_iterator.py:121-126``)."""
+    out = [burst[0].astype(np.float32)]
+    for f in range(1, burst.shape[0]):
+        out.append(flow_register_frame(burst[f], flows[f - 1]))
+    return np.stack(out)
+
+
 def tensor_divide_burst(burst: torch.Tensor, psize: int = 80, overlap: int = 40) -> torch.Tensor:
     """``[B,T,C,H,W] -> [B*nh*nw, T, C, psize+2*overlap, psize+2*overlap]`` (tile index row-major,
     batch fastest inside a tile as the reference's ``torch.cat(blocks, 0)`` yields for B=1)."""

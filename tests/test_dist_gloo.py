@@ -46,3 +46,53 @@ def test_two_rank_sharding_and_reductions():
     assert s0 == (0, 4) and s1 == (4, 7)
     assert full0 == full1 == [0.0, 10.0, 20.0, 30.0, 41.0, 51.0, 61.0]
     assert t0 == t1 == 150.0
+
+
+def _band_worker(rank, world, port, q):
+    """cfg4 row bands on two ranks: each rank owns one band of the burst and a contiguous tile shard.  The halo rows it needs
+    from the other band are fetched (here with gloo send/recv standing in for the NVLink peer loads of the CUDA kernel) exactly
+    as `halo_sources` says, and the tiles it builds from (own band + halo) must equal the oracle's tiles of the whole image."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from fbanet_b200.dist import band_rows, halo_sources, init_from_env, shard_range
+    from oracle.fbanet_oracle import tensor_divide_burst
+    r, _, w = init_from_env("gloo")
+    T, C, H, W, ps, ov = 2, 3, 50, 30, 20, 10
+    full = torch.rand(1, T, C, H, W, generator=torch.Generator().manual_seed(0))   # same on both ranks (seeded); only the band is "owned"
+    row0 = band_rows(H, w)
+    band = full[0, :, :, row0[r]:row0[r + 1]].clone()
+    nh, nw = -(-H // ps), -(-W // ps)
+    t0, t1 = shard_range(nh * nw, r, w)
+    need = halo_sources(H, ps, ov, (t0 // nw, (t1 - 1) // nw + 1), row0)
+    # exchange: every rank sends its whole band to whoever needs rows of it (a superset of the halo; sizes are asserted below)
+    other = 1 - r
+    theirs = torch.empty(T, C, row0[other + 1] - row0[other], W)
+    reqs = [dist.isend(band, other), dist.irecv(theirs, other)]
+    for x in reqs:
+        x.wait()
+    canvas = torch.full((T, C, H, W), float("nan"))
+    canvas[:, :, row0[r]:row0[r + 1]] = band
+    if other in need:
+        canvas[:, :, row0[other]:row0[other + 1]] = theirs
+    ref = tensor_divide_burst(full, ps, ov)[t0:t1]
+    got = tensor_divide_burst(canvas[None], ps, ov)[t0:t1]      # NaN anywhere = a row `halo_sources` did not announce
+    ok = bool(torch.equal(got, ref))
+    dist.barrier()
+    q.put((r, (t0, t1), dict(need), ok))
+    dist.destroy_process_group()
+
+
+def test_two_rank_row_bands_and_halo_plan():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_band_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, s0, need0, ok0), (_, s1, need1, ok1) = res
+    assert s0 == (0, 3) and s1 == (3, 6)                      # 3 x 2 tiles of 20 px over a 50 x 30 image
+    assert ok0 and ok1
+    assert need0 == {0: 25, 1: 25} and need1 == {0: 15, 1: 25}   # rank 0's tile rows 0-1 reach rows 0..49, rank 1's rows 10..49

@@ -398,6 +398,69 @@ def test_tile_divide_merge(cuda):
     assert torch.equal(out.cpu(), refm[0])
 
 
+@pytest.mark.parametrize("nbands", [1, 2, 3, 8])
+def test_tile_divide_merge_banded(cuda, nbands):
+    """cfg4 / 8e: the row-band kernels (bands possibly in peer memory; here all on one GPU, as separate allocations) must gather
+    exactly the tiles, and stitch exactly the image, of the restated utils/dataset_utils.py -- including tiles whose halo or
+    core crosses band boundaries and bands thinner than the halo."""
+    from fbanet_b200 import ops
+    from fbanet_b200.dist import band_rows, shard_range
+    from oracle.fbanet_oracle import tensor_divide_burst, tensor_merge
+    T, Cc, H, W, ps, ov = 3, 3, 50, 70, 20, 10
+    burst = torch.rand(1, T, Cc, H, W, generator=torch.Generator().manual_seed(0))
+    ref = tensor_divide_burst(burst, ps, ov)
+    row0 = band_rows(H, nbands)
+    bands = [burst[0, :, :, row0[k]:row0[k + 1]].contiguous().to(cuda) for k in range(nbands)]
+    ntiles = ref.shape[0]
+    sr = torch.rand(ntiles, Cc, 4 * (ps + 2 * ov), 4 * (ps + 2 * ov), generator=torch.Generator().manual_seed(1))
+    refm = tensor_merge(sr, (4 * H, 4 * W), 4 * ps, 4 * ov)[0]
+    obands = [torch.full((Cc, 4 * (row0[k + 1] - row0[k]), 4 * W), -1.0, device=cuda) for k in range(nbands)]
+    for r in range(2):                                  # two tile shards, as two ranks would run them
+        b, e = shard_range(ntiles, r, 2)
+        got = ops.tile_divide_banded([x.data_ptr() for x in bands], row0, T, Cc, H, W, ps, ov, b, e, cuda)
+        assert torch.equal(got.cpu(), ref[b:e])
+        ops.tile_merge_banded(sr[b:e].contiguous().to(cuda), [x.data_ptr() for x in obands], row0, H, W, ps, ov, 4, b, e)
+    assert torch.equal(torch.cat([x.cpu() for x in obands], 1), refm)
+
+
+@pytest.mark.parametrize("layout", ["BTCHW", "BTHWC"])
+@pytest.mark.parametrize("shape", [(2, 5, 3, 37, 53), (1, 14, 4, 80, 80), (3, 1, 3, 16, 24), (1, 3, 2, 9, 7)])
+def test_flow_warp_matches_oracle(cuda, layout, shape):
+    """8f-4: registration/optical_flow/register.py:11-47 -- bilinear sample at grid - flow with edge-clamped indices.  Flows reach
+    far outside the image, include exact integers and NaN-free extremes; frame 0 has no flow and is copied."""
+    from fbanet_b200 import ops
+    from oracle.fbanet_oracle import flow_register_burst, flow_register_frame
+    B, T, Cc, H, W = shape
+    g = torch.Generator().manual_seed(3)
+    burst = torch.rand(B, T, H, W, Cc, generator=g)
+    nf = 1 if T == 1 else T - 1
+    flow = (torch.rand(B, nf, H, W, 2, generator=g) - 0.5) * 2 * max(H, W) * 0.6
+    flow[:, :, ::3, ::2] = torch.round(flow[:, :, ::3, ::2])          # exact-integer displacements
+    flow[:, :, 0, 0] = torch.tensor([1e9, -1e9])                      # wild values must clamp, not overflow
+    if T == 1:
+        ref = np.stack([flow_register_frame(burst[b, 0].numpy(), flow[b, 0].numpy())[None] for b in range(B)])
+    else:
+        ref = np.stack([flow_register_burst(burst[b].numpy(), flow[b].numpy()) for b in range(B)])
+    x = burst if layout == "BTHWC" else burst.permute(0, 1, 4, 2, 3).contiguous()
+    out = ops.flow_warp_burst(x.to(cuda), flow.to(cuda), layout=layout).cpu()
+    out = out if layout == "BTHWC" else out.permute(0, 1, 3, 4, 2)
+    assert np.abs(out.numpy() - ref).max() <= 2e-6, np.abs(out.numpy() - ref).max()
+    if T > 1:
+        assert torch.equal(out[:, 0], burst[:, 0])
+
+
+def test_flow_warp_zero_flow_is_identity_and_shift_is_exact(cuda):
+    from fbanet_b200 import ops
+    x = torch.rand(1, 3, 3, 32, 40, generator=torch.Generator().manual_seed(0)).to(cuda)
+    assert torch.equal(ops.flow_warp_burst(x, torch.zeros(1, 2, 32, 40, 2)), x)
+    fl = torch.zeros(1, 2, 32, 40, 2)
+    fl[..., 0], fl[..., 1] = 2.0, -3.0                                # out(y,x) = in(y-2, x+3), clamped at the edges
+    out = ops.flow_warp_burst(x, fl)
+    yy = (torch.arange(32) - 2).clamp(0, 31)
+    xx = (torch.arange(40) + 3).clamp(0, 39)
+    assert torch.equal(out[:, 1:].cpu(), x.cpu()[:, 1:][..., yy, :][..., xx])
+
+
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("cin,hw", [(3, (21, 33)), (4, (16, 16))])
 def test_head_conv_direct(cuda, dt, cin, hw):

@@ -103,3 +103,18 @@ def test_shard_range_tiles_exactly(n, world):
     assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     sizes = [e - b for b, e in spans]
     assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("H,world", [(1080, 8), (1080, 2), (50, 3), (7, 7)])
+def test_band_rows_and_halo_sources(H, world):
+    """cfg4 row bands: boundaries tile [0, H) exactly; the rows a rank gathers for its tile rows come from its own band and the
+    neighbours the 40-pixel halo (or a reflection at the image border) reaches."""
+    from fbanet_b200.dist import band_rows, halo_sources
+    r = band_rows(H, world)
+    assert r[0] == 0 and r[-1] == H and len(r) == world + 1 and all(b > a for a, b in zip(r, r[1:]))
+    assert max(b - a for a, b in zip(r, r[1:])) - min(b - a for a, b in zip(r, r[1:])) <= 1
+    if H == 1080 and world == 8:
+        assert halo_sources(H, 80, 40, (0, 2), r) == {0: 135, 1: 65}     # rows 0..199 (the top halo reflects into rows 1..40)
+        assert halo_sources(H, 80, 40, (12, 14), r) == {7: 135, 6: 25}   # rows 920..1079; the padded rows reflect back inside
+    tot = halo_sources(H, min(80, H), min(40, H - 1), (0, -(-H // min(80, H))), r)
+    assert sum(tot.values()) == H                                        # all tile rows together touch every image row once

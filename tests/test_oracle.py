@@ -154,3 +154,28 @@ def test_golden_warp():
     g = np.load(os.path.join(GOLD, "warp.npz"))
     out = O.warp_burst(g["burst"], g["M"])
     assert np.abs(out - g["out"]).max() < 1e-12
+
+
+def test_flow_registration_oracle_matches_scipy_map_coordinates():
+    """8f-4 pin: the restated jax map_coordinates(order=1, mode="nearest") of registration/optical_flow/register.py:11-47 against
+    scipy.ndimage.map_coordinates evaluated in float64 (the API jax.scipy mirrors).  Tolerance = fp32 rounding of the
+    coordinates (the reference computes them in fp32)."""
+    import numpy as np
+    import scipy.ndimage as ndi
+    from oracle.fbanet_oracle import flow_register_burst, flow_register_frame
+    rng = np.random.default_rng(0)
+    for (H, W, C, amp) in [(37, 53, 3, 12.0), (80, 80, 4, 3.0), (9, 7, 1, 30.0)]:
+        f = rng.random((H, W, C)).astype(np.float32)
+        fl = ((rng.random((H, W, 2)) - 0.5) * amp).astype(np.float32)
+        gy, gx = np.mgrid[:H, :W]
+        ref = np.stack([ndi.map_coordinates(f[..., c].astype(np.float64), [gy - fl[..., 0].astype(np.float64), gx - fl[..., 1].astype(np.float64)],
+                                            order=1, mode="nearest") for c in range(C)], -1)
+        assert np.abs(flow_register_frame(f, fl) - ref).max() < 5e-6
+    # integer flows are exact shifts with edge replication; the reference frame passes through
+    f = rng.random((3, 8, 10, 2)).astype(np.float32)
+    fl = np.zeros((2, 8, 10, 2), np.float32)
+    fl[..., 0], fl[..., 1] = 1.0, -2.0
+    out = flow_register_burst(f, fl)
+    assert np.array_equal(out[0], f[0])
+    yy, xx = np.clip(np.arange(8) - 1, 0, 7), np.clip(np.arange(10) + 2, 0, 9)
+    assert np.array_equal(out[1], f[1][yy][:, xx])
