@@ -211,6 +211,10 @@ def main():
         Mh = Mh.to(dev)
         ops.warp_burst(x, Mh)
         fam.update(ops.profile_ops(lambda: [ops.warp_burst(x, Mh) for _ in range(3)], stream, by_tag=False))
+        # 8f-4 optical-flow registration (registration/optical_flow/register.py), same burst shape, +-4 px synthetic flow
+        flow = (torch.rand(B, CFG["num_frames"] - 1, CFG["img_size"], CFG["img_size"], 2, generator=torch.Generator().manual_seed(2)) * 8 - 4).to(dev)
+        ops.flow_warp_burst(x, flow)
+        fam.update(ops.profile_ops(lambda: [ops.flow_warp_burst(x, flow) for _ in range(3)], stream, by_tag=False))
         if args.breakdown and rank == 0:
             bd = ops.profile_ops(lambda: model(x), stream)
             tot = sum(v[0] for v in bd.values())
@@ -268,7 +272,7 @@ def main():
     }
     hbm_peak = pk["hbm_gbs"]
     hbm_kernels = []
-    for name in ("fbanet_warp_sm100", "fbanet_faf_gate_sm100", "fbanet_head_conv_sm100", "fbanet_layernorm_sm100", "fbanet_assemble_sm100",
+    for name in ("fbanet_warp_sm100", "fbanet_flow_warp_sm100", "fbanet_faf_gate_sm100", "fbanet_head_conv_sm100", "fbanet_layernorm_sm100", "fbanet_assemble_sm100",
                  "fbanet_window_attention_sm100", "fbanet_leff_fc2_sm100"):
         if name in fam and fam[name][0] > 0:
             t_ms, n, by = fam[name]

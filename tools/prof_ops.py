@@ -67,6 +67,12 @@ def warp(B, S):
     return (lambda: ops.warp_burst(x, M)), 2 * x.numel() * 4 / 1e9
 
 
+def flow(B, S):
+    x = torch.rand(B, 14, 3, S, S, device=dev)
+    fl = (torch.rand(B, 13, S, S, 2, device=dev) * 8 - 4)
+    return (lambda: ops.flow_warp_burst(x, fl)), (2 * x.numel() + fl.numel()) * 4 / 1e9
+
+
 def leff(B, S, C):
     Hd = 4 * C
     h1 = (torch.rand(B, S, S, Hd, device=dev) - 0.5).to(BF)
@@ -96,6 +102,7 @@ CASES = {
     "gate_160": lambda: gate(64, 160),
     "head_160": lambda: head(64, 160),
     "warp_160": lambda: warp(64, 160),
+    "flow_160": lambda: flow(64, 160),
 }
 
 if __name__ == "__main__":
