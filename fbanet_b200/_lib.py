@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBANET_B200_LIB") or os.path.join(_HERE, "csrc", "libfbanet_b200.so")   # env override: A/B two builds in one process tree
-ABI_VERSION = 14
+ABI_VERSION = 15
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -153,11 +153,27 @@ class FlowWarpParams(C.Structure):
     ]
 
 
+class EccPrepareParams(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("planes", C.c_void_p),
+        ("s_frame", C.c_int64), ("s_y", C.c_int64), ("s_x", C.c_int64), ("s_c", C.c_int64),
+        ("gray_weight", C.c_float * 4), ("frames", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+    ]
+
+
+class EccParams(C.Structure):
+    _fields_ = [
+        ("planes", C.c_void_p), ("warp", C.c_void_p), ("rho", C.c_void_p), ("iters_done", C.c_void_p), ("eps", C.c_double),
+        ("frames", C.c_int32), ("frames_per_burst", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("max_iters", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
 STRUCTS = {
     "fbanet_src": Src, "fbanet_conv_params": ConvParams, "fbanet_warp_params": WarpParams,
     "fbanet_to_nhwc_params": ToNhwcParams, "fbanet_s2d_params": S2dParams, "fbanet_head_conv_params": HeadConvParams, "fbanet_assemble_params": AssembleParams, "fbanet_layernorm_params": LayerNormParams, "fbanet_attn_params": AttnParams,
     "fbanet_dwconv_params": DwconvParams, "fbanet_faf_gate_params": FafGateParams, "fbanet_leff_fc2_params": LeffFc2Params, "fbanet_tile_params": TileParams,
     "fbanet_tile_band_params": TileBandParams, "fbanet_flow_warp_params": FlowWarpParams,
+    "fbanet_ecc_prepare_params": EccPrepareParams, "fbanet_ecc_params": EccParams,
 }
 
 # every symbol include/fbanet_b200.h declares
@@ -166,6 +182,7 @@ OPS = {
     "fbanet_layernorm_sm100": LayerNormParams, "fbanet_window_attention_sm100": AttnParams, "fbanet_dwconv3x3_sm100": DwconvParams,
     "fbanet_faf_gate_sm100": FafGateParams, "fbanet_leff_fc2_sm100": LeffFc2Params, "fbanet_tile_divide_sm100": TileParams, "fbanet_tile_merge_sm100": TileParams,
     "fbanet_tile_divide_banded_sm100": TileBandParams, "fbanet_tile_merge_banded_sm100": TileBandParams, "fbanet_flow_warp_sm100": FlowWarpParams,
+    "fbanet_ecc_prepare_sm100": EccPrepareParams, "fbanet_ecc_homography_sm100": EccParams,
 }
 MISC_SYMBOLS = ["fbanet_abi_version", "fbanet_abi_sizeof", "fbanet_last_cuda_error", "fbanet_conv_gemm_tcgen05_supported", "fbanet_leff_fc2_supported"]
 

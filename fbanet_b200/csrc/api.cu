@@ -55,6 +55,8 @@ extern "C" int fbanet_abi_sizeof(const char* n) {
   SZ(fbanet_tile_params);
   SZ(fbanet_tile_band_params);
   SZ(fbanet_flow_warp_params);
+  SZ(fbanet_ecc_prepare_params);
+  SZ(fbanet_ecc_params);
 #undef SZ
   return -1;
 }

@@ -481,6 +481,54 @@ def flow_warp_burst(burst: torch.Tensor, flow: torch.Tensor, layout: str = "BTCH
     return out
 
 
+def ecc_homography_burst(burst: torch.Tensor, layout: str = "BTCHW", gray_weights=None, max_iters: int = 100, eps: float = 1e-10,
+                         init: Optional[torch.Tensor] = None):
+    """ECC alignment of every non-base frame to frame 0 of its burst: the GPU form of ``register_frame``'s
+    ``cv2.findTransformECC(gray(img1), gray(img2), eye(3), MOTION_HOMOGRAPHY, (COUNT|EPS, 100, 1e-10))``
+    (``homography_alignment.py:19-45``).  Returns ``(M [B,T,3,3] float64, rho [B,T] float64, iters [B,T] int32)``; ``M`` maps
+    base-frame pixel coordinates to frame coordinates -- pass it straight to :func:`warp_burst` (``WARP_INVERSE_MAP``, ``:46-55``).
+    ``M[:, 0]`` is the identity.  ``iters < 0`` marks pairs where cv2 would have thrown ("stopped before its convergence").
+
+    ``gray_weights``: per-channel weights of the grey conversion; default = ``cv2.COLOR_BGR2GRAY`` applied to the channels in
+    storage order (0.114, 0.587, 0.299) for 3 channels, the channel mean otherwise."""
+    assert burst.is_cuda and burst.dtype == torch.float32 and burst.is_contiguous() and burst.dim() == 5
+    B, T = burst.shape[:2]
+    assert T >= 2, "a burst needs a base frame and at least one frame to align"
+    if layout == "BTCHW":
+        Cc, H, W = burst.shape[2:]
+        sf, sc, sy, sx = Cc * H * W, H * W, W, 1
+    elif layout == "BTHWC":
+        H, W, Cc = burst.shape[2:]
+        sf, sy, sx, sc = H * W * Cc, W * Cc, Cc, 1
+    else:
+        raise ValueError(layout)
+    if gray_weights is None:
+        gray_weights = (0.114, 0.587, 0.299) if Cc == 3 else tuple(1.0 / Cc for _ in range(Cc))
+    assert len(gray_weights) == Cc <= 4
+    dev = burst.device
+    planes = torch.empty((B * T, 3, H, W), device=dev, dtype=torch.float32)
+    pp = L.EccPrepareParams()
+    pp.src, pp.planes = burst.data_ptr(), planes.data_ptr()
+    pp.s_frame, pp.s_y, pp.s_x, pp.s_c = sf, sy, sx, sc
+    for c in range(4):
+        pp.gray_weight[c] = float(gray_weights[c]) if c < Cc else 0.0
+    pp.frames, pp.H, pp.W, pp.C = B * T, H, W, Cc
+    _call("fbanet_ecc_prepare_sm100", pp, nbytes=(burst.numel() + planes.numel()) * 4)
+    if init is None:
+        M = torch.eye(3, dtype=torch.float64, device=dev).repeat(B, T, 1, 1).contiguous()
+    else:
+        M = init.to(device=dev, dtype=torch.float64).contiguous().clone()
+        assert M.shape == (B, T, 3, 3)
+    rho = torch.zeros((B, T), dtype=torch.float64, device=dev)
+    rho[:, 0] = 1.0
+    iters = torch.zeros((B, T), dtype=torch.int32, device=dev)
+    p = L.EccParams()
+    p.planes, p.warp, p.rho, p.iters_done = planes.data_ptr(), M.data_ptr(), rho.data_ptr(), iters.data_ptr()
+    p.eps, p.frames, p.frames_per_burst, p.H, p.W, p.max_iters = float(eps), B * T, T, H, W, int(max_iters)
+    _call("fbanet_ecc_homography_sm100", p)
+    return M, rho, iters
+
+
 def _band_params(bands, row0, tiles, T, Cc, H, W, psize, overlap, tile_begin, tile_end, scale):
     assert 1 <= len(bands) <= L.MAX_BANDS and len(row0) == len(bands) + 1 and row0[0] == 0 and row0[-1] == H
     p = L.TileBandParams()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 14
+#define FBANET_ABI_VERSION 15
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -314,6 +314,32 @@ typedef struct fbanet_flow_warp_params {
   int32_t _pad;
 } fbanet_flow_warp_params;
 
+/* ECC homography estimation.  Replaces `cv2.findTransformECC(gray(img1), gray(img2), eye(3), MOTION_HOMOGRAPHY,
+ * (COUNT | EPS, 100, 1e-10))` of `register_frame`, homography_alignment.py:19-45: every non-base frame of a burst is aligned to
+ * frame 0; the resulting 3x3 matrices map base-frame coordinates to frame coordinates, i.e. they are exactly the `M` that
+ * fbanet_warp_sm100 (cv2.warpPerspective with WARP_INVERSE_MAP, :46-55) takes.
+ * Step 1, fbanet_ecc_prepare_sm100: gray = sum_c gray_weight[c] * x_c (cv2.cvtColor(..., COLOR_BGR2GRAY): 0.114, 0.587, 0.299),
+ * GaussianBlur 5x5 (OpenCV's fixed [1,4,6,4,1]/16 kernel, BORDER_REFLECT_101), central-difference gradients ->
+ * planes [frames][3][H][W] = (blurred, d/dx, d/dy).  Strides as in fbanet_warp_params.
+ * Step 2, fbanet_ecc_homography_sm100: the forward-additive ECC iterations, one CTA per (burst, frame) pair, all on the device. */
+typedef struct fbanet_ecc_prepare_params {
+  const float* src;
+  float* planes;                  /* out [frames][3][H][W] fp32                                          */
+  int64_t s_frame, s_y, s_x, s_c;
+  float gray_weight[4];
+  int32_t frames, H, W, C;
+} fbanet_ecc_prepare_params;
+
+typedef struct fbanet_ecc_params {
+  const float* planes;            /* [frames][3][H][W] from fbanet_ecc_prepare_sm100                     */
+  double* warp;                   /* in/out [frames][9] row-major 3x3: initial guess (identity) -> estimate; base frames untouched */
+  double* rho;                    /* optional out [frames]: final enhanced correlation coefficient (-1: failed) */
+  int32_t* iters_done;            /* optional out [frames]: iterations run; negative = stopped on failure (degenerate image,
+                                     lambda_d <= 0: cv2 throws "the algorithm stopped before its convergence")   */
+  double eps;                     /* stop when |rho - last_rho| < eps                                     */
+  int32_t frames, frames_per_burst, H, W, max_iters, _pad;
+} fbanet_ecc_params;
+
 int fbanet_abi_version(void);
 /* sizeof() of the named parameter struct as compiled, for binding self-checks; -1 if unknown */
 int fbanet_abi_sizeof(const char* struct_name);
@@ -340,6 +366,8 @@ int fbanet_tile_merge_sm100(const fbanet_tile_params* p, void* stream);
 int fbanet_tile_divide_banded_sm100(const fbanet_tile_band_params* p, void* stream);
 int fbanet_tile_merge_banded_sm100(const fbanet_tile_band_params* p, void* stream);
 int fbanet_flow_warp_sm100(const fbanet_flow_warp_params* p, void* stream);
+int fbanet_ecc_prepare_sm100(const fbanet_ecc_prepare_params* p, void* stream);
+int fbanet_ecc_homography_sm100(const fbanet_ecc_params* p, void* stream);
 
 #ifdef __cplusplus
 }

@@ -582,3 +582,127 @@ def psnr(a: torch.Tensor, b: torch.Tensor, max_val: float = 1.0) -> float:
     """utils/image_utils.py:127 -- ``20 log10(max) - 10 log10(mse)``."""
     mse = torch.mean((a.double() - b.double()) ** 2).item()
     return 20.0 * math.log10(max_val) - 10.0 * math.log10(max(mse, 1e-30))
+
+
+# ------------------------------------------------------------------------------------------------
+# 8f-4  ECC homography estimation: `cv2.findTransformECC(template_gray, input_gray, eye(3), MOTION_HOMOGRAPHY, (COUNT|EPS, 100,
+# 1e-10))` as called by `homography_alignment.py:19-45` (`register_frame`).  The algorithm lives in OpenCV
+# (opencv-contrib-python-headless-rolling 5.0.0.20221015, `pyproject.toml:28`; absent from /root/reference), restated here from
+# its published form -- Evangelidis & Psarakis, "Parametric image alignment using enhanced correlation coefficient maximization",
+# PAMI 2008, forward-additive scheme, as implemented in `modules/video/src/ecc.cpp` -- and PINNED against the cv2 4.13 in this
+# container (`tests/test_oracle.py::test_ecc_oracle_matches_cv2`).  Deliberate difference: the warp-back samples with exact
+# bilinear coordinates (OpenCV quantises them to 1/32 px, Appendix A-20), which moves the fixed point by ~1e-3 px.
+# ------------------------------------------------------------------------------------------------
+def bgr2gray(img: np.ndarray) -> np.ndarray:
+    """`cv2.cvtColor(img, COLOR_BGR2GRAY)` on float32 `[H,W,3]` (`homography_alignment.py:39-40`): 0.114 c0 + 0.587 c1 + 0.299 c2."""
+    img = img.astype(np.float32)
+    return (img[..., 0] * np.float32(0.114) + img[..., 1] * np.float32(0.587) + img[..., 2] * np.float32(0.299)).astype(np.float32)
+
+
+def _reflect101(i: np.ndarray, n: int) -> np.ndarray:
+    i = np.abs(i)
+    return np.where(i >= n, 2 * (n - 1) - i, i)
+
+
+def ecc_blur5(img: np.ndarray) -> np.ndarray:
+    """`GaussianBlur(img, (5,5), 0)`: OpenCV's fixed small kernel [1,4,6,4,1]/16, separable, BORDER_REFLECT_101."""
+    k = np.array([1, 4, 6, 4, 1], np.float64) / 16.0
+    H, W = img.shape
+    x = img.astype(np.float64)
+    cols = _reflect101(np.arange(W)[None, :] + np.arange(-2, 3)[:, None], W)
+    x = sum(k[j] * x[:, cols[j]] for j in range(5))
+    rows = _reflect101(np.arange(H)[None, :] + np.arange(-2, 3)[:, None], H)
+    x = sum(k[j] * x[rows[j], :] for j in range(5))
+    return x.astype(np.float32)
+
+
+def ecc_gradients(img: np.ndarray):
+    """`filter2D(img, -1, [-0.5, 0, 0.5])` along x and along y (BORDER_REFLECT_101: the gradient is 0 on the border)."""
+    H, W = img.shape
+    x = img.astype(np.float64)
+    gx = 0.5 * (x[:, _reflect101(np.arange(W) + 1, W)] - x[:, _reflect101(np.arange(W) - 1, W)])
+    gy = 0.5 * (x[_reflect101(np.arange(H) + 1, H), :] - x[_reflect101(np.arange(H) - 1, H), :])
+    return gx.astype(np.float32), gy.astype(np.float32)
+
+
+def _bilinear_border0(img: np.ndarray, sx: np.ndarray, sy: np.ndarray) -> np.ndarray:
+    H, W = img.shape
+    x0, y0 = np.floor(sx), np.floor(sy)
+    ax, ay = sx - x0, sy - y0
+    x0, y0 = x0.astype(np.int64), y0.astype(np.int64)
+    out = np.zeros(sx.shape, np.float64)
+    for dy, wy in ((0, 1 - ay), (1, ay)):
+        for dx, wx in ((0, 1 - ax), (1, ax)):
+            xx, yy = x0 + dx, y0 + dy
+            ok = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
+            out += np.where(ok, img[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)], 0.0) * wy * wx
+    return out
+
+
+def ecc_homography(template: np.ndarray, image: np.ndarray, iters: int = 100, eps: float = 1e-10, warp: np.ndarray = None,
+                   quantize_1_32: bool = False):
+    """`(rho, warp[3,3]) = findTransformECC(template, image, warp0 = I, MOTION_HOMOGRAPHY)` on single-channel float images of one
+    size.  `warp` maps template coordinates to image coordinates (use with WARP_INVERSE_MAP).  float64 arithmetic.
+    `quantize_1_32`: round the sampling coordinates to 1/32 px as OpenCV's remap does (test mode: explains the residual
+    difference to cv2)."""
+    H, W = template.shape
+    t = ecc_blur5(template).astype(np.float64)
+    im = ecc_blur5(image).astype(np.float64)
+    gx, gy = ecc_gradients(im.astype(np.float32))
+    gx, gy = gx.astype(np.float64), gy.astype(np.float64)
+    M = np.eye(3) if warp is None else np.array(warp, np.float64)
+    Y, X = np.mgrid[:H, :W].astype(np.float64)
+    rho, last_rho = -1.0, -eps
+    for _ in range(iters):
+        if abs(rho - last_rho) < eps:
+            break
+        den = M[2, 0] * X + M[2, 1] * Y + M[2, 2]
+        sx = (M[0, 0] * X + M[0, 1] * Y + M[0, 2]) / den
+        sy = (M[1, 0] * X + M[1, 1] * Y + M[1, 2]) / den
+        if quantize_1_32:
+            sx, sy = np.rint(sx * 32.0) / 32.0, np.rint(sy * 32.0) / 32.0
+        iw = _bilinear_border0(im, sx, sy)
+        gxw = _bilinear_border0(gx, sx, sy)
+        gyw = _bilinear_border0(gy, sx, sy)
+        rx, ry = np.rint(sx), np.rint(sy)                       # warped all-ones mask, INTER_NEAREST, border 0
+        mask = (rx >= 0) & (rx < W) & (ry >= 0) & (ry < H)
+        n = mask.sum()
+        imean, tmean = iw[mask].mean(), t[mask].mean()
+        izm = np.where(mask, iw - imean, iw)                    # subtract(..., mask): pixels outside the mask keep their value
+        tzm = np.where(mask, t - tmean, 0.0)
+        inorm, tnorm = np.sqrt((izm[mask] ** 2).sum()), np.sqrt((tzm[mask] ** 2).sum())
+        # image_jacobian_homo_ECC
+        den_ = 1.0 / (X * M[2, 0] + Y * M[2, 1] + 1.0)
+        hx = -(X * M[0, 0] + Y * M[0, 1] + M[0, 2]) * den_
+        hy = -(X * M[1, 0] + Y * M[1, 1] + M[1, 2]) * den_
+        gxp, gyp = gxw * den_, gyw * den_
+        tmp = hx * gxp + hy * gyp
+        J = np.stack([gxp * X, gyp * X, tmp * X, gxp * Y, gyp * Y, tmp * Y, gxp, gyp], 0).reshape(8, -1)
+        Hs = J @ J.T
+        Hinv = np.linalg.inv(Hs)
+        corr = float((tzm * izm).sum())
+        last_rho, rho = rho, corr / (inorm * tnorm)
+        ip, tp = J @ izm.reshape(-1), J @ tzm.reshape(-1)
+        iph = Hinv @ ip
+        lam_n = inorm * inorm - ip @ iph
+        lam_d = corr - tp @ iph
+        if lam_d <= 0:
+            raise ValueError("ECC: the algorithm stopped before its convergence (lambda_d <= 0)")
+        lam = lam_n / lam_d
+        dp = Hinv @ (lam * tp - ip)                             # J^T (lam * tzm - izm)
+        M[0, 0] += dp[0]; M[1, 0] += dp[1]; M[2, 0] += dp[2]
+        M[0, 1] += dp[3]; M[1, 1] += dp[4]; M[2, 1] += dp[5]
+        M[0, 2] += dp[6]; M[1, 2] += dp[7]
+    return rho, M
+
+
+def homography_coord_diff(Ma, Mb, H: int, W: int) -> float:
+    """Largest difference (pixels) between the source coordinates two 3x3 matrices assign to the pixels of an H x W image."""
+    Y, X = np.mgrid[:H, :W].astype(np.float64)
+
+    def co(M):
+        M = np.asarray(M, np.float64)
+        d = M[2, 0] * X + M[2, 1] * Y + M[2, 2]
+        return (M[0, 0] * X + M[0, 1] * Y + M[0, 2]) / d, (M[1, 0] * X + M[1, 1] * Y + M[1, 2]) / d
+    (a, b), (c, d) = co(Ma), co(Mb)
+    return float(max(np.abs(a - c).max(), np.abs(b - d).max()))

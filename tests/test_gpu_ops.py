@@ -499,3 +499,81 @@ def test_assemble_sr_plus_bilinear_base(cuda, dt):
     ref = sr[..., :3].permute(0, 3, 1, 2) + F.interpolate(burst[:, 0], scale_factor=4, mode="bilinear", align_corners=False)
     out = ops.assemble(sr.to(cuda, dt), burst.to(cuda)[:, 0], 3)
     assert (out.cpu() - ref).abs().max().item() < 1e-5
+
+
+def test_ecc_prepare_matches_oracle(cuda):
+    """8f-4: grey conversion + 5x5 Gaussian + central differences of fbanet_ecc_prepare_sm100 vs the cv2-pinned restatement."""
+    from fbanet_b200 import _lib as L, ops  # noqa: F401
+    from oracle.fbanet_oracle import bgr2gray, ecc_blur5, ecc_gradients
+    import ctypes as C
+    g = torch.Generator().manual_seed(5)
+    burst = torch.rand(2, 3, 3, 37, 50, generator=g)
+    x = burst.to(cuda)
+    planes = torch.empty((6, 3, 37, 50), device=cuda)
+    pp = L.EccPrepareParams()
+    pp.src, pp.planes = x.data_ptr(), planes.data_ptr()
+    pp.s_frame, pp.s_c, pp.s_y, pp.s_x = 3 * 37 * 50, 37 * 50, 50, 1
+    for c, w in enumerate((0.114, 0.587, 0.299, 0.0)):
+        pp.gray_weight[c] = w
+    pp.frames, pp.H, pp.W, pp.C = 6, 37, 50, 3
+    ops._call("fbanet_ecc_prepare_sm100", pp)
+    got = planes.cpu().numpy()
+    for f in range(6):
+        b = ecc_blur5(bgr2gray(burst.view(6, 3, 37, 50)[f].permute(1, 2, 0).numpy()))
+        gx, gy = ecc_gradients(b)
+        assert np.abs(got[f, 0] - b).max() < 1e-6 and np.abs(got[f, 1] - gx).max() < 1e-6 and np.abs(got[f, 2] - gy).max() < 1e-6
+
+
+@pytest.mark.parametrize("layout", ["BTCHW", "BTHWC"])
+def test_ecc_homography_matches_oracle_and_registers(cuda, layout):
+    """8f-4: the on-device ECC iterations (fp32 pixel maths, fp64 reductions and solve) against the float64 restatement of
+    cv2.findTransformECC, on bursts whose frames are known homographies of the base frame + noise; then the estimated matrices,
+    fed to the K1 warp, must register the frames (PSNR to the base frame goes up)."""
+    import cv2
+    from fbanet_b200 import ops
+    from oracle.fbanet_oracle import bgr2gray, ecc_homography, homography_coord_diff as _coord_diff
+    H, W, T, B = 96, 128, 4, 2
+    rng = np.random.default_rng(7)
+    burst = np.zeros((B, T, H, W, 3), np.float32)
+    for b in range(B):
+        base = cv2.GaussianBlur(rng.random((H, W, 3)).astype(np.float32), (0, 0), 2.5)
+        base = (base - base.min()) / (base.max() - base.min())
+        burst[b, 0] = base
+        for t in range(1, T):
+            M = np.eye(3, dtype=np.float32)
+            M[0, 2], M[1, 2] = rng.uniform(-3, 3), rng.uniform(-3, 3)
+            M[0, 1], M[1, 0] = rng.uniform(-0.01, 0.01), rng.uniform(-0.01, 0.01)
+            M[2, 1] = rng.uniform(-1e-5, 1e-5)
+            burst[b, t] = cv2.warpPerspective(base, M, (W, H), flags=cv2.INTER_LINEAR) + rng.normal(0, 0.01, (H, W, 3)).astype(np.float32)
+    xb = torch.from_numpy(burst)
+    x = (xb if layout == "BTHWC" else xb.permute(0, 1, 4, 2, 3).contiguous()).to(cuda)
+    M, rho, iters = ops.ecc_homography_burst(x, layout=layout)
+    M, rho, iters = M.cpu().numpy(), rho.cpu().numpy(), iters.cpu().numpy()
+    assert np.array_equal(M[:, 0], np.tile(np.eye(3), (B, 1, 1))) and (iters[:, 1:] > 0).all()
+    for b in range(B):
+        g0 = bgr2gray(burst[b, 0])
+        for t in range(1, T):
+            r_ref, M_ref = ecc_homography(g0, bgr2gray(burst[b, t]))
+            assert abs(rho[b, t] - r_ref) < 2e-4, (rho[b, t], r_ref)
+            assert _coord_diff(M[b, t], M_ref, H, W) < 5e-3, _coord_diff(M[b, t], M_ref, H, W)
+    reg = ops.warp_burst(x, torch.from_numpy(M), layout=layout).cpu()
+    reg = reg if layout == "BTHWC" else reg.permute(0, 1, 3, 4, 2)
+
+    def psnr_in(a, c):   # inner region: the warp leaves a border of zeros
+        return -10 * np.log10(((a[8:-8, 8:-8] - c[8:-8, 8:-8]) ** 2).mean())
+    for b in range(B):
+        for t in range(1, T):
+            assert psnr_in(reg[b, t].numpy(), burst[b, 0]) > psnr_in(burst[b, t], burst[b, 0]) + 6.0
+
+
+def test_ecc_degenerate_pair_reports_failure(cuda):
+    """A constant frame has no gradient: J^T J is singular, cv2 throws; the kernel flags the pair (iters < 0, rho = -1) and
+    leaves the other pairs alone."""
+    from fbanet_b200 import ops
+    x = torch.rand(1, 3, 1, 40, 48, generator=torch.Generator().manual_seed(0))
+    x[0, 1] = 0.5
+    x[0, 2] = x[0, 0]
+    M, rho, iters = ops.ecc_homography_burst(x.to(cuda))
+    assert iters[0, 1].item() < 0 and rho[0, 1].item() == -1.0
+    assert iters[0, 2].item() > 0 and rho[0, 2].item() > 0.999
+    assert (M[0, 2].cpu() - torch.eye(3, dtype=torch.float64)).abs().max() < 1e-3

@@ -179,3 +179,41 @@ def test_flow_registration_oracle_matches_scipy_map_coordinates():
     assert np.array_equal(out[0], f[0])
     yy, xx = np.clip(np.arange(8) - 1, 0, 7), np.clip(np.arange(10) + 2, 0, 9)
     assert np.array_equal(out[1], f[1][yy][:, xx])
+
+
+def _ecc_pair(seed, H=96, W=128, noise=0.01):
+    import cv2
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    img = cv2.GaussianBlur(rng.random((H, W)).astype(np.float32), (0, 0), 2.5)
+    img = (img - img.min()) / (img.max() - img.min())
+    M = np.eye(3, dtype=np.float32)
+    M[0, 2], M[1, 2] = rng.uniform(-3, 3), rng.uniform(-3, 3)
+    M[0, 1], M[1, 0] = rng.uniform(-0.01, 0.01), rng.uniform(-0.01, 0.01)
+    M[2, 0] = rng.uniform(-1e-5, 1e-5)
+    inp = cv2.warpPerspective(img, M, (W, H), flags=cv2.INTER_LINEAR) + rng.normal(0, noise, (H, W)).astype(np.float32)
+    return img, inp.astype(np.float32)
+
+
+def test_ecc_oracle_matches_cv2():
+    """8f-4 pin: the restated forward-additive ECC (homography_alignment.py:19-45 -> cv2.findTransformECC, MOTION_HOMOGRAPHY, 100
+    iterations, eps 1e-10, gaussFiltSize 5) against the cv2 in this container, stage by stage and end to end.  The end-to-end
+    tolerance (0.01 px over the image, 5e-4 in rho) is OpenCV's own 1/32-px coordinate quantisation in warpPerspective."""
+    import cv2
+    import numpy as np
+    from oracle.fbanet_oracle import bgr2gray, ecc_blur5, ecc_gradients, ecc_homography, homography_coord_diff as _coord_diff
+    rng = np.random.default_rng(0)
+    a = rng.random((45, 61)).astype(np.float32)
+    assert np.abs(ecc_blur5(a) - cv2.GaussianBlur(a, (5, 5), 0)).max() < 5e-7
+    gx, gy = ecc_gradients(a)
+    assert np.abs(gx - cv2.filter2D(a, -1, np.array([[-0.5, 0, 0.5]], np.float32))).max() < 1e-7
+    assert np.abs(gy - cv2.filter2D(a, -1, np.array([[-0.5], [0], [0.5]], np.float32))).max() < 1e-7
+    c = rng.random((20, 30, 3)).astype(np.float32)
+    assert np.abs(bgr2gray(c) - cv2.cvtColor(c, cv2.COLOR_BGR2GRAY)).max() < 5e-7
+    crit = (cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 100, 1e-10)
+    for seed in range(3):
+        t, i = _ecc_pair(seed)
+        cc, wm = cv2.findTransformECC(t, i, np.eye(3, dtype=np.float32), cv2.MOTION_HOMOGRAPHY, crit)
+        rho, M = ecc_homography(t, i)
+        assert abs(cc - rho) < 5e-4, (cc, rho)
+        assert _coord_diff(wm, M, *t.shape) < 1e-2
