@@ -10,6 +10,7 @@
 //             8x8 system (Cholesky, fp64) and updates the warp.  The planes of a pair (4 x 100 KB at 160^2) stay in L2 across the
 //             100 iterations; nothing returns to the host until the warp matrices are final.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -64,6 +65,31 @@ __device__ __forceinline__ float tap(const float* pl, int W, int H, int xx, int 
   return (xx >= 0 && xx < W && yy >= 0 && yy < H) ? __ldg(pl + yy * W + xx) : 0.f;
 }
 
+// one bilinear tap of (image, d/dx, d/dy) from the blurred image plane alone: the gradients are re-derived on the fly with the same
+// formula ecc_grad_kernel uses (bit-identical), so only ONE plane has to live in shared memory
+__device__ __forceinline__ void tap3(const float* b, int W, int H, int xx, int yy, float w, float& iw, float& gx, float& gy) {
+  // branch-free: out-of-image taps get weight 0 and a clamped (valid) address
+  const bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H;
+  w = ok ? w : 0.f;
+  xx = min(max(xx, 0), W - 1);
+  yy = min(max(yy, 0), H - 1);
+  const int xp = xx + 1 < W ? xx + 1 : W - 2, xm = xx > 0 ? xx - 1 : 1;      // BORDER_REFLECT_101 neighbours
+  const int yp = yy + 1 < H ? yy + 1 : H - 2, ym = yy > 0 ? yy - 1 : 1;
+  const float* row = b + yy * W;
+  iw = fmaf(w, row[xx], iw);
+  gx = fmaf(w, 0.5f * (row[xp] - row[xm]), gx);
+  gy = fmaf(w, 0.5f * (b[yp * W + xx] - b[ym * W + xx]), gy);
+}
+
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // 1 ulp: ~1e-5 px on a 160-px coordinate, far inside the ECC tolerance
+  return y;
+}
+
+// SMEM: the pair's blurred image and template planes are copied into shared memory once (2 x 100 KB at 160 x 160) and all taps of
+// all iterations are served from there (832 pairs: 52.7 -> 29.7 ms together with the branch-free taps); otherwise they are read through L2.
+template <bool SMEM>
 __global__ void __launch_bounds__(ECC_THREADS) ecc_iterate_kernel(const fbanet_ecc_params p) {
   const int f = blockIdx.x;
   const int fpb = p.frames_per_burst;
@@ -74,6 +100,12 @@ __global__ void __launch_bounds__(ECC_THREADS) ecc_iterate_kernel(const fbanet_e
   const float* img = p.planes + (int64_t)f * 3 * hw;
   const float* gxp_ = img + hw;
   const float* gyp_ = img + 2 * hw;
+  extern __shared__ __align__(16) float ecc_sm[];
+  if (SMEM) {
+    for (int i = threadIdx.x; i < npx; i += ECC_THREADS) { ecc_sm[i] = __ldg(img + i); ecc_sm[npx + i] = __ldg(tmpl + i); }
+  }
+  const float* img_s = ecc_sm;
+  const float* tmpl_s = ecc_sm + npx;
 
   __shared__ double red[ECC_THREADS / 32][ECC_NSUM];
   __shared__ double Msh[9];
@@ -92,23 +124,34 @@ __global__ void __launch_bounds__(ECC_THREADS) ecc_iterate_kernel(const fbanet_e
     float a[ECC_NSUM];
 #pragma unroll
     for (int k = 0; k < ECC_NSUM; ++k) a[k] = 0.f;
-    for (int r = threadIdx.x; r < npx; r += ECC_THREADS) {
-      const int py = r / W, px = r - py * W;
+    const int step_y = ECC_THREADS / W, step_x = ECC_THREADS - step_y * W;   // r += ECC_THREADS without a division per pixel
+    int py = threadIdx.x / W, px = threadIdx.x - py * W;
+    for (int r = threadIdx.x; r < npx; r += ECC_THREADS, px += step_x, py += step_y) {
+      if (px >= W) { px -= W; ++py; }
       const float x = (float)px, y = (float)py;
-      const float rden = 1.0f / fmaf(m20, x, fmaf(m21, y, m22));
+      const float rden = SMEM ? rcp_fast(fmaf(m20, x, fmaf(m21, y, m22))) : 1.0f / fmaf(m20, x, fmaf(m21, y, m22));
       const float sx = fmaf(m00, x, fmaf(m01, y, m02)) * rden, sy = fmaf(m10, x, fmaf(m11, y, m12)) * rden;
       const float fx = floorf(sx), fy = floorf(sy);
       const float ax = sx - fx, ay = sy - fy;
       const int x0 = (int)fminf(fmaxf(fx, -2.f), (float)W + 1.f), y0 = (int)fminf(fmaxf(fy, -2.f), (float)H + 1.f);
       const float w00 = (1.f - ay) * (1.f - ax), w01 = (1.f - ay) * ax, w10 = ay * (1.f - ax), w11 = ay * ax;
-      const float iw = w00 * tap(img, W, H, x0, y0) + w01 * tap(img, W, H, x0 + 1, y0) + w10 * tap(img, W, H, x0, y0 + 1) + w11 * tap(img, W, H, x0 + 1, y0 + 1);
-      const float gxw = w00 * tap(gxp_, W, H, x0, y0) + w01 * tap(gxp_, W, H, x0 + 1, y0) + w10 * tap(gxp_, W, H, x0, y0 + 1) + w11 * tap(gxp_, W, H, x0 + 1, y0 + 1);
-      const float gyw = w00 * tap(gyp_, W, H, x0, y0) + w01 * tap(gyp_, W, H, x0 + 1, y0) + w10 * tap(gyp_, W, H, x0, y0 + 1) + w11 * tap(gyp_, W, H, x0 + 1, y0 + 1);
+      float iw, gxw, gyw;
+      if (SMEM) {
+        iw = gxw = gyw = 0.f;
+        tap3(img_s, W, H, x0, y0, w00, iw, gxw, gyw);
+        tap3(img_s, W, H, x0 + 1, y0, w01, iw, gxw, gyw);
+        tap3(img_s, W, H, x0, y0 + 1, w10, iw, gxw, gyw);
+        tap3(img_s, W, H, x0 + 1, y0 + 1, w11, iw, gxw, gyw);
+      } else {
+        iw = w00 * tap(img, W, H, x0, y0) + w01 * tap(img, W, H, x0 + 1, y0) + w10 * tap(img, W, H, x0, y0 + 1) + w11 * tap(img, W, H, x0 + 1, y0 + 1);
+        gxw = w00 * tap(gxp_, W, H, x0, y0) + w01 * tap(gxp_, W, H, x0 + 1, y0) + w10 * tap(gxp_, W, H, x0, y0 + 1) + w11 * tap(gxp_, W, H, x0 + 1, y0 + 1);
+        gyw = w00 * tap(gyp_, W, H, x0, y0) + w01 * tap(gyp_, W, H, x0 + 1, y0) + w10 * tap(gyp_, W, H, x0, y0 + 1) + w11 * tap(gyp_, W, H, x0 + 1, y0 + 1);
+      }
       const float rx = rintf(sx), ry = rintf(sy);             // warped all-ones mask, nearest, border 0
       const bool mask = rx >= 0.f && rx <= (float)(W - 1) && ry >= 0.f && ry <= (float)(H - 1);
-      const float t = __ldg(tmpl + r);
+      const float t = SMEM ? tmpl_s[r] : __ldg(tmpl + r);
       // image_jacobian_homo_ECC
-      const float den_ = 1.0f / fmaf(x, m20, fmaf(y, m21, 1.0f));
+      const float den_ = SMEM ? rcp_fast(fmaf(x, m20, fmaf(y, m21, 1.0f))) : 1.0f / fmaf(x, m20, fmaf(y, m21, 1.0f));
       const float hx = -fmaf(x, m00, fmaf(y, m01, m02)) * den_, hy = -fmaf(x, m10, fmaf(y, m11, m12)) * den_;
       const float gxp = gxw * den_, gyp = gyw * den_;
       const float tmp = fmaf(hx, gxp, hy * gyp);
@@ -216,6 +259,19 @@ extern "C" int fbanet_ecc_homography_sm100(const fbanet_ecc_params* p, void* str
   if (!p || !p->planes || !p->warp || p->frames <= 0 || p->frames_per_burst < 2 || p->frames % p->frames_per_burst || p->H < 3 || p->W < 3 ||
       p->max_iters < 1 || (int64_t)p->H * p->W > (int64_t)1 << 28)
     return FBANET_E_BADSHAPE;
-  ecc_iterate_kernel<<<p->frames, ECC_THREADS, 0, (cudaStream_t)stream>>>(*p);
+  // both planes of a pair in shared memory when they fit (160 x 160: 200 KB); FBANET_ECC_SMEM=0 forces the L2 path (experiments)
+  const size_t need = (size_t)2 * p->H * p->W * sizeof(float);
+  static const char* env = getenv("FBANET_ECC_SMEM");
+  if (need <= 200 * 1024 && !(env && env[0] == '0')) {
+    static size_t opted = 0;
+    if (need > opted) {
+      cudaError_t e = cudaFuncSetAttribute(ecc_iterate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+      if (e != cudaSuccess) { cudaGetLastError(); set_last_error(e); return FBANET_E_LAUNCH; }
+      opted = need;
+    }
+    ecc_iterate_kernel<true><<<p->frames, ECC_THREADS, need, (cudaStream_t)stream>>>(*p);
+  } else {
+    ecc_iterate_kernel<false><<<p->frames, ECC_THREADS, 0, (cudaStream_t)stream>>>(*p);
+  }
   return check_launch();
 }

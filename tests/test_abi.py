@@ -34,6 +34,21 @@ def test_bad_params_are_rejected_without_a_gpu(lib):
     assert lib.fbanet_window_attention_sm100(ctypes.byref(a), None) == -1
     w = _lib.WarpParams()
     assert lib.fbanet_warp_sm100(ctypes.byref(w), None) == -1
+    # the front-end / multi-GPU entry points added for SURVEY 8e / 8f-4 refuse empty or inconsistent requests the same way
+    for fn, st in (("fbanet_flow_warp_sm100", _lib.FlowWarpParams), ("fbanet_ecc_prepare_sm100", _lib.EccPrepareParams),
+                   ("fbanet_ecc_homography_sm100", _lib.EccParams), ("fbanet_tile_divide_banded_sm100", _lib.TileBandParams),
+                   ("fbanet_tile_merge_banded_sm100", _lib.TileBandParams)):
+        assert getattr(lib, fn)(ctypes.byref(st()), None) == -1, fn
+    b = _lib.TileBandParams()
+    b.tiles, b.nbands, b.H, b.W, b.T, b.C, b.psize, b.overlap, b.tile_end, b.scale = 1, 2, 50, 70, 1, 1, 20, 10, 1, 1
+    b.band[0], b.band[1] = 1, 1
+    b.row0[0], b.row0[1], b.row0[2] = 0, 25, 49          # bands must tile [0, H) exactly
+    assert lib.fbanet_tile_divide_banded_sm100(ctypes.byref(b), None) == -1
+    b.row0[2], b.row0[1] = 50, 0                          # empty band
+    assert lib.fbanet_tile_divide_banded_sm100(ctypes.byref(b), None) == -1
+    e = _lib.EccParams()
+    e.planes, e.warp, e.frames, e.frames_per_burst, e.H, e.W, e.max_iters = 1, 1, 7, 2, 16, 16, 10   # 7 frames are not whole bursts of 2
+    assert lib.fbanet_ecc_homography_sm100(ctypes.byref(e), None) == -1
 
 
 def test_missing_library_fails_loudly(monkeypatch):
