@@ -556,6 +556,20 @@ class BaseModel(nn.Module):
         return self.forward_stages(x, None)
 
     @torch.no_grad()
+    def forward_unaligned(self, x: torch.Tensor, max_iters: int = 100, eps: float = 1e-10, return_alignment: bool = False):
+        """Raw (unregistered) bursts in, SR out: the reference's offline pre-processing and its model in one device-resident call --
+        ECC homography of every frame against frame 0 (``cv2.findTransformECC``, ``homography_alignment.py:19-45``), bilinear warp
+        with those matrices (``cv2.warpPerspective(..., WARP_INVERSE_MAP)``, ``:46-55``), then :meth:`forward`.  Frames whose ECC
+        fails (cv2 would raise) keep the identity.  ``return_alignment``: also return ``(M, rho, iters)``."""
+        from . import ops
+        x = x.contiguous().float()
+        M, rho, iters = ops.ecc_homography_burst(x, max_iters=max_iters, eps=eps)
+        eye = torch.eye(3, dtype=M.dtype, device=M.device)
+        M = torch.where((iters < 0)[..., None, None], eye, M)
+        y = self.forward(ops.warp_burst(x, M))
+        return (y, (M, rho, iters)) if return_alignment else y
+
+    @torch.no_grad()
     def forward_fhwc(self, x: torch.Tensor) -> torch.Tensor:
         """The reference's JAX signature: ``x [F,H,W,C] -> [4H,4W,C]`` (models/fba_net.py:242)."""
         return self.forward(x.permute(0, 3, 1, 2).unsqueeze(0)).squeeze(0).permute(1, 2, 0)

@@ -210,3 +210,30 @@ def test_raw_config_with_warp_front_end_bf16(cuda):
     got = m(xw).cpu()
     assert got.shape == (1, 4, 320, 320)
     assert psnr(got, ref) > 40.0
+
+
+def test_forward_unaligned_registers_then_restores(cuda):
+    """8f-4 + the forward in one call: a burst whose frames are shifted copies of the base frame must, after the on-device ECC +
+    warp, give (nearly) the SR image of the perfectly aligned burst -- and be far from the SR image of the unaligned one."""
+    from fbanet_b200 import ops
+    from oracle.fbanet_oracle import psnr
+    _, m = _pair(SMALL, "fp32", cuda)
+    S, T, C = SMALL["img_size"], SMALL["num_frames"], SMALL["in_channels"]
+    g = torch.Generator().manual_seed(11)
+    base = torch.rand(1, 1, C, S + 16, S + 16, generator=g)
+    k = torch.ones(C, 1, 5, 5) / 25.0
+    for _ in range(3):
+        base = torch.nn.functional.conv2d(torch.nn.functional.pad(base[:, 0], (2, 2, 2, 2), mode="reflect"), k, groups=C)[:, None]
+    base = base[..., 8:-8, 8:-8].contiguous()
+    base = (base - base.amin()) / (base.amax() - base.amin())
+    aligned = base.expand(1, T, C, S, S).contiguous().to(cuda)
+    M = torch.eye(3, dtype=torch.float64).repeat(1, T, 1, 1)
+    M[0, 1:, :2, 2] = torch.rand(T - 1, 2, generator=g, dtype=torch.float64) * 3 - 1.5
+    shifted = ops.warp_burst(aligned, M)
+    shifted[:, 0] = aligned[:, 0]
+    y_ref = m(aligned).cpu()
+    y_raw = m(shifted).cpu()
+    y_reg, (Mh, rho, iters) = m.forward_unaligned(shifted, return_alignment=True)
+    assert (iters[:, 1:] > 0).all() and (rho[:, 1:] > 0.98).all()
+    inner = (slice(None), slice(None), slice(32, -32), slice(32, -32))     # the warp leaves a zero border
+    assert psnr(y_reg.cpu()[inner], y_ref[inner]) > psnr(y_raw[inner], y_ref[inner]) + 3.0
