@@ -366,23 +366,55 @@ __global__ void __launch_bounds__(256) assemble_kernel(const fbanet_assemble_par
   }
 }
 
+// The bf16-path shape of the same assembly: fp32 SR rows of 8 columns (0..3 hi-weight part, 4..7 lo-weight part), C <= 4.
+// grid = (x blocks, rows, images): no 64-bit divisions, the pixel's 32 bytes arrive as two 16-byte loads (the generic kernel's six
+// scalar loads and three 64-bit divisions per pixel held it at 2.5 TB/s), same arithmetic -> bit-identical output.
+__global__ void __launch_bounds__(256) assemble_f32x8_kernel(const fbanet_assemble_params p) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= p.W) return;
+  const int y = blockIdx.y;
+  const int Hb = p.H >> 2, Wb = p.W >> 2;
+  float sy = 0.25f * (y + 0.5f) - 0.5f, sx = 0.25f * (x + 0.5f) - 0.5f;
+  sy = sy < 0.f ? 0.f : sy;
+  sx = sx < 0.f ? 0.f : sx;
+  const int yb = (int)sy, xb = (int)sx;
+  const int y1 = yb + (yb < Hb - 1 ? 1 : 0), x1 = xb + (xb < Wb - 1 ? 1 : 0);
+  const float wy = sy - yb, wx = sx - xb, hy = 1.f - wy, hx = 1.f - wx;
+  for (int n = blockIdx.z; n < p.N; n += gridDim.z) {
+    const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.sr) + (((int64_t)n * p.H + y) * p.W + x) * 8);
+    const float4 hi = __ldg(s), lo = __ldg(s + 1);
+    const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < p.C) {
+        const float* bp = p.base + (int64_t)n * p.base_img_stride + (int64_t)c * Hb * Wb;
+        const float bl = hy * (hx * __ldg(bp + yb * Wb + xb) + wx * __ldg(bp + yb * Wb + x1)) +
+                         wy * (hx * __ldg(bp + y1 * Wb + xb) + wx * __ldg(bp + y1 * Wb + x1));
+        p.out[(((int64_t)n * p.C + c) * p.H + y) * p.W + x] = (hv[c] + lv[c]) + bl;
+      }
+    }
+  }
+}
+
 // channels-last view -> space-to-depth(2), one thread per 16-byte vector of the destination
 template <typename T>
 __global__ void __launch_bounds__(256) s2d_kernel(const fbanet_s2d_params p) {
+  // grid = (vectors of one output row, output rows, images): 32-bit index math only (the flat 64-bit version spent five 64-bit
+  // divisions per 16-byte vector)
   constexpr int V = Vec16<T>::N;
   const int cg = p.C / V, Ho = p.H / 2, Wo = p.W / 2;
-  const int64_t total = (int64_t)p.N * Ho * Wo * 4 * cg;
+  const int row_vecs = Wo * 4 * cg;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= row_vecs) return;
+  const int c0 = (i % cg) * V;
+  const int r = i / cg;
+  const int sub = r & 3, x = r >> 2;
+  const int y = blockIdx.y;
   const T* src = reinterpret_cast<const T*>(p.src);
   T* dst = reinterpret_cast<T*>(p.dst);
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int c0 = (int)(idx % cg) * V;
-    int64_t r = idx / cg;
-    const int sub = (int)(r % 4); r /= 4;
-    const int x = (int)(r % Wo); r /= Wo;
-    const int y = (int)(r % Ho);
-    const int64_t n = r / Ho;
-    const T* s = src + n * p.img_stride + ((int64_t)(2 * y + (sub >> 1)) * p.W + (2 * x + (sub & 1))) * p.ld + c0;
-    *reinterpret_cast<uint4*>(dst + idx * V) = *reinterpret_cast<const uint4*>(s);
+  for (int n = blockIdx.z; n < p.N; n += gridDim.z) {
+    const T* s = src + (int64_t)n * p.img_stride + ((int64_t)(2 * y + (sub >> 1)) * p.W + (2 * x + (sub & 1))) * p.ld + c0;
+    *reinterpret_cast<uint4*>(dst + (((int64_t)n * Ho + y) * row_vecs + i) * V) = *reinterpret_cast<const uint4*>(s);
   }
 }
 
@@ -1038,6 +1070,11 @@ extern "C" int fbanet_head_conv_sm100(const fbanet_head_conv_params* p, void* st
 extern "C" int fbanet_assemble_sm100(const fbanet_assemble_params* p, void* stream) {
   if (!p || !p->sr || !p->base || !p->out || p->N <= 0 || p->C <= 0 || p->Cp < p->C || (p->H % 4) || (p->W % 4) || p->lo_offset < 0 || (p->lo_offset > 0 && p->lo_offset + p->C > p->Cp)) return FBANET_E_BADSHAPE;
   const int64_t total = (int64_t)p->N * p->H * p->W;
+  if (p->dtype == FBANET_F32 && p->Cp == 8 && p->lo_offset == 4 && p->C <= 4 && ((uintptr_t)p->sr % 16) == 0 && p->H <= 65535) {
+    const dim3 grid((unsigned)ceil_div(p->W, 256), (unsigned)p->H, (unsigned)(p->N < 65535 ? p->N : 65535));
+    assemble_f32x8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+    return check_launch();
+  }
   if (p->dtype == FBANET_F32) assemble_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
   else if (p->dtype == FBANET_BF16) assemble_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
   else return FBANET_E_DTYPE;
@@ -1049,9 +1086,10 @@ extern "C" int fbanet_space_to_depth_sm100(const fbanet_s2d_params* p, void* str
   const int v = p->dtype == FBANET_F32 ? 4 : 8;
   if (p->C % v) return FBANET_E_BADSHAPE;
   if ((p->ld % v) || (p->img_stride % v) || ((uintptr_t)p->src % 16) || ((uintptr_t)p->dst % 16)) return FBANET_E_ALIGN;
-  const int64_t total = (int64_t)p->N * (p->H / 2) * (p->W / 2) * 4 * (p->C / v);
-  if (p->dtype == FBANET_F32) s2d_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
-  else if (p->dtype == FBANET_BF16) s2d_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  if (p->H / 2 > 65535) return FBANET_E_BADSHAPE;
+  const dim3 grid((unsigned)ceil_div((int64_t)(p->W / 2) * 4 * (p->C / v), 256), (unsigned)(p->H / 2), (unsigned)(p->N < 65535 ? p->N : 65535));
+  if (p->dtype == FBANET_F32) s2d_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+  else if (p->dtype == FBANET_BF16) s2d_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
   else return FBANET_E_DTYPE;
   return check_launch();
 }
