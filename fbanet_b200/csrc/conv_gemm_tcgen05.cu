@@ -13,6 +13,7 @@
 // (one lane), warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> bias/act/residual ->
 // bf16 -> 16-byte global stores, each thread owns one pixel row).
 #include <cuda.h>
+#include <type_traits>
 #include <stdlib.h>
 #include <string.h>
 
@@ -66,6 +67,8 @@ struct TcParams {
   int b_slots, b_resident;
   int tma_store;          // 1: each epilogue warp stages 32x64 bf16 sub-tiles in smem and stores them with TMA
   int stage_bufs;         // staging buffers per epilogue warp (2, or 1 when shared memory is tight)
+  int tapsum;             // > 0: tap-stacked 3x3 conv with `tapsum` outputs per tap (see the TAPSUM epilogue); tiles step by (tw-2, th-2)
+  int step_x, step_y, org;  // tile origin = tile index * step + org (tw, th, 0 except in tapsum mode: tw-2, th-2, -1)
   int nacc, nacc_shift;   // accumulator stages in TMEM (4 when 4 x BN <= 512 columns, else 2) and log2 of it
   int debug;              // FBANET_TC_DEBUG timing experiments (results are garbage): 1 = epilogue only hands the accumulator back,
                           // 2 = no tcgen05.mma issued (commits only), 4 = A producer arrives without loading
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
   }
   if (warp >= 4) {   // this CTA owns N-tile blockIdx.x % n_tiles_n for its whole life: stage its bias once
     const int i = threadIdx.x - 128;
-    if (i < 256) bias_s[i] = (p.bias && i < BN) ? __ldg(p.bias + (blockIdx.x % p.n_tiles_n) * BN + i) : 0.f;
+    if (i < 256) bias_s[i] = (p.bias && i < (p.tapsum ? p.Cout_store : BN)) ? __ldg(p.bias + (blockIdx.x % p.n_tiles_n) * BN + i) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
     uint32_t phase = 0;
     for (int mt = mt0; mt < p.m_tiles; mt += mt_step) {
       const int img = mt / tiles_per_img, r = mt % tiles_per_img;
-      const int y0 = (r / p.tiles_x) * p.th, x0 = (r % p.tiles_x) * p.tw;
+      const int y0 = (r / p.tiles_x) * p.step_y + p.org, x0 = (r % p.tiles_x) * p.step_x + p.org;
       for (int u = 0; u < units; ++u) {
         mbar_wait(&a_empty[slot], phase ^ 1);
         if (p.debug & 4) {
@@ -359,8 +362,13 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
       if (mt0 < p.m_tiles)
         for (int s = 0; s < p.nsteps; ++s) {
           if (elect_one()) {
-            mbar_expect_tx(&b_full[s], b_bytes);
-            tma_load_2d(smem_b + (size_t)s * b_bytes, &p.bmap, &b_full[s], bk(s), nt * BN);
+            if (p.tapsum) {   // weights [co][tap][ci] viewed as {ci, co, tap}: the box lands as rows tap * Ct + co
+              mbar_expect_tx(&b_full[s], (uint32_t)(9 * p.tapsum * TC_BK * 2));
+              tma_load_3d(smem_b + (size_t)s * b_bytes, &p.bmap, &b_full[s], s * TC_BK, 0, 0);
+            } else {
+              mbar_expect_tx(&b_full[s], b_bytes);
+              tma_load_2d(smem_b + (size_t)s * b_bytes, &p.bmap, &b_full[s], bk(s), nt * BN);
+            }
           }
           __syncwarp();
         }
@@ -459,6 +467,83 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[it & nacc_mask]);
+      }
+    } else if (p.tapsum) {
+      // ---- TAPSUM epilogue: 3x3 convs with a handful of outputs (the FAF score conv 64 -> 2, the final conv 64 -> 3 as hi/lo
+      // halves) are operand-fetch bound as implicit GEMMs: 36 MMAs per 128 pixels whatever N is (42 cycles each at N = 16,
+      // tools/ubench/umma.cu).  Here the nine taps are stacked along N instead -- B rows = tap * Ct + co -- so ONE pass of
+      // K/16 MMAs over a tile of 16 x 8 INPUT pixels yields P[q][tap][co] = W_tap . in[q] for every tap at once, and the
+      // convolution is the shifted sum  out[p][co] = bias + sum_tap P[p + off_tap][tap][co]  over the tile's 14 x 6 interior,
+      // done here through shared memory (rows padded to BN + 1 floats: the gather walks rows at a fixed column).
+      // Whole tiles alternate between the two sets of four epilogue warps; the other set only hands the accumulator back.
+      const int Ct = p.tapsum;
+      const int pst = BN + 1;
+      float* P = reinterpret_cast<float*>(smem_stage) + (size_t)slot * 128 * pst;
+      const int bar_id = 1 + slot;
+      for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
+        const int acc = it & nacc_mask;
+        const uint32_t acc_phase = (it >> nacc_shift) & 1;
+        const bool mine = (it % TC_EPI_SLOTS) == slot;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        if (mine) {
+          const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+          float* prow = P + row * pst;
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            const int nc = BN - c0 >= 32 ? 32 : 16;
+            if (nc == 32) tmem_ld32(taddr0 + c0, v); else tmem_ld16(taddr0 + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nc) prow[c0 + j] = __uint_as_float(v[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (!mine) continue;
+        named_bar_sync(bar_id, 128);                       // the four lane quarters of this tile have written P
+        const int img = mt / tiles_per_img, r = mt % tiles_per_img;
+        const int oy = (r / p.tiles_x) * p.step_y + ly - 1, ox = (r % p.tiles_x) * p.step_x + lx - 1;
+        if (lx >= 1 && lx <= 14 && ly >= 1 && ly <= 6 && oy < p.Ho && ox < p.Wo) {
+          float* op = reinterpret_cast<float*>(p.out) + img * p.out_img_stride + ((int64_t)oy * p.Wo + ox) * p.out_ld;
+          const float* pc = P + ((ly - 1) * 16 + (lx - 1)) * pst;   // P row of tap (0,0) for this output pixel
+          auto gather = [&](auto ct_tag) {
+            constexpr int CT = decltype(ct_tag)::value;             // compile-time outputs per tap: all 9 * CT loads independent
+            float sacc[CT];
+#pragma unroll
+            for (int j = 0; j < CT; ++j) sacc[j] = bias_s[j];
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+#pragma unroll
+              for (int j = 0; j < CT; ++j) sacc[j] += pc[((t / 3) * 16 + (t % 3)) * pst + t * CT + j];
+            if (CT == 2) *reinterpret_cast<float2*>(op) = make_float2(sacc[0], sacc[1]);
+            else if (CT == 4) *reinterpret_cast<float4*>(op) = make_float4(sacc[0], sacc[1], sacc[2], sacc[3]);
+            else if (CT == 8) {
+              *reinterpret_cast<float4*>(op) = make_float4(sacc[0], sacc[1], sacc[2], sacc[3]);
+              *reinterpret_cast<float4*>(op + 4) = make_float4(sacc[4], sacc[5], sacc[6], sacc[7]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < CT; ++j) op[j] = sacc[j];
+            }
+          };
+          switch (Ct) {
+            case 1: gather(std::integral_constant<int, 1>{}); break;
+            case 2: gather(std::integral_constant<int, 2>{}); break;
+            case 3: gather(std::integral_constant<int, 3>{}); break;
+            case 4: gather(std::integral_constant<int, 4>{}); break;
+            case 8: gather(std::integral_constant<int, 8>{}); break;
+            default:
+              for (int j = 0; j < Ct; ++j) {
+                float sj = bias_s[j];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) sj += pc[((t / 3) * 16 + (t % 3)) * pst + t * Ct + j];
+                op[j] = sj;
+              }
+          }
+        }
+        named_bar_sync(bar_id, 128);                       // P is free for this set's next tile
       }
     } else if (p.tma_store) {
       // ---- per-warp staged epilogue.  A warp owns 32 pixel rows of the tile (its TMEM lane quarter), which form a
@@ -709,19 +794,28 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   static thread_local TcParams tp;  // ~2.6 KB; filled per call, passed by value
   memset(&tp, 0, sizeof(tp));
   const bool s2d = p->src_s2d != 0;
-  const bool halo = is_halo(p);
+  // tap-stacked mode for 3x3 convs with a handful of fp32 outputs (see the TAPSUM epilogue); FBANET_TC_TAPSUM=0 = plain halo conv
+  const char* tsenv = getenv("FBANET_TC_TAPSUM");
+  // (measured, batch 64: score conv 64 -> 2 @160^2 x 896 frames 1.67 -> 1.08 ms; with 8 outputs per tap -- the final conv's hi/lo
+  // rows -- the shared-memory gather costs what the MMAs save, 2.0 vs 1.9 ms, so the mode is limited to <= 4 outputs)
+  const bool tapsum = is_halo(p) && p->store_mode == FBANET_STORE_NHWC_F32 && p->Cout_store >= 1 && p->Cout_store <= 4 &&
+                      p->Cout_store <= p->Cout && !p->residual && p->act == FBANET_ACT_NONE && !(tsenv && tsenv[0] == '0') &&
+                      ((uintptr_t)p->out % 16) == 0 && (p->out_ld % (p->Cout_store >= 4 ? 4 : 2)) == 0 && (p->out_img_stride % 4) == 0;   // vector stores of the gather
+  const bool halo = is_halo(p) && !tapsum;
   // tile space = output pixels; for s2d sources the source view already has the output resolution
   const int Hs = s2d ? p->H / 2 : p->H, Ws = s2d ? p->W / 2 : p->W;
   if (Hs != p->Ho || Ws != p->Wo) return FBANET_E_BADSHAPE;
   int tw = 16, th = 8;
-  if (halo) { tw = TC_HALO_TW; th = TC_HALO_TH; } else pick_tile(p->Ho, p->Wo, &tw, &th);
+  if (halo) { tw = TC_HALO_TW; th = TC_HALO_TH; } else if (tapsum) { tw = 16; th = 8; } else pick_tile(p->Ho, p->Wo, &tw, &th);
   tp.tw = tw; tp.th = th;
-  tp.tiles_x = (p->Wo + tw - 1) / tw;
-  tp.tiles_y = (p->Ho + th - 1) / th;
+  tp.step_x = tapsum ? tw - 2 : tw; tp.step_y = tapsum ? th - 2 : th; tp.org = tapsum ? -1 : 0;
+  tp.tapsum = tapsum ? p->Cout_store : 0;
+  tp.tiles_x = (p->Wo + tp.step_x - 1) / tp.step_x;
+  tp.tiles_y = (p->Ho + tp.step_y - 1) / tp.step_y;
   tp.m_tiles = p->N * tp.tiles_x * tp.tiles_y;
   tp.N = p->N; tp.Ho = p->Ho; tp.Wo = p->Wo;
-  tp.BN = pick_bn(p->Cout, halo, conv_ctot(p));
-  tp.n_tiles_n = p->Cout / tp.BN;
+  tp.BN = tapsum ? (9 * p->Cout_store + 15) / 16 * 16 : pick_bn(p->Cout, halo, conv_ctot(p));
+  tp.n_tiles_n = tapsum ? 1 : p->Cout / tp.BN;
   tp.Cout = p->Cout; tp.Cout_store = p->Cout_store;
   tp.a_box_bytes = tw * th * TC_BK * 2;
   // Measured (profiles/r1_notes.md): the wide box wins 4-16 % for N tiles of 128 and for N = 16, where TMA / L2 traffic
@@ -749,7 +843,17 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   tp.ctot = ctot;
   const int taps = p->KH * p->KW;
   const int K = taps * ctot;
-  {
+  if (tapsum) {
+    // weights [Cout][tap][ctot] seen as {ci, co, tap}: one box {64, Ct, 9} lands as B rows tap * Ct + co
+    const cuuint64_t dims[3] = {(cuuint64_t)ctot, (cuuint64_t)p->Cout, 9};
+    const cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)ctot * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)p->Cout_store, 9};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&tp.bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p->weight), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return FBANET_E_BADSHAPE;
+  } else {
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)p->Cout};
     const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
     const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)tp.BN};
@@ -772,8 +876,8 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
     tp.nchunks = nch;
     ns = nch * 9;
   } else {
-    // K-step table in weight order: k = (tap * Ctot + concat channel)
-    for (int tap = 0; tap < taps; ++tap) {
+    // K-step table in weight order: k = (tap * Ctot + concat channel); tap-stacked mode: the taps live in N, one step per chunk
+    for (int tap = 0; tap < (tapsum ? 1 : taps); ++tap) {
       const int ky = tap / p->KW, kx = tap % p->KW;
       for (int s = 0; s < p->nsrc; ++s) {
         const int cc = s2d ? p->src[s].C / 4 : p->src[s].C;
@@ -788,8 +892,8 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
             st.dx = (int16_t)((rx - xs) / 2);
             st.c0 = (int16_t)((ys * 2 + xs) * cc + c0);
           } else {
-            st.dy = (int16_t)(ky - p->pad);
-            st.dx = (int16_t)(kx - p->pad);
+            st.dy = (int16_t)(tapsum ? 0 : ky - p->pad);
+            st.dx = (int16_t)(tapsum ? 0 : kx - p->pad);
             st.c0 = (int16_t)c0;
           }
         }
@@ -881,6 +985,11 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
         tp.tma_store = 1; tp.stage_bufs = bufs; stage_bytes = sb; epi_slots = slots; p0 = p1;
       }
     }
+  }
+  if (tapsum) {   // two P tiles (one per epilogue warp set) of 128 rows x (BN + 1) floats; weights must be resident
+    stage_bytes = 2 * 128 * (tp.BN + 1) * 4;
+    if (!plan(216 * 1024 - stage_bytes, &p0) || !p0.resident) return FBANET_E_UNSUPPORTED;
+    epi_slots = 2;
   }
   tp.b_resident = p0.resident; tp.a_slots = p0.a_slots; tp.b_slots = p0.b_slots;
   { const char* dbg = getenv("FBANET_TC_DEBUG"); tp.debug = dbg ? atoi(dbg) : 0; }

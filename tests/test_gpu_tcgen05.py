@@ -104,6 +104,28 @@ def test_tc_downsample_space_to_depth(cuda, cin, cout, hw):
     _check(out.permute(0, 3, 1, 2), ref)
 
 
+@pytest.mark.parametrize("cin,ct,h,w,n", [(64, 2, 160, 160, 2), (64, 1, 13, 29, 3), (128, 3, 40, 22, 2), (64, 4, 6, 14, 1), (192, 2, 7, 15, 2)])
+def test_tc_tapsum_conv3x3(cuda, cin, ct, h, w, n):
+    """3x3 convs with <= 4 fp32 outputs run tap-stacked (nine taps along N, shifted sum in the epilogue): must equal the plain
+    convolution, including images that are not multiples of the 14 x 6 interior, several K chunks, and the FBANET_TC_TAPSUM=0
+    fallback (same result from the halo-mode implicit GEMM)."""
+    import os
+    from fbanet_b200 import ops, _lib as L
+    x, wt, b = _r(n, cin, h, w, seed=1), _r(ct, cin, 3, 3, seed=2, scale=1 / math.sqrt(cin * 9)), _r(ct, seed=3, scale=0.1)
+    ref = F.conv2d(x, wt, b, padding=1)
+    wp = F.pad(_pack(wt, cuda), (0, 0, 0, 16 - ct)).contiguous()        # N padded to the tensor-core minimum, as the model packs it
+    bp = F.pad(b, (0, 16 - ct)).to(cuda)
+    outs = []
+    for mode in ("1", "0"):
+        os.environ["FBANET_TC_TAPSUM"] = mode
+        out = torch.full((n, h, w, ct), -7.0, device=cuda, dtype=torch.float32)   # odd widths (1, 3) take the halo path in both modes
+        ops.conv_gemm([_nhwc(x, cuda)], wp, out, kh=3, kw=3, pad=1, bias=bp, store_mode=L.STORE_NHWC_F32, cout_store=ct, impl=L.IMPL_TCGEN05)
+        _check(out.permute(0, 3, 1, 2), ref, tol=1e-2)
+        outs.append(out.cpu())
+    os.environ.pop("FBANET_TC_TAPSUM")
+    assert (outs[0] - outs[1]).abs().max() < 1e-4                        # same products, different summation order
+
+
 def test_tc_final_conv_nchw_base(cuda):
     from fbanet_b200 import ops, _lib as L
     x, w, b = _r(2, 64, 64, 96, seed=1), _r(3, 64, 3, 3, seed=2, scale=0.03), _r(3, seed=3)
