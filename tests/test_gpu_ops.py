@@ -577,3 +577,26 @@ def test_ecc_degenerate_pair_reports_failure(cuda):
     assert iters[0, 1].item() < 0 and rho[0, 1].item() == -1.0
     assert iters[0, 2].item() > 0 and rho[0, 2].item() > 0.999
     assert (M[0, 2].cpu() - torch.eye(3, dtype=torch.float64)).abs().max() < 1e-3
+
+
+def test_tile_kernels_match_vectors_from_the_reference_code(cuda):
+    """8f-1: the GPU tile gather / stitch (plain and row-band forms) against vectors produced by running the reference's own
+    utils/dataset_utils.py (tests/golden/make_golden_reference.py) -- bit exact."""
+    from fbanet_b200 import ops
+    from fbanet_b200.dist import band_rows
+    from tests_golden_helpers import tiling_reference
+    d, sr = tiling_reference()
+    ps, ov, sc = int(d["psize"]), int(d["overlap"]), int(d["scale"])
+    burst = torch.from_numpy(d["burst"])[0].to(cuda)
+    T, Cc, H, W = burst.shape
+    assert np.array_equal(ops.tile_divide(burst, ps, ov).cpu().numpy(), d["tiles"])
+    out = torch.zeros(Cc, sc * H, sc * W, device=cuda)
+    ops.tile_merge(torch.from_numpy(sr).to(cuda), out, H, W, ps, ov, sc)
+    assert np.array_equal(out.cpu().numpy(), d["merged"][0])
+    row0 = band_rows(H, 3)
+    bands = [burst[:, :, row0[k]:row0[k + 1]].contiguous() for k in range(3)]
+    n = d["tiles"].shape[0]
+    assert np.array_equal(ops.tile_divide_banded([b.data_ptr() for b in bands], row0, T, Cc, H, W, ps, ov, 0, n, cuda).cpu().numpy(), d["tiles"])
+    ob = [torch.zeros(Cc, sc * (row0[k + 1] - row0[k]), sc * W, device=cuda) for k in range(3)]
+    ops.tile_merge_banded(torch.from_numpy(sr).to(cuda), [b.data_ptr() for b in ob], row0, H, W, ps, ov, sc, 0, n)
+    assert np.array_equal(torch.cat(ob, 1).cpu().numpy(), d["merged"][0])

@@ -118,3 +118,40 @@ def test_band_rows_and_halo_sources(H, world):
         assert halo_sources(H, 80, 40, (12, 14), r) == {7: 135, 6: 25}   # rows 920..1079; the padded rows reflect back inside
     tot = halo_sources(H, min(80, H), min(40, H - 1), (0, -(-H // min(80, H))), r)
     assert sum(tot.values()) == H                                        # all tile rows together touch every image row once
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/fba_net/utils/model_utils.py"), reason="reference tree only exists in the build container")
+def test_reference_checkpoint_helpers_accept_our_model(tmp_path):
+    """Drop-in boundary exercised with the reference's OWN code: `fba_net/utils/model_utils.py` (torch-only) is loaded
+    by file path and its `save_checkpoint` / `load_checkpoint` / `load_checkpoint_multigpu` / `load_start_epoch` / `load_optim`
+    are run against our `BaseModel` -- including the `module.`-prefixed keys a `DataParallel` run saves -- and against files
+    written by our helpers, and vice versa."""
+    import importlib.util
+    import torch
+    from fbanet_b200 import BaseModel
+    from fbanet_b200.utils import model_utils as ours
+    spec = importlib.util.spec_from_file_location("ref_model_utils", "/root/reference/fba_net/utils/model_utils.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    cfg = dict(num_frames=4, img_size=40, in_channels=3, embed_dim=32, window_length=10, token_projection="linear", token_mlp="leff")
+    a, b = BaseModel(**cfg, seed=1), BaseModel(**cfg, seed=2)
+    opt = torch.optim.AdamW(a.parameters(), lr=3e-4)
+    state = {"epoch": 7, "state_dict": a.state_dict(), "optimizer": opt.state_dict()}
+    ref.save_checkpoint(str(tmp_path), state, "ref")                       # the reference writes ...
+    path = os.path.join(str(tmp_path), "model_epoch_7_ref.pth")
+    ours.load_checkpoint(b, path)                                          # ... we read
+    assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), b.state_dict().values()))
+    assert ours.load_start_epoch(path) == ref.load_start_epoch(path) == 7
+    assert ours.load_optim(torch.optim.AdamW(b.parameters(), lr=1.0), path) == ref.load_optim(torch.optim.AdamW(b.parameters(), lr=1.0), path) == 3e-4
+    c = BaseModel(**cfg, seed=3)
+    ours.save_checkpoint(str(tmp_path), {"epoch": 8, "state_dict": {"module." + k: v for k, v in a.state_dict().items()}, "optimizer": opt.state_dict()}, "ours")
+    path2 = os.path.join(str(tmp_path), "model_epoch_8_ours.pth")
+    ref.load_checkpoint(c, path2)                                          # we write (DataParallel-style keys), the reference's loader reads
+    assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), c.state_dict().values()))
+    d = BaseModel(**cfg, seed=4)
+    ref.load_checkpoint_multigpu(d, path2)
+    assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), d.state_dict().values()))
+    ref.freeze(d)
+    assert ref.is_frozen(d) and ours.is_frozen(d)
+    ours.unfreeze(d)
+    assert not ref.is_frozen(d)

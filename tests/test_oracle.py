@@ -217,3 +217,18 @@ def test_ecc_oracle_matches_cv2():
         rho, M = ecc_homography(t, i)
         assert abs(cc - rho) < 5e-4, (cc, rho)
         assert _coord_diff(wm, M, *t.shape) < 1e-2
+
+
+def test_tiling_oracle_matches_vectors_from_the_reference_code():
+    """8f-1 pin: `tests/golden/tiling_reference.npz` was produced by executing the reference's own
+    `utils/dataset_utils.py::tensor_divide_burst / tensor_merge` (tests/golden/make_golden_reference.py); the restatement must
+    reproduce it bit for bit."""
+    import numpy as np
+    from oracle.fbanet_oracle import tensor_divide_burst, tensor_merge
+    from tests_golden_helpers import tiling_reference
+    d, sr = tiling_reference()
+    ps, ov, sc = int(d["psize"]), int(d["overlap"]), int(d["scale"])
+    burst = torch.from_numpy(d["burst"])
+    assert np.array_equal(tensor_divide_burst(burst, ps, ov).numpy(), d["tiles"])
+    H, W = burst.shape[-2:]
+    assert np.array_equal(tensor_merge(torch.from_numpy(sr), (sc * H, sc * W), sc * ps, sc * ov).numpy(), d["merged"])
