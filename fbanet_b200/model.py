@@ -510,6 +510,8 @@ class BaseModel(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("fbanet_b200.BaseModel runs on CUDA tensors only (use infer_host for host buffers); no CPU fallback")
         x = x.contiguous().float()
+        if x.shape[0] == 0:   # empty batch: nothing to launch
+            return torch.empty((0, self.in_channels, 4 * self.img_size, 4 * self.img_size), device=x.device, dtype=torch.float32)
         P = self.packed()
         st = stages
         B, Fr, Cin, S, _ = x.shape
@@ -606,6 +608,8 @@ class BaseModel(nn.Module):
         B = burst.shape[0]
         if out is None:
             out = torch.empty((B, self.in_channels, 4 * self.img_size, 4 * self.img_size), dtype=torch.float32, pin_memory=True)
+        if B == 0:
+            return out
         chunk = chunk or self.host_chunk
         if isinstance(chunk, int):
             sizes = [max(1, min(B, chunk))] * ((B + max(1, min(B, chunk)) - 1) // max(1, min(B, chunk)))

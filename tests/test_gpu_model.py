@@ -261,3 +261,14 @@ def test_full_resolution_row_bands_two_gpus(cuda):
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
     res = json.loads(line)
     assert res["bit_identical"] and res["n_gpus"] == 2 and res["halo_bytes_read_from_peers_per_image"] > 0
+
+
+def test_empty_batch(cuda):
+    """An empty batch is a valid input (a shard can be empty when bursts < ranks): empty output, no launch, on both entry points."""
+    _, m = _pair(SMALL, "bf16", cuda)
+    S, T, C = SMALL["img_size"], SMALL["num_frames"], SMALL["in_channels"]
+    y = m(torch.empty(0, T, C, S, S, device=cuda))
+    assert y.shape == (0, C, 4 * S, 4 * S) and y.dtype == torch.float32
+    assert m.infer_host(torch.empty(0, T, C, S, S)).shape == (0, C, 4 * S, 4 * S)
+    with pytest.raises(AssertionError):
+        m(torch.empty(1, T, C, S + 1, S, device=cuda))      # wrong frame size: the reference's shape assert (models/fba_net.py:244)
