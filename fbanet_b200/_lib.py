@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBANET_B200_LIB") or os.path.join(_HERE, "csrc", "libfbanet_b200.so")   # env override: A/B two builds in one process tree
-ABI_VERSION = 15
+ABI_VERSION = 16
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -38,7 +38,7 @@ class ConvParams(C.Structure):
         ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
         ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32), ("Cout_store", C.c_int32),
         ("act", C.c_int32), ("store_mode", C.c_int32), ("res_ld", C.c_int32), ("out_ld", C.c_int32),
-        ("src_s2d", C.c_int32), ("_pad", C.c_int32),
+        ("src_s2d", C.c_int32), ("fold_hi_lo", C.c_int32),
         ("ln_stats", C.c_void_p), ("_reserved", C.c_void_p),
     ]
 

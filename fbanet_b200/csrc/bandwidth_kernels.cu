@@ -369,6 +369,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(const fbanet_assemble_par
 // The bf16-path shape of the same assembly: fp32 SR rows of 8 columns (0..3 hi-weight part, 4..7 lo-weight part), C <= 4.
 // grid = (x blocks, rows, images): no 64-bit divisions, the pixel's 32 bytes arrive as two 16-byte loads (the generic kernel's six
 // scalar loads and three 64-bit divisions per pixel held it at 2.5 TB/s), same arithmetic -> bit-identical output.
+template <int CP>   // 8: hi columns 0..3 + lo columns 4..7; 4: already summed (fold_hi_lo conv)
 __global__ void __launch_bounds__(256) assemble_f32x8_kernel(const fbanet_assemble_params p) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= p.W) return;
@@ -381,8 +382,8 @@ __global__ void __launch_bounds__(256) assemble_f32x8_kernel(const fbanet_assemb
   const int y1 = yb + (yb < Hb - 1 ? 1 : 0), x1 = xb + (xb < Wb - 1 ? 1 : 0);
   const float wy = sy - yb, wx = sx - xb, hy = 1.f - wy, hx = 1.f - wx;
   for (int n = blockIdx.z; n < p.N; n += gridDim.z) {
-    const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.sr) + (((int64_t)n * p.H + y) * p.W + x) * 8);
-    const float4 hi = __ldg(s), lo = __ldg(s + 1);
+    const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.sr) + (((int64_t)n * p.H + y) * p.W + x) * CP);
+    const float4 hi = __ldg(s), lo = CP == 8 ? __ldg(s + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__(256) assemble_f32x8_kernel(const fbanet_assemb
         const float* bp = p.base + (int64_t)n * p.base_img_stride + (int64_t)c * Hb * Wb;
         const float bl = hy * (hx * __ldg(bp + yb * Wb + xb) + wx * __ldg(bp + yb * Wb + x1)) +
                          wy * (hx * __ldg(bp + y1 * Wb + xb) + wx * __ldg(bp + y1 * Wb + x1));
-        p.out[(((int64_t)n * p.C + c) * p.H + y) * p.W + x] = (hv[c] + lv[c]) + bl;
+        p.out[(((int64_t)n * p.C + c) * p.H + y) * p.W + x] = (CP == 8 ? hv[c] + lv[c] : hv[c]) + bl;
       }
     }
   }
@@ -1070,9 +1071,11 @@ extern "C" int fbanet_head_conv_sm100(const fbanet_head_conv_params* p, void* st
 extern "C" int fbanet_assemble_sm100(const fbanet_assemble_params* p, void* stream) {
   if (!p || !p->sr || !p->base || !p->out || p->N <= 0 || p->C <= 0 || p->Cp < p->C || (p->H % 4) || (p->W % 4) || p->lo_offset < 0 || (p->lo_offset > 0 && p->lo_offset + p->C > p->Cp)) return FBANET_E_BADSHAPE;
   const int64_t total = (int64_t)p->N * p->H * p->W;
-  if (p->dtype == FBANET_F32 && p->Cp == 8 && p->lo_offset == 4 && p->C <= 4 && ((uintptr_t)p->sr % 16) == 0 && p->H <= 65535) {
+  if (p->dtype == FBANET_F32 && ((p->Cp == 8 && p->lo_offset == 4) || (p->Cp == 4 && p->lo_offset == 0)) && p->C <= 4 && ((uintptr_t)p->sr % 16) == 0 &&
+      p->H <= 65535) {
     const dim3 grid((unsigned)ceil_div(p->W, 256), (unsigned)p->H, (unsigned)(p->N < 65535 ? p->N : 65535));
-    assemble_f32x8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+    if (p->Cp == 8) assemble_f32x8_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+    else assemble_f32x8_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
     return check_launch();
   }
   if (p->dtype == FBANET_F32) assemble_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*p);

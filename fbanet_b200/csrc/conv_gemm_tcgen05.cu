@@ -67,6 +67,7 @@ struct TcParams {
   int b_slots, b_resident;
   int tma_store;          // 1: each epilogue warp stages 32x64 bf16 sub-tiles in smem and stores them with TMA
   int stage_bufs;         // staging buffers per epilogue warp (2, or 1 when shared memory is tight)
+  int fold;               // tapsum mode: outputs are hi + lo halves (see fbanet_conv_params.fold_hi_lo)
   int tapsum;             // > 0: tap-stacked 3x3 conv with `tapsum` outputs per tap (see the TAPSUM epilogue); tiles step by (tw-2, th-2)
   int step_x, step_y, org;  // tile origin = tile index * step + org (tw, th, 0 except in tapsum mode: tw-2, th-2, -1)
   int nacc, nacc_shift;   // accumulator stages in TMEM (4 when 4 x BN <= 512 columns, else 2) and log2 of it
@@ -528,6 +529,31 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
               for (int j = 0; j < CT; ++j) op[j] = sacc[j];
             }
           };
+          auto gather_fold = [&](auto h_tag) {                       // Ct = 2h rows: [0, h) hi, [h, 2h) lo; out[j] = hi_j + lo_j
+            constexpr int HH = decltype(h_tag)::value;
+            float sacc[HH];
+#pragma unroll
+            for (int j = 0; j < HH; ++j) sacc[j] = bias_s[j] + bias_s[HH + j];
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+#pragma unroll
+              for (int j = 0; j < HH; ++j) {
+                const float* q = pc + ((t / 3) * 16 + (t % 3)) * pst + t * 2 * HH + j;
+                sacc[j] += q[0] + q[HH];
+              }
+            if constexpr (HH == 1) op[0] = sacc[0];
+            else if constexpr (HH == 2) *reinterpret_cast<float2*>(op) = make_float2(sacc[0], sacc[1]);
+            else if constexpr (HH == 3) *reinterpret_cast<float4*>(op) = make_float4(sacc[0], sacc[1], sacc[2], 0.f);
+            else *reinterpret_cast<float4*>(op) = make_float4(sacc[0], sacc[1], sacc[2], sacc[3]);
+          };
+          if (p.fold) {
+            switch (Ct) {
+              case 2: gather_fold(std::integral_constant<int, 1>{}); break;
+              case 4: gather_fold(std::integral_constant<int, 2>{}); break;
+              case 6: gather_fold(std::integral_constant<int, 3>{}); break;
+              default: gather_fold(std::integral_constant<int, 4>{}); break;
+            }
+          } else
           switch (Ct) {
             case 1: gather(std::integral_constant<int, 1>{}); break;
             case 2: gather(std::integral_constant<int, 2>{}); break;
@@ -798,9 +824,12 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   const char* tsenv = getenv("FBANET_TC_TAPSUM");
   // (measured, batch 64: score conv 64 -> 2 @160^2 x 896 frames 1.67 -> 1.08 ms; with 8 outputs per tap -- the final conv's hi/lo
   // rows -- the shared-memory gather costs what the MMAs save, 2.0 vs 1.9 ms, so the mode is limited to <= 4 outputs)
-  const bool tapsum = is_halo(p) && p->store_mode == FBANET_STORE_NHWC_F32 && p->Cout_store >= 1 && p->Cout_store <= 4 &&
+  const bool fold = p->fold_hi_lo != 0;
+  if (fold && (p->Cout_store < 2 || p->Cout_store > 8 || (p->Cout_store & 1))) return FBANET_E_BADSHAPE;
+  const bool tapsum = is_halo(p) && p->store_mode == FBANET_STORE_NHWC_F32 && p->Cout_store >= 1 && p->Cout_store <= (fold ? 8 : 4) &&
                       p->Cout_store <= p->Cout && !p->residual && p->act == FBANET_ACT_NONE && !(tsenv && tsenv[0] == '0') &&
-                      ((uintptr_t)p->out % 16) == 0 && (p->out_ld % (p->Cout_store >= 4 ? 4 : 2)) == 0 && (p->out_img_stride % 4) == 0;   // vector stores of the gather
+                      ((uintptr_t)p->out % 16) == 0 && (p->out_ld % ((fold ? p->Cout_store / 2 : p->Cout_store) >= 3 ? 4 : 2)) == 0 && (p->out_img_stride % 4) == 0;   // vector stores of the gather
+  if (fold && !tapsum) return FBANET_E_UNSUPPORTED;
   const bool halo = is_halo(p) && !tapsum;
   // tile space = output pixels; for s2d sources the source view already has the output resolution
   const int Hs = s2d ? p->H / 2 : p->H, Ws = s2d ? p->W / 2 : p->W;
@@ -810,6 +839,7 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   tp.tw = tw; tp.th = th;
   tp.step_x = tapsum ? tw - 2 : tw; tp.step_y = tapsum ? th - 2 : th; tp.org = tapsum ? -1 : 0;
   tp.tapsum = tapsum ? p->Cout_store : 0;
+  tp.fold = fold ? 1 : 0;
   tp.tiles_x = (p->Wo + tp.step_x - 1) / tp.step_x;
   tp.tiles_y = (p->Ho + tp.step_y - 1) / tp.step_y;
   tp.m_tiles = p->N * tp.tiles_x * tp.tiles_y;

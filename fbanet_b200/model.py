@@ -195,6 +195,8 @@ class BaseModel(nn.Module):
         # batch-64 step and a lower mean PSNR delta over seeds (0.0043 vs 0.0049 dB), but one of three seeds lands at 0.0105 dB,
         # 5 % over the 0.01 dB parity tolerance, so it stays off by default; FBANET_FOLD_LN=1 (or the attribute) turns it on.
         self.fold_ln = os.environ.get("FBANET_FOLD_LN", "0") == "1"
+        # final conv through the tap-stacked kernel mode with hi + lo summed in its epilogue (FBANET_FOLD_FINAL=0: plain implicit GEMM)
+        self.fold_final = os.environ.get("FBANET_FOLD_FINAL", "1") == "1"
         self.host_chunk = 32       # bursts per pipelined chunk of infer_host (int, or an explicit schedule of chunk sizes)
         self._io_streams = None
         self.host_graphs = True    # infer_host replays CUDA graphs (captured per chunk size) instead of launching eagerly
@@ -352,6 +354,10 @@ class BaseModel(nn.Module):
             w16 = torch.zeros((16, w32.shape[1]), device=w32.device, dtype=T)
             w16[: self.in_channels], w16[4: 4 + self.in_channels] = hi, lo
             P["tail.1.w"] = w16.contiguous()
+            # the same rows packed [hi; lo] back to back for the tap-stacked kernel mode that sums them itself (fold_hi_lo)
+            wf = torch.zeros((16, w32.shape[1]), device=w32.device, dtype=T)
+            wf[: self.in_channels], wf[self.in_channels: 2 * self.in_channels] = hi, lo
+            P["tail.1.wfold"] = wf.contiguous()
             P["tail.1.b"] = torch.nn.functional.pad(f32(self.tail[1].bias), (0, 16 - self.in_channels)).contiguous()
         return P
 
@@ -544,9 +550,16 @@ class BaseModel(nn.Module):
             # last conv stores its (few) real columns channels-last in FP32 -- rounding the SR residual to bf16 right before the
             # base add would be the largest single error of the whole bf16 path; the planar fp32 + bilinear-base assembly is a
             # separate coalesced bandwidth kernel (:315-320)
-            t3 = torch.empty((B, 4 * S, 4 * S, 8), device=x.device, dtype=torch.float32)   # columns 0..3 hi-weight part, 4..7 lo-weight part
-            self._conv3(P, "tail.1", [t2], out=t3, store=L.STORE_NHWC_F32, cout_store=8)
-            out = ops.assemble(t3, x[:, 0], Cin, lo_offset=4)
+            if self.fold_final and os.environ.get("FBANET_TC_TAPSUM", "1") != "0":
+                # tap-stacked final conv: hi + lo halves summed inside the kernel, 16 bytes per pixel to the assembly
+                t3 = torch.empty((B, 4 * S, 4 * S, 4), device=x.device, dtype=torch.float32)
+                ops.conv_gemm([t2], P["tail.1.wfold"], t3, kh=3, kw=3, pad=1, bias=P["tail.1.b"], store_mode=L.STORE_NHWC_F32,
+                              cout_store=2 * Cin, impl=self.impl, fold_hi_lo=True)
+                out = ops.assemble(t3, x[:, 0], Cin, lo_offset=0)
+            else:
+                t3 = torch.empty((B, 4 * S, 4 * S, 8), device=x.device, dtype=torch.float32)   # columns 0..3 hi-weight part, 4..7 lo-weight part
+                self._conv3(P, "tail.1", [t2], out=t3, store=L.STORE_NHWC_F32, cout_store=8)
+                out = ops.assemble(t3, x[:, 0], Cin, lo_offset=4)
         else:
             out = torch.empty((B, Cin, 4 * S, 4 * S), device=x.device, dtype=torch.float32)
             self._conv3(P, "tail.1", [t2], out=out, store=L.STORE_NCHW_BASE, base=x[:, 0], cout_store=Cin)  # :315-320 (+ bilinear x4 base)

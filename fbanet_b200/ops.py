@@ -95,6 +95,7 @@ def conv_gemm(
     alg_cin: Optional[int] = None,
     src_s2d: bool = False,
     ln_stats: Optional[torch.Tensor] = None,
+    fold_hi_lo: bool = False,
 ) -> torch.Tensor:
     """out = act(conv(concat(srcs)) + bias) + residual.  ``weight`` is packed ``[Cout, kh*kw*sum(C)]``.
 
@@ -153,7 +154,11 @@ def conv_gemm(
         p.out, p.out_img_stride = out.data_ptr(), p.Cout_store * Ho * Wo
         p.base, p.base_img_stride = base.data_ptr(), (base.stride(0) if N > 1 else 0)
     elif store_mode == L.STORE_NHWC_F32:
-        assert out.dtype == torch.float32 and out.shape == (N, Ho, Wo, p.Cout_store)
+        if fold_hi_lo:   # hi / lo weight rows summed by the kernel: Cout_store / 2 outputs (3 are stored as 4 with a zero column)
+            p.fold_hi_lo = 1
+            assert out.dtype == torch.float32 and out.shape == (N, Ho, Wo, 4 if p.Cout_store // 2 == 3 else p.Cout_store // 2)
+        else:
+            assert out.dtype == torch.float32 and out.shape == (N, Ho, Wo, p.Cout_store)
         op, _, old, ois = _cl(out)
         p.out, p.out_ld, p.out_img_stride = op, old, ois
     else:

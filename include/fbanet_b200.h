@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 15
+#define FBANET_ABI_VERSION 16
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -99,7 +99,11 @@ typedef struct fbanet_conv_params {
   int32_t src_s2d;        /* 1: sources are space-to-depth(2) views [N,H/2,W/2,(ys,xs,c)] of the logical
                              [N,H,W,C] inputs (fbanet_space_to_depth_sm100); only KH=KW=4, stride 2, pad 1,
                              tensor-core path.  src[i].C is then 4*C_i.                                */
-  int32_t _pad;
+  int32_t fold_hi_lo;     /* 1 (3x3 stride-1 pad-1 conv, FBANET_STORE_NHWC_F32, tensor-core path): the Cout_store (even, <= 8)
+                             weight rows are hi / lo bf16 halves of Cout_store/2 filters -- rows [0, h) hi, [h, 2h) lo -- and
+                             out(n,y,x,j) = conv_j^hi + conv_j^lo for j < h is stored (out_ld >= 4 when h = 3: a zero 4th column
+                             is written); the final conv of models/fba_net.py:315 in the bf16 path.  FBANET_E_UNSUPPORTED if
+                             the tap-stacked kernel mode cannot take the problem.                             */
   /* LayerNorm folded into a 1x1 GEMM (layers/fba_net.py:196,246 feeding linear_projection.py:27-28 /
    * locally_enhanced_feed_forward.py:27), tensor-core path.  With W' = W diag(gamma) and W'' = W' - rowmean(W') 1^T
    * (every row centred, so W'' x = W' (x - mean(x) 1): the mean subtraction lives in the weights), the GEMM runs on the RAW
