@@ -256,6 +256,26 @@ __device__ __forceinline__ void mma_loop_resident(const int mt0, const int mt_st
   }
 }
 
+// (image, tile row, tile column) of the tiles a CTA owns, advanced incrementally: the role loops used two 32-bit divisions per
+// tile, and with 4-MMA tiles (1x1 GEMMs with K = 64, the tap-stacked convs) every serial instruction of a role loop shows
+struct TileIter {
+  int img, ty, tx, d_img, d_ty, d_tx, tiles_x, tiles_y;
+  __device__ __forceinline__ TileIter(int mt0, int mt_step, int tiles_x_, int tiles_y_) : tiles_x(tiles_x_), tiles_y(tiles_y_) {
+    const int per_img = tiles_x * tiles_y;
+    img = mt0 / per_img;
+    int r = mt0 - img * per_img;
+    ty = r / tiles_x; tx = r - ty * tiles_x;
+    d_img = mt_step / per_img;
+    r = mt_step - d_img * per_img;
+    d_ty = r / tiles_x; d_tx = r - d_ty * tiles_x;
+  }
+  __device__ __forceinline__ void next() {
+    tx += d_tx; ty += d_ty; img += d_img;
+    if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+    if (ty >= tiles_y) { ty -= tiles_y; ++img; }
+  }
+};
+
 constexpr int TC_MAX_A_SLOTS = 8;
 // warps: 0 A-producer, 1 MMA, 2 TMEM alloc, 3 B-producer, 4.. epilogue (TC_EPI_SLOTS warps per TMEM lane quarter).
 // Measured in one box: 3 slots (512 threads, 128 registers) speed the staged TMA-store epilogue up (fc1 128->512 0.675 -> 0.568 ms,
@@ -323,33 +343,39 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
     // ================= A producer (TMA); warp-uniform loop, one elected lane issues =================
     int slot = 0;
     uint32_t phase = 0;
-    for (int mt = mt0; mt < p.m_tiles; mt += mt_step) {
-      const int img = mt / tiles_per_img, r = mt % tiles_per_img;
-      const int y0 = (r / p.tiles_x) * p.step_y + p.org, x0 = (r % p.tiles_x) * p.step_x + p.org;
+    const int halo = p.halo, a_slots = p.a_slots, step_x = p.step_x, step_y = p.step_y, org = p.org, m_tiles = p.m_tiles;
+    const uint32_t a_slot_bytes = (uint32_t)p.a_slot_bytes, a_box_bytes = (uint32_t)p.a_box_bytes;
+    const bool noload = (p.debug & 4) != 0;
+    const uint32_t bar_ae = smem_u32(&a_empty[0]);
+    TileIter ti(mt0, mt_step, p.tiles_x, p.tiles_y);
+    for (int mt = mt0; mt < m_tiles; mt += mt_step, ti.next()) {
+      const int img = ti.img;
+      const int y0 = ti.ty * step_y + org, x0 = ti.tx * step_x + org;
       for (int u = 0; u < units; ++u) {
-        mbar_wait(&a_empty[slot], phase ^ 1);
-        if (p.debug & 4) {
-          if (elect_one()) mbar_arrive(&a_full[slot]);
+        mbar_wait_a(bar_ae + (uint32_t)slot * 8u, phase ^ 1);
+        uint64_t* afull = &a_full[slot];
+        if (noload) {
+          if (elect_one()) mbar_arrive(afull);
         } else if (elect_one()) {
-          uint8_t* sa = smem_a + (size_t)slot * p.a_slot_bytes;
-          if (p.halo) {
+          uint8_t* sa = smem_a + (size_t)slot * a_slot_bytes;
+          if (halo) {
             const Chunk ch = p.chunks[u];
-            if (p.halo == 1) {
-              mbar_expect_tx(&a_full[slot], 3u * (uint32_t)TC_HALO_COPY);
+            if (halo == 1) {
+              mbar_expect_tx(afull, 3u * (uint32_t)TC_HALO_COPY);
 #pragma unroll
-              for (int d = 0; d < 3; ++d) tma_load_4d(sa + d * TC_HALO_COPY, &p.amap[ch.src], &a_full[slot], ch.c0, x0 + d - 1, y0 - 1, img);
+              for (int d = 0; d < 3; ++d) tma_load_4d(sa + d * TC_HALO_COPY, &p.amap[ch.src], afull, ch.c0, x0 + d - 1, y0 - 1, img);
             } else {
-              mbar_expect_tx(&a_full[slot], (uint32_t)TC_HALO_WSLOT);
-              tma_load_4d(sa, &p.amap[ch.src], &a_full[slot], ch.c0, x0 - 4, y0 - 1, img);
+              mbar_expect_tx(afull, (uint32_t)TC_HALO_WSLOT);
+              tma_load_4d(sa, &p.amap[ch.src], afull, ch.c0, x0 - 4, y0 - 1, img);
             }
           } else {
             const KStep ks = p.steps[u];
-            mbar_expect_tx(&a_full[slot], (uint32_t)p.a_box_bytes);
-            tma_load_4d(sa, &p.amap[ks.src], &a_full[slot], ks.c0, x0 + ks.dx, y0 + ks.dy, img);
+            mbar_expect_tx(afull, a_box_bytes);
+            tma_load_4d(sa, &p.amap[ks.src], afull, ks.c0, x0 + ks.dx, y0 + ks.dy, img);
           }
         }
         __syncwarp();
-        if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
+        if (++slot == a_slots) { slot = 0; phase ^= 1; }
       }
     }
   } else if (warp == 3) {
@@ -481,7 +507,8 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
       const int pst = BN + 1;
       float* P = reinterpret_cast<float*>(smem_stage) + (size_t)slot * 128 * pst;
       const int bar_id = 1 + slot;
-      for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
+      TileIter ti(mt0, mt_step, p.tiles_x, p.tiles_y);
+      for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it, ti.next()) {
         const int acc = it & nacc_mask;
         const uint32_t acc_phase = (it >> nacc_shift) & 1;
         const bool mine = (it % TC_EPI_SLOTS) == slot;
@@ -505,8 +532,8 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         if (!mine) continue;
         named_bar_sync(bar_id, 128);                       // the four lane quarters of this tile have written P
-        const int img = mt / tiles_per_img, r = mt % tiles_per_img;
-        const int oy = (r / p.tiles_x) * p.step_y + ly - 1, ox = (r % p.tiles_x) * p.step_x + lx - 1;
+        const int img = ti.img;
+        const int oy = ti.ty * p.step_y + ly - 1, ox = ti.tx * p.step_x + lx - 1;
         if (lx >= 1 && lx <= 14 && ly >= 1 && ly <= 6 && oy < p.Ho && ox < p.Wo) {
           float* op = reinterpret_cast<float*>(p.out) + img * p.out_img_stride + ((int64_t)oy * p.Wo + ox) * p.out_ld;
           const float* pc = P + ((ly - 1) * 16 + (lx - 1)) * pst;   // P row of tap (0,0) for this output pixel
@@ -591,11 +618,12 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
       const int bw = p.tw < 32 ? p.tw : 32;
       const int ply = lane / bw, plx = lane - ply * bw;         // this thread's pixel inside the rectangle
       uint32_t res_phase = 0, nb = 0;
-      for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
+      TileIter ti(mt0, mt_step, p.tiles_x, p.tiles_y);
+      for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it, ti.next()) {
         const int acc = it & nacc_mask;
         const uint32_t acc_phase = (it >> nacc_shift) & 1;
-        const int img = mt / tiles_per_img, r = mt % tiles_per_img;
-        const int y0 = (r / p.tiles_x) * p.th + wy0, x0 = (r % p.tiles_x) * p.tw + wx0;
+        const int img = ti.img;
+        const int y0 = ti.ty * p.th + wy0, x0 = ti.tx * p.tw + wx0;
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
         float ln_rstd = 0.f;   // 1/sigma of this thread's row, fetched while the MMAs still run
         if (HAS_LN && y0 + ply < p.Ho && x0 + plx < p.Wo)
@@ -678,11 +706,12 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
       __syncwarp();
     } else {
       const int npieces = BN >= 32 ? BN / 32 : 1;      // 32-column pieces (one 16-column piece for BN = 16)
-      for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
+      TileIter ti(mt0, mt_step, p.tiles_x, p.tiles_y);
+      for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it, ti.next()) {
         const int acc = it & nacc_mask;
         const uint32_t acc_phase = (it >> nacc_shift) & 1;
-        const int img = mt / tiles_per_img, r = mt % tiles_per_img;
-        const int y = (r / p.tiles_x) * p.th + ly, x = (r % p.tiles_x) * p.tw + lx;
+        const int img = ti.img;
+        const int y = ti.ty * p.th + ly, x = ti.tx * p.tw + lx;
         const bool valid = (ly < p.th) && (y < p.Ho) && (x < p.Wo);
         // this warp's first piece of the tile; its residual is fetched while the MMAs of the tile are still running
         int j0 = (slot - (it * npieces) % TC_EPI_SLOTS + TC_EPI_SLOTS) % TC_EPI_SLOTS;

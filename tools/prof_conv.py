@@ -28,6 +28,8 @@ CASES = {
     "fc1_256_1024": (64, 80, 80, 256, 1024, 1, L.ACT_GELU_TANH, False, L.STORE_NHWC),
     "fc2_1024_256": (64, 80, 80, 1024, 256, 1, L.ACT_NONE, True, L.STORE_NHWC),
     "head_64_64": (896, 160, 160, 64, 64, 1, L.ACT_NONE, False, L.STORE_NHWC),
+    "score3x3_64_2": (896, 160, 160, 64, 16, 3, L.ACT_NONE, False, L.STORE_NHWC_F32),     # FAF score conv: 2 fp32 outputs, tap-stacked
+    "final3x3_64_3fold": (64, 640, 640, 64, 16, 3, L.ACT_NONE, False, -1),                  # final conv: hi/lo rows folded, tap-stacked
     "fuse_896_64": (64, 160, 160, 896, 64, 1, L.ACT_PRELU, False, L.STORE_NHWC),
 }
 
@@ -39,14 +41,22 @@ def run_case(name, reps, dev):
     w = ((torch.rand(co, k * k * ci, device=dev, generator=g) - 0.5) * 0.05).to(BF)
     b = torch.zeros(co, device=dev)
     alpha = torch.full((1,), 0.25, device=dev)
-    if store == L.STORE_CONVT2:
+    kw = {}
+    if store == L.STORE_NHWC_F32:
+        out = torch.empty(N, H, W, 2, device=dev, dtype=torch.float32)
+        kw = dict(cout_store=2)
+    elif store == -1:
+        store = L.STORE_NHWC_F32
+        out = torch.empty(N, H, W, 4, device=dev, dtype=torch.float32)
+        kw = dict(cout_store=6, fold_hi_lo=True)
+    elif store == L.STORE_CONVT2:
         out = torch.empty(N, 2 * H, 2 * W, co // 4, device=dev, dtype=BF)
     else:
         out = torch.empty(N, H, W, co, device=dev, dtype=BF)
     r = torch.zeros_like(out) if res else None
 
     def go():
-        ops.conv_gemm([x], w, out, kh=k, kw=k, pad=k // 2, bias=b, act=act, alpha=alpha, residual=r, store_mode=store, impl=L.IMPL_TCGEN05)
+        ops.conv_gemm([x], w, out, kh=k, kw=k, pad=k // 2, bias=b, act=act, alpha=alpha, residual=r, store_mode=store, impl=L.IMPL_TCGEN05, **kw)
 
     go()
     torch.cuda.synchronize()
