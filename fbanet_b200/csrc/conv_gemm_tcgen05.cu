@@ -487,6 +487,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
     const int ly = row / p.tw, lx = row - ly * p.tw;
     const float alpha = (p.act == FBANET_ACT_PRELU) ? __ldg(p.alpha) : 0.f;
     int it = 0;
+    const uint32_t bar_tf = smem_u32(&tmem_full[0]), bar_te = smem_u32(&tmem_empty[0]);   // raw shared addresses (see mma_loop_resident)
     if (p.debug & 1) {
       for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
         mbar_wait(&tmem_full[it & nacc_mask], (it >> nacc_shift) & 1);
@@ -512,7 +513,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
         const int acc = it & nacc_mask;
         const uint32_t acc_phase = (it >> nacc_shift) & 1;
         const bool mine = (it % TC_EPI_SLOTS) == slot;
-        mbar_wait(&tmem_full[acc], acc_phase);
+        mbar_wait_a(bar_tf + (uint32_t)acc * 8u, acc_phase);
         tc_fence_after();
         if (mine) {
           const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -529,7 +530,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) mbar_arrive_a(bar_te + (uint32_t)acc * 8u);
         if (!mine) continue;
         named_bar_sync(bar_id, 128);                       // the four lane quarters of this tile have written P
         const int img = ti.img;
@@ -613,7 +614,8 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
       const int r7 = lane & 7;
       const int nchunks = BN >> 6;
       const bool has_res = p.residual != nullptr;
-      const int Co = p.store_mode == FBANET_STORE_CONVT2 ? (p.Cout >> 2) : p.Cout;
+      const bool ct2 = p.store_mode == FBANET_STORE_CONVT2;
+      const int Co = ct2 ? (p.Cout >> 2) : p.Cout;
       const int wy0 = (q * 32) / p.tw, wx0 = (q * 32) % p.tw;   // this warp's rectangle inside the tile
       const int bw = p.tw < 32 ? p.tw : 32;
       const int ply = lane / bw, plx = lane - ply * bw;         // this thread's pixel inside the rectangle
@@ -646,7 +648,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
             }
           }
           __syncwarp();
-          if (!waited) { mbar_wait(&tmem_full[acc], acc_phase); tc_fence_after(); waited = true; }
+          if (!waited) { mbar_wait_a(bar_tf + (uint32_t)acc * 8u, acc_phase); tc_fence_after(); waited = true; }
           uint32_t v[64];
           tmem_ld32(taddr0 + cidx * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
           tmem_ld32(taddr0 + cidx * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
@@ -692,15 +694,15 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
           fence_proxy_async();                           // generic-proxy smem writes -> visible to the TMA engine
           __syncwarp();
           if (lane == 0) {
-            const int qq = col0 / Co;                    // 2x2 scatter store: sub-pixel plane of this chunk (0 for NHWC)
+            const int qq = ct2 ? col0 / Co : 0;          // 2x2 scatter store: sub-pixel plane of this chunk (0 for NHWC)
             tma_store_4d(&p.omap[qq], gbuf, col0 - qq * Co, x0, y0, img);
             bulk_commit();
           }
         }
-        if (!waited) { mbar_wait(&tmem_full[acc], acc_phase); tc_fence_after(); }
+        if (!waited) { mbar_wait_a(bar_tf + (uint32_t)acc * 8u, acc_phase); tc_fence_after(); }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) mbar_arrive_a(bar_te + (uint32_t)acc * 8u);
       }
       if (lane == 0) bulk_wait0();                       // all stores of this warp have completed
       __syncwarp();
@@ -724,7 +726,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
         }
         float ln_rstd = 1.f;
         if (HAS_LN && valid) ln_rstd = __ldg(p.ln_stats + (((int64_t)img * p.Ho + y) * p.Wo + x) * 2 + 1);
-        mbar_wait(&tmem_full[acc], acc_phase);
+        mbar_wait_a(bar_tf + (uint32_t)acc * 8u, acc_phase);
         tc_fence_after();
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
         for (int j = j0; j < npieces; j += TC_EPI_SLOTS) {
@@ -739,7 +741,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) mbar_arrive_a(bar_te + (uint32_t)acc * 8u);
       }
     }
   }

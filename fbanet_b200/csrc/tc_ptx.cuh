@@ -54,6 +54,9 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void umma_commit_a(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
