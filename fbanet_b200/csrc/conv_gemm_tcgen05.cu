@@ -880,10 +880,12 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   tp.Cout = p->Cout; tp.Cout_store = p->Cout_store;
   tp.a_box_bytes = tw * th * TC_BK * 2;
   // Measured (profiles/r1_notes.md): the wide box wins 4-16 % for N tiles of 128 and for N = 16, where TMA / L2 traffic
-  // bounds the tile, and loses 7 % at N = 64, where the MMA's fetch of A rows that straddle 1 KB boundaries shows instead.
+  // bounds the tile; at N = 64 it lost 7 % with the unrolled issuer loop of session 2.
   // The hardware swizzle is purely address based: base-offset 0 (mode 3) is the correct descriptor, mode 2 computes garbage.
   static const char* henv = getenv("FBANET_TC_HALO");   // experiment switch: 1 = three dx-shifted copies, 3 = one wide box
-  const int halo_mode = halo ? (henv ? atoi(henv) : (tp.BN == 64 ? 1 : 3)) : 0;
+  // (with the rolled issuer loop the wide box is also the better one at N = 64: 64->64 body conv 1.80 -> 1.76 ms, A/B in one box, and
+  // its 36 KB slots leave room for a third A slot there)
+  const int halo_mode = halo ? (henv ? atoi(henv) : 3) : 0;
   if (halo && halo_mode != 1 && halo_mode != 3) return FBANET_E_UNSUPPORTED;
   tp.halo = halo_mode;
 
