@@ -600,3 +600,23 @@ def test_tile_kernels_match_vectors_from_the_reference_code(cuda):
     ob = [torch.zeros(Cc, sc * (row0[k + 1] - row0[k]), sc * W, device=cuda) for k in range(3)]
     ops.tile_merge_banded(torch.from_numpy(sr).to(cuda), [b.data_ptr() for b in ob], row0, H, W, ps, ov, sc, 0, n)
     assert np.array_equal(torch.cat(ob, 1).cpu().numpy(), d["merged"][0])
+
+
+def test_ecc_large_frame_takes_the_l2_path(cuda):
+    """Frames whose two planes do not fit in shared memory (here 232 x 248: 460 KB) run the ECC iterations with their taps through
+    L2 instead; same result contract against the float64 restatement."""
+    import cv2
+    from fbanet_b200 import ops
+    from oracle.fbanet_oracle import bgr2gray, ecc_homography, homography_coord_diff
+    H, W = 232, 248
+    rng = np.random.default_rng(21)
+    base = cv2.GaussianBlur(rng.random((H, W, 3)).astype(np.float32), (0, 0), 3.0)
+    base = (base - base.min()) / (base.max() - base.min())
+    M = np.eye(3, dtype=np.float32)
+    M[0, 2], M[1, 2], M[0, 1], M[2, 0] = 2.4, -1.6, 0.006, 8e-6
+    frame = cv2.warpPerspective(base, M, (W, H), flags=cv2.INTER_LINEAR) + rng.normal(0, 0.01, (H, W, 3)).astype(np.float32)
+    burst = torch.from_numpy(np.stack([base, frame])[None]).contiguous()          # [1,2,H,W,3]
+    Mg, rho, iters = ops.ecc_homography_burst(burst.to(cuda), layout="BTHWC")
+    r_ref, M_ref = ecc_homography(bgr2gray(base), bgr2gray(frame))
+    assert iters[0, 1].item() > 0 and abs(rho[0, 1].item() - r_ref) < 2e-4
+    assert homography_coord_diff(Mg[0, 1].cpu().numpy(), M_ref, H, W) < 5e-3
