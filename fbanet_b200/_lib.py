@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBANET_B200_LIB") or os.path.join(_HERE, "csrc", "libfbanet_b200.so")   # env override: A/B two builds in one process tree
-ABI_VERSION = 16
+ABI_VERSION = 17
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -168,12 +168,19 @@ class EccParams(C.Structure):
     ]
 
 
+class TrainLossParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("y", C.c_void_p), ("grad", C.c_void_p), ("partial", C.c_void_p), ("loss", C.c_void_p),
+        ("eps", C.c_float), ("gw_weight", C.c_float), ("inv_n", C.c_float), ("planes", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+    ]
+
+
 STRUCTS = {
     "fbanet_src": Src, "fbanet_conv_params": ConvParams, "fbanet_warp_params": WarpParams,
     "fbanet_to_nhwc_params": ToNhwcParams, "fbanet_s2d_params": S2dParams, "fbanet_head_conv_params": HeadConvParams, "fbanet_assemble_params": AssembleParams, "fbanet_layernorm_params": LayerNormParams, "fbanet_attn_params": AttnParams,
     "fbanet_dwconv_params": DwconvParams, "fbanet_faf_gate_params": FafGateParams, "fbanet_leff_fc2_params": LeffFc2Params, "fbanet_tile_params": TileParams,
     "fbanet_tile_band_params": TileBandParams, "fbanet_flow_warp_params": FlowWarpParams,
-    "fbanet_ecc_prepare_params": EccPrepareParams, "fbanet_ecc_params": EccParams,
+    "fbanet_ecc_prepare_params": EccPrepareParams, "fbanet_ecc_params": EccParams, "fbanet_train_loss_params": TrainLossParams,
 }
 
 # every symbol include/fbanet_b200.h declares
@@ -182,9 +189,10 @@ OPS = {
     "fbanet_layernorm_sm100": LayerNormParams, "fbanet_window_attention_sm100": AttnParams, "fbanet_dwconv3x3_sm100": DwconvParams,
     "fbanet_faf_gate_sm100": FafGateParams, "fbanet_leff_fc2_sm100": LeffFc2Params, "fbanet_tile_divide_sm100": TileParams, "fbanet_tile_merge_sm100": TileParams,
     "fbanet_tile_divide_banded_sm100": TileBandParams, "fbanet_tile_merge_banded_sm100": TileBandParams, "fbanet_flow_warp_sm100": FlowWarpParams,
-    "fbanet_ecc_prepare_sm100": EccPrepareParams, "fbanet_ecc_homography_sm100": EccParams,
+    "fbanet_ecc_prepare_sm100": EccPrepareParams, "fbanet_ecc_homography_sm100": EccParams, "fbanet_train_loss_sm100": TrainLossParams,
 }
-MISC_SYMBOLS = ["fbanet_abi_version", "fbanet_abi_sizeof", "fbanet_last_cuda_error", "fbanet_conv_gemm_tcgen05_supported", "fbanet_leff_fc2_supported"]
+MISC_SYMBOLS = ["fbanet_abi_version", "fbanet_abi_sizeof", "fbanet_last_cuda_error", "fbanet_conv_gemm_tcgen05_supported", "fbanet_leff_fc2_supported",
+                "fbanet_train_loss_workspace_doubles"]
 
 _lib = None
 
@@ -208,6 +216,8 @@ def load() -> C.CDLL:
     lib.fbanet_conv_gemm_tcgen05_supported.argtypes = [C.POINTER(ConvParams)]
     lib.fbanet_leff_fc2_supported.restype = C.c_int
     lib.fbanet_leff_fc2_supported.argtypes = [C.POINTER(LeffFc2Params)]
+    lib.fbanet_train_loss_workspace_doubles.restype = C.c_int64
+    lib.fbanet_train_loss_workspace_doubles.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     if lib.fbanet_abi_version() != ABI_VERSION:
         raise RuntimeError(f"fbanet_b200: ABI mismatch (library {lib.fbanet_abi_version()}, binding {ABI_VERSION}); rebuild")
     for name, st in STRUCTS.items():

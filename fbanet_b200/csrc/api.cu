@@ -57,6 +57,7 @@ extern "C" int fbanet_abi_sizeof(const char* n) {
   SZ(fbanet_flow_warp_params);
   SZ(fbanet_ecc_prepare_params);
   SZ(fbanet_ecc_params);
+  SZ(fbanet_train_loss_params);
 #undef SZ
   return -1;
 }

@@ -534,6 +534,28 @@ def ecc_homography_burst(burst: torch.Tensor, layout: str = "BTCHW", gray_weight
     return M, rho, iters
 
 
+def training_loss(restored: torch.Tensor, target: torch.Tensor, eps: float = 1e-3, gw_weight: float = 3.0, need_grad: bool = True):
+    """Training loss of the reference trainer (``train.py.bak:118-119,168``): ``CharbonnierLoss()(restored, target) + 3 *
+    GWLoss()(restored, target)`` (``losses.py:39-80``) and its gradient with respect to ``restored`` in one kernel pass.
+
+    ``restored``, ``target``: fp32 ``[B,C,H,W]`` on the GPU.  Returns ``(loss [3] float64 = (total, charbonnier, gw), grad or None)``."""
+    assert restored.is_cuda and restored.dtype == torch.float32 and restored.is_contiguous() and restored.dim() == 4
+    assert target.shape == restored.shape and target.dtype == torch.float32 and target.is_contiguous() and target.device == restored.device
+    B, Cc, H, W = restored.shape
+    lib = L.load()
+    nws = lib.fbanet_train_loss_workspace_doubles(B * Cc, H, W)
+    ws = torch.empty(nws, dtype=torch.float64, device=restored.device)
+    loss = torch.empty(3, dtype=torch.float64, device=restored.device)
+    grad = torch.empty_like(restored) if need_grad else None
+    p = L.TrainLossParams()
+    p.x, p.y, p.partial, p.loss = restored.data_ptr(), target.data_ptr(), ws.data_ptr(), loss.data_ptr()
+    p.grad = grad.data_ptr() if grad is not None else None
+    p.eps, p.gw_weight, p.inv_n = float(eps), float(gw_weight), 1.0 / restored.numel()
+    p.planes, p.H, p.W = B * Cc, H, W
+    _call("fbanet_train_loss_sm100", p, nbytes=restored.numel() * 4 * (3 if need_grad else 2))
+    return loss, grad
+
+
 def _band_params(bands, row0, tiles, T, Cc, H, W, psize, overlap, tile_begin, tile_end, scale):
     assert 1 <= len(bands) <= L.MAX_BANDS and len(row0) == len(bands) + 1 and row0[0] == 0 and row0[-1] == H
     p = L.TileBandParams()

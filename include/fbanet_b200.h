@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 16
+#define FBANET_ABI_VERSION 17
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -344,6 +344,22 @@ typedef struct fbanet_ecc_params {
   int32_t frames, frames_per_burst, H, W, max_iters, _pad;
 } fbanet_ecc_params;
 
+/* Training loss (first brick of the training step): train.py.bak:118-119,168
+ *   loss = CharbonnierLoss()(restored, target) + gw_weight * GWLoss()(restored, target)      (losses.py:39-51, 53-80)
+ * value and gradient with respect to `restored` in one pass.  x = restored, y = target: planar fp32 [planes = B*C][H][W];
+ * inv_n = 1 / (planes*H*W) (both losses are means); eps = 1e-3, gw_weight = 3 in the reference; gw_weight = 0 skips GWLoss.
+ * partial: workspace of fbanet_train_loss_workspace_doubles(planes, H, W) doubles; loss: 3 doubles (total, Charbonnier, GW).
+ * The reduction is two-stage in fp64 with a fixed order: results are bit-reproducible. */
+typedef struct fbanet_train_loss_params {
+  const float* x;
+  const float* y;
+  float* grad;            /* optional dL/dx, same shape as x                                        */
+  double* partial;
+  double* loss;
+  float eps, gw_weight, inv_n;
+  int32_t planes, H, W;
+} fbanet_train_loss_params;
+
 int fbanet_abi_version(void);
 /* sizeof() of the named parameter struct as compiled, for binding self-checks; -1 if unknown */
 int fbanet_abi_sizeof(const char* struct_name);
@@ -372,6 +388,9 @@ int fbanet_tile_merge_banded_sm100(const fbanet_tile_band_params* p, void* strea
 int fbanet_flow_warp_sm100(const fbanet_flow_warp_params* p, void* stream);
 int fbanet_ecc_prepare_sm100(const fbanet_ecc_prepare_params* p, void* stream);
 int fbanet_ecc_homography_sm100(const fbanet_ecc_params* p, void* stream);
+int fbanet_train_loss_sm100(const fbanet_train_loss_params* p, void* stream);
+/* doubles of workspace fbanet_train_loss_sm100 needs (2 per thread block) */
+int64_t fbanet_train_loss_workspace_doubles(int32_t planes, int32_t H, int32_t W);
 
 #ifdef __cplusplus
 }

@@ -706,3 +706,32 @@ def homography_coord_diff(Ma, Mb, H: int, W: int) -> float:
         return (M[0, 0] * X + M[0, 1] * Y + M[0, 2]) / d, (M[1, 0] * X + M[1, 1] * Y + M[1, 2]) / d
     (a, b), (c, d) = co(Ma), co(Mb)
     return float(max(np.abs(a - c).max(), np.abs(b - d).max()))
+
+
+# ------------------------------------------------------------------------------------------------
+# 8f-3 (first brick): the training loss of train.py.bak:118-119,168 -- CharbonnierLoss + 3 * GWLoss (losses.py:39-80).
+# Restated in torch so that autograd supplies the reference gradient; pinned bit-for-bit... to fp32 rounding against vectors produced by
+# executing the reference's own losses.py (tests/golden/loss_reference.npz, tests/golden/make_golden_reference.py).
+# ------------------------------------------------------------------------------------------------
+def charbonnier_loss(x: torch.Tensor, y: torch.Tensor, eps: float = 1e-3) -> torch.Tensor:
+    """`CharbonnierLoss(eps)(x, y)` (losses.py:39-51): mean(sqrt((x - y)^2 + eps^2))."""
+    d = x - y
+    return torch.mean(torch.sqrt(d * d + eps * eps))
+
+
+def gw_loss(x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    """`GWLoss()(x1, x2)` (losses.py:53-80): both images clamped to [0,1], per-channel Sobel responses (cross-correlation, zero
+    padding), mean((1 + 4|Ix1 - Ix2|)(1 + 4|Iy1 - Iy2|)|x1 - x2|)."""
+    x1, x2 = torch.clamp(x1, 0.0, 1.0), torch.clamp(x2, 0.0, 1.0)
+    c = x1.shape[1]
+    sx = torch.tensor([[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]], dtype=x1.dtype).expand(c, 1, 3, 3)
+    sy = torch.tensor([[-1, -2, -1], [0, 0, 0], [1, 2, 1]], dtype=x1.dtype).expand(c, 1, 3, 3)
+    conv = torch.nn.functional.conv2d
+    dx = torch.abs(conv(x1, sx, padding=1, groups=c) - conv(x2, sx, padding=1, groups=c))
+    dy = torch.abs(conv(x1, sy, padding=1, groups=c) - conv(x2, sy, padding=1, groups=c))
+    return torch.mean((1 + 4 * dx) * (1 + 4 * dy) * torch.abs(x1 - x2))
+
+
+def training_loss(x: torch.Tensor, y: torch.Tensor, eps: float = 1e-3, gw_weight: float = 3.0) -> torch.Tensor:
+    """`criterion1(restored, target) + 3 * criterion2(restored, target)` (train.py.bak:168)."""
+    return charbonnier_loss(x, y, eps) + gw_weight * gw_loss(x, y)

@@ -38,3 +38,21 @@ merged = ref.tensor_merge([t for t in sr], torch.zeros(1, C, scale * H, scale * 
 np.savez_compressed(os.path.join(HERE, "tiling_reference.npz"), burst=burst.numpy(), tiles=tiles.numpy(), merged=merged.numpy(),
                     psize=ps, overlap=ov, scale=scale)
 print("reference tiling fixtures:", tuple(tiles.shape), tuple(merged.shape))
+
+# ---- training loss (8f-3): the reference's own losses.py (torch-only), value + autograd gradient on a seeded pair whose values
+# leave [0, 1] (clamp branches) and contain exact ties (sign(0) branches)
+spec = importlib.util.spec_from_file_location("ref_losses", "/root/reference/fba_net/losses.py")
+ref_losses = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(ref_losses)
+g = torch.Generator().manual_seed(321)
+lx = (torch.rand(2, 3, 14, 18, generator=g) * 1.3 - 0.15)
+ly = (torch.rand(2, 3, 14, 18, generator=g) * 1.3 - 0.15)
+ly[0, 0, 3:6, 4:9] = lx[0, 0, 3:6, 4:9]                      # identical patch: zero differences and zero Sobel responses
+lx.requires_grad_(True)
+c1, c2 = ref_losses.CharbonnierLoss(), ref_losses.GWLoss(rgb_range=1.0)
+lc, lg = c1(lx, ly), c2(lx, ly)
+total = lc + 3 * lg                                          # train.py.bak:168
+total.backward()
+np.savez_compressed(os.path.join(HERE, "loss_reference.npz"), x=lx.detach().numpy(), y=ly.numpy(), charbonnier=lc.item(), gw=lg.item(),
+                    total=total.item(), grad=lx.grad.numpy())
+print("reference loss fixtures:", lc.item(), lg.item(), total.item())

@@ -19,7 +19,7 @@ def test_library_loads_and_abi_matches(lib):
 
 def test_every_declared_symbol_is_exported(lib):
     hdr = open(os.path.join(ROOT, "include", "fbanet_b200.h")).read()
-    decl = set(re.findall(r"^(?:int|const char\*)\s+(fbanet_\w+)\s*\(", hdr, flags=re.M))
+    decl = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(fbanet_\w+)\s*\(", hdr, flags=re.M))
     from fbanet_b200 import _lib
     assert decl == set(_lib.OPS) | set(_lib.MISC_SYMBOLS), decl ^ (set(_lib.OPS) | set(_lib.MISC_SYMBOLS))
     for s in decl:

@@ -620,3 +620,33 @@ def test_ecc_large_frame_takes_the_l2_path(cuda):
     r_ref, M_ref = ecc_homography(bgr2gray(base), bgr2gray(frame))
     assert iters[0, 1].item() > 0 and abs(rho[0, 1].item() - r_ref) < 2e-4
     assert homography_coord_diff(Mg[0, 1].cpu().numpy(), M_ref, H, W) < 5e-3
+
+
+@pytest.mark.parametrize("shape,gw", [((2, 3, 14, 18), 3.0), ((1, 3, 64, 80), 3.0), ((3, 4, 33, 17), 0.0), ((1, 1, 5, 300), 1.5)])
+def test_training_loss_matches_oracle_autograd(cuda, shape, gw):
+    """8f-3: CharbonnierLoss + gw * GWLoss (losses.py:39-80, train.py.bak:168) -- value and dL/d(restored) from the one-pass kernel
+    against torch autograd through the restated losses, on images that leave [0,1] (clamp) and share an identical patch (sign(0))."""
+    from fbanet_b200 import ops
+    from oracle.fbanet_oracle import training_loss
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(shape, generator=g) * 1.3 - 0.15
+    y = torch.rand(shape, generator=g) * 1.3 - 0.15
+    y[0, 0, 1:4, 2:5] = x[0, 0, 1:4, 2:5]
+    xr = x.clone().requires_grad_(True)
+    ref = training_loss(xr, y, gw_weight=gw)
+    ref.backward()
+    loss, grad = ops.training_loss(x.to(cuda), y.to(cuda), gw_weight=gw)
+    assert abs(loss[0].item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+    assert (grad.cpu() - xr.grad).abs().max().item() < 1e-5 * xr.grad.abs().max().item() + 1e-9
+    loss2, none = ops.training_loss(x.to(cuda), y.to(cuda), gw_weight=gw, need_grad=False)
+    assert none is None and torch.equal(loss2, loss)                              # deterministic reduction
+
+
+def test_training_loss_matches_vectors_from_the_reference_code(cuda):
+    import os
+    from fbanet_b200 import ops
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_reference.npz"))
+    loss, grad = ops.training_loss(torch.from_numpy(d["x"]).to(cuda), torch.from_numpy(d["y"]).to(cuda))
+    assert abs(loss[0].item() - float(d["total"])) < 1e-5 * float(d["total"]) and abs(loss[1].item() - float(d["charbonnier"])) < 1e-6
+    assert abs(loss[2].item() - float(d["gw"])) < 1e-5 * float(d["gw"])
+    assert np.abs(grad.cpu().numpy() - d["grad"]).max() < 1e-5 * np.abs(d["grad"]).max()

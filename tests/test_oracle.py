@@ -232,3 +232,19 @@ def test_tiling_oracle_matches_vectors_from_the_reference_code():
     assert np.array_equal(tensor_divide_burst(burst, ps, ov).numpy(), d["tiles"])
     H, W = burst.shape[-2:]
     assert np.array_equal(tensor_merge(torch.from_numpy(sr), (sc * H, sc * W), sc * ps, sc * ov).numpy(), d["merged"])
+
+
+def test_training_loss_oracle_matches_vectors_from_the_reference_code():
+    """8f-3 pin: value and autograd gradient of the restated CharbonnierLoss + 3 * GWLoss against `tests/golden/loss_reference.npz`,
+    produced by executing the reference's own `losses.py` (tests/golden/make_golden_reference.py)."""
+    import os
+    import numpy as np
+    from oracle.fbanet_oracle import charbonnier_loss, gw_loss, training_loss
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_reference.npz"))
+    x, y = torch.from_numpy(d["x"]).requires_grad_(True), torch.from_numpy(d["y"])
+    assert abs(charbonnier_loss(x, y).item() - float(d["charbonnier"])) < 1e-7
+    assert abs(gw_loss(x, y).item() - float(d["gw"])) < 1e-6
+    total = training_loss(x, y)
+    total.backward()
+    assert abs(total.item() - float(d["total"])) < 1e-6
+    assert np.abs(x.grad.numpy() - d["grad"]).max() < 1e-7
