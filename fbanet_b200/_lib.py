@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBANET_B200_LIB") or os.path.join(_HERE, "csrc", "libfbanet_b200.so")   # env override: A/B two builds in one process tree
-ABI_VERSION = 17
+ABI_VERSION = 18
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -175,12 +175,22 @@ class TrainLossParams(C.Structure):
     ]
 
 
+class AdamParams(C.Structure):
+    _fields_ = [
+        ("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("n", C.c_int64),
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+        ("step_size", C.c_float), ("bias2_sqrt", C.c_float), ("grad_scale", C.c_float), ("one_minus_beta1", C.c_float), ("one_minus_beta2", C.c_float),
+        ("decoupled", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
 STRUCTS = {
     "fbanet_src": Src, "fbanet_conv_params": ConvParams, "fbanet_warp_params": WarpParams,
     "fbanet_to_nhwc_params": ToNhwcParams, "fbanet_s2d_params": S2dParams, "fbanet_head_conv_params": HeadConvParams, "fbanet_assemble_params": AssembleParams, "fbanet_layernorm_params": LayerNormParams, "fbanet_attn_params": AttnParams,
     "fbanet_dwconv_params": DwconvParams, "fbanet_faf_gate_params": FafGateParams, "fbanet_leff_fc2_params": LeffFc2Params, "fbanet_tile_params": TileParams,
     "fbanet_tile_band_params": TileBandParams, "fbanet_flow_warp_params": FlowWarpParams,
     "fbanet_ecc_prepare_params": EccPrepareParams, "fbanet_ecc_params": EccParams, "fbanet_train_loss_params": TrainLossParams,
+    "fbanet_adam_params": AdamParams,
 }
 
 # every symbol include/fbanet_b200.h declares
@@ -190,6 +200,7 @@ OPS = {
     "fbanet_faf_gate_sm100": FafGateParams, "fbanet_leff_fc2_sm100": LeffFc2Params, "fbanet_tile_divide_sm100": TileParams, "fbanet_tile_merge_sm100": TileParams,
     "fbanet_tile_divide_banded_sm100": TileBandParams, "fbanet_tile_merge_banded_sm100": TileBandParams, "fbanet_flow_warp_sm100": FlowWarpParams,
     "fbanet_ecc_prepare_sm100": EccPrepareParams, "fbanet_ecc_homography_sm100": EccParams, "fbanet_train_loss_sm100": TrainLossParams,
+    "fbanet_adam_step_sm100": AdamParams,
 }
 MISC_SYMBOLS = ["fbanet_abi_version", "fbanet_abi_sizeof", "fbanet_last_cuda_error", "fbanet_conv_gemm_tcgen05_supported", "fbanet_leff_fc2_supported",
                 "fbanet_train_loss_workspace_doubles"]

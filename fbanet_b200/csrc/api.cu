@@ -58,6 +58,7 @@ extern "C" int fbanet_abi_sizeof(const char* n) {
   SZ(fbanet_ecc_prepare_params);
   SZ(fbanet_ecc_params);
   SZ(fbanet_train_loss_params);
+  SZ(fbanet_adam_params);
 #undef SZ
   return -1;
 }

@@ -122,3 +122,35 @@ extern "C" int fbanet_train_loss_sm100(const fbanet_train_loss_params* p, void* 
   train_loss_finish_kernel<<<1, TL_THREADS, 0, (cudaStream_t)stream>>>(*p, (int64_t)grid.x * grid.y);
   return check_launch();
 }
+
+// ------------------------------------------------------------------------------------------------
+// SURVEY 8f-3, second brick: the optimizer step of train.py.bak:72-78 -- torch.optim.Adam / AdamW(lr, betas = (0.9, 0.999),
+// eps = 1e-8, weight_decay) -- over ONE flat fp32 buffer holding all 19.2 M parameters (and flat gradient / moment buffers), so the
+// whole update is one coalesced bandwidth pass (16 B read + 12 B written per parameter) instead of ~460 per-tensor launches.
+//   AdamW (decoupled):  p *= 1 - lr*wd;            Adam (L2):  g += wd * p
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// grad_scale multiplies the incoming gradient first (1 / world after a sum all-reduce, or a loss-scale inverse).
+// ------------------------------------------------------------------------------------------------
+namespace fbanet {
+__global__ void __launch_bounds__(256) adam_step_kernel(const fbanet_adam_params p) {
+  const float b2 = p.beta2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
+    float w = p.param[i], g = p.grad[i] * p.grad_scale, m = p.exp_avg[i], v = p.exp_avg_sq[i];
+    if (p.decoupled) w *= 1.f - p.lr * p.weight_decay;
+    else g = fmaf(p.weight_decay, w, g);
+    m = fmaf(p.one_minus_beta1, g - m, m);        // torch: exp_avg.lerp_(grad, 1 - beta1)
+    v = fmaf(p.one_minus_beta2 * g, g, b2 * v);   // torch: exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
+    const float denom = sqrtf(v) / p.bias2_sqrt + p.eps;
+    w -= p.step_size * (m / denom);
+    p.param[i] = w; p.exp_avg[i] = m; p.exp_avg_sq[i] = v;
+  }
+}
+}  // namespace fbanet
+
+extern "C" int fbanet_adam_step_sm100(const fbanet_adam_params* p, void* stream) {
+  if (!p || !p->param || !p->grad || !p->exp_avg || !p->exp_avg_sq || p->n <= 0 || !(p->bias2_sqrt > 0.f)) return FBANET_E_BADSHAPE;
+  int64_t blocks = (p->n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  adam_step_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch();
+}

@@ -8,6 +8,8 @@ Channels-last views: a tensor ``[N,H,W,C]`` with ``stride(-1) == 1`` and ``strid
 """
 from __future__ import annotations
 
+import math
+
 import ctypes as C
 from typing import Optional, Sequence
 
@@ -554,6 +556,23 @@ def training_loss(restored: torch.Tensor, target: torch.Tensor, eps: float = 1e-
     p.planes, p.H, p.W = B * Cc, H, W
     _call("fbanet_train_loss_sm100", p, nbytes=restored.numel() * 4 * (3 if need_grad else 2))
     return loss, grad
+
+
+def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int, lr: float,
+              betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, decoupled: bool = True, grad_scale: float = 1.0) -> None:
+    """One ``torch.optim.AdamW`` (``decoupled``) / ``Adam`` update (``train.py.bak:72-78``) over flat fp32 buffers, in place.
+    ``step`` is the 1-based step count after this update (torch's ``state["step"]`` once incremented)."""
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel()
+    assert step >= 1
+    p = L.AdamParams()
+    p.param, p.grad, p.exp_avg, p.exp_avg_sq, p.n = param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel()
+    p.lr, p.beta1, p.beta2, p.eps, p.weight_decay = float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay)
+    p.step_size = float(lr) / (1.0 - float(betas[0]) ** step)
+    p.bias2_sqrt = math.sqrt(1.0 - float(betas[1]) ** step)
+    p.one_minus_beta1, p.one_minus_beta2 = 1.0 - float(betas[0]), 1.0 - float(betas[1])
+    p.grad_scale, p.decoupled = float(grad_scale), 1 if decoupled else 0
+    _call("fbanet_adam_step_sm100", p, nbytes=param.numel() * 28)
 
 
 def _band_params(bands, row0, tiles, T, Cc, H, W, psize, overlap, tile_begin, tile_end, scale):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 17
+#define FBANET_ABI_VERSION 18
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -360,6 +360,21 @@ typedef struct fbanet_train_loss_params {
   int32_t planes, H, W;
 } fbanet_train_loss_params;
 
+/* Optimizer step: torch.optim.Adam / AdamW(lr, betas=(0.9, 0.999), eps=1e-8, weight_decay), train.py.bak:72-78, over
+ * flat fp32 buffers of n elements.  The host passes the step-dependent scalars: step_size = lr / (1 - beta1^t),
+ * bias2_sqrt = sqrt(1 - beta2^t).  decoupled = 1: AdamW (p *= 1 - lr*wd), 0: Adam (g += wd*p).  grad_scale: applied to the gradient
+ * first (1/world after a sum all-reduce). */
+typedef struct fbanet_adam_params {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+  float lr, beta1, beta2, eps, weight_decay, step_size, bias2_sqrt, grad_scale;
+  float one_minus_beta1, one_minus_beta2;   /* formed in double on the host, as torch does (1 - 0.999f is off by 1.3e-5 relative) */
+  int32_t decoupled, _pad;
+} fbanet_adam_params;
+
 int fbanet_abi_version(void);
 /* sizeof() of the named parameter struct as compiled, for binding self-checks; -1 if unknown */
 int fbanet_abi_sizeof(const char* struct_name);
@@ -389,6 +404,7 @@ int fbanet_flow_warp_sm100(const fbanet_flow_warp_params* p, void* stream);
 int fbanet_ecc_prepare_sm100(const fbanet_ecc_prepare_params* p, void* stream);
 int fbanet_ecc_homography_sm100(const fbanet_ecc_params* p, void* stream);
 int fbanet_train_loss_sm100(const fbanet_train_loss_params* p, void* stream);
+int fbanet_adam_step_sm100(const fbanet_adam_params* p, void* stream);
 /* doubles of workspace fbanet_train_loss_sm100 needs (2 per thread block) */
 int64_t fbanet_train_loss_workspace_doubles(int32_t planes, int32_t H, int32_t W);
 

@@ -650,3 +650,24 @@ def test_training_loss_matches_vectors_from_the_reference_code(cuda):
     assert abs(loss[0].item() - float(d["total"])) < 1e-5 * float(d["total"]) and abs(loss[1].item() - float(d["charbonnier"])) < 1e-6
     assert abs(loss[2].item() - float(d["gw"])) < 1e-5 * float(d["gw"])
     assert np.abs(grad.cpu().numpy() - d["grad"]).max() < 1e-5 * np.abs(d["grad"]).max()
+
+
+@pytest.mark.parametrize("decoupled,wd", [(True, 0.02), (False, 0.02), (True, 0.0)])
+def test_adam_step_matches_torch_optim(cuda, decoupled, wd):
+    """8f-3: the flat-buffer optimizer step against torch.optim.AdamW / Adam (the reference's optimizer, train.py.bak:72-78) over five
+    steps with fresh gradients; CPU torch is the reference here (it is the library the reference trainer calls)."""
+    from fbanet_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    n = 100_003
+    w0 = torch.randn(n, generator=g) * 0.1
+    ref = torch.nn.Parameter(w0.clone())
+    opt = (torch.optim.AdamW if decoupled else torch.optim.Adam)([ref], lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+    w, m, v = w0.clone().to(cuda), torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+    for step in range(1, 6):
+        gr = torch.randn(n, generator=g) * (0.5 if step % 2 else 2.0)
+        ref.grad = gr.clone()
+        opt.step()
+        ops.adam_step(w, (gr * 4.0).to(cuda), m, v, step, lr=2e-4, weight_decay=wd, decoupled=decoupled, grad_scale=0.25)   # as after a 4-rank sum
+        assert (w.cpu() - ref.detach()).abs().max().item() < 2e-7, step
+    st = opt.state[ref]
+    assert (m.cpu() - st["exp_avg"]).abs().max().item() < 1e-6 and (v.cpu() - st["exp_avg_sq"]).abs().max().item() < 1e-6
