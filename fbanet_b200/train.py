@@ -1,0 +1,67 @@
+"""Training-step plumbing that does not depend on the (not yet built) backward kernels -- SURVEY 8f-3, BASELINE config 5:
+flat parameter / gradient / moment buffers, the data-parallel gradient all-reduce (the ONE collective of the whole system:
+``ncclAllReduce(sum)`` over the 19.2 M gradients, reference ``train.py.bak:83-84`` ``DataParallel`` / north-star "NCCL allreduce appears only
+in the training-step config"), the fused Adam / AdamW step (``train.py.bak:72-78``) and the loss (``:118-119,168``).
+
+What a training step will be once the backward exists::
+
+    loss, d_restored = ops.training_loss(model(burst), target)      # built (fbanet_train_loss_sm100)
+    backward(model, d_restored) -> flat.grad                        # NOT built: DESIGN.md 8c
+    flat.all_reduce()                                               # built: one NCCL sum over the flat gradient buffer
+    flat.adam_step(lr)                                              # built (fbanet_adam_step_sm100), grad_scale = 1 / world
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class FlatParams:
+    """All parameters of a module re-pointed into ONE contiguous fp32 buffer (plus flat gradient and Adam moment buffers of the same
+    layout), so the all-reduce is one collective and the optimizer one bandwidth pass.  ``module.state_dict()`` / checkpoints are
+    unaffected: the parameters keep their names and shapes, only their storage moves."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        assert self.params, "no trainable parameters"
+        dev = self.params[0].device
+        assert all(p.device == dev and p.dtype == torch.float32 for p in self.params), "one device, fp32 master parameters"
+        self.offsets, n = [], 0
+        for p in self.params:
+            self.offsets.append(n)
+            n += p.numel()
+        self.numel = n
+        self.data = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.step = 0
+        for p, o in zip(self.params, self.offsets):
+            self.data[o:o + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self.data[o:o + p.numel()].view_as(p)                # the parameter now lives inside the flat buffer
+            p.grad = self.grad[o:o + p.numel()].view_as(p)                # and its gradient inside the flat gradient buffer
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+
+    def all_reduce(self, group=None) -> float:
+        """Sum the flat gradient over the data-parallel ranks (one collective); returns the scale (1 / world) the optimizer step
+        must apply -- the division is fused into ``adam_step`` instead of being a pass of its own."""
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1.0
+        world = dist.get_world_size(group)
+        if world > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+        return 1.0 / world
+
+    def adam_step(self, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, decoupled: bool = True,
+                  grad_scale: float = 1.0) -> None:
+        """One fused Adam / AdamW update of every parameter (``fbanet_adam_step_sm100``); CUDA only, no fallback."""
+        from . import ops
+        self.step += 1
+        ops.adam_step(self.data, self.grad, self.exp_avg, self.exp_avg_sq, self.step, lr, betas, eps, weight_decay, decoupled, grad_scale)
+
+    def optimizer_state(self) -> dict:
+        return {"step": self.step, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}

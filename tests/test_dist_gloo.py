@@ -96,3 +96,43 @@ def test_two_rank_row_bands_and_halo_plan():
     assert s0 == (0, 3) and s1 == (3, 6)                      # 3 x 2 tiles of 20 px over a 50 x 30 image
     assert ok0 and ok1
     assert need0 == {0: 25, 1: 25} and need1 == {0: 15, 1: 25}   # rank 0's tile rows 0-1 reach rows 0..49, rank 1's rows 10..49
+
+
+def _flat_worker(rank, world, port, q):
+    """Config 5's only collective: every rank's flat gradient buffer is summed in ONE all-reduce; the 1/world scale is handed to the
+    optimizer step.  Parameters keep living inside the flat buffer (views), so state_dict / checkpoints are unaffected."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from fbanet_b200.dist import init_from_env
+    from fbanet_b200.train import FlatParams
+    r, _, w = init_from_env("gloo")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.PReLU(), torch.nn.Linear(7, 3))
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    flat = FlatParams(net.parameters())
+    same = all(torch.equal(before[k], v) for k, v in net.state_dict().items())            # values survive the re-pointing
+    views = all(p.data.data_ptr() >= flat.data.data_ptr() and p.data.data_ptr() < flat.data.data_ptr() + flat.numel * 4 for p in net.parameters())
+    x = torch.full((4, 5), float(r + 1))
+    net(x).sum().backward()                                                               # autograd accumulates INTO the flat gradient buffer
+    local = flat.grad.clone()
+    scale = flat.all_reduce()
+    gathered = [torch.empty_like(local) for _ in range(w)]
+    dist.all_gather(gathered, local)
+    ok = bool(torch.allclose(flat.grad, sum(gathered))) and flat.grad.abs().sum().item() > 0
+    dist.barrier()
+    q.put((r, same, views, ok, scale, flat.numel))
+    dist.destroy_process_group()
+
+
+def test_two_rank_flat_gradient_all_reduce():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_flat_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r, same, views, ok, scale, n in res:
+        assert same and views and ok and scale == 0.5 and n == 5 * 7 + 7 + 1 + 7 * 3 + 3

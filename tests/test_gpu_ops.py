@@ -671,3 +671,26 @@ def test_adam_step_matches_torch_optim(cuda, decoupled, wd):
         assert (w.cpu() - ref.detach()).abs().max().item() < 2e-7, step
     st = opt.state[ref]
     assert (m.cpu() - st["exp_avg"]).abs().max().item() < 1e-6 and (v.cpu() - st["exp_avg_sq"]).abs().max().item() < 1e-6
+
+
+def test_flat_params_adam_step_matches_torch_on_a_module(cuda):
+    """8f-3: FlatParams (parameters re-pointed into one buffer) + the fused AdamW step against torch.optim.AdamW on a twin module,
+    three steps with autograd gradients accumulated straight into the flat gradient buffer."""
+    import copy
+    from fbanet_b200.train import FlatParams
+    torch.manual_seed(1)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.PReLU(), torch.nn.Conv2d(8, 3, 3, padding=1)).to(cuda)
+    twin = copy.deepcopy(net)
+    opt = torch.optim.AdamW(twin.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.02)
+    flat = FlatParams(net.parameters())
+    for step in range(3):
+        x = torch.rand(2, 3, 16, 16, device=cuda, generator=torch.Generator(device=cuda).manual_seed(step))
+        flat.zero_grad()
+        opt.zero_grad()
+        net(x).square().mean().backward()
+        twin(x).square().mean().backward()
+        flat.adam_step(1e-3, weight_decay=0.02)
+        opt.step()
+        for a, b in zip(net.parameters(), twin.parameters()):
+            assert (a - b).abs().max().item() < 1e-6, step
+    assert set(net.state_dict()) == set(twin.state_dict())
