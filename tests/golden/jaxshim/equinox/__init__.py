@@ -8,9 +8,11 @@ import dataclasses as _dc
 from . import nn  # noqa: F401
 
 
-def field(*, init=True, default=_dc.MISSING, static=False, **kw):
+def field(*, init=True, default=_dc.MISSING, default_factory=_dc.MISSING, static=False, **kw):
     if default is not _dc.MISSING:
         return _dc.field(init=init, default=default)
+    if default_factory is not _dc.MISSING:
+        return _dc.field(init=init, default_factory=default_factory)
     return _dc.field(init=init)
 
 

@@ -45,3 +45,7 @@ def zeros(shape, dtype=_np.float32):
 
 def roll(a, shift, axis=None):
     return asarray(_roll(a, shift, axis))
+
+
+def linspace(start, stop, num=50):
+    return asarray(_np.linspace(start, stop, num, dtype=_np.float32))

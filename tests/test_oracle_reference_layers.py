@@ -169,7 +169,7 @@ def test_reference_layers_faf_block(ref):
     feat = t(x).permute(0, 3, 1, 2)[None]  # [1, F, C, H, W]
     g, gate = faf.guided(feat)
     close(g[0].permute(0, 2, 3, 1), ref["faf/guided"])
-    assert float(gate.min()) >= 0.5  # sigmoid(|.|): the gate never attenuates below one half
+    assert gate.min().item() >= 0.5  # sigmoid(|.|): the gate never attenuates below one half
     fused, _ = faf.fuse(t(ref["faf/guided"]).permute(0, 3, 1, 2)[None])
     close(fused[0].permute(1, 2, 0), ref["faf/fused"])
     close(faf(feat)[0].permute(1, 2, 0), ref["faf/y"])
@@ -220,3 +220,104 @@ def test_reference_layers_plain_layer_as_written(ref):
         if i < 2:
             u = act(u)
     close(2 * u, ref[pre + "y"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the model file (models/fba_net.py): structure as the reference's own constructor built it, wiring as its own __call__ ran it
+# (tests/golden/make_golden_model.py)
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg,kw", [("cfg2_rgb160", dict()), ("cfg3_raw80", dict(in_channels=4, img_size=80))])
+def test_reference_model_structure(cfg, kw):
+    import json
+
+    with open(os.path.join(os.path.dirname(GOLD), "model_structure_reference.json")) as f:
+        want = json.load(f)[cfg]
+    m = O.OracleBaseModel(**kw)
+    E, cin = m.embed_dim, m.in_channels
+    extra_tail_conv = E * 4 * E * 9 + 4 * E  # A-17: the reference builds a x2 tail (scale_pow_two=1); x4 needs one more conv E -> 4E
+    assert sum(p.numel() for p in m.parameters()) == want["total_params"] + extra_tail_conv
+    names = {n for n, _ in m.named_children()}
+    assert names == set(want["modules"]) - {"pos_drop"}  # Dropout(0.0), no parameters (A-8)
+    for name, row in want["modules"].items():
+        if name == "pos_drop":
+            continue
+        sub = getattr(m, name)
+        have = sum(p.numel() for p in sub.parameters())
+        assert have == row["params"] + (extra_tail_conv if name == "tail" else 0), name
+        if "layers" in row:  # an FBANetBlock (blocks/fba_net.py) of FBANetLayers
+            assert len(sub.blocks) == row["depth"] == len(row["layers"])
+            for lay, r in zip(sub.blocks, row["layers"]):
+                assert (lay.dim, list(lay.res), lay.attn.heads, lay.win, lay.shift) == (row["dim"], row["input_resolution"], r["heads"], r["window"], r["shift"]), name
+                assert lay.dim // lay.attn.heads == r["dim_head"] and lay.mlp.linear1[0].out_features == r["mlp_hidden"]
+                assert list(lay.attn.relative_position_bias_table.shape) == r["bias_table"]
+    assert cin == (4 if "raw" in cfg else 3)
+
+
+class _Mix(torch.nn.Module):
+    """torch mirror of make_golden_model.py's `Stub`, in the layouts the oracle passes (tokens [B,T,C] or images [B,C,H,W])."""
+
+    def __init__(self, z, name, kind):
+        super().__init__()
+        self.M, self.b, self.kind = t(z[f"stub/{name}/M"]).float(), t(z[f"stub/{name}/b"]).float(), kind
+
+    def mix(self, x):
+        return torch.tanh(x @ self.M + self.b)
+
+    def forward(self, x, H=None, W=None):
+        if self.kind == "tokens":
+            return self.mix(x)
+        if self.kind == "image":
+            return self.mix(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+        if self.kind == "tail":
+            return self.mix(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2).repeat_interleave(4, 2).repeat_interleave(4, 3)
+        B, T, C = x.shape
+        img = x.view(B, H, W, C)
+        if self.kind == "down":
+            img = img.view(B, H // 2, 2, W // 2, 2, C).mean(dim=(2, 4))
+        else:
+            img = img.repeat_interleave(2, 1).repeat_interleave(2, 2)
+        return self.mix(img.reshape(B, -1, C))
+
+
+class _Fusion(torch.nn.Module):
+    def __init__(self, z):
+        super().__init__()
+        self.inner = _Mix(z, "fusion", "image")
+
+    def guided(self, feat):
+        return feat, None
+
+    def fuse(self, g):  # [B,F,C,H,W]: frames concatenated along channels, frame-major
+        B, Fr, C, H, W = g.shape
+        return self.inner(g.reshape(B, Fr * C, H, W)), None
+
+
+def test_reference_model_wiring():
+    z = np.load(os.path.join(os.path.dirname(GOLD), "model_wiring_reference.npz"))
+    x = t(z["x"])  # [F, S, S, 3]
+    Fr, S = x.shape[0], x.shape[1]
+    m = O.OracleBaseModel(num_frames=Fr, img_size=S, in_channels=3, embed_dim=4, window_length=2)
+    for name in ("head", "body", "input_proj", "output_proj", "output_proj_2", "output_proj_HG2_0", "output_proj_HG2_1"):
+        setattr(m, name, _Mix(z, name, "image"))
+    m.tail = _Mix(z, "tail", "tail")
+    m.fusion = _Fusion(z)
+    for hg in ("HG1", "HG2"):
+        for name in (f"{hg}_encoderlayer_0", f"{hg}_encoderlayer_1", f"conv_{hg}", f"{hg}_decoderlayer_0", f"{hg}_decoderlayer_1"):
+            setattr(m, name, _Mix(z, name, "tokens"))
+        for i in (0, 1):
+            setattr(m, f"{hg}_downsample_{i}", _Mix(z, f"{hg}_downsample_{i}", "down"))
+            setattr(m, f"{hg}_upsample_{i}", _Mix(z, f"{hg}_upsample_{i}", "up"))
+    st = m.forward_stages(x.permute(0, 3, 1, 2)[None])
+    img = lambda v: v[0].permute(1, 2, 0)
+    close(img(st["fusion"]), z["out/fusion"])
+    close(st["input_proj"][0], z["out/input_proj"])
+    for hg in ("HG1", "HG2"):
+        for stage, mod in (("conv0", f"{hg}_encoderlayer_0"), ("pool0", f"{hg}_downsample_0"), ("conv1", f"{hg}_encoderlayer_1"),
+                           ("pool1", f"{hg}_downsample_1"), ("conv2", f"conv_{hg}"), ("up0", f"{hg}_upsample_0"),
+                           ("deconv0", f"{hg}_decoderlayer_0"), ("up1", f"{hg}_upsample_1"), ("deconv1", f"{hg}_decoderlayer_1")):
+            close(st[f"{hg}.{stage}"][0], z[f"out/{mod}"])
+    close(st["HG2.deconv0_in"][0], z["out/output_proj_HG2_0"])  # cat[up0, conv1, up0_2, conv1_2] (:305)
+    close(st["HG2.deconv1_in"][0], z["out/output_proj_HG2_1"])  # cat[up1, conv0, up1_2, conv0_2] (:309)
+    close(st["output_proj"][0], z["out/output_proj"])
+    close(img(st["output_proj_2"]), z["out/output_proj_2"])
+    close(img(st["tail"]), z["out/tail"])
