@@ -6,7 +6,7 @@ The reference's model is JAX/Equinox; neither library is installed and the whole
 restates the documented semantics of the ~20 primitives the layers call in numpy, and this script imports the UNMODIFIED reference
 packages `fba_net.layers.*` / `fba_net.blocks.*` from /root/reference on top of it, runs every layer that is executable as
 written on seeded inputs and stores (weights as the reference holds them, inputs, outputs) in `layers_reference.npz`.
-`tests/test_oracle.py::test_reference_layers_*` loads the weights into the oracle's modules (converting the layouts as SURVEY
+`tests/test_oracle_reference_layers.py` loads the weights into the oracle's modules (converting the layouts as SURVEY
 A-11 says) and must reproduce the outputs.  What gets pinned is the reference's own composition code: axis swaps around the
 convolutions, PReLU placement, the q / k / v split pattern, the attention arithmetic (heads = 1, the only case its asserts allow),
 the FAF gate and hourglass wiring, window partition / cyclic shift / reverse and the 9-region mask construction.
@@ -168,6 +168,37 @@ put("layer_plain", **{"norm1.weight": lay.norm1.weight, "norm1.bias": lay.norm1.
                       "norm2.bias": lay.norm2.bias, "mlp.0.weight": lay.mlp.layers[0].weight, "mlp.0.bias": lay.mlp.layers[0].bias,
                       "mlp.1.weight": lay.mlp.layers[1].weight, "mlp.1.bias": lay.mlp.layers[1].bias,
                       "mlp.2.weight": lay.mlp.layers[2].weight, "mlp.2.bias": lay.mlp.layers[2].bias}, x=x, y=lay(x))
+
+# ---- FAFBlock once more at a size the CUDA path runs (num_feats 32, 4 frames, 40 x 40 = tests/test_gpu_model.py SMALL): weights and input
+# come from `det_array` (rebuilt by the test from the seeds), only the reference's output is stored.  `-m gpu` compares the CUDA FAF
+# (gate kernel + implicit GEMMs) with it directly, not via the oracle.
+sys.path.insert(0, os.path.dirname(HERE))
+from tests_golden_helpers import det_array, faf_gpu_weights  # noqa: E402
+
+def faf_gpu_case(prefix, nf, frames, side, seed0, x_seed):
+    faf = FAFBlock(num_feats=nf, num_frames=frames)
+    weights = faf_gpu_weights(nf, frames, seed0)
+
+    def set_conv(conv, name):
+        assert conv.weight.shape == weights[name + ".weight"].shape and conv.bias.shape == weights[name + ".bias"].shape, name
+        conv.weight, conv.bias = jnp.asarray(weights.pop(name + ".weight")), jnp.asarray(weights.pop(name + ".bias"))
+
+    for name in ("temporal_attn0", "temporal_attn1", "downsample0", "downsample1", "upsample0", "upsample1", "fusion_tail"):
+        set_conv(conv_of(getattr(faf, name)), name)
+    set_conv(conv_of(faf.feature_fusion[0]), "feature_fusion.0")
+    for i, seq in enumerate(faf.res_blocks):
+        for j in range(2):
+            for k in (0, 2):
+                set_conv(conv_of(seq[j].fn.body[k]), f"res_blocks.{i}.{j}.body.{k}")
+    assert not weights
+    x = jnp.asarray(det_array((frames, side, side, nf), x_seed, -1.0, 1.0))
+    guided = faf.compute_guided_aligned_features(x)
+    g_, x_ = np.asarray(guided, dtype=np.float64)[1:], np.asarray(x, dtype=np.float64)[1:]
+    put(prefix, gate=(g_ * x_).sum(-1) / (x_ * x_).sum(-1), y=faf(x), nf=nf, frames=frames, side=side, seed0=seed0, x_seed=x_seed)
+
+
+faf_gpu_case("faf_gpu", 32, 4, 40, 1000, 999)      # fp32 CUDA-core path (tests/test_gpu_model.py SMALL)
+faf_gpu_case("faf_gpu64", 64, 4, 40, 2000, 1999)   # 64-channel granularity: the tcgen05 path in bf16
 
 np.savez_compressed(os.path.join(HERE, "layers_reference.npz"), **{k: np.asarray(v, dtype=np.float32) if np.asarray(v).dtype.kind == "f" else np.asarray(v)
                                                                   for k, v in out.items()})

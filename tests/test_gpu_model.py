@@ -272,3 +272,35 @@ def test_empty_batch(cuda):
     assert m.infer_host(torch.empty(0, T, C, S, S)).shape == (0, C, 4 * S, 4 * S)
     with pytest.raises(AssertionError):
         m(torch.empty(1, T, C, S + 1, S, device=cuda))      # wrong frame size: the reference's shape assert (models/fba_net.py:244)
+
+
+@pytest.mark.parametrize("pre,dtype", [("faf_gpu", "fp32"), ("faf_gpu64", "fp32"), ("faf_gpu64", "bf16")])
+def test_faf_against_reference_executed_fixture(cuda, pre, dtype):
+    """CUDA FAF (gate kernel + fuse GEMM + hourglass convs) against the output of the REFERENCE'S OWN `FAFBlock` code
+    (tests/golden/layers_reference.npz `faf_gpu*/`, produced by tests/golden/make_golden_layers.py executing
+    blocks/federated_affinity_fusion.py:18-182).  The oracle module is only the carrier of the layout-converted weights here;
+    the values compared are the reference's.  bf16 with 64 channels runs the tcgen05 implicit-GEMM path."""
+    import numpy as np
+    from fbanet_b200 import BaseModel
+    from oracle.fbanet_oracle import psnr
+    from test_oracle_reference_layers import GOLD, faf_gpu_case
+
+    z = np.load(GOLD)
+    carrier, feat, gate, y = faf_gpu_case({k: z[k] for k in z.files if k.startswith(pre + "/")}, pre)
+    nf, frames, side = feat.shape[2], feat.shape[1], feat.shape[3]
+    m = BaseModel(num_frames=frames, img_size=side, in_channels=3, embed_dim=nf, window_length=10, token_projection="linear",
+                  token_mlp="leff", dtype=dtype)
+    m.fusion.load_state_dict(carrier.state_dict())
+    m = m.to(cuda).eval()
+    x = feat.permute(0, 1, 3, 4, 2).contiguous().to(cuda).to(m.compute_dtype)  # [1,F,H,W,E]
+    out, _, g = m._faf(m.packed(), x)
+    torch.cuda.synchronize()
+    out, g = out.float().cpu()[0].numpy(), g.float().cpu()[0].numpy()
+    assert out.shape == y.shape and g.shape == gate.shape
+    if dtype == "fp32":
+        assert np.abs(g - gate).max() <= 1e-4, np.abs(g - gate).max()
+        assert np.abs(out - y).max() <= 1e-3, np.abs(out - y).max()          # north_star: fp32 max abs error <= 1e-3
+    else:
+        assert np.abs(g - gate).max() <= 2e-2, np.abs(g - gate).max()
+        span = float(y.max() - y.min())
+        assert psnr(torch.from_numpy(out), torch.from_numpy(y), max_val=span) > 40.0

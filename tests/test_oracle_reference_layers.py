@@ -149,15 +149,15 @@ def test_reference_layers_window_attention(ref):
     close(attn(t(ref["window_attention/x"])[None])[0], ref["window_attention/y"])
 
 
-def load_faf(faf, ref):
+def load_faf(faf, ref, pre="faf"):
     for name in ("temporal_attn0", "temporal_attn1", "downsample0", "downsample1", "upsample0", "upsample1", "fusion_tail"):
-        load_conv(getattr(faf, name), ref, f"faf/{name}")
-    load_conv(faf.feature_fusion[0], ref, "faf/feature_fusion.0")
-    faf.feature_fusion[1].weight.data = t(ref["faf/feature_fusion.1.weight"]).reshape(1)
+        load_conv(getattr(faf, name), ref, f"{pre}/{name}")
+    load_conv(faf.feature_fusion[0], ref, f"{pre}/feature_fusion.0")
+    faf.feature_fusion[1].weight.data = t(ref[f"{pre}/feature_fusion.1.weight"]).reshape(1)
     for i in range(5):
         for j in range(2):
-            load_conv(faf.res_blocks[i][j].body[0], ref, f"faf/res_blocks.{i}.{j}.body.0")
-            load_conv(faf.res_blocks[i][j].body[2], ref, f"faf/res_blocks.{i}.{j}.body.2")
+            load_conv(faf.res_blocks[i][j].body[0], ref, f"{pre}/res_blocks.{i}.{j}.body.0")
+            load_conv(faf.res_blocks[i][j].body[2], ref, f"{pre}/res_blocks.{i}.{j}.body.2")
 
 
 def test_reference_layers_faf_block(ref):
@@ -321,3 +321,26 @@ def test_reference_model_wiring():
     close(st["output_proj"][0], z["out/output_proj"])
     close(img(st["output_proj_2"]), z["out/output_proj_2"])
     close(img(st["tail"]), z["out/tail"])
+
+
+def faf_gpu_case(ref, pre="faf_gpu"):
+    """A GPU-sized FAF case of the fixture: (oracle FAFBlock carrying the reference's weights, input [1,F,C,H,W], reference gate, output)."""
+    from tests_golden_helpers import det_array, faf_gpu_weights
+
+    nf, frames, side = int(ref[pre + "/nf"]), int(ref[pre + "/frames"]), int(ref[pre + "/side"])
+    w = {f"{pre}/{k}": v for k, v in faf_gpu_weights(nf, frames, int(ref[pre + "/seed0"])).items()}
+    w[pre + "/feature_fusion.1.weight"] = np.float32(0.1)  # nn.PReLU(init_alpha=0.1), federated_affinity_fusion.py:47
+    faf = O.FAFBlock(nf, frames)
+    load_faf(faf, w, pre)
+    x = det_array((frames, side, side, nf), int(ref[pre + "/x_seed"]), -1.0, 1.0)
+    return faf, t(x).permute(0, 3, 1, 2)[None].contiguous(), ref[pre + "/gate"], ref[pre + "/y"]
+
+
+@pytest.mark.parametrize("pre", ["faf_gpu", "faf_gpu64"])
+def test_reference_layers_faf_block_gpu_size(ref, pre):
+    faf, feat, gate, y = faf_gpu_case(ref, pre)
+    with torch.no_grad():
+        g, gt = faf.guided(feat)
+        out, _ = faf.fuse(g)
+    np.testing.assert_allclose(gt[0].numpy(), gate, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out[0].permute(1, 2, 0).numpy(), y, rtol=1e-4, atol=1e-4)
