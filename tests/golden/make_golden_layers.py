@@ -200,6 +200,27 @@ def faf_gpu_case(prefix, nf, frames, side, seed0, x_seed):
 faf_gpu_case("faf_gpu", 32, 4, 40, 1000, 999)      # fp32 CUDA-core path (tests/test_gpu_model.py SMALL)
 faf_gpu_case("faf_gpu64", 64, 4, 40, 2000, 1999)   # 64-channel granularity: the tcgen05 path in bf16
 
+# ---- WindowAttentionLayer at the size of the model's first encoder stage (dim 64, window 10, heads 1 -- models/fba_net.py:130-139 with
+# get_arch's window), four windows through `jax.vmap` as layers/fba_net.py:222 does; weights / windows from `det_array`.
+# And LinearProjectionLayer at the second stage's size (dim 128, heads 2): the q / k / v column layout the CUDA qkv GEMM must produce.
+dim, win, nwin = 64, 10, 4
+wa = WindowAttentionLayer(dim=dim, window_length=win, heads=1)
+lim = 1.0 / np.sqrt(dim)
+wa.qkv.to_q.weight, wa.qkv.to_q.bias = jnp.asarray(det_array((dim, dim), 3000, -lim, lim)), jnp.asarray(det_array((dim,), 3001, -lim, lim))
+wa.qkv.to_kv.weight, wa.qkv.to_kv.bias = jnp.asarray(det_array((2 * dim, dim), 3002, -lim, lim)), jnp.asarray(det_array((2 * dim,), 3003, -lim, lim))
+wa.proj.weight, wa.proj.bias = jnp.asarray(det_array((dim, dim), 3004, -lim, lim)), jnp.asarray(det_array((dim,), 3005, -lim, lim))
+wa.relative_position_bias_table = jnp.asarray(det_array(((2 * win - 1) ** 2, 1), 3006, -1.0, 1.0))
+xw = jnp.asarray(det_array((nwin, win * win, dim), 3007, -2.0, 2.0))
+put("attn_gpu", y=jax.vmap(wa)(xw), index_as_written=wa.relative_position_index, dim=dim, win=win, nwin=nwin, seed0=3000)
+
+dim2, heads2 = 128, 2
+lp = LinearProjectionLayer(dim=dim2, heads=heads2)
+lim = 1.0 / np.sqrt(dim2)
+lp.to_q.weight, lp.to_q.bias = jnp.asarray(det_array((dim2, dim2), 3100, -lim, lim)), jnp.asarray(det_array((dim2,), 3101, -lim, lim))
+lp.to_kv.weight, lp.to_kv.bias = jnp.asarray(det_array((2 * dim2, dim2), 3102, -lim, lim)), jnp.asarray(det_array((2 * dim2,), 3103, -lim, lim))
+q, k, v = lp(jnp.asarray(det_array((100, dim2), 3104, -1.0, 1.0)))
+put("qkv_gpu", q=q, k=k, v=v, dim=dim2, heads=heads2, seed0=3100)
+
 np.savez_compressed(os.path.join(HERE, "layers_reference.npz"), **{k: np.asarray(v, dtype=np.float32) if np.asarray(v).dtype.kind == "f" else np.asarray(v)
                                                                   for k, v in out.items()})
 print("reference layer fixtures:", len(out), "arrays,", sum(np.asarray(v).size for v in out.values()), "values")

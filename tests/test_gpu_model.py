@@ -304,3 +304,68 @@ def test_faf_against_reference_executed_fixture(cuda, pre, dtype):
         assert np.abs(g - gate).max() <= 2e-2, np.abs(g - gate).max()
         span = float(y.max() - y.min())
         assert psnr(torch.from_numpy(out), torch.from_numpy(y), max_val=span) > 40.0
+
+
+def _ref_fixture(prefixes):
+    import numpy as np
+    from test_oracle_reference_layers import GOLD
+
+    z = np.load(GOLD)
+    return {k: z[k] for k in z.files if k.split("/")[0] in prefixes}
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_window_attention_against_reference_executed_fixture(cuda, dtype):
+    """qkv GEMM -> window attention kernel -> proj GEMM of the first encoder stage (dim 64, window 10, heads 1) against the output of
+    the REFERENCE'S OWN `WindowAttentionLayer` code (layers/window_attention.py:159-248 through `jax.vmap` over four windows,
+    `attn_gpu/*` of tests/golden/layers_reference.npz).  bf16 runs the tensor-core attention and the tcgen05 GEMMs."""
+    import numpy as np
+    from fbanet_b200 import BaseModel, ops
+    from oracle.fbanet_oracle import psnr, window_partition, window_reverse
+    from test_oracle_reference_layers import attn_gpu_case
+
+    carrier, xw, y = attn_gpu_case(_ref_fixture({"attn_gpu"}))
+    nwin, N, dim = xw.shape
+    win, side = int(round(N ** 0.5)), int(round((nwin * N) ** 0.5))
+    m = BaseModel(num_frames=2, img_size=side, in_channels=3, embed_dim=dim, window_length=win, token_projection="linear",
+                  token_mlp="leff", dtype=dtype)
+    ly = m.HG1_encoderlayer_0.blocks[0]
+    assert (ly.heads, ly.win, ly.shift, ly.dim) == (1, win, 0, dim)
+    ly.attn.load_state_dict(carrier.state_dict())
+    m = m.to(cuda).eval()
+    P, key = m.packed(), "HG1_encoderlayer_0.0"
+    x = window_reverse(xw, win, 1, side, side).contiguous().to(cuda).to(m.compute_dtype)  # [1,H,W,d]
+    qkv = m._lin(P, key + ".qkv", x)
+    att = ops.window_attention(qkv.view(-1, 3 * dim), P[key + ".rpb"], 1, side, side, 1, win, 0, dim ** -0.5, impl=m.impl,
+                               bias_expanded=P.get(key + ".rpbx"), q_prescaled=m._use_tc())
+    out = m._lin(P, key + ".proj", att.view(1, side, side, dim))
+    torch.cuda.synchronize()
+    got = window_partition(out.float().cpu(), win).numpy()
+    assert got.shape == y.shape
+    if dtype == "fp32":
+        assert np.abs(got - y).max() <= 1e-3, np.abs(got - y).max()
+    else:
+        assert psnr(torch.from_numpy(got), torch.from_numpy(y), max_val=float(y.max() - y.min())) > 40.0
+
+
+def test_qkv_layout_against_reference_executed_fixture(cuda):
+    """The fused q | k | v GEMM's column layout (head-major inside each third) against the reference's own
+    `LinearProjectionLayer` split `"n (hd h c) -> hd h n c"` (layers/linear_projection.py:38-43) at dim 128, heads 2."""
+    import numpy as np
+    from fbanet_b200 import BaseModel
+    from test_oracle_reference_layers import qkv_gpu_case
+
+    carrier, x, q, k, v = qkv_gpu_case(_ref_fixture({"qkv_gpu"}))
+    heads, n, dh = q.shape
+    dim = heads * dh
+    m = BaseModel(num_frames=2, img_size=20, in_channels=3, embed_dim=dim // 2, window_length=10, token_projection="linear",
+                  token_mlp="leff", dtype="fp32")
+    ly = m.HG1_encoderlayer_1.blocks[0]
+    assert (ly.heads, ly.dim) == (heads, dim)
+    ly.attn.qkv.load_state_dict(carrier.state_dict())
+    m = m.to(cuda).eval()
+    qkv = m._lin(m.packed(), "HG1_encoderlayer_1.0.qkv", x.view(1, 10, 10, dim).contiguous().to(cuda))
+    torch.cuda.synchronize()
+    got = qkv.float().cpu().view(n, 3, heads, dh).permute(1, 2, 0, 3).numpy()  # [3, h, n, dh]
+    for g, r in zip(got, (q, k, v)):
+        assert np.abs(g - r).max() <= 1e-4, np.abs(g - r).max()

@@ -344,3 +344,41 @@ def test_reference_layers_faf_block_gpu_size(ref, pre):
         out, _ = faf.fuse(g)
     np.testing.assert_allclose(gt[0].numpy(), gate, rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(out[0].permute(1, 2, 0).numpy(), y, rtol=1e-4, atol=1e-4)
+
+
+def attn_gpu_case(ref):
+    """(oracle WindowAttention carrying the reference's weights, windows [nW, N, d], the reference's output [nW, N, d])."""
+    from tests_golden_helpers import det_array
+
+    dim, win, nwin, s0 = (int(ref["attn_gpu/" + k]) for k in ("dim", "win", "nwin", "seed0"))
+    lim = 1.0 / np.sqrt(dim)
+    w = {"a/qkv.to_q.weight": det_array((dim, dim), s0, -lim, lim), "a/qkv.to_q.bias": det_array((dim,), s0 + 1, -lim, lim),
+         "a/qkv.to_kv.weight": det_array((2 * dim, dim), s0 + 2, -lim, lim), "a/qkv.to_kv.bias": det_array((2 * dim,), s0 + 3, -lim, lim),
+         "a/proj.weight": det_array((dim, dim), s0 + 4, -lim, lim), "a/proj.bias": det_array((dim,), s0 + 5, -lim, lim),
+         "a/relative_position_bias_table": det_array(((2 * win - 1) ** 2, 1), s0 + 6, -1.0, 1.0),
+         "a/relative_position_index_as_written": ref["attn_gpu/index_as_written"]}
+    attn = O.WindowAttention(dim, win, 1)
+    load_attention(attn, w, "a/", win)
+    return attn, t(det_array((nwin, win * win, dim), s0 + 7, -2.0, 2.0)), ref["attn_gpu/y"]
+
+
+def qkv_gpu_case(ref):
+    from tests_golden_helpers import det_array
+
+    dim, heads, s0 = (int(ref["qkv_gpu/" + k]) for k in ("dim", "heads", "seed0"))
+    lim = 1.0 / np.sqrt(dim)
+    lp = O.LinearProjection(dim, heads)
+    lp.load_state_dict({"to_q.weight": t(det_array((dim, dim), s0, -lim, lim)), "to_q.bias": t(det_array((dim,), s0 + 1, -lim, lim)),
+                        "to_kv.weight": t(det_array((2 * dim, dim), s0 + 2, -lim, lim)), "to_kv.bias": t(det_array((2 * dim,), s0 + 3, -lim, lim))})
+    return lp, t(det_array((100, dim), s0 + 4, -1.0, 1.0)), ref["qkv_gpu/q"], ref["qkv_gpu/k"], ref["qkv_gpu/v"]
+
+
+def test_reference_layers_attention_and_qkv_gpu_size(ref):
+    attn, xw, y = attn_gpu_case(ref)
+    with torch.no_grad():
+        np.testing.assert_allclose(attn(xw).numpy(), y, rtol=1e-4, atol=1e-4)
+    lp, x, q, k, v = qkv_gpu_case(ref)
+    with torch.no_grad():
+        got = lp(x[None])
+    for g, r in zip(got, (q, k, v)):
+        np.testing.assert_allclose(g[0].numpy(), r, rtol=1e-4, atol=1e-5)
