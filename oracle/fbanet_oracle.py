@@ -6,12 +6,20 @@ the product: only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``c
 ``--impl reference`` legs may import it.  The product package (``fbanet_b200``) never does, and it
 fails loudly when its CUDA library is missing.
 
-PARITY UNPINNED.  The reference ships no tests, no golden vectors and no checkpoint, JAX is not
-installed in the build image, and the reference forward cannot execute as written (SURVEY.md F2/F5,
-Appendix A).  The oracle is therefore pinned only against independent closed forms (numpy window
-index / shift-mask formulas, ``cv2.warpPerspective`` in 1/32-px mode, float64 restatements) and the
-committed fixtures under ``tests/golden/`` that *this file* generated (script:
-``tests/golden/make_golden.py``).
+PARITY: PINNED LAYER BY LAYER, UNPINNED AS A WHOLE.  The reference ships no tests, no golden vectors and no checkpoint, JAX
+is not installed in the build image, and the reference's whole forward cannot execute as written.
+What CAN execute of it is executed: `tests/golden/make_golden_layers.py` / `make_golden_model.py` import the unmodified
+`fba_net.layers.*`, `fba_net.blocks.*` and `fba_net.models.fba_net` from /root/reference on top of numpy stand-ins for the ~20
+jax / equinox primitives they call (`tests/golden/jaxshim/`) and record the outputs of every layer that runs as written --
+convolutions (3x3, 1x1, 4x4 s2, depthwise, transposed), ResBlock, InputProjLayer, LinearProjectionLayer (heads 1/2/4),
+WindowAttentionLayer (heads 1), the whole FAFBlock, FBANetLayer's mask / cyclic shift / window partition / reverse, the unshifted
+FBANetLayer, the model's constructor (structure, parameter counts) and its `__call__` wiring over stub sub-modules.  The classes and
+functions below reproduce those vectors (`tests/test_oracle_reference_layers.py`; fixtures `tests/golden/layers_reference.npz`,
+`model_structure_reference.json`, `model_wiring_reference.npz`).  Still pinned only by reading + closed forms: the places where the
+reference does not execute (Appendix A-1 mask add, A-2 index, A-3 heads > 1, A-4 residuals, A-5/6 LeFF reshape, A-17/18/19 x4 tail,
+PixelShuffle order, bilinear base) and the primitives' semantics the stand-ins restate from the Equinox / JAX documentation.
+Further independent pins: numpy window index / shift-mask formulas, ``cv2.warpPerspective`` in 1/32-px mode, float64
+restatements, scipy / cv2 for the alignment front ends, and the reference's own torch-only tiling / loss / checkpoint code.
 
 Every place where the reference is not executable follows the decision register of SURVEY.md
 Appendix A ("A-n" below).  Layout: channels-first ``[N,C,H,W]`` images and ``[N,T,C]`` tokens
