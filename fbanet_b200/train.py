@@ -65,3 +65,41 @@ class FlatParams:
 
     def optimizer_state(self) -> dict:
         return {"step": self.step, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# learning-rate schedules and stochastic-depth rates of the training configuration (host arithmetic, no tensors)
+# ------------------------------------------------------------------------------------------------------------------------------
+def warmup_cosine_lr(epoch: int, lr_initial: float = 1e-4, nepoch: int = 250, warmup_epochs: int = 3, eta_min: float = 1e-6) -> float:
+    """Learning rate DURING training epoch ``epoch`` (1-based, as the loop of ``train.py.bak:150`` counts) under ``--warmup``:
+    ``GradualWarmupScheduler(multiplier=1, total_epoch=warmup_epochs, after_scheduler=CosineAnnealingLR(nepoch - warmup_epochs,
+    eta_min=1e-6))`` stepped once before the first epoch and once after every epoch (``train.py.bak:104-110,220``,
+    ``warmup_scheduler/scheduler.py:24-39,57-67``).  Closed form of what that pair of objects actually does (checked against the
+    reference's scheduler executed over whole runs, ``tests/golden/lr_schedule_reference.npz``): a linear ramp ``lr * e / warmup`` for
+    ``e <= warmup`` (epoch ``warmup`` already runs at the full rate); at the hand-over the wrapper returns the cosine scheduler's
+    RECURSIVE ``get_lr()`` while that scheduler still sits at its epoch 0, so with ``c = e - warmup - 1`` and ``T = nepoch - warmup``
+    the rate is ``eta + (lr - eta) * (1 + cos(pi c / T)) / (1 + cos(pi / T))``: a slight overshoot above ``lr`` at ``c = 0``,
+    exactly ``lr`` at ``c = 1``, and a cosine that ends at ``c = T - 1`` (one epoch short of ``eta``)."""
+    import math
+    if epoch <= warmup_epochs:
+        return lr_initial * epoch / warmup_epochs
+    c, t_max = epoch - warmup_epochs - 1, nepoch - warmup_epochs
+    return eta_min + (lr_initial - eta_min) * (1.0 + math.cos(math.pi * c / t_max)) / (1.0 + math.cos(math.pi / t_max))
+
+
+def step_lr(epoch: int, lr_initial: float = 1e-4, step: int = 50, gamma: float = 0.5) -> float:
+    """Learning rate during epoch ``epoch`` (1-based) without ``--warmup``: ``StepLR(step_size=50, gamma=0.5)`` stepped once before
+    the first epoch (``train.py.bak:111-115``)."""
+    return lr_initial * gamma ** (epoch // step)
+
+
+def drop_path_rates(depths=(2, 2, 2, 2, 2, 2, 2, 2, 2), drop_path_rate: float = 0.1) -> dict:
+    """Per-layer stochastic-depth rates as ``models/fba_net.py:96-100`` hands them to the blocks of BOTH hourglasses:
+    ``enc = linspace(0, rate, sum(depths[:4]))``, bottleneck ``[rate] * depths[4]``, ``dec = enc[::-1]``; encoder 0 takes
+    ``enc[:d0]``, encoder 1 ``enc[d0:d0+d1]``, decoder 0 ``dec[:d5]``, decoder 1 ``dec[d5:d5+d6]`` (``:130-229``)."""
+    n = sum(depths[: len(depths) // 2])
+    enc = [drop_path_rate * i / (n - 1) for i in range(n)] if n > 1 else [0.0]
+    dec = enc[::-1]
+    d0, d1, d4, d5, d6 = depths[0], depths[1], depths[4], depths[5], depths[6]
+    return {"encoderlayer_0": enc[:d0], "encoderlayer_1": enc[d0:d0 + d1], "conv": [drop_path_rate] * d4,
+            "decoderlayer_0": dec[:d5], "decoderlayer_1": dec[d5:d5 + d6]}

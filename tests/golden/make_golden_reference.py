@@ -56,3 +56,32 @@ total.backward()
 np.savez_compressed(os.path.join(HERE, "loss_reference.npz"), x=lx.detach().numpy(), y=ly.numpy(), charbonnier=lc.item(), gw=lg.item(),
                     total=total.item(), grad=lx.grad.numpy())
 print("reference loss fixtures:", lc.item(), lg.item(), total.item())
+
+# ---- learning-rate schedules of the training configuration (8f-3): the reference's own `warmup_scheduler/scheduler.py` (torch-only)
+# driven exactly as train.py.bak:104-115,220 drives it -- one step before the first epoch, one after every epoch -- recording the
+# optimizer's learning rate in effect DURING each epoch
+import warnings
+
+spec = importlib.util.spec_from_file_location("ref_scheduler", "/root/reference/fba_net/warmup_scheduler/scheduler.py")
+ref_sched = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(ref_sched)
+sched_out = {}
+for tag, nepoch, warm, lr0 in (("warmup_default", 250, 3, 1e-4), ("warmup_short", 20, 5, 2e-4), ("steplr", 250, 0, 1e-4)):
+    opt_ = torch.optim.AdamW([torch.nn.Parameter(torch.zeros(1))], lr=lr0, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.02)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if warm:
+            cosine = torch.optim.lr_scheduler.CosineAnnealingLR(opt_, nepoch - warm, eta_min=1e-6)
+            sched = ref_sched.GradualWarmupScheduler(opt_, multiplier=1, total_epoch=warm, after_scheduler=cosine)
+        else:
+            sched = torch.optim.lr_scheduler.StepLR(opt_, step_size=50, gamma=0.5)
+        sched.step()
+        lrs = []
+        for epoch in range(1, nepoch + 1):
+            lrs.append(opt_.param_groups[0]["lr"])
+            opt_.step()
+            sched.step()
+    sched_out[tag] = np.array(lrs, dtype=np.float64)
+    sched_out[tag + "_cfg"] = np.array([nepoch, warm, lr0], dtype=np.float64)
+np.savez_compressed(os.path.join(HERE, "lr_schedule_reference.npz"), **sched_out)
+print("reference lr schedules:", {k: (v[:6].round(8).tolist(), v[-1]) for k, v in sched_out.items() if not k.endswith("_cfg")})

@@ -155,3 +155,38 @@ def test_reference_checkpoint_helpers_accept_our_model(tmp_path):
     assert ref.is_frozen(d) and ours.is_frozen(d)
     ours.unfreeze(d)
     assert not ref.is_frozen(d)
+
+
+def test_lr_schedules_match_the_reference_scheduler():
+    """`train.warmup_cosine_lr` / `step_lr` against the reference's own `GradualWarmupScheduler` + torch schedulers executed over whole
+    runs as train.py.bak:104-115,220 drives them (tests/golden/make_golden_reference.py -> lr_schedule_reference.npz)."""
+    import os
+
+    import numpy as np
+    from fbanet_b200.train import step_lr, warmup_cosine_lr
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "lr_schedule_reference.npz"))
+    for tag in ("warmup_default", "warmup_short"):
+        nepoch, warm, lr0 = int(z[tag + "_cfg"][0]), int(z[tag + "_cfg"][1]), float(z[tag + "_cfg"][2])
+        mine = np.array([warmup_cosine_lr(e, lr0, nepoch, warm) for e in range(1, nepoch + 1)])
+        np.testing.assert_allclose(mine, z[tag], rtol=1e-9, atol=0)
+        assert mine[warm] > lr0 and abs(mine[warm + 1] - lr0) < 1e-12 * lr0  # the hand-over overshoot, then exactly lr
+    mine = np.array([step_lr(e) for e in range(1, 251)])
+    np.testing.assert_allclose(mine, z["steplr"], rtol=1e-12, atol=0)
+
+
+def test_drop_path_rates_match_the_reference_constructor():
+    """`train.drop_path_rates` against the rates the reference's own constructor handed to its layers (model_structure_reference.json)."""
+    import json
+    import os
+
+    from fbanet_b200.train import drop_path_rates
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "model_structure_reference.json")) as f:
+        mods = json.load(f)["cfg2_rgb160"]["modules"]
+    rates = drop_path_rates()
+    for hg in ("HG1", "HG2"):
+        for mine, name in (("encoderlayer_0", f"{hg}_encoderlayer_0"), ("encoderlayer_1", f"{hg}_encoderlayer_1"), ("conv", f"conv_{hg}"),
+                           ("decoderlayer_0", f"{hg}_decoderlayer_0"), ("decoderlayer_1", f"{hg}_decoderlayer_1")):
+            want = [layer["drop_path_rate"] for layer in mods[name]["layers"]]
+            assert len(want) == len(rates[mine]) and all(abs(a - b) < 1e-6 for a, b in zip(rates[mine], want)), (name, rates[mine], want)
