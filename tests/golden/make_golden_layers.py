@@ -221,6 +221,13 @@ lp.to_kv.weight, lp.to_kv.bias = jnp.asarray(det_array((2 * dim2, dim2), 3102, -
 q, k, v = lp(jnp.asarray(det_array((100, dim2), 3104, -1.0, 1.0)))
 put("qkv_gpu", q=q, k=k, v=v, dim=dim2, heads=heads2, seed0=3100)
 
+# ---- PixelShuffleLayer (layers/pixel_shuffle.py:9-10): its pattern drops the channel axis, so it only runs on exactly 4 channels
+# (SURVEY A-18) -- enough to pin which of the 4 sub-pixels lands where
+from fba_net.layers.pixel_shuffle import PixelShuffleLayer  # noqa: E402
+
+x = rand(3, 5, 4)
+put("pixel_shuffle", x=x, y=PixelShuffleLayer(2)(x))
+
 np.savez_compressed(os.path.join(HERE, "layers_reference.npz"), **{k: np.asarray(v, dtype=np.float32) if np.asarray(v).dtype.kind == "f" else np.asarray(v)
                                                                   for k, v in out.items()})
 print("reference layer fixtures:", len(out), "arrays,", sum(np.asarray(v).size for v in out.values()), "values")

@@ -382,3 +382,11 @@ def test_reference_layers_attention_and_qkv_gpu_size(ref):
         got = lp(x[None])
     for g, r in zip(got, (q, k, v)):
         np.testing.assert_allclose(g[0].numpy(), r, rtol=1e-4, atol=1e-5)
+
+
+def test_reference_layers_pixel_shuffle_order(ref):
+    """A-18: the reference's `"h w (h2 w2) -> (h h2) (w w2)"` on its one executable case (4 channels -> 1) is torch's PixelShuffle(2)
+    order, in-channel `2 i + j` -> out `(2 y + i, 2 x + j)`, which the oracle's tail (and the CUDA tail's folded row permutation) use."""
+    x = ref["pixel_shuffle/x"]  # [h, w, 4]
+    y = torch.nn.PixelShuffle(2)(to_chw(x))  # [1, 1, 2h, 2w]
+    assert np.array_equal(y[0, 0].numpy(), ref["pixel_shuffle/y"])
