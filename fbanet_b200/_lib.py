@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBANET_B200_LIB") or os.path.join(_HERE, "csrc", "libfbanet_b200.so")   # env override: A/B two builds in one process tree
-ABI_VERSION = 18
+ABI_VERSION = 19
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -184,13 +184,38 @@ class AdamParams(C.Structure):
     ]
 
 
+class WgradParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("dy", C.c_void_p), ("dw", C.c_void_p), ("db", C.c_void_p), ("partial", C.c_void_p),
+        ("x_img_stride", C.c_int64), ("dy_img_stride", C.c_int64), ("x_ld", C.c_int32), ("dy_ld", C.c_int32),
+        ("dtype", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32),
+        ("Cout", C.c_int32), ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("splits", C.c_int32),
+        ("accumulate", C.c_int32),
+    ]
+
+
+class LayerNormBwdParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("dy", C.c_void_p), ("gamma", C.c_void_p), ("dx", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+        ("partial", C.c_void_p), ("rows", C.c_int64), ("eps", C.c_float), ("dtype", C.c_int32), ("C", C.c_int32), ("accumulate", C.c_int32),
+    ]
+
+
+class ActBwdParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("dy", C.c_void_p), ("dx", C.c_void_p), ("alpha", C.c_void_p), ("dalpha", C.c_void_p), ("partial", C.c_void_p),
+        ("n", C.c_int64), ("dtype", C.c_int32), ("act", C.c_int32), ("accumulate", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
 STRUCTS = {
     "fbanet_src": Src, "fbanet_conv_params": ConvParams, "fbanet_warp_params": WarpParams,
     "fbanet_to_nhwc_params": ToNhwcParams, "fbanet_s2d_params": S2dParams, "fbanet_head_conv_params": HeadConvParams, "fbanet_assemble_params": AssembleParams, "fbanet_layernorm_params": LayerNormParams, "fbanet_attn_params": AttnParams,
     "fbanet_dwconv_params": DwconvParams, "fbanet_faf_gate_params": FafGateParams, "fbanet_leff_fc2_params": LeffFc2Params, "fbanet_tile_params": TileParams,
     "fbanet_tile_band_params": TileBandParams, "fbanet_flow_warp_params": FlowWarpParams,
     "fbanet_ecc_prepare_params": EccPrepareParams, "fbanet_ecc_params": EccParams, "fbanet_train_loss_params": TrainLossParams,
-    "fbanet_adam_params": AdamParams,
+    "fbanet_adam_params": AdamParams, "fbanet_wgrad_params": WgradParams, "fbanet_layernorm_bwd_params": LayerNormBwdParams,
+    "fbanet_act_bwd_params": ActBwdParams,
 }
 
 # every symbol include/fbanet_b200.h declares
@@ -200,10 +225,11 @@ OPS = {
     "fbanet_faf_gate_sm100": FafGateParams, "fbanet_leff_fc2_sm100": LeffFc2Params, "fbanet_tile_divide_sm100": TileParams, "fbanet_tile_merge_sm100": TileParams,
     "fbanet_tile_divide_banded_sm100": TileBandParams, "fbanet_tile_merge_banded_sm100": TileBandParams, "fbanet_flow_warp_sm100": FlowWarpParams,
     "fbanet_ecc_prepare_sm100": EccPrepareParams, "fbanet_ecc_homography_sm100": EccParams, "fbanet_train_loss_sm100": TrainLossParams,
-    "fbanet_adam_step_sm100": AdamParams,
+    "fbanet_adam_step_sm100": AdamParams, "fbanet_wgrad_sm100": WgradParams, "fbanet_layernorm_bwd_sm100": LayerNormBwdParams,
+    "fbanet_act_bwd_sm100": ActBwdParams,
 }
 MISC_SYMBOLS = ["fbanet_abi_version", "fbanet_abi_sizeof", "fbanet_last_cuda_error", "fbanet_conv_gemm_tcgen05_supported", "fbanet_leff_fc2_supported",
-                "fbanet_train_loss_workspace_doubles"]
+                "fbanet_train_loss_workspace_doubles", "fbanet_layernorm_bwd_blocks", "fbanet_act_bwd_blocks"]
 
 _lib = None
 
@@ -229,6 +255,9 @@ def load() -> C.CDLL:
     lib.fbanet_leff_fc2_supported.argtypes = [C.POINTER(LeffFc2Params)]
     lib.fbanet_train_loss_workspace_doubles.restype = C.c_int64
     lib.fbanet_train_loss_workspace_doubles.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    for fn in (lib.fbanet_layernorm_bwd_blocks, lib.fbanet_act_bwd_blocks):
+        fn.restype = C.c_int32
+        fn.argtypes = [C.c_int64]
     if lib.fbanet_abi_version() != ABI_VERSION:
         raise RuntimeError(f"fbanet_b200: ABI mismatch (library {lib.fbanet_abi_version()}, binding {ABI_VERSION}); rebuild")
     for name, st in STRUCTS.items():

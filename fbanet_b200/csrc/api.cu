@@ -59,6 +59,9 @@ extern "C" int fbanet_abi_sizeof(const char* n) {
   SZ(fbanet_ecc_params);
   SZ(fbanet_train_loss_params);
   SZ(fbanet_adam_params);
+  SZ(fbanet_wgrad_params);
+  SZ(fbanet_layernorm_bwd_params);
+  SZ(fbanet_act_bwd_params);
 #undef SZ
   return -1;
 }

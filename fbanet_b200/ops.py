@@ -575,6 +575,81 @@ def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, ex
     _call("fbanet_adam_step_sm100", p, nbytes=param.numel() * 28)
 
 
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, kh: int = 1, kw: int = 1, stride: int = 1, pad: int = 0, need_bias: bool = True,
+               dw: Optional[torch.Tensor] = None, db: Optional[torch.Tensor] = None, accumulate: bool = False, splits: Optional[int] = None):
+    """Weight and bias gradient of ``y = conv(x, w) + b`` (or of a linear layer: ``kh = kw = 1``): ``x`` ``[N,H,W,Cin]``, ``dy``
+    ``[N,Ho,Wo,Cout]`` channels-last views of one dtype -> ``(dw [Cout,Cin,kh,kw] fp32, db [Cout] fp32 or None)`` in the torch
+    parameter layouts (so they can be views into ``train.FlatParams.grad``).  Fixed-order split reduction: bit-reproducible."""
+    assert x.is_cuda and dy.is_cuda and x.dtype == dy.dtype
+    N, H, W, Cin = x.shape
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    assert dy.shape[:3] == (N, Ho, Wo), (dy.shape, (N, Ho, Wo))
+    Cout = dy.shape[3]
+    xp, _, xld, xis = _cl(x)
+    dp, _, dld, dis = _cl(dy)
+    if dw is None:
+        dw = torch.empty((Cout, Cin, kh, kw), device=x.device, dtype=torch.float32)
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == Cout * Cin * kh * kw
+    if need_bias and db is None:
+        db = torch.empty(Cout, device=x.device, dtype=torch.float32)
+    if db is not None:
+        assert db.dtype == torch.float32 and db.is_contiguous() and db.numel() == Cout
+    P = N * Ho * Wo
+    if splits is None:   # enough CTAs for two waves of the 148 SMs, at least 256 pixels per chunk
+        tiles = ((Cout + 63) // 64) * kh * kw * ((Cin + 63) // 64)
+        splits = max(1, min((2 * 148 + tiles - 1) // tiles, (P + 255) // 256, 1024))
+    partial = torch.empty(splits * (Cout * kh * kw * Cin + Cout), device=x.device, dtype=torch.float32)
+    p = L.WgradParams()
+    p.x, p.dy, p.dw, p.partial = xp, dp, dw.data_ptr(), partial.data_ptr()
+    p.db = db.data_ptr() if db is not None else None
+    p.x_img_stride, p.dy_img_stride, p.x_ld, p.dy_ld = xis, dis, xld, dld
+    p.dtype, p.N, p.H, p.W, p.Cin, p.Ho, p.Wo, p.Cout = _DT[x.dtype], N, H, W, Cin, Ho, Wo, Cout
+    p.KH, p.KW, p.stride, p.pad, p.splits, p.accumulate = kh, kw, stride, pad, splits, 1 if accumulate else 0
+    esz = x.element_size()
+    _call("fbanet_wgrad_sm100", p, tag=f"wgrad k{kh}s{stride} {Cin}->{Cout} @{Ho}x{Wo}", nbytes=(kh * kw * x.numel() + dy.numel()) * esz)
+    return dw, db
+
+
+def layernorm_backward(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float = 1e-5, dgamma: Optional[torch.Tensor] = None,
+                       dbeta: Optional[torch.Tensor] = None, accumulate: bool = False):
+    """Backward of the per-token LayerNorm (``layers/fba_net.py:196,246``): ``x``, ``dy`` ``[rows, C]`` contiguous, ``C <= 256`` ->
+    ``(dx [rows, C] in x's dtype, dgamma [C] fp32, dbeta [C] fp32)``."""
+    assert x.is_cuda and x.dim() == 2 and x.is_contiguous() and dy.shape == x.shape and dy.dtype == x.dtype and dy.is_contiguous()
+    rows, Cc = x.shape
+    assert gamma.dtype == torch.float32 and gamma.is_contiguous() and gamma.numel() == Cc and Cc <= 256
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(Cc, device=x.device, dtype=torch.float32) if dgamma is None else dgamma
+    dbeta = torch.empty(Cc, device=x.device, dtype=torch.float32) if dbeta is None else dbeta
+    for t in (dgamma, dbeta):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == Cc
+    blocks = L.load().fbanet_layernorm_bwd_blocks(rows)
+    partial = torch.empty(blocks * 2 * Cc, device=x.device, dtype=torch.float32)
+    p = L.LayerNormBwdParams()
+    p.x, p.dy, p.gamma, p.dx = x.data_ptr(), dy.data_ptr(), gamma.data_ptr(), dx.data_ptr()
+    p.dgamma, p.dbeta, p.partial = dgamma.data_ptr(), dbeta.data_ptr(), partial.data_ptr()
+    p.rows, p.eps, p.dtype, p.C, p.accumulate = rows, float(eps), _DT[x.dtype], Cc, 1 if accumulate else 0
+    _call("fbanet_layernorm_bwd_sm100", p, nbytes=3 * x.numel() * x.element_size())
+    return dx, dgamma, dbeta
+
+
+def act_backward(x: torch.Tensor, dy: torch.Tensor, act: int, alpha: Optional[torch.Tensor] = None, dalpha: Optional[torch.Tensor] = None,
+                 accumulate: bool = False):
+    """``dx = dy * act'(x)`` for the PRE-activation ``x`` (``act``: ``L.ACT_RELU / ACT_PRELU / ACT_GELU_TANH / ACT_GELU_ERF``); for PReLU
+    also the gradient of the scalar slope.  Returns ``dx`` (``(dx, dalpha)`` for PReLU)."""
+    assert x.is_cuda and x.is_contiguous() and dy.is_contiguous() and dy.shape == x.shape and dy.dtype == x.dtype
+    dx = torch.empty_like(x)
+    p = L.ActBwdParams()
+    p.x, p.dy, p.dx, p.n, p.dtype, p.act, p.accumulate = x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(), _DT[x.dtype], act, 1 if accumulate else 0
+    if act == L.ACT_PRELU:
+        assert alpha is not None and alpha.dtype == torch.float32 and alpha.numel() == 1
+        dalpha = torch.empty(1, device=x.device, dtype=torch.float32) if dalpha is None else dalpha
+        assert dalpha.dtype == torch.float32 and dalpha.numel() == 1
+        partial = torch.empty(L.load().fbanet_act_bwd_blocks(x.numel()), device=x.device, dtype=torch.float32)
+        p.alpha, p.dalpha, p.partial = alpha.data_ptr(), dalpha.data_ptr(), partial.data_ptr()
+    _call("fbanet_act_bwd_sm100", p, nbytes=3 * x.numel() * x.element_size())
+    return (dx, dalpha) if act == L.ACT_PRELU else dx
+
+
 def _band_params(bands, row0, tiles, T, Cc, H, W, psize, overlap, tile_begin, tile_end, scale):
     assert 1 <= len(bands) <= L.MAX_BANDS and len(row0) == len(bands) + 1 and row0[0] == 0 and row0[-1] == H
     p = L.TileBandParams()

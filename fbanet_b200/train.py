@@ -67,6 +67,18 @@ class FlatParams:
         return {"step": self.step, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
 
 
+def dgrad_weight(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Packed weight that turns the FORWARD implicit GEMM into the data gradient of a stride-1 convolution / linear layer:
+    for ``y = conv(x, w)`` with ``w [Co,Ci,kh,kw]``, stride 1 and padding ``pad``, ``dx = conv(dy, w')`` with ``w'[ci][ky][kx][co] =
+    w[co][ci][kh-1-ky][kw-1-kx]`` and padding ``k - 1 - pad`` -- i.e. ``ops.conv_gemm([dy], dgrad_weight(w, dt), dx, kh=kh, kw=kw,
+    pad=kh-1-pad)``; a linear layer ``[out, in]`` is the ``kh = kw = 1`` case (``dx = dy @ w``).  Returned in ``conv_gemm``'s packed
+    layout ``[Ci, kh*kw*Co]`` (K index ``(ky*kw + kx)*Co + co``), so in bf16 the data gradients run on the tcgen05 kernel."""
+    w = weight.detach()
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    return w.flip(2, 3).permute(1, 2, 3, 0).reshape(w.shape[1], -1).to(dtype).contiguous()
+
+
 # ------------------------------------------------------------------------------------------------------------------------------
 # learning-rate schedules and stochastic-depth rates of the training configuration (host arithmetic, no tensors)
 # ------------------------------------------------------------------------------------------------------------------------------

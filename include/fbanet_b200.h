@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 18
+#define FBANET_ABI_VERSION 19
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -375,6 +375,59 @@ typedef struct fbanet_adam_params {
   int32_t decoupled, _pad;
 } fbanet_adam_params;
 
+/* Backward bricks of the training step (what torch autograd did for train.py.bak:163-169, what
+ * eqx.filter_value_and_grad does at train.py:63).  The DATA gradient of every stride-1 convolution / linear layer is the forward
+ * implicit GEMM itself (fbanet_conv_gemm_sm100) run on dY with the spatially flipped, in/out-transposed weights; these three ops are
+ * the rest that the convolutional / token-wise layers need.
+ *
+ * Weight + bias gradient of a convolution or linear layer (layers/conv2d.py:33-43, eqx.nn.Linear call sites):
+ *   dw[co][ci][ky][kx] (+)= sum_{n,yo,xo} dy(n,yo,xo,co) * x(n, yo*stride + ky - pad, xo*stride + kx - pad, ci)   (zero outside)
+ *   db[co]             (+)= sum_{n,yo,xo} dy(n,yo,xo,co)
+ * x, dy: channels-last views (see the conventions above) of `dtype`; dw, db: fp32 in the torch parameter layouts.  The pixel axis is
+ * cut into `splits` contiguous chunks whose partial sums go to `partial` (splits * (Cout*KH*KW*Cin + Cout) floats) and are added in
+ * a fixed order: bit-reproducible.  accumulate = 1 adds to dw / db instead of overwriting them. */
+typedef struct fbanet_wgrad_params {
+  const void* x;
+  const void* dy;
+  float* dw;
+  float* db;              /* optional */
+  float* partial;
+  int64_t x_img_stride, dy_img_stride;
+  int32_t x_ld, dy_ld;
+  int32_t dtype, N, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad, splits, accumulate;
+} fbanet_wgrad_params;
+
+/* LayerNorm backward (eqx.nn.LayerNorm at layers/fba_net.py:77-78, applied per token at :196,246): rows x C, contiguous rows.
+ *   xhat = (x - mean) * rstd,  g = dy * gamma,  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),
+ *   dgamma[c] (+)= sum_rows dy * xhat,  dbeta[c] (+)= sum_rows dy.       C <= 256.
+ * partial: fbanet_layernorm_bwd_blocks(rows) * 2 * C floats; fixed-order reduction. */
+typedef struct fbanet_layernorm_bwd_params {
+  const void* x;
+  const void* dy;
+  const float* gamma;
+  void* dx;
+  float* dgamma;
+  float* dbeta;
+  float* partial;
+  int64_t rows;
+  float eps;
+  int32_t dtype, C, accumulate;
+} fbanet_layernorm_bwd_params;
+
+/* Activation backward: dx = dy * act'(x) on n contiguous elements, x = the PRE-activation.  act: FBANET_ACT_RELU / PRELU /
+ * GELU_TANH / GELU_ERF.  PReLU (eqx.nn.PReLU, scalar slope): alpha = device scalar, dalpha (+)= sum dy * x over x < 0 (optional;
+ * partial: fbanet_act_bwd_blocks(n) floats). */
+typedef struct fbanet_act_bwd_params {
+  const void* x;
+  const void* dy;
+  void* dx;
+  const float* alpha;
+  float* dalpha;
+  float* partial;
+  int64_t n;
+  int32_t dtype, act, accumulate, _pad;
+} fbanet_act_bwd_params;
+
 int fbanet_abi_version(void);
 /* sizeof() of the named parameter struct as compiled, for binding self-checks; -1 if unknown */
 int fbanet_abi_sizeof(const char* struct_name);
@@ -405,6 +458,12 @@ int fbanet_ecc_prepare_sm100(const fbanet_ecc_prepare_params* p, void* stream);
 int fbanet_ecc_homography_sm100(const fbanet_ecc_params* p, void* stream);
 int fbanet_train_loss_sm100(const fbanet_train_loss_params* p, void* stream);
 int fbanet_adam_step_sm100(const fbanet_adam_params* p, void* stream);
+int fbanet_wgrad_sm100(const fbanet_wgrad_params* p, void* stream);
+int fbanet_layernorm_bwd_sm100(const fbanet_layernorm_bwd_params* p, void* stream);
+int fbanet_act_bwd_sm100(const fbanet_act_bwd_params* p, void* stream);
+/* thread blocks (= partial rows) the two reductions above use for a problem of this size */
+int fbanet_layernorm_bwd_blocks(int64_t rows);
+int fbanet_act_bwd_blocks(int64_t n);
 /* doubles of workspace fbanet_train_loss_sm100 needs (2 per thread block) */
 int64_t fbanet_train_loss_workspace_doubles(int32_t planes, int32_t H, int32_t W);
 

@@ -46,6 +46,19 @@ def test_bad_params_are_rejected_without_a_gpu(lib):
     assert lib.fbanet_tile_divide_banded_sm100(ctypes.byref(b), None) == -1
     b.row0[2], b.row0[1] = 50, 0                          # empty band
     assert lib.fbanet_tile_divide_banded_sm100(ctypes.byref(b), None) == -1
+    # backward bricks of the training step: empty requests, inconsistent output sizes, too-wide LayerNorm rows
+    for fn, st in (("fbanet_wgrad_sm100", _lib.WgradParams), ("fbanet_layernorm_bwd_sm100", _lib.LayerNormBwdParams),
+                   ("fbanet_act_bwd_sm100", _lib.ActBwdParams)):
+        assert getattr(lib, fn)(ctypes.byref(st()), None) == -1, fn
+    g = _lib.WgradParams()
+    g.x, g.dy, g.dw, g.partial = 1, 1, 1, 1
+    g.N, g.H, g.W, g.Cin, g.Cout, g.KH, g.KW, g.stride, g.pad, g.splits, g.x_ld, g.dy_ld = 1, 8, 8, 4, 4, 3, 3, 1, 1, 1, 4, 4
+    g.Ho, g.Wo = 8, 7                                     # Wo must be (W + 2 pad - KW) / stride + 1
+    assert lib.fbanet_wgrad_sm100(ctypes.byref(g), None) == -1
+    n = _lib.LayerNormBwdParams()
+    n.x, n.dy, n.gamma, n.dx, n.partial, n.rows, n.C, n.eps = 1, 1, 1, 1, 1, 4, 512, 1e-5   # C > 256
+    assert lib.fbanet_layernorm_bwd_sm100(ctypes.byref(n), None) == -1
+    assert lib.fbanet_layernorm_bwd_blocks(0) == -1 and lib.fbanet_act_bwd_blocks(0) == -1
     e = _lib.EccParams()
     e.planes, e.warp, e.frames, e.frames_per_burst, e.H, e.W, e.max_iters = 1, 1, 7, 2, 16, 16, 10   # 7 frames are not whole bursts of 2
     assert lib.fbanet_ecc_homography_sm100(ctypes.byref(e), None) == -1
