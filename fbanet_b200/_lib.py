@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBANET_B200_LIB") or os.path.join(_HERE, "csrc", "libfbanet_b200.so")   # env override: A/B two builds in one process tree
-ABI_VERSION = 19
+ABI_VERSION = 20
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -208,6 +208,39 @@ class ActBwdParams(C.Structure):
     ]
 
 
+class DwconvBwdParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("dy", C.c_void_p), ("weight", C.c_void_p), ("dx", C.c_void_p), ("dw", C.c_void_p), ("db", C.c_void_p),
+        ("partial", C.c_void_p), ("dtype", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+        ("accumulate", C.c_int32),
+    ]
+
+
+class AttnBwdParams(C.Structure):
+    _fields_ = [
+        ("qkv", C.c_void_p), ("dout", C.c_void_p), ("dqkv", C.c_void_p), ("bias_table", C.c_void_p), ("dbias", C.c_void_p),
+        ("partial", C.c_void_p), ("dtype", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+        ("heads", C.c_int32), ("win", C.c_int32), ("shift", C.c_int32), ("qkv_ld", C.c_int32), ("dout_ld", C.c_int32),
+        ("dqkv_ld", C.c_int32), ("scale", C.c_float), ("accumulate", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
+class FafGateBwdParams(C.Structure):
+    _fields_ = [
+        ("feat", C.c_void_p), ("dgated", C.c_void_p), ("gate", C.c_void_p), ("score", C.c_void_p), ("wsum", C.c_void_p),
+        ("dfeat", C.c_void_p), ("dscore", C.c_void_p), ("dwsum", C.c_void_p), ("partial", C.c_void_p),
+        ("dtype", C.c_int32), ("B", C.c_int32), ("F", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+        ("accumulate", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
+class DropPathParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("skip", C.c_void_p), ("out", C.c_void_p), ("scale", C.c_void_p), ("per_burst", C.c_int64),
+        ("dtype", C.c_int32), ("B", C.c_int32),
+    ]
+
+
 STRUCTS = {
     "fbanet_src": Src, "fbanet_conv_params": ConvParams, "fbanet_warp_params": WarpParams,
     "fbanet_to_nhwc_params": ToNhwcParams, "fbanet_s2d_params": S2dParams, "fbanet_head_conv_params": HeadConvParams, "fbanet_assemble_params": AssembleParams, "fbanet_layernorm_params": LayerNormParams, "fbanet_attn_params": AttnParams,
@@ -215,7 +248,8 @@ STRUCTS = {
     "fbanet_tile_band_params": TileBandParams, "fbanet_flow_warp_params": FlowWarpParams,
     "fbanet_ecc_prepare_params": EccPrepareParams, "fbanet_ecc_params": EccParams, "fbanet_train_loss_params": TrainLossParams,
     "fbanet_adam_params": AdamParams, "fbanet_wgrad_params": WgradParams, "fbanet_layernorm_bwd_params": LayerNormBwdParams,
-    "fbanet_act_bwd_params": ActBwdParams,
+    "fbanet_act_bwd_params": ActBwdParams, "fbanet_dwconv_bwd_params": DwconvBwdParams, "fbanet_attn_bwd_params": AttnBwdParams,
+    "fbanet_faf_gate_bwd_params": FafGateBwdParams, "fbanet_drop_path_params": DropPathParams,
 }
 
 # every symbol include/fbanet_b200.h declares
@@ -226,10 +260,13 @@ OPS = {
     "fbanet_tile_divide_banded_sm100": TileBandParams, "fbanet_tile_merge_banded_sm100": TileBandParams, "fbanet_flow_warp_sm100": FlowWarpParams,
     "fbanet_ecc_prepare_sm100": EccPrepareParams, "fbanet_ecc_homography_sm100": EccParams, "fbanet_train_loss_sm100": TrainLossParams,
     "fbanet_adam_step_sm100": AdamParams, "fbanet_wgrad_sm100": WgradParams, "fbanet_layernorm_bwd_sm100": LayerNormBwdParams,
-    "fbanet_act_bwd_sm100": ActBwdParams,
+    "fbanet_act_bwd_sm100": ActBwdParams, "fbanet_dwconv3x3_bwd_sm100": DwconvBwdParams,
+    "fbanet_window_attention_bwd_sm100": AttnBwdParams, "fbanet_faf_gate_bwd_sm100": FafGateBwdParams,
+    "fbanet_drop_path_add_sm100": DropPathParams,
 }
 MISC_SYMBOLS = ["fbanet_abi_version", "fbanet_abi_sizeof", "fbanet_last_cuda_error", "fbanet_conv_gemm_tcgen05_supported", "fbanet_leff_fc2_supported",
-                "fbanet_train_loss_workspace_doubles", "fbanet_layernorm_bwd_blocks", "fbanet_act_bwd_blocks"]
+                "fbanet_train_loss_workspace_doubles", "fbanet_layernorm_bwd_blocks", "fbanet_act_bwd_blocks",
+                "fbanet_dwconv_bwd_blocks", "fbanet_faf_gate_bwd_blocks", "fbanet_attn_bwd_partial_floats"]
 
 _lib = None
 
@@ -255,9 +292,11 @@ def load() -> C.CDLL:
     lib.fbanet_leff_fc2_supported.argtypes = [C.POINTER(LeffFc2Params)]
     lib.fbanet_train_loss_workspace_doubles.restype = C.c_int64
     lib.fbanet_train_loss_workspace_doubles.argtypes = [C.c_int32, C.c_int32, C.c_int32]
-    for fn in (lib.fbanet_layernorm_bwd_blocks, lib.fbanet_act_bwd_blocks):
+    for fn in (lib.fbanet_layernorm_bwd_blocks, lib.fbanet_act_bwd_blocks, lib.fbanet_dwconv_bwd_blocks, lib.fbanet_faf_gate_bwd_blocks):
         fn.restype = C.c_int32
         fn.argtypes = [C.c_int64]
+    lib.fbanet_attn_bwd_partial_floats.restype = C.c_int64
+    lib.fbanet_attn_bwd_partial_floats.argtypes = [C.c_int32] * 5
     if lib.fbanet_abi_version() != ABI_VERSION:
         raise RuntimeError(f"fbanet_b200: ABI mismatch (library {lib.fbanet_abi_version()}, binding {ABI_VERSION}); rebuild")
     for name, st in STRUCTS.items():

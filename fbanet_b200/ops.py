@@ -650,6 +650,112 @@ def act_backward(x: torch.Tensor, dy: torch.Tensor, act: int, alpha: Optional[to
     return (dx, dalpha) if act == L.ACT_PRELU else dx
 
 
+def dwconv3x3_backward(x: torch.Tensor, dy: torch.Tensor, weight9c: torch.Tensor, need_dx: bool = True, dw: Optional[torch.Tensor] = None,
+                       db: Optional[torch.Tensor] = None, accumulate: bool = False):
+    """Backward of the LeFF depthwise 3x3 (``layers/locally_enhanced_feed_forward.py:39-52``): ``x``, ``dy`` channels-last
+    ``[N,H,W,C]``, ``weight9c`` the forward's packed fp32 ``[9,C]`` -> ``(dx [N,H,W,C] or None, dw [C,1,3,3] fp32, db [C] fp32)``
+    (torch parameter layouts, so ``dw`` / ``db`` may be views into ``FlatParams.grad``)."""
+    assert x.is_cuda and x.dim() == 4 and x.is_contiguous() and dy.shape == x.shape and dy.dtype == x.dtype and dy.is_contiguous()
+    N, H, W, Cc = x.shape
+    assert weight9c.dtype == torch.float32 and weight9c.is_contiguous() and weight9c.shape == (9, Cc)
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.empty((Cc, 1, 3, 3), device=x.device, dtype=torch.float32) if dw is None else dw
+    db = torch.empty(Cc, device=x.device, dtype=torch.float32) if db is None else db
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == 9 * Cc and db.dtype == torch.float32 and db.is_contiguous() and db.numel() == Cc
+    blocks = L.load().fbanet_dwconv_bwd_blocks(N * H * W)
+    partial = torch.empty(blocks * 10 * Cc, device=x.device, dtype=torch.float32)
+    p = L.DwconvBwdParams()
+    p.x, p.dy, p.weight, p.dw, p.db, p.partial = x.data_ptr(), dy.data_ptr(), weight9c.data_ptr(), dw.data_ptr(), db.data_ptr(), partial.data_ptr()
+    p.dx = dx.data_ptr() if dx is not None else None
+    p.dtype, p.N, p.H, p.W, p.C, p.accumulate = _DT[x.dtype], N, H, W, Cc, 1 if accumulate else 0
+    _call("fbanet_dwconv3x3_bwd_sm100", p, nbytes=(3 if need_dx else 2) * x.numel() * x.element_size())
+    return dx, dw, db
+
+
+def window_attention_backward(qkv: torch.Tensor, dout: torch.Tensor, bias_table: torch.Tensor, B: int, H: int, W: int, heads: int, win: int,
+                              shift: int, scale: float, need_dbias: bool = True, dbias: Optional[torch.Tensor] = None,
+                              accumulate: bool = False):
+    """Backward of :func:`window_attention` (``layers/window_attention.py:159-248``): ``qkv [B*H*W, 3C]`` (UNSCALED q, as the fp32
+    forward takes it), ``dout [B*H*W, C]`` -> ``(dqkv [B*H*W, 3C], dbias_table [(2win-1)^2, heads] fp32 or None)``."""
+    assert qkv.is_cuda and qkv.dim() == 2 and qkv.is_contiguous() and dout.is_cuda and dout.dim() == 2 and dout.is_contiguous()
+    T, C3 = qkv.shape
+    Cc = C3 // 3
+    assert T == B * H * W and C3 == 3 * Cc and dout.shape == (T, Cc) and dout.dtype == qkv.dtype
+    R = (2 * win - 1) ** 2
+    assert bias_table.dtype == torch.float32 and bias_table.is_contiguous() and bias_table.shape == (R, heads)
+    dqkv = torch.empty_like(qkv)
+    p = L.AttnBwdParams()
+    p.qkv, p.dout, p.dqkv, p.bias_table = qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), bias_table.data_ptr()
+    if need_dbias:
+        dbias = torch.empty((R, heads), device=qkv.device, dtype=torch.float32) if dbias is None else dbias
+        assert dbias.dtype == torch.float32 and dbias.is_contiguous() and dbias.numel() == R * heads
+        n = L.load().fbanet_attn_bwd_partial_floats(B, H, W, heads, win)
+        assert n > 0, "H, W must be multiples of win"
+        partial = torch.empty(n, device=qkv.device, dtype=torch.float32)
+        p.dbias, p.partial = dbias.data_ptr(), partial.data_ptr()
+    else:
+        dbias = None
+    p.dtype, p.B, p.H, p.W, p.C, p.heads, p.win, p.shift = _DT[qkv.dtype], B, H, W, Cc, heads, win, shift
+    p.qkv_ld, p.dout_ld, p.dqkv_ld, p.scale, p.accumulate = C3, Cc, C3, float(scale), 1 if accumulate else 0
+    _call("fbanet_window_attention_bwd_sm100", p, tag=f"attn bwd dh{Cc // heads}", nbytes=(2 * qkv.numel() + dout.numel()) * qkv.element_size())
+    return dqkv, dbias
+
+
+def faf_gate_backward(feat: torch.Tensor, dgated: torch.Tensor, gate: torch.Tensor, score: torch.Tensor, wsum: torch.Tensor,
+                      dwsum: Optional[torch.Tensor] = None, accumulate: bool = False):
+    """Backward of :func:`faf_gate` (``blocks/federated_affinity_fusion.py:79-105``): ``feat [B,F,H,W,C]``, ``dgated [B,H,W,F*C]``
+    (gradient of the gated, pixel-major features), ``gate [B,F-1,H,W]`` fp32 as the forward returned it, ``score`` fp32
+    ``[B*F,H,W]`` or the ``[B*F,H,W,2]`` hi / lo form of :func:`faf_scores` -> ``(dfeat [B,F,H,W,C], dwsum [9,C] fp32)``.
+    ``dwsum`` is the gradient of EVERY output channel of ``temporal_attn1.weight`` (``dW1[co, ci, ky, kx] = dwsum[ky*3+kx, ci]``);
+    ``temporal_attn0`` and both biases cancel out of the gate as the reference writes it and get zero (:func:`faf_weight_grads`)."""
+    assert feat.is_cuda and feat.dim() == 5 and feat.is_contiguous()
+    B, Fr, H, W, Cc = feat.shape
+    assert dgated.is_contiguous() and dgated.dtype == feat.dtype and dgated.numel() == feat.numel() and dgated.shape[:3] == (B, H, W)
+    assert gate.dtype == torch.float32 and gate.is_contiguous() and gate.shape == (B, Fr - 1, H, W)
+    assert wsum.dtype == torch.float32 and wsum.is_contiguous() and wsum.shape == (9, Cc)
+    assert score.dtype == torch.float32
+    if score.dim() == 4 and score.shape[-1] == 2:
+        score = score[..., 0] + score[..., 1]
+    score = score.reshape(B, Fr, H, W).contiguous()
+    dfeat = torch.empty_like(feat)
+    dscore = torch.empty((B, Fr, H, W), device=feat.device, dtype=torch.float32)
+    dwsum = torch.empty((9, Cc), device=feat.device, dtype=torch.float32) if dwsum is None else dwsum
+    assert dwsum.dtype == torch.float32 and dwsum.is_contiguous() and dwsum.numel() == 9 * Cc
+    blocks = L.load().fbanet_faf_gate_bwd_blocks(B * Fr * H * W)
+    partial = torch.empty(blocks * 9 * Cc, device=feat.device, dtype=torch.float32)
+    p = L.FafGateBwdParams()
+    p.feat, p.dgated, p.gate, p.score, p.wsum = feat.data_ptr(), dgated.data_ptr(), gate.data_ptr(), score.data_ptr(), wsum.data_ptr()
+    p.dfeat, p.dscore, p.dwsum, p.partial = dfeat.data_ptr(), dscore.data_ptr(), dwsum.data_ptr(), partial.data_ptr()
+    p.dtype, p.B, p.F, p.H, p.W, p.C, p.accumulate = _DT[feat.dtype], B, Fr, H, W, Cc, 1 if accumulate else 0
+    _call("fbanet_faf_gate_bwd_sm100", p, nbytes=4 * feat.numel() * feat.element_size())
+    return dfeat, dwsum
+
+
+def faf_weight_grads(dwsum: torch.Tensor, cout: int):
+    """Gradient of the two FAF embedding convolutions from the gate's ``dwsum [9,C]``: ``temporal_attn1.weight [cout,C,3,3]`` receives
+    ``dwsum`` in every output channel (``wsum`` is the sum over them); ``temporal_attn0.weight`` and both biases receive zero --
+    ``emb_ref`` and the biases cancel in ``aff[f] - aff[0]`` (``federated_affinity_fusion.py:84-99``)."""
+    Cc = dwsum.shape[1]
+    return dwsum.t().reshape(1, Cc, 3, 3).expand(cout, Cc, 3, 3)
+
+
+def drop_path_add(x: torch.Tensor, scale: torch.Tensor, skip: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out[b] = skip[b] + scale[b] * x[b]`` (``layers/drop_path.py:39-63`` "global" mode under ``jax.vmap``: one draw per burst;
+    the residuals of ``layers/fba_net.py:245,248``); ``skip=None``: the branch's backward ``dx[b] = scale[b] * dy[b]``.
+    ``scale``: fp32 ``[B]`` from :func:`fbanet_b200.train.drop_path_scales`."""
+    assert x.is_cuda and x.is_contiguous() and scale.dtype == torch.float32 and scale.is_contiguous() and scale.numel() == x.shape[0]
+    if skip is not None:
+        assert skip.shape == x.shape and skip.dtype == x.dtype and skip.is_contiguous()
+    out = torch.empty_like(x) if out is None else out
+    assert out.shape == x.shape and out.dtype == x.dtype and out.is_contiguous()
+    p = L.DropPathParams()
+    p.x, p.out, p.scale = x.data_ptr(), out.data_ptr(), scale.data_ptr()
+    p.skip = skip.data_ptr() if skip is not None else None
+    p.per_burst, p.dtype, p.B = x.numel() // x.shape[0], _DT[x.dtype], x.shape[0]
+    _call("fbanet_drop_path_add_sm100", p, nbytes=(3 if skip is not None else 2) * x.numel() * x.element_size())
+    return out
+
+
 def _band_params(bands, row0, tiles, T, Cc, H, W, psize, overlap, tile_begin, tile_end, scale):
     assert 1 <= len(bands) <= L.MAX_BANDS and len(row0) == len(bands) + 1 and row0[0] == 0 and row0[-1] == H
     p = L.TileBandParams()

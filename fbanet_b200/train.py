@@ -1,4 +1,4 @@
-"""Training-step plumbing that does not depend on the (not yet built) backward kernels -- SURVEY 8f-3, BASELINE config 5:
+"""Training-step plumbing around the backward bricks -- SURVEY 8f-3, BASELINE config 5:
 flat parameter / gradient / moment buffers, the data-parallel gradient all-reduce (the ONE collective of the whole system:
 ``ncclAllReduce(sum)`` over the 19.2 M gradients, reference ``train.py.bak:83-84`` ``DataParallel`` / north-star "NCCL allreduce appears only
 in the training-step config"), the fused Adam / AdamW step (``train.py.bak:72-78``) and the loss (``:118-119,168``).
@@ -115,3 +115,19 @@ def drop_path_rates(depths=(2, 2, 2, 2, 2, 2, 2, 2, 2), drop_path_rate: float = 
     d0, d1, d4, d5, d6 = depths[0], depths[1], depths[4], depths[5], depths[6]
     return {"encoderlayer_0": enc[:d0], "encoderlayer_1": enc[d0:d0 + d1], "conv": [drop_path_rate] * d4,
             "decoderlayer_0": dec[:d5], "decoderlayer_1": dec[d5:d5 + d6]}
+
+
+def drop_path_scales(batch: int, rate: float, generator: Optional[torch.Generator] = None, device=None) -> torch.Tensor:
+    """Per-burst multipliers of one ``DropPath`` call (``layers/drop_path.py:52-63``, "global" mode mapped over the batch by
+    ``jax.vmap``): ``bernoulli(keep) / keep`` with ``keep = 1 - rate``; all ones for ``rate == 0`` (the layer returns ``x`` itself),
+    all zeros for ``rate == 1`` (the reference skips the division when ``keep == 0``).  fp32 ``[batch]`` for
+    ``ops.drop_path_add``; drawn on the host generator so that every data-parallel rank can reproduce its own stream."""
+    assert 0.0 <= rate <= 1.0
+    keep = 1.0 - rate
+    if rate == 0.0:
+        s = torch.ones(batch, dtype=torch.float32)
+    else:
+        s = torch.bernoulli(torch.full((batch,), keep, dtype=torch.float32), generator=generator)
+        if keep > 0.0:
+            s = s / keep
+    return s.to(device) if device is not None else s

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 19
+#define FBANET_ABI_VERSION 20
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -428,6 +428,79 @@ typedef struct fbanet_act_bwd_params {
   int32_t dtype, act, accumulate, _pad;
 } fbanet_act_bwd_params;
 
+/* ---- SURVEY 8f-3, second set of backward bricks: the layers whose gradient is not a dense GEMM ---- */
+
+/* Backward of the LeFF depthwise 3x3 (layers/locally_enhanced_feed_forward.py:39-52; forward: fbanet_dwconv3x3_sm100 with act NONE,
+ * the GELU after it goes through fbanet_act_bwd_sm100).  x, dy, dx: contiguous channels-last [N,H,W,C] of `dtype`; weight: the
+ * forward's packed fp32 [9][C].
+ *   dx(q,c) = sum_tap w[tap][c] dy(q - (tap - 1), c),  dw[c][tap] (+)= sum_q dy(q,c) x(q + tap - 1, c),  db[c] (+)= sum_q dy(q,c)
+ * dw, db: fp32 in the torch parameter layouts [C,1,3,3] / [C]; any of dx, dw, db may be NULL (not all three).
+ * partial: fbanet_dwconv_bwd_blocks(N*H*W) * 10 * C floats; fixed-order reduction. */
+typedef struct fbanet_dwconv_bwd_params {
+  const void* x;
+  const void* dy;
+  const float* weight;
+  void* dx;
+  float* dw;
+  float* db;
+  float* partial;
+  int32_t dtype, N, H, W, C, accumulate;
+} fbanet_dwconv_bwd_params;
+
+/* Backward of the windowed attention core (layers/window_attention.py:159-248 with the cyclic shift / window partition / shift mask
+ * of layers/fba_net.py:149-238; forward: fbanet_window_attention_sm100, same token layout and the same `scale`).
+ *   P = softmax(scale q k^T + bias + mask),  dv = P^T dO,  dP = dO v^T,  dS = P o (dP - rowsum(P o dP)),
+ *   dq = scale dS k,  dk = dS^T (scale q),  dbias_table[index(i,j)][h] (+)= sum over windows of dS_ij
+ * qkv, dqkv: [B*H*W, 3C] (q | k | v); dout: [B*H*W, C]; every element of dqkv is written.  dbias: optional fp32
+ * [(2*win-1)^2][heads]; partial: fbanet_attn_bwd_partial_floats(...) floats (needed with dbias); fixed-order reduction. */
+typedef struct fbanet_attn_bwd_params {
+  const void* qkv;
+  const void* dout;
+  void* dqkv;
+  const float* bias_table;
+  float* dbias;
+  float* partial;
+  int32_t dtype, B, H, W, C, heads, win, shift;
+  int32_t qkv_ld, dout_ld, dqkv_ld;
+  float scale;
+  int32_t accumulate, _pad;
+} fbanet_attn_bwd_params;
+
+/* Backward of the Federated-Affinity gate (blocks/federated_affinity_fusion.py:79-105; forward: fbanet_faf_gate_sm100).
+ * With s_f(p) = sum_{tap,c} wsum[tap][c] feat_f(p + tap - 1, c) and g_f = sigmoid(|s_f - s_0|):
+ *   ds_f = sign(s_f - s_0) g_f (1 - g_f) sum_c dgated_f feat_f  (f >= 1),  ds_0 = -sum_f ds_f,
+ *   dfeat_f(q,c) = dgated_f(q,c) g_f(q) [g_0 = 1] + sum_tap wsum[tap][c] ds_f(q - (tap - 1)),
+ *   dwsum[tap][c] (+)= sum_{b,f,q} feat_f(q,c) ds_f(q - (tap - 1))
+ * (every output channel of temporal_attn1.weight receives dwsum; temporal_attn0 and both biases cancel out of the gate as written
+ * and receive zero).  feat, dfeat: [B][F][H][W][C]; dgated: [B][H][W][F][C] (the forward's `gated` layout) of `dtype`;
+ * gate: fp32 [B][F-1][H][W] as the forward stored it; score: fp32 [B][F][H][W] (s_f); dscore: fp32 [B][F][H][W] workspace / output;
+ * partial: fbanet_faf_gate_bwd_blocks(B*F*H*W) * 9 * C floats. */
+typedef struct fbanet_faf_gate_bwd_params {
+  const void* feat;
+  const void* dgated;
+  const float* gate;
+  const float* score;
+  const float* wsum;
+  void* dfeat;
+  float* dscore;
+  float* dwsum;
+  float* partial;
+  int32_t dtype, B, F, H, W, C, accumulate, _pad;
+} fbanet_faf_gate_bwd_params;
+
+/* DropPath residual (layers/drop_path.py:39-63 in its "global" mode under jax.vmap: ONE Bernoulli draw per burst and call;
+ * layers/fba_net.py:245,248):  out[b][i] = skip[b][i] + scale[b] * x[b][i],  scale[b] = 0 or 1 / keep_prob, drawn by the caller
+ * (fp32 device array).  skip = NULL gives the branch's backward  dx = scale[b] * dy.  A dropped burst (scale 0) contributes
+ * exactly 0.  x, skip, out: B * per_burst contiguous elements of `dtype`; out may alias skip or x. */
+typedef struct fbanet_drop_path_params {
+  const void* x;
+  const void* skip;       /* optional */
+  void* out;
+  const float* scale;     /* [B] fp32 */
+  int64_t per_burst;
+  int32_t dtype, B;
+} fbanet_drop_path_params;
+
 int fbanet_abi_version(void);
 /* sizeof() of the named parameter struct as compiled, for binding self-checks; -1 if unknown */
 int fbanet_abi_sizeof(const char* struct_name);
@@ -461,9 +534,17 @@ int fbanet_adam_step_sm100(const fbanet_adam_params* p, void* stream);
 int fbanet_wgrad_sm100(const fbanet_wgrad_params* p, void* stream);
 int fbanet_layernorm_bwd_sm100(const fbanet_layernorm_bwd_params* p, void* stream);
 int fbanet_act_bwd_sm100(const fbanet_act_bwd_params* p, void* stream);
+int fbanet_dwconv3x3_bwd_sm100(const fbanet_dwconv_bwd_params* p, void* stream);
+int fbanet_window_attention_bwd_sm100(const fbanet_attn_bwd_params* p, void* stream);
+int fbanet_faf_gate_bwd_sm100(const fbanet_faf_gate_bwd_params* p, void* stream);
+int fbanet_drop_path_add_sm100(const fbanet_drop_path_params* p, void* stream);
 /* thread blocks (= partial rows) the two reductions above use for a problem of this size */
 int fbanet_layernorm_bwd_blocks(int64_t rows);
 int fbanet_act_bwd_blocks(int64_t n);
+int fbanet_dwconv_bwd_blocks(int64_t pixels);            /* pixels = N*H*W */
+int fbanet_faf_gate_bwd_blocks(int64_t frame_pixels);    /* frame_pixels = B*F*H*W */
+/* floats of `partial` fbanet_window_attention_bwd_sm100 needs for the table gradient; -1 for an inconsistent shape */
+int64_t fbanet_attn_bwd_partial_floats(int32_t B, int32_t H, int32_t W, int32_t heads, int32_t win);
 /* doubles of workspace fbanet_train_loss_sm100 needs (2 per thread block) */
 int64_t fbanet_train_loss_workspace_doubles(int32_t planes, int32_t H, int32_t W);
 

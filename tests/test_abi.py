@@ -59,6 +59,21 @@ def test_bad_params_are_rejected_without_a_gpu(lib):
     n.x, n.dy, n.gamma, n.dx, n.partial, n.rows, n.C, n.eps = 1, 1, 1, 1, 1, 4, 512, 1e-5   # C > 256
     assert lib.fbanet_layernorm_bwd_sm100(ctypes.byref(n), None) == -1
     assert lib.fbanet_layernorm_bwd_blocks(0) == -1 and lib.fbanet_act_bwd_blocks(0) == -1
+    # second set of backward bricks (depthwise 3x3, window attention, FAF gate, DropPath residual)
+    for fn, st in (("fbanet_dwconv3x3_bwd_sm100", _lib.DwconvBwdParams), ("fbanet_window_attention_bwd_sm100", _lib.AttnBwdParams),
+                   ("fbanet_faf_gate_bwd_sm100", _lib.FafGateBwdParams), ("fbanet_drop_path_add_sm100", _lib.DropPathParams)):
+        assert getattr(lib, fn)(ctypes.byref(st()), None) == -1, fn
+    d = _lib.DwconvBwdParams()
+    d.x, d.dy, d.weight, d.partial, d.N, d.H, d.W, d.C, d.dtype = 1, 1, 1, 1, 1, 4, 4, 8, 0      # no output requested
+    assert lib.fbanet_dwconv3x3_bwd_sm100(ctypes.byref(d), None) == -1
+    t = _lib.AttnBwdParams()
+    t.qkv, t.dout, t.dqkv, t.bias_table, t.dbias = 1, 1, 1, 1, 1                                  # table gradient without its workspace
+    t.B, t.H, t.W, t.C, t.heads, t.win, t.qkv_ld, t.dout_ld, t.dqkv_ld = 1, 10, 10, 64, 1, 10, 192, 64, 192
+    assert lib.fbanet_window_attention_bwd_sm100(ctypes.byref(t), None) == -1
+    t.dbias, t.H = None, 12                                                                        # H not a multiple of win
+    assert lib.fbanet_window_attention_bwd_sm100(ctypes.byref(t), None) == -1
+    assert lib.fbanet_attn_bwd_partial_floats(2, 20, 20, 4, 10) == 2 * 4 * 4 * 361 and lib.fbanet_attn_bwd_partial_floats(1, 12, 10, 1, 10) == -1
+    assert lib.fbanet_dwconv_bwd_blocks(0) == -1 and lib.fbanet_faf_gate_bwd_blocks(0) == -1 and lib.fbanet_dwconv_bwd_blocks(9) == 3
     e = _lib.EccParams()
     e.planes, e.warp, e.frames, e.frames_per_burst, e.H, e.W, e.max_iters = 1, 1, 7, 2, 16, 16, 10   # 7 frames are not whole bursts of 2
     assert lib.fbanet_ecc_homography_sm100(ctypes.byref(e), None) == -1

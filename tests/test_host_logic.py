@@ -190,3 +190,17 @@ def test_drop_path_rates_match_the_reference_constructor():
                            ("decoderlayer_0", f"{hg}_decoderlayer_0"), ("decoderlayer_1", f"{hg}_decoderlayer_1")):
             want = [layer["drop_path_rate"] for layer in mods[name]["layers"]]
             assert len(want) == len(rates[mine]) and all(abs(a - b) < 1e-6 for a, b in zip(rates[mine], want)), (name, rates[mine], want)
+
+
+def test_drop_path_scales_follow_the_reference_layer():
+    """layers/drop_path.py:52-63: bernoulli(keep) / keep per burst; p == 0 returns x itself (all ones); keep == 0 skips the division."""
+    import torch
+    from fbanet_b200 import train
+    assert torch.equal(train.drop_path_scales(4, 0.0), torch.ones(4))
+    assert torch.equal(train.drop_path_scales(4, 1.0), torch.zeros(4))
+    s = train.drop_path_scales(20000, 0.1, generator=torch.Generator().manual_seed(0))
+    assert set(s.unique().tolist()) == {0.0, float(torch.tensor(1.0) / 0.9)}
+    assert abs(s.mean().item() - 1.0) < 0.01                      # E[noise / keep] = 1: the layer is unbiased
+    a = train.drop_path_scales(64, 0.5, generator=torch.Generator().manual_seed(3))
+    b = train.drop_path_scales(64, 0.5, generator=torch.Generator().manual_seed(3))
+    assert torch.equal(a, b)
