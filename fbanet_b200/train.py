@@ -7,7 +7,8 @@ What a training step will be once the backward exists::
 
     loss, d_restored = ops.training_loss(model(burst), target)      # built (fbanet_train_loss_sm100)
     backward(model, d_restored) -> flat.grad                        # NOT built: DESIGN.md 8c
-    flat.all_reduce()                                               # built: one NCCL sum over the flat gradient buffer
+    flat.all_reduce()                                               # built: one NCCL sum over the flat gradient buffer (or begin_reduce /
+                                                                    # mark_ready / finish_reduce: the same sum in buckets, overlapped)
     flat.adam_step(lr)                                              # built (fbanet_adam_step_sm100), grad_scale = 1 / world
 """
 from __future__ import annotations
@@ -55,6 +56,67 @@ class FlatParams:
         if world > 1:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
         return 1.0 / world
+
+    # ---- the same sum as bucketed collectives issued WHILE the backward still runs -------------------------
+    def begin_reduce(self, group=None, bucket_bytes: int = 16 << 20) -> None:
+        """Start a bucketed reduction of the flat gradient: the parameters are grouped, from the TAIL of the buffer (the backward
+        reaches the last layers first), into runs of at least ``bucket_bytes``; :meth:`mark_ready` launches a run's
+        ``all_reduce(sum, async_op=True)`` as soon as the gradient of every parameter in it is final, so the transfers overlap the
+        rest of the backward; :meth:`finish_reduce` launches what is left and waits.  On NVSwitch the cost of a collective does not
+        depend on link count, so the bucket size only trades launch latency (few, large) against overlap (many, small): 16 MiB
+        gives 5 buckets for the 77 MB of fp32 gradients.  Every element takes part in exactly one collective, so the result equals
+        :meth:`all_reduce`'s."""
+        self._group = group
+        self._world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        if getattr(self, "_bucket_bytes", None) != bucket_bytes:
+            self._bucket_bytes, self._buckets, self._bucket_of = bucket_bytes, [], {}
+            end, size = self.numel, 0
+            for k in range(len(self.params) - 1, -1, -1):
+                size += self.params[k].numel() * 4
+                if size >= bucket_bytes or k == 0:
+                    self._buckets.append((self.offsets[k], end, k))                      # [begin, end) in elements, first param index
+                    end, size = self.offsets[k], 0
+            first = [b[2] for b in self._buckets]
+            for bi, f in enumerate(first):
+                last = first[bi - 1] if bi > 0 else len(self.params)
+                for k in range(f, last):
+                    self._bucket_of[id(self.params[k])] = bi
+        self._pending = [0] * len(self._buckets)
+        for p in self.params:
+            self._pending[self._bucket_of[id(p)]] += 1
+        self._ready, self._launched, self._handles = set(), [False] * len(self._buckets), []
+
+    def _launch(self, bi: int) -> None:
+        if self._launched[bi]:
+            return
+        self._launched[bi] = True
+        if self._world > 1:
+            b, e, _ = self._buckets[bi]
+            self._handles.append(dist.all_reduce(self.grad[b:e], op=dist.ReduceOp.SUM, group=self._group, async_op=True))
+
+    def mark_ready(self, param: torch.nn.Parameter) -> None:
+        """The gradient of ``param`` is final (the backward will not touch it again in this step).  Buckets are launched in bucket
+        order only -- every rank must issue the same sequence of collectives -- so a bucket that completes early waits for the ones
+        before it."""
+        if id(param) in self._ready:
+            return
+        self._ready.add(id(param))
+        self._pending[self._bucket_of[id(param)]] -= 1
+        for bi in range(len(self._buckets)):
+            if self._launched[bi]:
+                continue
+            if self._pending[bi] > 0:
+                break
+            self._launch(bi)
+
+    def finish_reduce(self) -> float:
+        """Launch the buckets not yet launched, wait for all of them; returns 1 / world like :meth:`all_reduce`."""
+        for bi in range(len(self._buckets)):
+            self._launch(bi)
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+        return 1.0 / self._world
 
     def adam_step(self, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, decoupled: bool = True,
                   grad_scale: float = 1.0) -> None:

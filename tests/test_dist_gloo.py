@@ -136,3 +136,56 @@ def test_two_rank_flat_gradient_all_reduce():
         assert p.exitcode == 0
     for r, same, views, ok, scale, n in res:
         assert same and views and ok and scale == 0.5 and n == 5 * 7 + 7 + 1 + 7 * 3 + 3
+
+
+def _bucket_worker(rank, world, port, q):
+    """The bucketed form of config 5's collective: parameters marked ready in backward order (and one out of order), buckets launched
+    in bucket order on every rank, result identical to the one-shot all-reduce."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from fbanet_b200.dist import init_from_env
+    from fbanet_b200.train import FlatParams
+    r, _, w = init_from_env("gloo")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(*[torch.nn.Linear(16, 16) for _ in range(6)])
+    flat = FlatParams(net.parameters())
+    g = torch.Generator().manual_seed(100 + r)
+    flat.grad.copy_(torch.randn(flat.numel, generator=g))
+    local = flat.grad.clone()
+    flat.begin_reduce(bucket_bytes=2 * (16 * 16 + 16) * 4)                                 # two layers per bucket -> 3 buckets
+    nb, launched = len(flat._buckets), []
+    order = list(reversed(flat.params))
+    order[0], order[5] = order[5], order[0]                                                # one parameter becomes ready "late"
+    for p in order:
+        flat.mark_ready(p)
+        launched.append(sum(flat._launched))
+    scale = flat.finish_reduce()
+    bucketed = flat.grad.clone()
+    flat.grad.copy_(local)
+    flat.all_reduce()
+    covered = sorted((b, e) for b, e, _ in flat._buckets)
+    tiles = covered[0][0] == 0 and covered[-1][1] == flat.numel and all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
+    flat.begin_reduce(bucket_bytes=2 * (16 * 16 + 16) * 4)                                 # second step: nothing marked, finish launches all
+    flat.grad.copy_(local)
+    flat.finish_reduce()
+    again = torch.equal(flat.grad, bucketed)
+    dist.barrier()
+    q.put((r, nb, launched, scale, torch.equal(bucketed, flat.grad) and again, tiles))
+    dist.destroy_process_group()
+
+
+def test_two_rank_bucketed_gradient_reduce_equals_one_shot():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r, nb, launched, scale, same, tiles in res:
+        assert nb == 3 and scale == 0.5 and same and tiles
+        # the tail bucket (layers 5, 4) needs the late parameter (layer 5's bias, marked 6th): nothing launches before it; the middle
+        # bucket (layers 3, 2) completes with layer 2's weight (8th), the head bucket with the last parameter
+        assert launched[:5] == [0] * 5 and launched[5:7] == [1, 1] and launched[7] == 2 and launched[-2:] == [2, 3], launched
