@@ -141,6 +141,104 @@ def dgrad_weight(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return w.flip(2, 3).permute(1, 2, 3, 0).reshape(w.shape[1], -1).to(dtype).contiguous()
 
 
+def dgrad_weight_convT2(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Data gradient of ``ConvTranspose2d(Ci, Co, 2, 2)`` (``layers/upsample.py:19-30``, ``upsample_flatten.py:6-12``; weight
+    ``[Ci,Co,2,2]``) as a 1x1 GEMM over the space-to-depth view of ``dy``: ``dx(y,x,ci) = sum_{a,b,co} dy(2y+a, 2x+b, co) w[ci,co,a,b]``
+    = ``ops.conv_gemm([ops.space_to_depth(dy)], dgrad_weight_convT2(w, dt), dx)``.  Packed ``[Ci, 4*Co]``, K index ``(a*2+b)*Co + co``
+    (the channel order ``fbanet_space_to_depth_sm100`` writes)."""
+    w = weight.detach()
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(dtype).contiguous()
+
+
+def dgrad_weight_down4(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Data gradient of ``Conv2d(Ci, Co, 4, stride 2, padding 1)`` (``layers/downsample.py:19-30``, ``downsample_flatten.py:6-13``;
+    weight ``[Co,Ci,4,4]``) as ONE 3x3 implicit GEMM over ``dy`` whose 4*Ci output rows are the four sub-pixel phases of ``dx``,
+    scattered by the forward's ConvTranspose-style store: input pixel ``(2i+a, 2j+b)`` is read by output pixel ``i + d`` through
+    tap ``ky = a + 1 - 2d`` (``d`` in {-1,0,1}, two of the three valid per phase), so
+    ``W'[(a*2+b)*Ci + ci][((d+1)*3 + (e+1))*Co + co] = w[co,ci,a+1-2d,b+1-2e]`` (0 where the tap falls outside 0..3) and
+    ``dx = ops.conv_gemm([dy], W', dx[N,2Ho,2Wo,Ci], kh=3, kw=3, pad=1, store_mode=STORE_CONVT2)``.  (5/9 of the MACs multiply
+    zeros; the kernel is the verified forward one.)"""
+    w = weight.detach()
+    Co, Ci = w.shape[:2]
+    out = torch.zeros(2, 2, Ci, 3, 3, Co, dtype=w.dtype, device=w.device)
+    for a in range(2):
+        for ty in range(3):
+            ky = a + 3 - 2 * ty
+            if not 0 <= ky < 4:
+                continue
+            for b in range(2):
+                for tx in range(3):
+                    kx = b + 3 - 2 * tx
+                    if 0 <= kx < 4:
+                        out[a, b, :, ty, tx, :] = w[:, :, ky, kx].t()
+    return out.reshape(4 * Ci, 9 * Co).to(dtype).contiguous()
+
+
+def dgrad_weight_pixel_shuffle(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Data gradient of ``Conv2d(Ci, 4C, 3, padding 1)`` followed by ``PixelShuffle(2)`` (``blocks/upsampler.py:22-32``,
+    ``layers/pixel_shuffle.py:9-10``; weight ``[4C,Ci,3,3]``): the un-shuffled gradient ``dz(y,x,4c+2i+j) = dy(2y+i,2x+j,c)`` is the
+    space-to-depth view of ``dy`` with its channels in ``(2i+j)*C + c`` order, so the permutation goes into the K axis of the
+    ordinary flipped-weight packing: ``dx = ops.conv_gemm([ops.space_to_depth(dy)], W', dx, kh=3, kw=3, pad=1)``."""
+    w = weight.detach()
+    C4, Ci = w.shape[:2]
+    wf = w.flip(2, 3).permute(1, 2, 3, 0).reshape(Ci, 3, 3, C4 // 4, 4).permute(0, 1, 2, 4, 3)     # [ci, ky, kx, (i,j), c]
+    return wf.reshape(Ci, -1).to(dtype).contiguous()
+
+
+def convT2_dgrad(dy: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """``dy [N,2H,2W,Co]`` channels-last -> ``dx [N,H,W,Ci]`` for ``ConvTranspose2d(Ci,Co,2,2)`` (CUDA only)."""
+    from . import ops
+    N, H2, W2, _ = dy.shape
+    dx = torch.empty((N, H2 // 2, W2 // 2, weight.shape[0]), device=dy.device, dtype=dy.dtype)
+    return ops.conv_gemm([ops.space_to_depth(dy)], dgrad_weight_convT2(weight, dy.dtype), dx)
+
+
+def down4_dgrad(dy: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """``dy [N,Ho,Wo,Co]`` channels-last -> ``dx [N,2Ho,2Wo,Ci]`` for ``Conv2d(Ci,Co,4,2,1)`` (CUDA only)."""
+    from . import ops, _lib as L
+    N, Ho, Wo, _ = dy.shape
+    dx = torch.empty((N, 2 * Ho, 2 * Wo, weight.shape[1]), device=dy.device, dtype=dy.dtype)
+    return ops.conv_gemm([dy], dgrad_weight_down4(weight, dy.dtype), dx, kh=3, kw=3, pad=1, store_mode=L.STORE_CONVT2)
+
+
+def pixel_shuffle_conv_dgrad(dy: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """``dy [N,2H,2W,C]`` channels-last (gradient of the SHUFFLED output) -> ``dx [N,H,W,Ci]`` for conv3x3 ``[4C,Ci,3,3]`` +
+    ``PixelShuffle(2)`` (CUDA only)."""
+    from . import ops
+    N, H2, W2, _ = dy.shape
+    dx = torch.empty((N, H2 // 2, W2 // 2, weight.shape[1]), device=dy.device, dtype=dy.dtype)
+    return ops.conv_gemm([ops.space_to_depth(dy)], dgrad_weight_pixel_shuffle(weight, dy.dtype), dx, kh=3, kw=3, pad=1)
+
+
+def convT2_wgrad(x: torch.Tensor, dy: torch.Tensor):
+    """Weight / bias gradient of ``ConvTranspose2d(Ci,Co,2,2)`` in the torch layouts (``[Ci,Co,2,2]``, ``[Co]``): the 1x1 weight
+    gradient between ``x [N,H,W,Ci]`` and the space-to-depth view of ``dy [N,2H,2W,Co]`` gives rows ``(a,b,co)``; the bias sums
+    the four phases (CUDA only)."""
+    from . import ops
+    Co = dy.shape[-1]
+    dw4, db4 = ops.conv_wgrad(x, ops.space_to_depth(dy))                                          # [4Co, Ci, 1, 1], [4Co]
+    return convT2_wgrad_layout(dw4, db4, Co)
+
+
+def convT2_wgrad_layout(dw4: torch.Tensor, db4: torch.Tensor, Co: int):
+    Ci = dw4.shape[1]
+    return dw4.reshape(2, 2, Co, Ci).permute(3, 2, 0, 1).contiguous(), db4.reshape(4, Co).sum(0)
+
+
+def pixel_shuffle_conv_wgrad(x: torch.Tensor, dy: torch.Tensor):
+    """Weight / bias gradient of conv3x3 ``[4C,Ci,3,3]`` + ``PixelShuffle(2)``: the 3x3 weight gradient between ``x`` and the
+    space-to-depth view of ``dy`` has its output channels in ``(2i+j)*C + c`` order; re-ordered to torch's ``4c+2i+j`` (CUDA only)."""
+    from . import ops
+    dw, db = ops.conv_wgrad(x, ops.space_to_depth(dy), 3, 3, 1, 1)
+    return pixel_shuffle_wgrad_layout(dw, db)
+
+
+def pixel_shuffle_wgrad_layout(dw: torch.Tensor, db: torch.Tensor):
+    C4 = dw.shape[0]
+    return (dw.reshape(4, C4 // 4, *dw.shape[1:]).transpose(0, 1).reshape(dw.shape).contiguous(),
+            db.reshape(4, C4 // 4).t().reshape(-1).contiguous())
+
+
 # ------------------------------------------------------------------------------------------------------------------------------
 # learning-rate schedules and stochastic-depth rates of the training configuration (host arithmetic, no tensors)
 # ------------------------------------------------------------------------------------------------------------------------------

@@ -159,3 +159,62 @@ def test_drop_path_add_forward_and_backward(cuda, dtype):
     assert torch.equal(dx, (skip.float() * scale[:, None, None]).to(dtype))
     ones = train.drop_path_scales(B, 0.0, device=cuda)
     assert torch.equal(ops.drop_path_add(skip, ones), skip)
+
+
+# ---- resampling layers: gradients as compositions of the FORWARD kernels with re-packed weights (train.dgrad_weight_* / *_wgrad).
+# The packings are checked on the CPU against an emulation of the kernels' contracts (tests/test_host_logic.py::
+# test_resampling_layer_gradients_through_forward_kernels); here the real kernels run them.
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_convT2_gradients_through_forward_kernels(cuda, dtype):
+    """ConvTranspose2d(4E, E, 2, 2) of layers/upsample.py:19-30 (E = 64)."""
+    from fbanet_b200 import train
+    g = torch.Generator().manual_seed(21)
+    N, H, W, Ci, Co = 2, 10, 12, 256, 64
+    w = (torch.randn(Ci, Co, 2, 2, generator=g) / Ci ** 0.5).to(cuda)
+    x = torch.randn(N, H, W, Ci, generator=g).to(dtype).to(cuda)
+    dy = torch.randn(N, 2 * H, 2 * W, Co, generator=g).to(dtype).to(cuda)
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    wr = w.to(dtype).float().requires_grad_(True)
+    br = torch.zeros(Co, device=cuda, requires_grad=True)
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        F.conv_transpose2d(xr, wr, br, stride=2).backward(dy.float().permute(0, 3, 1, 2))
+    dx = train.convT2_dgrad(dy, w)
+    assert _rel(dx.float(), xr.grad.permute(0, 2, 3, 1)) < _tol(dtype), _rel(dx.float(), xr.grad.permute(0, 2, 3, 1))
+    dw, db = train.convT2_wgrad(x, dy)
+    assert dw.shape == w.shape and _rel(dw, wr.grad) < 2e-4 and _rel(db, br.grad) < 2e-4
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_pixel_shuffle_conv_gradients_through_forward_kernels(cuda, dtype):
+    """conv3x3 E -> 4E + PixelShuffle(2) of blocks/upsampler.py:22-32 (E = 64)."""
+    from fbanet_b200 import train
+    g = torch.Generator().manual_seed(23)
+    N, H, W, Ci, C = 2, 10, 12, 64, 64
+    w = (torch.randn(4 * C, Ci, 3, 3, generator=g) / (9 * Ci) ** 0.5).to(cuda)
+    x = torch.randn(N, H, W, Ci, generator=g).to(dtype).to(cuda)
+    dy = torch.randn(N, 2 * H, 2 * W, C, generator=g).to(dtype).to(cuda)
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    wr = w.to(dtype).float().requires_grad_(True)
+    br = torch.zeros(4 * C, device=cuda, requires_grad=True)
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        F.pixel_shuffle(F.conv2d(xr, wr, br, padding=1), 2).backward(dy.float().permute(0, 3, 1, 2))
+    dx = train.pixel_shuffle_conv_dgrad(dy, w)
+    assert _rel(dx.float(), xr.grad.permute(0, 2, 3, 1)) < _tol(dtype), _rel(dx.float(), xr.grad.permute(0, 2, 3, 1))
+    dw, db = train.pixel_shuffle_conv_wgrad(x, dy)
+    assert dw.shape == w.shape and _rel(dw, wr.grad) < 2e-4 and _rel(db, br.grad) < 2e-4
+
+
+@pytest.mark.parametrize("dtype,Ci,Co", [(torch.float32, 32, 64), (torch.float32, 64, 128), (torch.bfloat16, 32, 64), (torch.bfloat16, 64, 128)])
+def test_downsample4_data_gradient_through_forward_kernel(cuda, dtype, Ci, Co):
+    """Conv2d(E, 2E, 4, 2, 1) of layers/downsample.py:19-30 (E = 32, 64): four sub-pixel phases as rows of one 3x3 GEMM over dy."""
+    from fbanet_b200 import train
+    g = torch.Generator().manual_seed(22)
+    N, Ho, Wo = 2, 10, 12
+    w = (torch.randn(Co, Ci, 4, 4, generator=g) / (16 * Ci) ** 0.5).to(cuda)
+    dy = torch.randn(N, Ho, Wo, Co, generator=g).to(dtype).to(cuda)
+    xr = torch.zeros(N, Ci, 2 * Ho, 2 * Wo, device=cuda, requires_grad=True)
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        F.conv2d(xr, w.to(dtype).float(), None, stride=2, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    dx = train.down4_dgrad(dy, w)
+    assert dx.shape == (N, 2 * Ho, 2 * Wo, Ci)
+    assert _rel(dx.float(), xr.grad.permute(0, 2, 3, 1)) < _tol(dtype), _rel(dx.float(), xr.grad.permute(0, 2, 3, 1))

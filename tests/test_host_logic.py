@@ -204,3 +204,84 @@ def test_drop_path_scales_follow_the_reference_layer():
     a = train.drop_path_scales(64, 0.5, generator=torch.Generator().manual_seed(3))
     b = train.drop_path_scales(64, 0.5, generator=torch.Generator().manual_seed(3))
     assert torch.equal(a, b)
+
+
+# ---- data / weight gradients of the resampling layers as compositions of the FORWARD kernels (train.dgrad_weight_*) ----------------
+# The kernels are emulated on the CPU by their documented contracts (include/fbanet_b200.h: packed weight [Cout, taps*Cin] with
+# K index tap*Cin + ci, FBANET_STORE_CONVT2 col = (2i+j)*Co + co -> out(2y+i, 2x+j, co), space-to-depth channel (ys*2+xs)*C + c);
+# the emulation is first validated against the packings model.py feeds the real kernels for the forward (those are GPU-verified),
+# then the gradient packings are checked against autograd.
+def _emu_conv_gemm(src, packed, k=1, pad=0, convt2=False):
+    import torch
+    import torch.nn.functional as F
+    Cout, C = packed.shape[0], src.shape[-1]
+    w = packed.reshape(Cout, k, k, C).permute(0, 3, 1, 2)
+    g = F.conv2d(src.permute(0, 3, 1, 2), w, None, padding=pad).permute(0, 2, 3, 1)          # [N,H,W,Cout]
+    if not convt2:
+        return g
+    N, H, W, _ = g.shape
+    Co = Cout // 4
+    return g.reshape(N, H, W, 2, 2, Co).permute(0, 1, 3, 2, 4, 5).reshape(N, 2 * H, 2 * W, Co)
+
+
+def _emu_s2d(x):
+    N, H, W, C = x.shape
+    return x.reshape(N, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(N, H // 2, W // 2, 4 * C)
+
+
+def test_resampling_layer_gradients_through_forward_kernels():
+    import torch
+    import torch.nn.functional as F
+    from fbanet_b200 import train
+    from fbanet_b200.model import BaseModel
+    torch.manual_seed(0)
+    m = BaseModel(img_size=40, embed_dim=16, window_length=10, token_mlp="leff", dtype="fp32", num_frames=3).double()
+    m.compute_dtype = torch.float64
+    P = {k: v.double() for k, v in m._pack().items()}
+    dd = torch.float64
+    # -- the emulation reproduces the forward of the three layers from model.py's own packings
+    up, down, ps = m.fusion.upsample0, m.fusion.downsample0, m.tail[0][0]
+    x = torch.randn(2, 6, 8, up.weight.shape[0], dtype=dd)
+    want = F.conv_transpose2d(x.permute(0, 3, 1, 2), up.weight, None, stride=2).permute(0, 2, 3, 1)
+    assert torch.allclose(_emu_conv_gemm(x, P["fusion.up0.w"], convt2=True), want, atol=1e-12)
+    xp = torch.randn(2, 6, 8, ps.weight.shape[1], dtype=dd)
+    want = F.pixel_shuffle(F.conv2d(xp.permute(0, 3, 1, 2), ps.weight, None, padding=1), 2).permute(0, 2, 3, 1)
+    assert torch.allclose(_emu_conv_gemm(xp, P["tail.0.0.w"], 3, 1, convt2=True), want, atol=1e-12)
+    assert torch.equal(_emu_s2d(torch.arange(2 * 4 * 6 * 3, dtype=dd).reshape(2, 4, 6, 3))[1, 1, 2, 2 * 3 + 1],
+                       torch.arange(2 * 4 * 6 * 3, dtype=dd).reshape(2, 4, 6, 3)[1, 3, 4, 1])      # channel (ys*2+xs)*C + c, ys=1, xs=0
+
+    # -- ConvTranspose2d(2,2): data gradient = 1x1 GEMM over s2d(dy); weight gradient layout
+    xr = x.clone().requires_grad_(True)
+    wr = up.weight.detach().clone().requires_grad_(True)
+    br = torch.zeros(wr.shape[1], dtype=dd, requires_grad=True)
+    y = F.conv_transpose2d(xr.permute(0, 3, 1, 2), wr, br, stride=2).permute(0, 2, 3, 1)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    assert torch.allclose(_emu_conv_gemm(_emu_s2d(dy), train.dgrad_weight_convT2(wr, dd)), xr.grad, atol=1e-12)
+    dys = _emu_s2d(dy)                                                                           # what ops.conv_wgrad(x, s2d(dy)) returns:
+    dw4 = torch.einsum("nhwo,nhwi->oi", dys, x)[:, :, None, None]
+    dw, db = train.convT2_wgrad_layout(dw4, dys.sum((0, 1, 2)), wr.shape[1])
+    assert torch.allclose(dw, wr.grad, atol=1e-10) and torch.allclose(db, br.grad, atol=1e-10)
+
+    # -- Conv2d(4, stride 2, pad 1): data gradient = 3x3 GEMM over dy with phase rows + ConvT-style scatter
+    xd = torch.randn(2, 8, 12, down.weight.shape[1], dtype=dd, requires_grad=True)
+    y = F.conv2d(xd.permute(0, 3, 1, 2), down.weight, None, stride=2, padding=1).permute(0, 2, 3, 1)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    got = _emu_conv_gemm(dy, train.dgrad_weight_down4(down.weight, dd), 3, 1, convt2=True)
+    assert got.shape == xd.shape and torch.allclose(got, xd.grad, atol=1e-12)
+
+    # -- conv3x3 + PixelShuffle(2): data gradient = flipped-weight 3x3 GEMM over s2d(dy) with permuted K; weight gradient layout
+    xr = xp.clone().requires_grad_(True)
+    wr = ps.weight.detach().clone().requires_grad_(True)
+    br = torch.zeros(wr.shape[0], dtype=dd, requires_grad=True)
+    y = F.pixel_shuffle(F.conv2d(xr.permute(0, 3, 1, 2), wr, br, padding=1), 2).permute(0, 2, 3, 1)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    assert torch.allclose(_emu_conv_gemm(_emu_s2d(dy), train.dgrad_weight_pixel_shuffle(wr, dd), 3, 1), xr.grad, atol=1e-12)
+    dz = _emu_s2d(dy).permute(0, 3, 1, 2)                                                        # ops.conv_wgrad(x, s2d(dy), 3, 3, 1, 1):
+    wz = torch.zeros_like(wr, requires_grad=True)
+    bz = torch.zeros_like(br, requires_grad=True)
+    F.conv2d(xp.permute(0, 3, 1, 2), wz, bz, padding=1).backward(dz)
+    dw, db = train.pixel_shuffle_wgrad_layout(wz.grad, bz.grad)
+    assert torch.allclose(dw, wr.grad, atol=1e-10) and torch.allclose(db, br.grad, atol=1e-10)
