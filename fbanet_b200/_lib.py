@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBANET_B200_LIB") or os.path.join(_HERE, "csrc", "libfbanet_b200.so")   # env override: A/B two builds in one process tree
-ABI_VERSION = 20
+ABI_VERSION = 21
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -208,6 +208,10 @@ class ActBwdParams(C.Structure):
     ]
 
 
+class ActFwdParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("alpha", C.c_void_p), ("n", C.c_int64), ("dtype", C.c_int32), ("act", C.c_int32)]
+
+
 class DwconvBwdParams(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("dy", C.c_void_p), ("weight", C.c_void_p), ("dx", C.c_void_p), ("dw", C.c_void_p), ("db", C.c_void_p),
@@ -248,7 +252,7 @@ STRUCTS = {
     "fbanet_tile_band_params": TileBandParams, "fbanet_flow_warp_params": FlowWarpParams,
     "fbanet_ecc_prepare_params": EccPrepareParams, "fbanet_ecc_params": EccParams, "fbanet_train_loss_params": TrainLossParams,
     "fbanet_adam_params": AdamParams, "fbanet_wgrad_params": WgradParams, "fbanet_layernorm_bwd_params": LayerNormBwdParams,
-    "fbanet_act_bwd_params": ActBwdParams, "fbanet_dwconv_bwd_params": DwconvBwdParams, "fbanet_attn_bwd_params": AttnBwdParams,
+    "fbanet_act_bwd_params": ActBwdParams, "fbanet_act_fwd_params": ActFwdParams, "fbanet_dwconv_bwd_params": DwconvBwdParams, "fbanet_attn_bwd_params": AttnBwdParams,
     "fbanet_faf_gate_bwd_params": FafGateBwdParams, "fbanet_drop_path_params": DropPathParams,
 }
 
@@ -260,7 +264,7 @@ OPS = {
     "fbanet_tile_divide_banded_sm100": TileBandParams, "fbanet_tile_merge_banded_sm100": TileBandParams, "fbanet_flow_warp_sm100": FlowWarpParams,
     "fbanet_ecc_prepare_sm100": EccPrepareParams, "fbanet_ecc_homography_sm100": EccParams, "fbanet_train_loss_sm100": TrainLossParams,
     "fbanet_adam_step_sm100": AdamParams, "fbanet_wgrad_sm100": WgradParams, "fbanet_layernorm_bwd_sm100": LayerNormBwdParams,
-    "fbanet_act_bwd_sm100": ActBwdParams, "fbanet_dwconv3x3_bwd_sm100": DwconvBwdParams,
+    "fbanet_act_bwd_sm100": ActBwdParams, "fbanet_act_fwd_sm100": ActFwdParams, "fbanet_dwconv3x3_bwd_sm100": DwconvBwdParams,
     "fbanet_window_attention_bwd_sm100": AttnBwdParams, "fbanet_faf_gate_bwd_sm100": FafGateBwdParams,
     "fbanet_drop_path_add_sm100": DropPathParams,
 }

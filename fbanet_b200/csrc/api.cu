@@ -62,6 +62,7 @@ extern "C" int fbanet_abi_sizeof(const char* n) {
   SZ(fbanet_wgrad_params);
   SZ(fbanet_layernorm_bwd_params);
   SZ(fbanet_act_bwd_params);
+  SZ(fbanet_act_fwd_params);
   SZ(fbanet_dwconv_bwd_params);
   SZ(fbanet_attn_bwd_params);
   SZ(fbanet_faf_gate_bwd_params);

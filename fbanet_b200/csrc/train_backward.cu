@@ -243,6 +243,17 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const fbanet_act_bwd_param
   }
 }
 
+// training-mode forward of a stand-alone activation: y = act(x) with the PRE-activation kept by the caller for act_bwd_kernel
+// (the inference path applies activations inside the producing GEMM's epilogue and never stores x)
+template <typename T>
+__global__ void __launch_bounds__(256) act_fwd_kernel(const fbanet_act_fwd_params p) {
+  const T* __restrict__ X = static_cast<const T*>(p.x);
+  T* __restrict__ Y = static_cast<T*>(p.y);
+  const float alpha = (p.act == FBANET_ACT_PRELU && p.alpha) ? *p.alpha : 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x)
+    Y[i] = from_f32<T>(apply_act(to_f32<T>(X[i]), p.act, alpha));
+}
+
 __global__ void act_bwd_finish_kernel(const fbanet_act_bwd_params p, int blocks) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     float s = 0.f;
@@ -309,5 +320,16 @@ extern "C" int fbanet_act_bwd_sm100(const fbanet_act_bwd_params* p, void* stream
   if (p->dtype == FBANET_F32) act_bwd_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
   else act_bwd_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
   if (p->act == FBANET_ACT_PRELU && p->dalpha) act_bwd_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*p, blocks);
+  return check_launch();
+}
+
+extern "C" int fbanet_act_fwd_sm100(const fbanet_act_fwd_params* p, void* stream) {
+  if (!p || !p->x || !p->y || p->n <= 0) return FBANET_E_BADSHAPE;
+  if (p->act < FBANET_ACT_NONE || p->act > FBANET_ACT_GELU_ERF) return FBANET_E_BADSHAPE;
+  if (p->act == FBANET_ACT_PRELU && !p->alpha) return FBANET_E_BADSHAPE;
+  if (p->dtype != FBANET_F32 && p->dtype != FBANET_BF16) return FBANET_E_DTYPE;
+  const int blocks = fbanet_act_bwd_blocks(p->n);
+  if (p->dtype == FBANET_F32) act_fwd_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+  else act_fwd_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
   return check_launch();
 }

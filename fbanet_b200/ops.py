@@ -650,6 +650,19 @@ def act_backward(x: torch.Tensor, dy: torch.Tensor, act: int, alpha: Optional[to
     return (dx, dalpha) if act == L.ACT_PRELU else dx
 
 
+def act_forward(x: torch.Tensor, act: int, alpha: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Training-mode stand-alone activation ``y = act(x)``; the caller keeps ``x`` (the pre-activation) for :func:`act_backward`."""
+    assert x.is_cuda and x.is_contiguous()
+    y = torch.empty_like(x)
+    p = L.ActFwdParams()
+    p.x, p.y, p.n, p.dtype, p.act = x.data_ptr(), y.data_ptr(), x.numel(), _DT[x.dtype], act
+    if act == L.ACT_PRELU:
+        assert alpha is not None and alpha.dtype == torch.float32 and alpha.numel() == 1
+        p.alpha = alpha.data_ptr()
+    _call("fbanet_act_fwd_sm100", p, nbytes=2 * x.numel() * x.element_size())
+    return y
+
+
 def dwconv3x3_backward(x: torch.Tensor, dy: torch.Tensor, weight9c: torch.Tensor, need_dx: bool = True, dw: Optional[torch.Tensor] = None,
                        db: Optional[torch.Tensor] = None, accumulate: bool = False):
     """Backward of the LeFF depthwise 3x3 (``layers/locally_enhanced_feed_forward.py:39-52``): ``x``, ``dy`` channels-last

@@ -240,6 +240,111 @@ def pixel_shuffle_wgrad_layout(dw: torch.Tensor, db: torch.Tensor):
 
 
 # ------------------------------------------------------------------------------------------------------------------------------
+# one LeWin block in training mode: forward that keeps its activations, backward composed of the bricks
+# ------------------------------------------------------------------------------------------------------------------------------
+def _accumulate(p: torch.nn.Parameter, g: torch.Tensor) -> None:
+    """Add ``g`` to ``p.grad`` (a view into ``FlatParams.grad`` when the module was flattened; created on first use otherwise)."""
+    g = g.reshape(p.shape).to(p.dtype)
+    if p.grad is None:
+        p.grad = g.clone()
+    else:
+        p.grad.add_(g)
+
+
+def _linear(x4: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    from . import ops
+    out = torch.empty((*x4.shape[:3], weight.shape[0]), device=x4.device, dtype=x4.dtype)
+    return ops.conv_gemm([x4], weight.detach().to(x4.dtype).contiguous(), out, bias=None if bias is None else bias.detach().contiguous())
+
+
+def _linear_backward(lin_weight: torch.Tensor, x4: torch.Tensor, dy4: torch.Tensor):
+    """``(dx, dW [out,in], db)`` of ``y = x W^T + b``: data gradient through the forward GEMM, weight gradient through the wgrad kernel."""
+    from . import ops
+    dx = torch.empty_like(x4)
+    ops.conv_gemm([dy4], dgrad_weight(lin_weight, dy4.dtype), dx)
+    dw, db = ops.conv_wgrad(x4, dy4)
+    return dx, dw.reshape(dw.shape[0], dw.shape[1]), db
+
+
+def lewin_forward_train(ly, x: torch.Tensor, s_attn: Optional[torch.Tensor] = None, s_mlp: Optional[torch.Tensor] = None,
+                        gelu_act: Optional[int] = None, eps: float = 1e-5):
+    """(Parameters are used in their stored dtype: the fp32 masters the C-ABI ops require.)
+    Training-mode forward of one LeWin block (``FBANetLayer.__call__``, ``layers/fba_net.py:139-250`` with the residuals of SURVEY
+    Appendix A-4): ``x1 = x + s_attn * proj(attn(qkv(LN1 x)))``, ``y = x1 + s_mlp * fc2(gelu(dw(gelu(fc1(LN2 x1)))))``.  ``ly``: the
+    model's layer module (``model._Layer``: norm1, attn.{qkv.to_q, qkv.to_kv, proj, relative_position_bias_table}, norm2,
+    mlp.{linear1, dwconv, linear2}); ``x`` ``[B,H,W,C]`` channels-last on the GPU (fp32 or bf16); ``s_attn`` / ``s_mlp``: per-burst
+    DropPath multipliers (:func:`drop_path_scales`; ``None`` = ones, the layer's rate is 0 or the model is in eval mode).
+    Returns ``(y, saved)``; every step is one of the C-ABI ops, the activations ``saved`` keeps are what :func:`lewin_backward` reads."""
+    from . import ops, _lib as L
+    gelu_act = L.ACT_GELU_TANH if gelu_act is None else gelu_act
+    B, H, W, C = x.shape
+    T = B * H * W
+    ones = torch.ones(B, device=x.device, dtype=torch.float32)
+    s_attn = ones if s_attn is None else s_attn
+    s_mlp = ones if s_mlp is None else s_mlp
+    a = ly.attn
+    scale = (C // ly.heads) ** -0.5
+    ln1 = ops.layernorm(x.view(T, C), ly.norm1.weight.detach(), ly.norm1.bias.detach(), eps).view(B, H, W, C)
+    wqkv = torch.cat([a.qkv.to_q.weight.detach(), a.qkv.to_kv.weight.detach()], 0)
+    bqkv = torch.cat([a.qkv.to_q.bias.detach(), a.qkv.to_kv.bias.detach()], 0)
+    qkv = _linear(ln1, wqkv, bqkv)
+    rpb = a.relative_position_bias_table.detach().contiguous()
+    att = ops.window_attention(qkv.view(T, 3 * C), rpb, B, H, W, ly.heads, ly.win, ly.shift, scale).view(B, H, W, C)
+    pr = _linear(att, a.proj.weight, a.proj.bias)
+    x1 = ops.drop_path_add(pr, s_attn, skip=x)
+    ln2 = ops.layernorm(x1.view(T, C), ly.norm2.weight.detach(), ly.norm2.bias.detach(), eps).view(B, H, W, C)
+    fc1, dw, fc2 = ly.mlp.linear1[0], ly.mlp.dwconv[0], ly.mlp.linear2[0]
+    h0 = _linear(ln2, fc1.weight, fc1.bias)                                     # pre-activations are kept for the backward
+    h1 = ops.act_forward(h0, gelu_act)
+    w9c = dw.weight.detach().reshape(dw.weight.shape[0], 9).t().contiguous()
+    d0 = ops.dwconv3x3(h1, w9c, dw.bias.detach().contiguous(), L.ACT_NONE)
+    d1 = ops.act_forward(d0, gelu_act)
+    m = _linear(d1, fc2.weight, fc2.bias)
+    y = ops.drop_path_add(m, s_mlp, skip=x1)
+    saved = dict(x=x, ln1=ln1, qkv=qkv, att=att, x1=x1, ln2=ln2, h0=h0, h1=h1, d0=d0, d1=d1, s_attn=s_attn, s_mlp=s_mlp, wqkv=wqkv,
+                 w9c=w9c, rpb=rpb, scale=scale, gelu_act=gelu_act, eps=eps, ones=ones)
+    return y, saved
+
+
+def lewin_backward(ly, saved: dict, dy: torch.Tensor) -> torch.Tensor:
+    """Backward of :func:`lewin_forward_train`: returns ``dx`` and ACCUMULATES the gradients of the layer's 17 parameter tensors into
+    their ``.grad`` (views of ``FlatParams.grad`` when flattened).  Composition of the bricks only: ``fbanet_drop_path_add`` (branch
+    scaling and the residual sums), ``fbanet_conv_gemm`` with :func:`dgrad_weight` (data gradients of the four linear layers),
+    ``fbanet_wgrad``, ``fbanet_act_bwd``, ``fbanet_dwconv3x3_bwd``, ``fbanet_layernorm_bwd``, ``fbanet_window_attention_bwd``."""
+    from . import ops
+    S = saved
+    B, H, W, C = S["x"].shape
+    T = B * H * W
+    a, fc1, dw, fc2 = ly.attn, ly.mlp.linear1[0], ly.mlp.dwconv[0], ly.mlp.linear2[0]
+    act = S["gelu_act"]
+    # ---- LeFF branch: y = x1 + s_mlp * fc2(d1)
+    dm = ops.drop_path_add(dy.contiguous(), S["s_mlp"])
+    dd1, g_w, g_b = _linear_backward(fc2.weight, S["d1"], dm)
+    _accumulate(fc2.weight, g_w), _accumulate(fc2.bias, g_b)
+    dd0 = ops.act_backward(S["d0"], dd1, act)
+    dh1, g_w, g_b = ops.dwconv3x3_backward(S["h1"], dd0, S["w9c"])
+    _accumulate(dw.weight, g_w), _accumulate(dw.bias, g_b)
+    dh0 = ops.act_backward(S["h0"], dh1, act)
+    dln2, g_w, g_b = _linear_backward(fc1.weight, S["ln2"], dh0)
+    _accumulate(fc1.weight, g_w), _accumulate(fc1.bias, g_b)
+    dx1n, g_g, g_b = ops.layernorm_backward(S["x1"].view(T, C), dln2.view(T, C), ly.norm2.weight.detach().contiguous(), S["eps"])
+    _accumulate(ly.norm2.weight, g_g), _accumulate(ly.norm2.bias, g_b)
+    dx1 = ops.drop_path_add(dx1n.view(B, H, W, C), S["ones"], skip=dy.contiguous())             # skip path + LayerNorm path
+    # ---- attention branch: x1 = x + s_attn * proj(att)
+    dpr = ops.drop_path_add(dx1, S["s_attn"])
+    datt, g_w, g_b = _linear_backward(a.proj.weight, S["att"], dpr)
+    _accumulate(a.proj.weight, g_w), _accumulate(a.proj.bias, g_b)
+    dqkv, g_t = ops.window_attention_backward(S["qkv"].view(T, 3 * C), datt.view(T, C), S["rpb"], B, H, W, ly.heads, ly.win, ly.shift, S["scale"])
+    _accumulate(a.relative_position_bias_table, g_t)
+    dln1, g_w, g_b = _linear_backward(S["wqkv"], S["ln1"], dqkv.view(B, H, W, 3 * C))
+    _accumulate(a.qkv.to_q.weight, g_w[:C]), _accumulate(a.qkv.to_q.bias, g_b[:C])
+    _accumulate(a.qkv.to_kv.weight, g_w[C:]), _accumulate(a.qkv.to_kv.bias, g_b[C:])
+    dxn, g_g, g_b = ops.layernorm_backward(S["x"].view(T, C), dln1.view(T, C), ly.norm1.weight.detach().contiguous(), S["eps"])
+    _accumulate(ly.norm1.weight, g_g), _accumulate(ly.norm1.bias, g_b)
+    return ops.drop_path_add(dxn.view(B, H, W, C), S["ones"], skip=dx1)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
 # learning-rate schedules and stochastic-depth rates of the training configuration (host arithmetic, no tensors)
 # ------------------------------------------------------------------------------------------------------------------------------
 def warmup_cosine_lr(epoch: int, lr_initial: float = 1e-4, nepoch: int = 250, warmup_epochs: int = 3, eta_min: float = 1e-6) -> float:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 20
+#define FBANET_ABI_VERSION 21
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -428,6 +428,16 @@ typedef struct fbanet_act_bwd_params {
   int32_t dtype, act, accumulate, _pad;
 } fbanet_act_bwd_params;
 
+/* Training-mode forward of a stand-alone activation: y = act(x) on n contiguous elements, the caller keeps the pre-activation x for
+ * fbanet_act_bwd_sm100 (inference applies activations inside the producing GEMM's epilogue).  alpha: device scalar, PReLU only. */
+typedef struct fbanet_act_fwd_params {
+  const void* x;
+  void* y;
+  const float* alpha;
+  int64_t n;
+  int32_t dtype, act;
+} fbanet_act_fwd_params;
+
 /* ---- SURVEY 8f-3, second set of backward bricks: the layers whose gradient is not a dense GEMM ---- */
 
 /* Backward of the LeFF depthwise 3x3 (layers/locally_enhanced_feed_forward.py:39-52; forward: fbanet_dwconv3x3_sm100 with act NONE,
@@ -534,6 +544,7 @@ int fbanet_adam_step_sm100(const fbanet_adam_params* p, void* stream);
 int fbanet_wgrad_sm100(const fbanet_wgrad_params* p, void* stream);
 int fbanet_layernorm_bwd_sm100(const fbanet_layernorm_bwd_params* p, void* stream);
 int fbanet_act_bwd_sm100(const fbanet_act_bwd_params* p, void* stream);
+int fbanet_act_fwd_sm100(const fbanet_act_fwd_params* p, void* stream);
 int fbanet_dwconv3x3_bwd_sm100(const fbanet_dwconv_bwd_params* p, void* stream);
 int fbanet_window_attention_bwd_sm100(const fbanet_attn_bwd_params* p, void* stream);
 int fbanet_faf_gate_bwd_sm100(const fbanet_faf_gate_bwd_params* p, void* stream);

@@ -63,6 +63,10 @@ def test_bad_params_are_rejected_without_a_gpu(lib):
     for fn, st in (("fbanet_dwconv3x3_bwd_sm100", _lib.DwconvBwdParams), ("fbanet_window_attention_bwd_sm100", _lib.AttnBwdParams),
                    ("fbanet_faf_gate_bwd_sm100", _lib.FafGateBwdParams), ("fbanet_drop_path_add_sm100", _lib.DropPathParams)):
         assert getattr(lib, fn)(ctypes.byref(st()), None) == -1, fn
+    f = _lib.ActFwdParams()
+    assert lib.fbanet_act_fwd_sm100(ctypes.byref(f), None) == -1
+    f.x, f.y, f.n, f.act = 1, 1, 8, 2                                                             # PReLU without its slope
+    assert lib.fbanet_act_fwd_sm100(ctypes.byref(f), None) == -1
     d = _lib.DwconvBwdParams()
     d.x, d.dy, d.weight, d.partial, d.N, d.H, d.W, d.C, d.dtype = 1, 1, 1, 1, 1, 4, 4, 8, 0      # no output requested
     assert lib.fbanet_dwconv3x3_bwd_sm100(ctypes.byref(d), None) == -1

@@ -218,3 +218,50 @@ def test_downsample4_data_gradient_through_forward_kernel(cuda, dtype, Ci, Co):
     dx = train.down4_dgrad(dy, w)
     assert dx.shape == (N, 2 * Ho, 2 * Wo, Ci)
     assert _rel(dx.float(), xr.grad.permute(0, 2, 3, 1)) < _tol(dtype), _rel(dx.float(), xr.grad.permute(0, 2, 3, 1))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_act_forward_keeps_the_epilogue_semantics(cuda, dtype):
+    """Stand-alone training-mode activation == the functions the GEMM epilogues apply (common.cuh apply_act)."""
+    from fbanet_b200 import _lib as L, ops
+    x = (torch.randn(3, 11, 13, 24, generator=torch.Generator().manual_seed(4)) * 2).to(dtype).to(cuda)
+    alpha = torch.tensor([0.25], device=cuda)
+    for act, fn in ((L.ACT_NONE, lambda v: v), (L.ACT_RELU, F.relu), (L.ACT_GELU_TANH, lambda v: F.gelu(v, approximate="tanh")),
+                    (L.ACT_GELU_ERF, F.gelu), (L.ACT_PRELU, lambda v: F.prelu(v, alpha))):
+        y = ops.act_forward(x, act, alpha=alpha if act == L.ACT_PRELU else None)
+        assert _rel(y.float(), fn(x.float())) < (1e-6 if dtype == torch.float32 else 4e-3), act
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-3), (torch.bfloat16, 1e-1)])
+def test_lewin_block_training_forward_backward_on_the_gpu(cuda, dtype, tol):
+    """train.lewin_forward_train / lewin_backward (the composition tests/test_host_logic.py checks with op stand-ins) on the real
+    kernels, against autograd through the oracle's LeWinLayer in float64 on the CPU (layers/fba_net.py:139-250, Appendix A-4);
+    fp32 is the parity path, bf16 rounds every saved activation (loose bound, relative to each gradient's largest entry)."""
+    from fbanet_b200 import train, ops
+    from fbanet_b200.model import _Layer
+    from oracle.fbanet_oracle import LeWinLayer
+    torch.manual_seed(5)
+    dim, res, heads, win, shift, B = 64, (20, 20), 2, 10, 5, 2
+    ly = _Layer(dim, res, heads, win, shift, 4.0)
+    with torch.no_grad():
+        for n, p in ly.named_parameters():
+            p.copy_(torch.randn_like(p) * (0.5 if p.dim() == 1 or "table" in n else 1.5 / p[0].numel() ** 0.5))
+            if n.endswith(("norm1.weight", "norm2.weight")):
+                p.add_(1.0)
+    ref = LeWinLayer(dim, res, heads, win, shift, 4.0, "tanh").double()
+    ref.load_state_dict(ly.state_dict())
+    x = torch.randn(B, *res, dim).to(dtype)
+    dy = torch.randn(B, *res, dim).to(dtype)
+    xr = x.double().requires_grad_(True)
+    yr = ref(xr.view(B, -1, dim)).view(B, *res, dim)
+    yr.backward(dy.double())
+    ly = ly.to(cuda)
+    before = ops.LAUNCHES
+    y, saved = train.lewin_forward_train(ly, x.to(cuda))
+    dx = train.lewin_backward(ly, saved, dy.to(cuda))
+    assert ops.LAUNCHES - before >= 30                                   # the CUDA ops ran (no torch fallback inside the composition)
+    assert _rel(y.float().cpu(), yr.detach()) < tol / 5, _rel(y.float().cpu(), yr.detach())
+    assert _rel(dx.float().cpu(), xr.grad) < tol, _rel(dx.float().cpu(), xr.grad)
+    got = dict(ly.named_parameters())
+    for n, pr in ref.named_parameters():
+        assert got[n].grad is not None and _rel(got[n].grad.cpu(), pr.grad) < tol, (n, _rel(got[n].grad.cpu(), pr.grad))

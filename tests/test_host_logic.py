@@ -285,3 +285,117 @@ def test_resampling_layer_gradients_through_forward_kernels():
     F.conv2d(xp.permute(0, 3, 1, 2), wz, bz, padding=1).backward(dz)
     dw, db = train.pixel_shuffle_wgrad_layout(wz.grad, bz.grad)
     assert torch.allclose(dw, wr.grad, atol=1e-10) and torch.allclose(db, br.grad, atol=1e-10)
+
+
+# ---- the LeWin block's training forward / backward composition (train.lewin_forward_train / lewin_backward) on the CPU -----------
+# Every C-ABI op the composition calls is replaced by a torch stand-in with the SAME signature and contract (each real op is pinned
+# to exactly that contract by its own -m gpu test); what this checks is the composition: which activation feeds which brick, the
+# residual / DropPath gradient sums, where each parameter gradient lands.  Reference: autograd through the oracle's LeWinLayer.
+def _install_op_standins(monkeypatch):
+    import torch
+    import torch.nn.functional as F
+    from fbanet_b200 import ops, _lib as L
+    from test_gpu_train_spatial import _attention_reference
+
+    def act_fn(act):
+        return {L.ACT_NONE: lambda v: v, L.ACT_RELU: F.relu, L.ACT_GELU_TANH: lambda v: F.gelu(v, approximate="tanh"), L.ACT_GELU_ERF: F.gelu}[act]
+
+    def grad_of(fn, inputs, dy):
+        leaves = [t.detach().clone().requires_grad_(True) for t in inputs]
+        fn(*leaves).backward(dy)
+        return [t.grad for t in leaves]
+
+    def conv_gemm(srcs, weight, out, *, bias=None, act=L.ACT_NONE, **kw):
+        assert len(srcs) == 1 and not kw and out.shape == (*srcs[0].shape[:3], weight.shape[0])
+        y = srcs[0] @ weight.t()
+        out.copy_(act_fn(act)(y + bias if bias is not None else y))
+        return out
+
+    def conv_wgrad(x, dy, kh=1, kw=1, stride=1, pad=0):
+        assert kh == 1 and kw == 1
+        return torch.einsum("nhwo,nhwi->oi", dy, x)[:, :, None, None].contiguous(), dy.sum((0, 1, 2))
+
+    def window_attention(qkv, table, B, H, W, heads, win, shift, scale):
+        return _attention_reference(qkv, table, B, H, W, qkv.shape[1] // 3, heads, win, shift, scale)
+
+    def window_attention_backward(qkv, dout, table, B, H, W, heads, win, shift, scale):
+        C = qkv.shape[1] // 3
+        return tuple(grad_of(lambda q, t: _attention_reference(q, t, B, H, W, C, heads, win, shift, scale), [qkv, table], dout))
+
+    def dwconv3x3(x, w9c, b, act):
+        C = x.shape[-1]
+        return act_fn(act)(F.conv2d(x.permute(0, 3, 1, 2), w9c.t().reshape(C, 1, 3, 3), b, padding=1, groups=C)).permute(0, 2, 3, 1).contiguous()
+
+    def dwconv3x3_backward(x, dy, w9c):
+        C = x.shape[-1]
+        gx, gw, gb = grad_of(lambda a, w, b: F.conv2d(a.permute(0, 3, 1, 2), w, b, padding=1, groups=C).permute(0, 2, 3, 1),
+                             [x, w9c.t().reshape(C, 1, 3, 3), torch.zeros(C, dtype=x.dtype)], dy)
+        return gx, gw, gb
+
+    def layernorm_backward(x, dy, gamma, eps=1e-5):
+        return tuple(grad_of(lambda a, g, b: F.layer_norm(a, (a.shape[1],), g, b, eps), [x, gamma, torch.zeros_like(gamma)], dy))
+
+    def drop_path_add(x, scale, skip=None):
+        v = x * scale.view(-1, *([1] * (x.dim() - 1)))
+        return v if skip is None else skip + v
+
+    monkeypatch.setattr(ops, "conv_gemm", conv_gemm)
+    monkeypatch.setattr(ops, "conv_wgrad", conv_wgrad)
+    monkeypatch.setattr(ops, "layernorm", lambda x, g, b, eps=1e-5: F.layer_norm(x, (x.shape[1],), g, b, eps))
+    monkeypatch.setattr(ops, "layernorm_backward", layernorm_backward)
+    monkeypatch.setattr(ops, "window_attention", window_attention)
+    monkeypatch.setattr(ops, "window_attention_backward", window_attention_backward)
+    monkeypatch.setattr(ops, "dwconv3x3", dwconv3x3)
+    monkeypatch.setattr(ops, "dwconv3x3_backward", dwconv3x3_backward)
+    monkeypatch.setattr(ops, "act_forward", lambda x, act: act_fn(act)(x))
+    monkeypatch.setattr(ops, "act_backward", lambda x, dy, act: grad_of(act_fn(act), [x], dy)[0])
+    monkeypatch.setattr(ops, "drop_path_add", drop_path_add)
+
+
+@pytest.mark.parametrize("shift", [0, 2])
+def test_lewin_training_step_composition_matches_autograd_of_the_oracle_layer(monkeypatch, shift):
+    import torch
+    from fbanet_b200 import train
+    from fbanet_b200.model import _Layer
+    from oracle.fbanet_oracle import LeWinLayer
+    _install_op_standins(monkeypatch)
+    torch.manual_seed(3)
+    dim, res, heads, win, B = 16, (8, 8), 2, 4, 3
+    ly = _Layer(dim, res, heads, win, shift, 4.0).double()
+    with torch.no_grad():
+        for p in ly.parameters():
+            p.copy_(torch.randn_like(p) * 0.3)
+    ref = LeWinLayer(dim, res, heads, win, shift, 4.0, "tanh").double()
+    ref.load_state_dict(ly.state_dict())
+    x = torch.randn(B, *res, dim, dtype=torch.float64)
+    dy = torch.randn_like(x)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr.view(B, -1, dim)).view_as(x)
+    yr.backward(dy)
+    y, saved = train.lewin_forward_train(ly, x)
+    assert torch.allclose(y, yr.detach(), atol=1e-10)
+    dx = train.lewin_backward(ly, saved, dy)
+    assert torch.allclose(dx, xr.grad, atol=1e-9)
+    names = dict(ly.named_parameters())
+    assert len(names) == 17
+    for n, pr in ref.named_parameters():
+        assert names[n].grad is not None and torch.allclose(names[n].grad, pr.grad, atol=1e-8), n
+    # gradients ACCUMULATE (flat gradient buffer semantics): a second backward doubles them
+    train.lewin_backward(ly, saved, dy)
+    for n, pr in ref.named_parameters():
+        assert torch.allclose(names[n].grad, 2 * pr.grad, atol=1e-8), n
+    # DropPath: a burst whose two branches are dropped passes x and dy through untouched and contributes nothing to the parameters
+    for p in ly.parameters():
+        p.grad = None
+    s = torch.tensor([1.0, 0.0, 1.0], dtype=torch.float64)
+    y2, saved2 = train.lewin_forward_train(ly, x, s_attn=s / 0.75, s_mlp=s / 0.75)
+    dx2 = train.lewin_backward(ly, saved2, dy)
+    assert torch.equal(y2[1], x[1]) and torch.equal(dx2[1], dy[1])
+    keep = [0, 2]
+    for p in ly.parameters():
+        p.grad, p.gsave = None, p.grad.clone()
+    y3, saved3 = train.lewin_forward_train(ly, x[keep].contiguous(), s_attn=s[keep] / 0.75, s_mlp=s[keep] / 0.75)
+    train.lewin_backward(ly, saved3, dy[keep].contiguous())
+    assert torch.allclose(y3, y2[keep], atol=1e-12)
+    for n, p in ly.named_parameters():
+        assert torch.allclose(p.grad, p.gsave, atol=1e-9), n
