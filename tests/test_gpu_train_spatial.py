@@ -260,7 +260,7 @@ def test_lewin_block_training_forward_backward_on_the_gpu(cuda, dtype, tol):
     y, saved = train.lewin_forward_train(ly, x.to(cuda))
     dx = train.lewin_backward(ly, saved, dy.to(cuda))
     assert ops.LAUNCHES - before >= 30                                   # the CUDA ops ran (no torch fallback inside the composition)
-    assert _rel(y.float().cpu(), yr.detach()) < tol / 5, _rel(y.float().cpu(), yr.detach())
+    assert _rel(y.float().cpu(), yr.detach()) < (2e-4 if dtype == torch.float32 else 4e-2), _rel(y.float().cpu(), yr.detach())
     assert _rel(dx.float().cpu(), xr.grad) < tol, _rel(dx.float().cpu(), xr.grad)
     got = dict(ly.named_parameters())
     for n, pr in ref.named_parameters():
