@@ -187,6 +187,7 @@ class BaseModel(nn.Module):
         E, S, w = embed_dim, img_size, window_length
         self.num_frames, self.img_size, self.in_channels, self.embed_dim = num_frames, S, in_channels, E
         self.window_length, self.qk_scale = w, qk_scale
+        self.depths, self.drop_path_rate = tuple(depths), drop_path_rate     # training configuration (train.drop_path_rates)
         self.compute_dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[dtype]
         self.gelu_act = {"tanh": L.ACT_GELU_TANH, "erf": L.ACT_GELU_ERF}[gelu]
         self.impl = impl

@@ -345,6 +345,108 @@ def lewin_backward(ly, saved: dict, dy: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------------------------------------
+# reverse-mode tape over the C-ABI ops, and the LeWin hourglass (models/fba_net.py:271-287) on it
+# ------------------------------------------------------------------------------------------------------------------------------
+class Tape:
+    """Minimal reverse-mode tape: the training forward records, per composite op, its output tensor and a closure that maps the
+    output's gradient to ``[(input tensor, gradient), ...]`` (parameter gradients are accumulated into ``.grad`` inside the closure).
+    :meth:`backward` walks the records in reverse; a tensor consumed by several ops (skip connections) gets the SUM of its
+    gradients, formed by ``fbanet_drop_path_add`` with unit scales.  No torch autograd, no torch arithmetic: torch only owns the
+    buffers (``torch.cat`` / slicing of the concat inputs are copies)."""
+
+    def __init__(self):
+        self.records = []
+
+    def record(self, out: torch.Tensor, backward_fn) -> torch.Tensor:
+        self.records.append((out, backward_fn))
+        return out
+
+    def backward(self, out: torch.Tensor, dout: torch.Tensor) -> dict:
+        from . import ops
+        grads = {id(out): dout}
+        for o, fn in reversed(self.records):
+            g = grads.pop(id(o), None)
+            if g is None:
+                continue                                                   # this output did not reach the loss
+            for t, gt in fn(g):
+                gt = gt.contiguous()
+                if id(t) in grads:
+                    ones = torch.ones(gt.shape[0], device=gt.device, dtype=torch.float32)
+                    grads[id(t)] = ops.drop_path_add(gt, ones, skip=grads[id(t)].contiguous())
+                else:
+                    grads[id(t)] = gt
+        return grads                                                       # what is left: gradients of the tape's inputs, by id()
+
+
+def _t_block(tape: Tape, block, x: torch.Tensor, rates, generator, training: bool) -> torch.Tensor:
+    """A ``_Block`` (``blocks/fba_net.py:35-65``): its LeWin layers in sequence, each with its own stochastic-depth rate."""
+    for ly, rate in zip(block.blocks, rates):
+        B = x.shape[0]
+        s1 = drop_path_scales(B, rate, generator, x.device) if (training and rate > 0.0) else None
+        s2 = drop_path_scales(B, rate, generator, x.device) if (training and rate > 0.0) else None
+        y, saved = lewin_forward_train(ly, x, s1, s2)
+        x = tape.record(y, (lambda ly, saved, xin: (lambda g: [(xin, lewin_backward(ly, saved, g))]))(ly, saved, x))
+    return x
+
+
+def _t_down(tape: Tape, conv, x: torch.Tensor) -> torch.Tensor:
+    """``DownsampleLayer`` (``layers/downsample.py:19-30``): conv 4x4 stride 2 pad 1."""
+    from . import ops
+    N, H, W, _ = x.shape
+    out = torch.empty((N, H // 2, W // 2, conv.weight.shape[0]), device=x.device, dtype=x.dtype)
+    w = conv.weight.detach().permute(0, 2, 3, 1).reshape(conv.weight.shape[0], -1).to(x.dtype).contiguous()
+    ops.conv_gemm([x], w, out, kh=4, kw=4, stride=2, pad=1, bias=conv.bias.detach().contiguous())
+
+    def bwd(g):
+        dw, db = ops.conv_wgrad(x, g, 4, 4, 2, 1)
+        _accumulate(conv.weight, dw), _accumulate(conv.bias, db)
+        return [(x, down4_dgrad(g, conv.weight))]
+    return tape.record(out, bwd)
+
+
+def _t_up(tape: Tape, deconv, x: torch.Tensor) -> torch.Tensor:
+    """``UpsampleLayer`` (``layers/upsample.py:19-30``): ConvTranspose 2x2 stride 2 as a per-pixel GEMM with the 2x2 scatter store."""
+    from . import ops, _lib as L
+    N, H, W, _ = x.shape
+    Co = deconv.weight.shape[1]
+    out = torch.empty((N, 2 * H, 2 * W, Co), device=x.device, dtype=x.dtype)
+    w = deconv.weight.detach().permute(2, 3, 1, 0).reshape(-1, deconv.weight.shape[0]).to(x.dtype).contiguous()   # rows (i,j,co)
+    ops.conv_gemm([x], w, out, bias=deconv.bias.detach().repeat(4).contiguous(), store_mode=L.STORE_CONVT2)
+
+    def bwd(g):
+        dw, db = convT2_wgrad(x, g)
+        _accumulate(deconv.weight, dw), _accumulate(deconv.bias, db)
+        return [(x, convT2_dgrad(g, deconv.weight))]
+    return tape.record(out, bwd)
+
+
+def _t_cat(tape: Tape, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Channel concat ``[a | b]`` of two channels-last maps (``models/fba_net.py:282,286``); its backward is the two slices."""
+    Ca = a.shape[-1]
+    return tape.record(torch.cat([a, b], -1), lambda g: [(a, g[..., :Ca]), (b, g[..., Ca:])])
+
+
+def hourglass_forward_train(model, hg: str, y: torch.Tensor, generator: Optional[torch.Generator] = None, training: bool = True):
+    """Training-mode forward of the first LeWin hourglass (``models/fba_net.py:271-287``; ``hg = "HG1"``): encoder blocks, 4x4 s2
+    downsamples, bottleneck, 2x2 transposed-conv upsamples concatenated with the encoder outputs, decoder blocks -- ten LeWin layers
+    with the per-layer DropPath rates of :func:`drop_path_rates`.  ``y`` ``[B,S,S,E]`` channels-last.  Returns ``(deconv1, tape)``;
+    ``tape.backward(deconv1, d_deconv1)`` accumulates every parameter gradient and returns ``{id(y): dy}``."""
+    g = lambda n: getattr(model, n)
+    rates = drop_path_rates(tuple(model.depths), model.drop_path_rate)
+    tape = Tape()
+    conv0 = _t_block(tape, g(f"{hg}_encoderlayer_0"), y, rates["encoderlayer_0"], generator, training)
+    pool0 = _t_down(tape, g(f"{hg}_downsample_0").conv[0], conv0)
+    conv1 = _t_block(tape, g(f"{hg}_encoderlayer_1"), pool0, rates["encoderlayer_1"], generator, training)
+    pool1 = _t_down(tape, g(f"{hg}_downsample_1").conv[0], conv1)
+    conv2 = _t_block(tape, g(f"conv_{hg}"), pool1, rates["conv"], generator, training)
+    up0 = _t_up(tape, g(f"{hg}_upsample_0").deconv[0], conv2)
+    deconv0 = _t_block(tape, g(f"{hg}_decoderlayer_0"), _t_cat(tape, up0, conv1), rates["decoderlayer_0"], generator, training)
+    up1 = _t_up(tape, g(f"{hg}_upsample_1").deconv[0], deconv0)
+    deconv1 = _t_block(tape, g(f"{hg}_decoderlayer_1"), _t_cat(tape, up1, conv0), rates["decoderlayer_1"], generator, training)
+    return deconv1, tape
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
 # learning-rate schedules and stochastic-depth rates of the training configuration (host arithmetic, no tensors)
 # ------------------------------------------------------------------------------------------------------------------------------
 def warmup_cosine_lr(epoch: int, lr_initial: float = 1e-4, nepoch: int = 250, warmup_epochs: int = 3, eta_min: float = 1e-6) -> float:

@@ -265,3 +265,44 @@ def test_lewin_block_training_forward_backward_on_the_gpu(cuda, dtype, tol):
     got = dict(ly.named_parameters())
     for n, pr in ref.named_parameters():
         assert got[n].grad is not None and _rel(got[n].grad.cpu(), pr.grad) < tol, (n, _rel(got[n].grad.cpu(), pr.grad))
+
+
+def test_hourglass_training_forward_backward_on_the_gpu(cuda):
+    """train.hourglass_forward_train + Tape.backward on the real kernels (fp32 parity path): ten LeWin layers, 4x4 s2 downsamples,
+    transposed-conv upsamples, skip concats -- against autograd through the oracle's first hourglass in float64 on the CPU
+    (models/fba_net.py:271-287).  The composition itself is checked with op stand-ins in tests/test_host_logic.py."""
+    from fbanet_b200 import train, ops
+    from fbanet_b200.model import BaseModel
+    from oracle.fbanet_oracle import OracleBaseModel
+    cfg = dict(num_frames=2, img_size=40, embed_dim=32, window_length=10)
+    m = BaseModel(token_mlp="leff", dtype="fp32", seed=1, **cfg)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "relative_position_bias_table" in n or (p.dim() == 1 and "norm" not in n):
+                p.copy_(torch.randn_like(p) * 0.2)
+    o = OracleBaseModel(**cfg).double()
+    assert not o.load_state_dict(m.state_dict(), strict=False).missing_keys
+    B, S, E = 2, 40, 32
+    y = torch.randn(B, S, S, E, generator=torch.Generator().manual_seed(2))
+    dout = torch.randn(B, S, S, 2 * E, generator=torch.Generator().manual_seed(3))
+    yr = y.double().requires_grad_(True)
+    ref, _ = o._hourglass("HG1", yr.view(B, S * S, E))
+    ref.backward(dout.double().view(B, S * S, 2 * E))
+    m = m.to(cuda)
+    for p in m.parameters():
+        p.requires_grad_(True)
+        p.grad = None
+    yd = y.to(cuda)
+    before = ops.LAUNCHES
+    out, tape = train.hourglass_forward_train(m, "HG1", yd, training=False)
+    grads = tape.backward(out, dout.to(cuda))
+    assert ops.LAUNCHES - before >= 10 * 30
+    assert _rel(out.cpu().view(B, S * S, 2 * E), ref.detach()) < 5e-4
+    assert set(grads) == {id(yd)} and _rel(grads[id(yd)].cpu(), yr.grad.view(B, S, S, E)) < 2e-3
+    got, n_checked = dict(m.named_parameters()), 0
+    for n, pr in o.named_parameters():
+        if pr.grad is None:
+            continue
+        assert got[n].grad is not None and _rel(got[n].grad.cpu(), pr.grad) < 2e-3, (n, _rel(got[n].grad.cpu(), pr.grad))
+        n_checked += 1
+    assert n_checked == 10 * 17 + 4 * 2

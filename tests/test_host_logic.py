@@ -399,3 +399,83 @@ def test_lewin_training_step_composition_matches_autograd_of_the_oracle_layer(mo
     assert torch.allclose(y3, y2[keep], atol=1e-12)
     for n, p in ly.named_parameters():
         assert torch.allclose(p.grad, p.gsave, atol=1e-9), n
+
+
+def _install_conv_standins(monkeypatch):
+    """General conv stand-ins on top of :func:`_install_op_standins`: the implicit GEMM by its packed-weight contract (any k / stride /
+    pad, ConvT-style scatter store), space-to-depth, and the weight gradient via autograd of the same conv."""
+    import torch
+    import torch.nn.functional as F
+    from fbanet_b200 import ops, _lib as L
+
+    def conv_gemm(srcs, weight, out, *, kh=1, kw=1, stride=1, pad=0, bias=None, act=L.ACT_NONE, store_mode=L.STORE_NHWC):
+        assert len(srcs) == 1 and act == L.ACT_NONE
+        src = srcs[0]
+        w = weight.reshape(weight.shape[0], kh, kw, src.shape[-1]).permute(0, 3, 1, 2)
+        g = F.conv2d(src.permute(0, 3, 1, 2), w, bias, stride=stride, padding=pad).permute(0, 2, 3, 1)
+        if store_mode == L.STORE_CONVT2:
+            N, H, W, C4 = g.shape
+            g = g.reshape(N, H, W, 2, 2, C4 // 4).permute(0, 1, 3, 2, 4, 5).reshape(N, 2 * H, 2 * W, C4 // 4)
+        assert out.shape == g.shape, (out.shape, g.shape)
+        out.copy_(g)
+        return out
+
+    def conv_wgrad(x, dy, kh=1, kw=1, stride=1, pad=0):
+        w = torch.zeros(dy.shape[-1], x.shape[-1], kh, kw, dtype=x.dtype, requires_grad=True)
+        b = torch.zeros(dy.shape[-1], dtype=x.dtype, requires_grad=True)
+        F.conv2d(x.permute(0, 3, 1, 2), w, b, stride=stride, padding=pad).backward(dy.permute(0, 3, 1, 2))
+        return w.grad, b.grad
+
+    monkeypatch.setattr(ops, "conv_gemm", conv_gemm)
+    monkeypatch.setattr(ops, "conv_wgrad", conv_wgrad)
+    monkeypatch.setattr(ops, "space_to_depth", lambda x: _emu_s2d(x).contiguous())
+
+
+def test_hourglass_training_composition_matches_autograd_of_the_oracle(monkeypatch):
+    """train.hourglass_forward_train + Tape.backward (ten LeWin layers, two 4x4 s2 downsamples, two transposed-conv upsamples, two
+    skip concats whose sources receive summed gradients) against autograd through the oracle's first hourglass
+    (models/fba_net.py:271-287), op stand-ins as above; then DropPath in training mode: reproducible from the generator, and a rate
+    of zero everywhere reproduces the eval forward."""
+    import torch
+    from fbanet_b200 import train
+    from fbanet_b200.model import BaseModel
+    from oracle.fbanet_oracle import OracleBaseModel
+    _install_op_standins(monkeypatch)
+    _install_conv_standins(monkeypatch)
+    cfg = dict(num_frames=2, img_size=16, embed_dim=16, window_length=4)
+    m = BaseModel(token_mlp="leff", dtype="fp32", seed=1, **cfg).double()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "relative_position_bias_table" in n or (p.dim() == 1 and "norm" not in n):
+                p.copy_(torch.randn_like(p) * 0.2)                          # biases / tables away from their zero-ish init
+    o = OracleBaseModel(**cfg).double()
+    missing = o.load_state_dict(m.state_dict(), strict=False)
+    assert not missing.missing_keys, missing.missing_keys
+    B, S, E = 2, 16, 16
+    y = torch.randn(B, S, S, E, dtype=torch.float64)
+    dout = torch.randn(B, S, S, 2 * E, dtype=torch.float64)
+    yr = y.clone().requires_grad_(True)
+    ref, _ = o._hourglass("HG1", yr.view(B, S * S, E))
+    ref.backward(dout.view(B, S * S, 2 * E))
+    for p in m.parameters():
+        p.requires_grad_(True)
+        p.grad = None
+    out, tape = train.hourglass_forward_train(m, "HG1", y, training=False)
+    assert torch.allclose(out.view(B, S * S, 2 * E), ref.detach(), atol=1e-9)
+    grads = tape.backward(out, dout)
+    assert set(grads) == {id(y)} and torch.allclose(grads[id(y)], yr.grad, atol=1e-8)
+    got, n_checked = dict(m.named_parameters()), 0
+    for n, pr in o.named_parameters():
+        if pr.grad is None:
+            assert got[n].grad is None, n                                 # nothing outside the hourglass was touched
+            continue
+        assert got[n].grad is not None and torch.allclose(got[n].grad, pr.grad, atol=1e-7), n
+        n_checked += 1
+    assert n_checked == 10 * 17 + 4 * 2                                   # ten LeWin layers, two downsamples, two upsamples
+    # training mode: per-layer rates linspace(0, 0.1, 8) -> the first layer never drops, the rest draw from the generator
+    a, _ = train.hourglass_forward_train(m, "HG1", y, generator=torch.Generator().manual_seed(7))
+    b, _ = train.hourglass_forward_train(m, "HG1", y, generator=torch.Generator().manual_seed(7))
+    assert torch.equal(a, b) and not torch.allclose(a, out)
+    m.drop_path_rate = 0.0
+    c, _ = train.hourglass_forward_train(m, "HG1", y, generator=torch.Generator().manual_seed(7))
+    assert torch.equal(c, out)
