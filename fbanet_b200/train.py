@@ -426,6 +426,92 @@ def _t_cat(tape: Tape, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return tape.record(torch.cat([a, b], -1), lambda g: [(a, g[..., :Ca]), (b, g[..., Ca:])])
 
 
+def _t_conv(tape: Tape, conv, x: torch.Tensor, act: int = 0, alpha: Optional[torch.nn.Parameter] = None) -> torch.Tensor:
+    """Stride-1 ``k x k`` convolution (``layers/conv2d.py:12-46``; ``k`` = 1 or 3, padding ``k // 2``) + bias, optionally followed by
+    ReLU / PReLU (``alpha``: the scalar slope parameter) as a stand-alone pass that keeps the pre-activation."""
+    from . import ops, _lib as L
+    Co, Ci, k, _ = conv.weight.shape
+    N, H, W, _ = x.shape
+    pre = torch.empty((N, H, W, Co), device=x.device, dtype=x.dtype)
+    w = conv.weight.detach().permute(0, 2, 3, 1).reshape(Co, -1).to(x.dtype).contiguous()
+    ops.conv_gemm([x], w, pre, kh=k, kw=k, pad=k // 2, bias=conv.bias.detach().contiguous())
+    if act == L.ACT_NONE:
+        y = pre
+    elif act == L.ACT_PRELU:
+        y = ops.act_forward(pre, act, alpha=alpha.detach().contiguous())
+    else:
+        y = ops.act_forward(pre, act)
+
+    def bwd(g):
+        if act == L.ACT_PRELU:
+            g, dalpha = ops.act_backward(pre, g, act, alpha=alpha.detach().contiguous())
+            _accumulate(alpha, dalpha)
+        elif act != L.ACT_NONE:
+            g = ops.act_backward(pre, g, act)
+        dw, db = ops.conv_wgrad(x, g, k, k, 1, k // 2)
+        _accumulate(conv.weight, dw), _accumulate(conv.bias, db)
+        dx = torch.empty_like(x)
+        ops.conv_gemm([g], dgrad_weight(conv.weight, g.dtype), dx, kh=k, kw=k, pad=k - 1 - k // 2)
+        return [(x, dx)]
+    return tape.record(y, bwd)
+
+
+def _t_add(tape: Tape, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Residual sum ``a + b`` (``fbanet_drop_path_add`` with unit scales); both operands receive the output's gradient."""
+    from . import ops
+    ones = torch.ones(a.shape[0], device=a.device, dtype=torch.float32)
+    return tape.record(ops.drop_path_add(b, ones, skip=a), lambda g: [(a, g), (b, g)])
+
+
+def _t_resblock(tape: Tape, rb, x: torch.Tensor) -> torch.Tensor:
+    """``ResBlock`` (``blocks/residual.py:21-29``): ``x + conv(relu(conv(x)))``."""
+    from . import _lib as L
+    return _t_add(tape, x, _t_conv(tape, rb.body[2], _t_conv(tape, rb.body[0], x, L.ACT_RELU)))
+
+
+def _t_faf_gate(tape: Tape, fu, feat: torch.Tensor) -> torch.Tensor:
+    """``FAFBlock.compute_guided_aligned_features`` (``blocks/federated_affinity_fusion.py:67-108``): feat ``[B,F,H,W,E]`` -> gated
+    features ``[B,H,W,F*E]`` (pixel-major, the K axis of the 1x1 fusion conv).  The scores ``s_f = wsum (*) feat_f`` the backward
+    needs for ``sign(s_f - s_0)`` come from the 3x3 implicit GEMM: hi / lo bf16 rows on the tensor cores (bf16), or a 4-row padded
+    fp32 GEMM whose first column is the score (fp32)."""
+    from . import ops
+    B, Fr, H, W, E = feat.shape
+    w1 = fu.temporal_attn1.weight
+    wsum = w1.detach().double().sum(0).permute(1, 2, 0).reshape(9, E).to(torch.float32).contiguous()
+    gate, gated = ops.faf_gate(feat, wsum, want_gate=True, want_gated=True)
+    if feat.dtype == torch.bfloat16:
+        score = ops.faf_scores(feat, ops.faf_score_weight(wsum, feat.dtype))                     # [B*F,H,W,2]
+    else:
+        wpad = torch.zeros((4, 9 * E), device=feat.device, dtype=feat.dtype)
+        wpad[0] = wsum.reshape(-1)
+        s4 = torch.empty((B * Fr, H, W, 4), device=feat.device, dtype=feat.dtype)
+        ops.conv_gemm([feat.view(B * Fr, H, W, E)], wpad, s4, kh=3, kw=3, pad=1)
+        score = s4[..., 0].float().contiguous()
+
+    def bwd(g):
+        dfeat, dwsum = ops.faf_gate_backward(feat, g.reshape(B, H, W, Fr * E), gate, score, wsum)
+        _accumulate(w1, ops.faf_weight_grads(dwsum, w1.shape[0]))          # temporal_attn0 and both biases cancel: zero gradient
+        return [(feat, dfeat)]
+    return tape.record(gated, bwd)
+
+
+def faf_forward_train(fu, feat: torch.Tensor):
+    """Training-mode forward of the whole ``FAFBlock`` (``blocks/federated_affinity_fusion.py:166-182``: gate, 1x1 fusion + PReLU,
+    the residual-block hourglass with its 4x4 s2 / transposed-conv resampling, ``fusion_tail`` and the skip) on a :class:`Tape`.
+    ``fu``: the model's ``fusion`` module; ``feat`` ``[B,F,H,W,E]`` channels-last.  Returns ``(fused [B,H,W,E], tape)``."""
+    from . import _lib as L
+    tape = Tape()
+    gated = _t_faf_gate(tape, fu, feat)
+    z = _t_conv(tape, fu.feature_fusion[0], gated, L.ACT_PRELU, fu.feature_fusion[1].weight)
+    rb = fu.res_blocks
+    r0 = _t_resblock(tape, rb[0][1], _t_resblock(tape, rb[0][0], z))
+    r1 = _t_resblock(tape, rb[1][1], _t_resblock(tape, rb[1][0], _t_down(tape, fu.downsample0, r0)))
+    r2 = _t_resblock(tape, rb[2][1], _t_resblock(tape, rb[2][0], _t_down(tape, fu.downsample1, r1)))
+    r3 = _t_resblock(tape, rb[3][1], _t_resblock(tape, rb[3][0], _t_cat(tape, _t_up(tape, fu.upsample0, r2), r1)))
+    r4 = _t_resblock(tape, rb[4][1], _t_resblock(tape, rb[4][0], _t_cat(tape, _t_up(tape, fu.upsample1, r3), r0)))
+    return _t_add(tape, _t_conv(tape, fu.fusion_tail, r4), z), tape
+
+
 def hourglass_forward_train(model, hg: str, y: torch.Tensor, generator: Optional[torch.Generator] = None, training: bool = True):
     """Training-mode forward of the first LeWin hourglass (``models/fba_net.py:271-287``; ``hg = "HG1"``): encoder blocks, 4x4 s2
     downsamples, bottleneck, 2x2 transposed-conv upsamples concatenated with the encoder outputs, decoder blocks -- ten LeWin layers

@@ -306,3 +306,39 @@ def test_hourglass_training_forward_backward_on_the_gpu(cuda):
         assert got[n].grad is not None and _rel(got[n].grad.cpu(), pr.grad) < 2e-3, (n, _rel(got[n].grad.cpu(), pr.grad))
         n_checked += 1
     assert n_checked == 10 * 17 + 4 * 2
+
+
+def test_faf_block_training_forward_backward_on_the_gpu(cuda):
+    """train.faf_forward_train + Tape.backward on the real kernels (fp32 parity path): gate, 1x1 fusion + PReLU, ten ResBlocks with
+    4x4 s2 / transposed-conv resampling, fusion_tail, skip -- against autograd through the oracle's FAFBlock as written, float64 on
+    the CPU (blocks/federated_affinity_fusion.py:166-182).  Composition checked with op stand-ins in tests/test_host_logic.py."""
+    from fbanet_b200 import train, ops
+    from fbanet_b200.model import _FAF
+    from oracle.fbanet_oracle import FAFBlock
+    torch.manual_seed(12)
+    E, Fr, B, S = 32, 3, 2, 16
+    fu = _FAF(E, Fr)
+    with torch.no_grad():
+        for p in fu.parameters():
+            p.copy_(torch.randn_like(p) * (0.3 if p.dim() == 1 else 0.7 / p[0].numel() ** 0.5))
+    ref = FAFBlock(E, Fr).double()
+    ref.load_state_dict(fu.state_dict())
+    feat = torch.randn(B, Fr, S, S, E)
+    dout = torch.randn(B, S, S, E)
+    fr = feat.double().requires_grad_(True)
+    yr = ref(fr.permute(0, 1, 4, 2, 3))
+    yr.backward(dout.double().permute(0, 3, 1, 2))
+    fu = fu.to(cuda)
+    fd = feat.to(cuda)
+    before = ops.LAUNCHES
+    out, tape = train.faf_forward_train(fu, fd)
+    grads = tape.backward(out, dout.to(cuda))
+    assert ops.LAUNCHES - before >= 100
+    assert _rel(out.cpu(), yr.detach().permute(0, 2, 3, 1)) < 5e-4
+    assert set(grads) == {id(fd)} and _rel(grads[id(fd)].cpu(), fr.grad) < 2e-3, _rel(grads[id(fd)].cpu(), fr.grad)
+    got = dict(fu.named_parameters())
+    for n, pr in ref.named_parameters():
+        if n.startswith("temporal_attn0") or n == "temporal_attn1.bias":
+            assert got[n].grad is None, n
+            continue
+        assert got[n].grad is not None and _rel(got[n].grad.cpu(), pr.grad) < 2e-3, (n, _rel(got[n].grad.cpu(), pr.grad))

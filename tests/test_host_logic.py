@@ -347,8 +347,34 @@ def _install_op_standins(monkeypatch):
     monkeypatch.setattr(ops, "window_attention_backward", window_attention_backward)
     monkeypatch.setattr(ops, "dwconv3x3", dwconv3x3)
     monkeypatch.setattr(ops, "dwconv3x3_backward", dwconv3x3_backward)
-    monkeypatch.setattr(ops, "act_forward", lambda x, act: act_fn(act)(x))
-    monkeypatch.setattr(ops, "act_backward", lambda x, dy, act: grad_of(act_fn(act), [x], dy)[0])
+    def act_forward(x, act, alpha=None):
+        return F.prelu(x, alpha) if act == L.ACT_PRELU else act_fn(act)(x)
+
+    def act_backward(x, dy, act, alpha=None):
+        if act == L.ACT_PRELU:
+            return tuple(grad_of(F.prelu, [x, alpha], dy))
+        return grad_of(act_fn(act), [x], dy)[0]
+
+    def gate_forward(feat, wsum):                                            # feat [B,F,H,W,C], wsum [9,C]: the collapsed gate
+        B, Fr, H, W, C = feat.shape
+        w = wsum.t().reshape(1, C, 3, 3).to(feat.dtype).contiguous()
+        sc = F.conv2d(feat.reshape(B * Fr, H, W, C).permute(0, 3, 1, 2), w, None, padding=1).view(B, Fr, H, W)
+        gate = torch.sigmoid((sc[:, 1:] - sc[:, :1]).abs())
+        gated = torch.cat([feat[:, :1], feat[:, 1:] * gate[..., None]], 1)
+        return gate, gated.permute(0, 2, 3, 1, 4).reshape(B, H, W, Fr * C)
+
+    def faf_gate(feat, wsum, want_gate=True, want_gated=False, score=None):
+        gate, gated = gate_forward(feat, wsum)
+        return (gate, gated) if (want_gate and want_gated) else (gated if want_gated else gate)
+
+    def faf_gate_backward(feat, dgated, gate, score, wsum):
+        gf, gw = grad_of(lambda f, w: gate_forward(f, w)[1], [feat, wsum.to(feat.dtype)], dgated)
+        return gf, gw
+
+    monkeypatch.setattr(ops, "act_forward", act_forward)
+    monkeypatch.setattr(ops, "act_backward", act_backward)
+    monkeypatch.setattr(ops, "faf_gate", faf_gate)
+    monkeypatch.setattr(ops, "faf_gate_backward", faf_gate_backward)
     monkeypatch.setattr(ops, "drop_path_add", drop_path_add)
 
 
@@ -479,3 +505,42 @@ def test_hourglass_training_composition_matches_autograd_of_the_oracle(monkeypat
     m.drop_path_rate = 0.0
     c, _ = train.hourglass_forward_train(m, "HG1", y, generator=torch.Generator().manual_seed(7))
     assert torch.equal(c, out)
+
+
+def test_faf_block_training_composition_matches_autograd_of_the_oracle(monkeypatch):
+    """train.faf_forward_train + Tape.backward: the whole FAFBlock (gate, 1x1 fusion + PReLU(0.1), ten ResBlocks, 4x4 s2 / transposed
+    conv resampling, fusion_tail, skip) against autograd through the oracle's FAFBlock AS WRITTEN (two embedding convs): output,
+    d feat, every parameter gradient -- temporal_attn0 and both embedding biases must come out (numerically) zero in the reference
+    and untouched in the composition."""
+    import torch
+    from fbanet_b200 import train
+    from fbanet_b200.model import _FAF
+    from oracle.fbanet_oracle import FAFBlock
+    _install_op_standins(monkeypatch)
+    _install_conv_standins(monkeypatch)
+    torch.manual_seed(11)
+    E, Fr, B, S = 8, 3, 2, 8
+    fu = _FAF(E, Fr).double()
+    with torch.no_grad():
+        for p in fu.parameters():
+            p.copy_(torch.randn_like(p) * (0.3 if p.dim() == 1 else 0.7 / p[0].numel() ** 0.5))
+    ref = FAFBlock(E, Fr).double()
+    ref.load_state_dict(fu.state_dict())
+    feat = torch.randn(B, Fr, S, S, E, dtype=torch.float64)
+    dout = torch.randn(B, S, S, E, dtype=torch.float64)
+    fr = feat.clone().requires_grad_(True)
+    yr = ref(fr.permute(0, 1, 4, 2, 3))                                      # [B,E,S,S]
+    yr.backward(dout.permute(0, 3, 1, 2))
+    # the gate kernel's contract takes wsum in fp32, so even this float64 run carries one 2^-24 rounding: bounds are 1e-6 relative
+    def close(a, b):
+        return (a - b).abs().max().item() <= 1e-6 * b.abs().max().item()
+    out, tape = train.faf_forward_train(fu, feat)
+    assert close(out, yr.detach().permute(0, 2, 3, 1))
+    grads = tape.backward(out, dout)
+    assert set(grads) == {id(feat)} and close(grads[id(feat)], fr.grad)
+    got = dict(fu.named_parameters())
+    for n, pr in ref.named_parameters():
+        if n.startswith("temporal_attn0") or n == "temporal_attn1.bias":
+            assert pr.grad.abs().max().item() < 1e-12 and got[n].grad is None, n
+            continue
+        assert got[n].grad is not None and close(got[n].grad, pr.grad), n
