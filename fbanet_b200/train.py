@@ -32,9 +32,9 @@ class FlatParams:
         self.offsets, n = [], 0
         for p in self.params:
             self.offsets.append(n)
-            n += p.numel()
-        self.numel = n
-        self.data = torch.empty(n, dtype=torch.float32, device=dev)
+            n += (p.numel() + 3) // 4 * 4          # every parameter starts on a 16-byte boundary (vector loads of biases / tables)
+        self.numel = n                              # padding elements stay zero: zero gradient, zero update
+        self.data = torch.zeros(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -499,8 +499,12 @@ def faf_forward_train(fu, feat: torch.Tensor):
     """Training-mode forward of the whole ``FAFBlock`` (``blocks/federated_affinity_fusion.py:166-182``: gate, 1x1 fusion + PReLU,
     the residual-block hourglass with its 4x4 s2 / transposed-conv resampling, ``fusion_tail`` and the skip) on a :class:`Tape`.
     ``fu``: the model's ``fusion`` module; ``feat`` ``[B,F,H,W,E]`` channels-last.  Returns ``(fused [B,H,W,E], tape)``."""
-    from . import _lib as L
     tape = Tape()
+    return _faf_on_tape(tape, fu, feat), tape
+
+
+def _faf_on_tape(tape: Tape, fu, feat: torch.Tensor) -> torch.Tensor:
+    from . import _lib as L
     gated = _t_faf_gate(tape, fu, feat)
     z = _t_conv(tape, fu.feature_fusion[0], gated, L.ACT_PRELU, fu.feature_fusion[1].weight)
     rb = fu.res_blocks
@@ -509,7 +513,7 @@ def faf_forward_train(fu, feat: torch.Tensor):
     r2 = _t_resblock(tape, rb[2][1], _t_resblock(tape, rb[2][0], _t_down(tape, fu.downsample1, r1)))
     r3 = _t_resblock(tape, rb[3][1], _t_resblock(tape, rb[3][0], _t_cat(tape, _t_up(tape, fu.upsample0, r2), r1)))
     r4 = _t_resblock(tape, rb[4][1], _t_resblock(tape, rb[4][0], _t_cat(tape, _t_up(tape, fu.upsample1, r3), r0)))
-    return _t_add(tape, _t_conv(tape, fu.fusion_tail, r4), z), tape
+    return _t_add(tape, _t_conv(tape, fu.fusion_tail, r4), z)
 
 
 def hourglass_forward_train(model, hg: str, y: torch.Tensor, generator: Optional[torch.Generator] = None, training: bool = True):
@@ -517,19 +521,136 @@ def hourglass_forward_train(model, hg: str, y: torch.Tensor, generator: Optional
     downsamples, bottleneck, 2x2 transposed-conv upsamples concatenated with the encoder outputs, decoder blocks -- ten LeWin layers
     with the per-layer DropPath rates of :func:`drop_path_rates`.  ``y`` ``[B,S,S,E]`` channels-last.  Returns ``(deconv1, tape)``;
     ``tape.backward(deconv1, d_deconv1)`` accumulates every parameter gradient and returns ``{id(y): dy}``."""
+    tape = Tape()
+    return _hourglass_on_tape(tape, model, hg, y, None, generator, training)[0], tape
+
+
+def _hourglass_on_tape(tape: Tape, model, hg: str, y: torch.Tensor, prev, generator, training: bool):
+    """``prev``: ``(up0, conv1, up1, conv0)`` of the first hourglass -- the second one (``models/fba_net.py:294-310``) feeds its decoders
+    ``output_proj_HG2_k(cat[prev pair, own pair])`` (conv3x3 + PReLU) instead of the plain concat."""
+    from . import _lib as L
     g = lambda n: getattr(model, n)
     rates = drop_path_rates(tuple(model.depths), model.drop_path_rate)
-    tape = Tape()
     conv0 = _t_block(tape, g(f"{hg}_encoderlayer_0"), y, rates["encoderlayer_0"], generator, training)
     pool0 = _t_down(tape, g(f"{hg}_downsample_0").conv[0], conv0)
     conv1 = _t_block(tape, g(f"{hg}_encoderlayer_1"), pool0, rates["encoderlayer_1"], generator, training)
     pool1 = _t_down(tape, g(f"{hg}_downsample_1").conv[0], conv1)
     conv2 = _t_block(tape, g(f"conv_{hg}"), pool1, rates["conv"], generator, training)
     up0 = _t_up(tape, g(f"{hg}_upsample_0").deconv[0], conv2)
-    deconv0 = _t_block(tape, g(f"{hg}_decoderlayer_0"), _t_cat(tape, up0, conv1), rates["decoderlayer_0"], generator, training)
+    d0_in = _t_cat(tape, up0, conv1)
+    if prev is not None:
+        pr = model.output_proj_HG2_0.proj
+        d0_in = _t_conv(tape, pr[0], _t_cat(tape, _t_cat(tape, prev[0], prev[1]), d0_in), L.ACT_PRELU, pr[1].weight)
+    deconv0 = _t_block(tape, g(f"{hg}_decoderlayer_0"), d0_in, rates["decoderlayer_0"], generator, training)
     up1 = _t_up(tape, g(f"{hg}_upsample_1").deconv[0], deconv0)
-    deconv1 = _t_block(tape, g(f"{hg}_decoderlayer_1"), _t_cat(tape, up1, conv0), rates["decoderlayer_1"], generator, training)
-    return deconv1, tape
+    d1_in = _t_cat(tape, up1, conv0)
+    if prev is not None:
+        pr = model.output_proj_HG2_1.proj
+        d1_in = _t_conv(tape, pr[0], _t_cat(tape, _t_cat(tape, prev[2], prev[3]), d1_in), L.ACT_PRELU, pr[1].weight)
+    deconv1 = _t_block(tape, g(f"{hg}_decoderlayer_1"), d1_in, rates["decoderlayer_1"], generator, training)
+    return deconv1, (up0, conv1, up1, conv0)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# the whole model in training mode, and one training step (BASELINE config 5; train.py.bak:163-170, train.py:28-66)
+# ------------------------------------------------------------------------------------------------------------------------------
+def _t_head(tape: Tape, conv, x4: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Head conv (``models/fba_net.py:88,255``) straight from the planar burst: frames ``[N,Cin,S,S]`` fp32 -> channels-last with the
+    channels zero-padded to a 16-byte pixel, 3x3 conv with the weight padded alike.  The burst needs no gradient."""
+    from . import ops
+    Co, Ci = conv.weight.shape[:2]
+    cp = 4 if dtype == torch.float32 else 8
+    N, _, H, W = x4.shape
+    xn = ops.to_nhwc(x4, cp, dtype)
+    w = torch.nn.functional.pad(conv.weight.detach().permute(0, 2, 3, 1), (0, cp - Ci)).reshape(Co, -1).to(dtype).contiguous()
+    out = torch.empty((N, H, W, Co), device=x4.device, dtype=dtype)
+    ops.conv_gemm([xn], w, out, kh=3, kw=3, pad=1, bias=conv.bias.detach().contiguous())
+
+    def bwd(g):
+        dw, db = ops.conv_wgrad(xn, g, 3, 3, 1, 1)
+        _accumulate(conv.weight, dw[:, :Ci]), _accumulate(conv.bias, db)
+        return []
+    return tape.record(out, bwd)
+
+
+def _t_ps_conv(tape: Tape, conv, x: torch.Tensor) -> torch.Tensor:
+    """conv3x3 ``E -> 4E`` + ``PixelShuffle(2)`` (``blocks/upsampler.py:22-32``): the shuffle is the ConvT-style scatter store of the
+    GEMM whose rows are re-ordered from ``4c+2i+j`` to ``(2i+j)*E + c``."""
+    from . import ops, _lib as L
+    C4, Ci = conv.weight.shape[:2]
+    N, H, W, _ = x.shape
+    w = conv.weight.detach().permute(0, 2, 3, 1).reshape(C4 // 4, 4, -1).permute(1, 0, 2).reshape(C4, -1).to(x.dtype).contiguous()
+    b = conv.bias.detach().reshape(C4 // 4, 4).t().reshape(-1).contiguous()
+    out = torch.empty((N, 2 * H, 2 * W, C4 // 4), device=x.device, dtype=x.dtype)
+    ops.conv_gemm([x], w, out, kh=3, kw=3, pad=1, bias=b, store_mode=L.STORE_CONVT2)
+
+    def bwd(g):
+        dw, db = pixel_shuffle_conv_wgrad(x, g)
+        _accumulate(conv.weight, dw), _accumulate(conv.bias, db)
+        return [(x, pixel_shuffle_conv_dgrad(g, conv.weight))]
+    return tape.record(out, bwd)
+
+
+def _t_final(tape: Tape, conv, x: torch.Tensor, base: torch.Tensor) -> torch.Tensor:
+    """Last conv ``E -> C_in`` + the bilinear x4 base frame (``models/fba_net.py:315-320``): planar fp32 ``[B,C_in,4S,4S]`` out.  The
+    incoming gradient is planar fp32 (``fbanet_train_loss_sm100``); it is re-laid channels-last (padded to a 16-byte pixel) for the
+    weight-gradient kernel and for the flipped-weight data gradient.  The base path has no parameters."""
+    from . import ops, _lib as L
+    Co, Ci = conv.weight.shape[:2]
+    N, H, W, _ = x.shape
+    cp = 4 if x.dtype == torch.float32 else 8
+    w = conv.weight.detach().permute(0, 2, 3, 1).reshape(Co, -1).to(x.dtype).contiguous()
+    out = torch.empty((N, Co, H, W), device=x.device, dtype=torch.float32)
+    ops.conv_gemm([x], w, out, kh=3, kw=3, pad=1, bias=conv.bias.detach().contiguous(), store_mode=L.STORE_NCHW_BASE, base=base, cout_store=Co)
+
+    def bwd(g):
+        gn = ops.to_nhwc(g.contiguous(), cp, x.dtype)                                            # [N,H,W,cp], channels >= Co are zero
+        dw, db = ops.conv_wgrad(x, gn, 3, 3, 1, 1)
+        _accumulate(conv.weight, dw[:Co]), _accumulate(conv.bias, db[:Co])
+        wp = torch.nn.functional.pad(conv.weight.detach(), (0, 0, 0, 0, 0, 0, 0, cp - Co))       # zero rows for the padded channels
+        dx = torch.empty_like(x)
+        ops.conv_gemm([gn], dgrad_weight(wp, x.dtype), dx, kh=3, kw=3, pad=1)
+        return [(x, dx)]
+    return tape.record(out, bwd)
+
+
+def model_forward_train(model, burst: torch.Tensor, generator: Optional[torch.Generator] = None, training: bool = True):
+    """The whole ``FBANetModel.__call__`` (``models/fba_net.py:242-322``) in training mode on a :class:`Tape`: ``burst`` fp32
+    ``[B,F,C_in,S,S]`` on the GPU -> ``(restored [B,C_in,4S,4S] fp32, tape)``.  Every arithmetic step is a C-ABI op; activations
+    live in the model's compute dtype.  ``tape.backward(restored, d_restored)`` accumulates the gradient of every parameter the
+    output depends on (``fusion.temporal_attn0`` and the two embedding biases cancel out of the gate as written and stay untouched)."""
+    from . import _lib as L
+    B, Fr, Cin, S, _ = burst.shape
+    E, dt = model.embed_dim, model.compute_dtype
+    tape = Tape()
+    burst = burst.contiguous().float()
+    f = _t_head(tape, model.head, burst.view(B * Fr, Cin, S, S), dt)
+    f = _t_resblock(tape, model.body[1], _t_resblock(tape, model.body[0], f))
+    feat = tape.record(f.view(B, Fr, S, S, E), (lambda f: (lambda g: [(f, g.reshape(f.shape))]))(f))
+    fused = _faf_on_tape(tape, model.fusion, feat)
+    proj = lambda m, x: _t_conv(tape, m.proj[0], x, L.ACT_PRELU, m.proj[1].weight)
+    y = proj(model.input_proj, fused)
+    d1, prev = _hourglass_on_tape(tape, model, "HG1", y, None, generator, training)
+    y1 = proj(model.output_proj, d1)
+    d2, _ = _hourglass_on_tape(tape, model, "HG2", y1, prev, generator, training)
+    y2 = proj(model.output_proj_2, d2)
+    t2 = _t_ps_conv(tape, model.tail[0][2], _t_ps_conv(tape, model.tail[0][0], y2))
+    return _t_final(tape, model.tail[1], t2, burst[:, 0]), tape
+
+
+def train_step(model, flat: FlatParams, burst: torch.Tensor, target: torch.Tensor, lr: float, weight_decay: float = 0.02,
+               generator: Optional[torch.Generator] = None, group=None):
+    """One data-parallel training step of the reference trainer (``train.py.bak:163-170``: forward, ``CharbonnierLoss + 3 GWLoss``,
+    backward, ``AdamW`` step; ``DataParallel`` -> one process per GPU + the gradient all-reduce).  ``flat = FlatParams(model.parameters())``
+    (parameters set to ``requires_grad``).  Returns the loss triple ``(total, charbonnier, gw)`` as a float64 device tensor."""
+    from . import ops
+    flat.zero_grad()
+    restored, tape = model_forward_train(model, burst, generator, training=True)
+    loss, d_restored = ops.training_loss(restored, target)
+    tape.backward(restored, d_restored)
+    scale = flat.all_reduce(group)
+    flat.adam_step(lr, weight_decay=weight_decay, decoupled=True, grad_scale=scale)
+    return loss
 
 
 # ------------------------------------------------------------------------------------------------------------------------------

@@ -135,7 +135,7 @@ def test_two_rank_flat_gradient_all_reduce():
         p.join(timeout=60)
         assert p.exitcode == 0
     for r, same, views, ok, scale, n in res:
-        assert same and views and ok and scale == 0.5 and n == 5 * 7 + 7 + 1 + 7 * 3 + 3
+        assert same and views and ok and scale == 0.5 and n == 36 + 8 + 4 + 24 + 4          # each parameter padded to 16 bytes
 
 
 def _bucket_worker(rank, world, port, q):

@@ -342,3 +342,58 @@ def test_faf_block_training_forward_backward_on_the_gpu(cuda):
             assert got[n].grad is None, n
             continue
         assert got[n].grad is not None and _rel(got[n].grad.cpu(), pr.grad) < 2e-3, (n, _rel(got[n].grad.cpu(), pr.grad))
+
+
+def test_whole_model_training_step_on_the_gpu(cuda):
+    """BASELINE config 5 on the real kernels (fp32 parity path, small model): (1) the training-mode forward of the whole model
+    reproduces the inference forward; (2) loss + Tape.backward give the gradients autograd gives through the oracle model and the
+    oracle's CharbonnierLoss + 3 GWLoss (float64, CPU) for EVERY parameter; (3) two train_step calls (flat buffers, fused AdamW)
+    on the same sample lower the loss.  The composition is checked with op stand-ins in tests/test_host_logic.py."""
+    from fbanet_b200 import train, ops
+    from fbanet_b200.model import BaseModel
+    from oracle.fbanet_oracle import OracleBaseModel, training_loss
+    cfg = dict(num_frames=3, img_size=40, embed_dim=32, window_length=10)
+    m = BaseModel(token_mlp="leff", dtype="fp32", seed=4, **cfg)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "relative_position_bias_table" in n or (p.dim() == 1 and "norm" not in n):
+                p.copy_(torch.randn_like(p) * 0.1)
+    o = OracleBaseModel(**cfg).double()
+    o.load_state_dict(m.state_dict())
+    B = 2
+    burst = torch.rand(B, 3, 3, 40, 40, generator=torch.Generator().manual_seed(1))
+    target = torch.rand(B, 3, 160, 160, generator=torch.Generator().manual_seed(2))
+    ref = o(burst.double())
+    loss_ref = training_loss(ref, target.double())
+    loss_ref.backward()
+    m = m.to(cuda)
+    bd, td = burst.to(cuda), target.to(cuda)
+    infer = m(bd)                                                          # the inference path (graph of fused kernels)
+    for p in m.parameters():
+        p.requires_grad_(True)
+        p.grad = None
+    before = ops.LAUNCHES
+    restored, tape = train.model_forward_train(m, bd, training=False)
+    assert _rel(restored, infer) < 1e-4 and _rel(restored.cpu(), ref.detach()) < 1e-3
+    loss, d_restored = ops.training_loss(restored, td)
+    assert abs(loss[0].item() - loss_ref.item()) < 1e-4 * loss_ref.item()
+    assert tape.backward(restored, d_restored) == {}
+    assert ops.LAUNCHES - before >= 20 * 30 + 100                          # the C-ABI ops ran: no torch arithmetic on the path
+    got, worst = dict(m.named_parameters()), 0.0
+    for n, pr in o.named_parameters():
+        if n.startswith("fusion.temporal_attn0") or n == "fusion.temporal_attn1.bias":
+            assert got[n].grad is None, n
+            continue
+        assert got[n].grad is not None, n
+        e = _rel(got[n].grad.cpu(), pr.grad)
+        worst = max(worst, e)
+        assert e < 5e-3, (n, e)
+    # the optimizer loop
+    for p in m.parameters():
+        p.grad = None
+    m.drop_path_rate = 0.0
+    flat = train.FlatParams(m.parameters())
+    l1 = train.train_step(m, flat, bd, td, lr=2e-4)
+    l2 = train.train_step(m, flat, bd, td, lr=2e-4)
+    l3 = train.train_step(m, flat, bd, td, lr=2e-4)
+    assert flat.step == 3 and torch.isfinite(l3).all() and l3[0].item() < l1[0].item(), (l1, l2, l3)

@@ -434,11 +434,15 @@ def _install_conv_standins(monkeypatch):
     import torch.nn.functional as F
     from fbanet_b200 import ops, _lib as L
 
-    def conv_gemm(srcs, weight, out, *, kh=1, kw=1, stride=1, pad=0, bias=None, act=L.ACT_NONE, store_mode=L.STORE_NHWC):
+    def conv_gemm(srcs, weight, out, *, kh=1, kw=1, stride=1, pad=0, bias=None, act=L.ACT_NONE, store_mode=L.STORE_NHWC, base=None,
+                  cout_store=None):
         assert len(srcs) == 1 and act == L.ACT_NONE
         src = srcs[0]
         w = weight.reshape(weight.shape[0], kh, kw, src.shape[-1]).permute(0, 3, 1, 2)
         g = F.conv2d(src.permute(0, 3, 1, 2), w, bias, stride=stride, padding=pad).permute(0, 2, 3, 1)
+        if store_mode == L.STORE_NCHW_BASE:      # planar out + bilinear x4 of the base frame (half-pixel centres, edge clamp)
+            assert cout_store == weight.shape[0] and base.shape[1] == cout_store
+            g = g.permute(0, 3, 1, 2) + F.interpolate(base.to(g.dtype), scale_factor=4, mode="bilinear", align_corners=False)
         if store_mode == L.STORE_CONVT2:
             N, H, W, C4 = g.shape
             g = g.reshape(N, H, W, 2, 2, C4 // 4).permute(0, 1, 3, 2, 4, 5).reshape(N, 2 * H, 2 * W, C4 // 4)
@@ -455,6 +459,19 @@ def _install_conv_standins(monkeypatch):
     monkeypatch.setattr(ops, "conv_gemm", conv_gemm)
     monkeypatch.setattr(ops, "conv_wgrad", conv_wgrad)
     monkeypatch.setattr(ops, "space_to_depth", lambda x: _emu_s2d(x).contiguous())
+
+    def to_nhwc(x, cp, dtype):                   # planar [N,C,H,W] -> channels-last, channels zero-padded to cp
+        return F.pad(x.permute(0, 2, 3, 1), (0, cp - x.shape[1])).to(dtype).contiguous()
+
+    def training_loss(restored, target):
+        from oracle.fbanet_oracle import training_loss as ref_loss
+        r = restored.detach().to(target.dtype).requires_grad_(True)
+        loss = ref_loss(r, target)
+        loss.backward()
+        return loss.detach(), r.grad
+
+    monkeypatch.setattr(ops, "to_nhwc", to_nhwc)
+    monkeypatch.setattr(ops, "training_loss", training_loss)
 
 
 def test_hourglass_training_composition_matches_autograd_of_the_oracle(monkeypatch):
@@ -544,3 +561,95 @@ def test_faf_block_training_composition_matches_autograd_of_the_oracle(monkeypat
             assert pr.grad.abs().max().item() < 1e-12 and got[n].grad is None, n
             continue
         assert got[n].grad is not None and close(got[n].grad, pr.grad), n
+
+
+def test_whole_model_training_backward_matches_autograd_of_the_oracle(monkeypatch):
+    """train.model_forward_train + the training loss + Tape.backward: the WHOLE model (head, body, FAF block, input projection, both
+    hourglasses incl. HG2's four-way projections, output projections, two PixelShuffle stages, final conv + bilinear base) against
+    autograd through the oracle model and the oracle's CharbonnierLoss + 3 GWLoss: restored image, loss, and the gradient of every
+    parameter (models/fba_net.py:242-322, train.py.bak:163-169).  Op stand-ins as above."""
+    import torch
+    from fbanet_b200 import train, ops
+    from fbanet_b200.model import BaseModel
+    from oracle.fbanet_oracle import OracleBaseModel, training_loss
+    _install_op_standins(monkeypatch)
+    _install_conv_standins(monkeypatch)
+    cfg = dict(num_frames=2, img_size=16, embed_dim=16, window_length=4)
+    m = BaseModel(token_mlp="leff", dtype="fp32", seed=2, **cfg).double()
+    m.compute_dtype = torch.float64
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "relative_position_bias_table" in n or (p.dim() == 1 and "norm" not in n):
+                p.copy_(torch.randn_like(p) * 0.2)
+    o = OracleBaseModel(**cfg).double()
+    o.load_state_dict(m.state_dict())
+    B = 2
+    burst = torch.rand(B, 2, 3, 16, 16, dtype=torch.float64)
+    target = torch.rand(B, 3, 64, 64, dtype=torch.float64)
+    ref = o(burst)
+    loss_ref = training_loss(ref, target)
+    loss_ref.backward()
+    for p in m.parameters():
+        p.requires_grad_(True)
+        p.grad = None
+    monkeypatch.setattr(torch.Tensor, "float", lambda self: self)           # keep float64 through the composition's fp32 casts
+
+    # two fp32 roundings survive in this float64 run, both part of the kernels' contracts: wsum of the FAF gate and the planar fp32
+    # restored image; bounds are 1e-5 relative
+    def close(a, b, tol=1e-5):
+        return (a - b).abs().max().item() <= tol * max(b.abs().max().item(), 1e-30)
+    restored, tape = train.model_forward_train(m, burst, training=False)
+    assert restored.dtype == torch.float32 and close(restored.double(), ref.detach(), 1e-6)
+    loss, d_restored = ops.training_loss(restored, target)
+    assert abs(loss.item() - loss_ref.item()) < 1e-7
+    left = tape.backward(restored, d_restored)
+    assert left == {}                                                        # the burst itself takes no gradient
+    got, n_checked = dict(m.named_parameters()), 0
+    for n, pr in o.named_parameters():
+        if n.startswith("fusion.temporal_attn0") or n == "fusion.temporal_attn1.bias":
+            assert got[n].grad is None and pr.grad.abs().max().item() < 1e-12, n
+            continue
+        assert got[n].grad is not None and close(got[n].grad, pr.grad), (n, (got[n].grad - pr.grad).abs().max().item(), pr.grad.abs().max().item())
+        n_checked += 1
+    assert n_checked == len(got) - 3
+
+
+def test_train_step_plumbing(monkeypatch):
+    """train.train_step: zero the flat gradient, training-mode forward, loss, tape backward INTO the flat gradient buffer (the
+    parameters' .grad are views of it), all-reduce scale handed to the fused AdamW step (train.py.bak:163-170).  Stand-ins as above
+    plus the AdamW update formula for fbanet_adam_step_sm100 (the kernel itself is pinned to torch.optim by its -m gpu test)."""
+    import torch
+    from fbanet_b200 import train, ops
+    from fbanet_b200.model import BaseModel
+    _install_op_standins(monkeypatch)
+    _install_conv_standins(monkeypatch)
+    calls = []
+
+    def adam_step(param, grad, m, v, step, lr, betas, eps, wd, decoupled, grad_scale):
+        calls.append((step, lr, wd, decoupled, grad_scale))
+        g = grad * grad_scale
+        param.mul_(1 - lr * wd)
+        m.mul_(betas[0]).add_(g, alpha=1 - betas[0])
+        v.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+        param.addcdiv_(m / (1 - betas[0] ** step), (v / (1 - betas[1] ** step)).sqrt() + eps, value=-lr)
+    monkeypatch.setattr(ops, "adam_step", adam_step)
+    m = BaseModel(token_mlp="leff", dtype="fp32", seed=3, num_frames=2, img_size=16, embed_dim=16, window_length=4)
+    for p in m.parameters():
+        p.requires_grad_(True)
+    m.drop_path_rate = 0.0                                                  # (with one burst a dropped branch zeroes its layer's gradients)
+    flat = train.FlatParams(m.parameters())
+    before = flat.data.clone()
+    burst, target = torch.rand(1, 2, 3, 16, 16), torch.rand(1, 3, 64, 64)
+    gen = torch.Generator().manual_seed(5)
+    l1 = train.train_step(m, flat, burst, target, lr=1e-3, generator=gen)
+    assert calls == [(1, 1e-3, 0.02, True, 1.0)] and torch.isfinite(l1).all() and l1.item() > 0
+    used = flat.grad != 0
+    assert used.float().mean().item() > 0.9                                # all but the cancelled FAF embedding parameters
+    names = {id(p): n for n, p in m.named_parameters()}
+    dead = [names[id(p)] for p in flat.params if not p.grad.any()]
+    assert sorted(dead) == ["fusion.temporal_attn0.bias", "fusion.temporal_attn0.weight", "fusion.temporal_attn1.bias"], dead
+    moved = (flat.data - before).abs()
+    assert 0.5e-3 < moved[used].median().item() < 1.5e-3                    # first Adam step: |update| ~ lr
+    assert all(p.data.data_ptr() == flat.data[o:].data_ptr() for p, o in zip(flat.params, flat.offsets))   # still views
+    l2 = train.train_step(m, flat, burst, target, lr=1e-3, generator=gen)
+    assert calls[-1][0] == 2 and l2.item() < l1.item()                      # the same sample again: the loss went down
