@@ -242,13 +242,21 @@ def pixel_shuffle_wgrad_layout(dw: torch.Tensor, db: torch.Tensor):
 # ------------------------------------------------------------------------------------------------------------------------------
 # one LeWin block in training mode: forward that keeps its activations, backward composed of the bricks
 # ------------------------------------------------------------------------------------------------------------------------------
+_REDUCER: Optional["FlatParams"] = None      # set by train_step while a bucketed reduction is open
+
+
 def _accumulate(p: torch.nn.Parameter, g: torch.Tensor) -> None:
-    """Add ``g`` to ``p.grad`` (a view into ``FlatParams.grad`` when the module was flattened; created on first use otherwise)."""
+    """Add ``g`` to ``p.grad`` (a view into ``FlatParams.grad`` when the module was flattened; created on first use otherwise).
+    Every parameter of the model is consumed by exactly one tape record, so after this call its gradient is final for the step:
+    with a bucketed reduction open, the parameter is reported ready and complete buckets start their all-reduce while the rest of
+    the backward is still running."""
     g = g.reshape(p.shape).to(p.dtype)
     if p.grad is None:
         p.grad = g.clone()
     else:
         p.grad.add_(g)
+    if _REDUCER is not None:
+        _REDUCER.mark_ready(p)
 
 
 def _linear(x4: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
@@ -639,16 +647,22 @@ def model_forward_train(model, burst: torch.Tensor, generator: Optional[torch.Ge
 
 
 def train_step(model, flat: FlatParams, burst: torch.Tensor, target: torch.Tensor, lr: float, weight_decay: float = 0.02,
-               generator: Optional[torch.Generator] = None, group=None):
+               generator: Optional[torch.Generator] = None, group=None, bucket_bytes: int = 16 << 20):
     """One data-parallel training step of the reference trainer (``train.py.bak:163-170``: forward, ``CharbonnierLoss + 3 GWLoss``,
-    backward, ``AdamW`` step; ``DataParallel`` -> one process per GPU + the gradient all-reduce).  ``flat = FlatParams(model.parameters())``
+    backward, ``AdamW`` step; ``DataParallel`` -> one process per GPU + the gradient all-reduce, issued in buckets that overlap the backward).  ``flat = FlatParams(model.parameters())``
     (parameters set to ``requires_grad``).  Returns the loss triple ``(total, charbonnier, gw)`` as a float64 device tensor."""
     from . import ops
+    global _REDUCER
     flat.zero_grad()
     restored, tape = model_forward_train(model, burst, generator, training=True)
     loss, d_restored = ops.training_loss(restored, target)
-    tape.backward(restored, d_restored)
-    scale = flat.all_reduce(group)
+    flat.begin_reduce(group, bucket_bytes)
+    _REDUCER = flat
+    try:
+        tape.backward(restored, d_restored)          # buckets of finished gradients are all-reduced while this still runs
+    finally:
+        _REDUCER = None
+    scale = flat.finish_reduce()                     # the rest (incl. parameters the loss does not reach), then wait
     flat.adam_step(lr, weight_decay=weight_decay, decoupled=True, grad_scale=scale)
     return loss
 

@@ -189,3 +189,71 @@ def test_two_rank_bucketed_gradient_reduce_equals_one_shot():
         # the tail bucket (layers 5, 4) needs the late parameter (layer 5's bias, marked 6th): nothing launches before it; the middle
         # bucket (layers 3, 2) completes with layer 2's weight (8th), the head bucket with the last parameter
         assert launched[:5] == [0] * 5 and launched[5:7] == [1, 1] and launched[7] == 2 and launched[-2:] == [2, 3], launched
+
+
+def _train_step_worker(rank, world, port, q):
+    """Config 5 data-parallel: each rank runs train.train_step on ITS burst (op stand-ins from tests/test_host_logic.py, the only
+    collective is the bucketed sum of the flat gradient buffer); the summed gradient times 1 / world equals the gradient of one
+    process over the two-burst batch, and both ranks end the step with identical parameters."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import test_host_logic as H
+    from fbanet_b200 import ops, train
+    from fbanet_b200.dist import init_from_env
+    from fbanet_b200.model import BaseModel
+
+    class MP:
+        def setattr(self, o, n, v):
+            setattr(o, n, v)
+    H._install_op_standins(MP())
+    H._install_conv_standins(MP())
+
+    def adam_step(param, grad, m, v, step, lr, betas, eps, wd, decoupled, grad_scale):
+        g = grad * grad_scale
+        param.mul_(1 - lr * wd)
+        m.mul_(betas[0]).add_(g, alpha=1 - betas[0])
+        v.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+        param.addcdiv_(m / (1 - betas[0] ** step), (v / (1 - betas[1] ** step)).sqrt() + eps, value=-lr)
+    ops.adam_step = adam_step
+    r, _, w = init_from_env("gloo")
+    torch.set_num_threads(2)
+
+    def make():
+        m = BaseModel(token_mlp="leff", dtype="fp32", seed=3, num_frames=2, img_size=16, embed_dim=16, window_length=4)
+        m.drop_path_rate = 0.0
+        for p in m.parameters():
+            p.requires_grad_(True)
+        return m, train.FlatParams(m.parameters())
+    g = torch.Generator().manual_seed(9)
+    bursts, targets = torch.rand(w, 2, 3, 16, 16, generator=g), torch.rand(w, 3, 64, 64, generator=g)
+    m, flat = make()
+    train.train_step(m, flat, bursts[r:r + 1], targets[r:r + 1], lr=1e-3, bucket_bytes=64 << 10)
+    dp_grad = flat.grad * (1.0 / w)
+    both = [torch.empty_like(flat.data) for _ in range(w)]
+    dist.all_gather(both, flat.data)
+    same_params = all(torch.equal(both[0], b) for b in both)
+    # one process, the whole batch (no process group involvement: world-1 semantics through a fresh FlatParams and all_reduce skipped)
+    m1, flat1 = make()
+    restored, tape = train.model_forward_train(m1, bursts, training=False)
+    loss, d = ops.training_loss(restored, targets)
+    tape.backward(restored, d)
+    err = ((dp_grad - flat1.grad).abs().max() / flat1.grad.abs().max()).item()
+    dist.barrier()
+    q.put((r, same_params, err, len(flat._buckets)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_data_parallel_train_step():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_train_step_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r, same_params, err, nb in res:
+        assert same_params and err < 1e-4 and nb > 10, (r, same_params, err, nb)

@@ -653,3 +653,18 @@ def test_train_step_plumbing(monkeypatch):
     assert all(p.data.data_ptr() == flat.data[o:].data_ptr() for p, o in zip(flat.params, flat.offsets))   # still views
     l2 = train.train_step(m, flat, burst, target, lr=1e-3, generator=gen)
     assert calls[-1][0] == 2 and l2.item() < l1.item()                      # the same sample again: the loss went down
+    # bucketed reduction driven by the tape: with small buckets, all but the buckets holding the three unreached FAF parameters (and
+    # the ones queued behind them: buckets start in order) were complete -- i.e. would have been on the wire -- before finish_reduce
+    seen = {}
+    orig_finish = train.FlatParams.finish_reduce
+
+    def finish(self):
+        seen["launched"], seen["buckets"] = sum(self._launched), len(self._buckets)
+        seen["first_blocked"] = self._launched.index(False)
+        return orig_finish(self)
+    monkeypatch.setattr(train.FlatParams, "finish_reduce", finish)
+    train.train_step(m, flat, burst, target, lr=1e-3, generator=gen, bucket_bytes=64 << 10)
+    b, e, _ = flat._buckets[seen["first_blocked"]]
+    blocked = [names[id(p)] for p, o in zip(flat.params, flat.offsets) if b <= o < e]
+    assert seen["buckets"] > 10 and seen["launched"] >= seen["buckets"] - 3 and any(n.startswith("fusion.temporal_attn") for n in blocked), seen
+    assert train._REDUCER is None and all(flat._launched)
