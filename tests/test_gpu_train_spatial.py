@@ -159,241 +159,3 @@ def test_drop_path_add_forward_and_backward(cuda, dtype):
     assert torch.equal(dx, (skip.float() * scale[:, None, None]).to(dtype))
     ones = train.drop_path_scales(B, 0.0, device=cuda)
     assert torch.equal(ops.drop_path_add(skip, ones), skip)
-
-
-# ---- resampling layers: gradients as compositions of the FORWARD kernels with re-packed weights (train.dgrad_weight_* / *_wgrad).
-# The packings are checked on the CPU against an emulation of the kernels' contracts (tests/test_host_logic.py::
-# test_resampling_layer_gradients_through_forward_kernels); here the real kernels run them.
-@pytest.mark.parametrize("dtype", DTYPES)
-def test_convT2_gradients_through_forward_kernels(cuda, dtype):
-    """ConvTranspose2d(4E, E, 2, 2) of layers/upsample.py:19-30 (E = 64)."""
-    from fbanet_b200 import train
-    g = torch.Generator().manual_seed(21)
-    N, H, W, Ci, Co = 2, 10, 12, 256, 64
-    w = (torch.randn(Ci, Co, 2, 2, generator=g) / Ci ** 0.5).to(cuda)
-    x = torch.randn(N, H, W, Ci, generator=g).to(dtype).to(cuda)
-    dy = torch.randn(N, 2 * H, 2 * W, Co, generator=g).to(dtype).to(cuda)
-    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
-    wr = w.to(dtype).float().requires_grad_(True)
-    br = torch.zeros(Co, device=cuda, requires_grad=True)
-    with torch.backends.cudnn.flags(allow_tf32=False):
-        F.conv_transpose2d(xr, wr, br, stride=2).backward(dy.float().permute(0, 3, 1, 2))
-    dx = train.convT2_dgrad(dy, w)
-    assert _rel(dx.float(), xr.grad.permute(0, 2, 3, 1)) < _tol(dtype), _rel(dx.float(), xr.grad.permute(0, 2, 3, 1))
-    dw, db = train.convT2_wgrad(x, dy)
-    assert dw.shape == w.shape and _rel(dw, wr.grad) < 2e-4 and _rel(db, br.grad) < 2e-4
-
-
-@pytest.mark.parametrize("dtype", DTYPES)
-def test_pixel_shuffle_conv_gradients_through_forward_kernels(cuda, dtype):
-    """conv3x3 E -> 4E + PixelShuffle(2) of blocks/upsampler.py:22-32 (E = 64)."""
-    from fbanet_b200 import train
-    g = torch.Generator().manual_seed(23)
-    N, H, W, Ci, C = 2, 10, 12, 64, 64
-    w = (torch.randn(4 * C, Ci, 3, 3, generator=g) / (9 * Ci) ** 0.5).to(cuda)
-    x = torch.randn(N, H, W, Ci, generator=g).to(dtype).to(cuda)
-    dy = torch.randn(N, 2 * H, 2 * W, C, generator=g).to(dtype).to(cuda)
-    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
-    wr = w.to(dtype).float().requires_grad_(True)
-    br = torch.zeros(4 * C, device=cuda, requires_grad=True)
-    with torch.backends.cudnn.flags(allow_tf32=False):
-        F.pixel_shuffle(F.conv2d(xr, wr, br, padding=1), 2).backward(dy.float().permute(0, 3, 1, 2))
-    dx = train.pixel_shuffle_conv_dgrad(dy, w)
-    assert _rel(dx.float(), xr.grad.permute(0, 2, 3, 1)) < _tol(dtype), _rel(dx.float(), xr.grad.permute(0, 2, 3, 1))
-    dw, db = train.pixel_shuffle_conv_wgrad(x, dy)
-    assert dw.shape == w.shape and _rel(dw, wr.grad) < 2e-4 and _rel(db, br.grad) < 2e-4
-
-
-@pytest.mark.parametrize("dtype,Ci,Co", [(torch.float32, 32, 64), (torch.float32, 64, 128), (torch.bfloat16, 32, 64), (torch.bfloat16, 64, 128)])
-def test_downsample4_data_gradient_through_forward_kernel(cuda, dtype, Ci, Co):
-    """Conv2d(E, 2E, 4, 2, 1) of layers/downsample.py:19-30 (E = 32, 64): four sub-pixel phases as rows of one 3x3 GEMM over dy."""
-    from fbanet_b200 import train
-    g = torch.Generator().manual_seed(22)
-    N, Ho, Wo = 2, 10, 12
-    w = (torch.randn(Co, Ci, 4, 4, generator=g) / (16 * Ci) ** 0.5).to(cuda)
-    dy = torch.randn(N, Ho, Wo, Co, generator=g).to(dtype).to(cuda)
-    xr = torch.zeros(N, Ci, 2 * Ho, 2 * Wo, device=cuda, requires_grad=True)
-    with torch.backends.cudnn.flags(allow_tf32=False):
-        F.conv2d(xr, w.to(dtype).float(), None, stride=2, padding=1).backward(dy.float().permute(0, 3, 1, 2))
-    dx = train.down4_dgrad(dy, w)
-    assert dx.shape == (N, 2 * Ho, 2 * Wo, Ci)
-    assert _rel(dx.float(), xr.grad.permute(0, 2, 3, 1)) < _tol(dtype), _rel(dx.float(), xr.grad.permute(0, 2, 3, 1))
-
-
-@pytest.mark.parametrize("dtype", DTYPES)
-def test_act_forward_keeps_the_epilogue_semantics(cuda, dtype):
-    """Stand-alone training-mode activation == the functions the GEMM epilogues apply (common.cuh apply_act)."""
-    from fbanet_b200 import _lib as L, ops
-    x = (torch.randn(3, 11, 13, 24, generator=torch.Generator().manual_seed(4)) * 2).to(dtype).to(cuda)
-    alpha = torch.tensor([0.25], device=cuda)
-    for act, fn in ((L.ACT_NONE, lambda v: v), (L.ACT_RELU, F.relu), (L.ACT_GELU_TANH, lambda v: F.gelu(v, approximate="tanh")),
-                    (L.ACT_GELU_ERF, F.gelu), (L.ACT_PRELU, lambda v: F.prelu(v, alpha))):
-        y = ops.act_forward(x, act, alpha=alpha if act == L.ACT_PRELU else None)
-        assert _rel(y.float(), fn(x.float())) < (1e-6 if dtype == torch.float32 else 4e-3), act
-
-
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-3), (torch.bfloat16, 1e-1)])
-def test_lewin_block_training_forward_backward_on_the_gpu(cuda, dtype, tol):
-    """train.lewin_forward_train / lewin_backward (the composition tests/test_host_logic.py checks with op stand-ins) on the real
-    kernels, against autograd through the oracle's LeWinLayer in float64 on the CPU (layers/fba_net.py:139-250, Appendix A-4);
-    fp32 is the parity path, bf16 rounds every saved activation (loose bound, relative to each gradient's largest entry)."""
-    from fbanet_b200 import train, ops
-    from fbanet_b200.model import _Layer
-    from oracle.fbanet_oracle import LeWinLayer
-    torch.manual_seed(5)
-    dim, res, heads, win, shift, B = 64, (20, 20), 2, 10, 5, 2
-    ly = _Layer(dim, res, heads, win, shift, 4.0)
-    with torch.no_grad():
-        for n, p in ly.named_parameters():
-            p.copy_(torch.randn_like(p) * (0.5 if p.dim() == 1 or "table" in n else 1.5 / p[0].numel() ** 0.5))
-            if n.endswith(("norm1.weight", "norm2.weight")):
-                p.add_(1.0)
-    ref = LeWinLayer(dim, res, heads, win, shift, 4.0, "tanh").double()
-    ref.load_state_dict(ly.state_dict())
-    x = torch.randn(B, *res, dim).to(dtype)
-    dy = torch.randn(B, *res, dim).to(dtype)
-    xr = x.double().requires_grad_(True)
-    yr = ref(xr.view(B, -1, dim)).view(B, *res, dim)
-    yr.backward(dy.double())
-    ly = ly.to(cuda)
-    before = ops.LAUNCHES
-    y, saved = train.lewin_forward_train(ly, x.to(cuda))
-    dx = train.lewin_backward(ly, saved, dy.to(cuda))
-    assert ops.LAUNCHES - before >= 30                                   # the CUDA ops ran (no torch fallback inside the composition)
-    assert _rel(y.float().cpu(), yr.detach()) < (2e-4 if dtype == torch.float32 else 4e-2), _rel(y.float().cpu(), yr.detach())
-    assert _rel(dx.float().cpu(), xr.grad) < tol, _rel(dx.float().cpu(), xr.grad)
-    got = dict(ly.named_parameters())
-    for n, pr in ref.named_parameters():
-        assert got[n].grad is not None and _rel(got[n].grad.cpu(), pr.grad) < tol, (n, _rel(got[n].grad.cpu(), pr.grad))
-
-
-def test_hourglass_training_forward_backward_on_the_gpu(cuda):
-    """train.hourglass_forward_train + Tape.backward on the real kernels (fp32 parity path): ten LeWin layers, 4x4 s2 downsamples,
-    transposed-conv upsamples, skip concats -- against autograd through the oracle's first hourglass in float64 on the CPU
-    (models/fba_net.py:271-287).  The composition itself is checked with op stand-ins in tests/test_host_logic.py."""
-    from fbanet_b200 import train, ops
-    from fbanet_b200.model import BaseModel
-    from oracle.fbanet_oracle import OracleBaseModel
-    cfg = dict(num_frames=2, img_size=40, embed_dim=32, window_length=10)
-    m = BaseModel(token_mlp="leff", dtype="fp32", seed=1, **cfg)
-    with torch.no_grad():
-        for n, p in m.named_parameters():
-            if "relative_position_bias_table" in n or (p.dim() == 1 and "norm" not in n):
-                p.copy_(torch.randn_like(p) * 0.2)
-    o = OracleBaseModel(**cfg).double()
-    assert not o.load_state_dict(m.state_dict(), strict=False).missing_keys
-    B, S, E = 2, 40, 32
-    y = torch.randn(B, S, S, E, generator=torch.Generator().manual_seed(2))
-    dout = torch.randn(B, S, S, 2 * E, generator=torch.Generator().manual_seed(3))
-    yr = y.double().requires_grad_(True)
-    ref, _ = o._hourglass("HG1", yr.view(B, S * S, E))
-    ref.backward(dout.double().view(B, S * S, 2 * E))
-    m = m.to(cuda)
-    for p in m.parameters():
-        p.requires_grad_(True)
-        p.grad = None
-    yd = y.to(cuda)
-    before = ops.LAUNCHES
-    out, tape = train.hourglass_forward_train(m, "HG1", yd, training=False)
-    grads = tape.backward(out, dout.to(cuda))
-    assert ops.LAUNCHES - before >= 10 * 30
-    assert _rel(out.cpu().view(B, S * S, 2 * E), ref.detach()) < 5e-4
-    assert set(grads) == {id(yd)} and _rel(grads[id(yd)].cpu(), yr.grad.view(B, S, S, E)) < 2e-3
-    got, n_checked = dict(m.named_parameters()), 0
-    for n, pr in o.named_parameters():
-        if pr.grad is None:
-            continue
-        assert got[n].grad is not None and _rel(got[n].grad.cpu(), pr.grad) < 2e-3, (n, _rel(got[n].grad.cpu(), pr.grad))
-        n_checked += 1
-    assert n_checked == 10 * 17 + 4 * 2
-
-
-def test_faf_block_training_forward_backward_on_the_gpu(cuda):
-    """train.faf_forward_train + Tape.backward on the real kernels (fp32 parity path): gate, 1x1 fusion + PReLU, ten ResBlocks with
-    4x4 s2 / transposed-conv resampling, fusion_tail, skip -- against autograd through the oracle's FAFBlock as written, float64 on
-    the CPU (blocks/federated_affinity_fusion.py:166-182).  Composition checked with op stand-ins in tests/test_host_logic.py."""
-    from fbanet_b200 import train, ops
-    from fbanet_b200.model import _FAF
-    from oracle.fbanet_oracle import FAFBlock
-    torch.manual_seed(12)
-    E, Fr, B, S = 32, 3, 2, 16
-    fu = _FAF(E, Fr)
-    with torch.no_grad():
-        for p in fu.parameters():
-            p.copy_(torch.randn_like(p) * (0.3 if p.dim() == 1 else 0.7 / p[0].numel() ** 0.5))
-    ref = FAFBlock(E, Fr).double()
-    ref.load_state_dict(fu.state_dict())
-    feat = torch.randn(B, Fr, S, S, E)
-    dout = torch.randn(B, S, S, E)
-    fr = feat.double().requires_grad_(True)
-    yr = ref(fr.permute(0, 1, 4, 2, 3))
-    yr.backward(dout.double().permute(0, 3, 1, 2))
-    fu = fu.to(cuda)
-    fd = feat.to(cuda)
-    before = ops.LAUNCHES
-    out, tape = train.faf_forward_train(fu, fd)
-    grads = tape.backward(out, dout.to(cuda))
-    assert ops.LAUNCHES - before >= 100
-    assert _rel(out.cpu(), yr.detach().permute(0, 2, 3, 1)) < 5e-4
-    assert set(grads) == {id(fd)} and _rel(grads[id(fd)].cpu(), fr.grad) < 2e-3, _rel(grads[id(fd)].cpu(), fr.grad)
-    got = dict(fu.named_parameters())
-    for n, pr in ref.named_parameters():
-        if n.startswith("temporal_attn0") or n == "temporal_attn1.bias":
-            assert got[n].grad is None, n
-            continue
-        assert got[n].grad is not None and _rel(got[n].grad.cpu(), pr.grad) < 2e-3, (n, _rel(got[n].grad.cpu(), pr.grad))
-
-
-def test_whole_model_training_step_on_the_gpu(cuda):
-    """BASELINE config 5 on the real kernels (fp32 parity path, small model): (1) the training-mode forward of the whole model
-    reproduces the inference forward; (2) loss + Tape.backward give the gradients autograd gives through the oracle model and the
-    oracle's CharbonnierLoss + 3 GWLoss (float64, CPU) for EVERY parameter; (3) two train_step calls (flat buffers, fused AdamW)
-    on the same sample lower the loss.  The composition is checked with op stand-ins in tests/test_host_logic.py."""
-    from fbanet_b200 import train, ops
-    from fbanet_b200.model import BaseModel
-    from oracle.fbanet_oracle import OracleBaseModel, training_loss
-    cfg = dict(num_frames=3, img_size=40, embed_dim=32, window_length=10)
-    m = BaseModel(token_mlp="leff", dtype="fp32", seed=4, **cfg)
-    with torch.no_grad():
-        for n, p in m.named_parameters():
-            if "relative_position_bias_table" in n or (p.dim() == 1 and "norm" not in n):
-                p.copy_(torch.randn_like(p) * 0.1)
-    o = OracleBaseModel(**cfg).double()
-    o.load_state_dict(m.state_dict())
-    B = 2
-    burst = torch.rand(B, 3, 3, 40, 40, generator=torch.Generator().manual_seed(1))
-    target = torch.rand(B, 3, 160, 160, generator=torch.Generator().manual_seed(2))
-    ref = o(burst.double())
-    loss_ref = training_loss(ref, target.double())
-    loss_ref.backward()
-    m = m.to(cuda)
-    bd, td = burst.to(cuda), target.to(cuda)
-    infer = m(bd)                                                          # the inference path (graph of fused kernels)
-    for p in m.parameters():
-        p.requires_grad_(True)
-        p.grad = None
-    before = ops.LAUNCHES
-    restored, tape = train.model_forward_train(m, bd, training=False)
-    assert _rel(restored, infer) < 1e-4 and _rel(restored.cpu(), ref.detach()) < 1e-3
-    loss, d_restored = ops.training_loss(restored, td)
-    assert abs(loss[0].item() - loss_ref.item()) < 1e-4 * loss_ref.item()
-    assert tape.backward(restored, d_restored) == {}
-    assert ops.LAUNCHES - before >= 20 * 30 + 100                          # the C-ABI ops ran: no torch arithmetic on the path
-    got, worst = dict(m.named_parameters()), 0.0
-    for n, pr in o.named_parameters():
-        if n.startswith("fusion.temporal_attn0") or n == "fusion.temporal_attn1.bias":
-            assert got[n].grad is None, n
-            continue
-        assert got[n].grad is not None, n
-        e = _rel(got[n].grad.cpu(), pr.grad)
-        worst = max(worst, e)
-        assert e < 5e-3, (n, e)
-    # the optimizer loop
-    for p in m.parameters():
-        p.grad = None
-    m.drop_path_rate = 0.0
-    flat = train.FlatParams(m.parameters())
-    l1 = train.train_step(m, flat, bd, td, lr=2e-4)
-    l2 = train.train_step(m, flat, bd, td, lr=2e-4)
-    l3 = train.train_step(m, flat, bd, td, lr=2e-4)
-    assert flat.step == 3 and torch.isfinite(l3).all() and l3[0].item() < l1[0].item(), (l1, l2, l3)
