@@ -3,7 +3,8 @@
 Public API (mirrors the reference's): ``get_arch(opt)``, ``BaseModel``, ``load_checkpoint``; the alignment front end
 (``ecc_homography_burst`` = ``cv2.findTransformECC``, ``warp_burst`` = ``cv2.warpPerspective``, ``flow_warp_burst`` = the optical-flow
 ``register_frame``); the full-size tiled drivers in ``fbanet_b200.tiling`` (single GPU and row-band sharded over the GPUs of one box);
-and the first bricks of the training step (``training_loss``, ``fbanet_b200.train.FlatParams``).
+and the training step in ``fbanet_b200.train`` (``train_step``: training-mode forward on a reverse-mode tape over the C-ABI ops, ``training_loss``,
+backward into ``FlatParams`` flat buffers, bucketed gradient all-reduce, fused AdamW; learning-rate schedules and stochastic-depth rates).
 """
 from .model import BaseModel  # noqa: F401
 from .ops import ecc_homography_burst, flow_warp_burst, training_loss, warp_burst  # noqa: F401
