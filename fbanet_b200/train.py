@@ -123,10 +123,50 @@ class FlatParams:
         """One fused Adam / AdamW update of every parameter (``fbanet_adam_step_sm100``); CUDA only, no fallback."""
         from . import ops
         self.step += 1
+        self.param_groups[0].update(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
         ops.adam_step(self.data, self.grad, self.exp_avg, self.exp_avg_sq, self.step, lr, betas, eps, weight_decay, decoupled, grad_scale)
 
     def optimizer_state(self) -> dict:
         return {"step": self.step, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
+
+    # ---- checkpoint / resume in the reference's format: ``{"optimizer": optimizer.state_dict()}`` of ``optim.Adam / AdamW``
+    # (``train.py.bak:72-78,199-246``; read back by ``utils/model_utils.py:51-62`` ``load_optim(optimizer, weights)``, which only needs
+    # ``load_state_dict`` and ``param_groups``) -- so a FlatParams can be handed to the reference's helpers in the optimizer's place,
+    # and checkpoints written by either side resume on the other.
+    @property
+    def param_groups(self):
+        if not hasattr(self, "hyper"):
+            self.hyper = {"lr": 1e-4, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0.0, "amsgrad": False}
+        return [self.hyper]
+
+    def state_dict(self) -> dict:
+        state = {}
+        if self.step > 0:
+            for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+                n = p.numel()
+                state[i] = {"step": torch.tensor(float(self.step)), "exp_avg": self.exp_avg[o:o + n].view_as(p).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view_as(p).clone()}
+        return {"state": state, "param_groups": [dict(self.param_groups[0], params=list(range(len(self.params))))]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        groups = sd["param_groups"]
+        index = [i for g in groups for i in g["params"]]
+        assert len(index) == len(self.params), f"optimizer state holds {len(index)} parameters, the model has {len(self.params)}"
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = set()
+        for k, (p, o) in zip(index, zip(self.params, self.offsets)):
+            st = sd["state"].get(k)
+            if st is None:
+                continue
+            n = p.numel()
+            assert st["exp_avg"].numel() == n, f"parameter {k}: state of {st['exp_avg'].numel()} elements for {n}"
+            self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(st["step"]))
+        assert len(steps) <= 1, f"parameters at different step counts {sorted(steps)}: not a state this fused step can continue"
+        self.step = steps.pop() if steps else 0
+        self.hyper = {k: v for k, v in groups[0].items() if k != "params"}
 
 
 def dgrad_weight(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:

@@ -668,3 +668,35 @@ def test_train_step_plumbing(monkeypatch):
     blocked = [names[id(p)] for p, o in zip(flat.params, flat.offsets) if b <= o < e]
     assert seen["buckets"] > 10 and seen["launched"] >= seen["buckets"] - 3 and any(n.startswith("fusion.temporal_attn") for n in blocked), seen
     assert train._REDUCER is None and all(flat._launched)
+
+
+def test_flat_params_optimizer_state_round_trips_with_torch_adamw(tmp_path):
+    """Resume: FlatParams speaks torch.optim's state_dict format (train.py.bak:199-246 saves ``optimizer.state_dict()``,
+    utils/model_utils.py:51-62 ``load_optim`` restores it and reads the learning rate from ``param_groups``)."""
+    import copy
+    import torch
+    from fbanet_b200.train import FlatParams
+    from fbanet_b200.utils.model_utils import load_optim, save_checkpoint
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.PReLU(), torch.nn.Linear(7, 3))
+    twin = copy.deepcopy(net)
+    opt = torch.optim.AdamW(twin.parameters(), lr=3e-4, weight_decay=0.02)
+    for _ in range(3):
+        opt.zero_grad()
+        twin(torch.randn(4, 5)).square().mean().backward()
+        opt.step()
+    path = save_checkpoint(str(tmp_path), {"epoch": 3, "state_dict": twin.state_dict(), "optimizer": opt.state_dict()}, "s")
+    flat = FlatParams(net.parameters())
+    assert flat.state_dict()["state"] == {} and len(flat.state_dict()["param_groups"][0]["params"]) == 5
+    lr = load_optim(flat, path)                                            # the reference helper, FlatParams in the optimizer's place
+    assert lr == 3e-4 and flat.step == 3 and flat.param_groups[0]["weight_decay"] == 0.02
+    for i, (p, o) in enumerate(zip(flat.params, flat.offsets)):
+        st = opt.state[list(twin.parameters())[i]]
+        assert torch.equal(flat.exp_avg[o:o + p.numel()].view_as(p), st["exp_avg"])
+        assert torch.equal(flat.exp_avg_sq[o:o + p.numel()].view_as(p), st["exp_avg_sq"])
+    # and back: a torch optimizer resumes from what FlatParams writes
+    opt2 = torch.optim.AdamW(copy.deepcopy(twin).parameters(), lr=1.0)
+    opt2.load_state_dict(flat.state_dict())
+    assert opt2.param_groups[0]["lr"] == 3e-4
+    for a, b in zip(opt.state.values(), opt2.state.values()):
+        assert float(a["step"]) == float(b["step"]) and torch.equal(a["exp_avg"], b["exp_avg"]) and torch.equal(a["exp_avg_sq"], b["exp_avg_sq"])
