@@ -707,6 +707,36 @@ def train_step(model, flat: FlatParams, burst: torch.Tensor, target: torch.Tenso
     return loss
 
 
+def fit(model, flat: FlatParams, batches, nepoch: int, start_epoch: int = 1, lr_initial: float = 1e-4, warmup: bool = True,
+        warmup_epochs: int = 3, weight_decay: float = 0.02, model_dir: Optional[str] = None, checkpoint_every: int = 50,
+        generator: Optional[torch.Generator] = None, group=None, log=None) -> List[float]:
+    """The epoch loop of the reference trainer (``train.py.bak:150-246``) around :func:`train_step`: for every epoch the learning rate
+    of ``--warmup`` + cosine (:func:`warmup_cosine_lr`) or ``StepLR`` (:func:`step_lr`), one step per ``(burst, target)`` pair of
+    ``batches`` (any re-iterable of device tensors), the summed epoch loss, and -- on rank 0, when ``model_dir`` is given -- the
+    reference's checkpoints ``model_latest.pth`` every epoch and ``model_epoch_<e>.pth`` every ``checkpoint_every`` epochs, each
+    ``{"epoch", "state_dict", "optimizer"}`` (``:236-245``; resumable through ``utils.load_checkpoint`` / ``load_start_epoch`` /
+    ``load_optim``).  Validation, best-PSNR tracking and logging sinks are the caller's (the reference's CLI is out of scope).
+    Returns the list of epoch losses."""
+    import os
+    rank0 = not (dist.is_available() and dist.is_initialized()) or dist.get_rank(group) == 0
+    history = []
+    for epoch in range(start_epoch, nepoch + 1):
+        lr = warmup_cosine_lr(epoch, lr_initial, nepoch, warmup_epochs) if warmup else step_lr(epoch, lr_initial)
+        total = None
+        for burst, target in batches:
+            loss = train_step(model, flat, burst, target, lr, weight_decay, generator, group)
+            total = loss[0].clone() if total is None else total + loss[0]          # stays on the device: no sync per step
+        history.append(float(total) if total is not None else 0.0)
+        if log is not None:
+            log(epoch, lr, history[-1])
+        if model_dir is not None and rank0:
+            state = {"epoch": epoch, "state_dict": model.state_dict(), "optimizer": flat.state_dict()}
+            torch.save(state, os.path.join(model_dir, "model_latest.pth"))
+            if epoch % checkpoint_every == 0:
+                torch.save(state, os.path.join(model_dir, "model_epoch_{}.pth".format(epoch)))
+    return history
+
+
 # ------------------------------------------------------------------------------------------------------------------------------
 # learning-rate schedules and stochastic-depth rates of the training configuration (host arithmetic, no tensors)
 # ------------------------------------------------------------------------------------------------------------------------------
