@@ -98,7 +98,7 @@ class FlatParams:
         """The gradient of ``param`` is final (the backward will not touch it again in this step).  Buckets are launched in bucket
         order only -- every rank must issue the same sequence of collectives -- so a bucket that completes early waits for the ones
         before it."""
-        if id(param) in self._ready:
+        if id(param) in self._ready or id(param) not in self._bucket_of:      # (a frozen parameter is not part of the flat buffers)
             return
         self._ready.add(id(param))
         self._pending[self._bucket_of[id(param)]] -= 1
