@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBANET_B200_LIB") or os.path.join(_HERE, "csrc", "libfbanet_b200.so")   # env override: A/B two builds in one process tree
-ABI_VERSION = 21
+ABI_VERSION = 22
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -172,6 +172,7 @@ class TrainLossParams(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("y", C.c_void_p), ("grad", C.c_void_p), ("partial", C.c_void_p), ("loss", C.c_void_p),
         ("eps", C.c_float), ("gw_weight", C.c_float), ("inv_n", C.c_float), ("planes", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("clamp_restored", C.c_int32), ("_pad", C.c_int32),
     ]
 
 

@@ -2,6 +2,8 @@
 //   loss = CharbonnierLoss()(restored, target) + gw_weight * GWLoss()(restored, target)        (losses.py:39-80)
 // forward value AND its gradient with respect to `restored`, in one pass over the images, deterministic (two-stage fp64 reduction).
 //   Charbonnier: mean(sqrt(d^2 + eps^2)),  d = x - y                                   -> dL/dx = d / sqrt(d^2 + eps^2) / N
+//   clamp_restored = 1 (the trainer, train.py.bak:167: `restored = torch.clamp(restored, 0, 1)` BEFORE both criteria): d = clamp(x,0,1) - y
+//                and the Charbonnier gradient is gated by [0 <= x <= 1] too (torch.clamp's gradient); the target is not clamped there.
 //   GW:          mean((1 + 4|Sx*e|)(1 + 4|Sy*e|)|e|),  e = clamp(x,0,1) - clamp(y,0,1), Sx / Sy = Sobel cross-correlations with zero
 //                padding per (n, c) plane (the Sobel filters are linear, so Ix1 - Ix2 = Sx * e)
 //                -> dL/de_q = [A_q B_q sgn(e_q) + sum_p Sx[q-p] 4 sgn(gx_p) B_p C_p + sum_p Sy[q-p] 4 sgn(gy_p) A_p C_p] / N,
@@ -43,10 +45,11 @@ __global__ void __launch_bounds__(TL_THREADS) train_loss_kernel(const fbanet_tra
   if (r < H * W) {
     const int qy = r / W, qx = r - qy * W;
     const float xv = __ldg(x + r), yv = __ldg(y + r);
-    const float d = xv - yv;
+    const bool inside = xv >= 0.f && xv <= 1.f;
+    const float d = (p.clamp_restored ? tl_clamp01(xv) : xv) - yv;
     const float root = sqrtf(fmaf(d, d, p.eps * p.eps));
     part_c = (double)root;
-    float grad = d / root * p.inv_n;                                           // Charbonnier
+    float grad = (p.clamp_restored && !inside) ? 0.f : d / root * p.inv_n;     // Charbonnier
     if (p.gw_weight != 0.f) {
       float gxq, gyq, eq;
       tl_sobel(x, y, H, W, qy, qx, gxq, gyq, eq);
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(TL_THREADS) train_loss_kernel(const fbanet_tra
           const float Ap = 1.f + 4.f * fabsf(gxp), Bp = 1.f + 4.f * fabsf(gyp), Cp = fabsf(ep);
           ge += SX[2 - i][2 - j] * 4.f * tl_sgn(gxp) * Bp * Cp + SY[2 - i][2 - j] * 4.f * tl_sgn(gyp) * Ap * Cp;
         }
-      if (xv >= 0.f && xv <= 1.f) grad = fmaf(p.gw_weight * p.inv_n, ge, grad);
+      if (inside) grad = fmaf(p.gw_weight * p.inv_n, ge, grad);
     }
     if (p.grad) p.grad[(int64_t)plane * H * W + r] = grad;
   }

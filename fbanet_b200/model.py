@@ -232,7 +232,11 @@ class BaseModel(nn.Module):
     # -- weight packing --------------------------------------------------------------------------
     def _signature(self):
         dev = self.head.weight.device
-        return (str(dev), self.compute_dtype, tuple(p._version for p in self.parameters()), tuple(p.data_ptr() for p in self.parameters()))
+        # parameters re-pointed into train.FlatParams are updated by a raw-pointer kernel (no version bump, same address): its
+        # `generation` counter stands in for them
+        flats = {id(f): f for f in (getattr(p, "_fbanet_flat", None) for p in self.parameters()) if f is not None}
+        return (str(dev), self.compute_dtype, tuple(p._version for p in self.parameters()), tuple(p.data_ptr() for p in self.parameters()),
+                tuple(f.generation for f in flats.values()))
 
     def packed(self) -> Dict[str, torch.Tensor]:
         """Kernel-ready weights (K-major GEMM operands, fp32 biases), cached until parameters change."""

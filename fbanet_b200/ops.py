@@ -536,9 +536,12 @@ def ecc_homography_burst(burst: torch.Tensor, layout: str = "BTCHW", gray_weight
     return M, rho, iters
 
 
-def training_loss(restored: torch.Tensor, target: torch.Tensor, eps: float = 1e-3, gw_weight: float = 3.0, need_grad: bool = True):
+def training_loss(restored: torch.Tensor, target: torch.Tensor, eps: float = 1e-3, gw_weight: float = 3.0, need_grad: bool = True,
+                  clamp_restored: bool = False):
     """Training loss of the reference trainer (``train.py.bak:118-119,168``): ``CharbonnierLoss()(restored, target) + 3 *
     GWLoss()(restored, target)`` (``losses.py:39-80``) and its gradient with respect to ``restored`` in one kernel pass.
+    ``clamp_restored``: the trainer's ``restored = torch.clamp(restored, 0, 1)`` (``train.py.bak:167``) in front of BOTH criteria
+    (``train_step`` turns it on); off = the bare ``losses.py`` criteria.
 
     ``restored``, ``target``: fp32 ``[B,C,H,W]`` on the GPU.  Returns ``(loss [3] float64 = (total, charbonnier, gw), grad or None)``."""
     assert restored.is_cuda and restored.dtype == torch.float32 and restored.is_contiguous() and restored.dim() == 4
@@ -553,7 +556,7 @@ def training_loss(restored: torch.Tensor, target: torch.Tensor, eps: float = 1e-
     p.x, p.y, p.partial, p.loss = restored.data_ptr(), target.data_ptr(), ws.data_ptr(), loss.data_ptr()
     p.grad = grad.data_ptr() if grad is not None else None
     p.eps, p.gw_weight, p.inv_n = float(eps), float(gw_weight), 1.0 / restored.numel()
-    p.planes, p.H, p.W = B * Cc, H, W
+    p.planes, p.H, p.W, p.clamp_restored = B * Cc, H, W, int(bool(clamp_restored))
     _call("fbanet_train_loss_sm100", p, nbytes=restored.numel() * 4 * (3 if need_grad else 2))
     return loss, grad
 

@@ -39,10 +39,12 @@ class FlatParams:
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.step = 0
+        self.generation = 0                         # bumped by every raw-pointer update of `data` (see adam_step)
         for p, o in zip(self.params, self.offsets):
             self.data[o:o + p.numel()].copy_(p.data.reshape(-1))
             p.data = self.data[o:o + p.numel()].view_as(p)                # the parameter now lives inside the flat buffer
             p.grad = self.grad[o:o + p.numel()].view_as(p)                # and its gradient inside the flat gradient buffer
+            p._fbanet_flat = self                                         # BaseModel._signature reads `generation` through this
 
     def zero_grad(self) -> None:
         self.grad.zero_()
@@ -125,6 +127,9 @@ class FlatParams:
         self.step += 1
         self.param_groups[0].update(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
         ops.adam_step(self.data, self.grad, self.exp_avg, self.exp_avg_sq, self.step, lr, betas, eps, weight_decay, decoupled, grad_scale)
+        # the kernel writes through a raw pointer: neither a parameter's version counter nor its address changes, so the model's
+        # packed-weight / CUDA-graph caches (BaseModel.packed, _host_graph) are told explicitly that the weights moved
+        self.generation += 1
 
     def optimizer_state(self) -> dict:
         return {"step": self.step, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
@@ -315,7 +320,7 @@ def _linear_backward(lin_weight: torch.Tensor, x4: torch.Tensor, dy4: torch.Tens
 
 
 def lewin_forward_train(ly, x: torch.Tensor, s_attn: Optional[torch.Tensor] = None, s_mlp: Optional[torch.Tensor] = None,
-                        gelu_act: Optional[int] = None, eps: float = 1e-5):
+                        gelu_act: Optional[int] = None, eps: float = 1e-5, qk_scale: Optional[float] = None):
     """(Parameters are used in their stored dtype: the fp32 masters the C-ABI ops require.)
     Training-mode forward of one LeWin block (``FBANetLayer.__call__``, ``layers/fba_net.py:139-250`` with the residuals of SURVEY
     Appendix A-4): ``x1 = x + s_attn * proj(attn(qkv(LN1 x)))``, ``y = x1 + s_mlp * fc2(gelu(dw(gelu(fc1(LN2 x1)))))``.  ``ly``: the
@@ -331,7 +336,7 @@ def lewin_forward_train(ly, x: torch.Tensor, s_attn: Optional[torch.Tensor] = No
     s_attn = ones if s_attn is None else s_attn
     s_mlp = ones if s_mlp is None else s_mlp
     a = ly.attn
-    scale = (C // ly.heads) ** -0.5
+    scale = qk_scale or (C // ly.heads) ** -0.5          # `qk_scale or head_dim ** -0.5` (layers/window_attention.py:141-142)
     ln1 = ops.layernorm(x.view(T, C), ly.norm1.weight.detach(), ly.norm1.bias.detach(), eps).view(B, H, W, C)
     wqkv = torch.cat([a.qkv.to_q.weight.detach(), a.qkv.to_kv.weight.detach()], 0)
     bqkv = torch.cat([a.qkv.to_q.bias.detach(), a.qkv.to_kv.bias.detach()], 0)
@@ -426,13 +431,15 @@ class Tape:
         return grads                                                       # what is left: gradients of the tape's inputs, by id()
 
 
-def _t_block(tape: Tape, block, x: torch.Tensor, rates, generator, training: bool) -> torch.Tensor:
-    """A ``_Block`` (``blocks/fba_net.py:35-65``): its LeWin layers in sequence, each with its own stochastic-depth rate."""
+def _t_block(tape: Tape, block, x: torch.Tensor, rates, scales, training: bool, gelu_act: Optional[int] = None,
+             qk_scale: Optional[float] = None) -> torch.Tensor:
+    """A ``_Block`` (``blocks/fba_net.py:35-65``): its LeWin layers in sequence, each with its own stochastic-depth rate.
+    ``scales``: the step's :class:`DropPathDraws` (per-burst multipliers of every DropPath call, drawn once per step)."""
     for ly, rate in zip(block.blocks, rates):
         B = x.shape[0]
-        s1 = drop_path_scales(B, rate, generator, x.device) if (training and rate > 0.0) else None
-        s2 = drop_path_scales(B, rate, generator, x.device) if (training and rate > 0.0) else None
-        y, saved = lewin_forward_train(ly, x, s1, s2)
+        s1 = scales.next(B, rate) if (training and rate > 0.0) else None
+        s2 = scales.next(B, rate) if (training and rate > 0.0) else None
+        y, saved = lewin_forward_train(ly, x, s1, s2, gelu_act=gelu_act, qk_scale=qk_scale)
         x = tape.record(y, (lambda ly, saved, xin: (lambda g: [(xin, lewin_backward(ly, saved, g))]))(ly, saved, x))
     return x
 
@@ -564,38 +571,65 @@ def _faf_on_tape(tape: Tape, fu, feat: torch.Tensor) -> torch.Tensor:
     return _t_add(tape, _t_conv(tape, fu.fusion_tail, r4), z)
 
 
+_HG_BLOCKS = ("encoderlayer_0", "encoderlayer_1", "conv", "decoderlayer_0", "decoderlayer_1")
+
+
+class DropPathDraws:
+    """All DropPath multipliers of one training step, drawn in one go: the host generator is consumed in exactly the order the
+    forward will ask for them (per hourglass: the five blocks in execution order, per layer the attention branch then the LeFF
+    branch; layers with rate 0 draw nothing), stacked ``[calls, batch]`` and sent to the device with ONE pinned asynchronous copy
+    instead of ~40 small synchronous ones.  :meth:`next` hands out the rows in that order."""
+
+    def __init__(self, model, hourglasses: int, batch: int, generator: Optional[torch.Generator], device, training: bool = True):
+        rates = drop_path_rates(tuple(model.depths), model.drop_path_rate)
+        self.rates = [r for _ in range(hourglasses) for b in _HG_BLOCKS for r in rates[b] for _ in (0, 1) if r > 0.0] if training else []
+        rows = [drop_path_scales(batch, r, generator) for r in self.rates]
+        host = torch.stack(rows) if rows else torch.empty((0, batch), dtype=torch.float32)
+        if torch.device(device).type == "cuda" and rows:
+            host = host.pin_memory()
+        self.scales = host.to(device, non_blocking=True)
+        self.k = 0
+
+    def next(self, batch: int, rate: float) -> torch.Tensor:
+        assert self.k < len(self.rates) and self.rates[self.k] == rate and self.scales.shape[1] == batch, "DropPath draws out of order"
+        self.k += 1
+        return self.scales[self.k - 1]
+
+
 def hourglass_forward_train(model, hg: str, y: torch.Tensor, generator: Optional[torch.Generator] = None, training: bool = True):
     """Training-mode forward of the first LeWin hourglass (``models/fba_net.py:271-287``; ``hg = "HG1"``): encoder blocks, 4x4 s2
     downsamples, bottleneck, 2x2 transposed-conv upsamples concatenated with the encoder outputs, decoder blocks -- ten LeWin layers
     with the per-layer DropPath rates of :func:`drop_path_rates`.  ``y`` ``[B,S,S,E]`` channels-last.  Returns ``(deconv1, tape)``;
     ``tape.backward(deconv1, d_deconv1)`` accumulates every parameter gradient and returns ``{id(y): dy}``."""
     tape = Tape()
-    return _hourglass_on_tape(tape, model, hg, y, None, generator, training)[0], tape
+    draws = DropPathDraws(model, 1, y.shape[0], generator, y.device, training)
+    return _hourglass_on_tape(tape, model, hg, y, None, draws, training)[0], tape
 
 
-def _hourglass_on_tape(tape: Tape, model, hg: str, y: torch.Tensor, prev, generator, training: bool):
+def _hourglass_on_tape(tape: Tape, model, hg: str, y: torch.Tensor, prev, draws: DropPathDraws, training: bool):
     """``prev``: ``(up0, conv1, up1, conv0)`` of the first hourglass -- the second one (``models/fba_net.py:294-310``) feeds its decoders
     ``output_proj_HG2_k(cat[prev pair, own pair])`` (conv3x3 + PReLU) instead of the plain concat."""
     from . import _lib as L
     g = lambda n: getattr(model, n)
     rates = drop_path_rates(tuple(model.depths), model.drop_path_rate)
-    conv0 = _t_block(tape, g(f"{hg}_encoderlayer_0"), y, rates["encoderlayer_0"], generator, training)
+    act, qks = model.gelu_act, model.qk_scale            # the same GELU flavour and attention scale the inference path uses
+    conv0 = _t_block(tape, g(f"{hg}_encoderlayer_0"), y, rates["encoderlayer_0"], draws, training, act, qks)
     pool0 = _t_down(tape, g(f"{hg}_downsample_0").conv[0], conv0)
-    conv1 = _t_block(tape, g(f"{hg}_encoderlayer_1"), pool0, rates["encoderlayer_1"], generator, training)
+    conv1 = _t_block(tape, g(f"{hg}_encoderlayer_1"), pool0, rates["encoderlayer_1"], draws, training, act, qks)
     pool1 = _t_down(tape, g(f"{hg}_downsample_1").conv[0], conv1)
-    conv2 = _t_block(tape, g(f"conv_{hg}"), pool1, rates["conv"], generator, training)
+    conv2 = _t_block(tape, g(f"conv_{hg}"), pool1, rates["conv"], draws, training, act, qks)
     up0 = _t_up(tape, g(f"{hg}_upsample_0").deconv[0], conv2)
     d0_in = _t_cat(tape, up0, conv1)
     if prev is not None:
         pr = model.output_proj_HG2_0.proj
         d0_in = _t_conv(tape, pr[0], _t_cat(tape, _t_cat(tape, prev[0], prev[1]), d0_in), L.ACT_PRELU, pr[1].weight)
-    deconv0 = _t_block(tape, g(f"{hg}_decoderlayer_0"), d0_in, rates["decoderlayer_0"], generator, training)
+    deconv0 = _t_block(tape, g(f"{hg}_decoderlayer_0"), d0_in, rates["decoderlayer_0"], draws, training, act, qks)
     up1 = _t_up(tape, g(f"{hg}_upsample_1").deconv[0], deconv0)
     d1_in = _t_cat(tape, up1, conv0)
     if prev is not None:
         pr = model.output_proj_HG2_1.proj
         d1_in = _t_conv(tape, pr[0], _t_cat(tape, _t_cat(tape, prev[2], prev[3]), d1_in), L.ACT_PRELU, pr[1].weight)
-    deconv1 = _t_block(tape, g(f"{hg}_decoderlayer_1"), d1_in, rates["decoderlayer_1"], generator, training)
+    deconv1 = _t_block(tape, g(f"{hg}_decoderlayer_1"), d1_in, rates["decoderlayer_1"], draws, training, act, qks)
     return deconv1, (up0, conv1, up1, conv0)
 
 
@@ -678,9 +712,10 @@ def model_forward_train(model, burst: torch.Tensor, generator: Optional[torch.Ge
     fused = _faf_on_tape(tape, model.fusion, feat)
     proj = lambda m, x: _t_conv(tape, m.proj[0], x, L.ACT_PRELU, m.proj[1].weight)
     y = proj(model.input_proj, fused)
-    d1, prev = _hourglass_on_tape(tape, model, "HG1", y, None, generator, training)
+    draws = DropPathDraws(model, 2, B, generator, burst.device, training)
+    d1, prev = _hourglass_on_tape(tape, model, "HG1", y, None, draws, training)
     y1 = proj(model.output_proj, d1)
-    d2, _ = _hourglass_on_tape(tape, model, "HG2", y1, prev, generator, training)
+    d2, _ = _hourglass_on_tape(tape, model, "HG2", y1, prev, draws, training)
     y2 = proj(model.output_proj_2, d2)
     t2 = _t_ps_conv(tape, model.tail[0][2], _t_ps_conv(tape, model.tail[0][0], y2))
     return _t_final(tape, model.tail[1], t2, burst[:, 0]), tape
@@ -695,7 +730,7 @@ def train_step(model, flat: FlatParams, burst: torch.Tensor, target: torch.Tenso
     global _REDUCER
     flat.zero_grad()
     restored, tape = model_forward_train(model, burst, generator, training=True)
-    loss, d_restored = ops.training_loss(restored, target)
+    loss, d_restored = ops.training_loss(restored, target, clamp_restored=True)      # train.py.bak:167: clamp(restored, 0, 1) first
     flat.begin_reduce(group, bucket_bytes)
     _REDUCER = flat
     try:
@@ -716,9 +751,23 @@ def fit(model, flat: FlatParams, batches, nepoch: int, start_epoch: int = 1, lr_
     reference's checkpoints ``model_latest.pth`` every epoch and ``model_epoch_<e>.pth`` every ``checkpoint_every`` epochs, each
     ``{"epoch", "state_dict", "optimizer"}`` (``:236-245``; resumable through ``utils.load_checkpoint`` / ``load_start_epoch`` /
     ``load_optim``).  Validation, best-PSNR tracking and logging sinks are the caller's (the reference's CLI is out of scope).
-    Returns the list of epoch losses."""
+    ``generator`` (DropPath): default = a per-rank ``Generator`` seeded ``1234 + rank``.  Under data parallelism every rank must
+    supply the SAME number of batches per epoch (asserted when ``batches`` has a length).  Returns the list of epoch losses."""
     import os
-    rank0 = not (dist.is_available() and dist.is_initialized()) or dist.get_rank(group) == 0
+    distributed = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if distributed else 0
+    rank0 = rank == 0
+    if generator is None:
+        # the reference seeds every process alike (train.py.bak:56-59, 1234); data-parallel ranks hold DIFFERENT bursts, so each
+        # draws its own DropPath pattern: seed + rank
+        generator = torch.Generator().manual_seed(1234 + rank)
+    if distributed and dist.get_world_size(group) > 1 and hasattr(batches, "__len__"):
+        # every rank must take the same number of steps: a rank that runs out early would leave the others in finish_reduce
+        n = torch.tensor([len(batches)], dtype=torch.int64, device=flat.data.device)
+        lo, hi = n.clone(), n.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+        assert lo.item() == hi.item(), f"ranks hold different numbers of batches ({lo.item()}..{hi.item()}): pad or drop the last ones"
     history = []
     for epoch in range(start_epoch, nepoch + 1):
         lr = warmup_cosine_lr(epoch, lr_initial, nepoch, warmup_epochs) if warmup else step_lr(epoch, lr_initial)

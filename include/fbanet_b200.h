@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 21
+#define FBANET_ABI_VERSION 22
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -349,6 +349,8 @@ typedef struct fbanet_ecc_params {
  * value and gradient with respect to `restored` in one pass.  x = restored, y = target: planar fp32 [planes = B*C][H][W];
  * inv_n = 1 / (planes*H*W) (both losses are means); eps = 1e-3, gw_weight = 3 in the reference; gw_weight = 0 skips GWLoss.
  * partial: workspace of fbanet_train_loss_workspace_doubles(planes, H, W) doubles; loss: 3 doubles (total, Charbonnier, GW).
+ * clamp_restored = 1 restates train.py.bak:167 (clamp of the network output before the criteria): Charbonnier then sees
+ * clamp(x,0,1) - y and passes no gradient where x left [0,1]; 0 = the bare losses.py criteria on x as given.
  * The reduction is two-stage in fp64 with a fixed order: results are bit-reproducible. */
 typedef struct fbanet_train_loss_params {
   const float* x;
@@ -358,6 +360,8 @@ typedef struct fbanet_train_loss_params {
   double* loss;
   float eps, gw_weight, inv_n;
   int32_t planes, H, W;
+  int32_t clamp_restored; /* 1: the trainer's `restored = clamp(restored, 0, 1)` (train.py.bak:167) applied before BOTH criteria */
+  int32_t _pad;
 } fbanet_train_loss_params;
 
 /* Optimizer step: torch.optim.Adam / AdamW(lr, betas=(0.9, 0.999), eps=1e-8, weight_decay), train.py.bak:72-78, over

@@ -740,6 +740,9 @@ def gw_loss(x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
     return torch.mean((1 + 4 * dx) * (1 + 4 * dy) * torch.abs(x1 - x2))
 
 
-def training_loss(x: torch.Tensor, y: torch.Tensor, eps: float = 1e-3, gw_weight: float = 3.0) -> torch.Tensor:
-    """`criterion1(restored, target) + 3 * criterion2(restored, target)` (train.py.bak:168)."""
+def training_loss(x: torch.Tensor, y: torch.Tensor, eps: float = 1e-3, gw_weight: float = 3.0, clamp_restored: bool = False) -> torch.Tensor:
+    """`criterion1(restored, target) + 3 * criterion2(restored, target)` (train.py.bak:168); `clamp_restored`: with the trainer's
+    `restored = torch.clamp(restored, 0, 1)` of train.py.bak:167 in front of both criteria."""
+    if clamp_restored:
+        x = torch.clamp(x, 0.0, 1.0)
     return charbonnier_loss(x, y, eps) + gw_weight * gw_loss(x, y)

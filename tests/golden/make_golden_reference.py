@@ -53,8 +53,13 @@ c1, c2 = ref_losses.CharbonnierLoss(), ref_losses.GWLoss(rgb_range=1.0)
 lc, lg = c1(lx, ly), c2(lx, ly)
 total = lc + 3 * lg                                          # train.py.bak:168
 total.backward()
+# the same pair through the trainer's two lines as written (train.py.bak:167-168): clamp(restored, 0, 1), then both criteria
+lx2 = lx.detach().clone().requires_grad_(True)
+restored = torch.clamp(lx2, 0, 1)
+tc = c1(restored, ly) + 3 * c2(restored, ly)
+tc.backward()
 np.savez_compressed(os.path.join(HERE, "loss_reference.npz"), x=lx.detach().numpy(), y=ly.numpy(), charbonnier=lc.item(), gw=lg.item(),
-                    total=total.item(), grad=lx.grad.numpy())
+                    total=total.item(), grad=lx.grad.numpy(), total_clamped=tc.item(), grad_clamped=lx2.grad.numpy())
 print("reference loss fixtures:", lc.item(), lg.item(), total.item())
 
 # ---- learning-rate schedules of the training configuration (8f-3): the reference's own `warmup_scheduler/scheduler.py` (torch-only)

@@ -236,7 +236,7 @@ def _train_step_worker(rank, world, port, q):
     # one process, the whole batch (no process group involvement: world-1 semantics through a fresh FlatParams and all_reduce skipped)
     m1, flat1 = make()
     restored, tape = train.model_forward_train(m1, bursts, training=False)
-    loss, d = ops.training_loss(restored, targets)
+    loss, d = ops.training_loss(restored, targets, clamp_restored=True)      # what train_step computes (train.py.bak:167)
     tape.backward(restored, d)
     err = ((dp_grad - flat1.grad).abs().max() / flat1.grad.abs().max()).item()
     dist.barrier()

@@ -650,6 +650,10 @@ def test_training_loss_matches_vectors_from_the_reference_code(cuda):
     assert abs(loss[0].item() - float(d["total"])) < 1e-5 * float(d["total"]) and abs(loss[1].item() - float(d["charbonnier"])) < 1e-6
     assert abs(loss[2].item() - float(d["gw"])) < 1e-5 * float(d["gw"])
     assert np.abs(grad.cpu().numpy() - d["grad"]).max() < 1e-5 * np.abs(d["grad"]).max()
+    # train.py.bak:167-168 as written: clamp(restored, 0, 1) before both criteria (what train_step computes)
+    loss, grad = ops.training_loss(torch.from_numpy(d["x"]).to(cuda), torch.from_numpy(d["y"]).to(cuda), clamp_restored=True)
+    assert abs(loss[0].item() - float(d["total_clamped"])) < 1e-5 * float(d["total_clamped"])
+    assert np.abs(grad.cpu().numpy() - d["grad_clamped"]).max() < 1e-5 * np.abs(d["grad_clamped"]).max()
 
 
 @pytest.mark.parametrize("decoupled,wd", [(True, 0.02), (False, 0.02), (True, 0.0)])

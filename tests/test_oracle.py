@@ -248,3 +248,10 @@ def test_training_loss_oracle_matches_vectors_from_the_reference_code():
     total.backward()
     assert abs(total.item() - float(d["total"])) < 1e-6
     assert np.abs(x.grad.numpy() - d["grad"]).max() < 1e-7
+    # the trainer's two lines as written (train.py.bak:167-168): clamp(restored, 0, 1) in front of both criteria
+    xc = torch.from_numpy(d["x"]).requires_grad_(True)
+    tc = training_loss(xc, y, clamp_restored=True)
+    tc.backward()
+    assert abs(tc.item() - float(d["total_clamped"])) < 1e-6
+    assert np.abs(xc.grad.numpy() - d["grad_clamped"]).max() < 1e-7
+    assert np.abs(d["grad_clamped"] - d["grad"]).max() > 1e-6                # the fixture does leave [0, 1]: the two differ

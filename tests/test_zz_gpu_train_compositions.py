@@ -216,7 +216,7 @@ def test_whole_model_training_step_on_the_gpu(cuda):
     burst = torch.rand(B, 3, 3, 40, 40, generator=torch.Generator().manual_seed(1))
     target = torch.rand(B, 3, 160, 160, generator=torch.Generator().manual_seed(2))
     ref = o(burst.double())
-    loss_ref = training_loss(ref, target.double())
+    loss_ref = training_loss(ref, target.double(), clamp_restored=True)  # train.py.bak:167-168
     loss_ref.backward()
     m = m.to(cuda)
     bd, td = burst.to(cuda), target.to(cuda)
@@ -227,7 +227,7 @@ def test_whole_model_training_step_on_the_gpu(cuda):
     before = ops.LAUNCHES
     restored, tape = train.model_forward_train(m, bd, training=False)
     assert _rel(restored, infer) < 1e-4 and _rel(restored.cpu(), ref.detach()) < 1e-3
-    loss, d_restored = ops.training_loss(restored, td)
+    loss, d_restored = ops.training_loss(restored, td, clamp_restored=True)
     assert abs(loss[0].item() - loss_ref.item()) < 1e-4 * loss_ref.item()
     assert tape.backward(restored, d_restored) == {}
     assert ops.LAUNCHES - before >= 20 * 30 + 100                          # the C-ABI ops ran: no torch arithmetic on the path
@@ -249,3 +249,9 @@ def test_whole_model_training_step_on_the_gpu(cuda):
     l2 = train.train_step(m, flat, bd, td, lr=2e-4)
     l3 = train.train_step(m, flat, bd, td, lr=2e-4)
     assert flat.step == 3 and torch.isfinite(l3).all() and l3[0].item() < l1[0].item(), (l1, l2, l3)
+    # inference after training sees the UPDATED weights: the optimizer kernel writes through a raw pointer (no version bump, same
+    # address), so the packed-weight cache is invalidated through FlatParams.generation
+    after, _ = train.model_forward_train(m, bd, training=False)
+    assert _rel(m(bd), after) < 1e-4 and _rel(m(bd), infer) > 1e-4
+    out_host = m.infer_host(burst)                                         # the CUDA-graph path re-captures too
+    assert _rel(out_host, after.cpu()) < 1e-4
