@@ -113,11 +113,18 @@ class FlatParams:
 
     def finish_reduce(self) -> float:
         """Launch the buckets not yet launched, wait for all of them; returns 1 / world like :meth:`all_reduce`."""
+        ev = getattr(self, "reduce_events", None)          # a list: record (before, after) CUDA events = the EXPOSED reduction time
+        if ev is not None and self.grad.is_cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         for bi in range(len(self._buckets)):
             self._launch(bi)
         for h in self._handles:
             h.wait()
         self._handles = []
+        if ev is not None and self.grad.is_cuda:
+            e1.record()
+            ev.append((e0, e1))
         return 1.0 / self._world
 
     def adam_step(self, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, decoupled: bool = True,

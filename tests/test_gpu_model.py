@@ -107,13 +107,34 @@ def _psnr_delta(cuda, seed, fold_ln=False):
     return delta, direct
 
 
-@pytest.mark.parametrize("seed", [0, 1, 2])
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_full_config_bf16_psnr_delta(cuda, seed):
-    """north-star tolerance for the bf16 path: |PSNR(bf16, gt) - PSNR(oracle, gt)| <= 0.01 dB on the full cfg2 shape, for three
-    independent weight / burst draws (the delta is a projection of the fixed weight-rounding perturbation: 0.001 .. 0.007 dB)."""
+    """north-star tolerance for the bf16 path: |PSNR(bf16, gt) - PSNR(oracle, gt)| <= 0.01 dB on the full cfg2 shape, for eight
+    independent weight / burst draws (the delta is a projection of the fixed weight-rounding perturbation onto the image).
+    Fails at 0.01 dB, warns from 0.008 dB."""
+    import warnings
     delta, direct = _psnr_delta(cuda, seed)
     assert delta <= 0.01, delta
     assert direct >= 40.0, direct
+    if delta > 0.008:
+        warnings.warn(f"bf16 PSNR delta {delta:.4f} dB for seed {seed} is within 20 % of the 0.01 dB tolerance")
+
+
+def test_full_config_bf16_batch_invariance_and_graph_replay(cuda):
+    """The benchmarked path itself (bf16, embed 64, 160x160: every contraction on the tcgen05 kernels): a batch of 4 equals four
+    single-burst forwards BIT FOR BIT (bursts are independent units, jax.vmap(model), train.py:35 -- no kernel may let the tile
+    schedule or a neighbouring burst leak into a result), and the CUDA-graph replay of `infer_host` (whole batch and 2-burst
+    chunks) equals the eager forward."""
+    _, m = _pair(FULL, "bf16", cuda, seed=1)
+    x = _burst(FULL, 4, seed=4)
+    xd = x.to(cuda)
+    full = m(xd).cpu()
+    for i in range(4):
+        assert torch.equal(m(xd[i:i + 1]).cpu(), full[i:i + 1]), i
+    assert m.host_graphs
+    for chunk in (4, 2):
+        for _ in range(2):
+            assert torch.equal(m.infer_host(x, chunk=chunk), full), chunk
 
 
 def test_full_config_bf16_layernorm_fold(cuda):
@@ -210,6 +231,37 @@ def test_raw_config_with_warp_front_end_bf16(cuda):
     got = m(xw).cpu()
     assert got.shape == (1, 4, 320, 320)
     assert psnr(got, ref) > 40.0
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_raw_config_batch64_perspective_warp_against_oracle(cuda, dtype):
+    """BASELINE config 3 at its full batch: 64 packed-Bayer bursts (14x4x80x80), every frame warped by its own homography with a
+    NON-ZERO perspective row (translation U(-4,4) px, affine U(-0.01,0.01), perspective U(-1e-5,1e-5)), warp + forward
+    in one batch-64 call; one burst of each 32-burst host chunk is checked against the oracle (fp32: <= 1e-3 max abs and warp
+    <= 2e-6; bf16: PSNR > 40 dB)."""
+    import numpy as np
+    from fbanet_b200 import ops
+    from oracle.fbanet_oracle import psnr, warp_burst as warp_ref
+    o, m = _pair(RAW, dtype, cuda)
+    B, T = 64, RAW["num_frames"]
+    x = _burst(RAW, B, seed=3)
+    g = torch.Generator().manual_seed(1)
+    M = torch.eye(3, dtype=torch.float64).repeat(B, T, 1, 1)
+    M[:, 1:, :2, 2] = torch.rand(B, T - 1, 2, generator=g, dtype=torch.float64) * 8 - 4
+    M[:, 1:, :2, :2] += torch.rand(B, T - 1, 2, 2, generator=g, dtype=torch.float64) * 0.02 - 0.01
+    M[:, 1:, 2, :2] = torch.rand(B, T - 1, 2, generator=g, dtype=torch.float64) * 2e-5 - 1e-5
+    xw = ops.warp_burst(x.to(cuda), M.to(cuda))
+    got = m(xw).cpu()
+    assert got.shape == (B, 4, 320, 320)
+    for i in (5, 37):
+        ref_w = torch.from_numpy(np.asarray(warp_ref(x[i].permute(0, 2, 3, 1).numpy(), M[i].numpy()), np.float32)).permute(0, 3, 1, 2)[None].contiguous()
+        assert (xw[i:i + 1].cpu() - ref_w).abs().max().item() < 2e-6
+        with torch.no_grad():
+            ref = o(ref_w)
+        if dtype == "fp32":
+            assert (got[i:i + 1] - ref).abs().max().item() <= 1e-3, (i, (got[i:i + 1] - ref).abs().max().item())
+        else:
+            assert psnr(got[i:i + 1], ref) > 40.0, (i, psnr(got[i:i + 1], ref))
 
 
 def test_forward_unaligned_registers_then_restores(cuda):
