@@ -192,6 +192,8 @@ class BaseModel(nn.Module):
         self.gelu_act = {"tanh": L.ACT_GELU_TANH, "erf": L.ACT_GELU_ERF}[gelu]
         self.impl = impl
         self.fuse_leff = True
+        # dim <= 128 layers: the whole LeFF MLP in one kernel (ops.leff_mlp); FBANET_FUSE_MLP=0 keeps fc1 + leff_fc2
+        self.fuse_mlp = os.environ.get("FBANET_FUSE_MLP", "1") == "1"
         # bf16 path, optional: LayerNorm folded into the qkv / fc1 GEMMs (row statistics only; ops.fold_layernorm).  -1.3 ms per
         # batch-64 step and a lower mean PSNR delta over seeds (0.0043 vs 0.0049 dB), but one of three seeds lands at 0.0105 dB,
         # 5 % over the 0.01 dB parity tolerance, so it stays off by default; FBANET_FOLD_LN=1 (or the attribute) turns it on.
@@ -337,6 +339,12 @@ class BaseModel(nn.Module):
                     dw = ly.mlp.dwconv[0]
                     P[k + ".dw.w"] = dw.weight.detach().float().reshape(dw.weight.shape[0], 9).t().contiguous()
                     P[k + ".dw.b"] = f32(dw.bias)
+                    if tc and ly.dim <= 128 and not self.fold_ln:
+                        # one-kernel LeFF MLP (ops.leff_mlp): its contract wants HALF of linear1 / dwconv (exact: a power of two)
+                        P[k + ".fc1.wh"] = (0.5 * ly.mlp.linear1[0].weight.detach().float()).to(T).contiguous()
+                        P[k + ".fc1.bh"] = (0.5 * f32(ly.mlp.linear1[0].bias)).contiguous()
+                        P[k + ".dw.wh"] = (0.5 * P[k + ".dw.w"]).contiguous()
+                        P[k + ".dw.bh"] = (0.5 * P[k + ".dw.b"]).contiguous()
             put_conv(f"{hg}_downsample_0", getattr(self, f"{hg}_downsample_0").conv[0])
             put_conv(f"{hg}_downsample_1", getattr(self, f"{hg}_downsample_1").conv[0])
             put_convT(f"{hg}_upsample_0", getattr(self, f"{hg}_upsample_0").deconv[0])
@@ -424,6 +432,13 @@ class BaseModel(nn.Module):
             h = self._lin(P, key + ".fc1", x1, act=self.gelu_act, ln_stats=ops.row_stats(x1.view(-1, Cd)))
         else:
             ln2 = ops.layernorm(x1.view(-1, Cd), P[key + ".ln2.g"], P[key + ".ln2.b"]).view(B, H, W, Cd)
+            if self.fuse_mlp and (key + ".fc1.wh") in P:
+                # fc1 -> GELU -> depthwise 3x3 -> GELU -> fc2 + residual in ONE kernel: the 4C-channel hidden map never leaves the SM
+                if out is None:
+                    out = self._new(B, H, W, Cd)
+                if ops.leff_mlp(ln2, P[key + ".fc1.wh"], P[key + ".fc1.bh"], P[key + ".dw.wh"], P[key + ".dw.bh"], P[key + ".fc2.w"],
+                                P[key + ".fc2.b"], out, x1, self.gelu_act) is not None:
+                    return out
             h = self._lin(P, key + ".fc1", ln2, act=self.gelu_act)
         if self._use_tc() and self.fuse_leff:
             # depthwise 3x3 + GELU computed inside the fc2 GEMM as its A-operand producer (no HBM round trip)

@@ -385,6 +385,37 @@ def leff_fc2(h1: torch.Tensor, dw_w9c: torch.Tensor, dw_b: torch.Tensor, w2: tor
     return out
 
 
+def leff_mlp(x: torch.Tensor, w1h: torch.Tensor, b1h: torch.Tensor, dw_w9c_h: torch.Tensor, dw_bh: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+             out: torch.Tensor, residual: Optional[torch.Tensor], act: int) -> Optional[torch.Tensor]:
+    """The whole LeFF MLP in one kernel (bf16): ``out = Linear2(act(depthwise3x3(act(Linear1(x))) + dw_b)) + b2 + residual``
+    (``layers/locally_enhanced_feed_forward.py:25-57``); the 4C-channel hidden map never goes to HBM.  ``x`` / ``out`` /
+    ``residual``: channels-last views ``[N,H,W,C]``.  ``w1h [Hd,C]`` bf16, ``b1h [Hd]``, ``dw_w9c_h [9,Hd]``, ``dw_bh [Hd]`` hold HALF the
+    layer's values (the kernel's contract, see ``include/fbanet_b200.h``); ``w2 [C,Hd]`` bf16, ``b2 [C]``.  Returns ``None`` when the
+    kernel does not take the shape (C > 128)."""
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4
+    N, H, W, Cc = x.shape
+    Hd = w1h.shape[0]
+    assert w1h.dtype == torch.bfloat16 and w1h.is_contiguous() and w1h.shape == (Hd, Cc)
+    assert w2.dtype == torch.bfloat16 and w2.is_contiguous() and w2.shape == (Cc, Hd) and out.shape == (N, H, W, Cc)
+    assert dw_w9c_h.shape == (9, Hd) and dw_w9c_h.dtype == torch.float32 and dw_w9c_h.is_contiguous()
+    p = L.LeffMlpParams()
+    p.w1, p.bias1, p.dw_weight, p.dw_bias, p.w2, p.bias2 = (w1h.data_ptr(), b1h.data_ptr(), dw_w9c_h.data_ptr(), dw_bh.data_ptr(), w2.data_ptr(),
+                                                          b2.data_ptr())
+    xp, _, xld, xis = _cl(x)
+    p.x, p.x_ld, p.x_img_stride = xp, xld, xis
+    op, _, old, ois = _cl(out)
+    p.out, p.out_ld, p.out_img_stride = op, old, ois
+    if residual is not None:
+        rp, _, rld, ris = _cl(residual)
+        p.residual, p.res_ld, p.res_img_stride = rp, rld, ris
+    p.N, p.H, p.W, p.C, p.Hd, p.act = N, H, W, Cc, Hd, act
+    if not L.load().fbanet_leff_mlp_supported(C.byref(p)):
+        return None
+    _call("fbanet_leff_mlp_sm100", p, tag=f"{Cc}->{Hd}->{Cc} @{H}x{W}",
+          nbytes=(x.numel() + out.numel() * (2 if residual is not None else 1) + w1h.numel() + w2.numel()) * 2)
+    return out
+
+
 def faf_gate(feat: torch.Tensor, wsum: torch.Tensor, want_gate: bool = True, want_gated: bool = False,
              score: Optional[torch.Tensor] = None):
     """feat ``[B,F,H,W,C]`` contiguous -> gate ``[B,F-1,H,W]`` fp32 and/or gated features

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 22
+#define FBANET_ABI_VERSION 23
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -247,6 +247,29 @@ typedef struct fbanet_leff_fc2_params {
   int32_t N, H, W, C, Hd;
   int32_t act;            /* FBANET_ACT_GELU_TANH / _ERF (applied after the depthwise conv) */
 } fbanet_leff_fc2_params;
+
+/* The whole LeFF MLP in one kernel (bf16, tensor cores), hidden tensor never in HBM:
+ *   out = Linear2(GELU(depthwise3x3(GELU(Linear1(x)) reshaped to the H x W map) + b_dw)) + b2 + residual
+ * (layers/locally_enhanced_feed_forward.py:25-57 with the residual of layers/fba_net.py:248; x = LayerNorm2 output).  Linear1 is
+ * recomputed on each 8 x 16 tile's one-pixel halo instead of writing / re-reading the 4C-channel hidden map.
+ * CONTRACT: w1, bias1, dw_weight, dw_bias hold HALF the layer's values (exact scaling by a power of two; the kernel evaluates
+ * GELU on z = x / 2).  w1: bf16 [Hd][C]; dw_weight: fp32 [9][Hd]; w2: bf16 [C][Hd]; C in {64,128}; Hd % 64 == 0, Hd <= 512. */
+typedef struct fbanet_leff_mlp_params {
+  const void* x;          /* view [N,H,W,C]                                                          */
+  const void* w1;
+  const float* bias1;
+  const float* dw_weight;
+  const float* dw_bias;
+  const void* w2;
+  const float* bias2;
+  const void* residual;   /* optional view [N,H,W,C]                                                 */
+  void* out;              /* view [N,H,W,C]                                                          */
+  int64_t x_img_stride, res_img_stride, out_img_stride;
+  int32_t x_ld, res_ld, out_ld;
+  int32_t N, H, W, C, Hd;
+  int32_t act;            /* FBANET_ACT_GELU_TANH / _ERF (both GELUs)                                */
+  int32_t _pad;
+} fbanet_leff_mlp_params;
 
 /* K2 (gate): Federated-Affinity gate (blocks/federated_affinity_fusion.py:79-99).
  * gate[b][f-1][p] = sigmoid(| sum_{tap,c} wsum[tap][c] * (feat[b][f] - feat[b][0])(p+tap, c) |), f >= 1,
@@ -522,6 +545,8 @@ int fbanet_abi_sizeof(const char* struct_name);
 const char* fbanet_last_cuda_error(void);
 /* 1 if the fused LeFF kernel takes this problem, else 0 */
 int fbanet_leff_fc2_supported(const fbanet_leff_fc2_params* p);
+/* 1 if the one-kernel LeFF MLP takes this problem, else 0 */
+int fbanet_leff_mlp_supported(const fbanet_leff_mlp_params* p);
 /* 1 if the tcgen05 implicit-GEMM can run this problem, else 0 */
 int fbanet_conv_gemm_tcgen05_supported(const fbanet_conv_params* p);
 
@@ -536,6 +561,7 @@ int fbanet_window_attention_sm100(const fbanet_attn_params* p, void* stream);
 int fbanet_dwconv3x3_sm100(const fbanet_dwconv_params* p, void* stream);
 int fbanet_faf_gate_sm100(const fbanet_faf_gate_params* p, void* stream);
 int fbanet_leff_fc2_sm100(const fbanet_leff_fc2_params* p, void* stream);
+int fbanet_leff_mlp_sm100(const fbanet_leff_mlp_params* p, void* stream);
 int fbanet_tile_divide_sm100(const fbanet_tile_params* p, void* stream);
 int fbanet_tile_merge_sm100(const fbanet_tile_params* p, void* stream);
 int fbanet_tile_divide_banded_sm100(const fbanet_tile_band_params* p, void* stream);

@@ -205,3 +205,51 @@ def test_fused_leff_dwconv_fc2(cuda, C, Hd, n, h, w):
     assert out is not None
     _check(buf[..., C:], ref, tol=3e-2)
     assert buf[..., :C].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("C,n,h,w,act", [(64, 2, 32, 24, 3), (128, 2, 16, 40, 3), (128, 3, 20, 20, 3), (64, 70, 16, 16, 3), (128, 1, 37, 21, 3),
+                                         (64, 1, 160, 160, 3), (128, 2, 80, 80, 3), (64, 2, 24, 16, 4)])
+@pytest.mark.parametrize("poly", [0, 1])
+def test_fused_leff_mlp_one_kernel(cuda, monkeypatch, C, n, h, w, act, poly):
+    """The whole LeFF MLP in one kernel -- Linear1 + GELU (recomputed on each tile's one-pixel halo) -> depthwise 3x3 + GELU ->
+    Linear2 + residual (locally_enhanced_feed_forward.py:25-57, layers/fba_net.py:248) -- against torch fp32 on bf16-rounded
+    operands: every stage shape of the model with C <= 128 (enc0 64 @160, enc1 128 @80), ragged sizes (37 x 21: partial tiles in
+    both directions, out-of-image halo everywhere), more tiles than SMs (persistent loop, barrier phase wrap), views with a row
+    stride (concat slices), the erf flavour, and the FMA-pipe GELU variant of the second MMA tile (FBANET_LEFF_POLY=1)."""
+    from fbanet_b200 import ops, _lib as L
+    if poly and act == 4:
+        pytest.skip("the polynomial variant exists for tanh-GELU only")
+    monkeypatch.setenv("FBANET_LEFF_POLY", str(poly))
+    Hd = 4 * C
+    x = _r(n, C, h, w, seed=1)
+    w1, b1 = _r(Hd, C, seed=2, scale=1 / math.sqrt(C)), _r(Hd, seed=3, scale=0.2)
+    dw, db = _r(Hd, 1, 3, 3, seed=4, scale=0.3), _r(Hd, seed=5, scale=0.1)
+    w2, b2 = _r(C, Hd, seed=6, scale=1 / math.sqrt(Hd)), _r(C, seed=7)
+    res = _r(n, C, h, w, seed=8)
+    gelu = (lambda v: F.gelu(v, approximate="tanh")) if act == 3 else F.gelu
+    h1 = gelu(F.linear(x.permute(0, 2, 3, 1), w1, b1)).permute(0, 3, 1, 2).to(BF).float()   # the on-chip hidden tile is bf16
+    mid = gelu(F.conv2d(h1, dw, db, padding=1, groups=Hd)).to(BF).float()            # the A operand of Linear2 is bf16
+    ref = F.linear(mid.permute(0, 2, 3, 1), w2, b2) + res.permute(0, 2, 3, 1)
+    xin = torch.zeros(n, h, w, 2 * C, device=cuda, dtype=BF)                        # input and output as channel slices of wider buffers
+    xin[..., C:] = _nhwc(x, cuda)
+    buf = torch.zeros(n, h, w, 2 * C, device=cuda, dtype=BF)
+    out = ops.leff_mlp(xin[..., C:], (0.5 * w1).to(cuda, BF), (0.5 * b1).to(cuda), (0.5 * dw).reshape(Hd, 9).t().contiguous().to(cuda),
+                       (0.5 * db).to(cuda), w2.to(cuda, BF), b2.to(cuda), buf[..., :C], _nhwc(res, cuda), act)
+    assert out is not None
+    torch.cuda.synchronize()
+    _check(buf[..., :C], ref, tol=3e-2)
+    assert buf[..., C:].abs().max().item() == 0
+    # no residual, contiguous tensors
+    out2 = torch.empty(n, h, w, C, device=cuda, dtype=BF)
+    assert ops.leff_mlp(_nhwc(x, cuda), (0.5 * w1).to(cuda, BF), (0.5 * b1).to(cuda), (0.5 * dw).reshape(Hd, 9).t().contiguous().to(cuda),
+                        (0.5 * db).to(cuda), w2.to(cuda, BF), b2.to(cuda), out2, None, act) is not None
+    _check(out2, ref - res.permute(0, 2, 3, 1), tol=3e-2)
+
+
+def test_fused_leff_mlp_refuses_wide_layers(cuda):
+    """C = 256 (hidden 1024) does not fit the one-kernel plan (x tile 128 KB): the op says so and the model keeps fc1 + leff_fc2."""
+    from fbanet_b200 import ops, _lib as L
+    C, Hd = 256, 1024
+    z = lambda *s: torch.zeros(*s, device=cuda)
+    assert ops.leff_mlp(z(1, 8, 8, C).to(BF), z(Hd, C).to(BF), z(Hd), z(9, Hd), z(Hd), z(C, Hd).to(BF), z(C), z(1, 8, 8, C).to(BF), None,
+                        L.ACT_GELU_TANH) is None
