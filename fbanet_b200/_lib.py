@@ -9,13 +9,14 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBANET_B200_LIB") or os.path.join(_HERE, "csrc", "libfbanet_b200.so")   # env override: A/B two builds in one process tree
-ABI_VERSION = 23
+ABI_VERSION = 24
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_PRELU, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2, 3, 4
 STORE_NHWC, STORE_PS2, STORE_CONVT2, STORE_NCHW_BASE, STORE_NHWC_F32 = 0, 1, 2, 3, 4
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+CONVERT_U8_TO_F32, CONVERT_F32_TO_U8, CONVERT_F32_TO_F16 = 0, 1, 2
 
 ERRORS = {-1: "bad shape", -2: "misaligned pointer/stride", -3: "unsupported dtype", -4: "CUDA launch failure", -5: "impl unsupported for this problem"}
 
@@ -80,6 +81,10 @@ class AssembleParams(C.Structure):
         ("N", C.c_int32), ("C", C.c_int32), ("Cp", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("lo_offset", C.c_int32), ("_pad", C.c_int32),
     ]
+
+
+class ConvertIoParams(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("n", C.c_int64), ("mode", C.c_int32), ("_pad", C.c_int32)]
 
 
 class LayerNormParams(C.Structure):
@@ -258,7 +263,7 @@ class DropPathParams(C.Structure):
 
 STRUCTS = {
     "fbanet_src": Src, "fbanet_conv_params": ConvParams, "fbanet_warp_params": WarpParams,
-    "fbanet_to_nhwc_params": ToNhwcParams, "fbanet_s2d_params": S2dParams, "fbanet_head_conv_params": HeadConvParams, "fbanet_assemble_params": AssembleParams, "fbanet_layernorm_params": LayerNormParams, "fbanet_attn_params": AttnParams,
+    "fbanet_to_nhwc_params": ToNhwcParams, "fbanet_s2d_params": S2dParams, "fbanet_head_conv_params": HeadConvParams, "fbanet_assemble_params": AssembleParams, "fbanet_convert_io_params": ConvertIoParams, "fbanet_layernorm_params": LayerNormParams, "fbanet_attn_params": AttnParams,
     "fbanet_dwconv_params": DwconvParams, "fbanet_faf_gate_params": FafGateParams, "fbanet_leff_fc2_params": LeffFc2Params, "fbanet_leff_mlp_params": LeffMlpParams, "fbanet_tile_params": TileParams,
     "fbanet_tile_band_params": TileBandParams, "fbanet_flow_warp_params": FlowWarpParams,
     "fbanet_ecc_prepare_params": EccPrepareParams, "fbanet_ecc_params": EccParams, "fbanet_train_loss_params": TrainLossParams,
@@ -269,7 +274,7 @@ STRUCTS = {
 
 # every symbol include/fbanet_b200.h declares
 OPS = {
-    "fbanet_warp_sm100": WarpParams, "fbanet_to_nhwc_sm100": ToNhwcParams, "fbanet_space_to_depth_sm100": S2dParams, "fbanet_head_conv_sm100": HeadConvParams, "fbanet_assemble_sm100": AssembleParams, "fbanet_conv_gemm_sm100": ConvParams,
+    "fbanet_warp_sm100": WarpParams, "fbanet_to_nhwc_sm100": ToNhwcParams, "fbanet_space_to_depth_sm100": S2dParams, "fbanet_head_conv_sm100": HeadConvParams, "fbanet_assemble_sm100": AssembleParams, "fbanet_convert_io_sm100": ConvertIoParams, "fbanet_conv_gemm_sm100": ConvParams,
     "fbanet_layernorm_sm100": LayerNormParams, "fbanet_window_attention_sm100": AttnParams, "fbanet_dwconv3x3_sm100": DwconvParams,
     "fbanet_faf_gate_sm100": FafGateParams, "fbanet_leff_fc2_sm100": LeffFc2Params, "fbanet_leff_mlp_sm100": LeffMlpParams, "fbanet_tile_divide_sm100": TileParams, "fbanet_tile_merge_sm100": TileParams,
     "fbanet_tile_divide_banded_sm100": TileBandParams, "fbanet_tile_merge_banded_sm100": TileBandParams, "fbanet_flow_warp_sm100": FlowWarpParams,

@@ -47,6 +47,7 @@ extern "C" int fbanet_abi_sizeof(const char* n) {
   SZ(fbanet_s2d_params);
   SZ(fbanet_head_conv_params);
   SZ(fbanet_assemble_params);
+  SZ(fbanet_convert_io_params);
   SZ(fbanet_layernorm_params);
   SZ(fbanet_attn_params);
   SZ(fbanet_dwconv_params);

@@ -609,38 +609,59 @@ class BaseModel(nn.Module):
         """The reference's JAX signature: ``x [F,H,W,C] -> [4H,4W,C]`` (models/fba_net.py:242)."""
         return self.forward(x.permute(0, 3, 1, 2).unsqueeze(0)).squeeze(0).permute(1, 2, 0)
 
-    def _host_graph(self, n: int, slot: int):
+    def _host_io(self, x_in: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+        """Forward of one chunk with the narrow-I/O conversions on the device: uint8 frames are normalised (``/ 255``,
+        ``train.py:82-83``), the SR image is returned as fp32 (default), fp16, or uint8 (``clamp(0,1) * 255`` truncated -- the
+        reference's PNG path, ``test_in_any_resolution.py:93-101``)."""
+        x = x_in
+        if x_in.dtype == torch.uint8:
+            x = ops.convert_io(x_in, torch.empty(x_in.shape, device=x_in.device, dtype=torch.float32))
+        y = self.forward(x)
+        if out_dtype != torch.float32:
+            y = ops.convert_io(y, torch.empty(y.shape, device=y.device, dtype=out_dtype))
+        return y
+
+    def _host_graph(self, n: int, slot: int, in_dtype: torch.dtype = torch.float32, out_dtype: torch.dtype = torch.float32):
         """CUDA graph of one forward over ``n`` bursts with static input/output buffers (two slots per size, so consecutive
         chunks of :meth:`infer_host` can be in flight); re-captured whenever the packed weights change."""
         self.packed()
-        key = (n, slot)
+        key = (n, slot, in_dtype, out_dtype)
         ent = self._host_graphs.get(key)
         if ent is not None and ent[3] is self._packed_sig:
             return ent[:3]
         dev = self.head.weight.device
-        x_static = torch.zeros((n, self.num_frames, self.in_channels, self.img_size, self.img_size), device=dev, dtype=torch.float32)
-        self.forward(x_static)                      # eager warm-up: weight packing, kernel attributes, allocator pools
+        x_static = torch.zeros((n, self.num_frames, self.in_channels, self.img_size, self.img_size), device=dev, dtype=in_dtype)
+        self._host_io(x_static, out_dtype)          # eager warm-up: weight packing, kernel attributes, allocator pools
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            y_static = self.forward(x_static)
+            y_static = self._host_io(x_static, out_dtype)
         self._host_graphs[key] = (g, x_static, y_static, self._packed_sig)
         return g, x_static, y_static
 
     @torch.no_grad()
-    def infer_host(self, burst: torch.Tensor, out: Optional[torch.Tensor] = None, chunk=None) -> torch.Tensor:
+    def infer_host(self, burst: torch.Tensor, out: Optional[torch.Tensor] = None, chunk=None, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
         """End-to-end call with HOST buffers: pinned H2D copy, forward, D2H copy of the SR image.
 
         The batch is processed in chunks of ``chunk`` bursts (default ``self.host_chunk``) on three streams, so the H2D copy of
         chunk i+1 and the D2H copy of chunk i-1 overlap the forward of chunk i; only the first upload and the last download
         are exposed.  Each chunk's forward is a CUDA-graph replay over static device buffers (``self.host_graphs``; two
-        buffer sets alternate), captured on first use.  Returns after the last download has completed."""
+        buffer sets alternate), captured on first use.  Returns after the last download has completed.
+
+        Narrow I/O (the reference's own data path is 8-bit at both ends): a ``uint8`` ``burst`` is normalised on the device
+        (``/ 255``); ``out_dtype = torch.uint8`` returns ``clamp(SR, 0, 1) * 255`` truncated (what the reference writes to PNG),
+        ``torch.float16`` a plain cast.  fp32 in / fp32 out stays the default."""
         dev = self.head.weight.device
+        if burst.dtype not in (torch.float32, torch.uint8):
+            burst = burst.float()
+        if out_dtype not in (torch.float32, torch.float16, torch.uint8):
+            raise ValueError("out_dtype must be torch.float32, torch.float16 or torch.uint8")
         if not burst.is_pinned():
             burst = burst.pin_memory()
         B = burst.shape[0]
         if out is None:
-            out = torch.empty((B, self.in_channels, 4 * self.img_size, 4 * self.img_size), dtype=torch.float32, pin_memory=True)
+            out = torch.empty((B, self.in_channels, 4 * self.img_size, 4 * self.img_size), dtype=out_dtype, pin_memory=True)
+        assert out.dtype == out_dtype, "the output buffer must have out_dtype"
         if B == 0:
             return out
         chunk = chunk or self.host_chunk
@@ -662,7 +683,7 @@ class BaseModel(nn.Module):
         s_in, s_out = self._io_streams
         if self.host_graphs:   # capture (first use of a chunk size) happens before any copy is queued
             for k, (a, b) in enumerate(bounds):
-                self._host_graph(b - a, k & 1)
+                self._host_graph(b - a, k & 1, burst.dtype, out_dtype)
         s_in.wait_stream(comp)   # the caller's stream may still be producing / consuming these buffers
         s_out.wait_stream(comp)
         ev_comp = [None, None]   # forward that last read slot's input buffer
@@ -670,7 +691,7 @@ class BaseModel(nn.Module):
         for k, (i0, i1) in enumerate(bounds):
             slot = k & 1
             if self.host_graphs:
-                g, xs, ys = self._host_graph(i1 - i0, slot)
+                g, xs, ys = self._host_graph(i1 - i0, slot, burst.dtype, out_dtype)
                 with torch.cuda.stream(s_in):
                     if ev_comp[slot] is not None:
                         s_in.wait_event(ev_comp[slot])
@@ -689,7 +710,7 @@ class BaseModel(nn.Module):
                     ev_in.record(s_in)
                 comp.wait_event(ev_in)
                 xd.record_stream(comp)
-                y = self.forward(xd)
+                y = self._host_io(xd, out_dtype)
                 y.record_stream(s_out)
             ev_comp[slot] = torch.cuda.Event()
             ev_comp[slot].record(comp)

@@ -173,35 +173,45 @@ def conv_gemm(
             assert out.shape == (N, 2 * Ho, 2 * Wo, cout // 4)
         op, _, old, ois = _cl(out)
         p.out, p.out_ld, p.out_img_stride = op, old, ois
+    esz = srcs[0].element_size()
+    nbytes = N * H * W * ctot * esz + out.numel() * out.element_size() + (residual.numel() * esz if residual is not None else 0) + weight.numel() * esz
+    tag = f"k{kh}s{stride} {ctot}->{cout} @{Ho}x{Wo} act{act}{' res' if residual is not None else ''} st{store_mode}"
     if _PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _call("fbanet_conv_gemm_sm100", p)
         e1.record()
         flops = 2.0 * N * Ho * Wo * kh * kw * (ctot if alg_cin is None else alg_cin) * p.Cout_store
-        _PROFILE.append((e0, e1, flops))
+        _PROFILE.append((e0, e1, flops, tag, nbytes, kh * kw))
         return out
-    esz = srcs[0].element_size()
-    nbytes = N * H * W * ctot * esz + out.numel() * out.element_size() + (residual.numel() * esz if residual is not None else 0) + weight.numel() * esz
-    _call("fbanet_conv_gemm_sm100", p, tag=f"k{kh}s{stride} {ctot}->{cout} @{Ho}x{Wo} act{act}{' res' if residual is not None else ''} st{store_mode}", nbytes=nbytes)
+    _call("fbanet_conv_gemm_sm100", p, tag=tag, nbytes=nbytes)
     return out
 
 
 def profile_conv_gemm(fn, stream) -> dict:
     """Run ``fn`` once with CUDA events around every implicit-GEMM launch; returns summed device time,
-    algorithmic FLOPs (2*M*K*N with unpadded channels) and the achieved TFLOP/s of that kernel family."""
+    algorithmic FLOPs (2*M*K*N with unpadded channels) and the achieved TFLOP/s of that kernel family, plus the same split by
+    class -- ``"conv"`` (3x3 / 4x4 taps: tensor-pipe bound, judged in TFLOP/s) and ``"gemm1x1"`` (linear layers and 1x1 / transposed
+    convs: HBM bound at these channel counts, judged in GB/s) -- and per distinct launch shape (``"shapes"``: tag -> launches, ms,
+    flops, algorithmic bytes)."""
     global _PROFILE
     _PROFILE = []
     try:
         fn()
         stream.synchronize()
-        ms = sum(a.elapsed_time(b) for a, b, _ in _PROFILE)
-        flops = sum(f for _, _, f in _PROFILE)
-        n = len(_PROFILE)
+        recs = [(a.elapsed_time(b), f, tag, nb, taps) for a, b, f, tag, nb, taps in _PROFILE]
     finally:
         _PROFILE = None
+    ms = sum(r[0] for r in recs)
+    flops = sum(r[1] for r in recs)
+    classes, shapes = {}, {}
+    for t, f, tag, nb, taps in recs:
+        c = classes.setdefault("conv" if taps > 1 else "gemm1x1", {"ms": 0.0, "flops": 0.0, "bytes": 0, "launches": 0})
+        c["ms"] += t; c["flops"] += f; c["bytes"] += nb; c["launches"] += 1
+        sh = shapes.setdefault(tag, {"ms": 0.0, "flops": 0.0, "bytes": 0, "launches": 0, "taps": taps})
+        sh["ms"] += t; sh["flops"] += f; sh["bytes"] += nb; sh["launches"] += 1
     return {"kernel": "fbanet_conv_gemm_sm100 (implicit-GEMM conv/linear, all launches of one step)", "ms": ms, "flops": flops,
-            "launches": n, "tflops": flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}
+            "launches": len(recs), "tflops": flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0, "classes": classes, "shapes": shapes}
 
 
 def tcgen05_supported(p: L.ConvParams) -> bool:
@@ -254,6 +264,19 @@ def assemble(sr: torch.Tensor, base: torch.Tensor, C_out: int, lo_offset: int = 
     p.lo_offset = lo_offset
     _call("fbanet_assemble_sm100", p, nbytes=N * H * W * C_out * sr.element_size() + base.numel() * 4 + out.numel() * 4)
     return out
+
+
+def convert_io(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """Narrow host I/O on the device: ``uint8 -> fp32`` (``x / 255``, ``train.py:82-83``), ``fp32 -> uint8`` (``clamp(x,0,1)`` then
+    ``mul(255).byte()``: the reference's PNG path, ``test_in_any_resolution.py:93-101``) or ``fp32 -> fp16``; contiguous tensors of the
+    same shape with a multiple of 16 elements."""
+    assert src.is_cuda and dst.is_cuda and src.is_contiguous() and dst.is_contiguous() and src.shape == dst.shape
+    mode = {(torch.uint8, torch.float32): L.CONVERT_U8_TO_F32, (torch.float32, torch.uint8): L.CONVERT_F32_TO_U8,
+            (torch.float32, torch.float16): L.CONVERT_F32_TO_F16}[(src.dtype, dst.dtype)]
+    p = L.ConvertIoParams()
+    p.src, p.dst, p.n, p.mode = src.data_ptr(), dst.data_ptr(), src.numel(), mode
+    _call("fbanet_convert_io_sm100", p, nbytes=src.numel() * src.element_size() + dst.numel() * dst.element_size())
+    return dst
 
 
 def space_to_depth(x: torch.Tensor) -> torch.Tensor:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 23
+#define FBANET_ABI_VERSION 24
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -172,6 +172,18 @@ typedef struct fbanet_assemble_params {
   int32_t lo_offset;      /* > 0: SR value of channel c = sr[c] + sr[c + lo_offset] (final conv with hi/lo split weights) */
   int32_t _pad;
 } fbanet_assemble_params;
+
+/* Narrow host I/O of the end-to-end path (the reference's data path is 8-bit at both ends): mode U8_TO_F32 = the input
+ * normalisation `x.astype(float32) / 255.0` (train.py:82-83); F32_TO_U8 = `clamp(x, 0, 1)` + torchvision `ToPILImage` (`mul(255).byte()`:
+ * truncation), test_in_any_resolution.py:93-101; F32_TO_F16 = round-to-nearest cast.  n elements, n % 16 == 0, both pointers 16-byte
+ * aligned. */
+enum { FBANET_CONVERT_U8_TO_F32 = 0, FBANET_CONVERT_F32_TO_U8 = 1, FBANET_CONVERT_F32_TO_F16 = 2 };
+typedef struct fbanet_convert_io_params {
+  const void* src;
+  void* dst;
+  int64_t n;
+  int32_t mode, _pad;
+} fbanet_convert_io_params;
 
 /* channels-last view [N,H,W,C] -> contiguous [N,H/2,W/2,4C], channel (ys*2+xs)*C + c = src(2y+ys, 2x+xs, c).
  * Feeds the 4x4 stride-2 downsampling convs (layers/downsample_flatten.py:6-13) to the TMA/tcgen05 path. */
@@ -555,6 +567,7 @@ int fbanet_to_nhwc_sm100(const fbanet_to_nhwc_params* p, void* stream);
 int fbanet_space_to_depth_sm100(const fbanet_s2d_params* p, void* stream);
 int fbanet_head_conv_sm100(const fbanet_head_conv_params* p, void* stream);
 int fbanet_assemble_sm100(const fbanet_assemble_params* p, void* stream);
+int fbanet_convert_io_sm100(const fbanet_convert_io_params* p, void* stream);
 int fbanet_conv_gemm_sm100(const fbanet_conv_params* p, void* stream);
 int fbanet_layernorm_sm100(const fbanet_layernorm_params* p, void* stream);
 int fbanet_window_attention_sm100(const fbanet_attn_params* p, void* stream);

@@ -164,6 +164,26 @@ def test_batch_invariance_and_host_api(cuda):
             assert torch.equal(m.infer_host(x, chunk=chunk), full)
 
 
+def test_host_api_narrow_io(cuda):
+    """`infer_host` with the reference's 8-bit data path: uint8 frames are normalised on the device exactly as `x.astype(float32) /
+    255.0` (train.py:82-83), a uint8 result is `clamp(SR, 0, 1).mul(255).byte()` (test_in_any_resolution.py:93 + torchvision
+    ToPILImage: truncation), an fp16 result is the rounded fp32 one; eager and graph-replay paths agree."""
+    _, m = _pair(SMALL, "fp32", cuda)
+    g = torch.Generator().manual_seed(9)
+    xu = torch.randint(0, 256, (3, SMALL["num_frames"], SMALL["in_channels"], SMALL["img_size"], SMALL["img_size"]), generator=g, dtype=torch.uint8)
+    xf = xu.float() / 255.0
+    ref = m(xf.to(cuda)).cpu()
+    assert torch.equal(m.infer_host(xu), ref)
+    assert torch.equal(m.infer_host(xf, out_dtype=torch.float16), ref.half())
+    want = torch.clamp(ref, 0, 1).mul(255).byte()
+    for chunk in (3, 2):
+        got = m.infer_host(xu, out_dtype=torch.uint8, chunk=chunk)
+        assert got.dtype == torch.uint8 and torch.equal(got, want)
+    assert 0 < want.float().mean().item() < 255            # not saturated: the comparison means something
+    m.host_graphs = False
+    assert torch.equal(m.infer_host(xu, out_dtype=torch.uint8), want)
+
+
 def test_fhwc_adaptor(cuda):
     _, m = _pair(SMALL, "fp32", cuda)
     x = _burst(SMALL, 1)

@@ -255,3 +255,68 @@ def test_whole_model_training_step_on_the_gpu(cuda):
     assert _rel(m(bd), after) < 1e-4 and _rel(m(bd), infer) > 1e-4
     out_host = m.infer_host(burst)                                         # the CUDA-graph path re-captures too
     assert _rel(out_host, after.cpu()) < 1e-4
+
+
+def test_whole_model_training_step_bf16_embed64_on_the_gpu(cuda):
+    """BASELINE config 5 in its own arithmetic: embed_dim 64, bf16 activations -- every data gradient of the step runs on the tcgen05
+    implicit-GEMM kernel (incl. the 4x4-stride-2 data gradient with its 3x3 halo GEMM + ConvTranspose-style scatter, the transposed
+    convs and the pixel-shuffle convs), the forward is the bf16 training forward.  Checked against autograd through the oracle in
+    float64 for EVERY parameter: bf16 rounds every activation and every gradient tensor the tape keeps (8 mantissa bits, ~40 layers
+    deep), so the bar is per-parameter DIRECTION and scale -- cosine similarity and relative L2 error -- calibrated on the B200
+    (printed: worst cosine / worst relative error), not elementwise closeness.  Then three optimizer steps lower the loss."""
+    from fbanet_b200 import train, ops
+    from fbanet_b200.model import BaseModel
+    from oracle.fbanet_oracle import OracleBaseModel, training_loss
+    cfg = dict(num_frames=3, img_size=40, embed_dim=64, window_length=10)
+    m = BaseModel(token_mlp="leff", dtype="bf16", seed=6, **cfg)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "relative_position_bias_table" in n or (p.dim() == 1 and "norm" not in n):
+                p.copy_(torch.randn_like(p) * 0.1)
+    o = OracleBaseModel(**cfg).double()
+    o.load_state_dict(m.state_dict())
+    B = 2
+    burst = torch.rand(B, 3, 3, 40, 40, generator=torch.Generator().manual_seed(11))
+    target = torch.rand(B, 3, 160, 160, generator=torch.Generator().manual_seed(12))
+    ref = o(burst.double())
+    loss_ref = training_loss(ref, target.double(), clamp_restored=True)
+    loss_ref.backward()
+    m = m.to(cuda)
+    assert m._use_tc()
+    bd, td = burst.to(cuda), target.to(cuda)
+    for p in m.parameters():
+        p.requires_grad_(True)
+        p.grad = None
+    restored, tape = train.model_forward_train(m, bd, training=False)
+    from oracle.fbanet_oracle import psnr
+    assert psnr(restored.cpu(), ref.detach().float()) > 40.0
+    loss, d_restored = ops.training_loss(restored, td, clamp_restored=True)
+    assert abs(loss[0].item() - loss_ref.item()) < 2e-2 * loss_ref.item()
+    assert tape.backward(restored, d_restored) == {}
+    got = dict(m.named_parameters())
+    worst_cos, worst_rel, rows = 1.0, 0.0, []
+    for n, pr in o.named_parameters():
+        if n.startswith("fusion.temporal_attn0") or n == "fusion.temporal_attn1.bias":
+            assert got[n].grad is None, n
+            continue
+        assert got[n].grad is not None, n
+        a, b = got[n].grad.double().cpu().flatten(), pr.grad.flatten()
+        assert torch.isfinite(a).all(), n
+        cos = (a @ b / (a.norm() * b.norm() + 1e-300)).item()
+        rel = ((a - b).norm() / (b.norm() + 1e-300)).item()
+        rows.append((cos, rel, n))
+        worst_cos, worst_rel = min(worst_cos, cos), max(worst_rel, rel)
+    rows.sort()
+    print("bf16 E=64 whole-model gradients: worst cosine %.4f, worst relative L2 error %.4f; lowest five:" % (worst_cos, worst_rel), rows[:5])
+    # calibration (B200, this seed): see profiles/r2_train_bf16_parity.log
+    bad = [(c, r, n) for c, r, n in rows if c < 0.90 or r > 0.45]
+    assert not bad, bad[:8]
+    assert sum(c for c, _, _ in rows) / len(rows) > 0.985
+    for p in m.parameters():
+        p.grad = None
+    m.drop_path_rate = 0.0
+    flat = train.FlatParams(m.parameters())
+    l1 = train.train_step(m, flat, bd, td, lr=2e-4)
+    l2 = train.train_step(m, flat, bd, td, lr=2e-4)
+    l3 = train.train_step(m, flat, bd, td, lr=2e-4)
+    assert flat.step == 3 and torch.isfinite(l3).all() and l3[0].item() < l1[0].item(), (l1, l2, l3)
