@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBANET_B200_LIB") or os.path.join(_HERE, "csrc", "libfbanet_b200.so")   # env override: A/B two builds in one process tree
-ABI_VERSION = 24
+ABI_VERSION = 25
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -116,6 +116,14 @@ class FafGateParams(C.Structure):
         ("feat", C.c_void_p), ("gate", C.c_void_p), ("wsum", C.c_void_p), ("gated", C.c_void_p), ("dtype", C.c_int32),
         ("B", C.c_int32), ("F", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("_pad", C.c_int32),
         ("score", C.c_void_p),
+    ]
+
+
+class FafFuseParams(C.Structure):
+    _fields_ = [
+        ("feat", C.c_void_p), ("score_weight", C.c_void_p), ("fuse_weight", C.c_void_p), ("bias", C.c_void_p), ("alpha", C.c_void_p),
+        ("gate", C.c_void_p), ("out", C.c_void_p), ("out_img_stride", C.c_int64), ("out_ld", C.c_int32),
+        ("B", C.c_int32), ("F", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("_pad", C.c_int32 * 2),
     ]
 
 
@@ -264,7 +272,7 @@ class DropPathParams(C.Structure):
 STRUCTS = {
     "fbanet_src": Src, "fbanet_conv_params": ConvParams, "fbanet_warp_params": WarpParams,
     "fbanet_to_nhwc_params": ToNhwcParams, "fbanet_s2d_params": S2dParams, "fbanet_head_conv_params": HeadConvParams, "fbanet_assemble_params": AssembleParams, "fbanet_convert_io_params": ConvertIoParams, "fbanet_layernorm_params": LayerNormParams, "fbanet_attn_params": AttnParams,
-    "fbanet_dwconv_params": DwconvParams, "fbanet_faf_gate_params": FafGateParams, "fbanet_leff_fc2_params": LeffFc2Params, "fbanet_leff_mlp_params": LeffMlpParams, "fbanet_tile_params": TileParams,
+    "fbanet_dwconv_params": DwconvParams, "fbanet_faf_gate_params": FafGateParams, "fbanet_faf_fuse_params": FafFuseParams, "fbanet_leff_fc2_params": LeffFc2Params, "fbanet_leff_mlp_params": LeffMlpParams, "fbanet_tile_params": TileParams,
     "fbanet_tile_band_params": TileBandParams, "fbanet_flow_warp_params": FlowWarpParams,
     "fbanet_ecc_prepare_params": EccPrepareParams, "fbanet_ecc_params": EccParams, "fbanet_train_loss_params": TrainLossParams,
     "fbanet_adam_params": AdamParams, "fbanet_wgrad_params": WgradParams, "fbanet_layernorm_bwd_params": LayerNormBwdParams,
@@ -276,7 +284,7 @@ STRUCTS = {
 OPS = {
     "fbanet_warp_sm100": WarpParams, "fbanet_to_nhwc_sm100": ToNhwcParams, "fbanet_space_to_depth_sm100": S2dParams, "fbanet_head_conv_sm100": HeadConvParams, "fbanet_assemble_sm100": AssembleParams, "fbanet_convert_io_sm100": ConvertIoParams, "fbanet_conv_gemm_sm100": ConvParams,
     "fbanet_layernorm_sm100": LayerNormParams, "fbanet_window_attention_sm100": AttnParams, "fbanet_dwconv3x3_sm100": DwconvParams,
-    "fbanet_faf_gate_sm100": FafGateParams, "fbanet_leff_fc2_sm100": LeffFc2Params, "fbanet_leff_mlp_sm100": LeffMlpParams, "fbanet_tile_divide_sm100": TileParams, "fbanet_tile_merge_sm100": TileParams,
+    "fbanet_faf_gate_sm100": FafGateParams, "fbanet_faf_fuse_sm100": FafFuseParams, "fbanet_leff_fc2_sm100": LeffFc2Params, "fbanet_leff_mlp_sm100": LeffMlpParams, "fbanet_tile_divide_sm100": TileParams, "fbanet_tile_merge_sm100": TileParams,
     "fbanet_tile_divide_banded_sm100": TileBandParams, "fbanet_tile_merge_banded_sm100": TileBandParams, "fbanet_flow_warp_sm100": FlowWarpParams,
     "fbanet_ecc_prepare_sm100": EccPrepareParams, "fbanet_ecc_homography_sm100": EccParams, "fbanet_train_loss_sm100": TrainLossParams,
     "fbanet_adam_step_sm100": AdamParams, "fbanet_wgrad_sm100": WgradParams, "fbanet_layernorm_bwd_sm100": LayerNormBwdParams,
@@ -284,7 +292,7 @@ OPS = {
     "fbanet_window_attention_bwd_sm100": AttnBwdParams, "fbanet_faf_gate_bwd_sm100": FafGateBwdParams,
     "fbanet_drop_path_add_sm100": DropPathParams,
 }
-MISC_SYMBOLS = ["fbanet_abi_version", "fbanet_abi_sizeof", "fbanet_last_cuda_error", "fbanet_conv_gemm_tcgen05_supported", "fbanet_leff_fc2_supported", "fbanet_leff_mlp_supported",
+MISC_SYMBOLS = ["fbanet_abi_version", "fbanet_abi_sizeof", "fbanet_last_cuda_error", "fbanet_conv_gemm_tcgen05_supported", "fbanet_leff_fc2_supported", "fbanet_leff_mlp_supported", "fbanet_faf_fuse_supported",
                 "fbanet_train_loss_workspace_doubles", "fbanet_layernorm_bwd_blocks", "fbanet_act_bwd_blocks",
                 "fbanet_dwconv_bwd_blocks", "fbanet_faf_gate_bwd_blocks", "fbanet_attn_bwd_partial_floats"]
 
@@ -312,6 +320,8 @@ def load() -> C.CDLL:
     lib.fbanet_leff_fc2_supported.argtypes = [C.POINTER(LeffFc2Params)]
     lib.fbanet_leff_mlp_supported.restype = C.c_int
     lib.fbanet_leff_mlp_supported.argtypes = [C.POINTER(LeffMlpParams)]
+    lib.fbanet_faf_fuse_supported.restype = C.c_int
+    lib.fbanet_faf_fuse_supported.argtypes = [C.POINTER(FafFuseParams)]
     lib.fbanet_train_loss_workspace_doubles.restype = C.c_int64
     lib.fbanet_train_loss_workspace_doubles.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     for fn in (lib.fbanet_layernorm_bwd_blocks, lib.fbanet_act_bwd_blocks, lib.fbanet_dwconv_bwd_blocks, lib.fbanet_faf_gate_bwd_blocks):

@@ -52,6 +52,7 @@ extern "C" int fbanet_abi_sizeof(const char* n) {
   SZ(fbanet_attn_params);
   SZ(fbanet_dwconv_params);
   SZ(fbanet_faf_gate_params);
+  SZ(fbanet_faf_fuse_params);
   SZ(fbanet_leff_fc2_params);
   SZ(fbanet_leff_mlp_params);
   SZ(fbanet_tile_params);

@@ -192,6 +192,8 @@ class BaseModel(nn.Module):
         self.gelu_act = {"tanh": L.ACT_GELU_TANH, "erf": L.ACT_GELU_ERF}[gelu]
         self.impl = impl
         self.fuse_leff = True
+        # K2 (FAF gate + 1x1 fusion) in one kernel (ops.faf_fuse); FBANET_FUSE_FAF=0 keeps score conv + gate apply + fusion GEMM
+        self.fuse_faf = os.environ.get("FBANET_FUSE_FAF", "1") == "1"
         # dim <= 128 layers: the whole LeFF MLP in one kernel (ops.leff_mlp); FBANET_FUSE_MLP=0 keeps fc1 + leff_fc2
         self.fuse_mlp = os.environ.get("FBANET_FUSE_MLP", "1") == "1"
         # bf16 path, optional: LayerNorm folded into the qkv / fc1 GEMMs (row statistics only; ops.fold_layernorm).  -1.3 ms per
@@ -295,6 +297,7 @@ class BaseModel(nn.Module):
         P["fusion.wsum"] = fu.temporal_attn1.weight.detach().double().sum(0).permute(1, 2, 0).reshape(9, -1).float().contiguous()
         if tc and self.embed_dim == 64:  # the same dot products as a 3x3 implicit GEMM on the tensor cores (hi/lo weight rows)
             P["fusion.wscore"] = ops.faf_score_weight(P["fusion.wsum"], T)
+            P["fusion.wstack"] = ops.faf_fuse_score_weight(P["fusion.wsum"])   # tap-stacked form for the one-pass K2 kernel
         put_conv("fusion.fuse", fu.feature_fusion[0])
         P["fusion.fuse.alpha"] = f32(fu.feature_fusion[1].weight)
         put_conv("fusion.down0", fu.downsample0)
@@ -458,7 +461,16 @@ class BaseModel(nn.Module):
     def _faf(self, P, feat):
         """FAFBlock (blocks/federated_affinity_fusion.py:166-182). feat ``[B,F,H,W,E]``."""
         B, Fr, H, W, E = feat.shape
-        if self._use_tc():
+        z = gate = None
+        if self._use_tc() and self.fuse_faf and "fusion.wstack" in P:
+            # K2 in one pass: scores, gates and the K = F*E fusion GEMM from one read of the features (ops.faf_fuse)
+            r = ops.faf_fuse(feat, P["fusion.wstack"], P["fusion.fuse.w"], P["fusion.fuse.b"], P["fusion.fuse.alpha"], self._new(B, H, W, E),
+                             want_gate=True)
+            if r is not None:
+                z, gate = r
+        if z is not None:
+            pass
+        elif self._use_tc():
             # gate kernel also emits the gated features pixel-major [B,H,W,F*E] = the K axis of the 1x1 fusion GEMM
             score = ops.faf_scores(feat, P["fusion.wscore"]) if "fusion.wscore" in P else None
             gate, gated = ops.faf_gate(feat, P["fusion.wsum"], want_gate=True, want_gated=True, score=score)
@@ -664,6 +676,8 @@ class BaseModel(nn.Module):
         assert out.dtype == out_dtype, "the output buffer must have out_dtype"
         if B == 0:
             return out
+        if chunk is None and burst.dtype == torch.uint8 and out_dtype != torch.float32:
+            chunk = B            # 8-bit copies are ~1 ms each way: one full-batch forward beats two half-batch ones
         chunk = chunk or self.host_chunk
         if isinstance(chunk, int):
             sizes = [max(1, min(B, chunk))] * ((B + max(1, min(B, chunk)) - 1) // max(1, min(B, chunk)))

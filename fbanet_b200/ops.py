@@ -463,6 +463,41 @@ def faf_gate(feat: torch.Tensor, wsum: torch.Tensor, want_gate: bool = True, wan
     return gated if want_gated else gate
 
 
+def faf_fuse_score_weight(wsum: torch.Tensor) -> torch.Tensor:
+    """Gate weights ``wsum [9,64]`` fp32 as the tap-stacked B operand of :func:`faf_fuse`: bf16 ``[32,64]``, rows ``2t`` / ``2t+1`` = hi / lo
+    bf16 halves of tap ``t`` (their sum carries ~16 mantissa bits of the fp32 weights), rows 18..31 zero."""
+    hi = wsum.to(torch.bfloat16)
+    lo = (wsum - hi.float()).to(torch.bfloat16)
+    w = torch.zeros((32, wsum.shape[1]), device=wsum.device, dtype=torch.bfloat16)
+    w[0:18:2], w[1:18:2] = hi, lo
+    return w.contiguous()
+
+
+def faf_fuse(feat: torch.Tensor, score_weight: torch.Tensor, fuse_weight: torch.Tensor, bias: torch.Tensor, alpha: torch.Tensor,
+             out: torch.Tensor, want_gate: bool = False):
+    """K2 in one pass (bf16): FAF gate + the ``F*64 -> 64`` 1x1 fusion conv + PReLU (``blocks/federated_affinity_fusion.py:79-105,
+    121-128``) from ``feat [B,F,H,W,64]``, every feature read from HBM once; ``out``: channels-last view ``[B,H,W,64]``.  Returns
+    ``(out, gate or None)``, or ``None`` when the kernel does not take the shape."""
+    assert feat.is_cuda and feat.is_contiguous() and feat.dtype == torch.bfloat16 and feat.dim() == 5
+    B, Fr, H, W, Cc = feat.shape
+    assert score_weight.shape == (32, Cc) and score_weight.dtype == torch.bfloat16 and score_weight.is_contiguous()
+    assert fuse_weight.shape == (Cc, Fr * Cc) and fuse_weight.dtype == torch.bfloat16 and fuse_weight.is_contiguous()
+    assert out.shape == (B, H, W, Cc) and out.dtype == torch.bfloat16
+    gate = torch.empty((B, Fr - 1, H, W), device=feat.device, dtype=torch.float32) if want_gate else None
+    p = L.FafFuseParams()
+    p.feat, p.score_weight, p.fuse_weight, p.bias, p.alpha = feat.data_ptr(), score_weight.data_ptr(), fuse_weight.data_ptr(), bias.data_ptr(), alpha.data_ptr()
+    p.gate = gate.data_ptr() if gate is not None else None
+    op, _, old, ois = _cl(out)
+    p.out, p.out_ld, p.out_img_stride = op, old, ois
+    p.B, p.F, p.H, p.W, p.C = B, Fr, H, W, Cc
+    if not L.load().fbanet_faf_fuse_supported(C.byref(p)):
+        return None
+    # algorithmic bytes by SURVEY 8(d): (2F+2) H W E s -- what the three-launch form moves (read feat, write + read gated, write z); this
+    # kernel itself moves (F+1) H W E s
+    _call("fbanet_faf_fuse_sm100", p, nbytes=(Fr + 1) * B * H * W * Cc * 2 + (gate.numel() * 4 if gate is not None else 0))
+    return out, gate
+
+
 def faf_score_weight(wsum: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """Pack the summed FAF kernel ``wsum [9][C]`` (fp32) as the ``[16, 9*C]`` weight of a 3x3 implicit GEMM whose output
     column 0 / 1 carry the hi / lo ``dtype`` halves of ``wsum`` (hi + lo keeps ~16 mantissa bits), rows 2..15 zero."""

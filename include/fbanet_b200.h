@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 24
+#define FBANET_ABI_VERSION 25
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -301,6 +301,26 @@ typedef struct fbanet_faf_gate_params {
                              and streams the gated features.  NULL: the kernel computes them itself from `wsum`. */
 } fbanet_faf_gate_params;
 
+/* K2 in one pass (bf16, tensor cores, C = 64): gate + K = F*64 1x1 fusion conv + bias + PReLU of FAFBlock
+ * (blocks/federated_affinity_fusion.py:79-105 and :121-128) straight from the features, each read from HBM once:
+ *   s_f = wbar (*) feat_f (3x3),  g_f = sigmoid(|s_f - s_0|) (g_0 = 1),  out = PReLU(sum_f g_f * (feat_f W_f^T) + bias).
+ * feat: contiguous [B][F][H][W][64] bf16.  score_weight: bf16 [32][64], rows 2t / 2t+1 = hi / lo bf16 halves of wbar[tap t] (the
+ * gate weights summed over output channels, DESIGN.md "FAF gate identity"), rows 18..31 zero.  fuse_weight: bf16 [64][F*64]
+ * (feature_fusion.0.weight, input channel f*64 + c).  gate: optional fp32 [B][F-1][H][W].  2 <= F <= 14. */
+typedef struct fbanet_faf_fuse_params {
+  const void* feat;
+  const void* score_weight;
+  const void* fuse_weight;
+  const float* bias;      /* [64] or NULL */
+  const float* alpha;     /* PReLU slope (device scalar) or NULL = 0 */
+  float* gate;            /* optional */
+  void* out;              /* view [B,H,W,64] bf16 */
+  int64_t out_img_stride;
+  int32_t out_ld;
+  int32_t B, F, H, W, C;
+  int32_t _pad[2];
+} fbanet_faf_fuse_params;
+
 /* Full-size tiling (utils/dataset_utils.py:5-58,140-180): reflect-pad + overlapping tile gather,
  * centre-crop stitch.  Planar fp32. */
 typedef struct fbanet_tile_params {
@@ -559,6 +579,8 @@ const char* fbanet_last_cuda_error(void);
 int fbanet_leff_fc2_supported(const fbanet_leff_fc2_params* p);
 /* 1 if the one-kernel LeFF MLP takes this problem, else 0 */
 int fbanet_leff_mlp_supported(const fbanet_leff_mlp_params* p);
+/* 1 if the one-pass FAF gate + fusion kernel takes this problem, else 0 */
+int fbanet_faf_fuse_supported(const fbanet_faf_fuse_params* p);
 /* 1 if the tcgen05 implicit-GEMM can run this problem, else 0 */
 int fbanet_conv_gemm_tcgen05_supported(const fbanet_conv_params* p);
 
@@ -573,6 +595,7 @@ int fbanet_layernorm_sm100(const fbanet_layernorm_params* p, void* stream);
 int fbanet_window_attention_sm100(const fbanet_attn_params* p, void* stream);
 int fbanet_dwconv3x3_sm100(const fbanet_dwconv_params* p, void* stream);
 int fbanet_faf_gate_sm100(const fbanet_faf_gate_params* p, void* stream);
+int fbanet_faf_fuse_sm100(const fbanet_faf_fuse_params* p, void* stream);
 int fbanet_leff_fc2_sm100(const fbanet_leff_fc2_params* p, void* stream);
 int fbanet_leff_mlp_sm100(const fbanet_leff_mlp_params* p, void* stream);
 int fbanet_tile_divide_sm100(const fbanet_tile_params* p, void* stream);

@@ -253,3 +253,32 @@ def test_fused_leff_mlp_refuses_wide_layers(cuda):
     z = lambda *s: torch.zeros(*s, device=cuda)
     assert ops.leff_mlp(z(1, 8, 8, C).to(BF), z(Hd, C).to(BF), z(Hd), z(9, Hd), z(Hd), z(C, Hd).to(BF), z(C), z(1, 8, 8, C).to(BF), None,
                         L.ACT_GELU_TANH) is None
+
+
+@pytest.mark.parametrize("B,Fr,h,w", [(1, 14, 32, 24), (2, 5, 16, 40), (1, 14, 37, 21), (3, 2, 20, 20), (9, 14, 48, 32), (1, 3, 160, 160)])
+def test_faf_fuse_one_pass(cuda, B, Fr, h, w):
+    """K2 in one kernel -- scores, gates and the K = F*64 1x1 fusion conv + PReLU from one read of the features
+    (blocks/federated_affinity_fusion.py:79-105,121-128) -- against the as-written maths in torch fp32 on bf16-rounded operands:
+    gate = sigmoid(|wsum (*) f_i - wsum (*) f_0|), z = PReLU(W . cat(f_0, g_i f_i) + b).  Ragged sizes (partial tiles, out-of-image
+    halo), odd frame counts (the two pixel-warp sets get unequal shares), more tiles than SMs, output into a channel slice."""
+    from fbanet_b200 import ops
+    E = 64
+    feat = _r(B, Fr, E, h, w, seed=1)
+    wsum = (_r(9, E, seed=2, scale=0.05)).float()
+    hi = wsum.to(BF).float()
+    wsum_used = hi + (wsum - hi).to(BF).float()                       # what the hi + lo bf16 rows carry
+    wf, bf_, alpha = _r(E, Fr * E, seed=3, scale=1 / math.sqrt(Fr * E)), _r(E, seed=4, scale=0.2), torch.tensor([0.1])
+    kern = wsum_used.t().reshape(1, E, 3, 3)                          # [tap, c] -> [1, c, ky, kx]
+    s = F.conv2d(feat.reshape(B * Fr, E, h, w), kern, padding=1).reshape(B, Fr, h, w)
+    gate = torch.sigmoid((s[:, 1:] - s[:, :1]).abs())
+    gated = torch.cat([feat[:, :1], feat[:, 1:] * gate[:, :, None]], 1).reshape(B, Fr * E, h, w)
+    ref = F.prelu(F.conv2d(gated, wf[:, :, None, None], bf_), alpha).permute(0, 2, 3, 1)
+    fd = feat.permute(0, 1, 3, 4, 2).contiguous().to(cuda, BF)       # [B,F,H,W,E]
+    buf = torch.zeros(B, h, w, 2 * E, device=cuda, dtype=BF)
+    r = ops.faf_fuse(fd, ops.faf_fuse_score_weight(wsum.to(cuda)), wf.to(cuda, BF), bf_.to(cuda), alpha.to(cuda), buf[..., E:], want_gate=True)
+    assert r is not None
+    out, g = r
+    torch.cuda.synchronize()
+    assert (g.cpu() - gate).abs().max().item() < 2e-3, (g.cpu() - gate).abs().max().item()
+    _check(buf[..., E:], ref, tol=3e-2)
+    assert buf[..., :E].abs().max().item() == 0

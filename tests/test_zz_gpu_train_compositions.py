@@ -308,10 +308,11 @@ def test_whole_model_training_step_bf16_embed64_on_the_gpu(cuda):
         worst_cos, worst_rel = min(worst_cos, cos), max(worst_rel, rel)
     rows.sort()
     print("bf16 E=64 whole-model gradients: worst cosine %.4f, worst relative L2 error %.4f; lowest five:" % (worst_cos, worst_rel), rows[:5])
-    # calibration (B200, this seed): see profiles/r2_train_bf16_parity.log
-    bad = [(c, r, n) for c, r, n in rows if c < 0.90 or r > 0.45]
+    # calibration (B200, this seed, profiles/r2_train_bf16_parity.log): worst cosine 0.9965, worst relative error 0.153 (both on
+    # relative-position bias tables, whose gradients sum bf16 attention probabilities over every window); bars at ~2x that distance
+    bad = [(c, r, n) for c, r, n in rows if c < 0.990 or r > 0.30]
     assert not bad, bad[:8]
-    assert sum(c for c, _, _ in rows) / len(rows) > 0.985
+    assert sum(c for c, _, _ in rows) / len(rows) > 0.995
     for p in m.parameters():
         p.grad = None
     m.drop_path_rate = 0.0
