@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBANET_B200_LIB") or os.path.join(_HERE, "csrc", "libfbanet_b200.so")   # env override: A/B two builds in one process tree
-ABI_VERSION = 25
+ABI_VERSION = 26
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -100,7 +100,7 @@ class AttnParams(C.Structure):
         ("qkv", C.c_void_p), ("out", C.c_void_p), ("bias_table", C.c_void_p), ("dtype", C.c_int32),
         ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("heads", C.c_int32), ("win", C.c_int32), ("shift", C.c_int32),
         ("qkv_ld", C.c_int32), ("out_ld", C.c_int32), ("scale", C.c_float), ("impl", C.c_int32), ("bias_expanded", C.c_void_p),
-        ("q_prescaled", C.c_int32), ("_pad", C.c_int32),
+        ("q_prescaled", C.c_int32), ("_pad", C.c_int32), ("bias_wrap", C.c_void_p),
     ]
 
 
@@ -292,7 +292,7 @@ OPS = {
     "fbanet_window_attention_bwd_sm100": AttnBwdParams, "fbanet_faf_gate_bwd_sm100": FafGateBwdParams,
     "fbanet_drop_path_add_sm100": DropPathParams,
 }
-MISC_SYMBOLS = ["fbanet_abi_version", "fbanet_abi_sizeof", "fbanet_last_cuda_error", "fbanet_conv_gemm_tcgen05_supported", "fbanet_leff_fc2_supported", "fbanet_leff_mlp_supported", "fbanet_faf_fuse_supported",
+MISC_SYMBOLS = ["fbanet_abi_version", "fbanet_abi_sizeof", "fbanet_last_cuda_error", "fbanet_conv_gemm_tcgen05_supported", "fbanet_leff_fc2_supported", "fbanet_leff_mlp_supported", "fbanet_faf_fuse_supported", "fbanet_window_attention_tcgen05_supported",
                 "fbanet_train_loss_workspace_doubles", "fbanet_layernorm_bwd_blocks", "fbanet_act_bwd_blocks",
                 "fbanet_dwconv_bwd_blocks", "fbanet_faf_gate_bwd_blocks", "fbanet_attn_bwd_partial_floats"]
 
@@ -320,6 +320,8 @@ def load() -> C.CDLL:
     lib.fbanet_leff_fc2_supported.argtypes = [C.POINTER(LeffFc2Params)]
     lib.fbanet_leff_mlp_supported.restype = C.c_int
     lib.fbanet_leff_mlp_supported.argtypes = [C.POINTER(LeffMlpParams)]
+    lib.fbanet_window_attention_tcgen05_supported.restype = C.c_int
+    lib.fbanet_window_attention_tcgen05_supported.argtypes = [C.POINTER(AttnParams)]
     lib.fbanet_faf_fuse_supported.restype = C.c_int
     lib.fbanet_faf_fuse_supported.argtypes = [C.POINTER(FafFuseParams)]
     lib.fbanet_train_loss_workspace_doubles.restype = C.c_int64

@@ -30,6 +30,8 @@ int window_attention_tc_supported(const fbanet_attn_params* p);
 int window_attention_tc_launch(const fbanet_attn_params* p, cudaStream_t s);
 int window_attention_dh16_supported(const fbanet_attn_params* p);
 int window_attention_dh16_launch(const fbanet_attn_params* p, cudaStream_t s);
+int window_attention_tcgen05_supported(const fbanet_attn_params* p);
+int window_attention_tcgen05_launch(const fbanet_attn_params* p, cudaStream_t s);
 
 }  // namespace fbanet
 
@@ -91,12 +93,18 @@ extern "C" int fbanet_conv_gemm_sm100(const fbanet_conv_params* p, void* stream)
   return conv_gemm_simt_launch(p, (cudaStream_t)stream);
 }
 
+extern "C" int fbanet_window_attention_tcgen05_supported(const fbanet_attn_params* p) {
+  if (window_attention_validate(p) != FBANET_OK) return 0;
+  return window_attention_tcgen05_supported(p);
+}
+
 extern "C" int fbanet_window_attention_sm100(const fbanet_attn_params* p, void* stream) {
   int rc = window_attention_validate(p);
   if (rc != FBANET_OK) return rc;
   const bool tc_ok = window_attention_tc_supported(p) != 0;
   if (p->impl == FBANET_IMPL_TCGEN05 && !tc_ok) return FBANET_E_UNSUPPORTED;
   if (tc_ok && p->impl != FBANET_IMPL_SIMT) {
+    if (window_attention_tcgen05_supported(p)) return window_attention_tcgen05_launch(p, (cudaStream_t)stream);   // d_h = 64: tcgen05 + TMEM
     if (window_attention_dh16_supported(p)) return window_attention_dh16_launch(p, (cudaStream_t)stream);
     return window_attention_tc_launch(p, (cudaStream_t)stream);
   }

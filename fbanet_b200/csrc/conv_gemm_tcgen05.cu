@@ -517,7 +517,8 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
         tc_fence_after();
         if (mine) {
           const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-          float* prow = P + row * pst;
+          const uint32_t prow = smem_u32(P) + (uint32_t)(row * pst * 4);   // explicit shared-space stores / loads below: through the generic
+                                                                           // pointer the gather compiled to LD.E (long-scoreboard latency)
           for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
             const int nc = BN - c0 >= 32 ? 32 : 16;
@@ -525,7 +526,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (j < nc) prow[c0 + j] = __uint_as_float(v[j]);
+              if (j < nc) asm volatile("st.shared.b32 [%0], %1;" ::"r"(prow + (uint32_t)((c0 + j) * 4)), "r"(v[j]));
           }
         }
         tc_fence_before();
@@ -537,7 +538,12 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
         const int oy = ti.ty * p.step_y + ly - 1, ox = ti.tx * p.step_x + lx - 1;
         if (lx >= 1 && lx <= 14 && ly >= 1 && ly <= 6 && oy < p.Ho && ox < p.Wo) {
           float* op = reinterpret_cast<float*>(p.out) + img * p.out_img_stride + ((int64_t)oy * p.Wo + ox) * p.out_ld;
-          const float* pc = P + ((ly - 1) * 16 + (lx - 1)) * pst;   // P row of tap (0,0) for this output pixel
+          const uint32_t pc_a = smem_u32(P) + (uint32_t)((((ly - 1) * 16 + (lx - 1)) * pst) * 4);   // P row of tap (0,0) for this output pixel
+          auto pc = [&](int off) -> float {
+            float f;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(f) : "r"(pc_a + (uint32_t)(off * 4)));
+            return f;
+          };
           auto gather = [&](auto ct_tag) {
             constexpr int CT = decltype(ct_tag)::value;             // compile-time outputs per tap: all 9 * CT loads independent
             float sacc[CT];
@@ -546,7 +552,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
 #pragma unroll
             for (int t = 0; t < 9; ++t)
 #pragma unroll
-              for (int j = 0; j < CT; ++j) sacc[j] += pc[((t / 3) * 16 + (t % 3)) * pst + t * CT + j];
+              for (int j = 0; j < CT; ++j) sacc[j] += pc(((t / 3) * 16 + (t % 3)) * pst + t * CT + j);
             if (CT == 2) *reinterpret_cast<float2*>(op) = make_float2(sacc[0], sacc[1]);
             else if (CT == 4) *reinterpret_cast<float4*>(op) = make_float4(sacc[0], sacc[1], sacc[2], sacc[3]);
             else if (CT == 8) {
@@ -566,8 +572,8 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
             for (int t = 0; t < 9; ++t)
 #pragma unroll
               for (int j = 0; j < HH; ++j) {
-                const float* q = pc + ((t / 3) * 16 + (t % 3)) * pst + t * 2 * HH + j;
-                sacc[j] += q[0] + q[HH];
+                const int q = ((t / 3) * 16 + (t % 3)) * pst + t * 2 * HH + j;
+                sacc[j] += pc(q) + pc(q + HH);
               }
             if constexpr (HH == 1) op[0] = sacc[0];
             else if constexpr (HH == 2) *reinterpret_cast<float2*>(op) = make_float2(sacc[0], sacc[1]);
@@ -592,7 +598,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
               for (int j = 0; j < Ct; ++j) {
                 float sj = bias_s[j];
 #pragma unroll
-                for (int t = 0; t < 9; ++t) sj += pc[((t / 3) * 16 + (t % 3)) * pst + t * Ct + j];
+                for (int t = 0; t < 9; ++t) sj += pc(((t / 3) * 16 + (t % 3)) * pst + t * Ct + j);
                 op[j] = sj;
               }
           }

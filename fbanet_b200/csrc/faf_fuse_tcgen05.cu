@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(384, 1) faf_fuse_kernel(const __grid_constant_
     const int k = (warp - 4) >> 2, q = warp & 3;
     const int pix = q * 32 + lane;                       // this thread's pixel of the 8 x 16 tile = its TMEM lane
     const int py = pix / FF_TW, px = pix % FF_TW;
-    float* ps = ps_s + k * (FF_HPX * FF_PS_STRIDE);
+    const uint32_t ps_a = smem_u32(ps_s) + (uint32_t)(k * FF_HPX * FF_PS_STRIDE * 4);            // this set's score scratch
+    const uint32_t ps_g = ps_a + (uint32_t)((py * FF_HW + px) * FF_PS_STRIDE * 4);               // ... at this pixel's tap (0, 0)
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float alpha = p.alpha ? __ldg(p.alpha) : 0.f;
     const int bar_id = 1 + 2 * k;
@@ -194,16 +195,18 @@ __global__ void __launch_bounds__(384, 1) faf_fuse_kernel(const __grid_constant_
           uint32_t v[32];
           tmem_ld32(lane_addr + (uint32_t)k * 64u, v);                   // MMA tile 0: halo pixels 0..127
           tmem_ld_wait();
-          float* row = ps + pix * FF_PS_STRIDE;
+          const uint32_t row = ps_a + (uint32_t)(pix * FF_PS_STRIDE * 4);   // (explicit shared-space accesses: generic ones are LD.E / ST.E)
 #pragma unroll
-          for (int t = 0; t < 9; ++t) row[t] = __uint_as_float(v[2 * t]) + __uint_as_float(v[2 * t + 1]);
+          for (int t = 0; t < 9; ++t)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + (uint32_t)(t * 4)), "f"(__uint_as_float(v[2 * t]) + __uint_as_float(v[2 * t + 1])));
           if (q < 2) {                                                    // MMA tile 1: halo pixels 128..179 live in lane quarters 0, 1
             tmem_ld32(lane_addr + (uint32_t)k * 64u + 32u, v);
             tmem_ld_wait();
             if (128 + pix < FF_HPX) {
-              float* row1 = ps + (128 + pix) * FF_PS_STRIDE;
+              const uint32_t row1 = ps_a + (uint32_t)((128 + pix) * FF_PS_STRIDE * 4);
 #pragma unroll
-              for (int t = 0; t < 9; ++t) row1[t] = __uint_as_float(v[2 * t]) + __uint_as_float(v[2 * t + 1]);
+              for (int t = 0; t < 9; ++t)
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(row1 + (uint32_t)(t * 4)), "f"(__uint_as_float(v[2 * t]) + __uint_as_float(v[2 * t + 1])));
             }
           }
         }
@@ -213,7 +216,11 @@ __global__ void __launch_bounds__(384, 1) faf_fuse_kernel(const __grid_constant_
         named_bar_sync(bar_id, 128);                                      // the set's four warps have written the scratch
         float s = 0.f;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) s += ps[((py + t / 3) * FF_HW + px + t % 3) * FF_PS_STRIDE + t];
+        for (int t = 0; t < 9; ++t) {
+          float pv;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pv) : "r"(ps_g + (uint32_t)((((t / 3) * FF_HW + t % 3) * FF_PS_STRIDE + t) * 4)));
+          s += pv;
+        }
         named_bar_sync(bar_id + 1, 128);                                  // ... and read it: the next frame of this set may overwrite
         float g = 1.f;
         if (f == 0) {

@@ -337,6 +337,8 @@ class BaseModel(nn.Module):
                     P[k + ".rpb"] = f32(a.relative_position_bias_table)
                     if tc:  # dense per-head bias in log2 units for the tensor-core attention kernel
                         P[k + ".rpbx"] = ops.expand_rel_pos_bias(P[k + ".rpb"], ly.win)
+                        if ly.shift > 0 and ly.dim // ly.heads == 64 and ly.win == 10:   # tcgen05 attention: tables of the wrapping windows
+                            P[k + ".rpbw"] = ops.expand_rel_pos_bias_wrap(P[k + ".rpbx"], ly.win)
                     put_lin(k + ".proj", a.proj)
                     put_lin(k + ".fc2", ly.mlp.linear2[0])
                     dw = ly.mlp.dwconv[0]
@@ -429,7 +431,7 @@ class BaseModel(nn.Module):
             qkv = self._lin(P, key + ".qkv", ln1)
         scale = self.qk_scale or (Cd // ly.heads) ** -0.5
         att = ops.window_attention(qkv.view(-1, 3 * Cd), P[key + ".rpb"], B, H, W, ly.heads, ly.win, ly.shift, scale, impl=self.impl,
-                                   bias_expanded=P.get(key + ".rpbx"), q_prescaled=self._use_tc())
+                                   bias_expanded=P.get(key + ".rpbx"), q_prescaled=self._use_tc(), bias_wrap=P.get(key + ".rpbw"))
         x1 = self._lin(P, key + ".proj", att.view(B, H, W, Cd), residual=x)
         if fold:
             h = self._lin(P, key + ".fc1", x1, act=self.gelu_act, ln_stats=ops.row_stats(x1.view(-1, Cd)))

@@ -21,6 +21,7 @@ _DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
 
 # launch counter: bench.py reports how many of OUR kernels ran in the timed region
 LAUNCHES = 0
+LAST_ATTENTION_ON_TCGEN05 = False   # whether the last window_attention call took the tcgen05 / TMEM kernel (tests)
 # when a list, conv_gemm appends (start_event, end_event, algorithmic_flops) per launch (bench roofline)
 _PROFILE = None
 
@@ -351,9 +352,38 @@ def expand_rel_pos_bias(bias_table: torch.Tensor, win: int) -> torch.Tensor:
     return out.contiguous()
 
 
+def expand_rel_pos_bias_wrap(bias_expanded: torch.Tensor, win: int) -> torch.Tensor:
+    """Tables of the tcgen05 attention kernel for the windows of a SHIFTED layer that wrap around the image edge: ``[heads, 3, N, NP]``
+    fp32 for wrap type 1 (bottom edge), 2 (right edge), 3 (corner).  The kernel fetches such a window as 2 / 4 TMA boxes, so its tile
+    holds the tokens in box order -- type 1: rows ``iy < 5`` then ``iy >= 5`` (= natural order); type 2: columns ``ix < 5`` of every row,
+    then ``ix >= 5``; type 3: the four 5 x 5 quadrants -- and the table is the bias with rows and columns permuted alike, plus the Swin
+    shift mask (``-100`` in the reference, ``layers/fba_net.py:151-184``; log2 units here) between tokens of different boxes, which
+    are exactly the tokens of different shift regions."""
+    heads, N, NP = bias_expanded.shape
+    half = win // 2
+    dev = bias_expanded.device
+    r = torch.arange(N, device=dev)
+    toks, blocks = [], []
+    for t in (1, 2, 3):
+        if t == 1:
+            tok, blk = r, r // (half * win)
+        elif t == 2:
+            rr = r % (half * win)
+            tok, blk = (rr // half) * win + (r // (half * win)) * half + rr % half, r // (half * win)
+        else:
+            qd, rr = r // (half * half), r % (half * half)
+            tok, blk = ((qd // 2) * half + rr // half) * win + (qd % 2) * half + rr % half, qd
+        toks.append(tok), blocks.append(blk)
+    out = torch.full((heads, 3, N, NP), -1e30, device=dev, dtype=torch.float32)
+    for i, (tok, blk) in enumerate(zip(toks, blocks)):
+        tbl = bias_expanded[:, tok][:, :, tok]
+        out[:, i, :, :N] = tbl + (blk[:, None] != blk[None, :]).float() * (-100.0 * 1.4426950408889634)
+    return out.contiguous()
+
+
 def window_attention(qkv: torch.Tensor, bias_table: torch.Tensor, B: int, H: int, W: int, heads: int, win: int, shift: int,
                      scale: float, impl: int = L.IMPL_AUTO, bias_expanded: Optional[torch.Tensor] = None,
-                     q_prescaled: bool = False) -> torch.Tensor:
+                     q_prescaled: bool = False, bias_wrap: Optional[torch.Tensor] = None) -> torch.Tensor:
     """qkv ``[B*H*W, 3C]`` -> ``[B*H*W, C]``.  ``q_prescaled``: the q columns were produced by projection weights that
     already carry ``scale * log2(e)`` (bf16 tensor-core kernels only); ``scale`` is then ignored."""
     assert qkv.is_cuda and qkv.dim() == 2 and qkv.stride(1) == 1 and qkv.shape[0] == B * H * W
@@ -369,7 +399,13 @@ def window_attention(qkv: torch.Tensor, bias_table: torch.Tensor, B: int, H: int
         N = win * win
         assert bias_expanded.dtype == torch.float32 and bias_expanded.is_contiguous() and bias_expanded.shape == (heads, N, (N + 15) // 16 * 16)
         p.bias_expanded = bias_expanded.data_ptr()
-    _call("fbanet_window_attention_sm100", p, nbytes=(qkv.numel() + out.numel()) * qkv.element_size())
+    if bias_wrap is not None:
+        assert bias_expanded is not None and bias_wrap.dtype == torch.float32 and bias_wrap.is_contiguous() and bias_wrap.shape == (heads, 3) + tuple(bias_expanded.shape[1:])
+        p.bias_wrap = bias_wrap.data_ptr()
+    global LAST_ATTENTION_ON_TCGEN05
+    LAST_ATTENTION_ON_TCGEN05 = bool(L.load().fbanet_window_attention_tcgen05_supported(C.byref(p))) and impl != L.IMPL_SIMT
+    _call("fbanet_window_attention_sm100", p, tag=f"dh{Cc // heads} {'tcgen05' if LAST_ATTENTION_ON_TCGEN05 else 'mma.sync/simt'}",
+          nbytes=(qkv.numel() + out.numel()) * qkv.element_size())
     return out
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 25
+#define FBANET_ABI_VERSION 26
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -228,6 +228,11 @@ typedef struct fbanet_attn_params {
   int32_t q_prescaled;        /* nonzero: the q columns already carry scale*log2(e) (folded into the q projection weights by
                                  the caller); `scale` is then ignored.  Tensor-core (bf16) kernels only. */
   int32_t _pad;
+  const float* bias_wrap;     /* optional, tcgen05 kernel (d_h = 64) with shift > 0: dense fp32 [heads][3][win^2][NP], the table of
+                                 bias_expanded for the windows that wrap around the bottom edge (0), the right edge (1) or both (2):
+                                 rows and columns in the order the kernel fetches the tokens (box order: a split along x puts
+                                 columns 0..4 of every window row first) and with the shift mask (-100 * log2(e) between tokens of
+                                 different boxes = different shift regions) added */
 } fbanet_attn_params;
 
 /* K7: LeFF depthwise 3x3 (pad 1) + bias + GELU on a channels-last map
@@ -581,6 +586,8 @@ int fbanet_leff_fc2_supported(const fbanet_leff_fc2_params* p);
 int fbanet_leff_mlp_supported(const fbanet_leff_mlp_params* p);
 /* 1 if the one-pass FAF gate + fusion kernel takes this problem, else 0 */
 int fbanet_faf_fuse_supported(const fbanet_faf_fuse_params* p);
+/* 1 if fbanet_window_attention_sm100 runs this problem on the tcgen05 / TMEM kernel (d_h = 64, window 10, dense bias, prescaled q) */
+int fbanet_window_attention_tcgen05_supported(const fbanet_attn_params* p);
 /* 1 if the tcgen05 implicit-GEMM can run this problem, else 0 */
 int fbanet_conv_gemm_tcgen05_supported(const fbanet_conv_params* p);
 

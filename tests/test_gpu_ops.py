@@ -280,6 +280,48 @@ def test_window_attention(cuda, dt, C, heads, HW, win, shift, prescaled):
     _close(got.view(B, H, W, C), o, dt, scale=2.0)
 
 
+@pytest.mark.parametrize("C,heads,HW,shift,B,mag", [(64, 1, 20, 0, 2, 1.5), (64, 1, 20, 5, 2, 1.5), (128, 2, 30, 5, 2, 1.5), (64, 1, 40, 5, 1, 1.5),
+                                                     (128, 2, 40, 0, 3, 1.5), (64, 1, 160, 5, 2, 1.5), (128, 2, 30, 5, 1, 10.0)])
+def test_window_attention_tcgen05_dh64(cuda, C, heads, HW, shift, B, mag):
+    """K6 for the d_h = 64 stages on tcgen05 + TMEM (S = Q K^T and O = P V as tcgen05.mma, scores and P in tensor memory / shared
+    memory, one softmax thread per query row) against the oracle's roll + partition + WindowAttention + mask
+    (layers/fba_net.py:139-250, layers/window_attention.py:173-243): unshifted and shifted layers -- with 2, 3, 4 and 16 windows
+    per side every wrap type occurs (none, bottom edge, right edge, corner: the permuted row order and the block mask) -- one and
+    two heads, more items than SMs, and logits in the hundreds (exact row max)."""
+    from fbanet_b200 import ops
+    from oracle.fbanet_oracle import shift_attn_mask, window_partition, window_reverse, relative_position_index
+    dt, win = torch.bfloat16, 10
+    H = W = HW
+    N, dh = win * win, C // heads
+    scale = dh ** -0.5
+    qkv = _r(dt, B, H, W, 3 * C, seed=1, scale=mag)
+    qkv[..., 2 * C:] = _r(dt, B, H, W, C, seed=6, scale=1.0)
+    table = _r(torch.float32, (2 * win - 1) ** 2, heads, seed=2, scale=0.5)
+    qkv_in = qkv.reshape(-1, 3 * C).clone()
+    qkv_in[:, :C] = (qkv_in[:, :C] * (scale * 1.4426950408889634)).to(dt).float()      # what the folded q projection emits
+    qkv = qkv.clone()
+    qkv[..., :C] = qkv_in[:, :C].view(B, H, W, C) / (scale * 1.4426950408889634)       # the reference sees the same rounded q
+    y = torch.roll(qkv, (-shift, -shift), (1, 2)) if shift else qkv
+    yw = window_partition(y, win)
+    q, k, v = (yw[..., i * C:(i + 1) * C].view(-1, N, heads, dh).permute(0, 2, 1, 3) for i in range(3))
+    attn = (q.double() * scale) @ k.double().transpose(-2, -1)
+    attn = attn + table[relative_position_index(win).view(-1)].view(N, N, heads).permute(2, 0, 1)[None].double()
+    if shift:
+        mask = shift_attn_mask(H, W, win, shift)
+        attn = (attn.view(B, mask.shape[0], heads, N, N) + mask[None, :, None].double()).view(-1, heads, N, N)
+    o = (torch.softmax(attn, -1) @ v.double()).float().transpose(1, 2).reshape(-1, N, C)
+    o = window_reverse(o, win, B, H, W)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    tab = table.to(cuda)
+    bx = ops.expand_rel_pos_bias(tab, win)
+    got = ops.window_attention(qkv_in.to(cuda, dt), tab, B, H, W, heads, win, shift, scale, bias_expanded=bx, q_prescaled=True,
+                               bias_wrap=ops.expand_rel_pos_bias_wrap(bx, win) if shift else None)
+    assert ops.LAST_ATTENTION_ON_TCGEN05, "the d_h = 64 shapes must take the tcgen05 kernel"
+    assert torch.isfinite(got.float()).all()
+    _close(got.view(B, H, W, C), o, dt, scale=2.0)
+
+
 @pytest.mark.parametrize("prescaled", [False, True])
 @pytest.mark.parametrize("mag", [6.0, 14.0])
 def test_window_attention_huge_logits(cuda, prescaled, mag):

@@ -31,7 +31,8 @@ def attn(B, S, C, heads, shift):
     qkv = (torch.rand(B * S * S, 3 * C, device=dev) - 0.5).to(BF)
     table = torch.rand(361, heads, device=dev) * 0.1
     bx = ops.expand_rel_pos_bias(table, 10)
-    return (lambda: ops.window_attention(qkv, table, B, S, S, heads, 10, shift, (C // heads) ** -0.5, bias_expanded=bx, q_prescaled=True)), 2 * B * S * S * 4 * C / 1e9
+    bw = ops.expand_rel_pos_bias_wrap(bx, 10) if shift else None
+    return (lambda: ops.window_attention(qkv, table, B, S, S, heads, 10, shift, (C // heads) ** -0.5, bias_expanded=bx, q_prescaled=True, bias_wrap=bw)), 2 * B * S * S * 4 * C / 1e9
 
 
 def dw(B, S, C):
@@ -106,6 +107,7 @@ CASES = {
     "attn_dec1_128x8_s0": lambda: attn(64, 160, 128, 8, 0),
     "attn_dec0_256x16_s5": lambda: attn(64, 80, 256, 16, 5),
     "attn_enc0_64x1_s5": lambda: attn(64, 160, 64, 1, 5),
+    "attn_enc0_64x1_s0": lambda: attn(64, 160, 64, 1, 0),
     "attn_enc1_128x2_s5": lambda: attn(64, 80, 128, 2, 5),
     "attn_bott_256x16_s5": lambda: attn(64, 40, 256, 16, 5),
     "dw_160_512": lambda: dw(64, 160, 512),
