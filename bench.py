@@ -442,9 +442,16 @@ def main():
     if summ:
         sj = json.load(open(os.path.join(ROOT, "profiles", summ[-1])))
         cf = sj.get("families", {}).get("conv_gemm_tcgen05_kernel")
-        if cf and cf.get("launches"):
+        order, per_launch = prof.get("order", []), sj.get("conv_gemm_launches", [])
+        if per_launch and len(per_launch) == len(order):
+            # the ncu launch list and this run launch the same sequence of implicit GEMMs: take the 3x3 / 4x4 convolutions' share
+            sel = [d["dram_bytes"] for d, taps in zip(per_launch, order) if taps > 1]
+            traffic = sum(sel) / max(1, len(sel))
+            traffic_src = (f"profiles/{summ[-1]} (ncu dram__bytes_read+write per launch, the {len(sel)} conv launches of one batch-"
+                           f"{sj.get('batch', 64)} step, matched by launch order)")
+        elif cf and cf.get("launches"):
             traffic = cf["dram_bytes"] / cf["launches"]
-            traffic_src = f"profiles/{summ[-1]} (ncu dram__bytes_read+write, {cf['launches']} launches of one batch-{sj.get('batch', 64)} step)"
+            traffic_src = f"profiles/{summ[-1]} (ncu dram__bytes_read+write, all {cf['launches']} implicit-GEMM launches of one batch-{sj.get('batch', 64)} step)"
     step_ms = ms / args.steps
     cls = prof.get("classes", {})
     conv = cls.get("conv", {"ms": 0.0, "flops": 0.0, "bytes": 0, "launches": 0})

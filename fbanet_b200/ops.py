@@ -212,7 +212,8 @@ def profile_conv_gemm(fn, stream) -> dict:
         sh = shapes.setdefault(tag, {"ms": 0.0, "flops": 0.0, "bytes": 0, "launches": 0, "taps": taps})
         sh["ms"] += t; sh["flops"] += f; sh["bytes"] += nb; sh["launches"] += 1
     return {"kernel": "fbanet_conv_gemm_sm100 (implicit-GEMM conv/linear, all launches of one step)", "ms": ms, "flops": flops,
-            "launches": len(recs), "tflops": flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0, "classes": classes, "shapes": shapes}
+            "launches": len(recs), "tflops": flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0, "classes": classes, "shapes": shapes,
+            "order": [taps for _, _, _, _, taps in recs]}
 
 
 def tcgen05_supported(p: L.ConvParams) -> bool:

@@ -96,7 +96,17 @@ def mlp(B, S, C):
     return (lambda: ops.leff_mlp(x, w1, b1, dwt, db, w2, b2, out, res, L.ACT_GELU_TANH)), 2 * 3 * res.numel() / 1e9
 
 
+def faf_fuse(B, S):
+    """K2 in one pass (ops.faf_fuse): bytes = features read once + fused map written."""
+    feat = (torch.rand(B, 14, S, S, 64, device=dev) - 0.5).to(BF)
+    ws = ops.faf_fuse_score_weight((torch.rand(9, 64, device=dev) - 0.5) * 0.1)
+    wf, bf_, al = ((torch.rand(64, 14 * 64, device=dev) - 0.5) * 0.05).to(BF), torch.zeros(64, device=dev), torch.full((1,), 0.1, device=dev)
+    out = torch.empty(B, S, S, 64, device=dev, dtype=BF)
+    return (lambda: ops.faf_fuse(feat, ws, wf, bf_, al, out, want_gate=True)), (feat.numel() + out.numel()) * 2 / 1e9
+
+
 CASES = {
+    "faf_fuse_160": lambda: faf_fuse(64, 160),
     "mlp_dec1_128": lambda: mlp(64, 160, 128),
     "mlp_enc1_128": lambda: mlp(64, 80, 128),
     "mlp_enc0_64": lambda: mlp(64, 160, 64),
