@@ -5,7 +5,9 @@ Public API (mirrors the reference's): ``get_arch(opt)``, ``BaseModel``, ``load_c
 ``register_frame``); the full-size tiled drivers in ``fbanet_b200.tiling`` (single GPU and row-band sharded over the GPUs of one box);
 and the training step in ``fbanet_b200.train`` (``train_step``: training-mode forward on a reverse-mode tape over the C-ABI ops, ``training_loss``,
 backward into ``FlatParams`` flat buffers, bucketed gradient all-reduce, fused AdamW; learning-rate schedules and stochastic-depth rates).
+The per-kernel ops are also registered as ``torch.library`` custom ops (``torch.ops.fbanet.*``, :mod:`fbanet_b200.torch_ops`).
 """
+from . import torch_ops  # noqa: F401  (registers torch.ops.fbanet.*)
 from .model import BaseModel  # noqa: F401
 from .ops import ecc_homography_burst, flow_warp_burst, training_loss, warp_burst  # noqa: F401
 from .utils.model_utils import get_arch, load_checkpoint, load_checkpoint_multigpu, load_optim, load_start_epoch, save_checkpoint  # noqa: F401

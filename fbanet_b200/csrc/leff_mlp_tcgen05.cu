@@ -38,6 +38,11 @@ constexpr int LM_TW = 8, LM_TH = 16;                       // output tile (pixel
 constexpr int LM_HW = LM_TW + 2, LM_HH = LM_TH + 2;        // halo tile 10 x 18
 constexpr int LM_HPX = LM_HW * LM_HH;                      // 180 halo pixels
 constexpr int LM_XK_BYTES = 256 * 128;                     // one 64-channel K chunk of the x tile: two 128-row MMA tiles
+// C = 128: the K chunks are packed 184 rows apart (180 halo rows, rounded up to the 1 KB swizzle atom) instead of 256: the second MMA
+// tile of a chunk (rows 128..255) then reads 72 rows of whatever follows -- the next chunk, or the head of the hidden tile -- as its
+// accumulator rows 180..255, which nobody looks at.  The 17 KB this frees pay for a second fc2 A tile (P2 of chunk g+1 no longer
+// waits for fc2 of chunk g to retire).
+constexpr int LM_XK_PACKED = 184 * 128;
 constexpr int LM_XBOX_BYTES = LM_HPX * 128;                // bytes TMA writes per K chunk
 constexpr int LM_HID_ROW = 136;                           // bf16 hidden tile row: 64 ch x 2 B + 8 B of padding: P1's lanes (one pixel each, 8-byte
                                                            // stores of the same channels) fall into distinct banks; P2's warps read whole rows
@@ -137,10 +142,11 @@ __global__ void __launch_bounds__(128 + 32 * LM_CW, 1) leff_mlp_kernel(const __g
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int C = NK * 64;
   const int nchunks = p.nchunks;
-  constexpr uint32_t x_slot_bytes = (uint32_t)NK * LM_XK_BYTES;
+  constexpr uint32_t XK = NK == 1 ? (uint32_t)LM_XK_BYTES : (uint32_t)LM_XK_PACKED;   // bytes between the K chunks of an x tile
+  constexpr uint32_t x_slot_bytes = (uint32_t)NK * XK;
   constexpr uint32_t w1_slot_bytes = (uint32_t)NK * LM_W1K_BYTES;
   constexpr uint32_t w2_slot_bytes = (uint32_t)C * 128u;
-  constexpr uint32_t X_SLOTS = NK == 1 ? 2 : 1, A2_SLOTS = NK == 1 ? 2 : 1, W_SLOTS = 2;
+  constexpr uint32_t X_SLOTS = NK == 1 ? 2 : 1, A2_SLOTS = 2, W_SLOTS = 2;
   uint8_t* smem_x = smem;
   uint8_t* smem_hid = smem_x + X_SLOTS * x_slot_bytes;
   uint8_t* smem_w1 = smem_hid + LM_HID_BYTES;
@@ -215,7 +221,7 @@ __global__ void __launch_bounds__(128 + 32 * LM_CW, 1) leff_mlp_kernel(const __g
       if (elect_one()) {
         mbar_expect_tx(&bar_block[LB_X_FULL + xs], (uint32_t)NK * LM_XBOX_BYTES);
         for (int kc = 0; kc < NK; ++kc)
-          tma_load_4d(smem_x + (size_t)xs * x_slot_bytes + (size_t)kc * LM_XK_BYTES, &p.xmap, &bar_block[LB_X_FULL + xs], kc * 64, x0 - 1, y0 - 1, img);
+          tma_load_4d(smem_x + (size_t)xs * x_slot_bytes + (size_t)kc * XK, &p.xmap, &bar_block[LB_X_FULL + xs], kc * 64, x0 - 1, y0 - 1, img);
       }
       __syncwarp();
       if (has_res) {
@@ -288,7 +294,7 @@ __global__ void __launch_bounds__(128 + 32 * LM_CW, 1) leff_mlp_kernel(const __g
           const uint32_t tm = tmem_base + tm1_col0 + b * 128u + (uint32_t)t * 64u;
 #pragma unroll
           for (int kc = 0; kc < NK; ++kc) {
-            const uint32_t a16 = sx16 + ((xs * x_slot_bytes + (uint32_t)kc * LM_XK_BYTES + (uint32_t)t * 16384u) >> 4);
+            const uint32_t a16 = sx16 + ((xs * x_slot_bytes + (uint32_t)kc * XK + (uint32_t)t * 16384u) >> 4);
             const uint32_t b16 = sw1_16 + ((ws * w1_slot_bytes + (uint32_t)kc * LM_W1K_BYTES) >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(tm, desc0 + (uint64_t)(a16 + 2 * k), desc0 + (uint64_t)(b16 + 2 * k), idesc1, (uint32_t)((kc | k) != 0));
@@ -611,11 +617,11 @@ extern "C" int fbanet_leff_mlp_sm100(const fbanet_leff_mlp_params* p, void* stre
   lp.nchunks = p->Hd / 64;
   lp.nk = p->C / 64;
   // shared-memory plan (bytes): x tile(s) | fp32 hidden tile | W1 ring | W2 ring | fc2 A tile(s) | residual slice | identity
-  lp.x_slots = p->C == 64 ? 2 : 1;      // C = 128: one 64 KB x tile (the next tile's load waits for the last fc1 of this one)
+  lp.x_slots = p->C == 64 ? 2 : 1;      // C = 128: one 46 KB x tile (the next tile's load waits for the last fc1 of this one)
   lp.w_slots = 2;
-  lp.a2_slots = p->C == 64 ? 2 : 1;
+  lp.a2_slots = 2;
   { static const char* e = getenv("FBANET_LEFF_POLY"); lp.poly = (e && e[0] == '1') ? 1 : 0; }
-  const size_t smem = (size_t)lp.x_slots * lp.nk * LM_XK_BYTES + LM_HID_BYTES + (size_t)lp.w_slots * lp.nk * LM_W1K_BYTES +
+  const size_t smem = (size_t)lp.x_slots * lp.nk * (p->C == 64 ? LM_XK_BYTES : LM_XK_PACKED) + LM_HID_BYTES + (size_t)lp.w_slots * lp.nk * LM_W1K_BYTES +
                       (size_t)lp.w_slots * p->C * 128 + (size_t)lp.a2_slots * LM_A2_BYTES + LM_A2_BYTES + LM_I_BYTES + 1024;
   typedef void (*KernelFn)(const LmParams);
   const bool erf = p->act == FBANET_ACT_GELU_ERF;

@@ -15,6 +15,8 @@
 //   * writes O over the q rows it has consumed and streams it out with 16-byte stores.
 // The q columns of the fused qkv GEMM may be pre-multiplied by scale*log2(e) (`q_prescaled`), which removes
 // the per-score FFMA.  Bound: MUFU.EX2 (one per score) -- see DESIGN.md "K6".
+#include <stdlib.h>
+#include <initializer_list>
 #include <type_traits>
 
 #include "common.cuh"
@@ -42,6 +44,28 @@ __device__ __forceinline__ float ex2(float x) {
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // volatile: keeps the hand-made MUFU / MMA interleave
   return y;
 }
+// exp2 of two scores on the FMA pipe (no MUFU): x = n + f with n = round(x) taken from the low mantissa bits of x + 1.5 * 2^23,
+// 2^f on [-0.5, 0.5] as a degree-3 minimax polynomial (relative error 7.5e-5 = 2^-13.7: the result is rounded to bf16, 2^-9, right
+// after), and n added to the exponent field.  Scores are clamped to [-125, 126] first: the -1e30 of the padded keys and the shift
+// mask become 2^-125 (nothing), and a logit beyond 2^60 still drives the row sum out of the band that triggers the exact path.
+__device__ __forceinline__ uint32_t ex2_poly_pack2(float x0, float x1) {
+  x0 = fminf(fmaxf(x0, -125.f), 126.f);
+  x1 = fminf(fmaxf(x1, -125.f), 126.f);
+  const f32x2 x = pack_f2(x0, x1);
+  const f32x2 xf = add_f2(x, pack_f2(12582912.f, 12582912.f));
+  const f32x2 n = add_f2(xf, pack_f2(-12582912.f, -12582912.f));
+  const f32x2 f = fma_f2(n, pack_f2(-1.f, -1.f), x);
+  f32x2 r = fma_f2(pack_f2(0.055171649903059006f, 0.055171649903059006f), f, pack_f2(0.2426111251115799f, 0.2426111251115799f));
+  r = fma_f2(r, f, pack_f2(0.6932609677314758f, 0.6932609677314758f));
+  r = fma_f2(r, f, pack_f2(0.9999280571937561f, 0.9999280571937561f));
+  float r0, r1, n0, n1;
+  unpack_f2(r, r0, r1);
+  unpack_f2(xf, n0, n1);
+  const float y0 = __uint_as_float(__float_as_uint(r0) + (__float_as_uint(n0) << 23));
+  const float y1 = __uint_as_float(__float_as_uint(r1) + (__float_as_uint(n1) << 23));
+  __nv_bfloat162 v = __floats2bfloat162_rn(y0, y1);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -58,7 +82,11 @@ __device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
 // byte offset of 16-byte chunk `c` (0/1) of row `row` inside a swizzled [112][32 B] tile
 __device__ __forceinline__ uint32_t swz(int row, int c) { return (uint32_t)(row * ROWB + ((c ^ ((row >> 2) & 1)) << 4)); }
 
-template <bool PRESCALED>
+// POLY: how many of the four probability pairs of a 16-key step take the FMA-pipe exp2 (0 = all on MUFU.EX2, the default).  Measured
+// (profiles/r2_t_attn_poly_mlp_ab.log, dim 128 x 8 heads @160^2, batch 64): 0.592 / 0.601 / 0.678 / 0.751 ms for 0 / 1 / 2 / 3 pairs
+// -- every pair moved off the XU pipe costs ~12 issue slots and the kernel has none to spare (XU 66 % busy, issue-bound), so the
+// experiment stays behind FBANET_ATTN_POLY and MUFU.EX2 stays the path.
+template <bool PRESCALED, int POLY>
 __global__ void __launch_bounds__(WARPS * 32, 1) window_attention_dh16_kernel(const fbanet_attn_params p, const int win_chunk) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -236,11 +264,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) window_attention_dh16_kernel(co
         if (2 * ks + 2 < NTU) score_tile(sa[nxt], mt, 2 * ks + 2, m0, m1, c0, c1, shifted_tag, wrap_tag);
         if (2 * ks + 3 < NTU) score_tile(sb[nxt], mt, 2 * ks + 3, m0, m1, c0, c1, shifted_tag, wrap_tag);
         uint32_t pa[4];
-        pa[0] = pack2(ex2(sa[cur][0]), ex2(sa[cur][1]));
-        pa[1] = pack2(ex2(sa[cur][2]), ex2(sa[cur][3]));
+        pa[0] = POLY >= 1 ? ex2_poly_pack2(sa[cur][0], sa[cur][1]) : pack2(ex2(sa[cur][0]), ex2(sa[cur][1]));
+        pa[1] = POLY >= 3 ? ex2_poly_pack2(sa[cur][2], sa[cur][3]) : pack2(ex2(sa[cur][2]), ex2(sa[cur][3]));
         if (2 * ks + 1 < NTU) {
           pa[2] = pack2(ex2(sb[cur][0]), ex2(sb[cur][1]));
-          pa[3] = pack2(ex2(sb[cur][2]), ex2(sb[cur][3]));
+          pa[3] = POLY >= 2 ? ex2_poly_pack2(sb[cur][2], sb[cur][3]) : pack2(ex2(sb[cur][2]), ex2(sb[cur][3]));
         } else {
           pa[2] = pa[3] = 0u;   // keys 104..111 are padding
         }
@@ -334,8 +362,9 @@ int window_attention_dh16_launch(const fbanet_attn_params* p, cudaStream_t s) {
   static int n_sm = 0;
   static bool opted = false;
   if (!opted) {
-    cudaError_t e = cudaFuncSetAttribute(window_attention_dh16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(window_attention_dh16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaSuccess;
+    for (auto fn : {window_attention_dh16_kernel<true, 0>, window_attention_dh16_kernel<true, 1>, window_attention_dh16_kernel<false, 0>})
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int dev = 0;
     if (e == cudaSuccess) e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -349,8 +378,12 @@ int window_attention_dh16_launch(const fbanet_attn_params* p, cudaStream_t s) {
   if (nchunks > total_windows) nchunks = total_windows;
   const int chunk = (total_windows + nchunks - 1) / nchunks;
   dim3 grid(p->heads, (total_windows + chunk - 1) / chunk);
-  if (p->q_prescaled) window_attention_dh16_kernel<true><<<grid, WARPS * 32, smem, s>>>(*p, chunk);
-  else window_attention_dh16_kernel<false><<<grid, WARPS * 32, smem, s>>>(*p, chunk);
+  // FBANET_ATTN_POLY=1: one probability pair per step on the FMA-pipe exp2 (experiment, slower: see the kernel's comment)
+  static const int poly = [] { const char* e = getenv("FBANET_ATTN_POLY"); return e ? atoi(e) : 0; }();
+  if (p->q_prescaled) {
+    if (poly <= 0) window_attention_dh16_kernel<true, 0><<<grid, WARPS * 32, smem, s>>>(*p, chunk);
+    else window_attention_dh16_kernel<true, 1><<<grid, WARPS * 32, smem, s>>>(*p, chunk);
+  } else window_attention_dh16_kernel<false, 0><<<grid, WARPS * 32, smem, s>>>(*p, chunk);
   return check_launch();
 }
 

@@ -740,3 +740,54 @@ def test_flat_params_adam_step_matches_torch_on_a_module(cuda):
         for a, b in zip(net.parameters(), twin.parameters()):
             assert (a - b).abs().max().item() < 1e-6, step
     assert set(net.state_dict()) == set(twin.state_dict())
+
+
+def test_torch_library_custom_ops(cuda):
+    """the C-ABI launchers as ``torch.library`` custom ops -- ``torch.ops.fbanet.*`` against torch references on
+    bf16-rounded operands (conv3x3 + PReLU-free ReLU + residual, linear + GELU, LayerNorm, window attention, the LeFF MLP in both its
+    one-kernel (C = 64) and two-kernel (C = 256) forms, warp), and ``fbanet::forward`` == the model's own forward."""
+    import fbanet_b200.torch_ops as T
+    from fbanet_b200 import BaseModel, ops, _lib as L
+    from oracle.fbanet_oracle import build_oracle
+    dt = torch.bfloat16
+    # conv3x3 + ReLU + residual
+    x, w, b, r = _r(dt, 2, 64, 24, 20, seed=1), _r(dt, 64, 64, 3, 3, seed=2, scale=0.05), _r(torch.float32, 64, seed=3), _r(dt, 2, 64, 24, 20, seed=4)
+    ref = F.relu(F.conv2d(x, w, b, padding=1)) + r
+    got = torch.ops.fbanet.conv3x3(_nhwc(x, dt, cuda), _pack(w, dt, cuda), b.to(cuda), _nhwc(r, dt, cuda), L.ACT_RELU)
+    _close(got.permute(0, 3, 1, 2), ref, dt)
+    # linear + GELU
+    xl, wl, bl = _r(dt, 1, 15, 20, 128, seed=5), _r(dt, 512, 128, seed=6, scale=0.08), _r(torch.float32, 512, seed=7)
+    got = torch.ops.fbanet.linear(xl.to(cuda, dt), wl.to(cuda, dt), bl.to(cuda), None, L.ACT_GELU_TANH)
+    _close(got, F.gelu(F.linear(xl, wl, bl), approximate="tanh"), dt)
+    # LayerNorm
+    g, be = _r(torch.float32, 128, seed=8) + 1.0, _r(torch.float32, 128, seed=9)
+    _close(torch.ops.fbanet.layernorm(xl.to(cuda, dt), g.to(cuda), be.to(cuda), 1e-5), F.layer_norm(xl, (128,), g, be, 1e-5), dt, scale=2.0)
+    # window attention == the ctypes wrapper (itself checked against the oracle above)
+    qkv, table = _r(dt, 2, 20, 20, 192, seed=10, scale=1.5).to(cuda, dt), _r(torch.float32, 361, 4, seed=11, scale=0.5).to(cuda)
+    a = torch.ops.fbanet.window_attention(qkv, table, 4, 10, 5, 0.25)
+    assert torch.equal(a.view(-1, 64), ops.window_attention(qkv.view(-1, 192), table, 2, 20, 20, 4, 10, 5, 0.25))
+    # LeFF MLP, both forms
+    for C in (64, 256):
+        Hd = 4 * C
+        xm, res = _r(dt, 1, C, 16, 24, seed=12), _r(dt, 1, C, 16, 24, seed=13)
+        w1, b1 = _r(dt, Hd, C, seed=14, scale=1 / math.sqrt(C)), _r(torch.float32, Hd, seed=15, scale=0.2)
+        dw, db = _r(torch.float32, Hd, 1, 3, 3, seed=16, scale=0.3), _r(torch.float32, Hd, seed=17, scale=0.1)
+        w2, b2 = _r(dt, C, Hd, seed=18, scale=1 / math.sqrt(Hd)), _r(torch.float32, C, seed=19)
+        gelu = lambda v: F.gelu(v, approximate="tanh")
+        h1 = gelu(F.linear(xm.permute(0, 2, 3, 1), w1, b1)).permute(0, 3, 1, 2).to(dt).float()
+        mid = gelu(F.conv2d(h1, dw, db, padding=1, groups=Hd)).to(dt).float()
+        ref = F.linear(mid.permute(0, 2, 3, 1), w2, b2) + res.permute(0, 2, 3, 1)
+        got = torch.ops.fbanet.leff_mlp(_nhwc(xm, dt, cuda), w1.to(cuda), b1.to(cuda), dw.to(cuda), db.to(cuda), w2.to(cuda), b2.to(cuda),
+                                        _nhwc(res, dt, cuda), L.ACT_GELU_TANH)
+        _close(got, ref, dt, scale=2.0)
+    # warp == the ctypes wrapper; forward == the module call
+    burst = torch.rand(1, 4, 3, 40, 40, device=cuda)
+    M = torch.eye(3, dtype=torch.float64).repeat(1, 4, 1, 1)
+    M[:, 1:, 0, 2] = 1.5
+    assert torch.equal(torch.ops.fbanet.warp(burst, M), ops.warp_burst(burst, M))
+    cfg = dict(num_frames=4, img_size=40, in_channels=3, embed_dim=32, window_length=10)
+    m = BaseModel(**cfg, token_projection="linear", token_mlp="leff", dtype="fp32")
+    m.load_state_dict(build_oracle(0, **cfg).state_dict())
+    m = m.to(cuda).eval()
+    h = T.register_model(m)
+    assert torch.equal(torch.ops.fbanet.forward(burst, h), m(burst))

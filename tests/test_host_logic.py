@@ -752,3 +752,30 @@ def test_fit_epoch_loop_schedule_checkpoints_and_resume(monkeypatch, tmp_path):
     assert load_start_epoch(ck) == 2 and load_optim(flat2, ck) == want[1] and flat2.step == 4
     train.fit(m2, flat2, batches, nepoch=4, start_epoch=3, lr_initial=1e-3, warmup_epochs=2)
     assert torch.equal(flat2.data, final)
+
+
+def test_torch_library_ops_are_registered_with_fake_kernels_and_no_cpu_fallback():
+    """the C-ABI launchers are reachable as ``torch.library`` custom ops (``torch.ops.fbanet.*``); shapes propagate under
+    FakeTensorMode; a CPU tensor finds no kernel (there is no CPU fallback)."""
+    import pytest
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    import fbanet_b200.torch_ops as T
+
+    for n in T.OPS:
+        assert hasattr(torch.ops.fbanet, n), n
+    with FakeTensorMode():
+        b = torch.empty(2, 14, 3, 40, 40)
+        assert torch.ops.fbanet.warp(b, torch.empty(2, 14, 3, 3, dtype=torch.float64)).shape == b.shape
+        assert torch.ops.fbanet.forward(b, 0).shape == (2, 3, 160, 160)
+        x = torch.empty(2, 40, 40, 64, dtype=torch.bfloat16)
+        assert torch.ops.fbanet.conv3x3(x, torch.empty(128, 576, dtype=torch.bfloat16), None, None, 0).shape == (2, 40, 40, 128)
+        assert torch.ops.fbanet.linear(x, torch.empty(192, 64, dtype=torch.bfloat16), None, None, 0).shape == (2, 40, 40, 192)
+        assert torch.ops.fbanet.layernorm(x, torch.empty(64), torch.empty(64), 1e-5).shape == x.shape
+        assert torch.ops.fbanet.window_attention(torch.empty(2, 40, 40, 192, dtype=torch.bfloat16), torch.empty(361, 4), 4, 10, 5, 0.25).shape == x.shape
+        f = torch.empty(2, 14, 40, 40, 64, dtype=torch.bfloat16)
+        assert torch.ops.fbanet.faf_gate_fuse(f, torch.empty(9, 64), torch.empty(64, 896, dtype=torch.bfloat16), torch.empty(64),
+                                              torch.empty(1)).shape == (2, 40, 40, 64)
+    with pytest.raises(NotImplementedError):
+        torch.ops.fbanet.layernorm(torch.zeros(4, 8), torch.ones(8), torch.zeros(8), 1e-5)
