@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBANET_B200_LIB") or os.path.join(_HERE, "csrc", "libfbanet_b200.so")   # env override: A/B two builds in one process tree
-ABI_VERSION = 26
+ABI_VERSION = 27
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -72,6 +72,7 @@ class HeadConvParams(C.Structure):
     _fields_ = [
         ("src", C.c_void_p), ("dst", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p), ("dtype", C.c_int32),
         ("frames", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cout", C.c_int32),
+        ("frames_per_burst", C.c_int32), ("M", C.c_void_p),
     ]
 
 

@@ -93,20 +93,24 @@ __global__ void __launch_bounds__(256) warp_kernel(const fbanet_warp_params p) {
 // TB/s), the three homogeneous coordinates advance by one fp64 add per pixel, and every channel row is written as one float4.
 template <int CT>
 __global__ void __launch_bounds__(128) warp_planar4_kernel(const fbanet_warp_params p) {
-  const int W4 = p.W >> 2;
-  const int64_t total = (int64_t)p.frames * p.H * W4;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int x = (int)(idx % W4) * 4;
-  const int y = (int)((idx / W4) % p.H);
-  const int f = (int)(idx / ((int64_t)W4 * p.H));
-  {   // (a 2-D grid with the frame in blockIdx.y and 32-bit index math was measured SLOWER here: 0.245 vs 0.199 ms)
+  // 32-bit index math throughout (one frame spans < 2^31 elements, checked by the launcher): the first version spent 450 of its 820
+  // instructions per thread on 64-bit tap addresses and was issue bound (ncu: 63 % issue-active, 2.7 TB/s).
+  const unsigned W4 = (unsigned)p.W >> 2;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;   // < 2^31 (launcher): 32-bit divisions
+  if (idx >= (unsigned)p.frames * (unsigned)p.H * W4) return;
+  const unsigned rowi = idx / W4;
+  const int x = (int)(idx - rowi * W4) * 4;
+  const int f = (int)(rowi / (unsigned)p.H);
+  const int y = (int)(rowi - (unsigned)f * (unsigned)p.H);
   const float* s = p.src + (int64_t)f * p.s_frame;
-  float* d = p.dst + (int64_t)f * p.d_frame + (int64_t)y * p.d_y + x;
+  float* d = p.dst + (int64_t)f * p.d_frame;
+  asm volatile("" : "+l"(s), "+l"(d));   // keep the frame bases in registers: ptxas otherwise re-derives src + f * s_frame for every tap
+  const unsigned sy_ = (unsigned)p.s_y, sc_ = (unsigned)p.s_c, dc_ = (unsigned)p.d_c;
+  const unsigned dofs = (unsigned)y * (unsigned)p.d_y + (unsigned)x;
   if (f % p.frames_per_burst == 0) {  // base frame: identity (homography_alignment.py:168,179)
-    const float* s0 = s + (int64_t)y * p.s_y + x;
+    const unsigned sofs = (unsigned)y * sy_ + (unsigned)x;
 #pragma unroll
-    for (int c = 0; c < CT; ++c) *reinterpret_cast<float4*>(d + (int64_t)c * p.d_c) = __ldg(reinterpret_cast<const float4*>(s0 + (int64_t)c * p.s_c));
+    for (int c = 0; c < CT; ++c) *reinterpret_cast<float4*>(d + (dofs + c * dc_)) = __ldg(reinterpret_cast<const float4*>(s + (sofs + c * sc_)));
     return;
   }
   const double* M = p.M + (int64_t)f * 9;
@@ -115,49 +119,63 @@ __global__ void __launch_bounds__(128) warp_planar4_kernel(const fbanet_warp_par
   double u = fma(m0, X, fma(__ldg(M + 1), Y, __ldg(M + 2)));
   double v = fma(m3, X, fma(__ldg(M + 4), Y, __ldg(M + 5)));
   double w = fma(m6, X, fma(__ldg(M + 7), Y, __ldg(M + 8)));
+  // Out-of-image taps: index clamped to the edge pixel, weight set to zero -- every load is unconditional (16 * CT per thread with no
+  // predicate to carry: the predicated form spilled its 16 flags through P2R) and a zero weight adds +-0 exactly as the skipped
+  // term did, so results stay bit-identical to warp_kernel for finite images.
   float wt[4][4];
-  const float* r0[4];
-  bool ok[4][4];
+  unsigned o00[4], o01[4], o10[4], o11[4];
+  // the four reciprocals from ONE division (Montgomery's trick): 1 / (w0 w1 w2 w3), then products -- a few ulp each (< 1e-12 px)
+  double iwk[4];
+  {
+    const double w0 = w, w1 = w + m6, w2 = w1 + m6, w3 = w2 + m6;
+    const double p01 = w0 * w1, p23 = w2 * w3;
+    const double ip = 1.0 / (p01 * p23);
+    const double i01 = ip * p23, i23 = ip * p01;
+    iwk[0] = i01 * w1; iwk[1] = i01 * w0; iwk[2] = i23 * w3; iwk[3] = i23 * w2;
+  }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const double iw = 1.0 / w;          // relative error < 2^-51 per product: < 1e-12 px
+    const double iw = iwk[k];
     const double sx = u * iw, sy = v * iw;
-    u += m0; v += m3; w += m6;
-    const double fx = floor(sx), fy = floor(sy);
-    const float ax = (float)(sx - fx), ay = (float)(sy - fy);
-    const int x0 = (int)fmin(fmax(fx, -2.0), (double)p.W + 1.0);
-    const int y0 = (int)fmin(fmax(fy, -2.0), (double)p.H + 1.0);
-    const bool okx0 = x0 >= 0 && x0 < p.W, okx1 = x0 + 1 >= 0 && x0 + 1 < p.W;
-    const bool oky0 = y0 >= 0 && y0 < p.H, oky1 = y0 + 1 >= 0 && y0 + 1 < p.H;
-    ok[k][0] = oky0 && okx0; ok[k][1] = oky0 && okx1; ok[k][2] = oky1 && okx0; ok[k][3] = oky1 && okx1;
-    wt[k][0] = (1.f - ay) * (1.f - ax); wt[k][1] = (1.f - ay) * ax; wt[k][2] = ay * (1.f - ax); wt[k][3] = ay * ax;
-    r0[k] = s + (int64_t)y0 * p.s_y + x0;
+    u += m0; v += m3;
+    // floor in the integer domain: cvt.rmi saturates (and maps NaN to 0), so a wild homography cannot overflow; a saturated
+    // coordinate has no valid tap and its weights are zeroed
+    const int xf = __double2int_rd(sx), yf = __double2int_rd(sy);
+    const float ax = (float)(sx - (double)xf), ay = (float)(sy - (double)yf);
+    const bool okx0 = (unsigned)xf < (unsigned)p.W, okx1 = (unsigned)xf + 1u < (unsigned)p.W;   // unsigned: INT_MAX + 1 does not wrap into range
+    const bool oky0 = (unsigned)yf < (unsigned)p.H, oky1 = (unsigned)yf + 1u < (unsigned)p.H;
+    const int x0 = min(max(xf, -1), p.W), y0 = min(max(yf, -1), p.H);
+    const float wx0 = okx0 ? 1.f - ax : 0.f, wx1 = okx1 ? ax : 0.f, wy0 = oky0 ? 1.f - ay : 0.f, wy1 = oky1 ? ay : 0.f;
+    // (1 - ay)(1 - ax) etc. are the same products as before; a zeroed factor gives the exact zero weight
+    wt[k][0] = wy0 * wx0; wt[k][1] = wy0 * wx1; wt[k][2] = wy1 * wx0; wt[k][3] = wy1 * wx1;
+    const unsigned xa = (unsigned)min(max(x0, 0), p.W - 1), xb = (unsigned)min(max(x0 + 1, 0), p.W - 1);
+    const unsigned ya = (unsigned)min(max(y0, 0), p.H - 1) * sy_, yb = (unsigned)min(max(y0 + 1, 0), p.H - 1) * sy_;
+    o00[k] = ya + xa; o01[k] = ya + xb; o10[k] = yb + xa; o11[k] = yb + xb;
   }
   float t[CT][4][4];
 #pragma unroll
   for (int c = 0; c < CT; ++c)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float* q = r0[k] + (int64_t)c * p.s_c;
-      t[c][k][0] = ok[k][0] ? __ldg(q) : 0.f;
-      t[c][k][1] = ok[k][1] ? __ldg(q + 1) : 0.f;
-      t[c][k][2] = ok[k][2] ? __ldg(q + p.s_y) : 0.f;
-      t[c][k][3] = ok[k][3] ? __ldg(q + p.s_y + 1) : 0.f;
+      const unsigned oc = c * sc_;
+      t[c][k][0] = __ldg(s + (o00[k] + oc));
+      t[c][k][1] = __ldg(s + (o01[k] + oc));
+      t[c][k][2] = __ldg(s + (o10[k] + oc));
+      t[c][k][3] = __ldg(s + (o11[k] + oc));
     }
 #pragma unroll
   for (int c = 0; c < CT; ++c) {
     float o[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {   // same summation order as warp_kernel (bit-identical results)
+    for (int k = 0; k < 4; ++k) {   // same summation order as warp_kernel
       float acc = 0.f;
-      if (ok[k][0]) acc += wt[k][0] * t[c][k][0];
-      if (ok[k][1]) acc += wt[k][1] * t[c][k][1];
-      if (ok[k][2]) acc += wt[k][2] * t[c][k][2];
-      if (ok[k][3]) acc += wt[k][3] * t[c][k][3];
+      acc += wt[k][0] * t[c][k][0];
+      acc += wt[k][1] * t[c][k][1];
+      acc += wt[k][2] * t[c][k][2];
+      acc += wt[k][3] * t[c][k][3];
       o[k] = acc;
     }
-    *reinterpret_cast<float4*>(d + (int64_t)c * p.d_c) = make_float4(o[0], o[1], o[2], o[3]);
-  }
+    *reinterpret_cast<float4*>(d + (dofs + c * dc_)) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -1018,8 +1036,12 @@ extern "C" int fbanet_warp_sm100(const fbanet_warp_params* p, void* stream) {
   const int64_t total = (int64_t)p->frames * p->H * p->W;
   const bool planar4 = !p->coords && p->s_x == 1 && p->d_x == 1 && (p->W % 4) == 0 && (p->C == 3 || p->C == 4) && ((uintptr_t)p->src % 16) == 0 &&
                        ((uintptr_t)p->dst % 16) == 0 && (p->s_y % 4) == 0 && (p->d_y % 4) == 0 && (p->s_c % 4) == 0 && (p->d_c % 4) == 0 &&
-                       (p->s_frame % 4) == 0 && (p->d_frame % 4) == 0;
+                       (p->s_frame % 4) == 0 && (p->d_frame % 4) == 0 && (int64_t)p->C * p->s_c < ((int64_t)1 << 31) &&
+                       (int64_t)p->H * p->s_y < ((int64_t)1 << 31) && (int64_t)p->C * p->d_c < ((int64_t)1 << 31) && (int64_t)p->H * p->d_y < ((int64_t)1 << 31) &&
+                       total / 4 < ((int64_t)1 << 31) - 128;
   static const char* p4env = getenv("FBANET_WARP_PLANAR4");   // experiment switch: 0 = one pixel per thread everywhere
+  // (one warp per destination row with the lanes on consecutive pixels was tried against the four-pixels-per-thread form: 0.334 vs
+  // 0.203 ms -- the kernel is bound by instruction issue, not by L1 wavefronts; profiles/r2_ncu_warp.txt)
   if (planar4 && !(p4env && p4env[0] == '0')) {
     const int b4 = ceil_div(total / 4, 128);
     if (p->C == 3) warp_planar4_kernel<3><<<b4, 128, 0, (cudaStream_t)stream>>>(*p);
@@ -1059,11 +1081,12 @@ static int launch_head(const fbanet_head_conv_params* p, cudaStream_t s) {
 extern "C" int fbanet_head_conv_sm100(const fbanet_head_conv_params* p, void* stream) {
   if (!p || !p->src || !p->dst || !p->weight || !p->bias || p->frames <= 0 || p->Cout != 64) return FBANET_E_BADSHAPE;
   if ((uintptr_t)p->dst % 16) return FBANET_E_ALIGN;
-  if (p->dtype == FBANET_F32) return launch_head<float>(p, (cudaStream_t)stream);
+  if (p->M && (p->frames_per_burst <= 0 || ((uintptr_t)p->M % 8))) return FBANET_E_BADSHAPE;
+  if (p->dtype == FBANET_F32) return p->M ? FBANET_E_UNSUPPORTED : launch_head<float>(p, (cudaStream_t)stream);
   if (p->dtype == FBANET_BF16) {
     static const char* no_tc = getenv("FBANET_HEAD_TC");   // experiment switch: 0 = CUDA-core head conv
     if (!(no_tc && no_tc[0] == '0') && head_conv_tc_supported(p)) return head_conv_tc_launch(p, (cudaStream_t)stream);
-    return launch_head<bf16>(p, (cudaStream_t)stream);
+    return p->M ? FBANET_E_UNSUPPORTED : launch_head<bf16>(p, (cudaStream_t)stream);   // the fused warp lives in the tensor-core kernel only
   }
   return FBANET_E_DTYPE;
 }
@@ -1221,11 +1244,91 @@ extern "C" int fbanet_tile_merge_banded_sm100(const fbanet_tile_band_params* p, 
   return check_launch();
 }
 
+namespace fbanet {
+// Planar layouts (x stride 1 on both sides, W % 4 == 0, 16-byte aligned rows): one thread = 4 consecutive destination pixels -- two
+// 16-byte flow loads, 16 * CT unconditional taps in flight, one float4 store per channel row; 32-bit element offsets from frame
+// bases pinned in registers (the one-pixel kernel is latency bound at 3.2 TB/s).  Same arithmetic per pixel as flow_warp_kernel.
+template <int CT>
+__global__ void __launch_bounds__(128) flow_warp_planar4_kernel(const fbanet_flow_warp_params p) {
+  const int W4 = p.W >> 2;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)p.frames * p.H * W4) return;
+  const int x = (int)(idx % W4) * 4;
+  const int y = (int)((idx / W4) % p.H);
+  const int f = (int)(idx / ((int64_t)W4 * p.H));
+  const float* s = p.src + (int64_t)f * p.s_frame;
+  float* d = p.dst + (int64_t)f * p.d_frame;
+  asm volatile("" : "+l"(s), "+l"(d));
+  const unsigned sy_ = (unsigned)p.s_y, sc_ = (unsigned)p.s_c, dc_ = (unsigned)p.d_c;
+  const unsigned dofs = (unsigned)y * (unsigned)p.d_y + (unsigned)x;
+  int64_t ff = f;
+  if (p.frames_per_burst > 0) {
+    const int b = f / p.frames_per_burst, t = f - b * p.frames_per_burst;
+    if (t == 0) {   // base frame: not registered
+      const unsigned sofs = (unsigned)y * sy_ + (unsigned)x;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) *reinterpret_cast<float4*>(d + (dofs + c * dc_)) = __ldg(reinterpret_cast<const float4*>(s + (sofs + c * sc_)));
+      return;
+    }
+    ff = (int64_t)b * (p.frames_per_burst - 1) + (t - 1);
+  }
+  const float4* fp = reinterpret_cast<const float4*>(p.flow + ((ff * p.H + y) * p.W + x) * 2);
+  const float4 fa = __ldg(fp), fb = __ldg(fp + 1);
+  const float fdy[4] = {fa.x, fa.z, fb.x, fb.z}, fdx[4] = {fa.y, fa.w, fb.y, fb.w};   // (dy, dx) per pixel
+  float w4[4][4];
+  unsigned o00[4], o01[4], o10[4], o11[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float cy = __fsub_rn((float)y, fdy[k]), cx = __fsub_rn((float)(x + k), fdx[k]);   // grid - flow, one fp32 rounding
+    const float fy = floorf(cy), fx = floorf(cx);
+    const float uy = cy - fy, ux = cx - fx, ly = 1.f - uy, lx = 1.f - ux;
+    const int y0i = (int)fminf(fmaxf(fy, -1.f), (float)p.H), x0i = (int)fminf(fmaxf(fx, -1.f), (float)p.W);
+    const unsigned y0 = (unsigned)min(max(y0i, 0), p.H - 1) * sy_, y1 = (unsigned)min(max(y0i + 1, 0), p.H - 1) * sy_;
+    const unsigned x0 = (unsigned)min(max(x0i, 0), p.W - 1), x1 = (unsigned)min(max(x0i + 1, 0), p.W - 1);
+    o00[k] = y0 + x0; o01[k] = y0 + x1; o10[k] = y1 + x0; o11[k] = y1 + x1;
+    w4[k][0] = ly * lx; w4[k][1] = ly * ux; w4[k][2] = uy * lx; w4[k][3] = uy * ux;
+  }
+  float t[CT][4][4];
+#pragma unroll
+  for (int c = 0; c < CT; ++c)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned oc = c * sc_;
+      t[c][k][0] = __ldg(s + (o00[k] + oc));
+      t[c][k][1] = __ldg(s + (o01[k] + oc));
+      t[c][k][2] = __ldg(s + (o10[k] + oc));
+      t[c][k][3] = __ldg(s + (o11[k] + oc));
+    }
+#pragma unroll
+  for (int c = 0; c < CT; ++c) {
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)   // jax sums the four (index, weight) products in the order (lo,lo), (lo,hi), (hi,lo), (hi,hi)
+      o[k] = ((t[c][k][0] * w4[k][0] + t[c][k][1] * w4[k][1]) + t[c][k][2] * w4[k][2]) + t[c][k][3] * w4[k][3];
+    *reinterpret_cast<float4*>(d + (dofs + c * dc_)) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+}  // namespace fbanet
+
 extern "C" int fbanet_flow_warp_sm100(const fbanet_flow_warp_params* p, void* stream) {
   if (!p || !p->src || !p->dst || !p->flow || p->frames <= 0 || p->frames_per_burst < 0 || p->frames_per_burst == 1 || p->H <= 0 ||
       p->W <= 0 || p->C <= 0 || ((uintptr_t)p->flow % 8))
     return FBANET_E_BADSHAPE;
   if (p->frames_per_burst > 0 && p->frames % p->frames_per_burst) return FBANET_E_BADSHAPE;
+  // experiment switch, off by default: four pixels per thread measured SLOWER than one (0.246 vs 0.225 ms, 64 x 14 x 3 x 160^2:
+  // profiles/r2_w_warp_flow_ab.log) -- the flow field adds 8 bytes per pixel of streaming reads and the kernel wants more threads
+  // in flight, not more work per thread
+  const bool planar4 = p->s_x == 1 && p->d_x == 1 && (p->W % 4) == 0 && (p->C == 3 || p->C == 4) && ((uintptr_t)p->src % 16) == 0 &&
+                       ((uintptr_t)p->dst % 16) == 0 && ((uintptr_t)p->flow % 16) == 0 && (p->s_y % 4) == 0 && (p->d_y % 4) == 0 && (p->s_c % 4) == 0 &&
+                       (p->d_c % 4) == 0 && (p->s_frame % 4) == 0 && (p->d_frame % 4) == 0 && (int64_t)p->C * p->s_c < ((int64_t)1 << 31) &&
+                       (int64_t)p->H * p->s_y < ((int64_t)1 << 31) && (int64_t)p->C * p->d_c < ((int64_t)1 << 31) && (int64_t)p->H * p->d_y < ((int64_t)1 << 31);
+  static const char* f4env = getenv("FBANET_FLOW_PLANAR4");
+  if (planar4 && f4env && f4env[0] == '1') {
+    const int b4 = ceil_div((int64_t)p->frames * p->H * (p->W / 4), 128);
+    if (p->C == 3) flow_warp_planar4_kernel<3><<<b4, 128, 0, (cudaStream_t)stream>>>(*p);
+    else flow_warp_planar4_kernel<4><<<b4, 128, 0, (cudaStream_t)stream>>>(*p);
+    return check_launch();
+  }
   if (p->frames > 65535 || (int64_t)p->H * p->W > (int64_t)1 << 30) return FBANET_E_BADSHAPE;
   const dim3 blocks((unsigned)ceil_div((int64_t)p->H * p->W, 256), (unsigned)p->frames);
   if (p->C == 3) flow_warp_kernel<3><<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);

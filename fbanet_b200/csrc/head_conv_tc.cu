@@ -7,6 +7,12 @@
 // for the lo half); two producer groups take alternate tiles -- one elected thread issues M=128, N=64 MMAs into double-buffered TMEM accumulators, and eight epilogue
 // warps add the bias and stream 32-row x 128-byte sub-tiles out with per-warp TMA stores.  Weights are converted to bf16
 // and laid out as the B operand in shared memory once per CTA.
+//
+// Producers, second form: a group first stages the tile's 10 x 18 HALO of samples in shared memory (one or two pixels per
+// thread, the next tile's loads already in flight while this tile's im2col rows are built), then every thread gathers its 9 * C_in
+// neighbours from there: 180 * C_in global loads per tile instead of 128 * 9 * C_in.  With `M` given, a halo sample is the
+// homography-warped burst pixel (K1 fused: bilinear taps at the fp64 dst->src coordinates, same arithmetic as warp_kernel, base
+// frame copied), so the warped burst of homography_alignment.py:46-55 never exists in HBM.
 #include <string.h>
 
 #include "common.cuh"
@@ -25,11 +31,15 @@ struct HeadTcParams {
   const float* src;      // [frames][C][H][W]
   const float* weight;   // [9C][64] fp32
   const float* bias;     // [64]
-  int frames, H, W;
+  const double* M;       // [frames][3][3] dst->src homographies (WARP instantiation)
+  int frames, frames_per_burst, H, W;
   int tiles_x, tiles_y, m_tiles;
 };
 
-template <int CIN>
+constexpr int HT_HW = HT_TW + 2, HT_HH = HT_TH + 2, HT_HPX = HT_HW * HT_HH;   // halo tile 10 x 18 = 180 samples per channel
+constexpr int HT_HROW = 12;                                                   // floats per halo row in shared memory
+
+template <int CIN, bool WARP>
 __global__ void __launch_bounds__(HT_THREADS, 1) head_conv_tc_kernel(const __grid_constant__ HeadTcParams p) {
   constexpr int K1 = 9 * CIN;                 // real taps
   constexpr int K1P = (K1 + 1) & ~1;          // padded to a whole bf16 pair
@@ -47,6 +57,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_conv_tc_kernel(const __gri
   uint8_t* smem_a = smem;                                    // HT_A_SLOTS x NK64 x [128 rows][128 B]
   uint8_t* smem_b = smem_a + HT_A_SLOTS * A_SLOT;            // NK64 x [64 rows][128 B]
   uint8_t* smem_stage = smem_b + NK64 * 8192;                // 8 warps x 2 x 4 KB
+  float* smem_halo = reinterpret_cast<float*>(smem_stage + 8 * 8192);   // 2 producer groups x [CIN][18][12] fp32
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&p.omap);
@@ -106,25 +117,94 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_conv_tc_kernel(const __gri
     const int grp = (warp - 4) >> 2;
     const int r = (threadIdx.x - 128) & 127;
     const int ly = r / HT_TW, lx = r % HT_TW;
-    const int64_t hw = (int64_t)p.H * p.W;
+    const int hw = p.H * p.W;
     const uint32_t row_off = (uint32_t)r * 128u;
     const int r7 = r & 7;
-    int it = 0;
-    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++it) {
-      if ((it & 1) != grp) continue;
-      const int slot = it & (HT_A_SLOTS - 1);
+    float* halo = smem_halo + grp * (CIN * HT_HH * HT_HROW);
+    const uint32_t halo_u = smem_u32(halo);
+    constexpr int NT = WARP ? 4 : 1;          // taps per halo sample
+    // this thread's halo samples: h = r and r + 128 (< 180)
+    float tp[2][CIN][NT], wt[2][4];
+    bool okt[2][4];
+    auto issue = [&](int mt) {                 // loads of tile mt's halo samples (not waited for)
       const int f = mt / tiles_per_img, rr = mt % tiles_per_img;
-      const int y = (rr / p.tiles_x) * HT_TH + ly, x = (rr % p.tiles_x) * HT_TW + lx;
-      const float* sp = p.src + (int64_t)f * CIN * hw + (int64_t)y * p.W + x;
+      const int ty0 = (rr / p.tiles_x) * HT_TH - 1, tx0 = (rr % p.tiles_x) * HT_TW - 1;
+      const float* sf = p.src + (int64_t)f * CIN * hw;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int h = r + 128 * e;
+        const int hy = h / HT_HW, hx = h - hy * HT_HW;
+        const int gy = ty0 + hy, gx = tx0 + hx;
+        const bool in = h < HT_HPX && (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W;
+        if constexpr (!WARP) {
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) tp[e][c][0] = in ? __ldg(sf + c * hw + gy * p.W + gx) : 0.f;
+        } else {
+          bool ident = (f % p.frames_per_burst) == 0;   // base frame: identity (homography_alignment.py:168,179)
+          double sx = gx, sy = gy;
+          if (in && !ident) {                  // same arithmetic as warp_kernel (bit-identical samples)
+            const double* M = p.M + (int64_t)f * 9;
+            const double X = gx, Y = gy;
+            const double u = fma(__ldg(M + 0), X, fma(__ldg(M + 1), Y, __ldg(M + 2)));
+            const double v = fma(__ldg(M + 3), X, fma(__ldg(M + 4), Y, __ldg(M + 5)));
+            const double w = fma(__ldg(M + 6), X, fma(__ldg(M + 7), Y, __ldg(M + 8)));
+            const double iw = 1.0 / w;
+            sx = u * iw; sy = v * iw;
+          }
+          const double fx = floor(sx), fy = floor(sy);
+          const float ax = (float)(sx - fx), ay = (float)(sy - fy);
+          const int x0 = (int)fmin(fmax(fx, -2.0), (double)p.W + 1.0);
+          const int y0 = (int)fmin(fmax(fy, -2.0), (double)p.H + 1.0);
+          const bool okx0 = x0 >= 0 && x0 < p.W, okx1 = x0 + 1 >= 0 && x0 + 1 < p.W;
+          const bool oky0 = y0 >= 0 && y0 < p.H, oky1 = y0 + 1 >= 0 && y0 + 1 < p.H;
+          okt[e][0] = in && oky0 && okx0; okt[e][1] = in && oky0 && okx1; okt[e][2] = in && oky1 && okx0; okt[e][3] = in && oky1 && okx1;
+          wt[e][0] = (1.f - ay) * (1.f - ax); wt[e][1] = (1.f - ay) * ax; wt[e][2] = ay * (1.f - ax); wt[e][3] = ay * ax;
+          const float* q = sf + y0 * p.W + x0;
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) {
+            tp[e][c][0] = okt[e][0] ? __ldg(q + c * hw) : 0.f;
+            tp[e][c][1] = okt[e][1] ? __ldg(q + c * hw + 1) : 0.f;
+            tp[e][c][2] = okt[e][2] ? __ldg(q + c * hw + p.W) : 0.f;
+            tp[e][c][3] = okt[e][3] ? __ldg(q + c * hw + p.W + 1) : 0.f;
+          }
+        }
+      }
+    };
+    int it = grp, mt = blockIdx.x + grp * (int)gridDim.x;   // this group's tiles: every second one of the CTA
+    if (mt < p.m_tiles) issue(mt);
+    for (; mt < p.m_tiles; mt += 2 * (int)gridDim.x, it += 2) {
+      const int slot = it & (HT_A_SLOTS - 1);
+      // ---- halo samples -> shared memory ----
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int h = r + 128 * e;
+        if (h < HT_HPX) {
+          const int hy = h / HT_HW, hx = h - hy * HT_HW;
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) {
+            float val;
+            if constexpr (!WARP) val = tp[e][c][0];
+            else {   // same summation order as warp_kernel
+              float acc = 0.f;
+              if (okt[e][0]) acc += wt[e][0] * tp[e][c][0];
+              if (okt[e][1]) acc += wt[e][1] * tp[e][c][1];
+              if (okt[e][2]) acc += wt[e][2] * tp[e][c][2];
+              if (okt[e][3]) acc += wt[e][3] * tp[e][c][3];
+              val = acc;
+            }
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(halo_u + (uint32_t)(((c * HT_HH + hy) * HT_HROW + hx) * 4)), "f"(val));
+          }
+        }
+      }
+      named_bar_sync(1 + grp, 128);                          // the group's halo tile is complete
+      if (mt + 2 * (int)gridDim.x < p.m_tiles) issue(mt + 2 * (int)gridDim.x);   // next tile's loads fly during the im2col below
       float v[K1P];
       if (K1P > K1) v[K1P - 1] = 0.f;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int dy = t / 3 - 1, dx = t % 3 - 1;
-        const bool ok = (unsigned)(y + dy) < (unsigned)p.H && (unsigned)(x + dx) < (unsigned)p.W;
+      for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int c = 0; c < CIN; ++c) v[t * CIN + c] = ok ? __ldg(sp + c * hw + dy * p.W + dx) : 0.f;
-      }
+        for (int c = 0; c < CIN; ++c)
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[t * CIN + c]) : "r"(halo_u + (uint32_t)(((c * HT_HH + ly + t / 3) * HT_HROW + lx + t % 3) * 4)));
       // sample = hi + lo (bf16 each): columns [0,K1P) hi, [K1P, 2 K1P) lo, zero padding to a whole 16-byte chunk
       uint32_t e[NCH * 4];
 #pragma unroll
@@ -146,6 +226,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_conv_tc_kernel(const __gri
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[slot]);
+      named_bar_sync(1 + grp, 128);                          // everyone has read the halo tile: it may be overwritten
     }
   } else if (warp >= 12) {
     // ================= epilogue: warps 12..15 drain accumulator 0 (even tiles), 16..19 accumulator 1 (odd tiles) =================
@@ -202,7 +283,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_conv_tc_kernel(const __gri
   }
 }
 
-template <int CIN>
+template <int CIN, bool WARP>
 int launch_head_tc(const fbanet_head_conv_params* p, cudaStream_t stream) {
   EncodeTiledFn encode = get_encode();
   if (!encode) return FBANET_E_UNSUPPORTED;
@@ -215,16 +296,16 @@ int launch_head_tc(const fbanet_head_conv_params* p, cudaStream_t stream) {
   if (encode(&hp.omap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, p->dst, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return FBANET_E_BADSHAPE;
-  hp.src = p->src; hp.weight = p->weight; hp.bias = p->bias;
-  hp.frames = p->frames; hp.H = p->H; hp.W = p->W;
+  hp.src = p->src; hp.weight = p->weight; hp.bias = p->bias; hp.M = p->M;
+  hp.frames = p->frames; hp.frames_per_burst = p->frames_per_burst > 0 ? p->frames_per_burst : 1; hp.H = p->H; hp.W = p->W;
   hp.tiles_x = (p->W + HT_TW - 1) / HT_TW;
   hp.tiles_y = (p->H + HT_TH - 1) / HT_TH;
   hp.m_tiles = p->frames * hp.tiles_x * hp.tiles_y;
   constexpr int NK64 = (2 * ((9 * CIN + 1) & ~1) + 63) / 64;
-  constexpr size_t smem = (size_t)HT_A_SLOTS * NK64 * 16384 + NK64 * 8192 + 8 * 8192 + 1024;
+  constexpr size_t smem = (size_t)HT_A_SLOTS * NK64 * 16384 + NK64 * 8192 + 8 * 8192 + 2 * CIN * HT_HH * HT_HROW * 4 + 1024;
   static bool opted = false;
   if (!opted) {
-    cudaError_t e = cudaFuncSetAttribute(head_conv_tc_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(head_conv_tc_kernel<CIN, WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cudaGetLastError(); set_last_error(e); return FBANET_E_LAUNCH; }
     opted = true;
   }
@@ -232,7 +313,7 @@ int launch_head_tc(const fbanet_head_conv_params* p, cudaStream_t stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = hp.m_tiles < sms ? hp.m_tiles : sms;
-  head_conv_tc_kernel<CIN><<<grid, HT_THREADS, smem, stream>>>(hp);
+  head_conv_tc_kernel<CIN, WARP><<<grid, HT_THREADS, smem, stream>>>(hp);
   return check_launch();
 }
 
@@ -240,12 +321,13 @@ int launch_head_tc(const fbanet_head_conv_params* p, cudaStream_t stream) {
 
 // bf16 destination, 64 output channels, 3 or 4 input channels, 16-byte aligned dst
 int head_conv_tc_supported(const fbanet_head_conv_params* p) {
-  return p->dtype == FBANET_BF16 && p->Cout == 64 && (p->C == 3 || p->C == 4) && ((uintptr_t)p->dst % 16) == 0 && get_encode() != nullptr;
+  return p->dtype == FBANET_BF16 && p->Cout == 64 && (p->C == 3 || p->C == 4) && ((uintptr_t)p->dst % 16) == 0 && get_encode() != nullptr &&
+         (int64_t)p->C * p->H * p->W < ((int64_t)1 << 31) && (!p->M || (p->frames_per_burst > 0 && ((uintptr_t)p->M % 8) == 0));
 }
 
 int head_conv_tc_launch(const fbanet_head_conv_params* p, cudaStream_t stream) {
-  if (p->C == 3) return launch_head_tc<3>(p, stream);
-  if (p->C == 4) return launch_head_tc<4>(p, stream);
+  if (p->C == 3) return p->M ? launch_head_tc<3, true>(p, stream) : launch_head_tc<3, false>(p, stream);
+  if (p->C == 4) return p->M ? launch_head_tc<4, true>(p, stream) : launch_head_tc<4, false>(p, stream);
   return FBANET_E_UNSUPPORTED;
 }
 

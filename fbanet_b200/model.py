@@ -196,10 +196,15 @@ class BaseModel(nn.Module):
         self.fuse_faf = os.environ.get("FBANET_FUSE_FAF", "1") == "1"
         # dim <= 128 layers: the whole LeFF MLP in one kernel (ops.leff_mlp); FBANET_FUSE_MLP=0 keeps fc1 + leff_fc2
         self.fuse_mlp = os.environ.get("FBANET_FUSE_MLP", "1") == "1"
+        # forward(x, homographies=M): K1 fused into the head conv's sampling (ops.head_conv(M=)); FBANET_FUSE_WARP=0 = warp kernel first
+        self.fuse_warp = os.environ.get("FBANET_FUSE_WARP", "1") == "1"
         # bf16 path, optional: LayerNorm folded into the qkv / fc1 GEMMs (row statistics only; ops.fold_layernorm).  -1.3 ms per
         # batch-64 step and a lower mean PSNR delta over seeds (0.0043 vs 0.0049 dB), but one of three seeds lands at 0.0105 dB,
         # 5 % over the 0.01 dB parity tolerance, so it stays off by default; FBANET_FOLD_LN=1 (or the attribute) turns it on.
         self.fold_ln = os.environ.get("FBANET_FOLD_LN", "0") == "1"
+        # bf16 weights rounded so that every GEMM row keeps its sum (ops.round_rowsum): removes the per-channel bias that plain
+        # rounding leaves on inputs with a common mode; FBANET_ROWSUM_ROUND=0 = plain round-to-nearest
+        self.rowsum_round = os.environ.get("FBANET_ROWSUM_ROUND", "1") == "1"
         # final conv through the tap-stacked kernel mode with hi + lo summed in its epilogue (FBANET_FOLD_FINAL=0: plain implicit GEMM)
         self.fold_final = os.environ.get("FBANET_FOLD_FINAL", "1") == "1"
         self.host_chunk = 32       # bursts per pipelined chunk of infer_host (int, or an explicit schedule of chunk sizes)
@@ -256,11 +261,14 @@ class BaseModel(nn.Module):
         tc = self._use_tc()
         cin_pad = 4 if T == torch.float32 else 8  # head input channels padded to a 16-byte pixel
 
+        def rnd(w):  # fp32 [rows, K] -> compute dtype
+            return ops.round_rowsum(w, T) if self.rowsum_round else w.to(T).contiguous()
+
         def conv_w(w, pad_cin=None):  # [Co,Ci,kh,kw] -> [Co, kh*kw*Ci]
             w = w.detach().float().permute(0, 2, 3, 1)
             if pad_cin is not None and pad_cin > w.shape[-1]:
                 w = torch.nn.functional.pad(w, (0, pad_cin - w.shape[-1]))
-            return w.reshape(w.shape[0], -1).to(T).contiguous()
+            return rnd(w.reshape(w.shape[0], -1))
 
         def f32(t):
             return t.detach().float().contiguous()
@@ -271,11 +279,11 @@ class BaseModel(nn.Module):
 
         def put_convT(name, m):  # [Ci,Co,2,2] -> rows (i,j,co), cols ci
             w = m.weight.detach().float().permute(2, 3, 1, 0)
-            P[name + ".w"] = w.reshape(-1, w.shape[-1]).to(T).contiguous()
+            P[name + ".w"] = rnd(w.reshape(-1, w.shape[-1]))
             P[name + ".b"] = f32(m.bias).repeat(4)
 
         def put_lin(name, m):
-            P[name + ".w"] = m.weight.detach().to(T).contiguous()
+            P[name + ".w"] = rnd(m.weight.detach().float())
             P[name + ".b"] = f32(m.bias)
 
         if tc and self.embed_dim == 64 and self.in_channels in (3, 4):
@@ -284,7 +292,7 @@ class BaseModel(nn.Module):
             P["head.b"] = f32(self.head.bias)
         elif tc:  # head conv as a K=64 1x1 GEMM over the im2col'd burst (ops.to_nhwc(im2col3x3=True))
             w = self.head.weight.detach().float().permute(0, 2, 3, 1).reshape(self.embed_dim, -1)
-            P["head.w"] = torch.nn.functional.pad(w, (0, 64 - w.shape[1])).to(T).contiguous()
+            P["head.w"] = rnd(torch.nn.functional.pad(w, (0, 64 - w.shape[1])))
             P["head.b"] = f32(self.head.bias)
         else:
             put_conv("head", self.head, cin_pad)
@@ -332,7 +340,7 @@ class BaseModel(nn.Module):
                             ly.mlp.linear1[0].weight, ly.mlp.linear1[0].bias, ly.norm2.weight, ly.norm2.bias, T)
                         P[k + ".ln_folded"] = P[k + ".qkv.b"]   # marker: this layer's LayerNorms live in its GEMMs
                     else:
-                        P[k + ".qkv.w"], P[k + ".qkv.b"] = wqkv.to(T).contiguous(), bqkv
+                        P[k + ".qkv.w"], P[k + ".qkv.b"] = rnd(wqkv), bqkv
                         put_lin(k + ".fc1", ly.mlp.linear1[0])
                     P[k + ".rpb"] = f32(a.relative_position_bias_table)
                     if tc:  # dense per-head bias in log2 units for the tensor-core attention kernel
@@ -346,7 +354,7 @@ class BaseModel(nn.Module):
                     P[k + ".dw.b"] = f32(dw.bias)
                     if tc and ly.dim <= 128 and not self.fold_ln:
                         # one-kernel LeFF MLP (ops.leff_mlp): its contract wants HALF of linear1 / dwconv (exact: a power of two)
-                        P[k + ".fc1.wh"] = (0.5 * ly.mlp.linear1[0].weight.detach().float()).to(T).contiguous()
+                        P[k + ".fc1.wh"] = rnd(0.5 * ly.mlp.linear1[0].weight.detach().float())
                         P[k + ".fc1.bh"] = (0.5 * f32(ly.mlp.linear1[0].bias)).contiguous()
                         P[k + ".dw.wh"] = (0.5 * P[k + ".dw.w"]).contiguous()
                         P[k + ".dw.bh"] = (0.5 * P[k + ".dw.b"]).contiguous()
@@ -540,8 +548,12 @@ class BaseModel(nn.Module):
 
     # -- forward -----------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward_stages(self, x: torch.Tensor, stages: Optional[dict] = None) -> torch.Tensor:
-        """The forward; when ``stages`` is a dict every named intermediate (channels-last) is recorded."""
+    def forward_stages(self, x: torch.Tensor, stages: Optional[dict] = None, homographies: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The forward; when ``stages`` is a dict every named intermediate (channels-last) is recorded.
+
+        ``homographies`` ``[B,T,3,3]`` (dst->src, frame 0 ignored): the burst is unregistered and every frame is warped onto the base
+        frame first (``homography_alignment.py:46-55``).  On the tensor-core path the warp is fused into the head conv's sampling
+        (``ops.head_conv(M=)``): the warped burst never exists in HBM; elsewhere it is :func:`ops.warp_burst` + the plain forward."""
         L.load()  # fail loudly if the CUDA library is absent
         if x.dim() != 5 or tuple(x.shape[1:]) != (self.num_frames, self.in_channels, self.img_size, self.img_size):
             raise AssertionError(  # mirrors assert_shape at models/fba_net.py:244
@@ -557,8 +569,12 @@ class BaseModel(nn.Module):
         B, Fr, Cin, S, _ = x.shape
         E, T = self.embed_dim, self.compute_dtype
         cin_pad = 4 if T == torch.float32 else 8
+        if homographies is not None and not ("head.wkc" in P and T == torch.bfloat16 and self.fuse_warp):
+            x = ops.warp_burst(x, homographies)
+            homographies = None
         if "head.wkc" in P:
-            f = ops.head_conv(x.view(B * Fr, Cin, S, S), P["head.wkc"], P["head.b"], T)  # :255
+            f = ops.head_conv(x.view(B * Fr, Cin, S, S), P["head.wkc"], P["head.b"], T,   # :255
+                              M=None if homographies is None else homographies.reshape(B * Fr, 3, 3), frames_per_burst=Fr)
         elif self._use_tc():
             xn = ops.to_nhwc(x.view(B * Fr, Cin, S, S), 64, T, im2col3x3=True)
             f = ops.conv_gemm([xn], P["head.w"], self._new(B * Fr, S, S, E), bias=P["head.b"], impl=self.impl, alg_cin=9 * Cin)  # :255
@@ -601,8 +617,8 @@ class BaseModel(nn.Module):
             st.update({"output_proj": y1, "output_proj_2": y2, "tail.ps1": t1, "tail.ps2": t2, "out": out})
         return out
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return self.forward_stages(x, None)
+    def forward(self, x: torch.Tensor, homographies: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.forward_stages(x, None, homographies)
 
     @torch.no_grad()
     def forward_unaligned(self, x: torch.Tensor, max_iters: int = 100, eps: float = 1e-10, return_alignment: bool = False):
@@ -615,7 +631,7 @@ class BaseModel(nn.Module):
         M, rho, iters = ops.ecc_homography_burst(x, max_iters=max_iters, eps=eps)
         eye = torch.eye(3, dtype=M.dtype, device=M.device)
         M = torch.where((iters < 0)[..., None, None], eye, M)
-        y = self.forward(ops.warp_burst(x, M))
+        y = self.forward(x, homographies=M)
         return (y, (M, rho, iters)) if return_alignment else y
 
     @torch.no_grad()

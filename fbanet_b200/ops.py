@@ -234,9 +234,14 @@ def to_nhwc(x: torch.Tensor, cp: int, dtype: torch.dtype, im2col3x3: bool = Fals
     return out
 
 
-def head_conv(x: torch.Tensor, weight_kc: torch.Tensor, bias: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+def head_conv(x: torch.Tensor, weight_kc: torch.Tensor, bias: torch.Tensor, dtype: torch.dtype, M: Optional[torch.Tensor] = None,
+              frames_per_burst: int = 0) -> torch.Tensor:
     """3x3 pad-1 conv from the planar fp32 burst ``[frames,C,H,W]`` to channels-last ``[frames,H,W,64]``;
-    ``weight_kc`` is fp32 ``[9*C, 64]`` (k = (ky*3+kx)*C + c)."""
+    ``weight_kc`` is fp32 ``[9*C, 64]`` (k = (ky*3+kx)*C + c).
+
+    ``M`` ``[frames,3,3]`` float64 dst->src homographies: K1 fused into K0 -- every sample the conv reads is the bilinearly warped burst
+    pixel (the arithmetic of :func:`warp_burst`, bit for bit; frames ``f % frames_per_burst == 0`` are base frames and are copied), so
+    the warped burst is never materialised.  Tensor-core (bf16, 64-channel) path only; elsewhere the burst is warped first."""
     assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
     Fr, Cc, H, W = x.shape
     cout = weight_kc.shape[1]
@@ -245,6 +250,20 @@ def head_conv(x: torch.Tensor, weight_kc: torch.Tensor, bias: torch.Tensor, dtyp
     p = L.HeadConvParams()
     p.src, p.dst, p.weight, p.bias, p.dtype = x.data_ptr(), out.data_ptr(), weight_kc.data_ptr(), bias.data_ptr(), _DT[dtype]
     p.frames, p.C, p.H, p.W, p.Cout = Fr, Cc, H, W, cout
+    if M is not None:
+        assert frames_per_burst > 0 and Fr % frames_per_burst == 0
+        M = M.to(device=x.device, dtype=torch.float64).contiguous()
+        assert M.shape == (Fr, 3, 3)
+        p.M, p.frames_per_burst = M.data_ptr(), frames_per_burst
+        try:
+            _call("fbanet_head_conv_sm100", p, tag="+warp", nbytes=x.numel() * 4 + out.numel() * out.element_size())
+        except RuntimeError as e:
+            if "impl unsupported" not in str(e):
+                raise
+            # no fused kernel for this dtype / width: warp, then convolve
+            xw = warp_burst(x.view(Fr // frames_per_burst, frames_per_burst, Cc, H, W), M.view(-1, frames_per_burst, 3, 3))
+            return head_conv(xw.view(Fr, Cc, H, W), weight_kc, bias, dtype)
+        return out
     _call("fbanet_head_conv_sm100", p, nbytes=x.numel() * 4 + out.numel() * out.element_size())
     return out
 
@@ -337,6 +356,29 @@ def fold_layernorm(w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: 
         wf.scatter_(1, idx, (wf.gather(1, idx).double() - r / idx.shape[1]).to(dtype))
     bias = (w64 @ be64 + b.detach().double()).float().contiguous()
     return wf.contiguous(), bias
+
+
+def round_rowsum(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Round the rows of a GEMM weight matrix ``[rows, K]`` to ``dtype`` so that every row keeps its SUM.
+
+    Plain round-to-nearest leaves each output channel with a row-sum error of order ``sqrt(K) * 2^-10 * |w|``, i.e. a fixed bias
+    proportional to the COMMON MODE of its inputs -- and most inputs here have one (GELU / ReLU / PReLU outputs are mostly positive,
+    attention outputs are averages).  That bias is the same at every pixel, so it is the part of the weight-rounding error that moves
+    the PSNR against a ground truth, the north-star's bf16 criterion (``tools/emulate_bf16.py``: the PSNR delta of the parity test is
+    entirely weight rounding; sum-preserving rows lower it on every seed, mean 0.0048 -> 0.0035 dB).  The residual of a row is pushed
+    into its 8 smallest-magnitude non-zero elements (about one typical ulp each; their own ulps are far finer), then what their
+    rounding leaves into the single smallest (the scheme :func:`fold_layernorm` uses for its zero row sums).  fp32: a plain cast."""
+    if dtype != torch.bfloat16:
+        return w.detach().to(dtype).contiguous()
+    w64 = w.detach().double()
+    wf = w64.to(dtype)
+    mag = wf.abs().float()
+    mag[mag == 0] = float("inf")          # zero columns (channel padding) multiply zero inputs: leave them alone
+    for t in (8, 1):
+        r = wf.double().sum(1, keepdim=True) - w64.sum(1, keepdim=True)
+        idx = mag.topk(min(t, wf.shape[1]), dim=1, largest=False).indices
+        wf.scatter_(1, idx, (wf.gather(1, idx).double() - r / idx.shape[1]).to(dtype))
+    return wf.contiguous()
 
 
 def expand_rel_pos_bias(bias_table: torch.Tensor, win: int) -> torch.Tensor:

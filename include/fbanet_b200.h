@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 26
+#define FBANET_ABI_VERSION 27
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -156,6 +156,12 @@ typedef struct fbanet_head_conv_params {
   const float* bias;
   int32_t dtype;          /* of dst */
   int32_t frames, C, H, W, Cout;
+  /* K1 fused into K0 (homography_alignment.py:46-55 -> models/fba_net.py:255), bf16 / 64-channel tensor-core path only: with `M`
+   * ([frames][3][3] float64 dst->src, 8-byte aligned) every input sample is the bilinearly warped burst pixel -- the arithmetic of
+   * fbanet_warp_sm100, bit for bit -- so the warped burst is never written; frame f with f % frames_per_burst == 0 is the base frame
+   * (copied).  NULL: plain head conv.  FBANET_E_UNSUPPORTED when given on a path that cannot fuse (caller warps first). */
+  int32_t frames_per_burst;
+  const double* M;
 } fbanet_head_conv_params;
 
 /* Final assembly (models/fba_net.py:317-320): out[n][c][Y][X] = sr(n,Y,X,c) + bilinear_x4(base)[n][c][Y][X], with

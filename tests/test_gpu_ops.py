@@ -791,3 +791,53 @@ def test_torch_library_custom_ops(cuda):
     m = m.to(cuda).eval()
     h = T.register_model(m)
     assert torch.equal(torch.ops.fbanet.forward(burst, h), m(burst))
+
+
+@pytest.mark.parametrize("cin,hw,bursts,T", [(3, (40, 40), 2, 4), (4, (37, 21), 1, 5), (3, (160, 160), 2, 14), (4, (80, 80), 3, 14)])
+def test_head_conv_with_fused_homography_warp(cuda, cin, hw, bursts, T):
+    """K1 fused into K0 (homography_alignment.py:46-55 -> models/fba_net.py:255): the head conv sampling the unregistered burst through
+    the homographies equals warp kernel + head conv BIT FOR BIT (same fp64 coordinates, same tap order), base frames copied,
+    strong perspective / rotation so taps leave the image on every side, ragged tiles; and the warp itself is pinned to the
+    float64 oracle (1e-5 px coordinates) by test_warp_matches_float64_oracle."""
+    from fbanet_b200 import ops
+    H, W = hw
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(bursts, T, cin, H, W, generator=g).to(cuda)
+    M = torch.eye(3, dtype=torch.float64).repeat(bursts, T, 1, 1)
+    M[:, 1:, :2, 2] = torch.rand(bursts, T - 1, 2, generator=g, dtype=torch.float64) * 12 - 6
+    M[:, 1:, :2, :2] += torch.rand(bursts, T - 1, 2, 2, generator=g, dtype=torch.float64) * 0.2 - 0.1
+    M[:, 1:, 2, :2] = torch.rand(bursts, T - 1, 2, generator=g, dtype=torch.float64) * 2e-4 - 1e-4
+    w, b = _r(torch.float32, 64, cin, 3, 3, seed=2, scale=0.2), _r(torch.float32, 64, seed=3)
+    wkc = w.permute(2, 3, 1, 0).reshape(9 * cin, 64).contiguous().to(cuda)
+    ref = ops.head_conv(ops.warp_burst(x, M).view(bursts * T, cin, H, W), wkc, b.to(cuda), torch.bfloat16)
+    launches = ops.LAUNCHES
+    got = ops.head_conv(x.view(bursts * T, cin, H, W), wkc, b.to(cuda), torch.bfloat16, M=M.view(-1, 3, 3), frames_per_burst=T)
+    assert ops.LAUNCHES == launches + 1          # one kernel: no warp launch, no fallback
+    assert torch.equal(got, ref)
+
+
+def test_model_forward_with_homographies_fuses_the_warp(cuda):
+    """``model(burst, homographies=M)`` (cfg3's front end) == ``model(warp_burst(burst, M))`` bit for bit on the tensor-core path, with
+    one launch fewer; the fp32 path warps first and agrees as well."""
+    from fbanet_b200 import BaseModel, ops
+    from oracle.fbanet_oracle import build_oracle
+    cfg = dict(num_frames=5, img_size=40, in_channels=4, embed_dim=64, window_length=10)
+    sd = build_oracle(0, **cfg).state_dict()
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(2, 5, 4, 40, 40, generator=g).to(cuda)
+    M = torch.eye(3, dtype=torch.float64).repeat(2, 5, 1, 1)
+    M[:, 1:, :2, 2] = torch.rand(2, 4, 2, generator=g, dtype=torch.float64) * 6 - 3
+    M[:, 1:, 2, :2] = torch.rand(2, 4, 2, generator=g, dtype=torch.float64) * 2e-5 - 1e-5
+    for dtype in ("bf16", "fp32"):
+        m = BaseModel(**cfg, token_projection="linear", token_mlp="leff", dtype=dtype)
+        m.load_state_dict(sd)
+        m = m.to(cuda).eval()
+        ref = m(ops.warp_burst(x, M))
+        n0 = ops.LAUNCHES
+        m(ops.warp_burst(x, M))
+        n_two = ops.LAUNCHES - n0
+        n0 = ops.LAUNCHES
+        got = m(x, homographies=M)
+        n_fused = ops.LAUNCHES - n0
+        assert torch.equal(got, ref), dtype
+        assert n_fused == (n_two - 1 if dtype == "bf16" else n_two), (dtype, n_fused, n_two)

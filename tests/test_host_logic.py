@@ -779,3 +779,24 @@ def test_torch_library_ops_are_registered_with_fake_kernels_and_no_cpu_fallback(
                                               torch.empty(1)).shape == (2, 40, 40, 64)
     with pytest.raises(NotImplementedError):
         torch.ops.fbanet.layernorm(torch.zeros(4, 8), torch.ones(8), torch.zeros(8), 1e-5)
+
+
+def test_round_rowsum_keeps_row_sums_and_touches_few_elements():
+    """ops.round_rowsum: bf16 rows whose sums equal the fp32 rows' sums (plain rounding leaves ~sqrt(K) * 2^-10 * |w|), at most nine
+    elements per row moved off round-to-nearest, zero (padding) columns untouched, fp32 a plain cast."""
+    import torch
+    from fbanet_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    w = (torch.rand(96, 576, generator=g) * 2 - 1) / 24
+    w[:, 570:] = 0
+    plain = w.to(torch.bfloat16)
+    r = ops.round_rowsum(w, torch.bfloat16)
+    assert r.dtype == torch.bfloat16 and r.shape == w.shape
+    err_plain = (plain.double().sum(1) - w.double().sum(1)).abs()
+    err = (r.double().sum(1) - w.double().sum(1)).abs()
+    assert err.max() < 2e-6 and err.max() < 0.02 * err_plain.mean(), (err.max(), err_plain.mean())
+    assert ((r != plain).sum(1) <= 9).all()
+    assert (r[:, 570:] == 0).all()
+    assert (r.float() - w).abs().max() < 5e-4            # the moved elements change by about one ulp of a typical weight (max |w| ulp = 2.4e-4)
+    assert torch.equal(ops.round_rowsum(w, torch.float32), w)

@@ -128,6 +128,10 @@ def run(seed, variant, exact=()):
             ROUND = bf_rowsum
             apply_variant(m, every, every)
             ROUND = bf
+        elif v == "foldsum":
+            ROUND = bf_rowsum
+            apply_variant(m, every, every, fold=True)
+            ROUND = bf
         elif v == "allx":
             apply_variant(m, every, every, exact=exact)
         elif v == "foldx":

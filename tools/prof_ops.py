@@ -59,6 +59,17 @@ def head(B, S):
     return (lambda: ops.head_conv(x, w, b, BF)), (x.numel() * 4 + B * 14 * S * S * 64 * 2) / 1e9
 
 
+def head_warp(B, S):
+    """K1 fused into K0: the head conv sampling the unregistered burst through the homographies."""
+    x = torch.rand(B * 14, 3, S, S, device=dev)
+    w, b = torch.rand(27, 64, device=dev) - 0.5, torch.rand(64, device=dev)
+    M = torch.eye(3, dtype=torch.float64).repeat(B, 14, 1, 1)
+    M[:, 1:, :2, 2] = torch.rand(B, 13, 2, dtype=torch.float64) * 8 - 4
+    M[:, 1:, 2, :2] = (torch.rand(B, 13, 2, dtype=torch.float64) - 0.5) * 2e-5
+    M = M.view(-1, 3, 3).to(dev)
+    return (lambda: ops.head_conv(x, w, b, BF, M=M, frames_per_burst=14)), (x.numel() * 4 + B * 14 * S * S * 64 * 2) / 1e9
+
+
 def warp(B, S):
     x = torch.rand(B, 14, 3, S, S, device=dev)
     M = torch.eye(3, dtype=torch.float64).repeat(B, 14, 1, 1)
@@ -128,6 +139,7 @@ CASES = {
     "ln_80_256": lambda: ln(64, 80, 256),
     "gate_160": lambda: gate(64, 160),
     "head_160": lambda: head(64, 160),
+    "head_warp_160": lambda: head_warp(64, 160),
     "warp_160": lambda: warp(64, 160),
     "flow_160": lambda: flow(64, 160),
 }
