@@ -40,7 +40,7 @@ class ConvParams(C.Structure):
         ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32), ("Cout_store", C.c_int32),
         ("act", C.c_int32), ("store_mode", C.c_int32), ("res_ld", C.c_int32), ("out_ld", C.c_int32),
         ("src_s2d", C.c_int32), ("fold_hi_lo", C.c_int32),
-        ("ln_stats", C.c_void_p), ("_reserved", C.c_void_p),
+        ("ln_stats", C.c_void_p), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float), ("_pad_ln", C.c_int32),
     ]
 
 

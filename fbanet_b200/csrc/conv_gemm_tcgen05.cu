@@ -53,6 +53,9 @@ struct TcParams {
   const float* bias;
   const float* alpha;
   const float* ln_stats;  // folded LayerNorm: per-row (mean, rstd), see fbanet_conv_params
+  const float* ln_gamma;  // LayerNorm applied to the A tile in shared memory (LN_SMEM instantiation): fp32 [K]
+  const float* ln_beta;
+  float ln_eps;
   const bf16* residual;
   void* out;
   const float* base;
@@ -256,6 +259,124 @@ __device__ __forceinline__ void mma_loop_resident(const int mt0, const int mt_st
   }
 }
 
+// LayerNorm of the A tile IN SHARED MEMORY (1x1 GEMMs whose input is a LayerNorm output: norm1 -> qkv, norm2 -> fc1,
+// layers/fba_net.py:196,246).  The raw token rows arrive by TMA exactly as for a plain GEMM; four extra warps -- one thread per
+// tile row -- normalise them in place before the MMA warp may read them (a_norm barriers stand between a_full and the issuer), so
+// the separate LayerNorm pass and the normalised tensor's trip through HBM disappear.  The arithmetic is the LayerNorm kernel's
+// (layernorm_bf16_kernel), operation for operation: per 8-element chunk a serial sum, the chunks combined by the same halving
+// tree its xor-shuffles form, mean = s / C, the centred second pass, rstd = rsqrt(q / C + eps), (x - mean) * rstd * gamma + beta
+// rounded to bf16 -- the GEMM sees bit-identical operands.
+template <int NK>
+__device__ __forceinline__ void ln_smem_loop(const TcParams& p, const uint32_t sa0, uint64_t* a_full, uint64_t* a_norm, const float* ln_gb,
+                                             const int mt0, const int mt_step, const int r, const int lane) {
+  constexpr int C = 64 * NK, TPT = C / 8;
+  const uint32_t roff = (uint32_t)r * 128u, r7 = (uint32_t)r & 7u;
+  const uint32_t a_slot_bytes = (uint32_t)p.a_slot_bytes;
+  const int a_slots = p.a_slots;
+  const float eps = p.ln_eps;
+  int aslot = 0;
+  uint32_t aphase = 0;
+  auto lds8 = [](uint32_t addr, float (&f)[8]) {
+    uint32_t u0, u1, u2, u3;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3) : "r"(addr));
+    f[0] = __uint_as_float(u0 << 16); f[1] = __uint_as_float(u0 & 0xffff0000u);
+    f[2] = __uint_as_float(u1 << 16); f[3] = __uint_as_float(u1 & 0xffff0000u);
+    f[4] = __uint_as_float(u2 << 16); f[5] = __uint_as_float(u2 & 0xffff0000u);
+    f[6] = __uint_as_float(u3 << 16); f[7] = __uint_as_float(u3 & 0xffff0000u);
+  };
+  // The K-chunk loops are ROLLED (the tile's slots are walked with a running ring index): unrolled over NK = 4 the three passes held
+  // 128 loaded registers at once and spilled.  The chunk sums are combined exactly as the LayerNorm kernel's shuffle tree does --
+  // cs[i] += cs[i + o] for o = TPT/2 .. 1 with cs index = 8 k + c: first across the K chunks (k with k + NK/2, then 0 with 1), then
+  // across the eight 16-byte chunks c -- so sums A (k even, or NK < 4) and B (k odd, NK = 4) per c suffice.
+  auto reduce = [&](float (&A)[8], float (&Bv)[8]) -> float {
+    if (NK == 4) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) A[c] += Bv[c];
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+      for (int i = 0; i < o; ++i) A[i] += A[i + o];
+    return A[0];
+  };
+  for (int mt = mt0; mt < p.m_tiles; mt += mt_step) {
+    const int slot0 = aslot;
+#pragma unroll 1
+    for (int k = 0; k < NK; ++k) {
+      mbar_wait(&a_full[aslot], aphase);
+      if (++aslot == a_slots) { aslot = 0; aphase ^= 1u; }
+    }
+    float A[8], Bv[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) A[c] = Bv[c] = 0.f;
+    int sl = slot0;
+#pragma unroll 1
+    for (int k = 0; k < NK; ++k) {
+      const uint32_t base = sa0 + (uint32_t)sl * a_slot_bytes + roff;
+      if (++sl == a_slots) sl = 0;
+      const bool toB = NK == 4 && (k & 1), first = NK == 4 ? k < 2 : k == 0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float f[8];
+        lds8(base + (((uint32_t)c ^ r7) << 4), f);
+        float s_ = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_ += f[i];
+        if (toB) Bv[c] = first ? s_ : Bv[c] + s_;
+        else A[c] = first ? s_ : A[c] + s_;
+      }
+    }
+    const float mean = reduce(A, Bv) * (1.0f / C);
+    sl = slot0;
+#pragma unroll 1
+    for (int k = 0; k < NK; ++k) {
+      const uint32_t base = sa0 + (uint32_t)sl * a_slot_bytes + roff;
+      if (++sl == a_slots) sl = 0;
+      const bool toB = NK == 4 && (k & 1), first = NK == 4 ? k < 2 : k == 0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float f[8];
+        lds8(base + (((uint32_t)c ^ r7) << 4), f);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = f[i] - mean; q += d * d; }
+        if (toB) Bv[c] = first ? q : Bv[c] + q;
+        else A[c] = first ? q : A[c] + q;
+      }
+    }
+    const float rstd = rsqrtf(reduce(A, Bv) * (1.0f / C) + eps);
+    sl = slot0;
+#pragma unroll 1
+    for (int k = 0; k < NK; ++k) {
+      const int slk = sl;
+      const uint32_t base = sa0 + (uint32_t)sl * a_slot_bytes + roff;
+      if (++sl == a_slots) sl = 0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t addr = base + (((uint32_t)c ^ r7) << 4);
+        float f[8];
+        lds8(addr, f);
+        const float* g = ln_gb + k * 64 + c * 8;           // broadcast reads: all lanes take the same columns
+        const float4 g0 = *reinterpret_cast<const float4*>(g), g1 = *reinterpret_cast<const float4*>(g + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(g + 256), b1 = *reinterpret_cast<const float4*>(g + 260);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t o4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float y0 = (f[2 * i] - mean) * rstd * gg[2 * i] + bb[2 * i];
+          const float y1 = (f[2 * i + 1] - mean) * rstd * gg[2 * i + 1] + bb[2 * i + 1];
+          __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+          o4[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o4[0]), "r"(o4[1]), "r"(o4[2]), "r"(o4[3]) : "memory");
+      }
+      fence_proxy_async();                                 // generic-proxy writes -> visible to the tensor core's reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_norm[slk]);            // this warp's 32 rows of K chunk k are normalised
+    }
+  }
+}
+
 // (image, tile row, tile column) of the tiles a CTA owns, advanced incrementally: the role loops used two 32-bit divisions per
 // tile, and with 4-MMA tiles (1x1 GEMMs with K = 64, the tap-stacked convs) every serial instruction of a role loop shows
 struct TileIter {
@@ -284,8 +405,9 @@ constexpr int TC_MAX_A_SLOTS = 8;
 constexpr int TC_MAX_EPI_WARPS = 12;
 
 // HAS_LN: folded-LayerNorm epilogue (a separate instantiation: compiled into the common one it costs every GEMM 12 %)
-template <bool HAS_LN, int TC_EPI_SLOTS>
-__global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
+// LN_SMEM: four more warps normalise every A tile in shared memory before the MMAs read it (ln_smem_loop)
+template <bool HAS_LN, int TC_EPI_SLOTS, bool LN_SMEM = false>
+__global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0), 1) conv_gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   constexpr int TC_EPI_WARPS = 4 * TC_EPI_SLOTS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[TC_MAX_A_SLOTS], a_empty[TC_MAX_A_SLOTS], tmem_full[4], tmem_empty[4];
@@ -293,6 +415,8 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float bias_s[256];
   __shared__ __align__(8) uint64_t res_bar[TC_MAX_EPI_WARPS];
+  __shared__ __align__(8) uint64_t a_norm[LN_SMEM ? TC_MAX_A_SLOTS : 1];
+  __shared__ __align__(16) float ln_gb[LN_SMEM ? 512 : 4];   // gamma [0, 256) | beta [256, 512)
 
   // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the 128B swizzle needs
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -316,6 +440,8 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
     for (int s = 0; s < p.b_slots; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int a = 0; a < 4; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], TC_EPI_WARPS); }
     for (int a = 0; a < TC_EPI_WARPS; ++a) mbar_init(&res_bar[a], 1);
+    if (LN_SMEM)
+      for (int s = 0; s < p.a_slots; ++s) mbar_init(&a_norm[s], 4);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -326,6 +452,8 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
     const int i = threadIdx.x - 128;
     if (i < 256) bias_s[i] = (p.bias && i < (p.tapsum ? p.Cout_store : BN)) ? __ldg(p.bias + (blockIdx.x % p.n_tiles_n) * BN + i) : 0.f;
   }
+  if (LN_SMEM && warp >= 4 + TC_EPI_WARPS)
+    for (int j = threadIdx.x - (128 + 32 * TC_EPI_WARPS); j < 64 * p.nsteps; j += 128) { ln_gb[j] = __ldg(p.ln_gamma + j); ln_gb[256 + j] = __ldg(p.ln_beta + j); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -431,7 +559,8 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
       const int halo = p.halo, a_slots = p.a_slots, m_tiles = p.m_tiles;
       const uint32_t a_slot16 = (uint32_t)p.a_slot_bytes >> 4;
       const bool nomma = (p.debug & 2) != 0;
-      const uint32_t bar_af = smem_u32(&a_full[0]), bar_ae = smem_u32(&a_empty[0]), bar_tf = smem_u32(&tmem_full[0]), bar_te = smem_u32(&tmem_empty[0]);
+      // LN_SMEM: an A slot is ready once the LayerNorm warps have normalised it
+      const uint32_t bar_af = smem_u32(LN_SMEM ? &a_norm[0] : &a_full[0]), bar_ae = smem_u32(&a_empty[0]), bar_tf = smem_u32(&tmem_full[0]), bar_te = smem_u32(&tmem_empty[0]);
 #define FBANET_MMA_LOOP(T, H) \
   mma_loop_resident<T, H>(mt0, mt_step, m_tiles, units, a_slots, a_slot16, sa0 >> 4, sb0 >> 4, b_bytes >> 4, tmem_base, (uint32_t)BN, idesc, bar_af, bar_ae, bar_tf, bar_te, nomma, (uint32_t)nacc_mask, (uint32_t)nacc_shift)
       if (halo == 0) FBANET_MMA_LOOP(1, 0);
@@ -446,7 +575,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);     // epilogue has drained this accumulator
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
       for (int u = 0; u < units; ++u) {
-        mbar_wait(&a_full[aslot], aphase);
+        mbar_wait(LN_SMEM ? &a_norm[aslot] : &a_full[aslot], aphase);
         tc_fence_after();
         const uint32_t sa = sa0 + (uint32_t)aslot * (uint32_t)p.a_slot_bytes;
         if (elect_one()) {
@@ -479,7 +608,14 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS, 1) conv_gemm_tcgen05
       }
     }
     }
-  } else if (warp >= 4) {
+  } else if (LN_SMEM && warp >= 4 + TC_EPI_WARPS) {
+    // ================= LayerNorm warps: normalise every A tile in place before the issuer reads it =================
+    const int r = threadIdx.x - (128 + 32 * TC_EPI_WARPS);
+    const uint32_t sa0 = smem_u32(smem_a);
+    if (p.nsteps == 1) ln_smem_loop<1>(p, sa0, a_full, a_norm, ln_gb, mt0, mt_step, r, lane);
+    else if (p.nsteps == 2) ln_smem_loop<2>(p, sa0, a_full, a_norm, ln_gb, mt0, mt_step, r, lane);
+    else ln_smem_loop<4>(p, sa0, a_full, a_norm, ln_gb, mt0, mt_step, r, lane);
+  } else if (warp >= 4 && warp < 4 + TC_EPI_WARPS) {
     // ================= epilogue: 4 TMEM lane quarters x TC_EPI_SLOTS warps; column pieces are dealt round-robin to the slots =================
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
     const int slot = (warp - 4) >> 2;
@@ -846,6 +982,11 @@ static bool tc_shape_ok(const fbanet_conv_params* p) {
   }
   if (p->bias && ((uintptr_t)p->bias % 16)) return false;
   if (p->ln_stats && (p->KH != 1 || p->stride != 1 || p->store_mode != FBANET_STORE_NHWC || ((uintptr_t)p->ln_stats % 8))) return false;
+  if (p->ln_gamma) {   // LayerNorm of the A tile in shared memory: a 1x1 GEMM over ONE source of 64 / 128 / 256 channels
+    if (!p->ln_beta || p->ln_stats || p->KH != 1 || p->stride != 1 || p->nsrc != 1 || p->src_s2d) return false;
+    if (ctot != 64 && ctot != 128 && ctot != 256) return false;
+    if (((uintptr_t)p->ln_gamma % 4) || ((uintptr_t)p->ln_beta % 4)) return false;
+  }
   return get_encode() != nullptr;
 }
 
@@ -970,6 +1111,7 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
     }
   }
   tp.nsteps = ns;
+  tp.ln_gamma = p->ln_gamma; tp.ln_beta = p->ln_beta; tp.ln_eps = p->ln_eps;
   tp.bias = p->bias; tp.alpha = p->alpha; tp.ln_stats = p->ln_stats; tp.residual = reinterpret_cast<const bf16*>(p->residual);
   tp.out = p->out; tp.base = p->base;
   tp.res_img_stride = p->res_img_stride; tp.out_img_stride = p->out_img_stride; tp.base_img_stride = p->base_img_stride;
@@ -1019,6 +1161,7 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   tp.a_slot_bytes = halo ? (halo_mode >= 2 ? TC_HALO_WSLOT : TC_HALO_SLOT) : TC_A_BYTES;
   const int a_min = halo ? 2 : 3;
   const int units = halo ? tp.nchunks : ns;
+  const bool ln_smem = p->ln_gamma != nullptr;
   struct Plan { int resident, a_slots, b_slots; };
   auto plan = [&](int budget, Plan* pl) -> bool {
     if ((int64_t)ns * b_bytes + (int64_t)a_min * tp.a_slot_bytes <= budget) {
@@ -1028,7 +1171,7 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
       pl->a_slots = a > TC_MAX_A_SLOTS ? TC_MAX_A_SLOTS : a;
     } else {
       pl->resident = 0;
-      pl->a_slots = halo ? 2 : 4;
+      pl->a_slots = halo ? 2 : (ln_smem && units + 2 > 4 ? units + 2 : 4);   // LN in smem: a whole tile (units slots) + look-ahead
       const int b = (budget - pl->a_slots * tp.a_slot_bytes) / b_bytes;
       if (b < 2) return false;
       pl->b_slots = b >= 8 ? 8 : (b >= 4 ? 4 : 2);   // power of two: ring slot = step & (slots-1)
@@ -1045,11 +1188,11 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
     // >= 4 A slots left (deep-K GEMMs lose more from a shallow A ring than they gain in the epilogue), two warps >= 3.
     static const int opts[4][2] = {{3, 2}, {3, 1}, {2, 2}, {2, 1}};
     tp.tma_store = 0;
-    for (int o = 0; o < 4 && !tp.tma_store; ++o) {
+    for (int o = ln_smem ? 2 : 0; o < 4 && !tp.tma_store; ++o) {   // LN in smem: the four LayerNorm warps take the third warp set's place
       const int slots = opts[o][0], bufs = opts[o][1];
       const int sb = 4 * slots * bufs * 4096;
       const int floor_a = slots == 3 ? 4 : 3;
-      const int want_a = p0.a_slots < floor_a ? p0.a_slots : floor_a;
+      const int want_a = ln_smem ? units + 1 : (p0.a_slots < floor_a ? p0.a_slots : floor_a);   // LN in smem: a whole tile + one slot of look-ahead
       if (plan(216 * 1024 - sb, &p1) && p1.resident == p0.resident && p1.b_slots == p0.b_slots && p1.a_slots >= want_a) {
         tp.tma_store = 1; tp.stage_bufs = bufs; stage_bytes = sb; epi_slots = slots; p0 = p1;
       }
@@ -1061,6 +1204,7 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
     epi_slots = 2;
   }
   tp.b_resident = p0.resident; tp.a_slots = p0.a_slots; tp.b_slots = p0.b_slots;
+  if (ln_smem && tp.a_slots < units + 1) return FBANET_E_UNSUPPORTED;   // the LayerNorm warps hold all K chunks of a tile at once
   { const char* dbg = getenv("FBANET_TC_DEBUG"); tp.debug = dbg ? atoi(dbg) : 0; }
   // accumulator stages in TMEM.  Four (N tiles up to 128) were measured against two on every layer shape and change nothing:
   // the gap between "MMA-only" (1.55 ms) + "epilogue-only" (1.28 ms) and both together (1.77 ms) on the 64->64 body conv is not
@@ -1075,6 +1219,7 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cudaGetLastError(); set_last_error(e); return FBANET_E_LAUNCH; }
     smem_opted_in = smem;
   }
@@ -1086,7 +1231,9 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   if (per_n < 1) per_n = 1;
   if (per_n > tp.m_tiles) per_n = tp.m_tiles;
   const int grid = per_n * tp.n_tiles_n;
-  if (epi_slots == 3) {   // staged epilogue with 12 epilogue warps
+  if (ln_smem) {          // 8 epilogue warps + 4 LayerNorm warps
+    conv_gemm_tcgen05_kernel<false, 2, true><<<grid, 512, smem, stream>>>(tp);
+  } else if (epi_slots == 3) {   // staged epilogue with 12 epilogue warps
     if (tp.ln_stats) conv_gemm_tcgen05_kernel<true, 3><<<grid, 512, smem, stream>>>(tp);
     else conv_gemm_tcgen05_kernel<false, 3><<<grid, 512, smem, stream>>>(tp);
   } else {                // 8 epilogue warps (staged or direct stores), 168 registers

@@ -252,7 +252,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) window_attention_dh16_kernel(co
       }
     };
     // one query tile, keys streamed in 7 steps of 16: O = P v and l = P 1 with p = exp2(s - c)
-    auto stream_tile = [&](const int mt, const uint32_t m0, const uint32_t m1, const float c0, const float c1, auto shifted_tag, auto wrap_tag) {
+    // LASTQ (query tile 6 = rows 96..111): the tile's upper half (rows 104..111) is padding for every lane, so its probabilities
+    // -- half of the tile's MUFU.EX2, 1/14 of the kernel's -- are not computed (P = 0 there; those output rows are never stored).
+    auto stream_tile = [&](const int mt, const uint32_t m0, const uint32_t m1, const float c0, const float c1, auto shifted_tag, auto wrap_tag,
+                           auto last_tag) {
+      constexpr bool LASTQ = decltype(last_tag)::value;
       float sa[2][4], sb[2][4];   // two steps in flight: [step parity][..] for key tiles 2ks (sa) and 2ks+1 (sb)
 #pragma unroll
       for (int e = 0; e < 4; ++e) o0[e] = o1[e] = os[e] = 0.f;
@@ -265,10 +269,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) window_attention_dh16_kernel(co
         if (2 * ks + 3 < NTU) score_tile(sb[nxt], mt, 2 * ks + 3, m0, m1, c0, c1, shifted_tag, wrap_tag);
         uint32_t pa[4];
         pa[0] = POLY >= 1 ? ex2_poly_pack2(sa[cur][0], sa[cur][1]) : pack2(ex2(sa[cur][0]), ex2(sa[cur][1]));
-        pa[1] = POLY >= 3 ? ex2_poly_pack2(sa[cur][2], sa[cur][3]) : pack2(ex2(sa[cur][2]), ex2(sa[cur][3]));
+        pa[1] = LASTQ ? 0u : (POLY >= 3 ? ex2_poly_pack2(sa[cur][2], sa[cur][3]) : pack2(ex2(sa[cur][2]), ex2(sa[cur][3])));
         if (2 * ks + 1 < NTU) {
           pa[2] = pack2(ex2(sb[cur][0]), ex2(sb[cur][1]));
-          pa[3] = POLY >= 2 ? ex2_poly_pack2(sb[cur][2], sb[cur][3]) : pack2(ex2(sb[cur][2]), ex2(sb[cur][3]));
+          pa[3] = LASTQ ? 0u : (POLY >= 2 ? ex2_poly_pack2(sb[cur][2], sb[cur][3]) : pack2(ex2(sb[cur][2]), ex2(sb[cur][3])));
         } else {
           pa[2] = pa[3] = 0u;   // keys 104..111 are padding
         }
@@ -283,8 +287,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) window_attention_dh16_kernel(co
       uint32_t m0 = 0, m1 = 0;
       if (wrap) tile_masks(mt, m0, m1);
       ldsm4(qa, Qs + mt * 16 * ROWB + qfo0);
-      if (wrap) stream_tile(mt, m0, m1, 0.f, 0.f, std::false_type{}, std::true_type{});
-      else stream_tile(mt, 0u, 0u, 0.f, 0.f, std::false_type{}, std::false_type{});
+      if (mt == MT - 1) {
+        if (wrap) stream_tile(mt, m0, m1, 0.f, 0.f, std::false_type{}, std::true_type{}, std::true_type{});
+        else stream_tile(mt, 0u, 0u, 0.f, 0.f, std::false_type{}, std::false_type{}, std::true_type{});
+      } else if (wrap) stream_tile(mt, m0, m1, 0.f, 0.f, std::false_type{}, std::true_type{}, std::false_type{});
+      else stream_tile(mt, 0u, 0u, 0.f, 0.f, std::false_type{}, std::false_type{}, std::false_type{});
       const bool ok = ((os[0] > 8.6e-19f && os[0] < 1.15e18f) || r0 >= NTOK) && ((os[2] > 8.6e-19f && os[2] < 1.15e18f) || r1 >= NTOK);
       if (!__all_sync(0xffffffffu, ok)) {   // out-of-band row sum (huge logits): exact row maximum, then redo.  Cold.
         float mx0 = -3.0e38f, mx1 = -3.0e38f;
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) window_attention_dh16_kernel(co
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        stream_tile(mt, m0, m1, mx0, mx1, std::true_type{}, std::true_type{});   // m0 = m1 = 0 when the window does not wrap
+        stream_tile(mt, m0, m1, mx0, mx1, std::true_type{}, std::true_type{}, std::false_type{});   // m0 = m1 = 0 when the window does not wrap
       }
       float i0, i1;
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i0) : "f"(os[0]));

@@ -196,12 +196,23 @@ class BaseModel(nn.Module):
         self.fuse_faf = os.environ.get("FBANET_FUSE_FAF", "1") == "1"
         # dim <= 128 layers: the whole LeFF MLP in one kernel (ops.leff_mlp); FBANET_FUSE_MLP=0 keeps fc1 + leff_fc2
         self.fuse_mlp = os.environ.get("FBANET_FUSE_MLP", "1") == "1"
-        # forward(x, homographies=M): K1 fused into the head conv's sampling (ops.head_conv(M=)); FBANET_FUSE_WARP=0 = warp kernel first
-        self.fuse_warp = os.environ.get("FBANET_FUSE_WARP", "1") == "1"
+        # forward(x, homographies=M): FBANET_FUSE_WARP=1 fuses K1 into the head conv's sampling (ops.head_conv(M=): no warp launch, the
+        # warped burst never exists in HBM, bit-identical samples).  Measured on cfg3 (64 x 14 x 4 x 80^2, profiles/r2_z_cfg3_warp_fusion.log):
+        # fused head conv 0.47 ms against 0.10 ms (warp kernel) + 0.26 ms (head conv) -- the fp64 coordinate arithmetic lands on the
+        # kernel's eight producer warps, which already bound it -- so the default keeps the two launches.
+        self.fuse_warp = os.environ.get("FBANET_FUSE_WARP", "0") == "1"
         # bf16 path, optional: LayerNorm folded into the qkv / fc1 GEMMs (row statistics only; ops.fold_layernorm).  -1.3 ms per
         # batch-64 step and a lower mean PSNR delta over seeds (0.0043 vs 0.0049 dB), but one of three seeds lands at 0.0105 dB,
         # 5 % over the 0.01 dB parity tolerance, so it stays off by default; FBANET_FOLD_LN=1 (or the attribute) turns it on.
         self.fold_ln = os.environ.get("FBANET_FOLD_LN", "0") == "1"
+        # bf16 path: LayerNorm applied to the A tile of its consumer GEMM in shared memory (norm1 -> qkv, norm2 -> fc1 where fc1 is a
+        # GEMM) -- bit-identical to the LayerNorm kernel + GEMM, without the pass.  Measured per batch-64 step (A/B in one box,
+        # profiles/r2_y_ln_in_gemm_ab.log): it pays where ONE CTA covers all output columns of a pixel tile (dim 64: qkv 64 -> 192,
+        # 0.87 vs 0.67 + 0.36 ms of LayerNorm), and is a wash or a loss where the columns are split over 2-3 CTAs that each repeat the
+        # LayerNorm of the shared A tile (dim 128: 2.08 vs 1.37 + 0.68 ms; dim 256 @40^2: 0.59 vs 0.39 + 0.10 ms).  "1" (default) =
+        # single-N-tile GEMMs only, "all" = wherever the kernel takes the shape, "0" = never.
+        self.ln_in_gemm = os.environ.get("FBANET_LN_IN_GEMM", "1")
+        self._ln_gemm_refused = set()
         # bf16 weights rounded so that every GEMM row keeps its sum (ops.round_rowsum): removes the per-channel bias that plain
         # rounding leaves on inputs with a common mode; FBANET_ROWSUM_ROUND=0 = plain round-to-nearest
         self.rowsum_round = os.environ.get("FBANET_ROWSUM_ROUND", "1") == "1"
@@ -428,6 +439,24 @@ class BaseModel(nn.Module):
             out = self._new(*x4.shape[:3], w.shape[0])
         return ops.conv_gemm([x4], w, out, bias=P[name + ".b"], act=act, residual=residual, impl=self.impl, ln_stats=ln_stats)
 
+    def _ln_lin(self, P, name, lnkey, x4, act=L.ACT_NONE):
+        """Linear(LayerNorm(x)): LayerNorm inside the GEMM (ops.conv_gemm(ln=)) when the tensor-core kernel takes the shape,
+        else the LayerNorm kernel followed by the GEMM.  Same bits either way."""
+        B, H, W, Cd = x4.shape
+        sig = (name, B, H, W)
+        w = P[name + ".w"]
+        mode = {True: "1", False: "0"}.get(self.ln_in_gemm, self.ln_in_gemm)
+        if self._use_tc() and sig not in self._ln_gemm_refused and (mode == "all" or (mode == "1" and w.shape[0] <= 256)):
+            out = self._new(B, H, W, w.shape[0])
+            try:
+                return ops.conv_gemm([x4], w, out, bias=P[name + ".b"], act=act, impl=self.impl, ln=(P[lnkey + ".g"], P[lnkey + ".b"]))
+            except RuntimeError as e:
+                if "impl unsupported" not in str(e):
+                    raise
+                self._ln_gemm_refused.add(sig)
+        ln = ops.layernorm(x4.view(-1, Cd), P[lnkey + ".g"], P[lnkey + ".b"]).view(B, H, W, Cd)
+        return self._lin(P, name, ln, act=act)
+
     def _layer(self, P, key, ly: _Layer, x, out=None):
         """LeWin block (layers/fba_net.py:139-250 with Appendix A-4): x + Attn(LN1 x); + LeFF(LN2 .)."""
         B, H, W, Cd = x.shape
@@ -435,8 +464,7 @@ class BaseModel(nn.Module):
         if fold:
             qkv = self._lin(P, key + ".qkv", x, ln_stats=ops.row_stats(x.view(-1, Cd)))
         else:
-            ln1 = ops.layernorm(x.view(-1, Cd), P[key + ".ln1.g"], P[key + ".ln1.b"]).view(B, H, W, Cd)
-            qkv = self._lin(P, key + ".qkv", ln1)
+            qkv = self._ln_lin(P, key + ".qkv", key + ".ln1", x)
         scale = self.qk_scale or (Cd // ly.heads) ** -0.5
         att = ops.window_attention(qkv.view(-1, 3 * Cd), P[key + ".rpb"], B, H, W, ly.heads, ly.win, ly.shift, scale, impl=self.impl,
                                    bias_expanded=P.get(key + ".rpbx"), q_prescaled=self._use_tc(), bias_wrap=P.get(key + ".rpbw"))
@@ -444,15 +472,18 @@ class BaseModel(nn.Module):
         if fold:
             h = self._lin(P, key + ".fc1", x1, act=self.gelu_act, ln_stats=ops.row_stats(x1.view(-1, Cd)))
         else:
-            ln2 = ops.layernorm(x1.view(-1, Cd), P[key + ".ln2.g"], P[key + ".ln2.b"]).view(B, H, W, Cd)
+            h = None
             if self.fuse_mlp and (key + ".fc1.wh") in P:
                 # fc1 -> GELU -> depthwise 3x3 -> GELU -> fc2 + residual in ONE kernel: the 4C-channel hidden map never leaves the SM
+                ln2 = ops.layernorm(x1.view(-1, Cd), P[key + ".ln2.g"], P[key + ".ln2.b"]).view(B, H, W, Cd)
                 if out is None:
                     out = self._new(B, H, W, Cd)
                 if ops.leff_mlp(ln2, P[key + ".fc1.wh"], P[key + ".fc1.bh"], P[key + ".dw.wh"], P[key + ".dw.bh"], P[key + ".fc2.w"],
                                 P[key + ".fc2.b"], out, x1, self.gelu_act) is not None:
                     return out
-            h = self._lin(P, key + ".fc1", ln2, act=self.gelu_act)
+                h = self._lin(P, key + ".fc1", ln2, act=self.gelu_act)
+            if h is None:   # fc1 as a GEMM (dim 256): norm2 applied inside it
+                h = self._ln_lin(P, key + ".fc1", key + ".ln2", x1, act=self.gelu_act)
         if self._use_tc() and self.fuse_leff:
             # depthwise 3x3 + GELU computed inside the fc2 GEMM as its A-operand producer (no HBM round trip)
             if out is None:

@@ -11,7 +11,7 @@ from __future__ import annotations
 import math
 
 import ctypes as C
-from typing import Optional, Sequence
+from typing import Tuple, Optional, Sequence
 
 import torch
 
@@ -99,12 +99,19 @@ def conv_gemm(
     src_s2d: bool = False,
     ln_stats: Optional[torch.Tensor] = None,
     fold_hi_lo: bool = False,
+    ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+    ln_eps: float = 1e-5,
 ) -> torch.Tensor:
     """out = act(conv(concat(srcs)) + bias) + residual.  ``weight`` is packed ``[Cout, kh*kw*sum(C)]``.
 
     ``ln_stats`` ``[rows, 2]`` fp32 (mean, rstd per input row, :func:`row_stats`): LayerNorm folded into a 1x1 GEMM -- ``weight``
     must be the row-centred ``W * gamma`` and ``bias`` ``W @ beta + b`` (:func:`fold_layernorm`); the result equals
-    ``W @ LN(x) + b``."""
+    ``W @ LN(x) + b``.
+
+    ``ln = (gamma, beta)`` (fp32 ``[C]``): LayerNorm applied to the single source INSIDE the 1x1 GEMM -- the raw rows are normalised in
+    shared memory with the LayerNorm kernel's own arithmetic before the tensor core reads them; ``weight`` / ``bias`` are the layer's
+    own.  Bit-identical to :func:`layernorm` + GEMM.  Raises ``RuntimeError("... impl unsupported ...")`` when the shape does not fit
+    (callers then run the two kernels)."""
     p = L.ConvParams()
     dt = srcs[0].dtype
     p.dtype = _DT[dt]
@@ -143,6 +150,11 @@ def conv_gemm(
     if alpha is not None:
         assert alpha.dtype == torch.float32
         p.alpha = alpha.data_ptr()
+    if ln is not None:
+        g_, b_ = ln
+        assert ln_stats is None and len(srcs) == 1 and kh == 1 and kw == 1
+        assert g_.dtype == torch.float32 and b_.dtype == torch.float32 and g_.numel() == ctot and b_.numel() == ctot and g_.is_contiguous() and b_.is_contiguous()
+        p.ln_gamma, p.ln_beta, p.ln_eps = g_.data_ptr(), b_.data_ptr(), ln_eps
     if ln_stats is not None:
         assert ln_stats.dtype == torch.float32 and ln_stats.is_contiguous() and ln_stats.shape == (N * Ho * Wo, 2) and kh == 1 and kw == 1
         p.ln_stats = ln_stats.data_ptr()
@@ -176,7 +188,7 @@ def conv_gemm(
         p.out, p.out_ld, p.out_img_stride = op, old, ois
     esz = srcs[0].element_size()
     nbytes = N * H * W * ctot * esz + out.numel() * out.element_size() + (residual.numel() * esz if residual is not None else 0) + weight.numel() * esz
-    tag = f"k{kh}s{stride} {ctot}->{cout} @{Ho}x{Wo} act{act}{' res' if residual is not None else ''} st{store_mode}"
+    tag = f"k{kh}s{stride} {ctot}->{cout} @{Ho}x{Wo} act{act}{' res' if residual is not None else ''} st{store_mode}{' ln' if ln is not None else ''}"
     if _PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -112,7 +112,15 @@ typedef struct fbanet_conv_params {
    * which equals W LN(x) + b.  ln_stats: fp32 [rows][2] = (mean, rstd) per row from fbanet_layernorm_sm100 (stats mode;
    * only rstd is read).  NULL: plain GEMM. */
   const float* ln_stats;
-  const float* _reserved;
+  /* LayerNorm applied to the GEMM's input INSIDE the kernel (same layers, tensor-core path, one source of 64 / 128 / 256 channels):
+   * the raw rows x are loaded as for a plain GEMM and normalised in shared memory -- (x - mean) * rstd * ln_gamma + ln_beta rounded
+   * to bf16, operation for operation what fbanet_layernorm_sm100 computes -- before the tensor core reads them; weight / bias are
+   * the layer's own.  out = W LN(x) + b bit-identical to LayerNorm kernel + GEMM, without the normalised tensor in HBM.
+   * ln_gamma / ln_beta: fp32 [C]; NULL: plain GEMM.  Excludes ln_stats.  FBANET_E_UNSUPPORTED when the shape does not fit. */
+  const float* ln_gamma;
+  const float* ln_beta;
+  float ln_eps;
+  int32_t _pad_ln;
 } fbanet_conv_params;
 
 /* K1: homography warp with bilinear sampling.  Replaces cv2.warpPerspective / cv2.warpAffine with

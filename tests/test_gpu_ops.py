@@ -813,12 +813,16 @@ def test_head_conv_with_fused_homography_warp(cuda, cin, hw, bursts, T):
     launches = ops.LAUNCHES
     got = ops.head_conv(x.view(bursts * T, cin, H, W), wkc, b.to(cuda), torch.bfloat16, M=M.view(-1, 3, 3), frames_per_burst=T)
     assert ops.LAUNCHES == launches + 1          # one kernel: no warp launch, no fallback
-    assert torch.equal(got, ref)
+    # the planar warp kernel shares one fp64 division between four pixels (coordinates equal to ~1e-13 px), so a bilinear weight may
+    # round differently once in a few million samples: allow a handful of features to move by an ulp
+    diff = (got.float() - ref.float()).abs()
+    assert (diff > 0).float().mean().item() < 1e-5 and diff.max().item() < 0.02, ((diff > 0).sum().item(), diff.max().item())
 
 
 def test_model_forward_with_homographies_fuses_the_warp(cuda):
-    """``model(burst, homographies=M)`` (cfg3's front end) == ``model(warp_burst(burst, M))`` bit for bit on the tensor-core path, with
-    one launch fewer; the fp32 path warps first and agrees as well."""
+    """``model(burst, homographies=M)`` (cfg3's front end) == ``model(warp_burst(burst, M))``: bit for bit in the default mode (warp
+    kernel, then the forward), and with the warp fused into the head conv (``fuse_warp``, tensor-core path: one launch fewer, the same
+    image up to a weight rounding in a few samples per million); the fp32 path warps first either way."""
     from fbanet_b200 import BaseModel, ops
     from oracle.fbanet_oracle import build_oracle
     cfg = dict(num_frames=5, img_size=40, in_channels=4, embed_dim=64, window_length=10)
@@ -836,8 +840,12 @@ def test_model_forward_with_homographies_fuses_the_warp(cuda):
         n0 = ops.LAUNCHES
         m(ops.warp_burst(x, M))
         n_two = ops.LAUNCHES - n0
-        n0 = ops.LAUNCHES
-        got = m(x, homographies=M)
-        n_fused = ops.LAUNCHES - n0
-        assert torch.equal(got, ref), dtype
-        assert n_fused == (n_two - 1 if dtype == "bf16" else n_two), (dtype, n_fused, n_two)
+        for fuse in (False, True):
+            m.fuse_warp = fuse
+            n0 = ops.LAUNCHES
+            got = m(x, homographies=M)
+            n = ops.LAUNCHES - n0
+            assert (got - ref).abs().max().item() < 1e-3, (dtype, fuse)
+            if not fuse:
+                assert torch.equal(got, ref), dtype
+            assert n == (n_two - 1 if (dtype == "bf16" and fuse) else n_two), (dtype, fuse, n, n_two)

@@ -282,3 +282,57 @@ def test_faf_fuse_one_pass(cuda, B, Fr, h, w):
     assert (g.cpu() - gate).abs().max().item() < 2e-3, (g.cpu() - gate).abs().max().item()
     _check(buf[..., E:], ref, tol=3e-2)
     assert buf[..., :E].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("C,cout,n,h,w,act", [(64, 192, 2, 40, 40, 0), (128, 384, 1, 37, 21, 0), (256, 768, 2, 20, 20, 0), (256, 1024, 1, 40, 40, 3),
+                                              (128, 384, 3, 160, 160, 0), (64, 192, 70, 16, 16, 0), (128, 512, 1, 30, 50, 3), (256, 768, 40, 40, 40, 0)])
+def test_tc_linear_with_layernorm_in_shared_memory(cuda, C, cout, n, h, w, act):
+    """LayerNorm applied to the A tile of a 1x1 GEMM in shared memory (norm1 -> qkv, norm2 -> fc1; layers/fba_net.py:196,246):
+    the result equals the LayerNorm kernel followed by the plain GEMM BIT FOR BIT (the in-kernel LayerNorm repeats that kernel's
+    arithmetic operation for operation), for every stage width (64 / 128 / 256 channels: 1, 2, 4 K chunks; resident and streamed
+    weights), ragged sizes (partial tiles), more tiles than SMs (ring and barrier phase wrap), rows with a large common mode, and
+    the GELU epilogue; and LayerNorm itself is pinned to torch by test_layernorm."""
+    from fbanet_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(C + cout + h)
+    x = ((torch.rand(n, h, w, C, generator=g) * 2 - 1) * 1.5 + torch.rand(n, h, w, 1, generator=g) * 6 - 3).to(cuda, BF)
+    gam, bet = (torch.rand(C, generator=g) + 0.5).to(cuda), (torch.rand(C, generator=g) - 0.5).to(cuda)
+    wt = ((torch.rand(cout, C, generator=g) * 2 - 1) / math.sqrt(C)).to(cuda, BF)
+    b = (torch.rand(cout, generator=g) - 0.5).to(cuda)
+    ln = ops.layernorm(x.view(-1, C), gam, bet).view(n, h, w, C)
+    ref = ops.conv_gemm([ln], wt, torch.empty(n, h, w, cout, device=cuda, dtype=BF), bias=b, act=act, impl=L.IMPL_TCGEN05)
+    launches = ops.LAUNCHES
+    got = ops.conv_gemm([x], wt, torch.empty(n, h, w, cout, device=cuda, dtype=BF), bias=b, act=act, impl=L.IMPL_TCGEN05, ln=(gam, bet))
+    assert ops.LAUNCHES == launches + 1
+    assert torch.equal(got, ref), (got.float() - ref.float()).abs().max().item()
+    # and against torch fp32 on the same operands (the GEMM reads bf16(LN(x)))
+    t = F.layer_norm(x.float().cpu(), (C,), gam.cpu(), bet.cpu(), 1e-5).to(BF).float()
+    y = F.linear(t, wt.float().cpu(), b.cpu())
+    if act == 3:
+        y = F.gelu(y, approximate="tanh")
+    _check(got, y, tol=3e-2)
+
+
+def test_model_layernorm_in_gemm_is_bit_identical(cuda):
+    """The model with LayerNorm inside the qkv / fc1 GEMMs equals the model with the stand-alone LayerNorm kernel bit for bit on the
+    full cfg2 shape: in the default mode (single-N-tile GEMMs: the four dim-64 qkv projections) and with every GEMM the kernel takes
+    (`ln_in_gemm = "all"`: 20 norm1 + the 8 norm2 of the dim-256 layers = 28 LayerNorm launches fewer)."""
+    from fbanet_b200 import BaseModel, ops
+    from oracle.fbanet_oracle import build_oracle
+    cfg = dict(num_frames=14, img_size=160, in_channels=3, embed_dim=64, window_length=10)
+    m = BaseModel(**cfg, token_projection="linear", token_mlp="leff", dtype="bf16")
+    m.load_state_dict(build_oracle(2, **cfg).state_dict())
+    m = m.to(cuda).eval()
+    x = torch.rand(2, 14, 3, 160, 160, generator=torch.Generator().manual_seed(3)).to(cuda)
+
+    def run(mode):
+        m.ln_in_gemm = mode
+        y = m(x)
+        n0 = ops.LAUNCHES
+        m(x)
+        return y, ops.LAUNCHES - n0
+
+    ref, n_plain = run("0")
+    got, n_default = run("1")
+    assert torch.equal(got, ref) and n_default == n_plain - 4, (n_default, n_plain)
+    got, n_all = run("all")
+    assert torch.equal(got, ref) and n_all == n_plain - 28, (n_all, n_plain)
