@@ -923,7 +923,13 @@ static int conv_ctot(const fbanet_conv_params* p) {
 // per pixel tile instead of once per 128 output channels and the MMAs run at N = 256 (0.84 -> 0.66 ms on 512->256 @80x80,
 // 1475 TFLOP/s); with a shallow K (the 64->256 tail convs) the longer epilogue per tile is not hidden and 128 stays better.
 static int pick_bn(int cout, bool halo, int ctot) {
-  const int cap = (halo && ctot < 128) ? 128 : 256;
+  int cap = (halo && ctot < 128) ? 128 : 256;
+  // 1x1 GEMMs over 256 input channels: with 256-column tiles the resident weights (128 KB) leave three A slots and one staging buffer
+  // per epilogue warp; 192 / 128 columns measured 5-15 % faster (profiles/r2_bn_cap_1x1.log: qkv 256->768 0.213 -> 0.196 ms,
+  // proj 256->256 0.130 -> 0.110, fc1 256->1024 0.346 -> 0.326)
+  if (!halo && ctot >= 256) cap = 192;
+  static const char* bnenv = getenv("FBANET_TC_BN");   // experiment switch: cap of the N tile of 1x1 GEMMs (64 / 128 / 192 / 256)
+  if (!halo && bnenv) { const int v = atoi(bnenv); if (v >= 64 && v <= 256) cap = v; }
   if (cout <= cap) return cout;
   for (int bn = cap; bn >= 64; bn -= 64)
     if (cout % bn == 0) return bn;

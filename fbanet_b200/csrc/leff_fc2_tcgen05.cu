@@ -47,7 +47,8 @@ struct LeffParams {
 };
 
 // LF_DW_WARPS = depthwise/epilogue warps: 16 (4 output rows per thread) or 8 (8 rows per thread)
-template <int LF_DW_WARPS>
+// ITEM: the warp-per-block producer (16 warps, tanh GELU); else one thread per (column, 4 channels, RPT rows)
+template <int LF_DW_WARPS, bool ITEM>
 __global__ void __launch_bounds__(128 + 32 * LF_DW_WARPS, 1) leff_fc2_kernel(const __grid_constant__ LeffParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t h_full[LF_H_SLOTS], h_empty[LF_H_SLOTS], a_full[2], a_empty[2], b_full[8], b_empty[8], tmem_full[2], tmem_empty[2], r_full[2], r_empty[2];
@@ -251,6 +252,70 @@ __global__ void __launch_bounds__(128 + 32 * LF_DW_WARPS, 1) leff_fc2_kernel(con
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++it) {
       for (int c = 0; c < p.nchunks; ++c, ++g) {
         const uint32_t hs = g & (LF_H_SLOTS - 1), as = g & 1;
+        if constexpr (ITEM) {
+          // ---- item form (the P2 stage of leff_mlp_tcgen05.cu): this WARP computes a 4-row x 2-column block of output pixels, each
+          // lane one channel PAIR -- four halo columns serve two output columns, a row of 32 lanes reads 128 contiguous bytes of one
+          // halo pixel (conflict free), the taps are 18 registers per lane, and GELU runs on z = x / 2 (taps and bias halved on
+          // load: GELU_tanh(x) = z (1 + tanh(z (2 k0 + 8 k0 k1 z^2))), one multiply less).  409 -> ~260 instructions per warp and chunk.
+          const int wi = warp - 4;
+          const uint32_t cp2 = (uint32_t)(wi & 3) * 2u, r4 = (uint32_t)(wi >> 2) * 4u;   // output columns cp2, cp2 + 1; rows r4 .. r4 + 3
+          f32x2 wd[9], bd;
+          {
+            const float* wp = p.dw_w + c * 64 + 2 * lane;
+            const f32x2 half = pack_f2(0.5f, 0.5f);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const float2 a = __ldg(reinterpret_cast<const float2*>(wp + (size_t)t * p.Hd));
+              wd[t] = mul_f2(pack_f2(a.x, a.y), half);
+            }
+            const float2 a = __ldg(reinterpret_cast<const float2*>(p.dw_b + c * 64 + 2 * lane));
+            bd = mul_f2(pack_f2(a.x, a.y), half);
+          }
+          mbar_wait(&h_full[hs], (g / LF_H_SLOTS) & 1);  // halo tile landed
+          mbar_wait(&a_empty[as], ((g >> 1) & 1) ^ 1);   // A slot consumed by the MMAs that used it last
+          const uint32_t hp = smem_u32(smem_h) + hs * LF_H_SLOT + (r4 * LF_HW + cp2) * 128u + (uint32_t)lane * 4u;
+          f32x2 acc[4][2];
+#pragma unroll
+          for (int o = 0; o < 4; ++o) { acc[o][0] = bd; acc[o][1] = bd; }
+#pragma unroll
+          for (int hr = 0; hr < 6; ++hr) {             // halo rows r4 + hr feed output rows hr - ky
+            f32x2 hv[4];
+#pragma unroll
+            for (int hc = 0; hc < 4; ++hc) {
+              uint32_t u;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(hp + (uint32_t)((hr * LF_HW + hc) * 128)));
+              hv[hc] = bf16x2_to_f2(u);
+            }
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const int o = hr - ky;
+              if (o >= 0 && o < 4) {
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                  acc[o][0] = fma_f2(hv[kx], wd[ky * 3 + kx], acc[o][0]);
+                  acc[o][1] = fma_f2(hv[kx + 1], wd[ky * 3 + kx], acc[o][1]);
+                }
+              }
+            }
+          }
+          // A-tile row of output (r4 + o, cp2 + oc) = (r4 + o) * 8 + cp2 + oc: the swizzle phase is row & 7 = cp2 + oc
+          const uint32_t ab = smem_u32(smem_a) + as * LF_A_BYTES + (r4 * LF_TW + cp2) * 128u + ((uint32_t)lane & 3u) * 4u;
+          const uint32_t a0 = ab + ((((uint32_t)lane >> 2) ^ cp2) << 4), a1 = ab + 128u + ((((uint32_t)lane >> 2) ^ (cp2 + 1u)) << 4);
+          auto gelu_half = [](f32x2 z) -> f32x2 {
+            const float A = 2.f * 0.7978845608028654f, B = 8.f * 0.7978845608028654f * 0.044715f;
+            const f32x2 u = mul_f2(fma_f2(mul_f2(z, z), pack_f2(B, B), pack_f2(A, A)), z);
+            float u0, u1, t0, t1;
+            unpack_f2(u, u0, u1);
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+            return fma_f2(z, pack_f2(t0, t1), z);
+          };
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a0 + (uint32_t)(o * LF_TW * 128)), "r"(f2_to_bf16x2(gelu_half(acc[o][0]))));
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a1 + (uint32_t)(o * LF_TW * 128)), "r"(f2_to_bf16x2(gelu_half(acc[o][1]))));
+          }
+        } else {
         // depthwise weights / bias of this thread's 4 channels (L1-resident after the first tile)
         const int ch0 = c * 64 + cg4 * 4;
         // packed fp32x2 arithmetic (FFMA2): channel pairs (0,1) and (2,3) of the thread's 4 channels
@@ -313,6 +378,7 @@ __global__ void __launch_bounds__(128 + 32 * LF_DW_WARPS, 1) leff_fc2_kernel(con
             asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(abase + (uint32_t)(rr * 128 + (((cg4 >> 1) ^ (rr & 7)) << 4) + (cg4 & 1) * 8)),
                          "r"(ov.x), "r"(ov.y));
           }
+        }
         }
         fence_proxy_async();                          // A tile written through the generic proxy -> visible to the tensor core
         __syncwarp();
@@ -397,8 +463,9 @@ extern "C" int fbanet_leff_fc2_sm100(const fbanet_leff_fc2_params* p, void* stre
   const bool w8 = env8 && env8[0] == '1';
   static size_t opted = 0;
   if (smem > opted) {
-    cudaError_t e = cudaFuncSetAttribute(leff_fc2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(leff_fc2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(leff_fc2_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(leff_fc2_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(leff_fc2_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cudaGetLastError(); set_last_error(e); return FBANET_E_LAUNCH; }
     opted = smem;
   }
@@ -406,7 +473,10 @@ extern "C" int fbanet_leff_fc2_sm100(const fbanet_leff_fc2_params* p, void* stre
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = lp.m_tiles < sms ? lp.m_tiles : sms;
-  if (w8) leff_fc2_kernel<8><<<grid, 128 + 32 * 8, smem, (cudaStream_t)stream>>>(lp);
-  else leff_fc2_kernel<16><<<grid, 128 + 32 * 16, smem, (cudaStream_t)stream>>>(lp);
+  static const char* item_env = getenv("FBANET_LEFF_ITEM");   // experiment switch: 0 = the thread-per-column producer everywhere
+  const bool item = !w8 && p->act == FBANET_ACT_GELU_TANH && !(item_env && item_env[0] == '0');
+  if (w8) leff_fc2_kernel<8, false><<<grid, 128 + 32 * 8, smem, (cudaStream_t)stream>>>(lp);
+  else if (item) leff_fc2_kernel<16, true><<<grid, 128 + 32 * 16, smem, (cudaStream_t)stream>>>(lp);
+  else leff_fc2_kernel<16, false><<<grid, 128 + 32 * 16, smem, (cudaStream_t)stream>>>(lp);
   return check_launch();
 }

@@ -26,6 +26,9 @@ CASES = {
     "fc2_512_128": (64, 160, 160, 512, 128, 1, L.ACT_NONE, True, L.STORE_NHWC),
     "qkv_128_384": (64, 160, 160, 128, 384, 1, L.ACT_NONE, False, L.STORE_NHWC),
     "fc1_256_1024": (64, 80, 80, 256, 1024, 1, L.ACT_GELU_TANH, False, L.STORE_NHWC),
+    "qkv_256_768": (64, 80, 80, 256, 768, 1, L.ACT_NONE, False, L.STORE_NHWC),
+    "qkv_64_192": (64, 160, 160, 64, 192, 1, L.ACT_NONE, False, L.STORE_NHWC),
+    "proj_256_256": (64, 80, 80, 256, 256, 1, L.ACT_NONE, True, L.STORE_NHWC),
     "fc2_1024_256": (64, 80, 80, 1024, 256, 1, L.ACT_NONE, True, L.STORE_NHWC),
     "head_64_64": (896, 160, 160, 64, 64, 1, L.ACT_NONE, False, L.STORE_NHWC),
     "score3x3_64_2": (896, 160, 160, 64, 16, 3, L.ACT_NONE, False, L.STORE_NHWC_F32),     # FAF score conv: 2 fp32 outputs, tap-stacked
