@@ -14,7 +14,7 @@ from collections import OrderedDict, defaultdict
 
 def family(name: str) -> str:
     name = re.sub(r"^void\s+", "", name)
-    name = name.replace("fbanet::", "").replace("<unnamed>::", "").replace("(anonymous namespace)::", "")
+    name = name.replace("fbanet::", "").replace("<unnamed>::", "").replace("unnamed>::", "").replace("(anonymous namespace)::", "")
     name = re.sub(r"\(.*$", "", name)
     name = re.sub(r"<.*$", "", name)
     return name.strip()
@@ -37,7 +37,10 @@ def main():
         scale = {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "nsecond": 1e-6, "s": 1e3, "second": 1e3,
                  "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
         d[m] = val * scale
-    ours = [d for d in launches.values() if "fbanet" in d["name"] or "leff" in d["name"] or "conv_gemm" in d["name"]]
+    # this repo's kernels: everything that is not a torch / cub / cuBLAS kernel (a capture taken with `-k regex:fbanet --kernel-name-base
+    # demangled` lists base names without the namespace)
+    foreign = ("at::", "cub::", "cublas", "cutlass", "thrust::", "elementwise_kernel", "vectorized_", "nccl", "distribution_", "reduce_kernel", "index_")
+    ours = [d for d in launches.values() if not any(f in d["name"] for f in foreign)]
     # a forward starts with the head conv: take the last COMPLETE forward of the capture
     starts = [i for i, d in enumerate(ours) if "head_conv" in d["name"]]
     segs = [(a, b) for a, b in zip(starts, starts[1:]) if b - a == per_step]
