@@ -51,7 +51,7 @@ constexpr int LM_HID_BYTES = 2 * LM_HID_BUF;               // double buffered: P
 constexpr int LM_A2_BYTES = 128 * 128;                     // fc2 A tile: 128 px x 64 ch bf16
 constexpr int LM_I_BYTES = 64 * 128;                       // 64 x 64 bf16 identity
 constexpr int LM_W1K_BYTES = 64 * 128;                     // 64 hidden rows x 64 K
-constexpr int LM_CW = 16;                                  // compute warps
+constexpr int LM_CW = 16;                                  // P2 items per chunk (= compute warps of the first version)
 constexpr int LM_P1W = 6;                                  // of which P1 (fc1 epilogue) warps; the other 10 run P2
 
 struct LmParams {
@@ -71,6 +71,7 @@ struct LmParams {
   int tiles_x, tiles_y, m_tiles, nchunks, nk;
   int x_slots, w_slots, a2_slots;   // powers of two
   int poly;                         // P1: second MMA tile's GELU on the FMA pipe (polynomial) instead of MUFU.TANH
+  int fixed_order;                  // issuer: fc1(g+2), fc2(g) in program order instead of readiness driven
 };
 
 // z = x / 2  ->  GELU_tanh(x)
@@ -129,8 +130,9 @@ __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
 }
 
 // NK = C / 64 (K chunks of fc1 = 64-column slices of the output); POLY: second MMA tile's GELU on the FMA pipe
-template <int NK, bool ERF, bool POLY>
-__global__ void __launch_bounds__(128 + 32 * LM_CW, 1) leff_mlp_kernel(const __grid_constant__ LmParams p) {
+// CW = compute warps: 16 (96 registers per thread; default) or 24 (72 registers: six P1 + eighteen P2 warps -- measured slower)
+template <int NK, bool ERF, bool POLY, int CW>
+__global__ void __launch_bounds__(128 + 32 * CW, 1) leff_mlp_kernel(const __grid_constant__ LmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_block[LB_COUNT];
   __shared__ uint32_t tmem_base_slot;
@@ -173,8 +175,8 @@ __global__ void __launch_bounds__(128 + 32 * LM_CW, 1) leff_mlp_kernel(const __g
       mbar_init(&bar_block[LB_A2_FULL + s], LM_CW); mbar_init(&bar_block[LB_A2_EMPTY + s], 1);
       mbar_init(&bar_block[LB_TM1_FULL + s], 1); mbar_init(&bar_block[LB_TM1_EMPTY + s], LM_P1W);
       mbar_init(&bar_block[LB_TM2_FULL + s], 1); mbar_init(&bar_block[LB_TM2_EMPTY + s], 4);
-      mbar_init(&bar_block[LB_DW_FULL + s], 1); mbar_init(&bar_block[LB_DW_EMPTY + s], LM_CW - LM_P1W);
-      mbar_init(&bar_block[LB_HID_FULL + s], LM_P1W); mbar_init(&bar_block[LB_HID_EMPTY + s], LM_CW - LM_P1W);
+      mbar_init(&bar_block[LB_DW_FULL + s], 1); mbar_init(&bar_block[LB_DW_EMPTY + s], CW - LM_P1W);
+      mbar_init(&bar_block[LB_HID_FULL + s], LM_P1W); mbar_init(&bar_block[LB_HID_EMPTY + s], CW - LM_P1W);
     }
     mbar_init(&bar_block[LB_R_FULL], 1); mbar_init(&bar_block[LB_R_EMPTY], 1);
     fence_barrier_init();
@@ -344,14 +346,32 @@ __global__ void __launch_bounds__(128 + 32 * LM_CW, 1) leff_mlp_kernel(const __g
       ++g2;
       if (++c2 == nchunks) { c2 = 0; ++it2; }
     };
-    // fc1 runs TWO chunks ahead of fc2: the compute warps do P1(g) | P2(g-1) per interval, so fc2(g-1) can only be issued at the end
-    // of interval g; fc1(g+1) must not queue behind it (P1(g+1) needs it at the start of the next interval).  fc1(g+2) reuses the
-    // TMEM buffer P1(g) released early in interval g.
-    if (G > 0) issue_fc1();
-    if (G > 1) issue_fc1();
-    for (uint32_t g = 0; g < G; ++g) {
-      if (g + 2 < G) issue_fc1();
-      issue_fc2();
+    // Issue order is READINESS driven (FBANET_LEFF_ORDER=0: the fixed order fc1(g+2), fc2(g) of the first version).  In program order the
+    // issuer sat in the wait for P2(g-1)'s A tile before it could issue fc1(g+2), although that needs only P1(g)'s TMEM buffer and the W1
+    // slab: P1 then waited for fc1 (11 % of its time, ncu) and P2 for P1 (8 %).  Now whichever of the two next operations has all its
+    // barriers complete is issued first, fc1 preferred (it is at most two chunks ahead: two TMEM buffers).
+    if (p.fixed_order) {
+      if (G > 0) issue_fc1();
+      if (G > 1) issue_fc1();
+      for (uint32_t g = 0; g < G; ++g) {
+        if (g + 2 < G) issue_fc1();
+        issue_fc2();
+      }
+    } else {
+      auto ready_fc1 = [&]() -> bool {
+        const uint32_t xs = it1 & xmask, b = g1 & 1;
+        if (c1 == 0 && !mbar_test_all_a(LBAR(LB_X_FULL + xs), (it1 >> xshift) & 1)) return false;
+        return mbar_test_all_a(LBAR(LB_TM1_EMPTY + b), ((g1 >> 1) & 1) ^ 1) && mbar_test_all_a(LBAR(LB_W1_FULL + b), (g1 >> 1) & 1);
+      };
+      auto ready_fc2 = [&]() -> bool {
+        const uint32_t acc = it2 & 1, as = g2 & amask, ws = g2 & 1;
+        if (c2 == 0 && !mbar_test_all_a(LBAR(LB_TM2_EMPTY + acc), ((it2 >> 1) & 1) ^ 1)) return false;
+        return mbar_test_all_a(LBAR(LB_A2_FULL + as), (g2 >> ashift) & 1) && mbar_test_all_a(LBAR(LB_W2_FULL + ws), (g2 >> 1) & 1);
+      };
+      while (g2 < G) {
+        if (g1 < G && g1 < g2 + 3 && ready_fc1()) issue_fc1();
+        else if (ready_fc2()) issue_fc2();
+      }
     }
   } else {
     // ================= compute warps, specialised =================
@@ -621,19 +641,28 @@ extern "C" int fbanet_leff_mlp_sm100(const fbanet_leff_mlp_params* p, void* stre
   lp.w_slots = 2;
   lp.a2_slots = 2;
   { static const char* e = getenv("FBANET_LEFF_POLY"); lp.poly = (e && e[0] == '1') ? 1 : 0; }
+  { static const char* e = getenv("FBANET_LEFF_ORDER"); lp.fixed_order = (e && e[0] == '0') ? 1 : 0; }
   const size_t smem = (size_t)lp.x_slots * lp.nk * (p->C == 64 ? LM_XK_BYTES : LM_XK_PACKED) + LM_HID_BYTES + (size_t)lp.w_slots * lp.nk * LM_W1K_BYTES +
                       (size_t)lp.w_slots * p->C * 128 + (size_t)lp.a2_slots * LM_A2_BYTES + LM_A2_BYTES + LM_I_BYTES + 1024;
   typedef void (*KernelFn)(const LmParams);
   const bool erf = p->act == FBANET_ACT_GELU_ERF;
+  // experiment switch FBANET_LEFF_WARPS=24: measured slower (dec1 1.579 vs 1.483 ms, profiles/r2_cw_leff_warps_ab.log): the kernel is not
+  // occupancy bound, and at 72 registers the compiler has less room to interleave the GELU / FMA chains
+  static const int cw = [] { const char* e = getenv("FBANET_LEFF_WARPS"); return (e && atoi(e) == 24) ? 24 : 16; }();
   KernelFn fn;
-  if (p->C == 64) fn = erf ? leff_mlp_kernel<1, true, false> : (lp.poly ? leff_mlp_kernel<1, false, true> : leff_mlp_kernel<1, false, false>);
-  else fn = erf ? leff_mlp_kernel<2, true, false> : (lp.poly ? leff_mlp_kernel<2, false, true> : leff_mlp_kernel<2, false, false>);
+  if (cw == 16) {
+    if (p->C == 64) fn = erf ? leff_mlp_kernel<1, true, false, 16> : (lp.poly ? leff_mlp_kernel<1, false, true, 16> : leff_mlp_kernel<1, false, false, 16>);
+    else fn = erf ? leff_mlp_kernel<2, true, false, 16> : (lp.poly ? leff_mlp_kernel<2, false, true, 16> : leff_mlp_kernel<2, false, false, 16>);
+  } else {
+    if (p->C == 64) fn = erf ? leff_mlp_kernel<1, true, false, 24> : (lp.poly ? leff_mlp_kernel<1, false, true, 24> : leff_mlp_kernel<1, false, false, 24>);
+    else fn = erf ? leff_mlp_kernel<2, true, false, 24> : (lp.poly ? leff_mlp_kernel<2, false, true, 24> : leff_mlp_kernel<2, false, false, 24>);
+  }
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { cudaGetLastError(); set_last_error(e); return FBANET_E_LAUNCH; }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = lp.m_tiles < sms ? lp.m_tiles : sms;
-  fn<<<grid, 128 + 32 * LM_CW, smem, (cudaStream_t)stream>>>(lp);
+  fn<<<grid, 128 + 32 * cw, smem, (cudaStream_t)stream>>>(lp);
   return check_launch();
 }
