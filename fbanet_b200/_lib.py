@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBANET_B200_LIB") or os.path.join(_HERE, "csrc", "libfbanet_b200.so")   # env override: A/B two builds in one process tree
-ABI_VERSION = 27
+ABI_VERSION = 28
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -134,7 +134,7 @@ class LeffMlpParams(C.Structure):
         ("bias2", C.c_void_p), ("residual", C.c_void_p), ("out", C.c_void_p),
         ("x_img_stride", C.c_int64), ("res_img_stride", C.c_int64), ("out_img_stride", C.c_int64),
         ("x_ld", C.c_int32), ("res_ld", C.c_int32), ("out_ld", C.c_int32),
-        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("Hd", C.c_int32), ("act", C.c_int32), ("_pad", C.c_int32),
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("Hd", C.c_int32), ("act", C.c_int32), ("w2_f16", C.c_int32),
     ]
 
 

@@ -113,6 +113,37 @@ __device__ __forceinline__ f32x2 gelu_half_poly_f2(f32x2 z) {
   return pack_f2(fmaxf(z0 + z0, 0.f) - q0, fmaxf(z1 + z1, 0.f) - q1);
 }
 
+// ---- fp16 hidden path (H16): the on-chip hidden tile and the fc2 A tile are fp16 (11 significant bits: finer than the bf16 they replace),
+// the depthwise 3x3 and its GELU run on packed HALF2 -- HFMA2 takes the tile's words as they lie (no bf16 -> fp32 unpacking: 48 of a P2
+// item's 236 instructions), and one MUFU.TANH.F16x2 serves two values.  fp16 range: |x| < 65504 for the hidden activations (GELU outputs of
+// LayerNorm-ed inputs; a value beyond it would have been 3 decimal digits in bf16 as well).
+__device__ __forceinline__ uint32_t f2_to_f16x2(f32x2 v) {
+  float lo, hi;
+  unpack_f2(v, lo, hi);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // satfinite: a pre-activation beyond fp16's range stays finite
+  return r;
+}
+__device__ __forceinline__ uint32_t hfma2_(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t hmul2_(uint32_t a, uint32_t b) { uint32_t d; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+// z = x / 2 (two halves)  ->  GELU_tanh(x)
+__device__ __forceinline__ uint32_t gelu_half_h2(uint32_t z, uint32_t A2, uint32_t B2) {
+  uint32_t u = hmul2_(hfma2_(hmul2_(z, z), B2, A2), z), t;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(u));
+  return hfma2_(z, t, z);
+}
+// kind::f16 instruction descriptor with fp16 A and B operands (fp32 accumulate, both K-major, M = 128).  (An fp16 A with a bf16 B is
+// encodable but traps as an illegal instruction on the B200: fc2's weights are therefore passed as fp16 for this path.)
+__device__ __forceinline__ uint32_t make_idesc_f16(int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;                    // c_format = F32
+  d |= 0u << 7;                    // a_format = F16
+  d |= 0u << 10;                   // b_format = F16
+  d |= (uint32_t)(N >> 3) << 17;   // n_dim
+  d |= (uint32_t)(128 >> 4) << 24; // m_dim
+  return d;
+}
+
 // barrier block: one shared array, addressed as base + constant (a pointer per barrier costs an S2R + LEA chain at every use)
 enum : uint32_t {
   LB_X_FULL = 0, LB_X_EMPTY = 2, LB_W1_FULL = 4, LB_W1_EMPTY = 6, LB_W2_FULL = 8, LB_W2_EMPTY = 10, LB_A2_FULL = 12, LB_A2_EMPTY = 14,
@@ -131,7 +162,8 @@ __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
 
 // NK = C / 64 (K chunks of fc1 = 64-column slices of the output); POLY: second MMA tile's GELU on the FMA pipe
 // CW = compute warps: 16 (96 registers per thread; default) or 24 (72 registers: six P1 + eighteen P2 warps -- measured slower)
-template <int NK, bool ERF, bool POLY, int CW>
+// H16: fp16 hidden tile / fc2 A tile with HALF2 depthwise + GELU (tanh flavour only)
+template <int NK, bool ERF, bool POLY, int CW, bool H16>
 __global__ void __launch_bounds__(128 + 32 * CW, 1) leff_mlp_kernel(const __grid_constant__ LmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_block[LB_COUNT];
@@ -275,7 +307,7 @@ __global__ void __launch_bounds__(128 + 32 * CW, 1) leff_mlp_kernel(const __grid
       }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    const uint32_t idesc1 = make_idesc_bf16(64), idesc2 = make_idesc_bf16(C);
+    const uint32_t idesc1 = make_idesc_bf16(64), idesc2 = H16 ? make_idesc_f16(C) : make_idesc_bf16(C);
     const uint64_t desc0 = make_sw128_desc(0);
     const uint32_t sx16 = smem_u32(smem_x) >> 4, sw1_16 = smem_u32(smem_w1) >> 4, sw2_16 = smem_u32(smem_w2) >> 4;
     const uint32_t sa2_16 = smem_u32(smem_a2) >> 4, sr16 = smem_u32(smem_r) >> 4, si16 = smem_u32(smem_i) >> 4;
@@ -429,7 +461,9 @@ __global__ void __launch_bounds__(128 + 32 * CW, 1) leff_mlp_kernel(const __grid
                   if (ERF) { f0 = gelu_half_erf_f2(f0); f1 = gelu_half_erf_f2(f1); }
                   else if (POLY && h == 1) { f0 = gelu_half_poly_f2(f0); f1 = gelu_half_poly_f2(f1); }
                   else { f0 = gelu_half_f2(f0); f1 = gelu_half_f2(f1); }
-                  asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(row + (uint32_t)(h * 64 + j * 8)), "r"(f2_to_bf16x2(f0)), "r"(f2_to_bf16x2(f1)));
+                  // (H16: P1 keeps its GELU in fp32 -- the half2 form was measured no faster here, 1.406 vs 1.390 ms -- and rounds once, to fp16)
+                  if (H16) asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(row + (uint32_t)(h * 64 + j * 8)), "r"(f2_to_f16x2(f0)), "r"(f2_to_f16x2(f1)));
+                  else asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(row + (uint32_t)(h * 64 + j * 8)), "r"(f2_to_bf16x2(f0)), "r"(f2_to_bf16x2(f1)));
                 }
               } else {                                   // outside the image: the depthwise conv pads the hidden map with zeros
 #pragma unroll
@@ -501,11 +535,49 @@ __global__ void __launch_bounds__(128 + 32 * CW, 1) leff_mlp_kernel(const __grid
 #pragma unroll
             for (int t = 0; t < 9; ++t) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(wd[t]) : "r"(dwl + b * (uint32_t)LM_DW_SLOT + (uint32_t)(t * 256)));
             asm volatile("ld.shared.b64 %0, [%1];" : "=l"(bd) : "r"(dwl + b * (uint32_t)LM_DW_SLOT + 9u * 256u));
+            uint32_t wh[9], bh = 0, A2 = 0, B2 = 0;          // H16: the taps / bias of this lane's channel pair as half2
+            if (H16) {
+#pragma unroll
+              for (int t = 0; t < 9; ++t) wh[t] = f2_to_f16x2(wd[t]);
+              bh = f2_to_f16x2(bd);
+              A2 = f2_to_f16x2(pack_f2(2.f * 0.7978845608028654f, 2.f * 0.7978845608028654f));
+              B2 = f2_to_f16x2(pack_f2(8.f * 0.7978845608028654f * 0.044715f, 8.f * 0.7978845608028654f * 0.044715f));
+            }
             mbar_wait_a(LBAR(LB_A2_EMPTY + as), ((g >> ashift) & 1) ^ 1);   // fc2 of the chunk that used this A tile last has retired
 #pragma unroll 1
             while (next < lim) {
               const uint32_t m = next & 15u, cp2 = (m & 3u) * 2u, r4 = (m >> 2) * 4u;   // output columns cp2, cp2+1; rows r4 .. r4+3
               const uint32_t hp = hid0 + b * (uint32_t)LM_HID_BUF + (r4 * LM_HW + cp2) * (uint32_t)LM_HID_ROW + (uint32_t)lane * 4u;
+              // A-tile row of output (r4 + o, cp2 + oc) = (r4 + o) * 8 + cp2 + oc: the swizzle phase is row & 7 = cp2 + oc
+              const uint32_t ab = a2_0 + as * (uint32_t)LM_A2_BYTES + (r4 * LM_TW + cp2) * 128u + ((uint32_t)lane & 3u) * 4u;
+              const uint32_t a0 = ab + ((((uint32_t)lane >> 2) ^ cp2) << 4), a1 = ab + 128u + ((((uint32_t)lane >> 2) ^ (cp2 + 1u)) << 4);
+              if (H16) {
+                uint32_t hacc[4][2];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) { hacc[o][0] = bh; hacc[o][1] = bh; }
+#pragma unroll
+                for (int hr = 0; hr < 6; ++hr) {           // halo rows r4 + hr feed output rows hr - ky
+                  uint32_t hv[4];
+#pragma unroll
+                  for (int hc = 0; hc < 4; ++hc) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hv[hc]) : "r"(hp + (uint32_t)((hr * LM_HW + hc) * LM_HID_ROW)));
+#pragma unroll
+                  for (int ky = 0; ky < 3; ++ky) {
+                    const int o = hr - ky;
+                    if (o >= 0 && o < 4) {
+#pragma unroll
+                      for (int kx = 0; kx < 3; ++kx) {
+                        hacc[o][0] = hfma2_(hv[kx], wh[ky * 3 + kx], hacc[o][0]);
+                        hacc[o][1] = hfma2_(hv[kx + 1], wh[ky * 3 + kx], hacc[o][1]);
+                      }
+                    }
+                  }
+                }
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                  asm volatile("st.shared.b32 [%0], %1;" ::"r"(a0 + (uint32_t)(o * LM_TW * 128)), "r"(gelu_half_h2(hacc[o][0], A2, B2)));
+                  asm volatile("st.shared.b32 [%0], %1;" ::"r"(a1 + (uint32_t)(o * LM_TW * 128)), "r"(gelu_half_h2(hacc[o][1], A2, B2)));
+                }
+              } else {
               f32x2 acc[4][2];
 #pragma unroll
               for (int o = 0; o < 4; ++o) { acc[o][0] = bd; acc[o][1] = bd; }
@@ -530,15 +602,13 @@ __global__ void __launch_bounds__(128 + 32 * CW, 1) leff_mlp_kernel(const __grid
                   }
                 }
               }
-              // A-tile row of output (r4 + o, cp2 + oc) = (r4 + o) * 8 + cp2 + oc: the swizzle phase is row & 7 = cp2 + oc
-              const uint32_t ab = a2_0 + as * (uint32_t)LM_A2_BYTES + (r4 * LM_TW + cp2) * 128u + ((uint32_t)lane & 3u) * 4u;
-              const uint32_t a0 = ab + ((((uint32_t)lane >> 2) ^ cp2) << 4), a1 = ab + 128u + ((((uint32_t)lane >> 2) ^ (cp2 + 1u)) << 4);
 #pragma unroll
               for (int o = 0; o < 4; ++o) {
                 const f32x2 y0 = ERF ? gelu_half_erf_f2(acc[o][0]) : gelu_half_f2(acc[o][0]);
                 const f32x2 y1 = ERF ? gelu_half_erf_f2(acc[o][1]) : gelu_half_f2(acc[o][1]);
                 asm volatile("st.shared.b32 [%0], %1;" ::"r"(a0 + (uint32_t)(o * LM_TW * 128)), "r"(f2_to_bf16x2(y0)));
                 asm volatile("st.shared.b32 [%0], %1;" ::"r"(a1 + (uint32_t)(o * LM_TW * 128)), "r"(f2_to_bf16x2(y1)));
+              }
               }
               fence_proxy_async();                         // A tile written through the generic proxy -> visible to the tensor core
               __syncwarp();
@@ -584,6 +654,7 @@ extern "C" int fbanet_leff_mlp_supported(const fbanet_leff_mlp_params* p) {
   if ((p->x_ld % 8) || (p->x_img_stride % 8) || (p->out_ld % 8) || (p->out_img_stride % 8)) return 0;
   if (p->residual && (((uintptr_t)p->residual % 16) || (p->res_ld % 8) || (p->res_img_stride % 8))) return 0;
   if (p->act != FBANET_ACT_GELU_TANH && p->act != FBANET_ACT_GELU_ERF) return 0;
+  if (p->w2_f16 && p->act != FBANET_ACT_GELU_TANH) return 0;
   return get_encode() != nullptr;
 }
 
@@ -649,13 +720,17 @@ extern "C" int fbanet_leff_mlp_sm100(const fbanet_leff_mlp_params* p, void* stre
   // experiment switch FBANET_LEFF_WARPS=24: measured slower (dec1 1.579 vs 1.483 ms, profiles/r2_cw_leff_warps_ab.log): the kernel is not
   // occupancy bound, and at 72 registers the compiler has less room to interleave the GELU / FMA chains
   static const int cw = [] { const char* e = getenv("FBANET_LEFF_WARPS"); return (e && atoi(e) == 24) ? 24 : 16; }();
+  // w2_f16 (fc2 weights passed as fp16): fp16 hidden tile with HALF2 depthwise arithmetic; else bf16 hidden tile, fp32 (FFMA2) arithmetic
+  const bool h16 = p->w2_f16 != 0;
+  if (h16 && (erf || lp.poly || cw != 16)) return FBANET_E_UNSUPPORTED;
   KernelFn fn;
-  if (cw == 16) {
-    if (p->C == 64) fn = erf ? leff_mlp_kernel<1, true, false, 16> : (lp.poly ? leff_mlp_kernel<1, false, true, 16> : leff_mlp_kernel<1, false, false, 16>);
-    else fn = erf ? leff_mlp_kernel<2, true, false, 16> : (lp.poly ? leff_mlp_kernel<2, false, true, 16> : leff_mlp_kernel<2, false, false, 16>);
+  if (h16) fn = p->C == 64 ? leff_mlp_kernel<1, false, false, 16, true> : leff_mlp_kernel<2, false, false, 16, true>;
+  else if (cw == 16) {
+    if (p->C == 64) fn = erf ? leff_mlp_kernel<1, true, false, 16, false> : (lp.poly ? leff_mlp_kernel<1, false, true, 16, false> : leff_mlp_kernel<1, false, false, 16, false>);
+    else fn = erf ? leff_mlp_kernel<2, true, false, 16, false> : (lp.poly ? leff_mlp_kernel<2, false, true, 16, false> : leff_mlp_kernel<2, false, false, 16, false>);
   } else {
-    if (p->C == 64) fn = erf ? leff_mlp_kernel<1, true, false, 24> : (lp.poly ? leff_mlp_kernel<1, false, true, 24> : leff_mlp_kernel<1, false, false, 24>);
-    else fn = erf ? leff_mlp_kernel<2, true, false, 24> : (lp.poly ? leff_mlp_kernel<2, false, true, 24> : leff_mlp_kernel<2, false, false, 24>);
+    if (p->C == 64) fn = erf ? leff_mlp_kernel<1, true, false, 24, false> : (lp.poly ? leff_mlp_kernel<1, false, true, 24, false> : leff_mlp_kernel<1, false, false, 24, false>);
+    else fn = erf ? leff_mlp_kernel<2, true, false, 24, false> : (lp.poly ? leff_mlp_kernel<2, false, true, 24, false> : leff_mlp_kernel<2, false, false, 24, false>);
   }
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { cudaGetLastError(); set_last_error(e); return FBANET_E_LAUNCH; }

@@ -196,6 +196,9 @@ class BaseModel(nn.Module):
         self.fuse_faf = os.environ.get("FBANET_FUSE_FAF", "1") == "1"
         # dim <= 128 layers: the whole LeFF MLP in one kernel (ops.leff_mlp); FBANET_FUSE_MLP=0 keeps fc1 + leff_fc2
         self.fuse_mlp = os.environ.get("FBANET_FUSE_MLP", "1") == "1"
+        # one-kernel MLP with an fp16 on-chip hidden tile and half2 depthwise / GELU arithmetic (fc2 weights passed as fp16);
+        # FBANET_LEFF_F16=0: bf16 hidden tile, fp32 arithmetic
+        self.leff_f16 = os.environ.get("FBANET_LEFF_F16", "1") == "1"
         # forward(x, homographies=M): FBANET_FUSE_WARP=1 fuses K1 into the head conv's sampling (ops.head_conv(M=): no warp launch, the
         # warped burst never exists in HBM, bit-identical samples).  Measured on cfg3 (64 x 14 x 4 x 80^2, profiles/r2_z_cfg3_warp_fusion.log):
         # fused head conv 0.47 ms against 0.10 ms (warp kernel) + 0.26 ms (head conv) -- the fp64 coordinate arithmetic lands on the
@@ -369,6 +372,9 @@ class BaseModel(nn.Module):
                         P[k + ".fc1.bh"] = (0.5 * f32(ly.mlp.linear1[0].bias)).contiguous()
                         P[k + ".dw.wh"] = (0.5 * P[k + ".dw.w"]).contiguous()
                         P[k + ".dw.bh"] = (0.5 * P[k + ".dw.b"]).contiguous()
+                        if self.leff_f16 and self.gelu_act == L.ACT_GELU_TANH:
+                            # fc2 weights in fp16: selects the kernel's fp16 hidden tile / half2 depthwise path
+                            P[k + ".fc2.w16"] = ly.mlp.linear2[0].weight.detach().to(torch.float16).contiguous()
             put_conv(f"{hg}_downsample_0", getattr(self, f"{hg}_downsample_0").conv[0])
             put_conv(f"{hg}_downsample_1", getattr(self, f"{hg}_downsample_1").conv[0])
             put_convT(f"{hg}_upsample_0", getattr(self, f"{hg}_upsample_0").deconv[0])
@@ -478,7 +484,7 @@ class BaseModel(nn.Module):
                 ln2 = ops.layernorm(x1.view(-1, Cd), P[key + ".ln2.g"], P[key + ".ln2.b"]).view(B, H, W, Cd)
                 if out is None:
                     out = self._new(B, H, W, Cd)
-                if ops.leff_mlp(ln2, P[key + ".fc1.wh"], P[key + ".fc1.bh"], P[key + ".dw.wh"], P[key + ".dw.bh"], P[key + ".fc2.w"],
+                if ops.leff_mlp(ln2, P[key + ".fc1.wh"], P[key + ".fc1.bh"], P[key + ".dw.wh"], P[key + ".dw.bh"], P.get(key + ".fc2.w16", P[key + ".fc2.w"]),
                                 P[key + ".fc2.b"], out, x1, self.gelu_act) is not None:
                     return out
                 h = self._lin(P, key + ".fc1", ln2, act=self.gelu_act)

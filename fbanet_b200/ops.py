@@ -504,15 +504,17 @@ def leff_mlp(x: torch.Tensor, w1h: torch.Tensor, b1h: torch.Tensor, dw_w9c_h: to
     """The whole LeFF MLP in one kernel (bf16): ``out = Linear2(act(depthwise3x3(act(Linear1(x))) + dw_b)) + b2 + residual``
     (``layers/locally_enhanced_feed_forward.py:25-57``); the 4C-channel hidden map never goes to HBM.  ``x`` / ``out`` /
     ``residual``: channels-last views ``[N,H,W,C]``.  ``w1h [Hd,C]`` bf16, ``b1h [Hd]``, ``dw_w9c_h [9,Hd]``, ``dw_bh [Hd]`` hold HALF the
-    layer's values (the kernel's contract, see ``include/fbanet_b200.h``); ``w2 [C,Hd]`` bf16, ``b2 [C]``.  Returns ``None`` when the
-    kernel does not take the shape (C > 128)."""
+    layer's values (the kernel's contract, see ``include/fbanet_b200.h``); ``w2 [C,Hd]`` bf16 -- or fp16, which makes the kernel keep its
+    on-chip hidden tile in fp16 and run the depthwise conv + GELU on packed half2 (tanh GELU only) --, ``b2 [C]``.  Returns ``None`` when
+    the kernel does not take the shape (C > 128)."""
     assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4
     N, H, W, Cc = x.shape
     Hd = w1h.shape[0]
     assert w1h.dtype == torch.bfloat16 and w1h.is_contiguous() and w1h.shape == (Hd, Cc)
-    assert w2.dtype == torch.bfloat16 and w2.is_contiguous() and w2.shape == (Cc, Hd) and out.shape == (N, H, W, Cc)
+    assert w2.dtype in (torch.bfloat16, torch.float16) and w2.is_contiguous() and w2.shape == (Cc, Hd) and out.shape == (N, H, W, Cc)
     assert dw_w9c_h.shape == (9, Hd) and dw_w9c_h.dtype == torch.float32 and dw_w9c_h.is_contiguous()
     p = L.LeffMlpParams()
+    p.w2_f16 = 1 if w2.dtype == torch.float16 else 0   # fp16 fc2 weights select the fp16 hidden tile / half2 depthwise path (tanh GELU)
     p.w1, p.bias1, p.dw_weight, p.dw_bias, p.w2, p.bias2 = (w1h.data_ptr(), b1h.data_ptr(), dw_w9c_h.data_ptr(), dw_bh.data_ptr(), w2.data_ptr(),
                                                           b2.data_ptr())
     xp, _, xld, xis = _cl(x)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 27
+#define FBANET_ABI_VERSION 28
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -299,7 +299,9 @@ typedef struct fbanet_leff_mlp_params {
   int32_t x_ld, res_ld, out_ld;
   int32_t N, H, W, C, Hd;
   int32_t act;            /* FBANET_ACT_GELU_TANH / _ERF (both GELUs)                                */
-  int32_t _pad;
+  int32_t w2_f16;         /* 1: `w2` holds IEEE fp16 (not bf16) and the kernel keeps its on-chip hidden tile and the A operand of
+                             Linear2 in fp16 (11 significant bits instead of bf16's 8; |hidden| < 65504), running the depthwise conv
+                             and its GELU on packed half2 -- tanh GELU only.  x, w1, residual, out stay bf16.               */
 } fbanet_leff_mlp_params;
 
 /* K2 (gate): Federated-Affinity gate (blocks/federated_affinity_fusion.py:79-99).

@@ -246,6 +246,36 @@ def test_fused_leff_mlp_one_kernel(cuda, monkeypatch, C, n, h, w, act, poly):
     _check(out2, ref - res.permute(0, 2, 3, 1), tol=3e-2)
 
 
+@pytest.mark.parametrize("C,n,h,w", [(64, 2, 32, 24), (128, 2, 16, 40), (128, 3, 20, 20), (64, 70, 16, 16), (128, 1, 37, 21), (64, 1, 160, 160), (128, 2, 80, 80)])
+def test_fused_leff_mlp_fp16_hidden_tile(cuda, C, n, h, w):
+    """The one-kernel LeFF MLP with fp16 fc2 weights: the on-chip hidden tile and the A operand of Linear2 are fp16 and the depthwise
+    3x3 + GELU run on packed half2 (HFMA2, MUFU.TANH.F16x2).  Against torch fp32 with the hidden map rounded to fp16 at the same two
+    places; tolerance = the bf16 rounding of the output plus the half2 accumulation of nine taps.  Large pre-activations (|x| up to
+    ~30) exercise the half2 GELU's overflow-to-inf -> tanh = 1 branch."""
+    from fbanet_b200 import ops, _lib as L
+    Hd = 4 * C
+    x = _r(n, C, h, w, seed=1)
+    w1, b1 = _r(Hd, C, seed=2, scale=1 / math.sqrt(C)), _r(Hd, seed=3, scale=0.2)
+    w1[:8] *= 40.0                                                                     # a few channels with huge pre-activations
+    dw, db = _r(Hd, 1, 3, 3, seed=4, scale=0.3), _r(Hd, seed=5, scale=0.1)
+    w2 = ((torch.rand(C, Hd, generator=torch.Generator().manual_seed(6)) * 2 - 1) / math.sqrt(Hd)).half().float()
+    b2 = _r(C, seed=7)
+    res = _r(n, C, h, w, seed=8)
+    gelu = lambda v: F.gelu(v, approximate="tanh")
+    h1 = gelu(F.linear(x.permute(0, 2, 3, 1), w1.to(BF).float(), b1)).permute(0, 3, 1, 2).half().float()
+    mid = gelu(F.conv2d(h1, dw, db, padding=1, groups=Hd)).half().float()
+    ref = F.linear(mid.permute(0, 2, 3, 1), w2, b2) + res.permute(0, 2, 3, 1)
+    out = torch.empty(n, h, w, C, device=cuda, dtype=BF)
+    r = ops.leff_mlp(_nhwc(x, cuda), (0.5 * w1).to(cuda, BF), (0.5 * b1).to(cuda), (0.5 * dw).reshape(Hd, 9).t().contiguous().to(cuda),
+                     (0.5 * db).to(cuda), w2.to(cuda, torch.float16), b2.to(cuda), out, _nhwc(res, cuda), L.ACT_GELU_TANH)
+    assert r is not None
+    torch.cuda.synchronize()
+    got = out.float().cpu()
+    err = (got - ref).abs()
+    assert torch.isfinite(got).all()
+    assert (err <= 3e-2 + 2e-2 * ref.abs()).all(), err.max().item()
+
+
 def test_fused_leff_mlp_refuses_wide_layers(cuda):
     """C = 256 (hidden 1024) does not fit the one-kernel plan (x tile 128 KB): the op says so and the model keeps fc1 + leff_fc2."""
     from fbanet_b200 import ops, _lib as L

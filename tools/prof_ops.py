@@ -95,13 +95,14 @@ def leff(B, S, C):
     return (lambda: ops.leff_fc2(h1, dw, db, w2, b2, out, res, L.ACT_GELU_TANH)), 2 * (h1.numel() + 2 * res.numel()) / 1e9
 
 
-def mlp(B, S, C):
-    """The one-kernel LeFF MLP (ops.leff_mlp) at a stage shape; algorithmic bytes = x in, residual in, out."""
+def mlp(B, S, C, f16=False):
+    """The one-kernel LeFF MLP (ops.leff_mlp) at a stage shape; algorithmic bytes = x in, residual in, out.  f16: fp16 fc2 weights =
+    fp16 hidden tile + half2 depthwise path."""
     Hd = 4 * C
     x = (torch.rand(B, S, S, C, device=dev) - 0.5).to(BF)
     w1, b1 = ((torch.rand(Hd, C, device=dev) - 0.5) * 0.1).to(BF), torch.rand(Hd, device=dev) * 0.1
     dwt, db = (torch.rand(9, Hd, device=dev) - 0.5) * 0.3, torch.rand(Hd, device=dev) * 0.1
-    w2, b2 = ((torch.rand(C, Hd, device=dev) - 0.5) * 0.05).to(BF), torch.zeros(C, device=dev)
+    w2, b2 = ((torch.rand(C, Hd, device=dev) - 0.5) * 0.05).to(torch.float16 if f16 else BF), torch.zeros(C, device=dev)
     res = torch.zeros(B, S, S, C, device=dev, dtype=BF)
     out = torch.empty_like(res)
     return (lambda: ops.leff_mlp(x, w1, b1, dwt, db, w2, b2, out, res, L.ACT_GELU_TANH)), 2 * 3 * res.numel() / 1e9
@@ -118,6 +119,9 @@ def faf_fuse(B, S):
 
 CASES = {
     "faf_fuse_160": lambda: faf_fuse(64, 160),
+    "mlp16_dec1_128": lambda: mlp(64, 160, 128, True),
+    "mlp16_enc1_128": lambda: mlp(64, 80, 128, True),
+    "mlp16_enc0_64": lambda: mlp(64, 160, 64, True),
     "mlp_dec1_128": lambda: mlp(64, 160, 128),
     "mlp_enc1_128": lambda: mlp(64, 80, 128),
     "mlp_enc0_64": lambda: mlp(64, 160, 64),
