@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBANET_B200_LIB") or os.path.join(_HERE, "csrc", "libfbanet_b200.so")   # env override: A/B two builds in one process tree
-ABI_VERSION = 28
+ABI_VERSION = 29
 MAX_SRC = 16
 
 F32, BF16 = 0, 1
@@ -40,7 +40,7 @@ class ConvParams(C.Structure):
         ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32), ("Cout_store", C.c_int32),
         ("act", C.c_int32), ("store_mode", C.c_int32), ("res_ld", C.c_int32), ("out_ld", C.c_int32),
         ("src_s2d", C.c_int32), ("fold_hi_lo", C.c_int32),
-        ("ln_stats", C.c_void_p), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float), ("_pad_ln", C.c_int32),
+        ("ln_stats", C.c_void_p), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float), ("store_f16", C.c_int32),
     ]
 
 
@@ -144,6 +144,7 @@ class LeffFc2Params(C.Structure):
         ("residual", C.c_void_p), ("out", C.c_void_p), ("res_img_stride", C.c_int64), ("out_img_stride", C.c_int64),
         ("res_ld", C.c_int32), ("out_ld", C.c_int32),
         ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("Hd", C.c_int32), ("act", C.c_int32),
+        ("f16", C.c_int32), ("_pad", C.c_int32),
     ]
 
 

@@ -70,6 +70,7 @@ struct TcParams {
   int b_slots, b_resident;
   int tma_store;          // 1: each epilogue warp stages 32x64 bf16 sub-tiles in smem and stores them with TMA
   int stage_bufs;         // staging buffers per epilogue warp (2, or 1 when shared memory is tight)
+  int store_f16;          // staged epilogue: store IEEE fp16 instead of bf16
   int fold;               // tapsum mode: outputs are hi + lo halves (see fbanet_conv_params.fold_hi_lo)
   int tapsum;             // > 0: tap-stacked 3x3 conv with `tapsum` outputs per tap (see the TAPSUM epilogue); tiles step by (tw-2, th-2)
   int step_x, step_y, org;  // tile origin = tile index * step + org (tw, th, 0 except in tapsum mode: tw-2, th-2, -1)
@@ -191,6 +192,12 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
       float t[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) t[e] = f[j + e];
+      if (p.store_f16) {   // IEEE fp16 instead of bf16 (same 2-byte elements)
+        uint4 v;
+        v.x = f2_to_f16x2(pack_f2(t[0], t[1])); v.y = f2_to_f16x2(pack_f2(t[2], t[3]));
+        v.z = f2_to_f16x2(pack_f2(t[4], t[5])); v.w = f2_to_f16x2(pack_f2(t[6], t[7]));
+        *reinterpret_cast<uint4*>(op + j) = v;
+      } else
       store_vec<bf16, 8>(op + j, t);
     }
   }
@@ -830,8 +837,12 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
               f[0] = add_f2(f[0], bf16x2_to_f2(rv.x)); f[1] = add_f2(f[1], bf16x2_to_f2(rv.y));
               f[2] = add_f2(f[2], bf16x2_to_f2(rv.z)); f[3] = add_f2(f[3], bf16x2_to_f2(rv.w));
             }
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(f2_to_bf16x2(f[0])), "r"(f2_to_bf16x2(f[1])),
-                         "r"(f2_to_bf16x2(f[2])), "r"(f2_to_bf16x2(f[3])));
+            if (p.store_f16)
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(f2_to_f16x2(f[0])), "r"(f2_to_f16x2(f[1])),
+                           "r"(f2_to_f16x2(f[2])), "r"(f2_to_f16x2(f[3])));
+            else
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(f2_to_bf16x2(f[0])), "r"(f2_to_bf16x2(f[1])),
+                           "r"(f2_to_bf16x2(f[2])), "r"(f2_to_bf16x2(f[3])));
           }
           fence_proxy_async();                           // generic-proxy smem writes -> visible to the TMA engine
           __syncwarp();
@@ -922,12 +933,13 @@ static int conv_ctot(const fbanet_conv_params* p) {
 // N tile.  3x3 halo convs with a deep K (>= 128 input channels) take full 256-column tiles: the A halo is then fetched once
 // per pixel tile instead of once per 128 output channels and the MMAs run at N = 256 (0.84 -> 0.66 ms on 512->256 @80x80,
 // 1475 TFLOP/s); with a shallow K (the 64->256 tail convs) the longer epilogue per tile is not hidden and 128 stays better.
-static int pick_bn(int cout, bool halo, int ctot) {
+static int pick_bn(int cout, bool halo, int ctot, int64_t pixels) {
   int cap = (halo && ctot < 128) ? 128 : 256;
   // 1x1 GEMMs over 256 input channels: with 256-column tiles the resident weights (128 KB) leave three A slots and one staging buffer
   // per epilogue warp; 192 / 128 columns measured 5-15 % faster (profiles/r2_bn_cap_1x1.log: qkv 256->768 0.213 -> 0.196 ms,
   // proj 256->256 0.130 -> 0.110, fc1 256->1024 0.346 -> 0.326)
-  if (!halo && ctot >= 256) cap = 192;
+  // (at 40^2 x 64 bursts the narrower tiles lose instead: fc1 0.438 -> 0.479 ms -- only for >= 200 k pixels)
+  if (!halo && ctot >= 256 && pixels >= 200000) cap = 192;
   static const char* bnenv = getenv("FBANET_TC_BN");   // experiment switch: cap of the N tile of 1x1 GEMMs (64 / 128 / 192 / 256)
   if (!halo && bnenv) { const int v = atoi(bnenv); if (v >= 64 && v <= 256) cap = v; }
   if (cout <= cap) return cout;
@@ -973,7 +985,7 @@ static bool tc_shape_ok(const fbanet_conv_params* p) {
   const int taps = p->KH * p->KW;
   if (taps * (ctot / TC_BK) > TC_MAX_STEPS) return false;
   if (is_halo(p) && ctot / TC_BK > TC_MAX_CHUNKS) return false;
-  const int bn = pick_bn(p->Cout, is_halo(p), conv_ctot(p));
+  const int bn = pick_bn(p->Cout, is_halo(p), conv_ctot(p), (int64_t)p->N * p->Ho * p->Wo);
   if (bn != 16 && bn != 64 && bn != 128 && bn != 192 && bn != 256) return false;
   if ((uintptr_t)p->weight % 16) return false;
   if (p->store_mode == FBANET_STORE_NHWC || p->store_mode == FBANET_STORE_CONVT2) {
@@ -988,6 +1000,7 @@ static bool tc_shape_ok(const fbanet_conv_params* p) {
   }
   if (p->bias && ((uintptr_t)p->bias % 16)) return false;
   if (p->ln_stats && (p->KH != 1 || p->stride != 1 || p->store_mode != FBANET_STORE_NHWC || ((uintptr_t)p->ln_stats % 8))) return false;
+  if (p->store_f16 && (p->store_mode != FBANET_STORE_NHWC || p->residual)) return false;
   if (p->ln_gamma) {   // LayerNorm of the A tile in shared memory: a 1x1 GEMM over ONE source of 64 / 128 / 256 channels
     if (!p->ln_beta || p->ln_stats || p->KH != 1 || p->stride != 1 || p->nsrc != 1 || p->src_s2d) return false;
     if (ctot != 64 && ctot != 128 && ctot != 256) return false;
@@ -1028,7 +1041,7 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   tp.tiles_y = (p->Ho + tp.step_y - 1) / tp.step_y;
   tp.m_tiles = p->N * tp.tiles_x * tp.tiles_y;
   tp.N = p->N; tp.Ho = p->Ho; tp.Wo = p->Wo;
-  tp.BN = tapsum ? (9 * p->Cout_store + 15) / 16 * 16 : pick_bn(p->Cout, halo, conv_ctot(p));
+  tp.BN = tapsum ? (9 * p->Cout_store + 15) / 16 * 16 : pick_bn(p->Cout, halo, conv_ctot(p), (int64_t)p->N * p->Ho * p->Wo);
   tp.n_tiles_n = tapsum ? 1 : p->Cout / tp.BN;
   tp.Cout = p->Cout; tp.Cout_store = p->Cout_store;
   tp.a_box_bytes = tw * th * TC_BK * 2;
@@ -1117,7 +1130,7 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
     }
   }
   tp.nsteps = ns;
-  tp.ln_gamma = p->ln_gamma; tp.ln_beta = p->ln_beta; tp.ln_eps = p->ln_eps;
+  tp.ln_gamma = p->ln_gamma; tp.ln_beta = p->ln_beta; tp.ln_eps = p->ln_eps; tp.store_f16 = p->store_f16;
   tp.bias = p->bias; tp.alpha = p->alpha; tp.ln_stats = p->ln_stats; tp.residual = reinterpret_cast<const bf16*>(p->residual);
   tp.out = p->out; tp.base = p->base;
   tp.res_img_stride = p->res_img_stride; tp.out_img_stride = p->out_img_stride; tp.base_img_stride = p->base_img_stride;

@@ -44,6 +44,7 @@ struct LeffParams {
   int res_ld, out_ld;
   int N, H, W, C, Hd, act;
   int tiles_x, tiles_y, m_tiles, nchunks, b_slots, r_slots;
+  int f16;            // h1 / W2 / the A tile are fp16, the depthwise producer runs on half2
 };
 
 // LF_DW_WARPS = depthwise/epilogue warps: 16 (4 output rows per thread) or 8 (8 rows per thread)
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(128 + 32 * LF_DW_WARPS, 1) leff_fc2_kernel(con
       }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    const uint32_t idesc = make_idesc_bf16(C);
+    const uint32_t idesc = p.f16 ? make_idesc_f16(C) : make_idesc_bf16(C);
     const uint64_t desc_hi = make_sw128_desc(0);
     const uint32_t sa0 = smem_u32(smem_a), sb0 = smem_u32(smem_b);
     const uint32_t idesc64 = make_idesc_bf16(64);
@@ -274,6 +275,42 @@ __global__ void __launch_bounds__(128 + 32 * LF_DW_WARPS, 1) leff_fc2_kernel(con
           mbar_wait(&h_full[hs], (g / LF_H_SLOTS) & 1);  // halo tile landed
           mbar_wait(&a_empty[as], ((g >> 1) & 1) ^ 1);   // A slot consumed by the MMAs that used it last
           const uint32_t hp = smem_u32(smem_h) + hs * LF_H_SLOT + (r4 * LF_HW + cp2) * 128u + (uint32_t)lane * 4u;
+          // A-tile row of output (r4 + o, cp2 + oc) = (r4 + o) * 8 + cp2 + oc: the swizzle phase is row & 7 = cp2 + oc
+          const uint32_t ab = smem_u32(smem_a) + as * LF_A_BYTES + (r4 * LF_TW + cp2) * 128u + ((uint32_t)lane & 3u) * 4u;
+          const uint32_t a0 = ab + ((((uint32_t)lane >> 2) ^ cp2) << 4), a1 = ab + 128u + ((((uint32_t)lane >> 2) ^ (cp2 + 1u)) << 4);
+          if (p.f16) {   // fp16 hidden map: HFMA2 on the tile's words as they lie, MUFU.TANH.F16x2 (see leff_mlp_tcgen05.cu)
+            uint32_t wh[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) wh[t] = f2_to_f16x2(wd[t]);
+            const uint32_t bh = f2_to_f16x2(bd);
+            const uint32_t A2 = f2_to_f16x2(pack_f2(2.f * 0.7978845608028654f, 2.f * 0.7978845608028654f));
+            const uint32_t B2 = f2_to_f16x2(pack_f2(8.f * 0.7978845608028654f * 0.044715f, 8.f * 0.7978845608028654f * 0.044715f));
+            uint32_t hacc[4][2];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) { hacc[o][0] = bh; hacc[o][1] = bh; }
+#pragma unroll
+            for (int hr = 0; hr < 6; ++hr) {
+              uint32_t hv[4];
+#pragma unroll
+              for (int hc = 0; hc < 4; ++hc) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hv[hc]) : "r"(hp + (uint32_t)((hr * LF_HW + hc) * 128)));
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky) {
+                const int o = hr - ky;
+                if (o >= 0 && o < 4) {
+#pragma unroll
+                  for (int kx = 0; kx < 3; ++kx) {
+                    hacc[o][0] = hfma2_(hv[kx], wh[ky * 3 + kx], hacc[o][0]);
+                    hacc[o][1] = hfma2_(hv[kx + 1], wh[ky * 3 + kx], hacc[o][1]);
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(a0 + (uint32_t)(o * LF_TW * 128)), "r"(gelu_half_h2(hacc[o][0], A2, B2)));
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(a1 + (uint32_t)(o * LF_TW * 128)), "r"(gelu_half_h2(hacc[o][1], A2, B2)));
+            }
+          } else {
           f32x2 acc[4][2];
 #pragma unroll
           for (int o = 0; o < 4; ++o) { acc[o][0] = bd; acc[o][1] = bd; }
@@ -298,9 +335,6 @@ __global__ void __launch_bounds__(128 + 32 * LF_DW_WARPS, 1) leff_fc2_kernel(con
               }
             }
           }
-          // A-tile row of output (r4 + o, cp2 + oc) = (r4 + o) * 8 + cp2 + oc: the swizzle phase is row & 7 = cp2 + oc
-          const uint32_t ab = smem_u32(smem_a) + as * LF_A_BYTES + (r4 * LF_TW + cp2) * 128u + ((uint32_t)lane & 3u) * 4u;
-          const uint32_t a0 = ab + ((((uint32_t)lane >> 2) ^ cp2) << 4), a1 = ab + 128u + ((((uint32_t)lane >> 2) ^ (cp2 + 1u)) << 4);
           auto gelu_half = [](f32x2 z) -> f32x2 {
             const float A = 2.f * 0.7978845608028654f, B = 8.f * 0.7978845608028654f * 0.044715f;
             const f32x2 u = mul_f2(fma_f2(mul_f2(z, z), pack_f2(B, B), pack_f2(A, A)), z);
@@ -314,6 +348,7 @@ __global__ void __launch_bounds__(128 + 32 * LF_DW_WARPS, 1) leff_fc2_kernel(con
           for (int o = 0; o < 4; ++o) {
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(a0 + (uint32_t)(o * LF_TW * 128)), "r"(f2_to_bf16x2(gelu_half(acc[o][0]))));
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(a1 + (uint32_t)(o * LF_TW * 128)), "r"(f2_to_bf16x2(gelu_half(acc[o][1]))));
+          }
           }
         } else {
         // depthwise weights / bias of this thread's 4 channels (L1-resident after the first tile)
@@ -475,6 +510,8 @@ extern "C" int fbanet_leff_fc2_sm100(const fbanet_leff_fc2_params* p, void* stre
   const int grid = lp.m_tiles < sms ? lp.m_tiles : sms;
   static const char* item_env = getenv("FBANET_LEFF_ITEM");   // experiment switch: 0 = the thread-per-column producer everywhere
   const bool item = !w8 && p->act == FBANET_ACT_GELU_TANH && !(item_env && item_env[0] == '0');
+  if (p->f16 && !item) return FBANET_E_UNSUPPORTED;   // the fp16 hidden path lives in the item producer (tanh GELU)
+  lp.f16 = p->f16 ? 1 : 0;
   if (w8) leff_fc2_kernel<8, false><<<grid, 128 + 32 * 8, smem, (cudaStream_t)stream>>>(lp);
   else if (item) leff_fc2_kernel<16, true><<<grid, 128 + 32 * 16, smem, (cudaStream_t)stream>>>(lp);
   else leff_fc2_kernel<16, false><<<grid, 128 + 32 * 16, smem, (cudaStream_t)stream>>>(lp);

@@ -197,4 +197,33 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // the kernel
 // ------------------------------------------------------------------------------------------------
 
+// ---- fp16 / half2 helpers of the fp16 hidden-tile paths (leff_mlp_tcgen05.cu, leff_fc2_tcgen05.cu, fp16 store of conv_gemm_tcgen05.cu)
+__device__ __forceinline__ uint32_t f2_to_f16x2(f32x2 v) {
+  float lo, hi;
+  unpack_f2(v, lo, hi);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // satfinite: a pre-activation beyond fp16's range stays finite
+  return r;
+}
+__device__ __forceinline__ uint32_t hfma2_(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t hmul2_(uint32_t a, uint32_t b) { uint32_t d; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+// z = x / 2 (two halves)  ->  GELU_tanh(x)
+__device__ __forceinline__ uint32_t gelu_half_h2(uint32_t z, uint32_t A2, uint32_t B2) {
+  uint32_t u = hmul2_(hfma2_(hmul2_(z, z), B2, A2), z), t;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(u));
+  return hfma2_(z, t, z);
+}
+// kind::f16 instruction descriptor with fp16 A and B operands (fp32 accumulate, both K-major, M = 128).  (An fp16 A with a bf16 B is
+// encodable but traps as an illegal instruction on the B200: fc2's weights are therefore passed as fp16 for this path.)
+__device__ __forceinline__ uint32_t make_idesc_f16(int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;                    // c_format = F32
+  d |= 0u << 7;                    // a_format = F16
+  d |= 0u << 10;                   // b_format = F16
+  d |= (uint32_t)(N >> 3) << 17;   // n_dim
+  d |= (uint32_t)(128 >> 4) << 24; // m_dim
+  return d;
+}
+
+
 }  // namespace fbanet

@@ -363,6 +363,9 @@ class BaseModel(nn.Module):
                             P[k + ".rpbw"] = ops.expand_rel_pos_bias_wrap(P[k + ".rpbx"], ly.win)
                     put_lin(k + ".proj", a.proj)
                     put_lin(k + ".fc2", ly.mlp.linear2[0])
+                    if tc and self.leff_f16 and self.gelu_act == L.ACT_GELU_TANH and ly.dim > 128:
+                        # dim 256: fc1 stores its GELU output as fp16 and the fused depthwise + fc2 kernel runs on half2 (fp16 fc2 weights)
+                        P[k + ".fc2.w16"] = ly.mlp.linear2[0].weight.detach().to(torch.float16).contiguous()
                     dw = ly.mlp.dwconv[0]
                     P[k + ".dw.w"] = dw.weight.detach().float().reshape(dw.weight.shape[0], 9).t().contiguous()
                     P[k + ".dw.b"] = f32(dw.bias)
@@ -445,7 +448,7 @@ class BaseModel(nn.Module):
             out = self._new(*x4.shape[:3], w.shape[0])
         return ops.conv_gemm([x4], w, out, bias=P[name + ".b"], act=act, residual=residual, impl=self.impl, ln_stats=ln_stats)
 
-    def _ln_lin(self, P, name, lnkey, x4, act=L.ACT_NONE):
+    def _ln_lin(self, P, name, lnkey, x4, act=L.ACT_NONE, out_dtype=None):
         """Linear(LayerNorm(x)): LayerNorm inside the GEMM (ops.conv_gemm(ln=)) when the tensor-core kernel takes the shape,
         else the LayerNorm kernel followed by the GEMM.  Same bits either way."""
         B, H, W, Cd = x4.shape
@@ -453,7 +456,7 @@ class BaseModel(nn.Module):
         w = P[name + ".w"]
         mode = {True: "1", False: "0"}.get(self.ln_in_gemm, self.ln_in_gemm)
         if self._use_tc() and sig not in self._ln_gemm_refused and (mode == "all" or (mode == "1" and w.shape[0] <= 256)):
-            out = self._new(B, H, W, w.shape[0])
+            out = self._new(B, H, W, w.shape[0]) if out_dtype is None else torch.empty((B, H, W, w.shape[0]), device=x4.device, dtype=out_dtype)
             try:
                 return ops.conv_gemm([x4], w, out, bias=P[name + ".b"], act=act, impl=self.impl, ln=(P[lnkey + ".g"], P[lnkey + ".b"]))
             except RuntimeError as e:
@@ -461,7 +464,8 @@ class BaseModel(nn.Module):
                     raise
                 self._ln_gemm_refused.add(sig)
         ln = ops.layernorm(x4.view(-1, Cd), P[lnkey + ".g"], P[lnkey + ".b"]).view(B, H, W, Cd)
-        return self._lin(P, name, ln, act=act)
+        out = None if out_dtype is None else torch.empty((B, H, W, w.shape[0]), device=x4.device, dtype=out_dtype)
+        return self._lin(P, name, ln, out=out, act=act)
 
     def _layer(self, P, key, ly: _Layer, x, out=None):
         """LeWin block (layers/fba_net.py:139-250 with Appendix A-4): x + Attn(LN1 x); + LeFF(LN2 .)."""
@@ -489,13 +493,17 @@ class BaseModel(nn.Module):
                     return out
                 h = self._lin(P, key + ".fc1", ln2, act=self.gelu_act)
             if h is None:   # fc1 as a GEMM (dim 256): norm2 applied inside it
-                h = self._ln_lin(P, key + ".fc1", key + ".ln2", x1, act=self.gelu_act)
+                h = self._ln_lin(P, key + ".fc1", key + ".ln2", x1, act=self.gelu_act,
+                                 out_dtype=torch.float16 if (key + ".fc2.w16") in P and self.fuse_leff else None)
         if self._use_tc() and self.fuse_leff:
             # depthwise 3x3 + GELU computed inside the fc2 GEMM as its A-operand producer (no HBM round trip)
             if out is None:
                 out = self._new(B, H, W, Cd)
-            if ops.leff_fc2(h, P[key + ".dw.w"], P[key + ".dw.b"], P[key + ".fc2.w"], P[key + ".fc2.b"], out, x1, self.gelu_act) is not None:
+            w2 = P[key + ".fc2.w16"] if h.dtype == torch.float16 else P[key + ".fc2.w"]
+            if ops.leff_fc2(h, P[key + ".dw.w"], P[key + ".dw.b"], w2, P[key + ".fc2.b"], out, x1, self.gelu_act) is not None:
                 return out
+        if h.dtype != self.compute_dtype:   # an fp16 hidden map the fused kernel refused: back to the model's dtype for the plain kernels
+            h = h.to(self.compute_dtype)
         h = ops.dwconv3x3(h, P[key + ".dw.w"], P[key + ".dw.b"], self.gelu_act)
         return self._lin(P, key + ".fc2", h, out=out, residual=x1)
 

@@ -177,7 +177,11 @@ def conv_gemm(
         op, _, old, ois = _cl(out)
         p.out, p.out_ld, p.out_img_stride = op, old, ois
     else:
-        assert out.dtype == dt
+        if out.dtype == torch.float16 and dt == torch.bfloat16:   # fp16 store of the staged epilogue (the dim-256 LeFF's hidden map)
+            assert store_mode == L.STORE_NHWC and residual is None
+            p.store_f16 = 1
+        else:
+            assert out.dtype == dt
         if store_mode == L.STORE_NHWC:
             assert out.shape == (N, Ho, Wo, p.Cout_store)
         elif store_mode == L.STORE_PS2:
@@ -479,13 +483,14 @@ def dwconv3x3(x: torch.Tensor, weight9c: torch.Tensor, bias: torch.Tensor, act: 
 def leff_fc2(h1: torch.Tensor, dw_w9c: torch.Tensor, dw_b: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, out: torch.Tensor,
              residual: Optional[torch.Tensor], act: int) -> Optional[torch.Tensor]:
     """Fused LeFF tail (bf16): ``out = Linear2(act(depthwise3x3(h1) + dw_b)) + b2 + residual``.  ``h1`` contiguous
-    ``[N,H,W,Hd]``; ``w2`` ``[C,Hd]`` bf16.  Returns ``None`` when the fused kernel does not take the shape (caller
+    ``[N,H,W,Hd]``; ``w2`` ``[C,Hd]`` bf16 -- or both fp16 (``conv_gemm`` with an fp16 ``out``): half2 depthwise arithmetic.  Returns ``None`` when the fused kernel does not take the shape (caller
     then runs dwconv + GEMM)."""
-    assert h1.is_cuda and h1.is_contiguous() and h1.dtype == torch.bfloat16 and h1.dim() == 4
+    assert h1.is_cuda and h1.is_contiguous() and h1.dtype in (torch.bfloat16, torch.float16) and h1.dim() == 4
     N, H, W, Hd = h1.shape
     Cc = w2.shape[0]
-    assert w2.dtype == torch.bfloat16 and w2.is_contiguous() and w2.shape == (Cc, Hd) and out.shape == (N, H, W, Cc)
+    assert w2.dtype == h1.dtype and w2.is_contiguous() and w2.shape == (Cc, Hd) and out.shape == (N, H, W, Cc)
     p = L.LeffFc2Params()
+    p.f16 = 1 if h1.dtype == torch.float16 else 0   # fp16 hidden map + fp16 fc2 weights: half2 depthwise producer (tanh GELU)
     p.h1, p.dw_weight, p.dw_bias, p.w2, p.bias2 = h1.data_ptr(), dw_w9c.data_ptr(), dw_b.data_ptr(), w2.data_ptr(), b2.data_ptr()
     op, _, old, ois = _cl(out)
     p.out, p.out_ld, p.out_img_stride = op, old, ois

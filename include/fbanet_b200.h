@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FBANET_ABI_VERSION 28
+#define FBANET_ABI_VERSION 29
 
 enum { FBANET_F32 = 0, FBANET_BF16 = 1 };
 
@@ -120,7 +120,8 @@ typedef struct fbanet_conv_params {
   const float* ln_gamma;
   const float* ln_beta;
   float ln_eps;
-  int32_t _pad_ln;
+  int32_t store_f16;      /* 1 (FBANET_STORE_NHWC, tensor-core path): `out` receives IEEE fp16 instead of bf16
+                             (the hidden map of the dim-256 LeFF, consumed by fbanet_leff_fc2_sm100 with f16 = 1); no residual */
 } fbanet_conv_params;
 
 /* K1: homography warp with bilinear sampling.  Replaces cv2.warpPerspective / cv2.warpAffine with
@@ -277,6 +278,9 @@ typedef struct fbanet_leff_fc2_params {
   int32_t res_ld, out_ld;
   int32_t N, H, W, C, Hd;
   int32_t act;            /* FBANET_ACT_GELU_TANH / _ERF (applied after the depthwise conv) */
+  int32_t f16;            /* 1: `h1` and `w2` hold IEEE fp16 (the fc1 GEMM stored its GELU output with fbanet_conv_params.store_f16): the
+                             depthwise conv and its GELU run on packed half2 and the A operand of Linear2 is fp16 (tanh GELU only) */
+  int32_t _pad;
 } fbanet_leff_fc2_params;
 
 /* The whole LeFF MLP in one kernel (bf16, tensor cores), hidden tensor never in HBM:

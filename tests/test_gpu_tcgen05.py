@@ -207,6 +207,34 @@ def test_fused_leff_dwconv_fc2(cuda, C, Hd, n, h, w):
     assert buf[..., :C].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("C,Hd,n,h,w", [(256, 1024, 2, 16, 24), (256, 1024, 1, 37, 21), (128, 512, 2, 20, 20), (256, 1024, 3, 40, 40)])
+def test_fc1_fp16_store_and_fused_leff_tail_on_half2(cuda, C, Hd, n, h, w):
+    """The dim-256 LeFF in fp16: the fc1 GEMM's staged epilogue stores its GELU output as IEEE fp16 (`conv_gemm` with an fp16 `out`) and
+    `leff_fc2` with fp16 h1 / fp16 fc2 weights runs the depthwise conv + GELU on packed half2 with an fp16 A tile.  Against torch fp32
+    with the hidden map rounded to fp16 where the kernels round it."""
+    from fbanet_b200 import ops, _lib as L
+    x = _r(n, C, h, w, seed=1)
+    w1, b1 = _r(Hd, C, seed=2, scale=1 / math.sqrt(C)), _r(Hd, seed=3, scale=0.2)
+    dw, db = _r(Hd, 1, 3, 3, seed=4, scale=0.3), _r(Hd, seed=5, scale=0.1)
+    w2 = ((torch.rand(C, Hd, generator=torch.Generator().manual_seed(6)) * 2 - 1) / math.sqrt(Hd)).half().float()
+    b2, res = _r(C, seed=7), _r(n, C, h, w, seed=8)
+    gelu = lambda v: F.gelu(v, approximate="tanh")
+    h1_ref = gelu(F.linear(x.permute(0, 2, 3, 1), w1, b1)).half()
+    h1 = torch.empty(n, h, w, Hd, device=cuda, dtype=torch.float16)
+    ops.conv_gemm([_nhwc(x, cuda)], w1.to(cuda, BF), h1, bias=b1.to(cuda), act=L.ACT_GELU_TANH, impl=L.IMPL_TCGEN05)
+    e = (h1.float().cpu() - h1_ref.float()).abs()
+    assert (e <= 2e-3 + 4e-3 * h1_ref.float().abs()).all(), e.max().item()      # fp16 rounding + tanh.approx
+    mid = gelu(F.conv2d(h1.float().cpu().permute(0, 3, 1, 2), dw, db, padding=1, groups=Hd)).half().float()
+    ref = F.linear(mid.permute(0, 2, 3, 1), w2, b2) + res.permute(0, 2, 3, 1)
+    out = torch.empty(n, h, w, C, device=cuda, dtype=BF)
+    r = ops.leff_fc2(h1, dw.reshape(Hd, 9).t().contiguous().to(cuda), db.to(cuda), w2.to(cuda, torch.float16), b2.to(cuda), out, _nhwc(res, cuda),
+                     L.ACT_GELU_TANH)
+    assert r is not None
+    got = out.float().cpu()
+    err = (got - ref).abs()
+    assert torch.isfinite(got).all() and (err <= 3e-2 + 2e-2 * ref.abs()).all(), err.max().item()
+
+
 @pytest.mark.parametrize("C,n,h,w,act", [(64, 2, 32, 24, 3), (128, 2, 16, 40, 3), (128, 3, 20, 20, 3), (64, 70, 16, 16, 3), (128, 1, 37, 21, 3),
                                          (64, 1, 160, 160, 3), (128, 2, 80, 80, 3), (64, 2, 24, 16, 4)])
 @pytest.mark.parametrize("poly", [0, 1])

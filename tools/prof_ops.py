@@ -85,11 +85,12 @@ def flow(B, S):
     return (lambda: ops.flow_warp_burst(x, fl)), (2 * x.numel() + fl.numel()) * 4 / 1e9
 
 
-def leff(B, S, C):
+def leff(B, S, C, f16=False):
     Hd = 4 * C
-    h1 = (torch.rand(B, S, S, Hd, device=dev) - 0.5).to(BF)
+    T = torch.float16 if f16 else BF
+    h1 = (torch.rand(B, S, S, Hd, device=dev) - 0.5).to(T)
     dw, db = torch.rand(9, Hd, device=dev) - 0.5, torch.rand(Hd, device=dev)
-    w2, b2 = ((torch.rand(C, Hd, device=dev) - 0.5) * 0.05).to(BF), torch.zeros(C, device=dev)
+    w2, b2 = ((torch.rand(C, Hd, device=dev) - 0.5) * 0.05).to(T), torch.zeros(C, device=dev)
     res = torch.zeros(B, S, S, C, device=dev, dtype=BF)
     out = torch.empty_like(res)
     return (lambda: ops.leff_fc2(h1, dw, db, w2, b2, out, res, L.ACT_GELU_TANH)), 2 * (h1.numel() + 2 * res.numel()) / 1e9
@@ -127,6 +128,7 @@ CASES = {
     "mlp_enc0_64": lambda: mlp(64, 160, 64),
     "leff_dec1_128": lambda: leff(64, 160, 128),
     "leff_dec0_256": lambda: leff(64, 80, 256),
+    "leff16_dec0_256": lambda: leff(64, 80, 256, True),
     "leff_enc0_64": lambda: leff(64, 160, 64),
     "attn_dec1_128x8_s5": lambda: attn(64, 160, 128, 8, 5),
     "attn_dec1_128x8_s0": lambda: attn(64, 160, 128, 8, 0),
