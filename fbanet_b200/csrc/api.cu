@@ -89,7 +89,7 @@ extern "C" int fbanet_conv_gemm_sm100(const fbanet_conv_params* p, void* stream)
   const bool tc_ok = conv_gemm_tc_supported(p) != 0;
   if (p->impl == FBANET_IMPL_TCGEN05 && !tc_ok) return FBANET_E_UNSUPPORTED;
   if (tc_ok && p->impl != FBANET_IMPL_SIMT) return conv_gemm_tc_launch(p, (cudaStream_t)stream);
-  if (p->src_s2d || p->store_mode == FBANET_STORE_NHWC_F32 || p->ln_stats) return FBANET_E_UNSUPPORTED;  // TMA / tensor-core path only
+  if (p->src_s2d || p->store_mode == FBANET_STORE_NHWC_F32 || p->ln_stats || p->ln_gamma || p->store_f16) return FBANET_E_UNSUPPORTED;  // TMA / tensor-core path only
   return conv_gemm_simt_launch(p, (cudaStream_t)stream);
 }
 

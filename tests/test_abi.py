@@ -78,6 +78,22 @@ def test_bad_params_are_rejected_without_a_gpu(lib):
     assert lib.fbanet_window_attention_bwd_sm100(ctypes.byref(t), None) == -1
     assert lib.fbanet_attn_bwd_partial_floats(2, 20, 20, 4, 10) == 2 * 4 * 4 * 361 and lib.fbanet_attn_bwd_partial_floats(1, 12, 10, 1, 10) == -1
     assert lib.fbanet_dwconv_bwd_blocks(0) == -1 and lib.fbanet_faf_gate_bwd_blocks(0) == -1 and lib.fbanet_dwconv_bwd_blocks(9) == 3
+    # round-2 options that exist on the tensor-core path only are refused, not silently dropped, when a problem falls back to the
+    # CUDA-core kernel (fp32 here): LayerNorm inside the GEMM, fp16 store; the fused homography warp of the head conv likewise
+    c = _lib.ConvParams()
+    c.nsrc, c.weight, c.out, c.dtype = 1, 1, 1, 0
+    c.src[0].ptr, c.src[0].C, c.src[0].ld, c.src[0].img_stride = 1, 64, 64, 64 * 64
+    c.N, c.H, c.W, c.KH, c.KW, c.stride, c.pad, c.Ho, c.Wo, c.Cout, c.Cout_store, c.out_ld, c.out_img_stride = 1, 8, 8, 1, 1, 1, 0, 8, 8, 64, 64, 64, 64 * 64
+    c.ln_gamma, c.ln_beta = 1, 1
+    assert lib.fbanet_conv_gemm_sm100(ctypes.byref(c), None) == -5
+    c.ln_gamma, c.ln_beta, c.store_f16 = None, None, 1
+    assert lib.fbanet_conv_gemm_sm100(ctypes.byref(c), None) == -5
+    hc = _lib.HeadConvParams()
+    hc.src, hc.dst, hc.weight, hc.bias, hc.dtype, hc.frames, hc.C, hc.H, hc.W, hc.Cout = 256, 256, 256, 256, 0, 2, 3, 8, 8, 64
+    hc.M, hc.frames_per_burst = 256, 2
+    assert lib.fbanet_head_conv_sm100(ctypes.byref(hc), None) == -5          # fp32 destination: no fused warp
+    hc.frames_per_burst = 0
+    assert lib.fbanet_head_conv_sm100(ctypes.byref(hc), None) == -1
     e = _lib.EccParams()
     e.planes, e.warp, e.frames, e.frames_per_burst, e.H, e.W, e.max_iters = 1, 1, 7, 2, 16, 16, 10   # 7 frames are not whole bursts of 2
     assert lib.fbanet_ecc_homography_sm100(ctypes.byref(e), None) == -1
