@@ -415,6 +415,68 @@ __global__ void __launch_bounds__(256) assemble_f32x8_kernel(const fbanet_assemb
   }
 }
 
+// Four consecutive output pixels per thread (W % 4 == 0): at x4 upsampling the pixels x = 4k .. 4k+3 read base columns k-1, k, k+1 only, so
+// an interior thread loads 3 columns x 2 rows per channel for four outputs (18 cached loads instead of 48), takes the SR columns as
+// 16-byte loads and writes one float4 per channel row; the bilinear weights 0.625 / 0.875 / 0.125 / 0.375 are exact, and the blend keeps
+// assemble_f32x8_kernel's operation order (bit-identical results).  The two edge threads of a row use the per-pixel clamped form.
+// (the one-pixel kernel ran at 2.7-3.0 TB/s: ~65 instructions per pixel, issue bound)
+template <int CP>
+__global__ void __launch_bounds__(160) assemble_f32x8_quad_kernel(const fbanet_assemble_params p) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;   // base column = output quad index
+  const int Hb = p.H >> 2, Wb = p.W >> 2;
+  if (k >= Wb) return;
+  const int y = blockIdx.y, x = 4 * k;
+  float sy = 0.25f * (y + 0.5f) - 0.5f;
+  sy = sy < 0.f ? 0.f : sy;
+  const int yb = (int)sy;
+  const int y1 = yb + (yb < Hb - 1 ? 1 : 0);
+  const float wy = sy - yb, hy = 1.f - wy;
+  const bool interior = k >= 1 && k <= Wb - 2;
+  for (int n = blockIdx.z; n < p.N; n += gridDim.z) {
+    const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.sr) + (((int64_t)n * p.H + y) * p.W + x) * CP);
+    float sr[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 hi = __ldg(s + j * (CP / 4));
+      if (CP == 8) {
+        const float4 lo = __ldg(s + j * 2 + 1);
+        sr[j][0] = hi.x + lo.x; sr[j][1] = hi.y + lo.y; sr[j][2] = hi.z + lo.z; sr[j][3] = hi.w + lo.w;
+      } else { sr[j][0] = hi.x; sr[j][1] = hi.y; sr[j][2] = hi.z; sr[j][3] = hi.w; }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < p.C) {
+        const float* bp = p.base + (int64_t)n * p.base_img_stride + (int64_t)c * Hb * Wb;
+        float o[4];
+        if (interior) {
+          const float* r0 = bp + yb * Wb + k - 1;
+          const float* r1 = bp + y1 * Wb + k - 1;
+          const float a0 = __ldg(r0), a1 = __ldg(r0 + 1), a2 = __ldg(r0 + 2), b0 = __ldg(r1), b1 = __ldg(r1 + 1), b2 = __ldg(r1 + 2);
+          const float wx[4] = {0.625f, 0.875f, 0.125f, 0.375f};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float hx = 1.f - wx[j];
+            const float tl = j < 2 ? a0 : a1, tr = j < 2 ? a1 : a2, bl_ = j < 2 ? b0 : b1, br = j < 2 ? b1 : b2;
+            o[j] = sr[j][c] + (hy * (hx * tl + wx[j] * tr) + wy * (hx * bl_ + wx[j] * br));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float sx = 0.25f * (x + j + 0.5f) - 0.5f;
+            sx = sx < 0.f ? 0.f : sx;
+            const int xb = (int)sx;
+            const int x1 = xb + (xb < Wb - 1 ? 1 : 0);
+            const float wxj = sx - xb, hx = 1.f - wxj;
+            o[j] = sr[j][c] + (hy * (hx * __ldg(bp + yb * Wb + xb) + wxj * __ldg(bp + yb * Wb + x1)) +
+                               wy * (hx * __ldg(bp + y1 * Wb + xb) + wxj * __ldg(bp + y1 * Wb + x1)));
+          }
+        }
+        *reinterpret_cast<float4*>(p.out + (((int64_t)n * p.C + c) * p.H + y) * p.W + x) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
 // channels-last view -> space-to-depth(2), one thread per 16-byte vector of the destination
 template <typename T>
 __global__ void __launch_bounds__(256) s2d_kernel(const fbanet_s2d_params p) {
@@ -1096,6 +1158,15 @@ extern "C" int fbanet_assemble_sm100(const fbanet_assemble_params* p, void* stre
   const int64_t total = (int64_t)p->N * p->H * p->W;
   if (p->dtype == FBANET_F32 && ((p->Cp == 8 && p->lo_offset == 4) || (p->Cp == 4 && p->lo_offset == 0)) && p->C <= 4 && ((uintptr_t)p->sr % 16) == 0 &&
       p->H <= 65535) {
+    static const char* qenv = getenv("FBANET_ASSEMBLE_QUAD");   // experiment switch: 0 = one output pixel per thread
+    if ((p->W % 4) == 0 && p->W >= 16 && ((uintptr_t)p->out % 16) == 0 && !(qenv && qenv[0] == '0')) {
+      const int quads = p->W / 4;
+      const int bt = quads >= 128 ? (quads % 128 == 0 ? 128 : (quads % 160 == 0 ? 160 : 128)) : (quads + 31) / 32 * 32;   // 640 px rows: 160 threads, no idle warps
+      const dim3 gq((unsigned)ceil_div(quads, bt), (unsigned)p->H, (unsigned)(p->N < 65535 ? p->N : 65535));
+      if (p->Cp == 8) assemble_f32x8_quad_kernel<8><<<gq, bt, 0, (cudaStream_t)stream>>>(*p);
+      else assemble_f32x8_quad_kernel<4><<<gq, bt, 0, (cudaStream_t)stream>>>(*p);
+      return check_launch();
+    }
     const dim3 grid((unsigned)ceil_div(p->W, 256), (unsigned)p->H, (unsigned)(p->N < 65535 ? p->N : 65535));
     if (p->Cp == 8) assemble_f32x8_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
     else assemble_f32x8_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);

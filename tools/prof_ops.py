@@ -70,6 +70,13 @@ def head_warp(B, S):
     return (lambda: ops.head_conv(x, w, b, BF, M=M, frames_per_burst=14)), (x.numel() * 4 + B * 14 * S * S * 64 * 2) / 1e9
 
 
+def assemble(B, S):
+    """Final assembly: hi/lo-folded fp32 SR columns [B,4S,4S,4] + bilinear x4 of the planar base frame -> planar fp32 image."""
+    sr = torch.rand(B, 4 * S, 4 * S, 4, device=dev)
+    base = torch.rand(B, 3, S, S, device=dev)
+    return (lambda: ops.assemble(sr, base, 3)), (sr.numel() + 3 * B * 16 * S * S) * 4 / 1e9
+
+
 def warp(B, S):
     x = torch.rand(B, 14, 3, S, S, device=dev)
     M = torch.eye(3, dtype=torch.float64).repeat(B, 14, 1, 1)
@@ -147,6 +154,7 @@ CASES = {
     "head_160": lambda: head(64, 160),
     "head_warp_160": lambda: head_warp(64, 160),
     "warp_160": lambda: warp(64, 160),
+    "assemble_160": lambda: assemble(64, 160),
     "flow_160": lambda: flow(64, 160),
 }
 
