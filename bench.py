@@ -384,40 +384,59 @@ def main():
                 print(f"[breakdown] {t_ms:9.3f} ms {100 * t_ms / tot:5.1f}%  n={n:3d}  {by / t_ms / 1e9 if t_ms else 0:6.2f} TB/s alg  {k}", file=sys.stderr)
 
         # ---- end to end through the public API with HOST buffers (pinned H2D + D2H inside the timed region) ----
+        # headline: the streaming call a loop over batches makes (`infer_host_stream`: every step uploads its own 64 bursts from
+        # pinned host memory and downloads its own SR images into one of two pinned host buffers; the copies of neighbouring
+        # steps overlap the forward).  `e2e_blocking`: one blocking `infer_host` call per step (first upload / last download exposed).
         if args.host_chunk:
             model.host_chunk = args.host_chunk
-        for _ in range(2):
-            model.infer_host(host_in, host_out)
+        host_outs = [host_out, torch.empty_like(host_out).pin_memory()]
+
+        def stream_steps(n, src, dsts, out_dtype):
+            k = 0
+            for _ in model.infer_host_stream((src for _ in range(n)), outs=(dsts[i & 1] for i in range(n)), out_dtype=out_dtype, depth=2):
+                k += 1
+            assert k == n
+
+        stream_steps(max(3, args.warmup), host_in, host_outs, torch.float32)
         barrier()
         h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         h0.record(stream)
-        for _ in range(args.steps):
-            model.infer_host(host_in, host_out)
+        stream_steps(args.steps, host_in, host_outs, torch.float32)   # returns after the last download has landed
         h1.record(stream)
         stream.synchronize()
         barrier()
         ms_e2e = h0.elapsed_time(h1)
 
-        # ---- the same call with the reference's own 8-bit data path: uint8 frames in (normalised on the device, train.py:82-83),
-        # uint8 SR image out (clamp + ToPILImage truncation on the device, test_in_any_resolution.py:93-101) ----
-        host_in_u8 = (host_in * 255.0).to(torch.uint8).pin_memory()
-        host_out_u8 = torch.empty(host_out.shape, dtype=torch.uint8).pin_memory()
         for _ in range(2):
-            model.infer_host(host_in_u8, host_out_u8, out_dtype=torch.uint8)
+            model.infer_host(host_in, host_out)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(stream)
+        for _ in range(args.steps):
+            model.infer_host(host_in, host_out)
+        b1.record(stream)
+        stream.synchronize()
+        barrier()
+        ms_e2e_blocking = b0.elapsed_time(b1)
+
+        # ---- the same streaming call with the reference's own 8-bit data path: uint8 frames in (normalised on the device,
+        # train.py:82-83), uint8 SR image out (clamp + ToPILImage truncation on the device, test_in_any_resolution.py:93-101) ----
+        host_in_u8 = (host_in * 255.0).to(torch.uint8).pin_memory()
+        host_outs_u8 = [torch.empty(host_out.shape, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        stream_steps(3, host_in_u8, host_outs_u8, torch.uint8)
         barrier()
         n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0.record(stream)
-        for _ in range(args.steps):
-            model.infer_host(host_in_u8, host_out_u8, out_dtype=torch.uint8)
+        stream_steps(args.steps, host_in_u8, host_outs_u8, torch.uint8)
         n1.record(stream)
         stream.synchronize()
         barrier()
         ms_e2e_u8 = n0.elapsed_time(n1)
 
-    t = torch.tensor([ms, ms_e2e, ms_e2e_u8], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, ms_e2e, ms_e2e_u8, ms_e2e_blocking], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_e2e_u8 = t.tolist()
+    ms, ms_e2e, ms_e2e_u8, ms_e2e_blocking = t.tolist()
     others, used_graph = None, graph is not None
     if args.other_configs != "none" and args.dtype == "bf16":
         used_graph = graph is not None
@@ -540,7 +559,10 @@ def main():
                    "l2": f"inputs {host_in.numel() * 4 / 1e6:.0f} MB/step + GB-scale activations > 126 MB L2", "cuda_graph": used_graph,
                    "weights": "random init (reference distributions), seed 0"},
         "e2e": {"value": e2e, "unit": "bursts/s", "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
-                "ms_per_step": ms_e2e / args.steps, "host_chunk": model.host_chunk},
+                "ms_per_step": ms_e2e / args.steps, "api": "BaseModel.infer_host_stream (depth 2: one full-batch forward per step, the copies of "
+                "neighbouring steps overlap it; every step's upload and download lie inside the timed region)"},
+        "e2e_blocking": {"value": total_bursts / (ms_e2e_blocking / 1e3), "unit": "bursts/s", "ms_per_step": ms_e2e_blocking / args.steps,
+                         "host_chunk": model.host_chunk, "api": "one blocking BaseModel.infer_host call per step (chunked 3-stream pipeline inside the call)"},
         "e2e_narrow_io": {"value": total_bursts / (ms_e2e_u8 / 1e3), "unit": "bursts/s", "in_dtype": "u8", "out_dtype": "u8",
                           "h2d_bytes_per_step": host_in.numel(), "d2h_bytes_per_step": host_out.numel(), "ms_per_step": ms_e2e_u8 / args.steps,
                           "note": "the reference's own 8-bit data path (uint8 frames / 255 in, clamp * 255 truncated out), conversions on the device; not the headline"},

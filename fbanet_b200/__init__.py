@@ -8,9 +8,9 @@ backward into ``FlatParams`` flat buffers, bucketed gradient all-reduce, fused A
 The per-kernel ops are also registered as ``torch.library`` custom ops (``torch.ops.fbanet.*``, :mod:`fbanet_b200.torch_ops`).
 """
 from . import torch_ops  # noqa: F401  (registers torch.ops.fbanet.*)
-from .model import BaseModel  # noqa: F401
+from .model import BaseModel, HostResult  # noqa: F401
 from .ops import ecc_homography_burst, flow_warp_burst, training_loss, warp_burst  # noqa: F401
 from .utils.model_utils import get_arch, load_checkpoint, load_checkpoint_multigpu, load_optim, load_start_epoch, save_checkpoint  # noqa: F401
 
-__all__ = ["BaseModel", "get_arch", "load_checkpoint", "load_checkpoint_multigpu", "load_start_epoch", "load_optim", "save_checkpoint", "warp_burst",
+__all__ = ["BaseModel", "HostResult", "get_arch", "load_checkpoint", "load_checkpoint_multigpu", "load_start_epoch", "load_optim", "save_checkpoint", "warp_burst",
            "flow_warp_burst", "ecc_homography_burst", "training_loss"]

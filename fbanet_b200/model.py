@@ -145,6 +145,23 @@ def _init_reference_distributions(model: nn.Module, seed: int) -> None:
 # ------------------------------------------------------------------------------------------------
 # the model
 # ------------------------------------------------------------------------------------------------
+class HostResult:
+    """Handle of an asynchronous :meth:`BaseModel.infer_host` call (``wait=False``): ``wait()`` blocks the host until the last
+    download of the call has landed and returns the pinned output tensor; ``done()`` polls."""
+
+    def __init__(self, out: torch.Tensor, event, burst: Optional[torch.Tensor] = None):
+        self.out, self._event, self._burst = out, event, burst   # the (possibly re-pinned) input is kept alive until the copy is done
+
+    def done(self) -> bool:
+        return self._event is None or self._event.query()
+
+    def wait(self) -> torch.Tensor:
+        if self._event is not None:
+            self._event.synchronize()
+            self._event = self._burst = None
+        return self.out
+
+
 class BaseModel(nn.Module):
     """FBANet BaseModel (``FBANetModel``, models/fba_net.py:30-322) on B200.
 
@@ -225,6 +242,9 @@ class BaseModel(nn.Module):
         self._io_streams = None
         self.host_graphs = True    # infer_host replays CUDA graphs (captured per chunk size) instead of launching eagerly
         self._host_graphs = {}
+        self._host_events = {}     # per graph slot: the forward / download that last used its static buffers
+        self._host_pool = None
+        self._host_seq = 0         # chunks submitted so far: consecutive chunks (across calls too) alternate buffer slots
         self.head = nn.Conv2d(in_channels, E, 3, 1, 1)
         self.body = nn.Sequential(_ResBlock(E), _ResBlock(E))
         self.fusion = _FAF(E, num_frames)
@@ -593,8 +613,10 @@ class BaseModel(nn.Module):
 
     # -- forward -----------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward_stages(self, x: torch.Tensor, stages: Optional[dict] = None, homographies: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """The forward; when ``stages`` is a dict every named intermediate (channels-last) is recorded.
+    def forward_stages(self, x: torch.Tensor, stages: Optional[dict] = None, homographies: Optional[torch.Tensor] = None,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The forward; when ``stages`` is a dict every named intermediate (channels-last) is recorded.  ``out``: an existing
+        contiguous fp32 ``[B,C,4S,4S]`` tensor for the result (the static buffers of the host graphs).
 
         ``homographies`` ``[B,T,3,3]`` (dst->src, frame 0 ignored): the burst is unregistered and every frame is warped onto the base
         frame first (``homography_alignment.py:46-55``).  On the tensor-core path the warp is fused into the head conv's sampling
@@ -650,13 +672,15 @@ class BaseModel(nn.Module):
                 t3 = torch.empty((B, 4 * S, 4 * S, 4), device=x.device, dtype=torch.float32)
                 ops.conv_gemm([t2], P["tail.1.wfold"], t3, kh=3, kw=3, pad=1, bias=P["tail.1.b"], store_mode=L.STORE_NHWC_F32,
                               cout_store=2 * Cin, impl=self.impl, fold_hi_lo=True)
-                out = ops.assemble(t3, x[:, 0], Cin, lo_offset=0)
+                out = ops.assemble(t3, x[:, 0], Cin, lo_offset=0, out=out)
             else:
                 t3 = torch.empty((B, 4 * S, 4 * S, 8), device=x.device, dtype=torch.float32)   # columns 0..3 hi-weight part, 4..7 lo-weight part
                 self._conv3(P, "tail.1", [t2], out=t3, store=L.STORE_NHWC_F32, cout_store=8)
-                out = ops.assemble(t3, x[:, 0], Cin, lo_offset=4)
+                out = ops.assemble(t3, x[:, 0], Cin, lo_offset=4, out=out)
         else:
-            out = torch.empty((B, Cin, 4 * S, 4 * S), device=x.device, dtype=torch.float32)
+            if out is None:
+                out = torch.empty((B, Cin, 4 * S, 4 * S), device=x.device, dtype=torch.float32)
+            assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, Cin, 4 * S, 4 * S)
             self._conv3(P, "tail.1", [t2], out=out, store=L.STORE_NCHW_BASE, base=x[:, 0], cout_store=Cin)  # :315-320 (+ bilinear x4 base)
         if st is not None:
             st.update({"output_proj": y1, "output_proj_2": y2, "tail.ps1": t1, "tail.ps2": t2, "out": out})
@@ -684,17 +708,17 @@ class BaseModel(nn.Module):
         """The reference's JAX signature: ``x [F,H,W,C] -> [4H,4W,C]`` (models/fba_net.py:242)."""
         return self.forward(x.permute(0, 3, 1, 2).unsqueeze(0)).squeeze(0).permute(1, 2, 0)
 
-    def _host_io(self, x_in: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    def _host_io(self, x_in: torch.Tensor, out_dtype: torch.dtype, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Forward of one chunk with the narrow-I/O conversions on the device: uint8 frames are normalised (``/ 255``,
         ``train.py:82-83``), the SR image is returned as fp32 (default), fp16, or uint8 (``clamp(0,1) * 255`` truncated -- the
         reference's PNG path, ``test_in_any_resolution.py:93-101``)."""
         x = x_in
         if x_in.dtype == torch.uint8:
             x = ops.convert_io(x_in, torch.empty(x_in.shape, device=x_in.device, dtype=torch.float32))
+        if out_dtype == torch.float32:
+            return self.forward_stages(x, out=dst)
         y = self.forward(x)
-        if out_dtype != torch.float32:
-            y = ops.convert_io(y, torch.empty(y.shape, device=y.device, dtype=out_dtype))
-        return y
+        return ops.convert_io(y, dst if dst is not None else torch.empty(y.shape, device=y.device, dtype=out_dtype))
 
     def _host_graph(self, n: int, slot: int, in_dtype: torch.dtype = torch.float32, out_dtype: torch.dtype = torch.float32):
         """CUDA graph of one forward over ``n`` bursts with static input/output buffers (two slots per size, so consecutive
@@ -709,19 +733,31 @@ class BaseModel(nn.Module):
         self._host_io(x_static, out_dtype)          # eager warm-up: weight packing, kernel attributes, allocator pools
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            y_static = self._host_io(x_static, out_dtype)
+        if self._host_pool is None:   # all host graphs replay on one stream, one after the other: their activations share a pool
+            self._host_pool = torch.cuda.graph_pool_handle()
+        # the result buffer lives OUTSIDE the shared pool: a download still reading it on the copy stream while the next graph
+        # replays must not alias that graph's activations (a pool block is free for every capture that follows the one that freed it)
+        y_static = torch.empty((n, self.in_channels, 4 * self.img_size, 4 * self.img_size), device=dev, dtype=out_dtype)
+        with torch.cuda.graph(g, pool=self._host_pool):
+            self._host_io(x_static, out_dtype, y_static)
         self._host_graphs[key] = (g, x_static, y_static, self._packed_sig)
         return g, x_static, y_static
 
     @torch.no_grad()
-    def infer_host(self, burst: torch.Tensor, out: Optional[torch.Tensor] = None, chunk=None, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    def infer_host(self, burst: torch.Tensor, out: Optional[torch.Tensor] = None, chunk=None, out_dtype: torch.dtype = torch.float32,
+                   wait: bool = True):
         """End-to-end call with HOST buffers: pinned H2D copy, forward, D2H copy of the SR image.
 
         The batch is processed in chunks of ``chunk`` bursts (default ``self.host_chunk``) on three streams, so the H2D copy of
         chunk i+1 and the D2H copy of chunk i-1 overlap the forward of chunk i; only the first upload and the last download
         are exposed.  Each chunk's forward is a CUDA-graph replay over static device buffers (``self.host_graphs``; two
-        buffer sets alternate), captured on first use.  Returns after the last download has completed.
+        buffer sets alternate, across calls as well), captured on first use.  Returns after the last download has completed.
+
+        ``wait=False`` queues the work and returns a :class:`HostResult` at once (``.wait()`` -> the output tensor): the upload
+        of the NEXT call then overlaps this call's forward and this call's download overlaps the next forward, so a loop over
+        batches (:meth:`infer_host_stream`, the shape of the reference's evaluation loop, ``test_in_any_resolution.py:62-101``)
+        is bound by the forward alone.  ``burst`` must be fully written by the host when the call is made and must not be
+        modified, nor ``out`` read, before ``.wait()`` returns.
 
         Narrow I/O (the reference's own data path is 8-bit at both ends): a ``uint8`` ``burst`` is normalised on the device
         (``/ 255``); ``out_dtype = torch.uint8`` returns ``clamp(SR, 0, 1) * 255`` truncated (what the reference writes to PNG),
@@ -738,9 +774,11 @@ class BaseModel(nn.Module):
             out = torch.empty((B, self.in_channels, 4 * self.img_size, 4 * self.img_size), dtype=out_dtype, pin_memory=True)
         assert out.dtype == out_dtype, "the output buffer must have out_dtype"
         if B == 0:
-            return out
-        if chunk is None and burst.dtype == torch.uint8 and out_dtype != torch.float32:
-            chunk = B            # 8-bit copies are ~1 ms each way: one full-batch forward beats two half-batch ones
+            return out if wait else HostResult(out, None, burst)
+        if chunk is None and (not wait or (burst.dtype == torch.uint8 and out_dtype != torch.float32)):
+            # streaming: nothing but the very first upload is exposed, so one full-batch forward beats two half-batch ones;
+            # 8-bit copies are ~1 ms each way: same
+            chunk = B
         chunk = chunk or self.host_chunk
         if isinstance(chunk, int):
             sizes = [max(1, min(B, chunk))] * ((B + max(1, min(B, chunk)) - 1) // max(1, min(B, chunk)))
@@ -757,27 +795,32 @@ class BaseModel(nn.Module):
         comp = torch.cuda.current_stream(dev)
         if self._io_streams is None or self._io_streams[0].device != dev:
             self._io_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            self._host_events = {}
         s_in, s_out = self._io_streams
         if self.host_graphs:   # capture (first use of a chunk size) happens before any copy is queued
-            for k, (a, b) in enumerate(bounds):
-                self._host_graph(b - a, k & 1, burst.dtype, out_dtype)
-        s_in.wait_stream(comp)   # the caller's stream may still be producing / consuming these buffers
-        s_out.wait_stream(comp)
-        ev_comp = [None, None]   # forward that last read slot's input buffer
-        ev_out = [None, None]    # download that last read slot's output buffer
-        for k, (i0, i1) in enumerate(bounds):
-            slot = k & 1
+            for n in sorted({b - a for a, b in bounds}):
+                for slot in (0, 1):
+                    self._host_graph(n, slot, burst.dtype, out_dtype)
+        # the forwards of all calls are ordered on `comp`; the copy streams are tied to it by per-slot events only (NOT by
+        # wait_stream: that would queue this call's upload behind the previous call's forward)
+        if wait:   # a caller who blocks anyway may have queued device work on these host buffers
+            s_in.wait_stream(comp)
+            s_out.wait_stream(comp)
+        for (i0, i1) in bounds:
+            slot = self._host_seq & 1
+            self._host_seq += 1
             if self.host_graphs:
                 g, xs, ys = self._host_graph(i1 - i0, slot, burst.dtype, out_dtype)
+                evs = self._host_events.setdefault((i1 - i0, slot, burst.dtype, out_dtype), [None, None])  # [forward, download] that last used the slot
                 with torch.cuda.stream(s_in):
-                    if ev_comp[slot] is not None:
-                        s_in.wait_event(ev_comp[slot])
+                    if evs[0] is not None:
+                        s_in.wait_event(evs[0])      # the forward that last read this slot's input buffer
                     xs.copy_(burst[i0:i1], non_blocking=True)
                     ev_in = torch.cuda.Event()
                     ev_in.record(s_in)
                 comp.wait_event(ev_in)
-                if ev_out[slot] is not None:
-                    comp.wait_event(ev_out[slot])
+                if evs[1] is not None:
+                    comp.wait_event(evs[1])          # the download that last read this slot's output buffer
                 g.replay()
                 y = ys
             else:
@@ -789,16 +832,46 @@ class BaseModel(nn.Module):
                 xd.record_stream(comp)
                 y = self._host_io(xd, out_dtype)
                 y.record_stream(s_out)
-            ev_comp[slot] = torch.cuda.Event()
-            ev_comp[slot].record(comp)
-            s_out.wait_event(ev_comp[slot])
+            ev_comp = torch.cuda.Event()
+            ev_comp.record(comp)
+            s_out.wait_event(ev_comp)
             with torch.cuda.stream(s_out):
                 out[i0:i1].copy_(y, non_blocking=True)
-                ev_out[slot] = torch.cuda.Event()
-                ev_out[slot].record(s_out)
-        comp.wait_stream(s_out)
-        comp.synchronize()
-        return out
+                ev_out = torch.cuda.Event()
+                ev_out.record(s_out)
+            if self.host_graphs:
+                evs[0], evs[1] = ev_comp, ev_out
+        res = HostResult(out, ev_out, burst)
+        if not wait:
+            return res
+        comp.wait_event(ev_out)
+        return res.wait()
+
+    @torch.no_grad()
+    def infer_host_stream(self, bursts, outs=None, out_dtype: torch.dtype = torch.float32, depth: int = 2):
+        """Generator over an iterable of HOST batches (a data loader): yields each batch's SR image (a pinned host tensor) in
+        order, with ``depth`` batches in flight -- batch k+1 is uploaded and batch k-1 downloaded while batch k is in the
+        forward, so the loop runs at the forward's rate (the reference's evaluation loop reads, runs and writes one burst at
+        a time, ``test_in_any_resolution.py:62-101``).  ``outs``: an optional iterable of output buffers, one per batch;
+        otherwise ``depth + 1`` pinned buffers rotate, i.e. a yielded tensor stays valid until ``depth`` more have been
+        yielded."""
+        depth = max(1, int(depth))
+        outs = iter(outs) if outs is not None else None
+        ring, pending, k = {}, [], 0
+        for burst in bursts:
+            if outs is not None:
+                out = next(outs)
+            else:
+                key = (burst.shape[0], k % (depth + 1))
+                out = ring.get(key)
+                if out is None:
+                    out = ring[key] = torch.empty((burst.shape[0], self.in_channels, 4 * self.img_size, 4 * self.img_size), dtype=out_dtype, pin_memory=True)
+            pending.append(self.infer_host(burst, out, out_dtype=out_dtype, wait=False))
+            k += 1
+            if len(pending) >= depth:
+                yield pending.pop(0).wait()
+        while pending:
+            yield pending.pop(0).wait()
 
     # -- checkpoint compatibility (utils/model_utils.py:28-48) ----------------------------------------
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):

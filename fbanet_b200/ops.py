@@ -284,7 +284,7 @@ def head_conv(x: torch.Tensor, weight_kc: torch.Tensor, bias: torch.Tensor, dtyp
     return out
 
 
-def assemble(sr: torch.Tensor, base: torch.Tensor, C_out: int, lo_offset: int = 0) -> torch.Tensor:
+def assemble(sr: torch.Tensor, base: torch.Tensor, C_out: int, lo_offset: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``out[n,c] = sr[n,:,:,c] + bilinear_x4(base[n,c])``: channels-last SR ``[N,4h,4w,Cp]`` + planar fp32 base
     ``[N,C,h,w]`` (a view of the burst's frame 0) -> planar fp32 ``[N,C,4h,4w]``.  ``lo_offset > 0``: the SR value of channel
     ``c`` is ``sr[..., c] + sr[..., c + lo_offset]`` (the final conv run with hi/lo split weights)."""
@@ -292,7 +292,9 @@ def assemble(sr: torch.Tensor, base: torch.Tensor, C_out: int, lo_offset: int = 
     N, H, W, Cp = sr.shape
     assert base.dtype == torch.float32 and base.shape == (N, C_out, H // 4, W // 4)
     assert base.stride(3) == 1 and base.stride(2) == W // 4 and base.stride(1) == (H // 4) * (W // 4)
-    out = torch.empty((N, C_out, H, W), device=sr.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((N, C_out, H, W), device=sr.device, dtype=torch.float32)
+    assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (N, C_out, H, W)
     p = L.AssembleParams()
     p.sr, p.base, p.out = sr.data_ptr(), base.data_ptr(), out.data_ptr()
     p.base_img_stride = base.stride(0) if N > 1 else 0

@@ -164,6 +164,42 @@ def test_batch_invariance_and_host_api(cuda):
             assert torch.equal(m.infer_host(x, chunk=chunk), full)
 
 
+def test_host_api_streaming(cuda):
+    """Asynchronous host calls (`infer_host(wait=False)` handles, `infer_host_stream` over a loader-like iterable): uploads,
+    forwards and downloads of consecutive batches overlap, the buffer slots alternate across calls -- and every batch still
+    gets exactly its own image, in order, eager and graph-replayed, with ragged batch sizes in the stream."""
+    _, m = _pair(SMALL, "fp32", cuda)
+    batches = [_burst(SMALL, n, seed=20 + i) for i, n in enumerate((2, 2, 2, 3, 2, 1, 2))]
+    want = [m(b.to(cuda)).cpu() for b in batches]
+    for graphs in (True, False):
+        m.host_graphs = graphs
+        # handles: everything queued before anything is waited for
+        outs = [torch.empty_like(w).pin_memory() for w in want]
+        hs = [m.infer_host(b.pin_memory(), o, wait=False) for b, o in zip(batches, outs)]
+        for h, w in zip(reversed(hs), reversed(want)):
+            got = h.wait()
+            assert h.done() and torch.equal(got, w)
+        # generator, own rotating buffers: compare as they are yielded
+        for depth in (1, 2, 3):
+            n = 0
+            for got, w in zip(m.infer_host_stream(batches, depth=depth), want):
+                assert torch.equal(got, w), (graphs, depth, n)
+                n += 1
+            assert n == len(want)
+        # a blocking call between streamed ones, and narrow output
+        h = m.infer_host(batches[0], wait=False)
+        assert torch.equal(m.infer_host(batches[3]), want[3])
+        assert torch.equal(h.wait(), want[0])
+        # (graphs of several sizes / dtypes share one activation pool: a result buffer inside it would be overwritten by the
+        # next replay while its download is still running -- seen as torn uint8 images before the buffers moved out of the pool)
+        for rep in range(3):
+            for depth in (2, 3):
+                u8 = [g.clone() for g in m.infer_host_stream(batches, out_dtype=torch.uint8, depth=depth)]
+                for i, (got, w) in enumerate(zip(u8, want)):
+                    assert torch.equal(got, torch.clamp(w, 0, 1).mul(255).byte()), (graphs, rep, depth, i)
+    assert m.infer_host(batches[0][:0], wait=False).wait().shape[0] == 0
+
+
 def test_host_api_narrow_io(cuda):
     """`infer_host` with the reference's 8-bit data path: uint8 frames are normalised on the device exactly as `x.astype(float32) /
     255.0` (train.py:82-83), a uint8 result is `clamp(SR, 0, 1).mul(255).byte()` (test_in_any_resolution.py:93 + torchvision
