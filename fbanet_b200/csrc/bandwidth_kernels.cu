@@ -179,6 +179,175 @@ __global__ void __launch_bounds__(128) warp_planar4_kernel(const fbanet_warp_par
   }
 }
 
+// Planar layouts, source STAGED IN SHARED MEMORY: one CTA = one 32 x 16 tile of destination pixels.  The projective image of the
+// tile is a convex quadrilateral spanned by the images of its corners (w keeps one sign on the tile, checked), so the taps of all
+// its pixels lie in the corners' bounding box: that box (+ a safety pixel each side, x origin rounded down to a multiple of 4) is
+// copied once with coalesced 16-byte loads, zero-filled outside the image (BORDER_CONSTANT 0), and every pixel takes its four taps
+// per channel from shared memory at IMMEDIATE offsets (+1, +pitch, channel planes): one address per pixel instead of one 64-bit
+// address per tap, no validity flags, no clamps.  warp_planar4_kernel spends ~205 instructions per pixel, most of them on the 16 * CT
+// global tap addresses, and is bound by instruction issue (3.5 TB/s); this form needs ~90.  A lane owns one tile column, four rows:
+// consecutive lanes read consecutive shared-memory words (no bank conflicts) and write full 128-byte lines.
+// A tile whose box does not fit (strong zoom / rotation, w changing sign) gathers from global memory as before.
+// WT_TW = 32 (tile 32 x 16) or 16 (tile 16 x 32, two tile rows per warp step: frames whose width wastes less that way, e.g. W = 80)
+template <int CT, int WT_TW>
+__global__ void __launch_bounds__(128) warp_tile_kernel(const fbanet_warp_params p, const int tiles_x, const int tiles_y) {
+  constexpr int WT_TH = 512 / WT_TW;                       // destination tile rows
+  constexpr int WT_BW = WT_TW + 16, WT_BH = WT_TH + 12;    // staged box (floats per row = pitch, rows)
+  constexpr int RPW = 32 / WT_TW;                          // tile rows one warp covers per step (1 or 2)
+  __shared__ __align__(16) float box[CT][WT_BH][WT_BW];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const unsigned tpf = (unsigned)tiles_x * (unsigned)tiles_y;
+  const unsigned f = blockIdx.x / tpf, tr = blockIdx.x - f * tpf;
+  const int ty = (int)(tr / (unsigned)tiles_x), tx = (int)(tr - (unsigned)ty * (unsigned)tiles_x);
+  const int x0 = tx * WT_TW, y0 = ty * WT_TH;
+  const float* s = p.src + (int64_t)f * p.s_frame;
+  float* d = p.dst + (int64_t)f * p.d_frame;
+  const unsigned sy_ = (unsigned)p.s_y, sc_ = (unsigned)p.s_c, dc_ = (unsigned)p.d_c, dy_ = (unsigned)p.d_y;
+  const int x = x0 + (lane & (WT_TW - 1));                  // this lane's column; rows yb + RPW * k
+  const int yb = y0 + 4 * RPW * wrp + lane / WT_TW;
+  if (f % (unsigned)p.frames_per_burst == 0) {  // base frame: identity (homography_alignment.py:168,179)
+    if (x < p.W) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int y = yb + RPW * k;
+        if (y >= p.H) break;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) d[(unsigned)y * dy_ + (unsigned)x + c * dc_] = __ldg(s + ((unsigned)y * sy_ + (unsigned)x + c * sc_));
+      }
+    }
+    return;
+  }
+  const double* M = p.M + (int64_t)f * 9;
+  const double m0 = __ldg(M + 0), m1 = __ldg(M + 1), m2 = __ldg(M + 2), m3 = __ldg(M + 3), m4 = __ldg(M + 4), m5 = __ldg(M + 5);
+  const double m6 = __ldg(M + 6), m7 = __ldg(M + 7), m8 = __ldg(M + 8);
+  // ---- the staged box, derived by EVERY warp from the tile's four corners (lanes 0..3; exact quotients): no barrier, no broadcast ----
+  int minx4, miny, ncol4, nrow;
+  bool staged;
+  {
+    const int cx = (lane & 1) ? min(x0 + WT_TW, p.W) - 1 : x0, cy = (lane & 2) ? min(y0 + WT_TH, p.H) - 1 : y0;
+    const double X = cx, Y = cy;
+    const double w = fma(m6, X, fma(m7, Y, m8));
+    const double iw = 1.0 / w;
+    double sx = fma(m0, X, fma(m1, Y, m2)) * iw, sy = fma(m3, X, fma(m4, Y, m5)) * iw;
+    const bool fin = fabs(sx) < 1e9 && fabs(sy) < 1e9 && fabs(w) > 1e-300;     // NaN / huge -> not staged
+    const unsigned finm = __ballot_sync(0xffffffffu, fin) & 0xfu, pos = __ballot_sync(0xffffffffu, w > 0.0) & 0xfu;
+    if (!fin) { sx = 0.0; sy = 0.0; }
+    int lox = __double2int_rd(sx), loy = __double2int_rd(sy), hix = lox, hiy = loy;
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+      lox = min(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = max(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+      loy = min(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = max(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+    }
+    lox = __shfl_sync(0xffffffffu, lox, 0); hix = __shfl_sync(0xffffffffu, hix, 0);
+    loy = __shfl_sync(0xffffffffu, loy, 0); hiy = __shfl_sync(0xffffffffu, hiy, 0);
+    lox -= 1; loy -= 1; hix += 2; hiy += 2;                 // the second tap, and a pixel of slack for the last-ulp differences of the shared division
+    minx4 = lox & ~3;                                       // (two's complement: rounds towards -inf)
+    miny = loy;
+    ncol4 = ((hix - minx4) >> 2) + 1; nrow = hiy - loy + 1;
+    staged = finm == 0xfu && (pos == 0xfu || pos == 0u) && ncol4 * 4 <= WT_BW && nrow <= WT_BH;
+  }
+  if (staged) {
+    // 8 rows x 16 vector slots per pass (a box row has at most WT_BW / 4 <= 12 vectors); asynchronous 16-byte copies, zero-filled outside the image
+    const int j = tid & 15, gx = minx4 + 4 * j;
+    const bool inx = (unsigned)gx < (unsigned)p.W;        // W % 4 == 0 and gx % 4 == 0: a vector is inside or outside as a whole
+    if (j < ncol4) {
+      const unsigned sox = (unsigned)min(max(gx, 0), p.W - 4);
+#pragma unroll 1
+      for (int r = tid >> 4; r < nrow; r += 8) {
+        const int gy = miny + r;
+        const unsigned nbytes = (inx && (unsigned)gy < (unsigned)p.H) ? 16u : 0u;
+        const unsigned so = (unsigned)min(max(gy, 0), p.H - 1) * sy_ + sox;
+        const uint32_t dsts = (uint32_t)__cvta_generic_to_shared(&box[0][r][4 * j]);
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dsts + (uint32_t)(c * WT_BH * WT_BW * 4)), "l"(s + (so + (unsigned)c * sc_)), "r"(nbytes)
+                       : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const bool live = x < p.W && yb < p.H;
+  // this lane's four pixels (x, yb + k), computed while the copies are in flight: homogeneous coordinates advance by one fp64 add per
+  // row, one division for the four (Montgomery's trick)
+  const double X = min(x, p.W - 1), Y = min(yb, p.H - 1);
+  const double du = RPW * m1, dv = RPW * m4, dw = RPW * m7;   // (exact: RPW is 1 or 2)
+  double u = fma(m0, X, fma(m1, Y, m2)), v = fma(m3, X, fma(m4, Y, m5));
+  double iwk[4];
+  {
+    const double w0 = fma(m6, X, fma(m7, Y, m8)), w1 = w0 + dw, w2 = w1 + dw, w3 = w2 + dw;
+    const double p01 = w0 * w1, p23 = w2 * w3;
+    const double ip = 1.0 / (p01 * p23);
+    const double i01 = ip * p23, i23 = ip * p01;
+    iwk[0] = i01 * w1; iwk[1] = i01 * w0; iwk[2] = i23 * w3; iwk[3] = i23 * w2;
+  }
+  if (staged) {
+    const uint32_t box0 = (uint32_t)__cvta_generic_to_shared(&box[0][0][0]);
+    uint32_t a[4];
+    float wq[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double sx = u * iwk[k], sy = v * iwk[k];
+      u += du; v += dv;
+      const int xf = __double2int_rd(sx), yf = __double2int_rd(sy);
+      const float ax = (float)(sx - (double)xf), ay = (float)(sy - (double)yf);
+      const float wx0 = 1.f - ax, wy0 = 1.f - ay;
+      wq[k][0] = wy0 * wx0; wq[k][1] = wy0 * ax; wq[k][2] = ay * wx0; wq[k][3] = ay * ax;
+      // inside the box by construction; the clamp only keeps a pathological matrix from reading outside the array
+      const int lx = min(max(xf - minx4, 0), WT_BW - 2), ly = min(max(yf - miny, 0), WT_BH - 2);
+      a[k] = box0 + (uint32_t)(ly * WT_BW + lx) * 4u;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (!live) return;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (yb + RPW * k >= p.H) break;
+      const unsigned dofs = (unsigned)(yb + RPW * k) * dy_ + (unsigned)x;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        float t00, t01, t10, t11;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t00) : "r"(a[k] + (uint32_t)(c * WT_BH * WT_BW * 4)));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t01) : "r"(a[k] + (uint32_t)(c * WT_BH * WT_BW * 4 + 4)));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t10) : "r"(a[k] + (uint32_t)(c * WT_BH * WT_BW * 4 + WT_BW * 4)));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t11) : "r"(a[k] + (uint32_t)(c * WT_BH * WT_BW * 4 + WT_BW * 4 + 4)));
+        float acc = 0.f;                         // same summation order as warp_kernel (an outside tap is a staged zero)
+        acc += wq[k][0] * t00;
+        acc += wq[k][1] * t01;
+        acc += wq[k][2] * t10;
+        acc += wq[k][3] * t11;
+        d[dofs + c * dc_] = acc;
+      }
+    }
+  } else {
+    if (!live) return;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double sx = u * iwk[k], sy = v * iwk[k];
+      u += du; v += dv;
+      if (yb + RPW * k >= p.H) break;
+      const int xf = __double2int_rd(sx), yf = __double2int_rd(sy);
+      const float ax = (float)(sx - (double)xf), ay = (float)(sy - (double)yf);
+      const bool okx0 = (unsigned)xf < (unsigned)p.W, okx1 = (unsigned)xf + 1u < (unsigned)p.W;
+      const bool oky0 = (unsigned)yf < (unsigned)p.H, oky1 = (unsigned)yf + 1u < (unsigned)p.H;
+      const int xc = min(max(xf, -1), p.W), yc = min(max(yf, -1), p.H);
+      const float wx0 = okx0 ? 1.f - ax : 0.f, wx1 = okx1 ? ax : 0.f, wy0 = oky0 ? 1.f - ay : 0.f, wy1 = oky1 ? ay : 0.f;
+      const unsigned xa = (unsigned)min(max(xc, 0), p.W - 1), xb = (unsigned)min(max(xc + 1, 0), p.W - 1);
+      const unsigned ya = (unsigned)min(max(yc, 0), p.H - 1) * sy_, yb2 = (unsigned)min(max(yc + 1, 0), p.H - 1) * sy_;
+      const unsigned dofs = (unsigned)(yb + RPW * k) * dy_ + (unsigned)x;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        const unsigned oc = c * sc_;
+        float acc = 0.f;
+        acc += (wy0 * wx0) * __ldg(s + (ya + xa + oc));
+        acc += (wy0 * wx1) * __ldg(s + (ya + xb + oc));
+        acc += (wy1 * wx0) * __ldg(s + (yb2 + xa + oc));
+        acc += (wy1 * wx1) * __ldg(s + (yb2 + xb + oc));
+        d[dofs + c * dc_] = acc;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // planar fp32 [frames][C][H][W] -> channels-last [frames][H][W][Cp]
 // ------------------------------------------------------------------------------------------------
@@ -1104,6 +1273,23 @@ extern "C" int fbanet_warp_sm100(const fbanet_warp_params* p, void* stream) {
   static const char* p4env = getenv("FBANET_WARP_PLANAR4");   // experiment switch: 0 = one pixel per thread everywhere
   // (one warp per destination row with the lanes on consecutive pixels was tried against the four-pixels-per-thread form: 0.334 vs
   // 0.203 ms -- the kernel is bound by instruction issue, not by L1 wavefronts; profiles/r2_ncu_warp.txt)
+  // shared-memory staged form (default for planar layouts; FBANET_WARP_TILE=0: four adjacent pixels per thread gathering from global memory)
+  static const char* tlenv = getenv("FBANET_WARP_TILE");
+  if (planar4 && !(tlenv && tlenv[0] == '0') && !(p4env && p4env[0] == '0')) {
+    // tile 32 x 16, or 16 x 32 where that covers the frame with fewer idle lanes (W = 80: 5 x 16 instead of 3 x 32)
+    const int64_t cover32 = (int64_t)ceil_div(p->W, 32) * 32 * ceil_div(p->H, 16) * 16, cover16 = (int64_t)ceil_div(p->W, 16) * 16 * ceil_div(p->H, 32) * 32;
+    const int tw = cover16 < cover32 ? 16 : 32;
+    const int tiles_x = ceil_div(p->W, tw), tiles_y = ceil_div(p->H, 512 / tw);
+    const int64_t blocks = (int64_t)tiles_x * tiles_y * p->frames;
+    if (blocks < ((int64_t)1 << 31)) {
+      const cudaStream_t st = (cudaStream_t)stream;
+      if (p->C == 3 && tw == 32) warp_tile_kernel<3, 32><<<(unsigned)blocks, 128, 0, st>>>(*p, tiles_x, tiles_y);
+      else if (p->C == 3) warp_tile_kernel<3, 16><<<(unsigned)blocks, 128, 0, st>>>(*p, tiles_x, tiles_y);
+      else if (tw == 32) warp_tile_kernel<4, 32><<<(unsigned)blocks, 128, 0, st>>>(*p, tiles_x, tiles_y);
+      else warp_tile_kernel<4, 16><<<(unsigned)blocks, 128, 0, st>>>(*p, tiles_x, tiles_y);
+      return check_launch();
+    }
+  }
   if (planar4 && !(p4env && p4env[0] == '0')) {
     const int b4 = ceil_div(total / 4, 128);
     if (p->C == 3) warp_planar4_kernel<3><<<b4, 128, 0, (cudaStream_t)stream>>>(*p);

@@ -395,6 +395,41 @@ def test_warp_matches_float64_oracle(cuda, layout):
             assert np.abs(out[b, t].numpy() - ref).max() < 2e-6
 
 
+@pytest.mark.parametrize("shape", [(3, 48, 160), (4, 80, 80), (3, 20, 36), (4, 33, 64)])
+@pytest.mark.parametrize("kind", ["small", "zoom", "rotate", "horizon"])
+def test_warp_tile_staged_kernel_and_its_fallbacks(cuda, shape, kind):
+    """The planar warp kernel stages the source box of every 32 x 16 (or 16 x 32) destination tile in shared memory; tiles whose box
+    does not fit (zoom, rotation) or whose w changes sign (a horizon inside the frame) gather from global memory instead.  Every
+    family against the float64 oracle, on widths that use either tile shape, ragged edge tiles included."""
+    from fbanet_b200 import ops
+    from oracle.fbanet_oracle import warp_frame
+    Cc, H, W = shape
+    B, T = 2, 4
+    g = np.random.default_rng(11)
+    burst = torch.rand(B, T, Cc, H, W, generator=torch.Generator().manual_seed(3))
+    M = np.tile(np.eye(3), (B, T, 1, 1))
+    for b in range(B):
+        for t in range(1, T):
+            if kind == "small":
+                M[b, t, :2, :2] += g.uniform(-0.01, 0.01, (2, 2)); M[b, t, :2, 2] = g.uniform(-4, 4, 2); M[b, t, 2, :2] = g.uniform(-1e-5, 1e-5, 2)
+            elif kind == "zoom":
+                M[b, t, 0, 0] = M[b, t, 1, 1] = g.uniform(1.5, 2.5); M[b, t, :2, 2] = g.uniform(-20, 5, 2)
+            elif kind == "rotate":
+                a = g.uniform(0.5, 1.2); M[b, t, :2, :2] = [[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]; M[b, t, :2, 2] = g.uniform(0, W / 2, 2)
+            else:   # w = 1 - x / (W/2): changes sign in the middle of the frame
+                M[b, t, 2, 0] = -2.0 / W; M[b, t, :2, 2] = g.uniform(-3, 3, 2)
+    out = ops.warp_burst(burst.to(cuda), torch.from_numpy(M)).cpu()
+    for b in range(B):
+        assert torch.equal(out[b, 0], burst[b, 0])
+        for t in range(1, T):
+            ref = warp_frame(burst[b, t].permute(1, 2, 0).numpy(), M[b, t])
+            got = out[b, t].permute(1, 2, 0).numpy()
+            if kind == "horizon":   # next to the horizon the coordinates are huge and ill conditioned in any arithmetic: compare away from it
+                keep = np.abs(1.0 - 2.0 * np.arange(W) / W) > 0.05
+                ref, got = ref[:, keep], got[:, keep]
+            assert np.abs(got - ref).max() < 2e-6, (b, t, np.abs(got - ref).max())
+
+
 def test_warp_large_frame_coordinates(cuda):
     """fp32 cannot represent 1e-5 px at x ~ 1900; the kernel evaluates coordinates in fp64."""
     from fbanet_b200 import ops

@@ -77,8 +77,8 @@ def assemble(B, S):
     return (lambda: ops.assemble(sr, base, 3)), (sr.numel() + 3 * B * 16 * S * S) * 4 / 1e9
 
 
-def warp(B, S):
-    x = torch.rand(B, 14, 3, S, S, device=dev)
+def warp(B, S, C=3):
+    x = torch.rand(B, 14, C, S, S, device=dev)
     M = torch.eye(3, dtype=torch.float64).repeat(B, 14, 1, 1)
     M[:, 1:, :2, 2] = torch.rand(B, 13, 2, dtype=torch.float64) * 8 - 4
     M[:, 1:, 2, :2] = (torch.rand(B, 13, 2, dtype=torch.float64) - 0.5) * 2e-5
@@ -154,6 +154,7 @@ CASES = {
     "head_160": lambda: head(64, 160),
     "head_warp_160": lambda: head_warp(64, 160),
     "warp_160": lambda: warp(64, 160),
+    "warp_raw80": lambda: warp(64, 80, 4),
     "assemble_160": lambda: assemble(64, 160),
     "flow_160": lambda: flow(64, 160),
 }
