@@ -71,6 +71,7 @@ struct TcParams {
   int tma_store;          // 1: each epilogue warp stages 32x64 bf16 sub-tiles in smem and stores them with TMA
   int stage_bufs;         // staging buffers per epilogue warp (2, or 1 when shared memory is tight)
   int store_f16;          // staged epilogue: store IEEE fp16 instead of bf16
+  int gelu_h2;            // store_f16 + tanh-GELU: the activation runs on packed half2 (bias_s holds bias / 2; see the staged epilogue)
   int fold;               // tapsum mode: outputs are hi + lo halves (see fbanet_conv_params.fold_hi_lo)
   int tapsum;             // > 0: tap-stacked 3x3 conv with `tapsum` outputs per tap (see the TAPSUM epilogue); tiles step by (tw-2, th-2)
   int step_x, step_y, org;  // tile origin = tile index * step + org (tw, th, 0 except in tapsum mode: tw-2, th-2, -1)
@@ -100,6 +101,26 @@ __device__ __forceinline__ void apply_act_vec(float (&f)[NV], const int act, con
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t (&v)[32], const int nc, const int col0, const int img,
                                                const int y, const int x, const float alpha, const float* bias_s,
                                                const uint4* rpre = nullptr, const bool has_ln = false, const float ln_rstd = 1.f) {
+  if (p.gelu_h2) {
+    // fp16 store + tanh-GELU on packed half2: the staged epilogue's arithmetic, operation for operation (bias_s holds bias / 2), so a GEMM
+    // gives the same bits whichever epilogue its shared-memory plan selects (STORE_NHWC, no residual, no folded LayerNorm: launcher)
+    const uint32_t A2 = 0x3E623E62u, B2 = 0x34913491u;             // half2 (2 k0, 2 k0) and (8 k0 k1, 8 k0 k1)
+    bf16* op = reinterpret_cast<bf16*>(p.out) + img * p.out_img_stride + ((int64_t)y * p.Wo + x) * p.out_ld + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (j < nc && col0 + j < p.Cout_store) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + j), b1 = *reinterpret_cast<const float4*>(bias_s + j + 4);
+        const f32x2 bb[4] = {pack_f2(b0.x, b0.y), pack_f2(b0.z, b0.w), pack_f2(b1.x, b1.y), pack_f2(b1.z, b1.w)};
+        uint4 h;
+        uint32_t* hp = reinterpret_cast<uint32_t*>(&h);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          hp[e] = gelu_half_h2(f2_to_f16x2(fma_f2(pack_f2(__uint_as_float(v[j + 2 * e]), __uint_as_float(v[j + 2 * e + 1])), pack_f2(0.5f, 0.5f), bb[e])), A2, B2);
+        *reinterpret_cast<uint4*>(op + j) = h;
+      }
+    }
+    return;
+  }
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = (j < nc) ? __uint_as_float(v[j]) : 0.f;
@@ -457,7 +478,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
   }
   if (warp >= 4) {   // this CTA owns N-tile blockIdx.x % n_tiles_n for its whole life: stage its bias once
     const int i = threadIdx.x - 128;
-    if (i < 256) bias_s[i] = (p.bias && i < (p.tapsum ? p.Cout_store : BN)) ? __ldg(p.bias + (blockIdx.x % p.n_tiles_n) * BN + i) : 0.f;
+    if (i < 256) bias_s[i] = ((p.bias && i < (p.tapsum ? p.Cout_store : BN)) ? __ldg(p.bias + (blockIdx.x % p.n_tiles_n) * BN + i) : 0.f) * (p.gelu_h2 ? 0.5f : 1.f);
   }
   if (LN_SMEM && warp >= 4 + TC_EPI_WARPS)
     for (int j = threadIdx.x - (128 + 32 * TC_EPI_WARPS); j < 64 * p.nsteps; j += 128) { ln_gb[j] = __ldg(p.ln_gamma + j); ln_gb[256 + j] = __ldg(p.ln_beta + j); }
@@ -809,6 +830,19 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
           for (int c = 0; c < 8; ++c) {                  // 8 columns = one 16-byte smem chunk at a time
             const float4 b0 = *reinterpret_cast<const float4*>(bs + c * 8), b1 = *reinterpret_cast<const float4*>(bs + c * 8 + 4);
             f32x2 f[4], bb[4] = {pack_f2(b0.x, b0.y), pack_f2(b0.z, b0.w), pack_f2(b1.x, b1.y), pack_f2(b1.z, b1.w)};
+            const uint32_t saddr = row_addr + (uint32_t)((c ^ r7) << 4);   // SWIZZLE_128B position of chunk c in this row
+            if (!HAS_LN && p.gelu_h2) {
+              // fp16 store + tanh-GELU (the dim-256 LeFF's fc1): z = (acc + bias) / 2 in fp32 (bias_s holds bias / 2), rounded ONCE to fp16,
+              // then GELU(x) = z (1 + tanh(z (2 k0 + 8 k0 k1 z^2))) on packed half2 -- 1 FFMA2 + 1 F2FP + 4 HFMA2/HMUL2 + ONE MUFU.TANH.F16x2 per
+              // pair instead of 6 packed fp32 ops + 2 MUFU.TANH + the pack: this epilogue is what bounds the GEMM (XU and issue slots).
+              const uint32_t A2 = 0x3E623E62u, B2 = 0x34913491u;           // half2 (2 k0, 2 k0) and (8 k0 k1, 8 k0 k1)
+              uint32_t h[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                h[e] = gelu_half_h2(f2_to_f16x2(fma_f2(pack_f2(__uint_as_float(v[c * 8 + 2 * e]), __uint_as_float(v[c * 8 + 2 * e + 1])), pack_f2(0.5f, 0.5f), bb[e])), A2, B2);
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]));
+              continue;
+            }
             if (HAS_LN) {   // folded LayerNorm (row-centred weights): rstd * acc + bias
 #pragma unroll
               for (int e = 0; e < 4; ++e) f[e] = fma_f2(pack_f2(__uint_as_float(v[c * 8 + 2 * e]), __uint_as_float(v[c * 8 + 2 * e + 1])), ln_r2, bb[e]);
@@ -830,7 +864,6 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
                 f[e] = pack_f2(lo, hi);
               }
             }
-            const uint32_t saddr = row_addr + (uint32_t)((c ^ r7) << 4);   // SWIZZLE_128B position of chunk c in this row
             if (has_res) {
               uint4 rv;
               asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(saddr));
@@ -1131,6 +1164,10 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   }
   tp.nsteps = ns;
   tp.ln_gamma = p->ln_gamma; tp.ln_beta = p->ln_beta; tp.ln_eps = p->ln_eps; tp.store_f16 = p->store_f16;
+  {   // FBANET_FC1_GELU_H2=0: the fp32 GELU + one rounding (the first version of the fp16-store epilogue)
+    static const char* e = getenv("FBANET_FC1_GELU_H2");
+    tp.gelu_h2 = (p->store_f16 && p->act == FBANET_ACT_GELU_TANH && !(e && e[0] == '0')) ? 1 : 0;
+  }
   tp.bias = p->bias; tp.alpha = p->alpha; tp.ln_stats = p->ln_stats; tp.residual = reinterpret_cast<const bf16*>(p->residual);
   tp.out = p->out; tp.base = p->base;
   tp.res_img_stride = p->res_img_stride; tp.out_img_stride = p->out_img_stride; tp.base_img_stride = p->base_img_stride;
@@ -1223,6 +1260,7 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
     epi_slots = 2;
   }
   tp.b_resident = p0.resident; tp.a_slots = p0.a_slots; tp.b_slots = p0.b_slots;
+  if (tp.ln_stats) tp.gelu_h2 = 0;   // the half2 GELU is not in the folded-LayerNorm instantiation
   if (ln_smem && tp.a_slots < units + 1) return FBANET_E_UNSUPPORTED;   // the LayerNorm warps hold all K chunks of a tile at once
   { const char* dbg = getenv("FBANET_TC_DEBUG"); tp.debug = dbg ? atoi(dbg) : 0; }
   // accumulator stages in TMEM.  Four (N tiles up to 128) were measured against two on every layer shape and change nothing:

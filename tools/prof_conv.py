@@ -26,6 +26,8 @@ CASES = {
     "fc2_512_128": (64, 160, 160, 512, 128, 1, L.ACT_NONE, True, L.STORE_NHWC),
     "qkv_128_384": (64, 160, 160, 128, 384, 1, L.ACT_NONE, False, L.STORE_NHWC),
     "fc1_256_1024": (64, 80, 80, 256, 1024, 1, L.ACT_GELU_TANH, False, L.STORE_NHWC),
+    "fc1_256_1024_f16": (64, 80, 80, 256, 1024, 1, L.ACT_GELU_TANH, False, L.STORE_NHWC),      # fp16 store (the dim-256 LeFF's hidden map)
+    "fc1_256_1024_40_f16": (64, 40, 40, 256, 1024, 1, L.ACT_GELU_TANH, False, L.STORE_NHWC),
     "qkv_256_768": (64, 80, 80, 256, 768, 1, L.ACT_NONE, False, L.STORE_NHWC),
     "qkv_64_192": (64, 160, 160, 64, 192, 1, L.ACT_NONE, False, L.STORE_NHWC),
     "proj_256_256": (64, 80, 80, 256, 256, 1, L.ACT_NONE, True, L.STORE_NHWC),
@@ -55,7 +57,7 @@ def run_case(name, reps, dev):
     elif store == L.STORE_CONVT2:
         out = torch.empty(N, 2 * H, 2 * W, co // 4, device=dev, dtype=BF)
     else:
-        out = torch.empty(N, H, W, co, device=dev, dtype=BF)
+        out = torch.empty(N, H, W, co, device=dev, dtype=torch.float16 if name.endswith("_f16") else BF)
     r = torch.zeros_like(out) if res else None
 
     def go():
