@@ -67,6 +67,7 @@ struct TcParams {
   int BN, n_tiles_n, Cout, Cout_store;
   int act, store_mode, res_ld, out_ld;
   int a_slots, a_slot_bytes, a_box_bytes;
+  int a_mul;              // box origin = tile origin * a_mul + tap offset: 2 for the stride-2 conv read through element-strided TMA boxes, else 1
   int b_slots, b_resident;
   int tma_store;          // 1: each epilogue warp stages 32x64 bf16 sub-tiles in smem and stores them with TMA
   int stage_bufs;         // staging buffers per epilogue warp (2, or 1 when shared memory is tight)
@@ -499,7 +500,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
     // ================= A producer (TMA); warp-uniform loop, one elected lane issues =================
     int slot = 0;
     uint32_t phase = 0;
-    const int halo = p.halo, a_slots = p.a_slots, step_x = p.step_x, step_y = p.step_y, org = p.org, m_tiles = p.m_tiles;
+    const int halo = p.halo, a_slots = p.a_slots, step_x = p.step_x, step_y = p.step_y, org = p.org, m_tiles = p.m_tiles, a_mul = p.a_mul;
     const uint32_t a_slot_bytes = (uint32_t)p.a_slot_bytes, a_box_bytes = (uint32_t)p.a_box_bytes;
     const bool noload = (p.debug & 4) != 0;
     const uint32_t bar_ae = smem_u32(&a_empty[0]);
@@ -527,7 +528,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
           } else {
             const KStep ks = p.steps[u];
             mbar_expect_tx(afull, a_box_bytes);
-            tma_load_4d(sa, &p.amap[ks.src], afull, ks.c0, x0 + ks.dx, y0 + ks.dy, img);
+            tma_load_4d(sa, &p.amap[ks.src], afull, ks.c0, x0 * a_mul + ks.dx, y0 * a_mul + ks.dy, img);
           }
         }
         __syncwarp();
@@ -1004,7 +1005,9 @@ static bool tc_shape_ok(const fbanet_conv_params* p) {
   if (p->store_mode == FBANET_STORE_PS2) return false;
   const bool s1 = p->stride == 1 && p->KH == p->KW && (p->KH == 1 || p->KH == 3) && p->pad == p->KH / 2;
   const bool s2d = p->src_s2d && p->stride == 2 && p->KH == 4 && p->KW == 4 && p->pad == 1;
-  if (!s1 && !s2d) return false;
+  // 4x4 stride-2 conv straight from the full-resolution source: every tap is a TMA box that steps two pixels (elementStrides {1,2,2,1})
+  const bool s2 = !p->src_s2d && p->stride == 2 && p->KH == 4 && p->KW == 4 && p->pad == 1 && !(p->H & 1) && !(p->W & 1);
+  if (!s1 && !s2d && !s2) return false;
   if (p->src_s2d && !s2d) return false;
   int ctot = 0;
   for (int s = 0; s < p->nsrc; ++s) {
@@ -1062,8 +1065,10 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   if (fold && !tapsum) return FBANET_E_UNSUPPORTED;
   const bool halo = is_halo(p) && !tapsum;
   // tile space = output pixels; for s2d sources the source view already has the output resolution
-  const int Hs = s2d ? p->H / 2 : p->H, Ws = s2d ? p->W / 2 : p->W;
-  if (Hs != p->Ho || Ws != p->Wo) return FBANET_E_BADSHAPE;
+  const bool s2 = !s2d && p->stride == 2;   // element-strided boxes on the full-resolution source
+  const int Hs = s2d ? p->H / 2 : p->H, Ws = s2d ? p->W / 2 : p->W;   // source view the tensor maps describe
+  if ((s2 ? Hs / 2 : Hs) != p->Ho || (s2 ? Ws / 2 : Ws) != p->Wo) return FBANET_E_BADSHAPE;
+  tp.a_mul = s2 ? 2 : 1;
   int tw = 16, th = 8;
   if (halo) { tw = TC_HALO_TW; th = TC_HALO_TH; } else if (tapsum) { tw = 16; th = 8; } else pick_tile(p->Ho, p->Wo, &tw, &th);
   tp.tw = tw; tp.th = th;
@@ -1093,8 +1098,9 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
     const fbanet_src& S = p->src[s];
     const cuuint64_t dims[4] = {(cuuint64_t)S.C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)p->N};
     const cuuint64_t strides[3] = {(cuuint64_t)S.ld * 2, (cuuint64_t)S.ld * 2 * Ws, (cuuint64_t)S.img_stride * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(halo_mode >= 2 ? 16 : tw), (cuuint32_t)(halo ? th + 2 : th), 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    // (with elementStrides e the box is given in UNSTRIDED elements and ceil(box / e) of them land in shared memory -- tools/ubench/tma_stride.cu)
+    const cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(halo_mode >= 2 ? 16 : (s2 ? 2 * tw : tw)), (cuuint32_t)(halo ? th + 2 : (s2 ? 2 * th : th)), 1};
+    const cuuint32_t estr[4] = {1, s2 ? 2u : 1u, s2 ? 2u : 1u, 1};
     CUresult r = encode(&tp.amap[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(S.ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -216,6 +216,7 @@ class BaseModel(nn.Module):
         # one-kernel MLP with an fp16 on-chip hidden tile and half2 depthwise / GELU arithmetic (fc2 weights passed as fp16);
         # FBANET_LEFF_F16=0: bf16 hidden tile, fp32 arithmetic
         self.leff_f16 = os.environ.get("FBANET_LEFF_F16", "1") == "1"
+        self.down_s2d = os.environ.get("FBANET_DOWN_S2D", "0") == "1"   # 4x4 s2 downsample through a space-to-depth copy (the first form)
         # forward(x, homographies=M): FBANET_FUSE_WARP=1 fuses K1 into the head conv's sampling (ops.head_conv(M=): no warp launch, the
         # warped burst never exists in HBM, bit-identical samples).  Measured on cfg3 (64 x 14 x 4 x 80^2, profiles/r2_z_cfg3_warp_fusion.log):
         # fused head conv 0.47 ms against 0.10 ms (warp kernel) + 0.26 ms (head conv) -- the fp64 coordinate arithmetic lands on the
@@ -453,9 +454,10 @@ class BaseModel(nn.Module):
         w = P[name + ".w"]
         if out is None:
             out = self._new(N, H // 2, W // 2, w.shape[0])
-        if self._use_tc():  # TMA cannot stride: feed the 4x4 s2 conv a space-to-depth view
+        if self._use_tc() and (self.down_s2d or (H | W) & 1):  # first form: the 4x4 s2 conv on a space-to-depth copy of its input
             return ops.conv_gemm([ops.space_to_depth(x)], w, out, kh=4, kw=4, stride=2, pad=1, bias=P[name + ".b"], impl=self.impl,
                                  src_s2d=True)
+        # tensor-core path: every tap is a TMA box stepping two pixels (element strides) on x itself -- no copy pass
         return ops.conv_gemm([x], w, out, kh=4, kw=4, stride=2, pad=1, bias=P[name + ".b"], impl=self.impl)
 
     def _up(self, P, name, x, out):

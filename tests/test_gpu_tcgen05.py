@@ -104,6 +104,25 @@ def test_tc_downsample_space_to_depth(cuda, cin, cout, hw):
     _check(out.permute(0, 3, 1, 2), ref)
 
 
+@pytest.mark.parametrize("cin,cout,h,w,n", [(64, 128, 32, 32, 2), (128, 256, 16, 16, 2), (64, 128, 160, 160, 2), (64, 128, 20, 44, 3), (128, 256, 6, 10, 1), (64, 64, 2, 2, 2)])
+def test_tc_downsample_element_strided_boxes(cuda, cin, cout, h, w, n):
+    """The 4x4 stride-2 downsample conv straight from its full-resolution input: every tap is a TMA box that steps two pixels
+    (elementStrides {1,2,2,1}; layers/downsample.py) -- no space-to-depth copy.  Strided source view inside a concat buffer, ragged
+    tiles, and the same bits as the space-to-depth form (same MMAs on the same operands in the same order)."""
+    from fbanet_b200 import ops, _lib as L
+    x, wt, b = _r(n, cin, h, w, seed=1), _r(cout, cin, 4, 4, seed=2, scale=1 / math.sqrt(16 * cin)), _r(cout, seed=3)
+    ref = F.conv2d(x, wt, b, stride=2, padding=1)
+    wide = torch.zeros(n, h, w, 2 * cin, device=cuda, dtype=BF)
+    wide[..., cin:] = _nhwc(x, cuda)
+    src = wide[..., cin:]
+    out = torch.empty(n, h // 2, w // 2, cout, device=cuda, dtype=BF)
+    ops.conv_gemm([src], _pack(wt, cuda), out, kh=4, kw=4, stride=2, pad=1, bias=b.to(cuda), impl=L.IMPL_TCGEN05)
+    _check(out.permute(0, 3, 1, 2), ref)
+    out2 = torch.empty_like(out)
+    ops.conv_gemm([ops.space_to_depth(src)], _pack(wt, cuda), out2, kh=4, kw=4, stride=2, pad=1, bias=b.to(cuda), src_s2d=True, impl=L.IMPL_TCGEN05)
+    assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("cin,ct,h,w,n", [(64, 2, 160, 160, 2), (64, 1, 13, 29, 3), (128, 3, 40, 22, 2), (64, 4, 6, 14, 1), (192, 2, 7, 15, 2)])
 def test_tc_tapsum_conv3x3(cuda, cin, ct, h, w, n):
     """3x3 convs with <= 4 fp32 outputs run tap-stacked (nine taps along N, shifted sum in the epilogue): must equal the plain
