@@ -65,6 +65,8 @@ struct TcParams {
   int N, Ho, Wo;          // tile space == output pixels
   int tw, th, tiles_x, tiles_y, m_tiles;
   int BN, n_tiles_n, Cout, Cout_store;
+  int n_inner;            // N tiles one CTA computes per A tile (A-stationary; 1 = each CTA owns one N tile).  > 1: n_tiles_n is 1, all
+                          // n_inner * nsteps weight slabs are resident, an A tile's slots are released after its last N tile
   int act, store_mode, res_ld, out_ld;
   int a_slots, a_slot_bytes, a_box_bytes;
   int a_mul;              // box origin = tile origin * a_mul + tap offset: 2 for the stride-2 conv read through element-strided TMA boxes, else 1
@@ -240,7 +242,7 @@ __device__ __forceinline__ void mma_loop_resident(const int mt0, const int mt_st
                                                   const uint32_t a_slot16, const uint32_t sa16_0, const uint32_t sb16_0, const uint32_t bstep16,
                                                   const uint32_t tmem_base, const uint32_t BN, const uint32_t idesc, const uint32_t bar_af,
                                                   const uint32_t bar_ae, const uint32_t bar_tf, const uint32_t bar_te, const bool nomma, const uint32_t nacc_mask,
-                                                  const uint32_t nacc_shift) {
+                                                  const uint32_t nacc_shift, const int n_inner = 1) {
   const uint64_t desc_b = make_sw128_desc(0);        // descriptor with a zero start address
   const uint64_t desc_a = HALO >= 2 ? ((desc_b & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)(TC_HALO_WROW >> 4) << 32)) : desc_b;   // wide: 2 KB between atoms
   constexpr uint32_t A_START = HALO >= 2 ? (3u * 128u) >> 4 : 0u;
@@ -248,11 +250,15 @@ __device__ __forceinline__ void mma_loop_resident(const int mt0, const int mt_st
   int aslot = 0;
   uint32_t aphase = 0, sa16 = sa16_0;
   int it = 0;
-  for (int mt = mt0; mt < m_tiles; mt += mt_step, ++it) {
+  for (int mt = mt0; mt < m_tiles; mt += mt_step)
+  for (int ni = 0; ni < n_inner; ++ni, ++it) {       // A-stationary: the tile's A slots serve n_inner N tiles (weight slabs ni * units ..)
     const uint32_t acc = (uint32_t)it & nacc_mask;
     mbar_wait_a(bar_te + acc * 8u, (((uint32_t)it >> nacc_shift) & 1u) ^ 1u);     // epilogue has drained this accumulator
     const uint32_t tmem_d = tmem_base + acc * BN;
-    uint32_t b16 = sb16_0;
+    uint32_t b16 = sb16_0 + (uint32_t)(ni * units) * bstep16;
+    const int aslot0 = aslot;
+    const uint32_t aphase0 = aphase, sa16_t = sa16;
+    const bool last_n = ni == n_inner - 1;
     for (int u = 0; u < units; ++u) {
       mbar_wait_a(bar_af + (uint32_t)aslot * 8u, aphase);
       tc_fence_after();
@@ -278,13 +284,14 @@ __device__ __forceinline__ void mma_loop_resident(const int mt0, const int mt_st
         }
       }
       if (elect_one()) {
-        umma_commit_a(bar_ae + (uint32_t)aslot * 8u);                     // frees the A slot when these MMAs retire
+        if (last_n) umma_commit_a(bar_ae + (uint32_t)aslot * 8u);         // frees the A slot when these MMAs retire
         if (u == units - 1) umma_commit_a(bar_tf + acc * 8u);             // accumulator ready for the epilogue
       }
       __syncwarp();
       sa16 += a_slot16;
       if (++aslot == a_slots) { aslot = 0; aphase ^= 1u; sa16 = sa16_0; }
     }
+    if (!last_n) { aslot = aslot0; aphase = aphase0; sa16 = sa16_t; }    // next N tile: the same A slots (their full phase is still the completed one)
   }
 }
 
@@ -442,7 +449,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
   __shared__ __align__(8) uint64_t a_full[TC_MAX_A_SLOTS], a_empty[TC_MAX_A_SLOTS], tmem_full[4], tmem_empty[4];
   __shared__ __align__(8) uint64_t b_full[TC_MAX_STEPS], b_empty[TC_MAX_STEPS];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(16) float bias_s[256];
+  __shared__ __align__(16) float bias_s[512];                 // this CTA's N tile(s): BN <= 256 columns, or n_inner * BN <= 512
   __shared__ __align__(8) uint64_t res_bar[TC_MAX_EPI_WARPS];
   __shared__ __align__(8) uint64_t a_norm[LN_SMEM ? TC_MAX_A_SLOTS : 1];
   __shared__ __align__(16) float ln_gb[LN_SMEM ? 512 : 4];   // gamma [0, 256) | beta [256, 512)
@@ -479,7 +486,8 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
   }
   if (warp >= 4) {   // this CTA owns N-tile blockIdx.x % n_tiles_n for its whole life: stage its bias once
     const int i = threadIdx.x - 128;
-    if (i < 256) bias_s[i] = ((p.bias && i < (p.tapsum ? p.Cout_store : BN)) ? __ldg(p.bias + (blockIdx.x % p.n_tiles_n) * BN + i) : 0.f) * (p.gelu_h2 ? 0.5f : 1.f);
+    for (int j = i; j < 512; j += 32 * TC_EPI_WARPS)
+      bias_s[j] = ((p.bias && j < (p.tapsum ? p.Cout_store : p.n_inner * BN)) ? __ldg(p.bias + (blockIdx.x % p.n_tiles_n) * BN + j) : 0.f) * (p.gelu_h2 ? 0.5f : 1.f);
   }
   if (LN_SMEM && warp >= 4 + TC_EPI_WARPS)
     for (int j = threadIdx.x - (128 + 32 * TC_EPI_WARPS); j < 64 * p.nsteps; j += 128) { ln_gb[j] = __ldg(p.ln_gamma + j); ln_gb[256 + j] = __ldg(p.ln_beta + j); }
@@ -542,7 +550,18 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
       const int u = s / 9, t = s - u * 9;
       return t * p.ctot + p.chunks[u].cg;
     };
-    if (p.b_resident) {
+    if (p.b_resident && p.n_inner > 1) {
+      if (mt0 < p.m_tiles)
+        for (int ni = 0; ni < p.n_inner; ++ni)
+          for (int s = 0; s < p.nsteps; ++s) {
+            const int sl = ni * p.nsteps + s;
+            if (elect_one()) {
+              mbar_expect_tx(&b_full[sl], b_bytes);
+              tma_load_2d(smem_b + (size_t)sl * b_bytes, &p.bmap, &b_full[sl], bk(s), ni * BN);
+            }
+            __syncwarp();
+          }
+    } else if (p.b_resident) {
       if (mt0 < p.m_tiles)
         for (int s = 0; s < p.nsteps; ++s) {
           if (elect_one()) {
@@ -584,14 +603,14 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
     int it = 0;
     if (p.b_resident) {
       if (mt0 < p.m_tiles)
-        for (int s = 0; s < p.nsteps; ++s) mbar_wait(&b_full[s], 0);
+        for (int s = 0; s < p.nsteps * p.n_inner; ++s) mbar_wait(&b_full[s], 0);
       const int halo = p.halo, a_slots = p.a_slots, m_tiles = p.m_tiles;
       const uint32_t a_slot16 = (uint32_t)p.a_slot_bytes >> 4;
       const bool nomma = (p.debug & 2) != 0;
       // LN_SMEM: an A slot is ready once the LayerNorm warps have normalised it
       const uint32_t bar_af = smem_u32(LN_SMEM ? &a_norm[0] : &a_full[0]), bar_ae = smem_u32(&a_empty[0]), bar_tf = smem_u32(&tmem_full[0]), bar_te = smem_u32(&tmem_empty[0]);
 #define FBANET_MMA_LOOP(T, H) \
-  mma_loop_resident<T, H>(mt0, mt_step, m_tiles, units, a_slots, a_slot16, sa0 >> 4, sb0 >> 4, b_bytes >> 4, tmem_base, (uint32_t)BN, idesc, bar_af, bar_ae, bar_tf, bar_te, nomma, (uint32_t)nacc_mask, (uint32_t)nacc_shift)
+  mma_loop_resident<T, H>(mt0, mt_step, m_tiles, units, a_slots, a_slot16, sa0 >> 4, sb0 >> 4, b_bytes >> 4, tmem_base, (uint32_t)BN, idesc, bar_af, bar_ae, bar_tf, bar_te, nomma, (uint32_t)nacc_mask, (uint32_t)nacc_shift, H == 0 ? p.n_inner : 1)
       if (halo == 0) FBANET_MMA_LOOP(1, 0);
       else if (halo == 1) FBANET_MMA_LOOP(9, 1);
       else if (halo == 3) FBANET_MMA_LOOP(9, 3);
@@ -654,7 +673,8 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
     int it = 0;
     const uint32_t bar_tf = smem_u32(&tmem_full[0]), bar_te = smem_u32(&tmem_empty[0]);   // raw shared addresses (see mma_loop_resident)
     if (p.debug & 1) {
-      for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it) {
+      for (int mt = mt0; mt < p.m_tiles; mt += mt_step)
+      for (int ni = 0; ni < p.n_inner; ++ni, ++it) {
         mbar_wait(&tmem_full[it & nacc_mask], (it >> nacc_shift) & 1);
         tc_fence_after();
         tc_fence_before();
@@ -792,7 +812,9 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
       const int ply = lane / bw, plx = lane - ply * bw;         // this thread's pixel inside the rectangle
       uint32_t res_phase = 0, nb = 0;
       TileIter ti(mt0, mt_step, p.tiles_x, p.tiles_y);
-      for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it, ti.next()) {
+      const int n_inner = p.n_inner;
+      for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ti.next())
+      for (int ni = 0; ni < n_inner; ++ni, ++it) {         // (A-stationary mode: the tile's n_inner N tiles arrive one accumulator after the other)
         const int acc = it & nacc_mask;
         const uint32_t acc_phase = (it >> nacc_shift) & 1;
         const int img = ti.img;
@@ -805,7 +827,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
         bool waited = false;
         for (int cidx = 0; cidx < nchunks; ++cidx) {
           if (((it * nchunks + cidx) % TC_EPI_SLOTS) != slot) continue;
-          const int col0 = nt * BN + cidx * 64;          // GEMM column of the chunk
+          const int col0 = (nt + ni) * BN + cidx * 64;   // GEMM column of the chunk
           const uint32_t boff = (nbufs == 2 ? (nb & 1u) : 0u) * 4096u;
           const uint32_t sbuf = stage_u + boff;
           uint8_t* gbuf = stage0 + boff;
@@ -825,7 +847,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
           tmem_ld32(taddr0 + cidx * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
           tmem_ld_wait();
           if (has_res) { mbar_wait(&res_bar[ew], res_phase); res_phase ^= 1; }
-          const float* bs = bias_s + cidx * 64;
+          const float* bs = bias_s + ni * BN + cidx * 64;
           const uint32_t row_addr = sbuf + (uint32_t)lane * 128u;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {                  // 8 columns = one 16-byte smem chunk at a time
@@ -896,7 +918,9 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
     } else {
       const int npieces = BN >= 32 ? BN / 32 : 1;      // 32-column pieces (one 16-column piece for BN = 16)
       TileIter ti(mt0, mt_step, p.tiles_x, p.tiles_y);
-      for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ++it, ti.next()) {
+      const int n_inner = p.n_inner;
+      for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ti.next())
+      for (int ni = 0; ni < n_inner; ++ni, ++it) {
         const int acc = it & nacc_mask;
         const uint32_t acc_phase = (it >> nacc_shift) & 1;
         const int img = ti.img;
@@ -907,7 +931,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
         uint4 rpre[4];
         const bool pre = valid && p.residual != nullptr && BN >= 32 && j0 < npieces;
         if (pre) {
-          const bf16* rp = p.residual + img * p.res_img_stride + ((int64_t)y * p.Wo + x) * p.res_ld + nt * BN + j0 * 32;
+          const bf16* rp = p.residual + img * p.res_img_stride + ((int64_t)y * p.Wo + x) * p.res_ld + (nt + ni) * BN + j0 * 32;
 #pragma unroll
           for (int j = 0; j < 4; ++j) rpre[j] = *reinterpret_cast<const uint4*>(rp + j * 8);
         }
@@ -922,7 +946,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
           const int nc = (BN - c0 >= 32) ? 32 : 16;
           if (nc == 32) tmem_ld32(taddr0 + c0, v); else tmem_ld16(taddr0 + c0, v);
           tmem_ld_wait();
-          if (valid) epilogue_chunk(p, v, nc, nt * BN + c0, img, y, x, alpha, bias_s + c0, (pre && j == j0) ? rpre : nullptr,
+          if (valid) epilogue_chunk(p, v, nc, (nt + ni) * BN + c0, img, y, x, alpha, bias_s + ni * BN + c0, (pre && j == j0) ? rpre : nullptr,
                                     HAS_LN, ln_rstd);
           __syncwarp();
         }
@@ -1224,13 +1248,31 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   const int a_min = halo ? 2 : 3;
   const int units = halo ? tp.nchunks : ns;
   const bool ln_smem = p->ln_gamma != nullptr;
+  // A-stationary mode: with LayerNorm in shared memory every CTA of an N tile would repeat the normalisation of the same A tile
+  // (measured a wash at 3 N tiles); where ALL the weights fit beside a whole A tile (+ look-ahead) and the staging buffers, one CTA walks
+  // the N tiles of each A tile instead, so the tile is loaded and normalised once.  FBANET_TC_NINNER=0 disables, =all also for plain 1x1 GEMMs.
+  tp.n_inner = 1;
+  {
+    static const char* e = getenv("FBANET_TC_NINNER");
+    const bool want = e ? (e[0] == 'a' ? true : (e[0] != '0' && ln_smem)) : ln_smem;
+    const int nt_all = tp.n_tiles_n;
+    const int64_t need = (int64_t)nt_all * ns * b_bytes + (int64_t)(units + 1) * tp.a_slot_bytes + 4 * 2 * 1 * 4096;
+    if (want && !halo && !tapsum && p->KH == 1 && p->stride == 1 && nt_all > 1 && nt_all * tp.BN <= 512 && nt_all * ns <= TC_MAX_STEPS && need <= 216 * 1024 &&
+        units + 1 <= TC_MAX_A_SLOTS) {
+      tp.n_inner = nt_all;
+      tp.n_tiles_n = 1;
+    }
+  }
+  const int nsb = ns * tp.n_inner;       // weight slabs when resident
   struct Plan { int resident, a_slots, b_slots; };
   auto plan = [&](int budget, Plan* pl) -> bool {
-    if ((int64_t)ns * b_bytes + (int64_t)a_min * tp.a_slot_bytes <= budget) {
+    if ((int64_t)nsb * b_bytes + (int64_t)a_min * tp.a_slot_bytes <= budget) {
       pl->resident = 1;
-      pl->b_slots = ns;
-      const int a = (budget - ns * b_bytes) / tp.a_slot_bytes;
+      pl->b_slots = nsb;
+      const int a = (budget - nsb * b_bytes) / tp.a_slot_bytes;
       pl->a_slots = a > TC_MAX_A_SLOTS ? TC_MAX_A_SLOTS : a;
+    } else if (tp.n_inner > 1) {
+      return false;                      // the A-stationary mode needs every slab resident
     } else {
       pl->resident = 0;
       pl->a_slots = halo ? 2 : (ln_smem && units + 2 > 4 ? units + 2 : 4);   // LN in smem: a whole tile (units slots) + look-ahead
@@ -1250,11 +1292,14 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
     // >= 4 A slots left (deep-K GEMMs lose more from a shallow A ring than they gain in the epilogue), two warps >= 3.
     static const int opts[4][2] = {{3, 2}, {3, 1}, {2, 2}, {2, 1}};
     tp.tma_store = 0;
+    // A-stationary mode: an A tile's slots stay occupied for n_inner N tiles, so the ring should hold TWO whole tiles (the next one is
+    // loaded and normalised meanwhile) even at the price of single staging buffers; second pass: one tile + one slot
+    for (int pass = tp.n_inner > 1 ? 0 : 1; pass < 2 && !tp.tma_store; ++pass)
     for (int o = ln_smem ? 2 : 0; o < 4 && !tp.tma_store; ++o) {   // LN in smem: the four LayerNorm warps take the third warp set's place
       const int slots = opts[o][0], bufs = opts[o][1];
       const int sb = 4 * slots * bufs * 4096;
       const int floor_a = slots == 3 ? 4 : 3;
-      const int want_a = ln_smem ? units + 1 : (p0.a_slots < floor_a ? p0.a_slots : floor_a);   // LN in smem: a whole tile + one slot of look-ahead
+      const int want_a = pass == 0 ? 2 * units : ((ln_smem || tp.n_inner > 1) ? units + 1 : (p0.a_slots < floor_a ? p0.a_slots : floor_a));   // LN in smem / A-stationary: a whole tile + one slot of look-ahead
       if (plan(216 * 1024 - sb, &p1) && p1.resident == p0.resident && p1.b_slots == p0.b_slots && p1.a_slots >= want_a) {
         tp.tma_store = 1; tp.stage_bufs = bufs; stage_bytes = sb; epi_slots = slots; p0 = p1;
       }
@@ -1267,7 +1312,7 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   }
   tp.b_resident = p0.resident; tp.a_slots = p0.a_slots; tp.b_slots = p0.b_slots;
   if (tp.ln_stats) tp.gelu_h2 = 0;   // the half2 GELU is not in the folded-LayerNorm instantiation
-  if (ln_smem && tp.a_slots < units + 1) return FBANET_E_UNSUPPORTED;   // the LayerNorm warps hold all K chunks of a tile at once
+  if ((ln_smem || tp.n_inner > 1) && tp.a_slots < units + 1) return FBANET_E_UNSUPPORTED;   // the LayerNorm warps (the N-tile walk) hold all K chunks of a tile at once
   { const char* dbg = getenv("FBANET_TC_DEBUG"); tp.debug = dbg ? atoi(dbg) : 0; }
   // accumulator stages in TMEM.  Four (N tiles up to 128) were measured against two on every layer shape and change nothing:
   // the gap between "MMA-only" (1.55 ms) + "epilogue-only" (1.28 ms) and both together (1.77 ms) on the 64->64 body conv is not

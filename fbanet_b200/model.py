@@ -477,7 +477,10 @@ class BaseModel(nn.Module):
         sig = (name, B, H, W)
         w = P[name + ".w"]
         mode = {True: "1", False: "0"}.get(self.ln_in_gemm, self.ln_in_gemm)
-        if self._use_tc() and sig not in self._ln_gemm_refused and (mode == "all" or (mode == "1" and w.shape[0] <= 256)):
+        # "1": where the A tile is normalised once -- one N tile, or dim 128 whose whole weight matrix stays resident so that one CTA walks
+        # the N tiles of each A tile (the kernel's A-stationary mode)
+        once = w.shape[0] <= 256 or (Cd == 128 and w.shape[0] <= 512 and os.environ.get("FBANET_TC_NINNER", "1") != "0")
+        if self._use_tc() and sig not in self._ln_gemm_refused and (mode == "all" or (mode == "1" and once)):
             out = self._new(B, H, W, w.shape[0]) if out_dtype is None else torch.empty((B, H, W, w.shape[0]), device=x4.device, dtype=out_dtype)
             try:
                 return ops.conv_gemm([x4], w, out, bias=P[name + ".b"], act=act, impl=self.impl, ln=(P[lnkey + ".g"], P[lnkey + ".b"]))
