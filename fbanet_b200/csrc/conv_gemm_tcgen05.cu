@@ -101,10 +101,12 @@ __device__ __forceinline__ void apply_act_vec(float (&f)[NV], const int act, con
 }
 
 // bias + activation + residual + store of 32 (or 16) accumulator columns of one pixel row
+// XTRA: the instantiations that carry the half2 GELU (see the kernel's template parameters)
+template <bool XTRA>
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t (&v)[32], const int nc, const int col0, const int img,
                                                const int y, const int x, const float alpha, const float* bias_s,
                                                const uint4* rpre = nullptr, const bool has_ln = false, const float ln_rstd = 1.f) {
-  if (p.gelu_h2) {
+  if (XTRA && p.gelu_h2) {
     // fp16 store + tanh-GELU on packed half2: the staged epilogue's arithmetic, operation for operation (bias_s holds bias / 2), so a GEMM
     // gives the same bits whichever epilogue its shared-memory plan selects (STORE_NHWC, no residual, no folded LayerNorm: launcher)
     const uint32_t A2 = 0x3E623E62u, B2 = 0x34913491u;             // half2 (2 k0, 2 k0) and (8 k0 k1, 8 k0 k1)
@@ -237,12 +239,13 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
 // instructions (with spills) that ptxas hoisted in front of the first MMA to precompute all 72 descriptors.  That is longer than
 // the work the tcgen05 queue holds, so the tensor pipe ran dry once per tile (43 % active on the body conv where
 // tools/ubench/umma.cu gives 57-64 % as the N = 64 ceiling).
-template <int TAPS, int HALO>
+template <int TAPS, int HALO, bool NI = false>
 __device__ __forceinline__ void mma_loop_resident(const int mt0, const int mt_step, const int m_tiles, const int units, const int a_slots,
                                                   const uint32_t a_slot16, const uint32_t sa16_0, const uint32_t sb16_0, const uint32_t bstep16,
                                                   const uint32_t tmem_base, const uint32_t BN, const uint32_t idesc, const uint32_t bar_af,
                                                   const uint32_t bar_ae, const uint32_t bar_tf, const uint32_t bar_te, const bool nomma, const uint32_t nacc_mask,
-                                                  const uint32_t nacc_shift, const int n_inner = 1) {
+                                                  const uint32_t nacc_shift, const int n_inner_arg = 1) {
+  const int n_inner = NI ? n_inner_arg : 1;          // (compile-time 1 without NI: the N-tile walk folds away)
   const uint64_t desc_b = make_sw128_desc(0);        // descriptor with a zero start address
   const uint64_t desc_a = HALO >= 2 ? ((desc_b & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)(TC_HALO_WROW >> 4) << 32)) : desc_b;   // wide: 2 KB between atoms
   constexpr uint32_t A_START = HALO >= 2 ? (3u * 128u) >> 4 : 0u;
@@ -442,7 +445,10 @@ constexpr int TC_MAX_EPI_WARPS = 12;
 
 // HAS_LN: folded-LayerNorm epilogue (a separate instantiation: compiled into the common one it costs every GEMM 12 %)
 // LN_SMEM: four more warps normalise every A tile in shared memory before the MMAs read it (ln_smem_loop)
-template <bool HAS_LN, int TC_EPI_SLOTS, bool LN_SMEM = false>
+// XTRA: carries the features only a few launches use -- the half2 GELU of the fp16-store epilogue (gelu_h2) and the A-stationary N-tile
+//   walk (n_inner > 1).  They are compiled out of the other instantiations: merely present in the code they cost the 64 -> 64 body convs
+//   4-8 % (eager pass 3.88 -> 4.24 ms for four launches; registers / issue slots of the issuer and the direct-store epilogue).
+template <bool HAS_LN, int TC_EPI_SLOTS, bool LN_SMEM = false, bool XTRA = false>
 __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0), 1) conv_gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   constexpr int TC_EPI_WARPS = 4 * TC_EPI_SLOTS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -486,8 +492,10 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
   }
   if (warp >= 4) {   // this CTA owns N-tile blockIdx.x % n_tiles_n for its whole life: stage its bias once
     const int i = threadIdx.x - 128;
-    for (int j = i; j < 512; j += 32 * TC_EPI_WARPS)
-      bias_s[j] = ((p.bias && j < (p.tapsum ? p.Cout_store : p.n_inner * BN)) ? __ldg(p.bias + (blockIdx.x % p.n_tiles_n) * BN + j) : 0.f) * (p.gelu_h2 ? 0.5f : 1.f);
+    if (XTRA) {
+      for (int j = i; j < 512; j += 32 * TC_EPI_WARPS)
+        bias_s[j] = ((p.bias && j < p.n_inner * BN) ? __ldg(p.bias + (blockIdx.x % p.n_tiles_n) * BN + j) : 0.f) * (p.gelu_h2 ? 0.5f : 1.f);
+    } else if (i < 256) bias_s[i] = (p.bias && i < (p.tapsum ? p.Cout_store : BN)) ? __ldg(p.bias + (blockIdx.x % p.n_tiles_n) * BN + i) : 0.f;
   }
   if (LN_SMEM && warp >= 4 + TC_EPI_WARPS)
     for (int j = threadIdx.x - (128 + 32 * TC_EPI_WARPS); j < 64 * p.nsteps; j += 128) { ln_gb[j] = __ldg(p.ln_gamma + j); ln_gb[256 + j] = __ldg(p.ln_beta + j); }
@@ -550,7 +558,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
       const int u = s / 9, t = s - u * 9;
       return t * p.ctot + p.chunks[u].cg;
     };
-    if (p.b_resident && p.n_inner > 1) {
+    if (XTRA && p.b_resident && p.n_inner > 1) {
       if (mt0 < p.m_tiles)
         for (int ni = 0; ni < p.n_inner; ++ni)
           for (int s = 0; s < p.nsteps; ++s) {
@@ -603,14 +611,14 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
     int it = 0;
     if (p.b_resident) {
       if (mt0 < p.m_tiles)
-        for (int s = 0; s < p.nsteps * p.n_inner; ++s) mbar_wait(&b_full[s], 0);
+        for (int s = 0; s < p.nsteps * (XTRA ? p.n_inner : 1); ++s) mbar_wait(&b_full[s], 0);
       const int halo = p.halo, a_slots = p.a_slots, m_tiles = p.m_tiles;
       const uint32_t a_slot16 = (uint32_t)p.a_slot_bytes >> 4;
       const bool nomma = (p.debug & 2) != 0;
       // LN_SMEM: an A slot is ready once the LayerNorm warps have normalised it
       const uint32_t bar_af = smem_u32(LN_SMEM ? &a_norm[0] : &a_full[0]), bar_ae = smem_u32(&a_empty[0]), bar_tf = smem_u32(&tmem_full[0]), bar_te = smem_u32(&tmem_empty[0]);
 #define FBANET_MMA_LOOP(T, H) \
-  mma_loop_resident<T, H>(mt0, mt_step, m_tiles, units, a_slots, a_slot16, sa0 >> 4, sb0 >> 4, b_bytes >> 4, tmem_base, (uint32_t)BN, idesc, bar_af, bar_ae, bar_tf, bar_te, nomma, (uint32_t)nacc_mask, (uint32_t)nacc_shift, H == 0 ? p.n_inner : 1)
+  mma_loop_resident<T, H, XTRA && H == 0>(mt0, mt_step, m_tiles, units, a_slots, a_slot16, sa0 >> 4, sb0 >> 4, b_bytes >> 4, tmem_base, (uint32_t)BN, idesc, bar_af, bar_ae, bar_tf, bar_te, nomma, (uint32_t)nacc_mask, (uint32_t)nacc_shift, p.n_inner)
       if (halo == 0) FBANET_MMA_LOOP(1, 0);
       else if (halo == 1) FBANET_MMA_LOOP(9, 1);
       else if (halo == 3) FBANET_MMA_LOOP(9, 3);
@@ -674,7 +682,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
     const uint32_t bar_tf = smem_u32(&tmem_full[0]), bar_te = smem_u32(&tmem_empty[0]);   // raw shared addresses (see mma_loop_resident)
     if (p.debug & 1) {
       for (int mt = mt0; mt < p.m_tiles; mt += mt_step)
-      for (int ni = 0; ni < p.n_inner; ++ni, ++it) {
+      for (int ni = 0; ni < (XTRA ? p.n_inner : 1); ++ni, ++it) {
         mbar_wait(&tmem_full[it & nacc_mask], (it >> nacc_shift) & 1);
         tc_fence_after();
         tc_fence_before();
@@ -812,7 +820,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
       const int ply = lane / bw, plx = lane - ply * bw;         // this thread's pixel inside the rectangle
       uint32_t res_phase = 0, nb = 0;
       TileIter ti(mt0, mt_step, p.tiles_x, p.tiles_y);
-      const int n_inner = p.n_inner;
+      const int n_inner = XTRA ? p.n_inner : 1;
       for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ti.next())
       for (int ni = 0; ni < n_inner; ++ni, ++it) {         // (A-stationary mode: the tile's n_inner N tiles arrive one accumulator after the other)
         const int acc = it & nacc_mask;
@@ -854,7 +862,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
             const float4 b0 = *reinterpret_cast<const float4*>(bs + c * 8), b1 = *reinterpret_cast<const float4*>(bs + c * 8 + 4);
             f32x2 f[4], bb[4] = {pack_f2(b0.x, b0.y), pack_f2(b0.z, b0.w), pack_f2(b1.x, b1.y), pack_f2(b1.z, b1.w)};
             const uint32_t saddr = row_addr + (uint32_t)((c ^ r7) << 4);   // SWIZZLE_128B position of chunk c in this row
-            if (!HAS_LN && p.gelu_h2) {
+            if (XTRA && !HAS_LN && p.gelu_h2) {
               // fp16 store + tanh-GELU (the dim-256 LeFF's fc1): z = (acc + bias) / 2 in fp32 (bias_s holds bias / 2), rounded ONCE to fp16,
               // then GELU(x) = z (1 + tanh(z (2 k0 + 8 k0 k1 z^2))) on packed half2 -- 1 FFMA2 + 1 F2FP + 4 HFMA2/HMUL2 + ONE MUFU.TANH.F16x2 per
               // pair instead of 6 packed fp32 ops + 2 MUFU.TANH + the pack: this epilogue is what bounds the GEMM (XU and issue slots).
@@ -918,7 +926,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
     } else {
       const int npieces = BN >= 32 ? BN / 32 : 1;      // 32-column pieces (one 16-column piece for BN = 16)
       TileIter ti(mt0, mt_step, p.tiles_x, p.tiles_y);
-      const int n_inner = p.n_inner;
+      const int n_inner = XTRA ? p.n_inner : 1;
       for (int mt = mt0; mt < p.m_tiles; mt += mt_step, ti.next())
       for (int ni = 0; ni < n_inner; ++ni, ++it) {
         const int acc = it & nacc_mask;
@@ -946,7 +954,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_EPI_SLOTS + (LN_SMEM ? 128 : 0)
           const int nc = (BN - c0 >= 32) ? 32 : 16;
           if (nc == 32) tmem_ld32(taddr0 + c0, v); else tmem_ld16(taddr0 + c0, v);
           tmem_ld_wait();
-          if (valid) epilogue_chunk(p, v, nc, (nt + ni) * BN + c0, img, y, x, alpha, bias_s + ni * BN + c0, (pre && j == j0) ? rpre : nullptr,
+          if (valid) epilogue_chunk<XTRA>(p, v, nc, (nt + ni) * BN + c0, img, y, x, alpha, bias_s + ni * BN + c0, (pre && j == j0) ? rpre : nullptr,
                                     HAS_LN, ln_rstd);
           __syncwarp();
         }
@@ -1327,7 +1335,9 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cudaGetLastError(); set_last_error(e); return FBANET_E_LAUNCH; }
     smem_opted_in = smem;
   }
@@ -1339,13 +1349,17 @@ int conv_gemm_tc_launch(const fbanet_conv_params* p, cudaStream_t stream) {
   if (per_n < 1) per_n = 1;
   if (per_n > tp.m_tiles) per_n = tp.m_tiles;
   const int grid = per_n * tp.n_tiles_n;
+  const bool xtra = tp.gelu_h2 || tp.n_inner > 1;   // (never together with the folded-LayerNorm epilogue: gelu_h2 is cleared, n_inner needs ln_gamma or the env switch)
+  if (xtra && tp.ln_stats) return FBANET_E_UNSUPPORTED;
   if (ln_smem) {          // 8 epilogue warps + 4 LayerNorm warps
-    conv_gemm_tcgen05_kernel<false, 2, true><<<grid, 512, smem, stream>>>(tp);
+    conv_gemm_tcgen05_kernel<false, 2, true, true><<<grid, 512, smem, stream>>>(tp);
   } else if (epi_slots == 3) {   // staged epilogue with 12 epilogue warps
     if (tp.ln_stats) conv_gemm_tcgen05_kernel<true, 3><<<grid, 512, smem, stream>>>(tp);
+    else if (xtra) conv_gemm_tcgen05_kernel<false, 3, false, true><<<grid, 512, smem, stream>>>(tp);
     else conv_gemm_tcgen05_kernel<false, 3><<<grid, 512, smem, stream>>>(tp);
   } else {                // 8 epilogue warps (staged or direct stores), 168 registers
     if (tp.ln_stats) conv_gemm_tcgen05_kernel<true, 2><<<grid, 384, smem, stream>>>(tp);
+    else if (xtra) conv_gemm_tcgen05_kernel<false, 2, false, true><<<grid, 384, smem, stream>>>(tp);
     else conv_gemm_tcgen05_kernel<false, 2><<<grid, 384, smem, stream>>>(tp);
   }
   return check_launch();
